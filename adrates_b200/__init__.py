@@ -1,0 +1,18 @@
+"""adrates_b200 - B200-native valuation-and-Greeks path behind the Cavour/ADRates API.
+
+Host side: Python mirror of the reference interface for this path (Model.build_curve,
+curve.df_ad, OIS(...).position(model).compute([VALUE, DELTA, GAMMA]), Portfolio.compute).
+Device side: hand-written sm_100a CUDA kernels behind the C ABI in include/adrates_b200.h
+(adrates_b200/csrc), loaded with ctypes.  There is no CPU fallback for valuation.
+"""
+from .error import LibError
+from .dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
+                    DayCountTypes, FrequencyTypes, Schedule, to_tenor, times_from_dates)
+from .global_types import (SwapTypes, InstrumentTypes, RequestTypes, InterpTypes, CurveTypes,
+                           CurrencyTypes, CollateralType)
+
+__all__ = [
+    "LibError", "Date", "Calendar", "CalendarTypes", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
+    "DayCountTypes", "FrequencyTypes", "Schedule", "to_tenor", "times_from_dates", "SwapTypes",
+    "InstrumentTypes", "RequestTypes", "InterpTypes", "CurveTypes", "CurrencyTypes", "CollateralType",
+]

@@ -1,0 +1,276 @@
+"""Discount curves and the host-side planning that precedes the CUDA kernels.
+
+Two different node sets exist per curve, exactly as in the reference:
+
+* path A - `OISCurve._times/_dfs`, bootstrapped by `OISCurve._build_curve_ad`
+  (cavour/trades/rates/ois_curve.py:156-212): non-quoted coupon dates use log-linearly
+  interpolated par rates.  Serves `curve.df`, `curve.df_ad`, the non-AD `leg.value`.
+* path B - the dense engine grid of `Engine.build_curve_ad`
+  (cavour/market/position/engine.py:2246-2360): every coupon date of every calibration
+  swap is a node (duplicates kept) carrying its parent swap's rate.  VALUE/DELTA/GAMMA
+  use it.  Here only the *plan* (node times, accruals, parent swap, previous-annuity
+  node) is computed on the host; the recursion and its first/second-order tangents run
+  on the GPU (csrc/cav_bootstrap.cu).
+
+`plan_queries` turns cashflow times into (node, node, weight, weight) brackets with the
+reference's interpolation rules (cavour/market/curves/interpolator_ad.py:186-249):
+1e-10 grid snap to the first nearest node, +1e-12 bracket shift, searchsorted(side=
+'right') duplicate semantics, end clamping.  All quirks live here so the kernels stay
+generic (ln DF = wa*L[a] + wb*L[b]).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from .dates import Date, DayCount, DayCountTypes, times_from_dates
+from .error import LibError
+from .global_types import InterpTypes
+
+SNAP_TOL = 1e-10       # interpolator_ad.py:221
+BRACKET_EPS = 1e-12    # interpolator_ad.py:224
+TIME_FLOOR = 1e-15     # interpolator_ad.py:229
+
+
+# ======================================================================================
+# path B plan
+# ======================================================================================
+@dataclass
+class PathBPlan:
+    """Static (rate-independent) description of the engine's bootstrap grid."""
+    node_time: np.ndarray   # [G] f64, sorted, duplicates kept; node_time[0] = 0
+    node_acc: np.ndarray    # [G] f64 accrual of the coupon ending at the node
+    node_swap: np.ndarray   # [G] i32 parent calibration swap (root uses swap 0)
+    node_prev: np.ndarray   # [G] i32 node whose annuity precedes this coupon, -1 = none
+    n_rates: int
+    first_dup: np.ndarray   # [G] i32 first index sharing this node's time
+    last_dup: np.ndarray    # [G] i32 last index sharing this node's time
+
+    @property
+    def n_nodes(self) -> int:
+        return int(self.node_time.shape[0])
+
+
+def plan_path_b(swap_times, year_fracs) -> PathBPlan:
+    """Expand all coupon dates of all calibration swaps into the engine grid
+    (engine.py:2283-2328): maturity = running sum of accruals, dependency keys are
+    round(maturity, 2), stable sort by exact maturity, a key resolves to the FIRST node
+    carrying it."""
+    rows = [(0.0, 0.0, 0.0, None, 0)]  # (maturity, key, acc, prev_key, swap)
+    for s, fracs in enumerate(year_fracs):
+        run = 0.0
+        for j, frac in enumerate(fracs):
+            before = run
+            run += frac
+            rows.append((run, round(run, 2), frac, round(before, 2) if j > 0 else None, s))
+    order = sorted(range(len(rows)), key=lambda i: rows[i][0])  # stable
+    rows = [rows[i] for i in order]
+    first_with_key = {}
+    for idx, r in enumerate(rows):
+        first_with_key.setdefault(r[1], idx)
+    G = len(rows)
+    t = np.array([r[0] for r in rows], dtype=np.float64)
+    acc = np.array([r[2] for r in rows], dtype=np.float64)
+    swap = np.array([r[4] for r in rows], dtype=np.int32)
+    prev = np.array([-1 if r[3] is None else first_with_key.get(r[3], -1) for r in rows], dtype=np.int32)
+    first = np.searchsorted(t, t, side="left").astype(np.int32)
+    last = (np.searchsorted(t, t, side="right") - 1).astype(np.int32)
+    if np.any(prev >= np.arange(G)):
+        raise LibError("bootstrap plan is not causal (a coupon depends on a later node)")
+    return PathBPlan(t, acc, swap, prev, len(year_fracs), first, last)
+
+
+# ======================================================================================
+# query planning: time -> (a, b, wa, wb) with ln DF(t) = wa*L[a] + wb*L[b]
+# ======================================================================================
+def plan_queries(t, node_time: np.ndarray, interp_type: InterpTypes):
+    """Vectorised bracket planner.  Returns (a, b, wa, wb); a == b with wb == 0 for a
+    grid snap or an end clamp."""
+    if interp_type == InterpTypes.LINEAR_ZERO_RATES:
+        lzr = True
+    elif interp_type == InterpTypes.FLAT_FWD_RATES:
+        lzr = False
+    else:
+        raise LibError("Invalid interpolation scheme.")  # interpolator_ad.py:236-237
+    t = np.atleast_1d(np.asarray(t, dtype=np.float64))
+    x = node_time
+    G = x.shape[0]
+    # nearest node, first index on ties (jnp.argmin)
+    r = np.searchsorted(x, t, side="left")
+    lo = np.clip(r - 1, 0, G - 1)
+    hi = np.clip(r, 0, G - 1)
+    d_lo = np.abs(t - x[lo])
+    d_hi = np.abs(t - x[hi])
+    near = np.where(d_lo <= d_hi, lo, hi)
+    near = np.searchsorted(x, x[near], side="left")      # first duplicate of that time
+    snap = np.minimum(d_lo, d_hi) < SNAP_TOL
+    # bracket on the shifted time (jnp.interp semantics)
+    ts = t + BRACKET_EPS
+    b = np.clip(np.searchsorted(x, ts, side="right"), 1, G - 1)
+    a = b - 1
+    dx = x[b] - x[a]
+    flat = np.abs(dx) <= np.spacing(np.finfo(np.float64).eps)
+    w = np.where(flat, 0.0, (ts - x[a]) / np.where(flat, 1.0, dx))
+    above = ts > x[-1]
+    below = ts < x[0]
+    if lzr:
+        xa = np.maximum(x[a], TIME_FLOOR)
+        xb = np.maximum(x[b], TIME_FLOOR)
+        wa = t * (1.0 - w) / xa
+        wb = t * w / xb
+        wa_hi = t / np.maximum(x[-1], TIME_FLOOR)
+        wa_lo = t / np.maximum(x[0], TIME_FLOOR)
+    else:
+        wa = 1.0 - w
+        wb = w
+        wa_hi = np.ones_like(t)
+        wa_lo = np.ones_like(t)
+    a = np.where(above, G - 1, np.where(below, 0, a))
+    b = np.where(above, G - 1, np.where(below, 0, b))
+    wa = np.where(above, wa_hi, np.where(below, wa_lo, wa))
+    wb = np.where(above | below, 0.0, wb)
+    # snap overrides everything
+    a = np.where(snap, near, a)
+    b = np.where(snap, near, b)
+    wa = np.where(snap, 1.0, wa)
+    wb = np.where(snap, 0.0, wb)
+    return a.astype(np.int32), b.astype(np.int32), wa, wb
+
+
+# ======================================================================================
+# curve objects (path A + API surface)
+# ======================================================================================
+class DiscountCurve:
+    """Base curve: `df(date, day_count)` and `df_ad(t)` on the path-A nodes
+    (cavour/market/curves/discount_curve.py:300-436)."""
+
+    _value_dt: Date
+    _times: np.ndarray
+    _dfs: np.ndarray
+    _interp_type: InterpTypes
+
+    def df(self, dt, day_count=DayCountTypes.ACT_ACT_ISDA):
+        times = times_from_dates(dt, self._value_dt, day_count)
+        if isinstance(times, np.ndarray):
+            if np.any(times < 0.0):
+                raise LibError("Interpolate times must all be >= 0")
+            return np.array([self._node_df(float(u)) for u in times])
+        if times < 0.0:
+            raise LibError("Interpolate times must all be >= 0")
+        return self._node_df(float(times))
+
+    def _node_df(self, t: float) -> float:
+        """Scalar path-A interpolation (cavour/market/curves/interpolator.py:69-170):
+        exact hit on node 0, first segment flat in zero rate for LINEAR_ZERO_RATES,
+        true flat-forward extrapolation for FLAT_FWD_RATES."""
+        x, d = self._times, self._dfs
+        n = x.shape[0]
+        if t == x[0]:
+            return float(d[0])
+        i = int(np.searchsorted(x, t, side="left"))   # first node with x[i] >= t
+        if i > n - 1:
+            i = n - 1
+        if t > x[i]:
+            i = n
+        if self._interp_type == InterpTypes.LINEAR_ZERO_RATES:
+            if i == 1:
+                z1 = z2 = -math.log(d[1]) / x[1]
+                lo, hi = 0, 1
+            elif i < n:
+                z1 = -math.log(d[i - 1]) / x[i - 1]
+                z2 = -math.log(d[i]) / x[i]
+                lo, hi = i - 1, i
+            else:
+                z1 = z2 = -math.log(d[n - 1]) / x[n - 1]
+                lo, hi = n - 2, n - 1
+            z = ((x[hi] - t) * z1 + (t - x[lo]) * z2) / (x[hi] - x[lo])
+            return math.exp(-z * t)
+        if self._interp_type == InterpTypes.FLAT_FWD_RATES:
+            lo, hi = (i - 1, i) if i < n else (n - 2, n - 1)
+            y1, y2 = -math.log(d[lo]), -math.log(d[hi])
+            y = ((x[hi] - t) * y1 + (t - x[lo]) * y2) / (x[hi] - x[lo])
+            return math.exp(-y)
+        raise LibError("Invalid interpolation scheme.")
+
+    def df_ad(self, t, day_count=DayCountTypes.ACT_ACT_ISDA):
+        """DF at time(s) t in years: linear interpolation of piecewise forward rates on the
+        path-A nodes, independent of `_interp_type` (discount_curve.py:317-415).  Evaluated
+        by the CUDA library (cav_df_ad); there is no host fallback."""
+        from . import _native
+        tt = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        out = _native.lib().df_ad(self._times, self._dfs, tt)
+        return out[0] if np.ndim(t) == 0 else out
+
+
+class OISCurve(DiscountCurve):
+    """Curve implied by OIS par rates (ois_curve.py:86-212).  Construction collects
+    `swap_rates / swap_times / year_fracs` (the engine inputs) and bootstraps path A."""
+
+    def __init__(self, value_dt: Date, ois_swaps: list, interp_type: InterpTypes = InterpTypes.FLAT_FWD_RATES,
+                 check_refit: bool = False):
+        if not isinstance(value_dt, Date):
+            raise LibError("value_dt must be a Date")
+        if not ois_swaps:
+            raise LibError("OISCurve needs at least one calibration swap")
+        self._value_dt = value_dt
+        self._used_swaps = ois_swaps
+        self._interp_type = interp_type
+        self._check_refit = check_refit
+        self._interpolator = None
+        self._dc_type = ois_swaps[0]._float_leg._dc_type
+        days = DayCount(self._dc_type).days_in_year()
+        self.swap_rates = [s._fixed_coupon for s in ois_swaps]
+        self.swap_times = [(s._adjusted_fixed_dts[-1] - value_dt) / days for s in ois_swaps]
+        self.year_fracs = [list(s._fixed_leg._year_fracs) for s in ois_swaps]
+        self._plan_b = None
+        self._bootstrap_path_a()
+
+    # -- path A -----------------------------------------------------------------------
+    def _bootstrap_path_a(self):
+        """d = (1 - r*annuity_prev)/(1 + r*acc); coupon dates that are not quoted
+        maturities are filled in on demand with exp(interp(ln r)) par rates; annuities are
+        memoised by round(t, 2) (ois_curve.py:156-212)."""
+        st = np.array(self.swap_times, dtype=np.float64)
+        log_r = np.log(np.array(self.swap_rates, dtype=np.float64))
+        annuity = {}
+        times, dfs = [0.0], [1.0]
+
+        def node(i, t_mat, rate, drop):
+            fracs = self.year_fracs[i]
+            if len(fracs) == 1:
+                acc = fracs[0]
+                d = 1.0 / (acc * rate + 1.0)
+                a = acc * d
+            else:
+                acc = fracs[-1 - drop]
+                t_prev = sum(fracs[:-1 - drop])
+                key = round(t_prev, 2)
+                if key not in annuity:
+                    r_prev = float(np.exp(np.interp(t_prev, st, log_r)))
+                    annuity[key] = node(i, t_prev, r_prev, drop + 1)
+                d = (1.0 - rate * annuity[key]) / (acc * rate + 1.0)
+                a = annuity[key] + acc * d
+            times.append(t_mat)
+            dfs.append(d)
+            annuity[round(t_mat, 2)] = a
+            return a
+
+        for i in range(len(self._used_swaps)):
+            node(i, self.swap_times[i], self.swap_rates[i], 0)
+        self._times = np.array(times, dtype=np.float64)
+        self._dfs = np.array(dfs, dtype=np.float64)
+
+    # -- path B plan (cached; depends on dates only) --------------------------------------
+    def path_b_plan(self) -> PathBPlan:
+        if self._plan_b is None:
+            self._plan_b = plan_path_b(self.swap_times, self.year_fracs)
+        return self._plan_b
+
+    def _check_refits(self, swap_tol: float = 1e-10):
+        """Every calibration swap must reprice to ~0 on path A (ois_curve.py:344-358)."""
+        for swap in self._used_swaps:
+            v = swap.value(self._value_dt, self, self) / swap._fixed_leg._notional
+            if abs(v) > swap_tol:
+                raise LibError("Swap not repriced.")

@@ -1,0 +1,197 @@
+"""Trade objects that feed the flattener: OIS and its two legs.
+
+Interface mirror of the reference (constructor argument order, attribute names that the
+engine reads, error behaviour):
+    cavour/trades/rates/ois.py:100-205            OIS, OIS.position
+    cavour/trades/rates/swap_fixed_leg.py:63-196  SwapFixedLeg.generate_payments
+    cavour/trades/rates/swap_float_leg.py:65-186  SwapFloatLeg.generate_payment_dts
+The legs only generate schedules (host integer date math, once per trade).  Valuation and
+Greeks go through Position.compute -> the CUDA path; the non-AD `value()` helpers below
+are the reference's path-A (curve.df) arithmetic kept for API parity.
+"""
+from __future__ import annotations
+
+from .dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
+                    DayCountTypes, FrequencyTypes, Schedule)
+from .error import LibError
+from .global_types import SwapTypes, InstrumentTypes, CurveTypes, CurrencyTypes, ONE_MILLION
+
+
+def _resolve_end(effective_dt: Date, end):
+    return end if isinstance(end, Date) else effective_dt.add_tenor(end)
+
+
+class _SwapLeg:
+    """Schedule-bearing leg: accrual start/end, payment dates and accrual fractions."""
+
+    def _init_common(self, effective_dt, end_dt, leg_type, freq_type, dc_type, floating_index, currency,
+                     notional, payment_lag, cal_type, bd_type, dg_type, end_of_month, what):
+        if not isinstance(effective_dt, Date):
+            raise LibError("effective_dt must be a Date")
+        self._termination_dt = _resolve_end(effective_dt, end_dt)
+        self._maturity_dt = Calendar(cal_type).adjust(self._termination_dt, bd_type)
+        if effective_dt > self._maturity_dt:
+            raise LibError(what + " date after maturity date")
+        self._effective_dt = effective_dt
+        self._end_dt = end_dt
+        self._leg_type = leg_type
+        self._freq_type = freq_type
+        self._payment_lag = payment_lag
+        self._notional = notional
+        self._floating_index = floating_index
+        self._currency = currency
+        self._dc_type = dc_type
+        self._cal_type = cal_type
+        self._bd_type = bd_type
+        self._dg_type = dg_type
+        self._end_of_month = end_of_month
+
+    def _roll_schedule(self):
+        dts = Schedule(self._effective_dt, self._termination_dt, self._freq_type, self._cal_type,
+                       self._bd_type, self._dg_type, end_of_month=self._end_of_month)._adjusted_dts
+        if len(dts) < 2:
+            raise LibError("Schedule has none or only one date")
+        dc = DayCount(self._dc_type)
+        cal = Calendar(self._cal_type)
+        self._start_accrued_dts, self._end_accrued_dts = [], []
+        self._payment_dts, self._payment_dts_ad = [], []
+        self._year_fracs, self._accrued_days = [], []
+        for start, end in zip(dts[:-1], dts[1:]):
+            self._start_accrued_dts.append(start)
+            self._end_accrued_dts.append(end)
+            pay = end if self._payment_lag == 0 else cal.add_business_days(end, self._payment_lag)
+            self._payment_dts.append(pay)
+            self._payment_dts_ad.append(dc.year_frac(self._effective_dt, end)[0])
+            alpha, num, _ = dc.year_frac(start, end)
+            self._year_fracs.append(alpha)
+            self._accrued_days.append(num)
+
+
+class SwapFixedLeg(_SwapLeg):
+    def __init__(self, effective_dt: Date, end_dt, leg_type: SwapTypes, coupon: float,
+                 freq_type: FrequencyTypes, dc_type: DayCountTypes, floating_index: CurveTypes,
+                 currency: CurrencyTypes, notional: float = ONE_MILLION, principal: float = 0.0,
+                 payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False):
+        self.intrument_type = InstrumentTypes.SWAP_FIXED_LEG
+        self._init_common(effective_dt, end_dt, leg_type, freq_type, dc_type, floating_index, currency,
+                          notional, payment_lag, cal_type, bd_type, dg_type, end_of_month, "Effective")
+        self._principal = principal
+        self._cpn = coupon
+        self.generate_payments()
+
+    def generate_payments(self):
+        self._roll_schedule()
+        self._adjusted_fixed_dts = list(self._payment_dts)
+        self._rates = [self._cpn] * len(self._payment_dts)
+        self._payments = [a * self._notional * self._cpn for a in self._year_fracs]
+
+    def value(self, value_dt: Date, discount_curve):
+        """Path-A (curve.df) PV of the fixed leg (swap_fixed_leg.py:200-245)."""
+        df0 = discount_curve.df(value_dt, self._dc_type)
+        pv, df_p = 0.0, 0.0
+        for dt, amt in zip(self._payment_dts, self._payments):
+            if dt > value_dt:
+                df_p = discount_curve.df(dt, self._dc_type) / df0
+                pv += amt * df_p
+        if self._payment_dts[-1] > value_dt:
+            pv += self._principal * df_p * self._notional
+        return -pv if self._leg_type == SwapTypes.PAY else pv
+
+
+class SwapFloatLeg(_SwapLeg):
+    def __init__(self, effective_dt: Date, end_dt, leg_type: SwapTypes, spread: float,
+                 freq_type: FrequencyTypes, dc_type: DayCountTypes, floating_index: CurveTypes,
+                 currency: CurrencyTypes, notional: float = ONE_MILLION, principal: float = 0.0,
+                 payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False,
+                 notional_exchange: bool = False):
+        self.intrument_type = InstrumentTypes.SWAP_FLOAT_LEG
+        self._init_common(effective_dt, end_dt, leg_type, freq_type, dc_type, floating_index, currency,
+                          notional, payment_lag, cal_type, bd_type, dg_type, end_of_month, "Start")
+        self._principal = 0.0  # the reference ignores the argument (swap_float_leg.py:106)
+        self._notional_array = []
+        self._spread = spread
+        self._notional_exchange = notional_exchange
+        self._payments = []
+        self.generate_payment_dts()
+
+    def generate_payment_dts(self):
+        self._roll_schedule()
+
+    def value(self, value_dt: Date, discount_curve, index_curve=None, first_fixing_rate=None):
+        """Path-A PV of the floating leg without notional exchange (swap_float_leg.py:190-352)."""
+        if discount_curve is None:
+            raise LibError("Discount curve is None")
+        index_curve = index_curve or discount_curve
+        df0 = discount_curve.df(value_dt, self._dc_type)
+        idx_dc = DayCount(index_curve._dc_type)
+        pv, df_p, first = 0.0, 0.0, True
+        for i, dt in enumerate(self._payment_dts):
+            if not dt > value_dt:
+                continue
+            s, e = self._start_accrued_dts[i], self._end_accrued_dts[i]
+            if first and first_fixing_rate is not None:
+                fwd = first_fixing_rate
+            else:
+                fwd = (index_curve.df(s, self._dc_type) / index_curve.df(e, self._dc_type) - 1.0) \
+                    / idx_dc.year_frac(s, e)[0]
+            first = False
+            df_p = discount_curve.df(dt, self._dc_type) / df0
+            pv += (fwd + self._spread) * self._year_fracs[i] * self._notional * df_p
+        return -pv if self._leg_type == SwapTypes.PAY else pv
+
+
+class OIS:
+    """Overnight index swap: fixed leg against compounded overnight floating leg."""
+
+    def __init__(self, effective_dt: Date, term_dt_or_tenor, fixed_leg_type: SwapTypes, fixed_coupon: float,
+                 fixed_freq_type: FrequencyTypes, fixed_dc_type: DayCountTypes, floating_index: CurveTypes,
+                 currency: CurrencyTypes, notional: float = ONE_MILLION, payment_lag: int = 0,
+                 float_spread: float = 0.0, float_freq_type: FrequencyTypes = FrequencyTypes.ANNUAL,
+                 float_dc_type: DayCountTypes = DayCountTypes.THIRTY_E_360,
+                 cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD):
+        if not isinstance(fixed_leg_type, SwapTypes):
+            raise LibError("fixed_leg_type must be a SwapTypes")
+        self.derivative_type = InstrumentTypes.OIS_SWAP
+        self._termination_dt = _resolve_end(effective_dt, term_dt_or_tenor)
+        self._maturity_dt = Calendar(cal_type).adjust(self._termination_dt, bd_type)
+        if effective_dt > self._maturity_dt:
+            raise LibError("Start date after maturity date")
+        self._effective_dt = effective_dt
+        float_leg_type = SwapTypes.RECEIVE if fixed_leg_type == SwapTypes.PAY else SwapTypes.PAY
+        self._floating_index = floating_index
+        self._currency = currency
+        self._fixed_leg = SwapFixedLeg(effective_dt, self._termination_dt, fixed_leg_type, fixed_coupon,
+                                       fixed_freq_type, fixed_dc_type, floating_index, currency, notional, 0.0,
+                                       payment_lag, cal_type, bd_type, dg_type, False)
+        self._float_leg = SwapFloatLeg(effective_dt, self._termination_dt, float_leg_type, float_spread,
+                                       float_freq_type, float_dc_type, floating_index, currency, notional, 0.0,
+                                       payment_lag, cal_type, bd_type, dg_type, False, False)
+        self._adjusted_fixed_dts = self._fixed_leg._adjusted_fixed_dts
+        self._fixed_coupon = self._fixed_leg._cpn
+        self._fixed_year_fracs = self._fixed_leg._year_fracs
+        self._start_dt = self._fixed_leg._effective_dt
+        self._notional = notional
+
+    def position(self, model):
+        from .position import Position
+        return Position(self, model)
+
+    # --- non-AD path-A helpers (ois.py:209-320) ---
+    def value(self, value_dt: Date, ois_curve=None, discount_curve=None, first_fixing_rate=None):
+        discount_curve = discount_curve or ois_curve
+        return self._fixed_leg.value(value_dt, discount_curve) + \
+            self._float_leg.value(value_dt, discount_curve, ois_curve, first_fixing_rate)
+
+    def pv01(self, value_dt, discount_curve):
+        pv = self._fixed_leg.value(value_dt, discount_curve)
+        return abs(pv / self._fixed_leg._cpn / self._fixed_leg._notional * 100)
+
+    def swap_rate(self, value_dt, ois_curve, first_fixing_rate=None):
+        pv01 = self.pv01(value_dt, ois_curve)
+        return self._float_leg.value(value_dt, ois_curve, ois_curve, first_fixing_rate) / pv01 / self._fixed_leg._notional
