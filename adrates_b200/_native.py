@@ -1,0 +1,171 @@
+"""ctypes binding of the C ABI in include/adrates_b200.h.
+
+The product path has no CPU fallback: if the shared library is missing or no CUDA device
+is usable, calls raise LibError instead of silently computing elsewhere.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .error import LibError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libadrates_b200.so")
+
+REQ_VALUE, REQ_DELTA, REQ_GAMMA = 1, 2, 4
+NOUT = 1057
+
+_P = C.c_void_p
+_SIGS = {
+    "cav_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "cav_destroy": (None, [_P]),
+    "cav_last_error": (C.c_char_p, [_P]),
+    "cav_version": (C.c_int, []),
+    "cav_sync": (C.c_int, [_P]),
+    "cav_timer_start": (C.c_int, [_P]),
+    "cav_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),
+    "cav_launch_count": (C.c_int64, [_P]),
+    "cav_curve_build": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
+    "cav_curve_read": (C.c_int, [_P, _P, _P, _P]),
+    "cav_df_ad": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
+    "cav_portfolio_upload": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P,
+                                       C.c_int64, _P, _P, _P, _P]),
+    "cav_portfolio_value": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
+    "cav_portfolio_value_host": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
+    "cav_scenarios": (C.c_int, [_P, _P, C.c_int, _P]),
+}
+EXPORTS = tuple(_SIGS)
+
+_dll = None
+
+
+def load_dll():
+    """dlopen the library and type its entry points (no CUDA call is made)."""
+    global _dll
+    if _dll is None:
+        if not os.path.exists(LIB_PATH):
+            raise LibError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the valuation path)")
+        dll = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(dll, name)
+            fn.restype, fn.argtypes = res, args
+        _dll = dll
+    return _dll
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a)   # raw address (e.g. torch tensor .data_ptr())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One device context (cav_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self._dll = load_dll()
+        h = _P()
+        rc = self._dll.cav_create(C.byref(h), int(device))
+        if rc != 0 or not h:
+            raise LibError(f"cav_create(device={device}) failed with code {rc}: no usable CUDA device "
+                           "(the valuation path has no CPU fallback)")
+        self._h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._dll.cav_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise LibError(f"adrates_b200 native error {rc}: {self._dll.cav_last_error(self._h).decode()}")
+
+    # ---- misc
+    def sync(self):
+        self._ck(self._dll.cav_sync(self._h))
+
+    def timer_start(self):
+        self._ck(self._dll.cav_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._ck(self._dll.cav_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        return int(self._dll.cav_launch_count(self._h))
+
+    # ---- curve
+    def curve_build(self, interp_method: int, swap_rates, plan, order: int = 2):
+        r = _f64(swap_rates)
+        t, a = _f64(plan.node_time), _f64(plan.node_acc)
+        s = np.ascontiguousarray(plan.node_swap, dtype=np.int32)
+        p = np.ascontiguousarray(plan.node_prev, dtype=np.int32)
+        self._ck(self._dll.cav_curve_build(self._h, int(interp_method), _ptr(r), r.shape[0], _ptr(t), _ptr(a),
+                                           _ptr(s), _ptr(p), t.shape[0], int(order)))
+        self._G, self._R = t.shape[0], r.shape[0]
+
+    def curve_read(self, jac=True, hess=True):
+        G, R = self._G, self._R
+        d = np.empty(G)
+        J = np.empty((G, R)) if jac else None
+        H = np.empty((G, R, R)) if hess else None
+        self._ck(self._dll.cav_curve_read(self._h, _ptr(d), _ptr(J), _ptr(H)))
+        return d, J, H
+
+    def df_ad(self, node_time, node_df, t):
+        x, d, tt = _f64(node_time), _f64(node_df), _f64(t)
+        out = np.empty_like(tt)
+        self._ck(self._dll.cav_df_ad(self._h, _ptr(x), _ptr(d), x.shape[0], _ptr(tt), tt.shape[0], _ptr(out)))
+        return out
+
+    # ---- portfolio
+    def portfolio_upload(self, flat):
+        """flat: adrates_b200.flatten.FlatPortfolio (numpy or pinned torch-backed arrays)."""
+        self._ck(self._dll.cav_portfolio_upload(
+            self._h, flat.n_units, flat.n_terms, _ptr(flat.unit_offsets), flat.n_pairs, _ptr(flat.amt),
+            _ptr(flat.weight), _ptr(flat.node), flat.n_trades, flat.n_comp, _ptr(flat.comp_weight), flat.n_groups,
+            _ptr(flat.group_offsets), _ptr(flat.group_units), _ptr(flat.out_index), _ptr(flat.unit_weight)))
+        self._n_trades = flat.n_trades
+
+    def portfolio_value(self, mask: int, pv_dev=None, delta_dev=None, gamma_dev=None, agg_dev=None):
+        self._ck(self._dll.cav_portfolio_value(self._h, mask, _ptr(pv_dev), _ptr(delta_dev), _ptr(gamma_dev),
+                                               _ptr(agg_dev)))
+
+    def portfolio_value_host(self, mask: int, pv_dev=None, delta_dev=None, gamma_dev=None, agg_host=None):
+        if agg_host is None:
+            agg_host = np.empty(NOUT)
+        self._ck(self._dll.cav_portfolio_value_host(self._h, mask, _ptr(pv_dev), _ptr(delta_dev), _ptr(gamma_dev),
+                                                    _ptr(agg_host)))
+        return agg_host
+
+    def scenarios(self, shocked_rates, pnl_dev):
+        r = _f64(shocked_rates)
+        self._ck(self._dll.cav_scenarios(self._h, _ptr(r), r.shape[0], _ptr(pnl_dev)))
+
+
+_default = {}
+
+
+def lib(device: int = 0) -> Context:
+    """Process-wide default context per device."""
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]

@@ -1,0 +1,482 @@
+// cav_api.cu - C ABI (include/adrates_b200.h) over the kernels in cav_kernels.cuh.
+#include "../../include/adrates_b200.h"
+#include "cav_kernels.cuh"
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+struct CapTable {
+    std::vector<std::pair<void*, size_t>> v;
+    size_t get(void* p) const {
+        for (auto& e : v) if (e.first == p) return e.second;
+        return 0;
+    }
+    void set(void* p, size_t n) {
+        for (auto& e : v) if (e.first == p) { e.second = n; return; }
+        v.emplace_back(p, n);
+    }
+    void drop(void* p) {
+        for (size_t i = 0; i < v.size(); ++i) if (v[i].first == p) { v.erase(v.begin() + i); return; }
+    }
+};
+struct cav_ctx {
+    CapTable caps;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    // curve
+    int G = 0, R = 0, interp = 0, order = -1;
+    double *rates = nullptr, *node_time = nullptr, *node_acc = nullptr;
+    int *node_swap = nullptr, *node_prev = nullptr;
+    double *df = nullptr, *P = nullptr, *jac = nullptr, *dP = nullptr, *hess = nullptr, *d2P = nullptr;
+    double *L = nullptr, *g = nullptr, *Hf = nullptr, *Cf = nullptr;
+
+    // portfolio
+    int64_t n_units = 0, n_terms = 0, n_trades = 0, n_groups = 0;
+    int n_pairs = 2, n_comp = 1;
+    bool direct = false;
+    int64_t* unit_offsets = nullptr;
+    double *amt = nullptr, *weight = nullptr;
+    int* node = nullptr;
+    double* comp_weight = nullptr;
+    int64_t* group_offsets = nullptr;
+    int* group_units = nullptr;
+    int* trade_units = nullptr;
+    bool trade_units_valid = false;
+    int64_t* out_index = nullptr;
+    double* unit_weight = nullptr;
+
+    // scratch
+    double *u_pv = nullptr, *u_delta = nullptr, *u_gamma = nullptr;
+    double* partials = nullptr;
+    double* agg = nullptr;
+};
+
+namespace {
+
+int fail(cav_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    return code;
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(ctx, CAV_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+// Device buffers are grown, never shrunk: repeated uploads of same-sized portfolios (the
+// end-to-end benchmark loop) do not touch cudaMalloc/cudaFree.
+
+
+template <typename T>
+cudaError_t dev_alloc(cav_ctx* ctx, T** p, size_t n) {
+    const size_t bytes = n * sizeof(T);
+    if (*p && ctx->caps.get((void*)*p) >= bytes) return cudaSuccess;
+    if (*p) { ctx->caps.drop((void*)*p); cudaFree(*p); *p = nullptr; }
+    if (n == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)p, bytes);
+    if (e == cudaSuccess) ctx->caps.set((void*)*p, bytes);
+    return e;
+}
+
+template <typename T>
+cudaError_t upload(cav_ctx* ctx, T** p, const T* host, size_t n) {
+    cudaError_t e = dev_alloc(ctx, p, n);
+    if (e != cudaSuccess || n == 0) return e;
+    return cudaMemcpyAsync(*p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+}
+
+template <typename T>
+void dev_free(cav_ctx* ctx, T** p) {
+    if (*p) { ctx->caps.drop((void*)*p); cudaFree(*p); }
+    *p = nullptr;
+}
+
+int units_grid(const cav_ctx* ctx, int64_t n_units) {
+    int64_t want = (n_units + 7) / 8;
+    int64_t cap = (int64_t)ctx->sm_count;   // one 256-thread CTA per SM (register-heavy kernel)
+    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+}
+
+template <int NP>
+void launch_units(cav_ctx* ctx, const UnitsArgs& a, bool delta, bool gamma, int grid) {
+    if (gamma) k_units<NP, true, true><<<grid, 256, 0, ctx->stream>>>(a);
+    else if (delta) k_units<NP, true, false><<<grid, 256, 0, ctx->stream>>>(a);
+    else k_units<NP, false, false><<<grid, 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+}
+
+template <int K>
+void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma) {
+    k_expand<K><<<(unsigned)ctx->n_groups, 256, 0, ctx->stream>>>(
+        ctx->group_offsets, ctx->group_units, ctx->comp_weight, ctx->out_index, ctx->u_pv, ctx->u_delta,
+        ctx->u_gamma, pv, delta, gamma);
+    ctx->launches++;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cav_version(void) { return 100; }
+
+int cav_create(cav_ctx** out, int device) {
+    if (!out) return CAV_E_INVALID;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return CAV_E_CUDA;
+    cav_ctx* ctx = new cav_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->agg, CAV_NOUT * sizeof(double)) != cudaSuccess) {
+        delete ctx;
+        return CAV_E_CUDA;
+    }
+    *out = ctx;
+    return CAV_OK;
+}
+
+void cav_destroy(cav_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, &ctx->rates); dev_free(ctx, &ctx->node_time); dev_free(ctx, &ctx->node_acc);
+    dev_free(ctx, &ctx->node_swap); dev_free(ctx, &ctx->node_prev);
+    dev_free(ctx, &ctx->df); dev_free(ctx, &ctx->P); dev_free(ctx, &ctx->jac); dev_free(ctx, &ctx->dP);
+    dev_free(ctx, &ctx->hess); dev_free(ctx, &ctx->d2P);
+    dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
+    dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
+    dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
+    dev_free(ctx, &ctx->trade_units); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
+    dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
+    dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* cav_last_error(const cav_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t cav_launch_count(const cav_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int cav_sync(cav_ctx* ctx) {
+    if (!ctx) return CAV_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaGetLastError());
+    return CAV_OK;
+}
+
+int cav_timer_start(cav_ctx* ctx) {
+    if (!ctx) return CAV_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return CAV_OK;
+}
+
+int cav_timer_stop(cav_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return CAV_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return CAV_OK;
+}
+
+// ---------------------------------------------------------------------------- curve
+int cav_curve_build(cav_ctx* ctx, int interp_method, const double* swap_rates, int n_rates,
+                    const double* node_time, const double* node_acc, const int32_t* node_swap,
+                    const int32_t* node_prev, int n_nodes, int order) {
+    if (!ctx) return CAV_E_INVALID;
+    if (!swap_rates || !node_time || !node_acc || !node_swap || !node_prev || n_rates < 1 || n_nodes < 1 ||
+        order < 0 || order > 2)
+        return fail(ctx, CAV_E_INVALID, "cav_curve_build: null pointer or bad size");
+    if (n_rates > CAV_R) return fail(ctx, CAV_E_UNSUPPORTED, "cav_curve_build: more than 32 par-rate pillars");
+    if (interp_method != CAV_INTERP_FLAT_FWD_RATES && interp_method != CAV_INTERP_LINEAR_ZERO_RATES)
+        return fail(ctx, CAV_E_UNSUPPORTED, "Invalid interpolation scheme.");
+    if (node_prev[0] >= 0) return fail(ctx, CAV_E_INVALID, "cav_curve_build: node 0 must be a root");
+    for (int i = 0; i < n_nodes; ++i) {
+        if (node_prev[i] >= i || node_swap[i] < 0 || node_swap[i] >= n_rates)
+            return fail(ctx, CAV_E_INVALID, "cav_curve_build: plan is not causal or swap index out of range");
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t G = (size_t)n_nodes;
+    double padded[CAV_R] = {0};
+    std::memcpy(padded, swap_rates, sizeof(double) * n_rates);
+    CK(upload(ctx, &ctx->rates, padded, (size_t)CAV_R));
+    CK(upload(ctx, &ctx->node_time, node_time, G));
+    CK(upload(ctx, &ctx->node_acc, node_acc, G));
+    CK(upload(ctx, &ctx->node_swap, (const int*)node_swap, G));
+    CK(upload(ctx, &ctx->node_prev, (const int*)node_prev, G));
+    CK(dev_alloc(ctx, &ctx->df, G));
+    CK(dev_alloc(ctx, &ctx->P, G));
+    CK(dev_alloc(ctx, &ctx->L, G));
+    CK(dev_alloc(ctx, &ctx->jac, order >= 1 ? G * CAV_RW : 0));
+    CK(dev_alloc(ctx, &ctx->dP, order >= 1 ? G * CAV_RW : 0));
+    CK(dev_alloc(ctx, &ctx->g, order >= 1 ? G * CAV_RW : 0));
+    CK(dev_alloc(ctx, &ctx->hess, order >= 2 ? G * CAV_RR : 0));
+    CK(dev_alloc(ctx, &ctx->d2P, order >= 2 ? G * CAV_RR : 0));
+    CK(dev_alloc(ctx, &ctx->Hf, order >= 2 ? G * CAV_RR : 0));
+    CK(dev_alloc(ctx, &ctx->Cf, order >= 2 ? G * CAV_RR : 0));
+    k_bootstrap<<<1, 1024, 0, ctx->stream>>>(n_nodes, order, ctx->rates, ctx->node_acc, ctx->node_swap,
+                                             ctx->node_prev, ctx->df, ctx->P, ctx->jac, ctx->dP, ctx->hess,
+                                             ctx->d2P);
+    k_tables<<<n_nodes, 1024, 0, ctx->stream>>>(order, ctx->df, ctx->jac, ctx->hess, ctx->L, ctx->g, ctx->Hf,
+                                                ctx->Cf);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));   // `padded` and host inputs may go out of scope
+    ctx->G = n_nodes;
+    ctx->R = n_rates;
+    ctx->interp = interp_method;
+    ctx->order = order;
+    return CAV_OK;
+}
+
+int cav_curve_read(cav_ctx* ctx, double* dfs, double* jac, double* hess) {
+    if (!ctx) return CAV_E_INVALID;
+    if (ctx->order < 0) return fail(ctx, CAV_E_STATE, "cav_curve_read: no curve built");
+    CK(cudaSetDevice(ctx->device));
+    const int G = ctx->G, R = ctx->R;
+    if (dfs) CK(cudaMemcpyAsync(dfs, ctx->df, sizeof(double) * G, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> tmp;
+    if (jac) {
+        if (ctx->order < 1) return fail(ctx, CAV_E_STATE, "cav_curve_read: curve built without jacobian");
+        tmp.resize((size_t)G * CAV_RW);
+        CK(cudaMemcpyAsync(tmp.data(), ctx->jac, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < G; ++i)
+            for (int k = 0; k < R; ++k) jac[(size_t)i * R + k] = tmp[(size_t)i * CAV_RW + k];
+    }
+    if (hess) {
+        if (ctx->order < 2) return fail(ctx, CAV_E_STATE, "cav_curve_read: curve built without hessian");
+        tmp.resize((size_t)G * CAV_RR);
+        CK(cudaMemcpyAsync(tmp.data(), ctx->hess, sizeof(double) * tmp.size(), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int i = 0; i < G; ++i)
+            for (int j = 0; j < R; ++j)
+                for (int k = 0; k < R; ++k)
+                    hess[((size_t)i * R + j) * R + k] = tmp[(size_t)i * CAV_RR + j * CAV_RW + k];
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CAV_OK;
+}
+
+int cav_df_ad(cav_ctx* ctx, const double* node_time, const double* node_df, int n_nodes, const double* t,
+              int64_t n, double* out) {
+    if (!ctx) return CAV_E_INVALID;
+    if (!node_time || !node_df || n_nodes < 3 || (!t && n) || (!out && n) || n < 0)
+        return fail(ctx, CAV_E_INVALID, "cav_df_ad: null pointer or fewer than 3 nodes");
+    if (n == 0) return CAV_OK;
+    CK(cudaSetDevice(ctx->device));
+    double *x = nullptr, *d = nullptr, *tt = nullptr, *o = nullptr;
+    cudaError_t e = upload(ctx, &x, node_time, (size_t)n_nodes);
+    if (e == cudaSuccess) e = upload(ctx, &d, node_df, (size_t)n_nodes);
+    if (e == cudaSuccess) e = upload(ctx, &tt, t, (size_t)n);
+    if (e == cudaSuccess) e = dev_alloc(ctx, &o, (size_t)n);
+    if (e == cudaSuccess) {
+        k_df_ad<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(x, d, n_nodes, tt, n, o);
+        ctx->launches++;
+        e = cudaMemcpyAsync(out, o, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, &x); dev_free(ctx, &d); dev_free(ctx, &tt); dev_free(ctx, &o);
+    if (e != cudaSuccess) return fail(ctx, CAV_E_CUDA, std::string("cav_df_ad: ") + cudaGetErrorString(e));
+    return CAV_OK;
+}
+
+// ---------------------------------------------------------------------------- portfolio
+int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const int64_t* unit_offsets, int n_pairs,
+                         const double* amt, const double* weight, const int32_t* node, int64_t n_trades, int n_comp,
+                         const double* comp_weight, int64_t n_groups, const int64_t* group_offsets,
+                         const int32_t* group_units, const int64_t* out_index, const double* unit_weight) {
+    if (!ctx) return CAV_E_INVALID;
+    if (n_units < 0 || n_terms < 0 || n_trades < 0 || n_groups < 0 || !unit_offsets || !group_offsets ||
+        (n_terms && (!amt || !weight || !node)) || (n_trades && !comp_weight) || (n_groups && !group_units))
+        return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: null pointer or negative size");
+    if (n_pairs != 2 && n_pairs != 6) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_upload: n_pairs must be 2 or 6");
+    if (n_comp < 1 || n_comp > 4) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_upload: n_comp must be 1..4");
+    if (ctx->order < 0) return fail(ctx, CAV_E_STATE, "cav_portfolio_upload: build the curve first");
+    if (unit_offsets[0] != 0 || unit_offsets[n_units] != n_terms || group_offsets[0] != 0 ||
+        group_offsets[n_groups] != n_trades)
+        return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: offsets do not cover the arrays");
+    {   // bounds of every index the kernels will dereference (branch-free scans)
+        int lo = 0, hi = 0;
+        for (int64_t i = 0; i < n_terms * n_pairs; ++i) { lo = node[i] < lo ? node[i] : lo; hi = node[i] > hi ? node[i] : hi; }
+        if (lo < 0 || hi >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: node index out of range");
+        lo = hi = 0;
+        for (int64_t i = 0; i < n_groups * n_comp; ++i) { lo = group_units[i] < lo ? group_units[i] : lo; hi = group_units[i] > hi ? group_units[i] : hi; }
+        if (lo < 0 || (n_groups && hi >= n_units)) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: unit id out of range");
+        int64_t bad = 0;
+        for (int64_t u = 0; u < n_units; ++u) bad |= (unit_offsets[u + 1] - unit_offsets[u]) >> 63;
+        for (int64_t gi = 0; gi < n_groups; ++gi) bad |= (group_offsets[gi + 1] - group_offsets[gi]) >> 63;
+        if (out_index)
+            for (int64_t t = 0; t < n_trades; ++t) bad |= (out_index[t] >> 63) | ((n_trades - 1 - out_index[t]) >> 63);
+        if (bad) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: offsets not monotone or out_index out of range");
+    }
+    bool direct = (n_comp == 1 && n_units == n_trades && n_groups == n_trades);
+    if (direct) {
+        int64_t bad = 0;
+        for (int64_t t = 0; t < n_trades; ++t) bad |= (group_units[t] != t) | (comp_weight[t] != 1.0);
+        direct = !bad;
+    }
+    std::vector<double> W;
+    if (!direct && !unit_weight) {   // sum of trade weights per unit, in trade order
+        W.assign((size_t)n_units, 0.0);
+        for (int64_t gi = 0; gi < n_groups; ++gi)
+            for (int64_t t = group_offsets[gi]; t < group_offsets[gi + 1]; ++t)
+                for (int k = 0; k < n_comp; ++k) W[group_units[gi * n_comp + k]] += comp_weight[t * n_comp + k];
+        unit_weight = W.data();
+    }
+    CK(cudaSetDevice(ctx->device));
+    CK(upload(ctx, &ctx->unit_offsets, unit_offsets, (size_t)n_units + 1));
+    CK(upload(ctx, &ctx->amt, amt, (size_t)n_terms));
+    CK(upload(ctx, &ctx->weight, weight, (size_t)n_terms * n_pairs));
+    CK(upload(ctx, &ctx->node, (const int*)node, (size_t)n_terms * n_pairs));
+    CK(upload(ctx, &ctx->comp_weight, comp_weight, (size_t)n_trades * n_comp));
+    CK(upload(ctx, &ctx->group_offsets, group_offsets, (size_t)n_groups + 1));
+    CK(upload(ctx, &ctx->group_units, (const int*)group_units, (size_t)n_groups * n_comp));
+    if (!direct) CK(upload(ctx, &ctx->unit_weight, unit_weight, (size_t)n_units));
+    if (out_index) CK(upload(ctx, &ctx->out_index, out_index, (size_t)n_trades));
+    else dev_free(ctx, &ctx->out_index);
+    CK(cudaStreamSynchronize(ctx->stream));   // host buffers may be reused by the caller
+    ctx->n_units = n_units; ctx->n_terms = n_terms; ctx->n_trades = n_trades; ctx->n_groups = n_groups;
+    ctx->n_pairs = n_pairs; ctx->n_comp = n_comp; ctx->direct = direct;
+    ctx->trade_units_valid = false;
+    return CAV_OK;
+}
+
+static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, double* gamma, double* agg_dev,
+                      double* agg_host) {
+    if (!ctx) return CAV_E_INVALID;
+    if (ctx->order < 0) return fail(ctx, CAV_E_STATE, "cav_portfolio_value: no curve");
+    if (!ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_portfolio_value: no portfolio uploaded");
+    const bool want_d = (mask & CAV_REQ_DELTA) != 0, want_g = (mask & CAV_REQ_GAMMA) != 0;
+    if ((want_d || want_g) && ctx->order < 1) return fail(ctx, CAV_E_STATE, "curve built without jacobian");
+    if (want_g && ctx->order < 2) return fail(ctx, CAV_E_STATE, "curve built without hessian");
+    if (!want_d) delta = nullptr;
+    if (!want_g) gamma = nullptr;
+    if (!(mask & CAV_REQ_VALUE)) pv = nullptr;
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_units == 0) {
+        if (agg_dev) CK(cudaMemsetAsync(agg_dev, 0, sizeof(double) * CAV_NOUT, ctx->stream));
+        if (agg_host) std::memset(agg_host, 0, sizeof(double) * CAV_NOUT);
+        return CAV_OK;
+    }
+    const bool need_agg = agg_dev || agg_host;
+    const int grid = units_grid(ctx, ctx->n_units);
+    const int64_t rows = (int64_t)grid * 8;
+    if (need_agg) CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
+    UnitsArgs a;
+    a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
+    a.node = ctx->node; a.L = ctx->L; a.g = ctx->g; a.Hf = ctx->Hf; a.Cf = ctx->Cf;
+    a.partials = need_agg ? ctx->partials : nullptr;
+    if (ctx->direct) {
+        a.unit_weight = nullptr; a.out_index = ctx->out_index;
+        a.out_pv = pv; a.out_delta = delta; a.out_gamma = gamma;
+    } else {
+        const bool per_trade = pv || delta || gamma;
+        if (per_trade) {
+            CK(dev_alloc(ctx, &ctx->u_pv, (size_t)ctx->n_units));
+            if (delta) CK(dev_alloc(ctx, &ctx->u_delta, (size_t)ctx->n_units * CAV_RW));
+            if (gamma) CK(dev_alloc(ctx, &ctx->u_gamma, (size_t)ctx->n_units * CAV_RR));
+        }
+        a.unit_weight = ctx->unit_weight; a.out_index = nullptr;
+        a.out_pv = per_trade ? ctx->u_pv : nullptr;
+        a.out_delta = delta ? ctx->u_delta : nullptr;
+        a.out_gamma = gamma ? ctx->u_gamma : nullptr;
+    }
+    if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
+    else launch_units<6>(ctx, a, want_d, want_g, grid);
+    CK(cudaGetLastError());
+    if (!ctx->direct && (pv || delta || gamma) && ctx->n_groups > 0) {
+        switch (ctx->n_comp) {
+            case 1: launch_expand<1>(ctx, pv, delta, gamma); break;
+            case 2: launch_expand<2>(ctx, pv, delta, gamma); break;
+            case 3: launch_expand<3>(ctx, pv, delta, gamma); break;
+            default: launch_expand<4>(ctx, pv, delta, gamma); break;
+        }
+        CK(cudaGetLastError());
+    }
+    if (need_agg) {
+        double* dst = agg_dev ? agg_dev : ctx->agg;
+        k_reduce_partials<<<(CAV_NOUT + 127) / 128, 128, 0, ctx->stream>>>(ctx->partials, rows, dst);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        if (agg_host) {
+            CK(cudaMemcpyAsync(agg_host, dst, sizeof(double) * CAV_NOUT, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return CAV_OK;
+}
+
+int cav_portfolio_value(cav_ctx* ctx, uint32_t request_mask, double* pv_dev, double* delta_dev, double* gamma_dev,
+                        double* agg_dev) {
+    return value_impl(ctx, request_mask, pv_dev, delta_dev, gamma_dev, agg_dev, nullptr);
+}
+
+int cav_portfolio_value_host(cav_ctx* ctx, uint32_t request_mask, double* pv_dev, double* delta_dev,
+                             double* gamma_dev, double* agg_host) {
+    return value_impl(ctx, request_mask, pv_dev, delta_dev, gamma_dev, nullptr, agg_host);
+}
+
+// ---------------------------------------------------------------------------- scenarios
+int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev) {
+    if (!ctx) return CAV_E_INVALID;
+    if (!shocked_rates || n_scen < 1 || !pnl_dev) return fail(ctx, CAV_E_INVALID, "cav_scenarios: bad arguments");
+    if (ctx->order < 0 || !ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_scenarios: curve and portfolio first");
+    CK(cudaSetDevice(ctx->device));
+    const size_t S = (size_t)n_scen, G = (size_t)ctx->G;
+    double *rates = nullptr, *Pbuf = nullptr, *Ls = nullptr, *upv = nullptr;
+    cudaError_t e = upload(ctx, &rates, shocked_rates, S * ctx->R);
+    if (e == cudaSuccess) e = dev_alloc(ctx, &Pbuf, G * S);
+    if (e == cudaSuccess) e = dev_alloc(ctx, &Ls, G * S);
+    if (e == cudaSuccess) e = dev_alloc(ctx, &upv, (size_t)ctx->n_units * S);
+    if (e == cudaSuccess && !ctx->trade_units_valid) {
+        e = dev_alloc(ctx, &ctx->trade_units, (size_t)ctx->n_trades * ctx->n_comp);
+        if (e == cudaSuccess && ctx->n_groups > 0) {
+            k_trade_units<<<(unsigned)((ctx->n_groups + 127) / 128), 128, 0, ctx->stream>>>(
+                ctx->n_groups, ctx->n_comp, ctx->group_offsets, ctx->group_units, ctx->trade_units);
+            ctx->launches++;
+            ctx->trade_units_valid = true;
+        }
+    }
+    if (e == cudaSuccess) {
+        k_scen_bootstrap<<<(n_scen + 127) / 128, 128, 0, ctx->stream>>>(ctx->G, ctx->R, n_scen, rates, ctx->node_acc,
+                                                                      ctx->node_swap, ctx->node_prev, Pbuf, Ls);
+        dim3 gu((unsigned)ctx->n_units, (unsigned)((n_scen + 127) / 128));
+        if (ctx->n_pairs == 2)
+            k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, Ls, upv);
+        else
+            k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, Ls, upv);
+        dim3 ge((unsigned)((ctx->n_trades + 31) / 32), (unsigned)((n_scen + 31) / 32));
+        switch (ctx->n_comp) {
+            case 1: k_scen_expand<1><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
+            case 2: k_scen_expand<2><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
+            case 3: k_scen_expand<3><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
+            default: k_scen_expand<4><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
+        }
+        ctx->launches += 3;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    dev_free(ctx, &rates); dev_free(ctx, &Pbuf); dev_free(ctx, &Ls); dev_free(ctx, &upv);
+    if (e != cudaSuccess) return fail(ctx, CAV_E_CUDA, std::string("cav_scenarios: ") + cudaGetErrorString(e));
+    return CAV_OK;
+}
+
+}  // extern "C"

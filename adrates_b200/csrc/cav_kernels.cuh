@@ -1,0 +1,431 @@
+// cav_kernels.cuh - sm_100a kernels of the valuation-and-Greeks path (FP64 throughout).
+//
+//   k_bootstrap      engine grid bootstrap + exact 1st/2nd-order tangents
+//                    (reference: Engine.build_curve_ad scan + jacrev/hessian, engine.py:2337-2389)
+//   k_tables         ln-DF tables the valuation kernels read: L, g = 1e-4 J/d,
+//                    Hf = 1e-8 (C/d - J J^T/d^2) = hess(ln d), Cf = 1e-8 C/d
+//   k_units<NP,D,G>  fused interpolation + PV + delta ladder + 32x32 gamma per unit, one warp
+//                    per unit (reference: _price_fixed_leg_jax/_float_leg_jax + grad/hessian +
+//                    chain rule, engine.py:2414-2448, 2639-2728, 2551-2568)
+//   k_expand         per-trade outputs = weighted sums of unit outputs (streaming stores)
+//   k_reduce_partials  deterministic portfolio totals (reference: Portfolio.compute sums)
+//   k_df_ad          DiscountCurve._linear_forward_interp (discount_curve.py:385-415)
+//   k_scen_*         scenario re-bootstrap + revaluation (Model.scenario loop, models.py:507-557)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CAV_RW 32           // ladder width == warp size
+#define CAV_RR 1024         // gamma entries per trade
+#define CAV_NOUT 1057       // 1 + 32 + 1024
+
+// ------------------------------------------------------------------------------------------
+// Bootstrap with tangents.  One CTA of 1024 threads; thread (j,k) owns Hessian entry [j][k],
+// threads with j == 0 also own Jacobian entry [k].  Nodes are sequential (each depends on
+// the annuity of an earlier node), the R x R tangent algebra is parallel.
+//   u = 1 - r P_p, v = 1 + r a, d = u/v, P = P_p + a d            (engine.py:2341-2347)
+//   dd = (du - d dv)/v,  d2d = (d2u - dd dv^T - dv dd^T)/v
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1)
+k_bootstrap(int G, int order, const double* __restrict__ rates, const double* __restrict__ acc,
+            const int* __restrict__ swap, const int* __restrict__ prev,
+            double* df, double* P, double* jac, double* dP, double* hess, double* d2P)
+{
+    const int tid = threadIdx.x;
+    const int j = tid >> 5, k = tid & 31;
+    for (int i = 0; i < G; ++i) {
+        const int s = swap[i];
+        const int p = prev[i];
+        const double r = rates[s];
+        const double a = acc[i];
+        const double Pp = (p < 0) ? 0.0 : P[p];
+        const double u = 1.0 - r * Pp;
+        const double v = 1.0 + r * a;
+        const double d = u / v;
+        if (tid == 0) { df[i] = d; P[i] = Pp + a * d; }
+        if (order >= 1) {
+            const double dPp_j = (p < 0) ? 0.0 : dP[p * CAV_RW + j];
+            const double dPp_k = (p < 0) ? 0.0 : dP[p * CAV_RW + k];
+            const double du_j = -((j == s ? Pp : 0.0) + r * dPp_j);
+            const double du_k = -((k == s ? Pp : 0.0) + r * dPp_k);
+            const double dv_j = (j == s) ? a : 0.0;
+            const double dv_k = (k == s) ? a : 0.0;
+            const double dd_j = (du_j - d * dv_j) / v;
+            const double dd_k = (du_k - d * dv_k) / v;
+            if (j == 0) { jac[i * CAV_RW + k] = dd_k; dP[i * CAV_RW + k] = dPp_k + a * dd_k; }
+            if (order >= 2) {
+                const double d2Pp = (p < 0) ? 0.0 : d2P[(size_t)p * CAV_RR + tid];
+                const double d2u = -((j == s ? dPp_k : 0.0) + (k == s ? dPp_j : 0.0) + r * d2Pp);
+                const double d2d = (d2u - dd_j * dv_k - dv_j * dd_k) / v;
+                hess[(size_t)i * CAV_RR + tid] = d2d;
+                d2P[(size_t)i * CAV_RR + tid] = d2Pp + a * d2d;
+            }
+        }
+        __syncthreads();   // node i is visible to the CTA before any later node reads it
+    }
+}
+
+// One CTA per node, thread (j,k).
+__global__ void __launch_bounds__(1024)
+k_tables(int order, const double* __restrict__ df, const double* __restrict__ jac,
+         const double* __restrict__ hess, double* L, double* g, double* Hf, double* Cf)
+{
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int j = tid >> 5, k = tid & 31;
+    const double d = df[i];
+    const double inv = 1.0 / d;
+    if (tid == 0) L[i] = log(d);
+    if (order >= 1) {
+        const double Jj = jac[i * CAV_RW + j], Jk = jac[i * CAV_RW + k];
+        if (j == 0) g[i * CAV_RW + k] = 1e-4 * (Jk * inv);
+        if (order >= 2) {
+            const double c = hess[(size_t)i * CAV_RR + tid] * inv;
+            Cf[(size_t)i * CAV_RR + tid] = 1e-8 * c;
+            Hf[(size_t)i * CAV_RR + tid] = 1e-8 * (c - (Jj * inv) * (Jk * inv));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Units kernel.  One warp per unit, persistent warps (unit u handled by warp u mod #warps, so
+// the accumulation order of the portfolio partials is fixed).  Lanes = terms while evaluating
+// exp(); lanes = pillars (delta) / gamma columns while accumulating Greeks.
+//   ln DF_i = sum_m w_im L[n_im];  p_i = amt_i exp(ln DF_i)
+//   grad   += p_i v_i,                      v_i = sum_m w_im g[n_im]
+//   hess   += p_i (v_i v_i^T + sum_m w_im Hf[n_im])     (Cf[n] directly for a pure grid snap)
+// ------------------------------------------------------------------------------------------
+struct UnitsArgs {
+    int64_t n_units;
+    const int64_t* unit_offsets;
+    const double* amt;
+    const double* weight;      // [n_terms][NP]
+    const int* node;           // [n_terms][NP]
+    const double* L;           // [G]
+    const double* g;           // [G][32]
+    const double* Hf;          // [G][1024]
+    const double* Cf;          // [G][1024]
+    const double* unit_weight; // [n_units] sum of trade weights on this unit (portfolio totals)
+    const int64_t* out_index;  // direct mode: row of unit u in the outputs (or null = u)
+    double* out_pv;            // [rows]
+    double* out_delta;         // [rows][32]
+    double* out_gamma;         // [rows][1024]
+    double* partials;          // [n_warps][1057] or null
+};
+
+template <int NP, bool DELTA, bool GAMMA>
+__global__ void __launch_bounds__(256, 1)
+k_units(UnitsArgs A)
+{
+    __shared__ double vbuf[8][CAV_RW];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
+    const int64_t n_warps = (int64_t)gridDim.x * 8;
+
+    double tot_pv = 0.0, tot_delta = 0.0;
+    double tot_g[GAMMA ? CAV_RW : 1];
+    if (GAMMA) {
+#pragma unroll
+        for (int r = 0; r < CAV_RW; ++r) tot_g[r] = 0.0;
+    }
+
+    for (int64_t u = warp; u < A.n_units; u += n_warps) {
+        const int64_t t0 = A.unit_offsets[u], t1 = A.unit_offsets[u + 1];
+        double pv = 0.0, delta = 0.0;
+        double acc[GAMMA ? CAV_RW : 1];
+        if (GAMMA) {
+#pragma unroll
+            for (int r = 0; r < CAV_RW; ++r) acc[r] = 0.0;
+        }
+        for (int64_t base = t0; base < t1; base += 32) {
+            const int64_t i = base + lane;
+            const int cnt = (int)((t1 - base) < 32 ? (t1 - base) : 32);
+            double w[NP];
+            int n[NP];
+            double p = 0.0;
+            if (i < t1) {
+                double ell = 0.0;
+#pragma unroll
+                for (int m = 0; m < NP; ++m) {
+                    w[m] = A.weight[i * NP + m];
+                    n[m] = A.node[i * NP + m];
+                    ell += w[m] * A.L[n[m]];
+                }
+                p = A.amt[i] * exp(ell);
+            } else {
+#pragma unroll
+                for (int m = 0; m < NP; ++m) { w[m] = 0.0; n[m] = 0; }
+            }
+            pv += p;
+            if (DELTA || GAMMA) {
+                for (int jj = 0; jj < cnt; ++jj) {
+                    const double pj = __shfl_sync(0xffffffffu, p, jj);
+                    double wj[NP];
+                    int nj[NP];
+#pragma unroll
+                    for (int m = 0; m < NP; ++m) {
+                        wj[m] = __shfl_sync(0xffffffffu, w[m], jj);
+                        nj[m] = __shfl_sync(0xffffffffu, n[m], jj);
+                    }
+                    const bool snapped = (NP == 2) && (wj[0] == 1.0) && (wj[1] == 0.0);
+                    double v = 0.0;
+#pragma unroll
+                    for (int m = 0; m < NP; ++m)
+                        if (wj[m] != 0.0) v += wj[m] * __ldg(A.g + (size_t)nj[m] * CAV_RW + lane);
+                    delta += pj * v;
+                    if (GAMMA) {
+                        if (snapped) {
+                            const double* C = A.Cf + (size_t)nj[0] * CAV_RR + lane;
+#pragma unroll
+                            for (int r = 0; r < CAV_RW; ++r) acc[r] += pj * __ldg(C + r * CAV_RW);
+                        } else {
+                            __syncwarp();
+                            vbuf[wib][lane] = v;
+                            __syncwarp();
+                            const double pvk = pj * v;
+                            const double2* vb = reinterpret_cast<const double2*>(vbuf[wib]);
+#pragma unroll
+                            for (int r = 0; r < CAV_RW; r += 2) {
+                                const double2 vv = vb[r >> 1];
+                                acc[r] += pvk * vv.x;
+                                acc[r + 1] += pvk * vv.y;
+                            }
+#pragma unroll
+                            for (int m = 0; m < NP; ++m) {
+                                if (wj[m] != 0.0) {
+                                    const double pw = pj * wj[m];
+                                    const double* H = A.Hf + (size_t)nj[m] * CAV_RR + lane;
+#pragma unroll
+                                    for (int r = 0; r < CAV_RW; ++r) acc[r] += pw * __ldg(H + r * CAV_RW);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // unit PV = sum over lanes
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+        const int64_t row = A.out_index ? A.out_index[u] : u;
+        if (A.out_pv && lane == 0) A.out_pv[row] = pv;
+        if (DELTA && A.out_delta) A.out_delta[row * CAV_RW + lane] = delta;
+        if (GAMMA && A.out_gamma) {
+            double* o = A.out_gamma + row * CAV_RR + lane;
+#pragma unroll
+            for (int r = 0; r < CAV_RW; ++r) __stcs(o + r * CAV_RW, acc[r]);
+        }
+        if (A.partials) {
+            const double W = A.unit_weight ? A.unit_weight[u] : 1.0;
+            tot_pv += W * pv;
+            if (DELTA) tot_delta += W * delta;
+            if (GAMMA) {
+#pragma unroll
+                for (int r = 0; r < CAV_RW; ++r) tot_g[r] += W * acc[r];
+            }
+        }
+    }
+    if (A.partials) {
+        double* P = A.partials + warp * CAV_NOUT;
+        if (lane == 0) P[0] = tot_pv;
+        P[1 + lane] = DELTA ? tot_delta : 0.0;
+#pragma unroll
+        for (int r = 0; r < CAV_RW; ++r) P[33 + r * CAV_RW + lane] = GAMMA ? tot_g[r] : 0.0;
+    }
+}
+
+// totals[e] = sum_w partials[w][e] in warp order (deterministic)
+__global__ void k_reduce_partials(const double* __restrict__ partials, int64_t n_rows, double* totals)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= CAV_NOUT) return;
+    double s = 0.0;
+    for (int64_t w = 0; w < n_rows; ++w) s += partials[w * CAV_NOUT + e];
+    totals[e] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// Expansion: trade = sum_k weight_k * unit_k.  One CTA per group (trades sharing unit ids);
+// each thread keeps its slice of the group's unit outputs in registers and streams one 8 KB
+// gamma row per trade with 16-byte stores.  This is the HBM-write-bound stage.
+// ------------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(256)
+k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ group_units,
+         const double* __restrict__ comp_weight, const int64_t* __restrict__ out_index,
+         const double* __restrict__ u_pv, const double* __restrict__ u_delta, const double* __restrict__ u_gamma,
+         double* pv, double* delta, double* gamma)
+{
+    const int gidx = blockIdx.x, tid = threadIdx.x;
+    const int64_t t0 = group_offsets[gidx], t1 = group_offsets[gidx + 1];
+    int uid[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) uid[k] = group_units[gidx * K + k];
+    double2 ga[K], gb[K];
+    double dl[K], pvv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (gamma) {
+            const double2* src = reinterpret_cast<const double2*>(u_gamma + (size_t)uid[k] * CAV_RR);
+            ga[k] = src[tid * 2];
+            gb[k] = src[tid * 2 + 1];
+        }
+        dl[k] = (delta && tid < 32) ? u_delta[(size_t)uid[k] * CAV_RW + tid] : 0.0;
+        pvv[k] = (tid == 32) ? u_pv[uid[k]] : 0.0;
+    }
+    for (int64_t t = t0; t < t1; ++t) {
+        double w[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] = comp_weight[t * K + k];
+        const int64_t row = out_index ? out_index[t] : t;
+        if (gamma) {
+            double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                a.x += w[k] * ga[k].x; a.y += w[k] * ga[k].y;
+                b.x += w[k] * gb[k].x; b.y += w[k] * gb[k].y;
+            }
+            double2* dst = reinterpret_cast<double2*>(gamma + (size_t)row * CAV_RR);
+            __stcs(dst + tid * 2, a);
+            __stcs(dst + tid * 2 + 1, b);
+        }
+        if (delta && tid < 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) s += w[k] * dl[k];
+            delta[(size_t)row * CAV_RW + tid] = s;
+        }
+        if (pv && tid == 32) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < K; ++k) s += w[k] * pvv[k];
+            pv[row] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// df_ad: fwd_k = -ln(d_{k+1}/d_k)/(x_{k+1}-x_k); f = interp(t, x[:-1], fwd);
+//        i0 = searchsorted(x, t, 'right') - 1; DF = d[i0] exp(-f (t - x[i0]))
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int upper_bound(const double* x, int n, double t)
+{   // first index with x[i] > t
+    int lo = 0, hi = n;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (x[mid] <= t) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+__global__ void k_df_ad(const double* __restrict__ x, const double* __restrict__ d, int n,
+                        const double* __restrict__ t, int64_t m, double* out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= m) return;
+    const double tt = t[q];
+    const int nf = n - 1;                       // forward-rate knots x[0..nf-1]
+    auto fwd = [&](int k) { return -log(d[k + 1] / d[k]) / (x[k + 1] - x[k]); };
+    double f;
+    if (tt < x[0]) f = fwd(0);
+    else if (tt > x[nf - 1]) f = fwd(nf - 1);
+    else {
+        int i = upper_bound(x, nf, tt);
+        i = i < 1 ? 1 : (i > nf - 1 ? nf - 1 : i);
+        const double f0 = fwd(i - 1), f1 = fwd(i);
+        const double dx = x[i] - x[i - 1];
+        f = (fabs(dx) <= 4.930380657631324e-32) ? f0 : f0 + ((tt - x[i - 1]) / dx) * (f1 - f0);
+    }
+    int i0 = upper_bound(x, n, tt) - 1;
+    if (i0 < 0) i0 += n;                        // numpy/jax negative index wraps
+    out[q] = d[i0] * exp(-f * (tt - x[i0]));
+}
+
+// ------------------------------------------------------------------------------------------
+// Scenarios: thread per scenario re-bootstraps the grid (DFs only) and stores ln DF;
+// then unit PVs per scenario, then trades.
+// ------------------------------------------------------------------------------------------
+__global__ void k_scen_bootstrap(int G, int R, int n_scen, const double* __restrict__ rates /*[S][R]*/,
+                                 const double* __restrict__ acc, const int* __restrict__ swap,
+                                 const int* __restrict__ prev, double* Pbuf /*[G][S]*/, double* Ls /*[G][S]*/)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_scen) return;
+    for (int i = 0; i < G; ++i) {
+        const int p = prev[i];
+        const double r = rates[(size_t)s * R + swap[i]];
+        const double a = acc[i];
+        const double Pp = (p < 0) ? 0.0 : Pbuf[(size_t)p * n_scen + s];
+        const double d = (1.0 - r * Pp) / (1.0 + r * a);
+        Pbuf[(size_t)i * n_scen + s] = Pp + a * d;
+        Ls[(size_t)i * n_scen + s] = log(d);
+    }
+}
+
+// per-trade unit ids from the group table (one thread per group)
+__global__ void k_trade_units(int64_t n_groups, int K, const int64_t* __restrict__ group_offsets,
+                              const int* __restrict__ group_units, int* trade_units)
+{
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= n_groups) return;
+    for (int64_t t = group_offsets[gi]; t < group_offsets[gi + 1]; ++t)
+        for (int k = 0; k < K; ++k) trade_units[t * K + k] = group_units[gi * K + k];
+}
+
+// unit_pv[u][s]: block = 128 scenarios (threads) x loop over the unit's terms; grid (units, scen tiles)
+template <int NP>
+__global__ void __launch_bounds__(128)
+k_scen_units(int n_scen, const int64_t* __restrict__ unit_offsets, const double* __restrict__ amt,
+             const double* __restrict__ weight, const int* __restrict__ node,
+             const double* __restrict__ Ls, double* unit_pv /*[U][S]*/)
+{
+    const int64_t u = blockIdx.x;
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= n_scen) return;
+    const int64_t t0 = unit_offsets[u], t1 = unit_offsets[u + 1];
+    double pv = 0.0;
+    for (int64_t i = t0; i < t1; ++i) {
+        double ell = 0.0;
+#pragma unroll
+        for (int m = 0; m < NP; ++m) {
+            const double w = weight[i * NP + m];
+            if (w != 0.0) ell += w * Ls[(size_t)node[i * NP + m] * n_scen + s];
+        }
+        pv += amt[i] * exp(ell);
+    }
+    unit_pv[u * n_scen + s] = pv;
+}
+
+// pnl[s][row(t)] = sum_k w_tk unit_pv[u_k][s]; block handles 32 scenarios x 32 trades tile via smem transpose
+template <int K>
+__global__ void __launch_bounds__(256)
+k_scen_expand(int n_scen, int64_t n_trades, const int* __restrict__ trade_units /*[T][K]*/,
+              const double* __restrict__ comp_weight, const int64_t* __restrict__ out_index,
+              const double* __restrict__ unit_pv, double* pnl)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    const int64_t tbase = (int64_t)blockIdx.x * 32;
+    const int sbase = blockIdx.y * 32;
+    // load: rows = trades (ty..), cols = scenarios (tx) -> coalesced reads of unit_pv[u][s]
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t t = tbase + r;
+        const int s = sbase + tx;
+        double v = 0.0;
+        if (t < n_trades && s < n_scen) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const double w = comp_weight[t * K + k];
+                if (w != 0.0) v += w * unit_pv[(size_t)trade_units[t * K + k] * n_scen + s];
+            }
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    // store: rows = scenarios, cols = trades (tx) -> coalesced when out_index is near-identity
+    for (int r = ty; r < 32; r += 8) {
+        const int s = sbase + r;
+        const int64_t t = tbase + tx;
+        if (t < n_trades && s < n_scen) {
+            const int64_t row = out_index ? out_index[t] : t;
+            pnl[(size_t)s * n_trades + row] = tile[tx][r];
+        }
+    }
+}

@@ -1,0 +1,254 @@
+"""Cashflow-schedule flattener: trades -> SoA arrays for the CUDA valuation kernels.
+
+Replaces the per-trade host preparation inside the reference engine
+(cavour/market/position/engine.py:2519-2539 fixed leg, :2858-2897 floating leg):
+payment/start/end dates -> year fractions with the leg's own day count
+(times_from_dates, cavour/utils/helpers.py:154-197), past-cashflow masks (`>` for fixed,
+`>=` for floating: engine.py:2430 vs :2695), leg signs.
+
+Layout (see include/adrates_b200.h, cav_portfolio_upload):
+  unit   = set of terms  amt * prod_m DF-bracket  on the engine grid; each term carries
+           n_pairs (node, weight) pairs produced by curves.plan_queries
+  trade  = sum_k comp_weight[k] * unit[k]
+Vanilla fixed-float swaps are linear in (coupon*notional, notional, spread*notional) once
+the schedule is fixed, so with dedup=True trades that share a schedule share its units
+(annuity, floating, spread-annuity) and differ only in three weights; the Greeks of a unit
+are computed once and expanded per trade by a bandwidth-bound kernel.  dedup=False gives
+every trade a private unit (the general form for irregular trades).
+
+Floating coupons with payment_lag == 0 pay on their accrual end date, so
+((DF(s)/DF(e) - 1)/a + spread) * a * N * DF(e) = N (DF(s) - DF(e)) + spread a N DF(e):
+two single-DF terms.  With a payment lag the product DF(s) DF(p)/DF(e) is kept as one
+6-pair term.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from .curves import OISCurve, plan_queries
+from .dates import times_from_dates
+from .error import LibError
+from .global_types import InstrumentTypes, SwapTypes
+
+
+@dataclass
+class FlatPortfolio:
+    n_units: int
+    n_terms: int
+    unit_offsets: np.ndarray      # int64 [n_units+1]
+    n_pairs: int
+    amt: np.ndarray               # f64 [n_terms]
+    weight: np.ndarray            # f64 [n_terms*n_pairs]
+    node: np.ndarray              # i32 [n_terms*n_pairs]
+    n_trades: int
+    n_comp: int
+    comp_weight: np.ndarray       # f64 [n_trades*n_comp]
+    n_groups: int
+    group_offsets: np.ndarray     # int64 [n_groups+1]
+    group_units: np.ndarray       # i32 [n_groups*n_comp]
+    out_index: Optional[np.ndarray]   # int64 [n_trades] or None
+    unit_weight: np.ndarray       # f64 [n_units]
+
+    def h2d_bytes(self) -> int:
+        arrs = [self.unit_offsets, self.amt, self.weight, self.node, self.comp_weight, self.group_offsets,
+                self.group_units, self.unit_weight] + ([self.out_index] if self.out_index is not None else [])
+        return int(sum(a.nbytes for a in arrs))
+
+
+# a DF query list: times on the curve, each with an exponent (+1 / -1) inside one term
+@dataclass
+class _Unit:
+    times: list        # per term: tuple of (time, exponent) pairs, 1 or 3 entries
+    amts: list
+
+
+def _leg_sign(leg) -> float:
+    return +1.0 if leg._leg_type == SwapTypes.RECEIVE else -1.0
+
+
+def ois_components(swap, value_dt):
+    """[(key, unit, weight)] for one OIS (engine.py:153-189 = fixed leg + floating leg)."""
+    if getattr(swap, "derivative_type", None) != InstrumentTypes.OIS_SWAP:
+        raise LibError(f"{getattr(swap, 'derivative_type', type(swap))} not yet implemented")
+    out = []
+    fl, ft = swap._fixed_leg, swap._float_leg
+    # ---- fixed leg: sum_{t_i > t_val} alpha_i N c DF(t_i) (+ principal, 0 for OIS) ----
+    val_t = times_from_dates(value_dt, value_dt, fl._dc_type)
+    t_pay = [times_from_dates(d, value_dt, fl._dc_type) for d in fl._payment_dts]
+    live = [i for i, t in enumerate(t_pay) if t > val_t]
+    if live:
+        times = tuple(t_pay[i] for i in live)
+        alphas = tuple(fl._year_fracs[i] for i in live)
+        unit = _Unit([((t, 1.0),) for t in times], list(alphas))
+        out.append((("A", times, alphas), unit, _leg_sign(fl) * fl._notional * fl._cpn))
+        if fl._principal != 0.0:
+            unit_p = _Unit([((times[-1], 1.0),)], [1.0])
+            out.append((("P", times[-1]), unit_p, _leg_sign(fl) * fl._principal))
+    # ---- floating leg ----
+    val_t = times_from_dates(value_dt, value_dt, ft._dc_type)
+    tp = [times_from_dates(d, value_dt, ft._dc_type) for d in ft._payment_dts]
+    ts = [times_from_dates(d, value_dt, ft._dc_type) for d in ft._start_accrued_dts]
+    te = [times_from_dates(d, value_dt, ft._dc_type) for d in ft._end_accrued_dts]
+    al = list(ft._year_fracs)
+    live = [i for i, t in enumerate(tp) if t >= val_t]
+    notional = ft._notional
+    if ft._notional_array and any(n != notional for n in ft._notional_array):
+        raise LibError("amortising notionals need a private unit (dedup=False path)")
+    if live:
+        sgn = _leg_sign(ft)
+        fwd_terms, fwd_amts = [], []
+        for i in live:
+            if al[i] > 0:
+                if tp[i] == te[i]:
+                    fwd_terms += [((ts[i], 1.0),), ((te[i], 1.0),)]
+                    fwd_amts += [1.0, -1.0]
+                else:
+                    fwd_terms += [((ts[i], 1.0), (te[i], -1.0), (tp[i], 1.0)), ((tp[i], 1.0),)]
+                    fwd_amts += [1.0, -1.0]
+        if fwd_terms:
+            key = ("F", tuple(ts[i] for i in live), tuple(te[i] for i in live), tuple(tp[i] for i in live))
+            out.append((key, _Unit(fwd_terms, fwd_amts), sgn * notional))
+        if ft._spread != 0.0:
+            key = ("S", tuple(tp[i] for i in live), tuple(al[i] for i in live))
+            out.append((key, _Unit([((tp[i], 1.0),) for i in live], [al[i] for i in live]), sgn * notional * ft._spread))
+        if ft._principal != 0.0:
+            out.append((("P", tp[live[-1]]), _Unit([((tp[live[-1]], 1.0),)], [1.0]), sgn * ft._principal))
+    return out
+
+
+def _merge_single_df_terms(unit: _Unit):
+    """Sum amounts of single-DF terms that hit the same time; drop exact zeros."""
+    single = {}
+    multi_t, multi_a = [], []
+    for q, a in zip(unit.times, unit.amts):
+        if len(q) == 1 and q[0][1] == 1.0:
+            single[q[0][0]] = single.get(q[0][0], 0.0) + a
+        else:
+            multi_t.append(q)
+            multi_a.append(a)
+    ts = sorted(t for t, a in single.items() if a != 0.0)
+    return _Unit([((t, 1.0),) for t in ts] + multi_t, [single[t] for t in ts] + multi_a)
+
+
+class Flattener:
+    """Collects trades on one curve and emits a FlatPortfolio."""
+
+    def __init__(self, curve: OISCurve):
+        self.curve = curve
+        self.value_dt = curve._value_dt
+        self._trades = []   # list of [(key, unit, weight)]
+
+    def add_trade(self, swap):
+        self._trades.append(ois_components(swap, self.value_dt))
+
+    def add_components(self, comps):
+        self._trades.append(comps)
+
+    def finalize(self, dedup: bool = True, max_group: int = 256) -> FlatPortfolio:
+        n_trades = len(self._trades)
+        units, unit_ids = [], {}
+        trade_comps = []
+        if dedup:
+            for comps in self._trades:
+                row = []
+                for key, unit, w in comps:
+                    uid = unit_ids.get(key)
+                    if uid is None:
+                        uid = unit_ids[key] = len(units)
+                        units.append(_merge_single_df_terms(unit))
+                    row.append((uid, w))
+                trade_comps.append(row)
+        else:
+            for comps in self._trades:
+                big = _Unit([], [])
+                for _, unit, w in comps:
+                    big.times += unit.times
+                    big.amts += [a * w for a in unit.amts]
+                units.append(_merge_single_df_terms(big))
+                trade_comps.append([(len(units) - 1, 1.0)])
+        return assemble(self.curve, units, trade_comps, n_trades, direct=not dedup, max_group=max_group)
+
+
+def assemble(curve: OISCurve, units, trade_comps, n_trades, direct=False, max_group=256) -> FlatPortfolio:
+    """Plan every DF query of every unit in one vectorised call and lay out the arrays."""
+    plan = curve.path_b_plan()
+    n_pairs = 2
+    for u in units:
+        if any(len(q) > 1 for q in u.times):
+            n_pairs = 6
+            break
+    slots = n_pairs // 2
+    counts = np.array([len(u.amts) for u in units], dtype=np.int64)
+    unit_offsets = np.zeros(len(units) + 1, dtype=np.int64)
+    np.cumsum(counts, out=unit_offsets[1:])
+    n_terms = int(unit_offsets[-1])
+    amt = np.empty(n_terms)
+    q_time = np.zeros((n_terms, slots))
+    q_exp = np.zeros((n_terms, slots))
+    k = 0
+    for u in units:
+        for q, a in zip(u.times, u.amts):
+            amt[k] = a
+            for s, (t, e) in enumerate(q):
+                q_time[k, s] = t
+                q_exp[k, s] = e
+            k += 1
+    a_idx, b_idx, wa, wb = plan_queries(q_time.reshape(-1), plan.node_time, curve._interp_type)
+    ex = q_exp.reshape(-1)
+    weight = np.stack([wa * ex, wb * ex], axis=1).reshape(n_terms, n_pairs)
+    node = np.stack([a_idx, b_idx], axis=1).reshape(n_terms, n_pairs).astype(np.int32)
+    node[weight == 0.0] = 0
+    return layout_trades(len(units), unit_offsets, n_pairs, amt, weight.reshape(-1), node.reshape(-1), trade_comps,
+                         n_trades, direct, max_group)
+
+
+def layout_trades(n_units, unit_offsets, n_pairs, amt, weight, node, trade_comps, n_trades, direct, max_group):
+    n_terms = int(unit_offsets[-1])
+    if direct:
+        comp_weight = np.ones(n_trades)
+        group_offsets = np.arange(n_trades + 1, dtype=np.int64)
+        group_units = np.arange(n_trades, dtype=np.int32)
+        return FlatPortfolio(n_units, n_terms, unit_offsets, n_pairs, amt, weight, node, n_trades, 1, comp_weight,
+                             n_trades, group_offsets, group_units, None, np.ones(n_units))
+    n_comp = max([len(r) for r in trade_comps] + [1])
+    if n_comp > 4:
+        raise LibError("a trade decomposes into more than 4 units")
+    ids = np.zeros((n_trades, n_comp), dtype=np.int32)
+    ws = np.zeros((n_trades, n_comp))
+    for t, row in enumerate(trade_comps):
+        for k, (uid, w) in enumerate(row):
+            ids[t, k], ws[t, k] = uid, w
+        for k in range(len(row), n_comp):
+            ids[t, k] = row[0][0] if row else 0   # unused slot: weight 0 on an existing unit
+    return group_trades(n_units, unit_offsets, n_pairs, amt, weight, node, ids, ws, max_group)
+
+
+def group_trades(n_units, unit_offsets, n_pairs, amt, weight, node, ids, ws, max_group=256) -> FlatPortfolio:
+    """Sort trades by their unit ids so that a CTA of the expansion kernel serves one run."""
+    n_trades, n_comp = ids.shape
+    n_terms = int(unit_offsets[-1])
+    order = np.lexsort(tuple(ids[:, k] for k in reversed(range(n_comp)))) if n_trades else np.zeros(0, dtype=np.int64)
+    ids_s, ws_s = ids[order], ws[order]
+    if n_trades:
+        new_run = np.ones(n_trades, dtype=bool)
+        new_run[1:] = np.any(ids_s[1:] != ids_s[:-1], axis=1)
+        run_start = np.flatnonzero(new_run)
+        run_end = np.append(run_start[1:], n_trades)
+        starts = []
+        for s, e in zip(run_start, run_end):
+            starts.append(np.arange(s, e, max_group))
+        starts = np.concatenate(starts)
+        group_offsets = np.append(starts, n_trades).astype(np.int64)
+        group_units = ids_s[starts].astype(np.int32).reshape(-1)
+    else:
+        group_offsets = np.zeros(1, dtype=np.int64)
+        group_units = np.zeros(0, dtype=np.int32)
+    unit_weight = np.zeros(n_units)
+    for k in range(n_comp):
+        unit_weight += np.bincount(ids_s[:, k], weights=ws_s[:, k], minlength=n_units)
+    return FlatPortfolio(n_units, n_terms, unit_offsets, n_pairs, amt, weight, node, n_trades, n_comp,
+                         np.ascontiguousarray(ws_s.reshape(-1)), len(group_offsets) - 1, group_offsets, group_units,
+                         order.astype(np.int64), unit_weight)

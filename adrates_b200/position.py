@@ -1,0 +1,153 @@
+"""Position / Engine / Portfolio: the reference-facing entry points of the CUDA path.
+
+    Position(derivative, model).compute(request_list, collateral_type=None) -> AnalyticsResult
+        cavour/market/position/position.py:25-80, Engine.compute engine.py:89-124,
+        _compute_ois_natural engine.py:153-215
+    Portfolio(positions).compute(request_list) -> AnalyticsResult (sums)
+        cavour/market/portfolio/portfolio.py:8-67
+
+Unlike the reference, where every Position owns a fresh Engine and re-derives the curve
+Jacobian/Hessian (position.py:55, engine.py:2362-2412), curve tables are built once per
+(curve quotes, plan) on the device and shared; Portfolio.compute flattens all positions and
+values them in one batched launch instead of a Python loop.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List
+
+import numpy as np
+
+from . import _native
+from .curves import OISCurve
+from .dates import to_tenor
+from .error import LibError
+from .flatten import Flattener
+from .global_types import InstrumentTypes, RequestTypes
+from .results import AnalyticsResult, Delta, Gamma, Valuation
+
+
+def request_mask(request_list) -> int:
+    reqs = set(request_list)
+    unknown = [r for r in reqs if not isinstance(r, RequestTypes)]
+    if unknown:
+        raise LibError(f"Unknown request types: {unknown}")
+    mask = 0
+    if RequestTypes.VALUE in reqs:
+        mask |= _native.REQ_VALUE
+    if RequestTypes.DELTA in reqs:
+        mask |= _native.REQ_DELTA
+    if RequestTypes.GAMMA in reqs:
+        mask |= _native.REQ_GAMMA
+    if RequestTypes.CASHFLOWS in reqs:
+        raise NotImplementedError("CASHFLOWS reports use the non-AD path-A legs and are outside the CUDA path")
+    return mask
+
+
+class CurveSession:
+    """Device-resident tables of one curve (replaces Engine._cached_curve)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, curve: OISCurve, device: int = 0) -> "CurveSession":
+        key = (device, tuple(curve.swap_rates), tuple(curve.swap_times), tuple(map(tuple, curve.year_fracs)),
+               curve._interp_type)
+        sess = cls._cache.get(key)
+        if sess is None:
+            if len(cls._cache) >= 16:
+                cls._cache.pop(next(iter(cls._cache))).ctx.close()
+            sess = cls._cache[key] = CurveSession(curve, device)
+        return sess
+
+    def __init__(self, curve: OISCurve, device: int):
+        self.ctx = _native.Context(device)
+        self.curve = curve
+        self.ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+
+
+class Engine:
+    def __init__(self, model, device: int = 0):
+        self.model = model
+        self.device = device
+
+    def _curve_for(self, derivative) -> OISCurve:
+        try:
+            return getattr(self.model.curves, derivative._floating_index.name)
+        except AttributeError:
+            raise LibError(f"No curve {derivative._floating_index.name} in the model")
+
+    def compute(self, derivative, request_list, collateral_type=None) -> AnalyticsResult:
+        dtype = getattr(derivative, "derivative_type", None)
+        if dtype != InstrumentTypes.OIS_SWAP:
+            raise LibError(f"{dtype} not yet implemented")
+        if collateral_type is not None:
+            from .global_types import CurrencyTypes
+            if CurrencyTypes[collateral_type.name] != derivative._currency:
+                raise NotImplementedError("cross-currency collateral needs the XCCY curve path (not built yet)")
+        return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
+
+
+def value_positions(derivatives, curve: OISCurve, request_list, device: int = 0, dedup=None) -> AnalyticsResult:
+    """Flatten -> upload -> one batched valuation; returns the summed AnalyticsResult."""
+    mask = request_mask(request_list)
+    sess = CurveSession.get(curve, device)
+    fl = Flattener(curve)
+    for d in derivatives:
+        fl.add_trade(d)
+    flat = fl.finalize(dedup=(len(derivatives) > 1) if dedup is None else dedup)
+    sess.ctx.portfolio_upload(flat)
+    agg = sess.ctx.portfolio_value_host(mask)
+    return _result_from_totals(agg, mask, curve, derivatives[0])
+
+
+def _result_from_totals(agg, mask, curve: OISCurve, derivative) -> AnalyticsResult:
+    R = len(curve.swap_rates)
+    tenors = to_tenor(curve.swap_times)
+    ccy, idx = derivative._currency, derivative._floating_index
+    value = Valuation(float(agg[0]), ccy) if mask & _native.REQ_VALUE else None
+    delta = Delta(np.array(agg[1:1 + R]), tenors, ccy, idx) if mask & _native.REQ_DELTA else None
+    gamma = Gamma(np.array(agg[33:].reshape(32, 32)[:R, :R]), tenors, ccy, idx) if mask & _native.REQ_GAMMA else None
+    return AnalyticsResult(value=value, risk=delta, gamma=gamma)
+
+
+class Position:
+    def __init__(self, derivative, model):
+        self.derivative = derivative
+        self.model = model
+        self._engine = Engine(model)
+
+    def compute(self, request_list, collateral_type=None) -> AnalyticsResult:
+        return self._engine.compute(self.derivative, request_list, collateral_type)
+
+
+class Portfolio:
+    """Aggregates positions; compute() is ONE batched device valuation per curve."""
+
+    def __init__(self, positions: Iterable[Position] | None = None) -> None:
+        self._positions: List[Position] = list(positions or [])
+
+    def add_position(self, position: Position) -> None:
+        self._positions.append(position)
+
+    def positions(self) -> List[Position]:
+        return list(self._positions)
+
+    def compute(self, request_list: Iterable[RequestTypes]) -> AnalyticsResult:
+        request_list = list(request_list)
+        if not self._positions:
+            return AnalyticsResult()
+        buckets = {}
+        for pos in self._positions:
+            curve = pos._engine._curve_for(pos.derivative)
+            buckets.setdefault(id(curve), (curve, []))[1].append(pos.derivative)
+        total = None
+        for curve, derivs in buckets.values():
+            res = value_positions(derivs, curve, request_list)
+            if total is None:
+                total = res
+            else:   # same semantics as the reference's running sums (portfolio.py:48-65)
+                total = AnalyticsResult(
+                    value=None if res.value is None else total.value + res.value,
+                    risk=None if res.risk is None else total.risk + res.risk,
+                    gamma=None if res.gamma is None else total.gamma + res.gamma)
+        return total

@@ -1,0 +1,184 @@
+"""Result containers returned by Position.compute / Portfolio.compute.
+
+Field names and semantics follow cavour/requests/results.py: Valuation (:37-164),
+Delta (:228-380: `risk_ladder[R]`, `tenors`, `.value` = sum, `.ladder` tenor->value dict with
+the reference's label collisions), Gamma (:383-605: `risk_ladder[R,R]`, `.value` = sum of
+all entries), Risk (:839-942) and AnalyticsResult (:1124-1202).  Arrays are numpy float64.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, List, Optional
+
+import numpy as np
+
+from .global_types import CurrencyTypes, CurveTypes
+
+
+@dataclass(frozen=True)
+class Valuation:
+    amount: float
+    currency: CurrencyTypes = CurrencyTypes.NONE
+
+    def __post_init__(self):
+        if not isinstance(self.currency, CurrencyTypes):
+            raise TypeError(f"currency must be a CurrencyTypes enum, got {type(self.currency)}")
+
+    def __repr__(self):
+        return f"{self.amount:.2f} {self.currency.name}"
+
+    def _same(self, other, verb):
+        if self.currency is not other.currency:
+            raise ValueError(f"Cannot {verb} {self.currency.name} and {other.currency.name}")
+
+    def __add__(self, other: Any):
+        if not isinstance(other, Valuation):
+            return NotImplemented
+        self._same(other, "add")
+        return Valuation(self.amount + other.amount, self.currency)
+
+    def __radd__(self, other: Any):
+        return self if other == 0 else self.__add__(other)
+
+    def __sub__(self, other: Any):
+        if not isinstance(other, Valuation):
+            return NotImplemented
+        self._same(other, "subtract")
+        return Valuation(self.amount - other.amount, self.currency)
+
+    def __mul__(self, factor: float):
+        return Valuation(self.amount * factor, self.currency)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, divisor: float):
+        return Valuation(self.amount / divisor, self.currency)
+
+    def to_dict(self):
+        return {"amount": float(self.amount), "currency": self.currency.name}
+
+
+Value = Valuation
+
+
+class Ladder:
+    def __init__(self, data: dict, curve_name: str):
+        self.data = data
+        self._curve_name = curve_name
+
+    def __repr__(self):
+        return f"Ladder(curve={self._curve_name}, points={len(self.data)}, curve_data={self.data})"
+
+
+class _Sensitivity:
+    risk_ladder: np.ndarray
+    tenors: List[str]
+    currency: CurrencyTypes
+    curve_type: CurveTypes
+
+    def _validate(self):
+        arr = np.asarray(self.risk_ladder, dtype=np.float64)
+        object.__setattr__(self, "risk_ladder", arr)
+        if arr.shape[-1] != len(self.tenors):
+            raise ValueError(f"Expected {arr.shape[-1]} tenors, got {len(self.tenors)}")
+        if not isinstance(self.currency, CurrencyTypes):
+            raise TypeError(f"currency must be CurrencyTypes, got {type(self.currency)}")
+        if not isinstance(self.curve_type, CurveTypes):
+            raise TypeError(f"curve_type must be CurveTypes, got {type(self.curve_type)}")
+
+    @property
+    def value(self) -> Valuation:
+        return Valuation(float(np.sum(self.risk_ladder)), self.currency)
+
+    def __repr__(self):
+        return (f"{self.__class__.__name__}({self.curve_type.name}: {self.value.amount:.6g} "
+                f"{self.currency.name}, points={len(self.tenors)})")
+
+    def __add__(self, other: Any):
+        if not isinstance(other, self.__class__):
+            return NotImplemented
+        if (self.curve_type != other.curve_type or self.currency != other.currency or self.tenors != other.tenors):
+            raise ValueError(f"Cannot add {self.__class__.__name__} with mismatched curve_type, currency, or tenors")
+        return self.__class__(self.risk_ladder + other.risk_ladder, self.tenors, self.currency, self.curve_type)
+
+    def __radd__(self, other: Any):
+        return self if other == 0 else self.__add__(other)
+
+
+@dataclass(frozen=True, repr=False)
+class Delta(_Sensitivity):
+    """Per-bp ladder: risk_ladder[k] = 1e-4 * dPV/d(par rate k) (engine.py:2554-2555)."""
+    risk_ladder: np.ndarray
+    tenors: List[str]
+    currency: CurrencyTypes
+    curve_type: CurveTypes
+
+    def __post_init__(self):
+        self._validate()
+
+    @property
+    def ladder(self) -> Ladder:
+        return Ladder(dict(zip(self.tenors, self.risk_ladder.tolist())), self.curve_type.name)
+
+    def to_dict(self):
+        return {"risk_ladder": self.risk_ladder.tolist(), "tenors": self.tenors, "currency": self.currency.name,
+                "curve_type": self.curve_type.name, "total": float(np.sum(self.risk_ladder))}
+
+
+@dataclass(frozen=True, repr=False)
+class Gamma(_Sensitivity):
+    """Per-bp^2 matrix: risk_ladder[j,k] = 1e-8 * d2PV/d(rate j)d(rate k) (engine.py:2565-2568)."""
+    risk_ladder: np.ndarray
+    tenors: List[str]
+    currency: CurrencyTypes
+    curve_type: CurveTypes
+
+    def __post_init__(self):
+        self._validate()
+
+    @property
+    def to_dict(self) -> dict:
+        g = np.asarray(self.risk_ladder)
+        return {rt: {ct: float(g[i, j]) for j, ct in enumerate(self.tenors)} for i, rt in enumerate(self.tenors)}
+
+
+class Risk:
+    """Multi-curve container with attribute access by curve name (results.py:839-942)."""
+
+    def __init__(self, items):
+        self._items = {it.curve_type.name: it for it in items}
+
+    def __getattr__(self, name):
+        try:
+            return self.__dict__["_items"][name]
+        except KeyError:
+            raise AttributeError(f"No risk for curve {name}")
+
+    def __iter__(self):
+        return iter(self._items.values())
+
+
+class AnalyticsResult:
+    def __init__(self, value: Optional[Valuation] = None, risk=None, gamma=None, cashflows=None):
+        self._value, self._risk, self._gamma, self._cashflows = value, risk, gamma, cashflows
+
+    @property
+    def value(self):
+        return self._value
+
+    @property
+    def risk(self):
+        return self._risk
+
+    @property
+    def gamma(self):
+        return self._gamma
+
+    @property
+    def cashflows(self):
+        return self._cashflows
+
+    def __repr__(self):
+        parts = [f"{k}={v!r}" for k, v in (("value", self._value), ("risk", self._risk), ("gamma", self._gamma),
+                                           ("cashflows", self._cashflows)) if v is not None]
+        return f"AnalyticsResult({', '.join(parts)})"

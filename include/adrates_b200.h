@@ -1,0 +1,128 @@
+/*
+ * adrates_b200.h - C ABI of the B200-native valuation-and-Greeks library.
+ *
+ * The reference (ludcode/ADRates, "Cavour") has no FFI: its boundary for this path is the
+ * Python API Model.build_curve / curve.df_ad / Position.compute([VALUE, DELTA, GAMMA]) /
+ * Portfolio.compute.  The entry points below are what a Python (ctypes / jax.ffi) binding
+ * for that path calls; each one names the reference code it replaces.  See
+ * INTEGRATION.md for the reference-side stubs.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, IEEE FP64 only; no exceptions cross the ABI.
+ *   - every function returns CAV_OK (0) or a negative CAV_E_* code; cav_last_error(ctx)
+ *     returns a message for the last failure on that context.
+ *   - a context binds one CUDA device and owns one stream; calls on one context are
+ *     serialised on that stream.  Contexts are independent (one per GPU / per thread).
+ *   - pointer arguments are HOST pointers unless the name ends in `_dev`; caller owns
+ *     every buffer it passes in.  Functions that take `_dev` outputs are asynchronous on
+ *     the context stream; cav_sync() waits for them.
+ *   - pillars: n_rates <= 32 (one warp lane per par-rate pillar); ladders and gamma rows
+ *     are always written 32 wide, zero padded.
+ */
+#ifndef ADRATES_B200_H
+#define ADRATES_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAV_OK            0
+#define CAV_E_INVALID    -1   /* bad argument */
+#define CAV_E_CUDA       -2   /* CUDA runtime error (message has the detail) */
+#define CAV_E_STATE      -3   /* call order: curve / portfolio not set */
+#define CAV_E_UNSUPPORTED -4  /* e.g. n_rates > 32, unknown interpolation */
+
+#define CAV_R 32              /* ladder width */
+
+/* interpolation methods: InterpTypes values, cavour/utils/global_types.py:76-84 */
+#define CAV_INTERP_FLAT_FWD_RATES    1
+#define CAV_INTERP_LINEAR_ZERO_RATES 4
+
+/* request mask: RequestTypes, cavour/utils/global_types.py:69-74 */
+#define CAV_REQ_VALUE 1u
+#define CAV_REQ_DELTA 2u
+#define CAV_REQ_GAMMA 4u
+
+typedef struct cav_ctx cav_ctx;
+
+/* ---- context --------------------------------------------------------------------- */
+int         cav_create(cav_ctx** ctx, int device);
+void        cav_destroy(cav_ctx* ctx);
+const char* cav_last_error(const cav_ctx* ctx);
+int         cav_version(void);
+int         cav_sync(cav_ctx* ctx);
+/* CUDA-event timer on the context's own stream (torch.cuda.Event cannot see it). */
+int         cav_timer_start(cav_ctx* ctx);
+int         cav_timer_stop(cav_ctx* ctx, float* elapsed_ms);   /* synchronises */
+/* number of kernels this context has launched since creation */
+int64_t     cav_launch_count(const cav_ctx* ctx);
+
+/* ---- curve: replaces Engine.build_curve_ad + Engine._cached_curve ------------------
+ * (cavour/market/position/engine.py:2246-2412).  The host passes the rate-independent
+ * plan of the engine grid (node times, coupon accruals, parent swap, previous-annuity
+ * node: engine.py:2283-2334) and the par rates; the device runs the bootstrap recursion
+ * (engine.py:2337-2349) together with its exact first/second-order tangents, giving
+ * dfs[G], jac[G][R] (= jacrev, :2388) and hess[G][R][R] (= hessian, :2389), and derives
+ * the log-DF tables the valuation kernels read.  order: 0 = dfs, 1 = +jac, 2 = +hess. */
+int cav_curve_build(cav_ctx* ctx, int interp_method,
+                    const double* swap_rates, int n_rates,
+                    const double* node_time, const double* node_acc,
+                    const int32_t* node_swap, const int32_t* node_prev, int n_nodes,
+                    int order);
+/* copy the bootstrapped tables back (any pointer may be NULL); jac is [G][n_rates],
+ * hess is [G][n_rates][n_rates] - the shapes of the reference cache (engine.py:2405-2410) */
+int cav_curve_read(cav_ctx* ctx, double* dfs, double* jac, double* hess);
+
+/* ---- curve.df_ad: replaces DiscountCurve._linear_forward_interp -------------------
+ * (cavour/market/curves/discount_curve.py:385-415) on the path-A nodes. */
+int cav_df_ad(cav_ctx* ctx, const double* node_time, const double* node_df, int n_nodes,
+              const double* t, int64_t n, double* out);
+
+/* ---- portfolio: the flattened cashflow schedule ------------------------------------
+ * Replaces the per-trade host prep of Engine._fixed_leg_analytics / _float_leg_analytics
+ * (engine.py:2519-2539, 2858-2897).  A *unit* is a set of terms
+ *       value = sum_i amt[i] * exp( sum_{m < n_pairs} weight[i][m] * L[node[i][m]] ),  L = ln dfs,
+ * i.e. cashflows whose discount factors are the reference's interpolation of the engine
+ * grid (interpolator_ad.py:210-243): each DF query is one bracket = two (node, weight)
+ * pairs precomputed by the host planner (grid snap = weight 1 on one node).  n_pairs = 2
+ * for cashflows discounted by a single DF; n_pairs = 6 lets a term be a product
+ * DF(s)*DF(p)/DF(e) (floating coupons with a payment lag, engine.py:2675-2692).
+ * A *trade* is a weighted sum of n_comp units (weight 0 = unused slot): a vanilla OIS is
+ * {coupon*notional x annuity unit, notional x float unit}; an irregular trade is one
+ * private unit with weight 1.  Trades are grouped so that the trades of a group share
+ * their unit ids: group g covers trades [group_offsets[g], group_offsets[g+1]) and uses
+ * units group_units[g*n_comp ..].  out_index (or NULL = identity) is the row of each
+ * trade in the per-trade outputs.  unit_weight[n_units] (or NULL = computed here) is the
+ * sum over trades of the weights on each unit; it turns unit results into portfolio totals. */
+int cav_portfolio_upload(cav_ctx* ctx,
+                         int64_t n_units, int64_t n_terms, const int64_t* unit_offsets,
+                         int n_pairs, const double* amt, const double* weight, const int32_t* node,
+                         int64_t n_trades, int n_comp, const double* comp_weight,
+                         int64_t n_groups, const int64_t* group_offsets, const int32_t* group_units,
+                         const int64_t* out_index, const double* unit_weight);
+
+/* ---- valuation: replaces Position.compute / Portfolio.compute ----------------------
+ * (cavour/market/position/position.py:62-80, cavour/market/portfolio/portfolio.py:39-67,
+ * engine.py:153-189, 2541-2574, 2899-2932).
+ * Per-trade outputs (device pointers, may be NULL): pv[n_trades], delta[n_trades][32]
+ * (x1e-4, per bp), gamma[n_trades][32][32] (x1e-8, per bp^2, full symmetric matrix).
+ * agg_dev (device, may be NULL): portfolio totals [1 + 32 + 1024] = sum over trades,
+ * accumulated in a fixed order (bitwise reproducible for a given upload). */
+int cav_portfolio_value(cav_ctx* ctx, uint32_t request_mask,
+                        double* pv_dev, double* delta_dev, double* gamma_dev, double* agg_dev);
+/* same, writing the portfolio totals to host memory (synchronises) */
+int cav_portfolio_value_host(cav_ctx* ctx, uint32_t request_mask,
+                             double* pv_dev, double* delta_dev, double* gamma_dev, double* agg_host);
+
+/* ---- scenarios: replaces Model.scenario + rebuild + Position.compute([VALUE]) ------
+ * (cavour/models/models.py:507-557, engine.py:2337-2349).  Each row of shocked_rates is a
+ * full par-rate vector; every curve is re-bootstrapped (DFs only) and every trade
+ * revalued.  pnl_dev[s][trade] = PV under scenario s (device, [n_scen][n_trades]). */
+int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADRATES_B200_H */

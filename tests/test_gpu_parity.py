@@ -1,0 +1,217 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the committed
+golden vectors (unmodified reference engine) and the CPU oracle.  Tolerance: 1e-10 relative
+(north_star), with the scale-aware metric of SURVEY R3."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import cavour_oracle as orc  # noqa: E402
+from adrates_b200 import _native, RequestTypes  # noqa: E402
+from adrates_b200.curves import OISCurve  # noqa: E402
+from adrates_b200.dates import Date  # noqa: E402
+from adrates_b200.flatten import Flattener  # noqa: E402
+from adrates_b200.global_types import InterpTypes  # noqa: E402
+from adrates_b200.position import Portfolio, CurveSession  # noqa: E402
+from tests.conftest import GOLDEN  # noqa: E402
+from tests.util_trades import (METHOD, build_model, leg_arrays, make_calibration_swaps, make_trade, rel_err,  # noqa: E402
+                               trade_scales)
+
+TOL = 1e-10
+ALL = [RequestTypes.VALUE, RequestTypes.DELTA, RequestTypes.GAMMA]
+MASK = _native.REQ_VALUE | _native.REQ_DELTA | _native.REQ_GAMMA
+
+
+def _curve(cv):
+    vd, swaps = make_calibration_swaps(cv)
+    return OISCurve(vd, swaps, InterpTypes[cv["interp"]])
+
+
+def _run_flat(ctx, flat, mask=MASK):
+    n = flat.n_trades
+    pv = torch.zeros(n, dtype=torch.float64, device="cuda")
+    dl = torch.zeros(n, 32, dtype=torch.float64, device="cuda")
+    gm = torch.zeros(n, 32, 32, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.portfolio_upload(flat)
+    agg = ctx.portfolio_value_host(mask, pv.data_ptr(), dl.data_ptr(), gm.data_ptr())
+    ctx.sync()
+    return pv.cpu().numpy(), dl.cpu().numpy(), gm.cpu().numpy(), agg.copy()
+
+
+@pytest.mark.parametrize("key", ["gbp_readme_lzr", "usd_dec24_lzr", "gbp_semi_lzr"])
+def test_bootstrap_tables_match_reference_ad(ref_curves, key):
+    cv = ref_curves[key]
+    curve = _curve(cv)
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    d, J, H = ctx.curve_read()
+    ref = np.load(os.path.join(GOLDEN, f"ref_tables_{key}.npz"))
+    assert np.max(np.abs(d - np.array(cv["pathB_dfs"]))) <= 4e-16
+    assert rel_err(J, ref["jac"], 1.0) < 1e-12
+    assert rel_err(H, ref["hess"], 1.0) < 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("dedup", [True, False])
+def test_trades_match_reference_engine(ref_curves, ref_trades, dedup):
+    for key, cv in ref_curves.items():
+        specs = [s for s in ref_trades if s["curve"] == key]
+        if not specs:
+            continue
+        curve = _curve(cv)
+        ctx = _native.Context(0)
+        ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+        fl = Flattener(curve)
+        for s in specs:
+            fl.add_trade(make_trade(s, cv))
+        pv, dl, gm, agg = _run_flat(ctx, fl.finalize(dedup=dedup))
+        for i, s in enumerate(specs):
+            s_pv, s_d, s_g = trade_scales(s)
+            e = (rel_err(pv[i], s["value"], s_pv), rel_err(dl[i], s["delta"], s_d), rel_err(gm[i], s["gamma"], s_g))
+            assert max(e) < TOL, (s["id"], dedup, e)
+            assert np.allclose(gm[i], gm[i].T, rtol=1e-10, atol=1e-14)
+        # portfolio totals = sum of trades (Portfolio.compute semantics)
+        tot = np.concatenate([[pv.sum()], dl.sum(0), gm.sum(0).reshape(-1)])
+        scale = np.concatenate([[np.abs(pv).sum()], np.abs(dl).sum(0), np.abs(gm).sum(0).reshape(-1)]) + 1e-300
+        assert np.max(np.abs(agg - tot) / scale) < 1e-12
+        ctx.close()
+
+
+def test_position_compute_api_matches_notebook_and_readme(ref_curves, ref_trades):
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    nb = next(t for t in ref_trades if t["id"] == "nb_1w_par")
+    res = make_trade(nb, cv).position(model).compute(ALL)
+    assert abs(res.value.amount - 4.672529030358419e-11) < 1e-9        # notebook cell 36 (abs on 1e6 notional)
+    assert abs(res.risk.ladder.data["1W"] - 1.9158970567491282) < 1e-12   # '1D'/'1W' pillars share the '1W' label
+    assert abs(res.risk.risk_ladder[1] - 1.9158970567491282) < 1e-12   # cell 40
+    assert abs(res.gamma.value.amount - (-7.34132e-06)) < 5e-12       # cell 44
+    assert len(res.risk.ladder.data) == 31 and len(res.risk.tenors) == 32
+    rd = next(t for t in ref_trades if t["id"] == "readme_10y")
+    res = make_trade(rd, cv).position(model).compute(ALL)
+    s_pv, s_d, s_g = trade_scales(rd)
+    assert rel_err(res.value.amount, rd["value"], s_pv) < TOL
+    assert rel_err(res.risk.risk_ladder, rd["delta"], s_d) < TOL
+    assert rel_err(res.gamma.risk_ladder, rd["gamma"], s_g) < TOL
+    assert res.risk.tenors == rd["delta_tenors"]
+    only_v = make_trade(rd, cv).position(model).compute([RequestTypes.VALUE])
+    assert only_v.risk is None and only_v.gamma is None and rel_err(only_v.value.amount, rd["value"], s_pv) < TOL
+
+
+def test_portfolio_compute_sums_positions(ref_curves, ref_trades):
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    specs = [s for s in ref_trades if s["curve"] == "gbp_readme_lzr"]
+    port = Portfolio([make_trade(s, cv).position(model) for s in specs])
+    res = port.compute(ALL)
+    assert rel_err(res.value.amount, sum(s["value"] for s in specs), 1e7) < TOL
+    assert rel_err(res.risk.risk_ladder, np.sum([s["delta"] for s in specs], axis=0), 1e4) < TOL
+    assert rel_err(res.gamma.risk_ladder, np.sum([s["gamma"] for s in specs], axis=0), 1e1) < TOL
+
+
+def test_reference_property_tests_hold(ref_curves):
+    """tests/test_refit_curves.py:152-231 (every calibration swap reprices to |PV| <= 1e-5 through
+    Position.compute) and tests/test_ois_request_types.py:841-905 (PAY + RECEIVE = 0 within 1e-10)."""
+    from adrates_b200 import (OIS, SwapTypes, FrequencyTypes, DayCountTypes, CurveTypes, CurrencyTypes,
+                              BusDayAdjustTypes)
+    for key in ["gbp_dec24_lzr", "gbp_semi_lzr", "gbp_quarterly_lzr", "usd_dec24_lzr", "gbp_readme_ff"]:
+        cv = ref_curves[key]
+        model = build_model(cv)
+        vd = Date(*cv["value_dt"])
+        dc, fq = DayCountTypes[cv["dc"]], FrequencyTypes[cv["freq"]]
+
+        def mk(tenor, px, side):
+            return OIS(effective_dt=vd, term_dt_or_tenor=tenor, fixed_leg_type=side, fixed_coupon=px / 100,
+                       fixed_freq_type=fq, fixed_dc_type=dc, floating_index=CurveTypes[cv["name"]],
+                       currency=CurrencyTypes[cv["name"][:3]], bd_type=BusDayAdjustTypes.MODIFIED_FOLLOWING,
+                       float_freq_type=fq, float_dc_type=dc)
+        for tenor, px in zip(cv["tenors"], cv["px"]):
+            res = mk(tenor, px, SwapTypes.PAY).position(model).compute(ALL)
+            assert abs(res.value.amount) <= 1e-5, (key, tenor, res.value.amount)
+            g = res.gamma.risk_ladder
+            assert g.shape == (32, 32) and np.allclose(g, g.T, rtol=1e-10, atol=1e-14)
+        a = mk("10Y", 4.4, SwapTypes.PAY).position(model).compute(ALL)
+        b = mk("10Y", 4.4, SwapTypes.RECEIVE).position(model).compute(ALL)
+        assert abs(a.value.amount + b.value.amount) < 1e-10
+        assert np.max(np.abs(a.risk.risk_ladder + b.risk.risk_ladder)) < 1e-10
+
+
+def test_delta_gamma_explain_scenario_pnl(ref_curves):
+    """tests/test_ois_request_types.py:429-474, 577-641: AD delta vs central finite difference through
+    Model.scenario (1bp, rel err < 1e-4) and second-order Taylor on +-100bp."""
+    from adrates_b200 import OIS, SwapTypes, FrequencyTypes, DayCountTypes, CurveTypes, CurrencyTypes, BusDayAdjustTypes
+    cv = ref_curves["gbp_dec24_lzr"]
+    model = build_model(cv)
+    vd = Date(*cv["value_dt"])
+    swap = OIS(vd, "10Y", SwapTypes.PAY, 0.04, FrequencyTypes.ANNUAL, DayCountTypes.ACT_365F, CurveTypes.GBP_OIS_SONIA,
+               CurrencyTypes.GBP, bd_type=BusDayAdjustTypes.MODIFIED_FOLLOWING, float_freq_type=FrequencyTypes.ANNUAL,
+               float_dc_type=DayCountTypes.ACT_365F)
+    base = swap.position(model).compute(ALL)
+    up = swap.position(model.scenario("GBP_OIS_SONIA", 0.01)).compute([RequestTypes.VALUE]).value.amount
+    dn = swap.position(model.scenario("GBP_OIS_SONIA", -0.01)).compute([RequestTypes.VALUE]).value.amount
+    fd = (up - dn) / 2.0
+    assert abs(fd - base.risk.value.amount) / abs(fd) < 1e-4
+    for shock_bp in (100.0, -100.0):
+        pv_s = swap.position(model.scenario("GBP_OIS_SONIA", shock_bp / 100)).compute([RequestTypes.VALUE]).value.amount
+        actual = pv_s - base.value.amount
+        taylor1 = base.risk.value.amount * shock_bp
+        taylor2 = taylor1 + 0.5 * base.gamma.value.amount * shock_bp ** 2
+        assert abs(taylor2 - actual) < abs(taylor1 - actual)
+        assert abs(taylor2 - actual) / abs(actual) < 0.05
+
+
+def test_df_ad_matches_reference(ref_curves):
+    for key, cv in ref_curves.items():
+        model = build_model(cv)
+        curve = getattr(model.curves, cv["name"])
+        got = curve.df_ad(cv["df_ad_t"])
+        assert rel_err(got, cv["df_ad"], 1.0) < 1e-13, key
+        assert abs(float(curve.df_ad(5.0)) - cv["df_ad"][5]) < 1e-13
+        # non-AD df() on path A (host) also pinned
+        from adrates_b200.dates import DayCountTypes
+        for dmy, ref in zip(cv["df_dates"], cv["df"]):
+            assert abs(curve.df(Date(*dmy), DayCountTypes[cv["dc"]]) - ref) < 1e-14
+
+
+def test_scenarios_match_oracle_rebootstrap(ref_curves, ref_trades):
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
+    specs = [s for s in ref_trades if s["curve"] == "gbp_readme_lzr"]
+    vd = Date(*cv["value_dt"])
+    swaps = [make_trade(s, cv) for s in specs]
+    rng = np.random.default_rng(7)
+    S = 5
+    shocked = np.array(cv["swap_rates"])[None, :] + rng.normal(0, 1e-3, (S, 32))
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    for dedup in (True, False):
+        fl = Flattener(curve)
+        for sw in swaps:
+            fl.add_trade(sw)
+        flat = fl.finalize(dedup=dedup)
+        ctx.portfolio_upload(flat)
+        pnl = torch.zeros(S, flat.n_trades, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.scenarios(shocked, pnl.data_ptr())
+        got = pnl.cpu().numpy()
+        for s in range(S):
+            d = orc.bootstrap_dfs(shocked[s], plan)
+            for i, sw in enumerate(swaps):
+                fixed, floating = leg_arrays(sw, vd)
+                ref = orc.ois_value_only(plan["times"], d, METHOD[cv["interp"]], fixed, floating)
+                assert abs(got[s, i] - ref) <= TOL * max(abs(ref), specs[i]["notional"]), (s, specs[i]["id"])
+    ctx.close()
+
+
+def test_error_behaviour():
+    ctx = _native.Context(0)
+    from adrates_b200.error import LibError
+    with pytest.raises(LibError):
+        ctx.portfolio_value_host(MASK)          # no curve / portfolio yet
+    ctx.close()

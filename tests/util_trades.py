@@ -64,3 +64,14 @@ def trade_scales(spec):
     T = float(ten[:-1]) * {"D": 1 / 365, "W": 7 / 365, "M": 1 / 12, "Y": 1.0}[ten[-1]]
     T = max(T, 1.0)
     return n, n * 1e-4 * T, n * 1e-8 * T * T
+
+
+def build_model(cv):
+    """Model with the golden curve built through the reference-facing API."""
+    from adrates_b200.models import Model
+    m = Model(Date(*cv["value_dt"]))
+    m.build_curve(name=cv["name"], px_list=cv["px"], tenor_list=cv["tenors"], spot_days=0, swap_type=SwapTypes.PAY,
+                  fixed_dcc_type=DayCountTypes[cv["dc"]], fixed_freq_type=FrequencyTypes[cv["freq"]],
+                  float_freq_type=FrequencyTypes[cv["freq"]], float_dc_type=DayCountTypes[cv["dc"]],
+                  bus_day_type=BusDayAdjustTypes.MODIFIED_FOLLOWING, interp_type=InterpTypes[cv["interp"]])
+    return m
