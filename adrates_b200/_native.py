@@ -28,6 +28,9 @@ _SIGS = {
     "cav_timer_start": (C.c_int, [_P]),
     "cav_timer_stop": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cav_launch_count": (C.c_int64, [_P]),
+    "cav_set_stream": (C.c_int, [_P, _P]),
+    "cav_profile": (C.c_int, [_P, C.c_int]),
+    "cav_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cav_curve_build": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "cav_curve_read": (C.c_int, [_P, _P, _P, _P]),
     "cav_df_ad": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
@@ -108,6 +111,17 @@ class Context:
         ms = C.c_float()
         self._ck(self._dll.cav_timer_stop(self._h, C.byref(ms)))
         return float(ms.value)
+
+    def set_stream(self, cuda_stream: int):
+        self._ck(self._dll.cav_set_stream(self._h, int(cuda_stream)))
+
+    def profile(self, enable: bool):
+        self._ck(self._dll.cav_profile(self._h, 1 if enable else 0))
+
+    def last_kernel_ms(self):
+        ms = (C.c_float * 3)()
+        self._ck(self._dll.cav_last_kernel_ms(self._h, ms))
+        return [float(x) for x in ms]
 
     def launch_count(self) -> int:
         return int(self._dll.cav_launch_count(self._h))

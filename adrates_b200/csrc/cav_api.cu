@@ -27,6 +27,10 @@ struct cav_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool own_stream = true;
+    bool profile = false;
+    cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int evk_n = 0;
     std::string err;
     int64_t launches = 0;
 
@@ -144,6 +148,8 @@ int cav_create(cav_ctx** out, int device) {
         delete ctx;
         return CAV_E_CUDA;
     }
+    for (int i = 0; i < 5; ++i)
+        if (cudaEventCreate(&ctx->evk[i]) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     *out = ctx;
     return CAV_OK;
 }
@@ -164,7 +170,8 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
-    cudaStreamDestroy(ctx->stream);
+    for (int i = 0; i < 5; ++i) cudaEventDestroy(ctx->evk[i]);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -177,6 +184,33 @@ int cav_sync(cav_ctx* ctx) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaGetLastError());
+    return CAV_OK;
+}
+
+int cav_set_stream(cav_ctx* ctx, void* stream) {
+    if (!ctx) return CAV_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)stream;
+    ctx->own_stream = false;
+    return CAV_OK;
+}
+
+int cav_profile(cav_ctx* ctx, int enable) {
+    if (!ctx) return CAV_E_INVALID;
+    ctx->profile = enable != 0;
+    ctx->evk_n = 0;
+    return CAV_OK;
+}
+
+int cav_last_kernel_ms(cav_ctx* ctx, float* ms /* [3]: units, expand, totals */) {
+    if (!ctx || !ms) return CAV_E_INVALID;
+    ms[0] = ms[1] = ms[2] = 0.f;
+    if (ctx->evk_n < 4) return fail(ctx, CAV_E_STATE, "cav_last_kernel_ms: no profiled valuation");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaEventSynchronize(ctx->evk[3]));
+    for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->evk[i], ctx->evk[i + 1]));
     return CAV_OK;
 }
 
@@ -399,9 +433,11 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         a.out_delta = delta ? ctx->u_delta : nullptr;
         a.out_gamma = gamma ? ctx->u_gamma : nullptr;
     }
+    if (ctx->profile) CK(cudaEventRecord(ctx->evk[0], ctx->stream));
     if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
     else launch_units<6>(ctx, a, want_d, want_g, grid);
     CK(cudaGetLastError());
+    if (ctx->profile) CK(cudaEventRecord(ctx->evk[1], ctx->stream));
     if (!ctx->direct && (pv || delta || gamma) && ctx->n_groups > 0) {
         switch (ctx->n_comp) {
             case 1: launch_expand<1>(ctx, pv, delta, gamma); break;
@@ -411,11 +447,13 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         }
         CK(cudaGetLastError());
     }
+    if (ctx->profile) CK(cudaEventRecord(ctx->evk[2], ctx->stream));
     if (need_agg) {
         double* dst = agg_dev ? agg_dev : ctx->agg;
         k_reduce_partials<<<(CAV_NOUT + 127) / 128, 128, 0, ctx->stream>>>(ctx->partials, rows, dst);
         ctx->launches++;
         CK(cudaGetLastError());
+        if (ctx->profile) { CK(cudaEventRecord(ctx->evk[3], ctx->stream)); ctx->evk_n = 4; }
         if (agg_host) {
             CK(cudaMemcpyAsync(agg_host, dst, sizeof(double) * CAV_NOUT, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));

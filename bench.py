@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark: OIS trades/sec for PV + 32-pillar delta + 32x32 gamma (FP64).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
+    python bench.py --impl reference ...                      (CPU arm: the oracle port of the reference)
+
+Workload (BASELINE.json configs[2]): 1M synthetic SONIA OIS (1Y-50Y, annual) per GPU on the
+README 32-pillar LINEAR_ZERO_RATES curve; every step values the whole book: per-trade PV,
+delta[32] and gamma[32x32] written to HBM plus the portfolio totals (the Portfolio.compute
+result), all-reduced over ranks when N > 1 (weak scaling: each rank owns its own 1M trades).
+
+Printed JSON keys follow the driver contract; additionally
+  roofline      dominant kernel (per-trade expansion, HBM-write bound) against MEASURED_PEAKS.json
+  cpu_baseline  oracle/liboracle.so (C port of the reference algorithm) on this box's host cores
+  e2e           same metric through the reference-facing call with HOST buffers: H2D of the flattened
+                book from pinned memory + valuation + D2H of the portfolio totals, every step
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+BYTES_PER_TRADE = 9712          # 1256 B explicit-cashflow input + 8 + 256 + 8192 B output
+FLOPS_NOTE = "see DESIGN.md section 5"
+METRIC = "OIS trades/sec PV+delta+gamma FP64"
+WORKLOAD = ("BASELINE configs[2]: 1M synthetic SONIA OIS (1Y-50Y annual, 50% forward-starting) per GPU, "
+            "PV + 32-pillar delta + full 32x32 gamma incl. par-rate Jacobian chain, per-trade outputs written")
+
+
+def load_curve():
+    from adrates_b200.curves import OISCurve
+    from adrates_b200.global_types import InterpTypes
+    from tests.util_trades import make_calibration_swaps
+    with open(os.path.join(ROOT, "tests", "golden", "ref_curves.json")) as f:
+        cv = json.load(f)["gbp_readme_lzr"]
+    vd, swaps = make_calibration_swaps(cv)
+    return cv, OISCurve(vd, swaps, InterpTypes[cv["interp"]])
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag, self.proc = gpu_index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+                if self.stop_flag:
+                    break
+        except Exception:  # noqa: BLE001
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            p = [x.strip() for x in r.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        busy = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_oracle_rate(cv, curve, book, sample, dense, threads=0):
+    """trades/s of the C oracle on `sample` trades of the book (all host threads by default)."""
+    from oracle import cavour_oracle as orc, c_oracle
+    from adrates_b200.synthetic import reference_leg_tables
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+    lt = reference_leg_tables(book)
+    tr = dict(sched=book.sched[:sample], coupon=book.coupon[:sample], notional=book.notional[:sample],
+              spread=book.spread[:sample], fixed_sign=book.fixed_sign[:sample])
+    t0 = time.perf_counter()
+    out = c_oracle.ois_batch((plan["times"], d, J, C), curve._interp_type.value, lt, tr, want=7, dense=dense,
+                             n_threads=threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, (threads or c_oracle.max_threads()), out
+
+
+def run_reference(args):
+    """CPU arm: the reference's algorithm (oracle port; the reference itself needs JAX, which is not
+    installed) on a bounded sample of the same workload, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cv, curve = load_curve()
+    from adrates_b200.synthetic import make_book
+    sample = args.ref_sample
+    book = make_book(curve, max(sample, 1000), seed=20240430)
+    rates = []
+    cores = 0
+    for i in range(args.warmup + args.steps):
+        r, cores, _ = cpu_oracle_rate(cv, curve, book, sample, dense=True)
+        if i >= args.warmup:
+            rates.append(r)
+    value = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "trades/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_trades_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "trades/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} trades/step of the same book; oracle/liboracle.so dense chain rule "
+                                   "(reference algorithm, curve tables built once), OpenMP over all host threads"},
+        "e2e": {"value": value, "unit": "trades/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trades", type=int, default=1_000_000, help="trades per GPU")
+    ap.add_argument("--layout", default="dedup", choices=["dedup", "private"],
+                    help="dedup: trades share schedule units (product default); private: one unit per trade")
+    ap.add_argument("--ref-sample", type=int, default=2000)
+    ap.add_argument("--cpu-sample", type=int, default=4000)
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (private layout etc.)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from adrates_b200 import _native
+    from adrates_b200.synthetic import make_book, flatten_book
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the valuation path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    cv, curve = load_curve()
+    n = args.trades
+    t0 = time.perf_counter()
+    book = make_book(curve, n, seed=20240430 + rank)       # weak scaling: every rank has its own book
+    flat = flatten_book(book, dedup=(args.layout == "dedup"))
+    flatten_s = time.perf_counter() - t0
+
+    # pinned host copies of the flattened book (the e2e arm uploads from these every step)
+    def pin(a):
+        if a is None:
+            return None
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+    pinned = {k: pin(getattr(flat, k)) for k in ("unit_offsets", "amt", "weight", "node", "comp_weight",
+                                                 "group_offsets", "group_units", "out_index", "unit_weight")}
+    import copy
+    flat_pinned = copy.copy(flat)
+    for k, t in pinned.items():
+        setattr(flat_pinned, k, None if t is None else t.numpy())
+
+    ctx = _native.Context(local)
+    stream = torch.cuda.current_stream(dev)
+    ctx.set_stream(stream.cuda_stream)                     # kernels, events and NCCL order on one stream
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    ctx.portfolio_upload(flat_pinned)
+    pv = torch.empty(n, dtype=torch.float64, device=dev)
+    dl = torch.empty(n, 32, dtype=torch.float64, device=dev)
+    gm = torch.empty(n, 32, 32, dtype=torch.float64, device=dev)
+    agg = torch.zeros(_native.NOUT, dtype=torch.float64, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    MASK = _native.REQ_VALUE | _native.REQ_DELTA | _native.REQ_GAMMA
+
+    def step():
+        ctx.portfolio_value(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr())
+        if world > 1:
+            dist.all_reduce(agg)          # portfolio PV / ladder / gamma: 1057 doubles over NVLink
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- parity gate on a sample of this rank's book before any number is reported ----
+    gate = None
+    if rank == 0:
+        _, _, (pv_c, dl_c, gm_c) = cpu_oracle_rate(cv, curve, book, 256, dense=False)
+        N = book.notional[:256]
+        e_pv = np.max(np.abs(pv[:256].cpu().numpy() - pv_c) / np.maximum(np.abs(pv_c), N))
+        e_dl = np.max(np.abs(dl[:256, :].cpu().numpy() - dl_c) / np.maximum(np.abs(dl_c), (N * 1e-4)[:, None]))
+        e_gm = np.max(np.abs(gm[:256].cpu().numpy() - gm_c) / np.maximum(np.abs(gm_c), (N * 1e-8)[:, None, None]))
+        gate = float(max(e_pv, e_dl, e_gm))
+        if not gate < 1e-10:
+            raise SystemExit(f"parity gate failed: scaled error {gate:.3e} >= 1e-10")
+
+    # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps ----
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    ctx.profile(True)
+    launches0 = ctx.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kern_ms = []
+    barrier()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record(stream)
+        step()
+        b.record(stream)
+        b.synchronize()
+        kern_ms.append(ctx.last_kernel_ms())
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ctx.launch_count() - launches0
+    ctx.profile(False)
+    clocks = sampler.finish()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3)
+
+    # ---- e2e: host buffers -> H2D -> valuation -> D2H of portfolio totals, every step ----
+    agg_host = np.empty(_native.NOUT)
+    for _ in range(2):
+        ctx.portfolio_upload(flat_pinned)
+        ctx.portfolio_value_host(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.portfolio_upload(flat_pinned)
+        if world > 1:
+            ctx.portfolio_value(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr())
+            dist.all_reduce(agg)
+            agg_host[:] = agg.cpu().numpy()
+        else:
+            ctx.portfolio_value_host(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg_host)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * args.steps / float(e2e_s.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    k = np.array(kern_ms)                      # [steps, 3] units / expand / totals
+    dom = int(np.argmax(k.mean(0)))
+    dom_name = ["k_units (fused interpolation + PV + delta + gamma per schedule unit)",
+                "k_expand (per-trade PV/delta/gamma rows from unit results, streaming stores)",
+                "k_reduce_partials"][dom]
+    dom_ms = float(k[:, dom].mean())
+    achieved = n * BYTES_PER_TRADE / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
+                "algorithmic_bytes_per_launch": n * BYTES_PER_TRADE,
+                "step_frac": (n * BYTES_PER_TRADE / (ms_per_step * 1e-3) / 1e9) / peak,
+                "all_kernels_ms": {"k_units": float(k[:, 0].mean()), "k_expand": float(k[:, 1].mean()),
+                                   "k_reduce_partials": float(k[:, 2].mean())}}
+    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(prof):
+        try:
+            with open(prof) as f:
+                roofline["traffic"] = json.load(f).get(args.layout)
+        except Exception:  # noqa: BLE001
+            pass
+
+    cpu_dense, cores, _ = cpu_oracle_rate(cv, curve, book, min(args.cpu_sample, n), dense=True)
+    cpu_sparse, _, _ = cpu_oracle_rate(cv, curve, book, min(20 * args.cpu_sample, n), dense=False)
+    cpu_baseline = {"value": cpu_dense, "unit": "trades/s", "cores": cores, "kind": "port",
+                    "sample": f"first {min(args.cpu_sample, n)} trades of the same book, oracle/liboracle.so with the "
+                              "reference's dense chain rule (J^T H J + sum g_k C_k per leg), curve tables built once, "
+                              "OpenMP over all host threads",
+                    "value_sparse_port": cpu_sparse,
+                    "sparse_note": "same arithmetic skipping structurally-zero rows (fastest CPU port we have)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "trades/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "trades_per_gpu": n, "layout": args.layout,
+                   "units": flat.n_units, "terms": flat.n_terms, "groups": flat.n_groups,
+                   "l2": "flushed (256 MiB memset) before every timed step; each step also streams "
+                         f"{n * 8456 / 1e9:.2f} GB of outputs (>> 126 MB L2)",
+                   "timing": "per-step CUDA events on the launch stream, summed over K steps, max over ranks",
+                   "parity_gate_scaled_err": gate, "flatten_seconds_untimed": flatten_s,
+                   "wall_seconds_timed_region": wall},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "trades/s", "h2d_bytes_per_step": flat.h2d_bytes(),
+                "d2h_bytes_per_step": _native.NOUT * 8,
+                "note": "cav_portfolio_upload from pinned host arrays + cav_portfolio_value(_host) + totals D2H; "
+                        "per-trade rows stay in HBM"},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -56,6 +56,13 @@ int         cav_sync(cav_ctx* ctx);
 /* CUDA-event timer on the context's own stream (torch.cuda.Event cannot see it). */
 int         cav_timer_start(cav_ctx* ctx);
 int         cav_timer_stop(cav_ctx* ctx, float* elapsed_ms);   /* synchronises */
+/* run this context's work on a caller-owned CUDA stream (e.g. the framework's current
+ * stream, so its events and collectives order with the kernels here) */
+int         cav_set_stream(cav_ctx* ctx, void* cuda_stream);
+/* per-kernel CUDA-event timing of cav_portfolio_value: ms[0] units kernel, ms[1] per-trade
+ * expansion kernel, ms[2] portfolio-total reduction (needs agg output) */
+int         cav_profile(cav_ctx* ctx, int enable);
+int         cav_last_kernel_ms(cav_ctx* ctx, float* ms);
 /* number of kernels this context has launched since creation */
 int64_t     cav_launch_count(const cav_ctx* ctx);
 
