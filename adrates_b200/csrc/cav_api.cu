@@ -105,9 +105,8 @@ void dev_free(cav_ctx* ctx, T** p) {
 }
 
 int units_grid(const cav_ctx* ctx, int64_t n_units) {
-    int64_t want = (n_units + 7) / 8;
-    int64_t cap = (int64_t)ctx->sm_count;   // one 256-thread CTA per SM (register-heavy kernel)
-    return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    int64_t cap = (int64_t)ctx->sm_count * 4;   // persistent CTAs, 4 x 256 threads resident per SM (60-64 regs)
+    return (int)(n_units < cap ? (n_units < 1 ? 1 : n_units) : cap);
 }
 
 template <int NP>
@@ -356,10 +355,13 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
         if (lo < 0 || (n_groups && hi >= n_units)) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: unit id out of range");
         int64_t bad = 0;
         for (int64_t u = 0; u < n_units; ++u) bad |= (unit_offsets[u + 1] - unit_offsets[u]) >> 63;
-        for (int64_t gi = 0; gi < n_groups; ++gi) bad |= (group_offsets[gi + 1] - group_offsets[gi]) >> 63;
+        for (int64_t gi = 0; gi < n_groups; ++gi) {
+            const int64_t c = group_offsets[gi + 1] - group_offsets[gi];
+            bad |= (c >> 63) | ((256 - c) >> 63);      // 0 <= group size <= 256
+        }
         if (out_index)
             for (int64_t t = 0; t < n_trades; ++t) bad |= (out_index[t] >> 63) | ((n_trades - 1 - out_index[t]) >> 63);
-        if (bad) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: offsets not monotone or out_index out of range");
+        if (bad) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: offsets not monotone, group larger than 256 trades or out_index out of range");
     }
     bool direct = (n_comp == 1 && n_units == n_trades && n_groups == n_trades);
     if (direct) {
@@ -412,7 +414,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     }
     const bool need_agg = agg_dev || agg_host;
     const int grid = units_grid(ctx, ctx->n_units);
-    const int64_t rows = (int64_t)grid * 8;
+    const int64_t rows = (int64_t)grid;
     if (need_agg) CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
     UnitsArgs a;
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
@@ -450,7 +452,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[2], ctx->stream));
     if (need_agg) {
         double* dst = agg_dev ? agg_dev : ctx->agg;
-        k_reduce_partials<<<(CAV_NOUT + 127) / 128, 128, 0, ctx->stream>>>(ctx->partials, rows, dst);
+        k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
         ctx->launches++;
         CK(cudaGetLastError());
         if (ctx->profile) { CK(cudaEventRecord(ctx->evk[3], ctx->stream)); ctx->evk_n = 4; }

@@ -109,94 +109,87 @@ struct UnitsArgs {
     double* out_pv;            // [rows]
     double* out_delta;         // [rows][32]
     double* out_gamma;         // [rows][1024]
-    double* partials;          // [n_warps][1057] or null
+    double* partials;          // [gridDim.x][1057] or null
 };
 
+// CTA per unit (persistent: CTA b takes units b, b+grid, ...), 8 warps; warp w owns gamma rows
+// 4w..4w+3 (lane = column), warp 0 also owns the delta ladder and the PV.  Terms are staged in
+// shared memory 256 at a time (thread = term for the exp), then every warp walks the terms.
+// Few registers per thread -> many resident warps to cover the L1/L2 latency of the table rows.
+#define CAV_UW 8                 // warps per CTA
+#define CAV_ROWS 4               // gamma rows per warp
 template <int NP, bool DELTA, bool GAMMA>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256)
 k_units(UnitsArgs A)
 {
-    __shared__ double vbuf[8][CAV_RW];
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int64_t warp = (int64_t)blockIdx.x * 8 + wib;
-    const int64_t n_warps = (int64_t)gridDim.x * 8;
+    __shared__ double s_p[256];
+    __shared__ double s_w[256][NP];
+    __shared__ int s_n[256][NP];
+    __shared__ double s_red[CAV_UW];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int r0 = wib * CAV_ROWS;
 
     double tot_pv = 0.0, tot_delta = 0.0;
-    double tot_g[GAMMA ? CAV_RW : 1];
-    if (GAMMA) {
+    double tot_g[CAV_ROWS];
 #pragma unroll
-        for (int r = 0; r < CAV_RW; ++r) tot_g[r] = 0.0;
-    }
+    for (int q = 0; q < CAV_ROWS; ++q) tot_g[q] = 0.0;
 
-    for (int64_t u = warp; u < A.n_units; u += n_warps) {
+    for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
         const int64_t t0 = A.unit_offsets[u], t1 = A.unit_offsets[u + 1];
         double pv = 0.0, delta = 0.0;
-        double acc[GAMMA ? CAV_RW : 1];
-        if (GAMMA) {
+        double acc[CAV_ROWS];
 #pragma unroll
-            for (int r = 0; r < CAV_RW; ++r) acc[r] = 0.0;
-        }
-        for (int64_t base = t0; base < t1; base += 32) {
-            const int64_t i = base + lane;
-            const int cnt = (int)((t1 - base) < 32 ? (t1 - base) : 32);
-            double w[NP];
-            int n[NP];
+        for (int q = 0; q < CAV_ROWS; ++q) acc[q] = 0.0;
+        for (int64_t base = t0; base < t1; base += 256) {
+            const int cnt = (int)((t1 - base) < 256 ? (t1 - base) : 256);
+            __syncthreads();                       // previous chunk fully consumed
             double p = 0.0;
-            if (i < t1) {
+            if (tid < cnt) {
+                const int64_t i = base + tid;
                 double ell = 0.0;
 #pragma unroll
                 for (int m = 0; m < NP; ++m) {
-                    w[m] = A.weight[i * NP + m];
-                    n[m] = A.node[i * NP + m];
-                    ell += w[m] * A.L[n[m]];
+                    const double w = A.weight[i * NP + m];
+                    const int n = A.node[i * NP + m];
+                    s_w[tid][m] = w;
+                    s_n[tid][m] = n;
+                    ell += w * A.L[n];
                 }
                 p = A.amt[i] * exp(ell);
-            } else {
-#pragma unroll
-                for (int m = 0; m < NP; ++m) { w[m] = 0.0; n[m] = 0; }
+                s_p[tid] = p;
             }
             pv += p;
+            __syncthreads();
             if (DELTA || GAMMA) {
                 for (int jj = 0; jj < cnt; ++jj) {
-                    const double pj = __shfl_sync(0xffffffffu, p, jj);
+                    const double pj = s_p[jj];
                     double wj[NP];
                     int nj[NP];
 #pragma unroll
-                    for (int m = 0; m < NP; ++m) {
-                        wj[m] = __shfl_sync(0xffffffffu, w[m], jj);
-                        nj[m] = __shfl_sync(0xffffffffu, n[m], jj);
-                    }
+                    for (int m = 0; m < NP; ++m) { wj[m] = s_w[jj][m]; nj[m] = s_n[jj][m]; }
                     const bool snapped = (NP == 2) && (wj[0] == 1.0) && (wj[1] == 0.0);
                     double v = 0.0;
 #pragma unroll
                     for (int m = 0; m < NP; ++m)
                         if (wj[m] != 0.0) v += wj[m] * __ldg(A.g + (size_t)nj[m] * CAV_RW + lane);
-                    delta += pj * v;
+                    if (DELTA && wib == 0) delta += pj * v;
                     if (GAMMA) {
                         if (snapped) {
-                            const double* C = A.Cf + (size_t)nj[0] * CAV_RR + lane;
+                            const double* C = A.Cf + (size_t)nj[0] * CAV_RR + r0 * CAV_RW + lane;
 #pragma unroll
-                            for (int r = 0; r < CAV_RW; ++r) acc[r] += pj * __ldg(C + r * CAV_RW);
+                            for (int q = 0; q < CAV_ROWS; ++q) acc[q] += pj * __ldg(C + q * CAV_RW);
                         } else {
-                            __syncwarp();
-                            vbuf[wib][lane] = v;
-                            __syncwarp();
                             const double pvk = pj * v;
-                            const double2* vb = reinterpret_cast<const double2*>(vbuf[wib]);
 #pragma unroll
-                            for (int r = 0; r < CAV_RW; r += 2) {
-                                const double2 vv = vb[r >> 1];
-                                acc[r] += pvk * vv.x;
-                                acc[r + 1] += pvk * vv.y;
-                            }
+                            for (int q = 0; q < CAV_ROWS; ++q)
+                                acc[q] += pvk * __shfl_sync(0xffffffffu, v, r0 + q);
 #pragma unroll
                             for (int m = 0; m < NP; ++m) {
                                 if (wj[m] != 0.0) {
                                     const double pw = pj * wj[m];
-                                    const double* H = A.Hf + (size_t)nj[m] * CAV_RR + lane;
+                                    const double* H = A.Hf + (size_t)nj[m] * CAV_RR + r0 * CAV_RW + lane;
 #pragma unroll
-                                    for (int r = 0; r < CAV_RW; ++r) acc[r] += pw * __ldg(H + r * CAV_RW);
+                                    for (int q = 0; q < CAV_ROWS; ++q) acc[q] += pw * __ldg(H + q * CAV_RW);
                                 }
                             }
                         }
@@ -204,44 +197,63 @@ k_units(UnitsArgs A)
                 }
             }
         }
-        // unit PV = sum over lanes
+        // unit PV: fixed-order reduction over the CTA (lanes, then warps)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
-        const int64_t row = A.out_index ? A.out_index[u] : u;
-        if (A.out_pv && lane == 0) A.out_pv[row] = pv;
-        if (DELTA && A.out_delta) A.out_delta[row * CAV_RW + lane] = delta;
-        if (GAMMA && A.out_gamma) {
-            double* o = A.out_gamma + row * CAV_RR + lane;
+        __syncthreads();
+        if (lane == 0) s_red[wib] = pv;
+        __syncthreads();
+        if (wib == 0) {
+            pv = 0.0;
 #pragma unroll
-            for (int r = 0; r < CAV_RW; ++r) __stcs(o + r * CAV_RW, acc[r]);
+            for (int w = 0; w < CAV_UW; ++w) pv += s_red[w];
+        }
+        const int64_t row = A.out_index ? A.out_index[u] : u;
+        if (wib == 0) {
+            if (A.out_pv && lane == 0) A.out_pv[row] = pv;
+            if (DELTA && A.out_delta) A.out_delta[row * CAV_RW + lane] = delta;
+        }
+        if (GAMMA && A.out_gamma) {
+            double* o = A.out_gamma + row * CAV_RR + r0 * CAV_RW + lane;
+#pragma unroll
+            for (int q = 0; q < CAV_ROWS; ++q) __stcs(o + q * CAV_RW, acc[q]);
         }
         if (A.partials) {
             const double W = A.unit_weight ? A.unit_weight[u] : 1.0;
-            tot_pv += W * pv;
-            if (DELTA) tot_delta += W * delta;
+            if (wib == 0) {
+                tot_pv += W * pv;
+                if (DELTA) tot_delta += W * delta;
+            }
             if (GAMMA) {
 #pragma unroll
-                for (int r = 0; r < CAV_RW; ++r) tot_g[r] += W * acc[r];
+                for (int q = 0; q < CAV_ROWS; ++q) tot_g[q] += W * acc[q];
             }
         }
     }
     if (A.partials) {
-        double* P = A.partials + warp * CAV_NOUT;
-        if (lane == 0) P[0] = tot_pv;
-        P[1 + lane] = DELTA ? tot_delta : 0.0;
+        double* P = A.partials + (size_t)blockIdx.x * CAV_NOUT;
+        if (wib == 0) {
+            if (lane == 0) P[0] = tot_pv;
+            P[1 + lane] = DELTA ? tot_delta : 0.0;
+        }
 #pragma unroll
-        for (int r = 0; r < CAV_RW; ++r) P[33 + r * CAV_RW + lane] = GAMMA ? tot_g[r] : 0.0;
+        for (int q = 0; q < CAV_ROWS; ++q) P[33 + (r0 + q) * CAV_RW + lane] = GAMMA ? tot_g[q] : 0.0;
     }
 }
 
-// totals[e] = sum_w partials[w][e] in warp order (deterministic)
-__global__ void k_reduce_partials(const double* __restrict__ partials, int64_t n_rows, double* totals)
+// totals[e] = sum_rows partials[row][e]; one warp per entry, lane-strided partial sums combined
+// in a fixed butterfly order (bitwise reproducible for a given grid)
+__global__ void __launch_bounds__(256)
+k_reduce_partials(const double* __restrict__ partials, int64_t n_rows, double* totals)
 {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (e >= CAV_NOUT) return;
     double s = 0.0;
-    for (int64_t w = 0; w < n_rows; ++w) s += partials[w * CAV_NOUT + e];
-    totals[e] = s;
+    for (int64_t w = lane; w < n_rows; w += 32) s += partials[w * CAV_NOUT + e];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) totals[e] = s;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -256,8 +268,16 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
          const double* __restrict__ u_pv, const double* __restrict__ u_delta, const double* __restrict__ u_gamma,
          double* pv, double* delta, double* gamma)
 {
+    __shared__ double s_w[256][K];
+    __shared__ int64_t s_row[256];
     const int gidx = blockIdx.x, tid = threadIdx.x;
-    const int64_t t0 = group_offsets[gidx], t1 = group_offsets[gidx + 1];
+    const int64_t t0 = group_offsets[gidx];
+    const int cnt = (int)(group_offsets[gidx + 1] - t0);        // <= 256 (checked at upload)
+    if (tid < cnt) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s_w[tid][k] = comp_weight[(t0 + tid) * K + k];
+        s_row[tid] = out_index ? out_index[t0 + tid] : t0 + tid;
+    }
     int uid[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) uid[k] = group_units[gidx * K + k];
@@ -273,11 +293,12 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
         dl[k] = (delta && tid < 32) ? u_delta[(size_t)uid[k] * CAV_RW + tid] : 0.0;
         pvv[k] = (tid == 32) ? u_pv[uid[k]] : 0.0;
     }
-    for (int64_t t = t0; t < t1; ++t) {
+    __syncthreads();
+    for (int i = 0; i < cnt; ++i) {
         double w[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) w[k] = comp_weight[t * K + k];
-        const int64_t row = out_index ? out_index[t] : t;
+        for (int k = 0; k < K; ++k) w[k] = s_w[i][k];
+        const int64_t row = s_row[i];
         if (gamma) {
             double2 a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
 #pragma unroll
@@ -290,16 +311,16 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
             __stcs(dst + tid * 2 + 1, b);
         }
         if (delta && tid < 32) {
-            double s = 0.0;
+            double sdl = 0.0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) s += w[k] * dl[k];
-            delta[(size_t)row * CAV_RW + tid] = s;
+            for (int k = 0; k < K; ++k) sdl += w[k] * dl[k];
+            delta[(size_t)row * CAV_RW + tid] = sdl;
         }
         if (pv && tid == 32) {
-            double s = 0.0;
+            double spv = 0.0;
 #pragma unroll
-            for (int k = 0; k < K; ++k) s += w[k] * pvv[k];
-            pv[row] = s;
+            for (int k = 0; k < K; ++k) spv += w[k] * pvv[k];
+            pv[row] = spv;
         }
     }
 }

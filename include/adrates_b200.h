@@ -99,8 +99,8 @@ int cav_df_ad(cav_ctx* ctx, const double* node_time, const double* node_df, int 
  * A *trade* is a weighted sum of n_comp units (weight 0 = unused slot): a vanilla OIS is
  * {coupon*notional x annuity unit, notional x float unit}; an irregular trade is one
  * private unit with weight 1.  Trades are grouped so that the trades of a group share
- * their unit ids: group g covers trades [group_offsets[g], group_offsets[g+1]) and uses
- * units group_units[g*n_comp ..].  out_index (or NULL = identity) is the row of each
+ * their unit ids: group g covers trades [group_offsets[g], group_offsets[g+1]) (at most 256
+ * trades; split longer runs) and uses units group_units[g*n_comp ..].  out_index (or NULL = identity) is the row of each
  * trade in the per-trade outputs.  unit_weight[n_units] (or NULL = computed here) is the
  * sum over trades of the weights on each unit; it turns unit results into portfolio totals. */
 int cav_portfolio_upload(cav_ctx* ctx,
