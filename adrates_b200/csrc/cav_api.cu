@@ -3,6 +3,7 @@
 #include "cav_kernels.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -104,17 +105,49 @@ void dev_free(cav_ctx* ctx, T** p) {
     *p = nullptr;
 }
 
-int units_grid(const cav_ctx* ctx, int64_t n_units) {
-    int64_t cap = (int64_t)ctx->sm_count * 4;   // persistent CTAs, 4 x 256 threads resident per SM (60-64 regs)
-    return (int)(n_units < cap ? (n_units < 1 ? 1 : n_units) : cap);
+// ROWS (gamma rows per warp) trades registers against redundant per-term work; CAV_UNITS_ROWS
+// overrides the default for experiments.
+int units_rows() {
+    static int rows = [] {
+        const char* e = std::getenv("CAV_UNITS_ROWS");
+        int r = e ? std::atoi(e) : 32;
+        return (r == 4 || r == 8 || r == 16 || r == 32) ? r : 32;
+    }();
+    return rows;
+}
+
+int units_ctas_per_sm(int rows) { return rows == 32 ? 2 : (rows == 4 ? 4 : 3); }
+
+// returns grid size; *slots = number of persistent unit slots (= partial rows)
+int units_grid(const cav_ctx* ctx, int64_t n_units, bool gamma, int64_t* slots) {
+    const int rows = gamma ? units_rows() : 32;
+    const int wpu = 32 / rows;
+    int64_t want = (n_units * wpu + 7) / 8;
+    int64_t cap = (int64_t)ctx->sm_count * (gamma ? units_ctas_per_sm(rows) : 8);
+    int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+    *slots = (int64_t)grid * 8 / wpu;
+    return grid;
+}
+
+template <typename KernelT>
+void launch_units_kernel(cav_ctx* ctx, KernelT kern, const UnitsArgs& a, int grid, int rows) {
+    const size_t smem = a.partials ? (size_t)(8 / (32 / rows)) * CAV_NOUT * sizeof(double) : 0;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, 256, smem, ctx->stream>>>(a);
+    ctx->launches++;
 }
 
 template <int NP>
 void launch_units(cav_ctx* ctx, const UnitsArgs& a, bool delta, bool gamma, int grid) {
-    if (gamma) k_units<NP, true, true><<<grid, 256, 0, ctx->stream>>>(a);
-    else if (delta) k_units<NP, true, false><<<grid, 256, 0, ctx->stream>>>(a);
-    else k_units<NP, false, false><<<grid, 256, 0, ctx->stream>>>(a);
-    ctx->launches++;
+    if (gamma) {
+        switch (units_rows()) {
+            case 4: launch_units_kernel(ctx, k_units<NP, true, true, 4>, a, grid, 4); break;
+            case 8: launch_units_kernel(ctx, k_units<NP, true, true, 8>, a, grid, 8); break;
+            default: launch_units_kernel(ctx, k_units<NP, true, true, 32>, a, grid, 32); break;
+            case 16: launch_units_kernel(ctx, k_units<NP, true, true, 16>, a, grid, 16); break;
+        }
+    } else if (delta) launch_units_kernel(ctx, k_units<NP, true, false, 32>, a, grid, 32);
+    else launch_units_kernel(ctx, k_units<NP, false, false, 32>, a, grid, 32);
 }
 
 template <int K>
@@ -413,8 +446,8 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         return CAV_OK;
     }
     const bool need_agg = agg_dev || agg_host;
-    const int grid = units_grid(ctx, ctx->n_units);
-    const int64_t rows = (int64_t)grid;
+    int64_t rows = 0;
+    const int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
     if (need_agg) CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
     UnitsArgs a;
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;

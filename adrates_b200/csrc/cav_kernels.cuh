@@ -109,87 +109,106 @@ struct UnitsArgs {
     double* out_pv;            // [rows]
     double* out_delta;         // [rows][32]
     double* out_gamma;         // [rows][1024]
-    double* partials;          // [gridDim.x][1057] or null
+    double* partials;          // [unit slots][1057] or null
 };
 
-// CTA per unit (persistent: CTA b takes units b, b+grid, ...), 8 warps; warp w owns gamma rows
-// 4w..4w+3 (lane = column), warp 0 also owns the delta ladder and the PV.  Terms are staged in
-// shared memory 256 at a time (thread = term for the exp), then every warp walks the terms.
-// Few registers per thread -> many resident warps to cover the L1/L2 latency of the table rows.
-#define CAV_UW 8                 // warps per CTA
-#define CAV_ROWS 4               // gamma rows per warp
-template <int NP, bool DELTA, bool GAMMA>
+// A unit is handled by 32/ROWS independent warps; each owns ROWS rows of the 32x32 gamma
+// (lane = column) and re-derives the unit's term scalars itself (lanes = terms for the exp(),
+// then one shuffle-broadcast per term), so warps never synchronise with each other.  Warp
+// slots are persistent (slot s takes units s, s+S, ...), which fixes the accumulation order of
+// the portfolio partials.  ROWS trades registers (occupancy) against redundant per-term work.
+template <int NP, bool DELTA, bool GAMMA, int ROWS>
 __global__ void __launch_bounds__(256)
 k_units(UnitsArgs A)
 {
-    __shared__ double s_p[256];
-    __shared__ double s_w[256][NP];
-    __shared__ int s_n[256][NP];
-    __shared__ double s_red[CAV_UW];
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const int r0 = wib * CAV_ROWS;
+    constexpr int WPU = CAV_RW / ROWS;            // warps per unit
+    constexpr int SPC = 8 / WPU;                  // unit slots per CTA
+    __shared__ double vbuf[8][CAV_RW];
+    // portfolio partials live in shared memory (one 1057-double tile per unit slot), not in
+    // registers: keeping 32 more accumulators per thread starves the batch of table-row loads
+    extern __shared__ double s_tot[];             // [SPC][CAV_NOUT] when A.partials != null
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int64_t gw = (int64_t)blockIdx.x * 8 + wib;
+    const int64_t slot = gw / WPU;                 // unit slot of this warp
+    const int part = (int)(gw % WPU);              // which row block of the unit
+    const int r0 = part * ROWS;
+    const int64_t n_slots = (int64_t)gridDim.x * 8 / WPU;
+    const bool lead = (part == 0);
+    double* my_tot = s_tot + (size_t)(wib / WPU) * CAV_NOUT;
+    if (A.partials) {
+        for (int e = threadIdx.x; e < SPC * CAV_NOUT; e += 256) s_tot[e] = 0.0;
+        __syncthreads();
+    }
 
-    double tot_pv = 0.0, tot_delta = 0.0;
-    double tot_g[CAV_ROWS];
-#pragma unroll
-    for (int q = 0; q < CAV_ROWS; ++q) tot_g[q] = 0.0;
-
-    for (int64_t u = blockIdx.x; u < A.n_units; u += gridDim.x) {
+    for (int64_t u = slot; u < A.n_units; u += n_slots) {
         const int64_t t0 = A.unit_offsets[u], t1 = A.unit_offsets[u + 1];
         double pv = 0.0, delta = 0.0;
-        double acc[CAV_ROWS];
+        double acc[GAMMA ? ROWS : 1];
+        if (GAMMA) {
 #pragma unroll
-        for (int q = 0; q < CAV_ROWS; ++q) acc[q] = 0.0;
-        for (int64_t base = t0; base < t1; base += 256) {
-            const int cnt = (int)((t1 - base) < 256 ? (t1 - base) : 256);
-            __syncthreads();                       // previous chunk fully consumed
+            for (int r = 0; r < ROWS; ++r) acc[r] = 0.0;
+        }
+        for (int64_t base = t0; base < t1; base += 32) {
+            const int64_t i = base + lane;
+            const int cnt = (int)((t1 - base) < 32 ? (t1 - base) : 32);
+            double w[NP];
+            int n[NP];
             double p = 0.0;
-            if (tid < cnt) {
-                const int64_t i = base + tid;
+            if (i < t1) {
                 double ell = 0.0;
 #pragma unroll
                 for (int m = 0; m < NP; ++m) {
-                    const double w = A.weight[i * NP + m];
-                    const int n = A.node[i * NP + m];
-                    s_w[tid][m] = w;
-                    s_n[tid][m] = n;
-                    ell += w * A.L[n];
+                    w[m] = A.weight[i * NP + m];
+                    n[m] = A.node[i * NP + m];
+                    ell += w[m] * A.L[n[m]];
                 }
                 p = A.amt[i] * exp(ell);
-                s_p[tid] = p;
+            } else {
+#pragma unroll
+                for (int m = 0; m < NP; ++m) { w[m] = 0.0; n[m] = 0; }
             }
             pv += p;
-            __syncthreads();
             if (DELTA || GAMMA) {
                 for (int jj = 0; jj < cnt; ++jj) {
-                    const double pj = s_p[jj];
+                    const double pj = __shfl_sync(0xffffffffu, p, jj);
                     double wj[NP];
                     int nj[NP];
 #pragma unroll
-                    for (int m = 0; m < NP; ++m) { wj[m] = s_w[jj][m]; nj[m] = s_n[jj][m]; }
+                    for (int m = 0; m < NP; ++m) {
+                        wj[m] = __shfl_sync(0xffffffffu, w[m], jj);
+                        nj[m] = __shfl_sync(0xffffffffu, n[m], jj);
+                    }
                     const bool snapped = (NP == 2) && (wj[0] == 1.0) && (wj[1] == 0.0);
                     double v = 0.0;
 #pragma unroll
                     for (int m = 0; m < NP; ++m)
                         if (wj[m] != 0.0) v += wj[m] * __ldg(A.g + (size_t)nj[m] * CAV_RW + lane);
-                    if (DELTA && wib == 0) delta += pj * v;
+                    if (DELTA && lead) delta += pj * v;
                     if (GAMMA) {
                         if (snapped) {
                             const double* C = A.Cf + (size_t)nj[0] * CAV_RR + r0 * CAV_RW + lane;
 #pragma unroll
-                            for (int q = 0; q < CAV_ROWS; ++q) acc[q] += pj * __ldg(C + q * CAV_RW);
+                            for (int r = 0; r < ROWS; ++r) acc[r] += pj * __ldg(C + r * CAV_RW);
                         } else {
+                            __syncwarp();
+                            vbuf[wib][lane] = v;
+                            __syncwarp();
                             const double pvk = pj * v;
+                            const double2* vb = reinterpret_cast<const double2*>(vbuf[wib] + r0);
 #pragma unroll
-                            for (int q = 0; q < CAV_ROWS; ++q)
-                                acc[q] += pvk * __shfl_sync(0xffffffffu, v, r0 + q);
+                            for (int r = 0; r < ROWS; r += 2) {
+                                const double2 vv = vb[r >> 1];
+                                acc[r] += pvk * vv.x;
+                                acc[r + 1] += pvk * vv.y;
+                            }
 #pragma unroll
                             for (int m = 0; m < NP; ++m) {
                                 if (wj[m] != 0.0) {
                                     const double pw = pj * wj[m];
                                     const double* H = A.Hf + (size_t)nj[m] * CAV_RR + r0 * CAV_RW + lane;
 #pragma unroll
-                                    for (int q = 0; q < CAV_ROWS; ++q) acc[q] += pw * __ldg(H + q * CAV_RW);
+                                    for (int r = 0; r < ROWS; ++r) acc[r] += pw * __ldg(H + r * CAV_RW);
                                 }
                             }
                         }
@@ -197,47 +216,34 @@ k_units(UnitsArgs A)
                 }
             }
         }
-        // unit PV: fixed-order reduction over the CTA (lanes, then warps)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
-        __syncthreads();
-        if (lane == 0) s_red[wib] = pv;
-        __syncthreads();
-        if (wib == 0) {
-            pv = 0.0;
-#pragma unroll
-            for (int w = 0; w < CAV_UW; ++w) pv += s_red[w];
-        }
         const int64_t row = A.out_index ? A.out_index[u] : u;
-        if (wib == 0) {
+        if (lead) {
             if (A.out_pv && lane == 0) A.out_pv[row] = pv;
             if (DELTA && A.out_delta) A.out_delta[row * CAV_RW + lane] = delta;
         }
         if (GAMMA && A.out_gamma) {
             double* o = A.out_gamma + row * CAV_RR + r0 * CAV_RW + lane;
 #pragma unroll
-            for (int q = 0; q < CAV_ROWS; ++q) __stcs(o + q * CAV_RW, acc[q]);
+            for (int r = 0; r < ROWS; ++r) __stcs(o + r * CAV_RW, acc[r]);
         }
-        if (A.partials) {
+        if (A.partials) {     // each warp touches only its own rows of its slot's tile: no races
             const double W = A.unit_weight ? A.unit_weight[u] : 1.0;
-            if (wib == 0) {
-                tot_pv += W * pv;
-                if (DELTA) tot_delta += W * delta;
+            if (lead) {
+                if (lane == 0) my_tot[0] += W * pv;
+                if (DELTA) my_tot[1 + lane] += W * delta;
             }
             if (GAMMA) {
 #pragma unroll
-                for (int q = 0; q < CAV_ROWS; ++q) tot_g[q] += W * acc[q];
+                for (int r = 0; r < ROWS; ++r) my_tot[33 + (r0 + r) * CAV_RW + lane] += W * acc[r];
             }
         }
     }
     if (A.partials) {
-        double* P = A.partials + (size_t)blockIdx.x * CAV_NOUT;
-        if (wib == 0) {
-            if (lane == 0) P[0] = tot_pv;
-            P[1 + lane] = DELTA ? tot_delta : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < CAV_ROWS; ++q) P[33 + (r0 + q) * CAV_RW + lane] = GAMMA ? tot_g[q] : 0.0;
+        __syncthreads();
+        double* P = A.partials + (size_t)blockIdx.x * SPC * CAV_NOUT;
+        for (int e = threadIdx.x; e < SPC * CAV_NOUT; e += 256) P[e] = s_tot[e];
     }
 }
 
@@ -306,9 +312,11 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
                 a.x += w[k] * ga[k].x; a.y += w[k] * ga[k].y;
                 b.x += w[k] * gb[k].x; b.y += w[k] * gb[k].y;
             }
-            double2* dst = reinterpret_cast<double2*>(gamma + (size_t)row * CAV_RR);
-            __stcs(dst + tid * 2, a);
-            __stcs(dst + tid * 2 + 1, b);
+            // one 32-byte store per thread: a warp instruction covers 1 KB of the row contiguously
+            // (two 16-byte stores per thread leave 16-byte gaps per instruction and halve the rate)
+            double* dst = gamma + (size_t)row * CAV_RR + tid * 4;
+            asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                         :: "l"(dst), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
         }
         if (delta && tid < 32) {
             double sdl = 0.0;
