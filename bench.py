@@ -155,10 +155,20 @@ def main():
                     help="dedup: trades share schedule units (product default); private: one unit per trade")
     ap.add_argument("--ref-sample", type=int, default=2000)
     ap.add_argument("--cpu-sample", type=int, default=4000)
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements (private layout etc.)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--scenarios", type=int, default=2000, help="shocked curves for the config-4 extra")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+
+    # libraries (NCCL banner, warnings) must not pollute the one-line JSON contract: route fd 1 to
+    # stderr for the whole run and print the result on the saved descriptor
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        os.write(json_fd, (json.dumps(obj) + "\n").encode())
 
     import torch
     import torch.distributed as dist
@@ -285,6 +295,47 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(e2e_s.item())
 
+    # ---- secondary measurements (same book, device-resident inputs; reported under "extras") ----
+    extras = {}
+    if not args.no_extra:
+        def timed(fn, reps=10):
+            for _ in range(3):
+                fn()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(reps):
+                fn()
+            b.record(stream)
+            b.synchronize()
+            return a.elapsed_time(b) / reps
+        M_PD = _native.REQ_VALUE | _native.REQ_DELTA
+        ms = timed(lambda: ctx.portfolio_value(M_PD, pv.data_ptr(), dl.data_ptr(), None, agg.data_ptr()))
+        extras["pv_delta_config2"] = {"ms_per_step": ms, "trades_per_s_per_gpu": n / ms * 1e3,
+                                      "hbm_frac_algorithmic_1520B": n * 1520 / (ms * 1e-3) / 1e9 / measured_peak()[0]}
+        ms = timed(lambda: ctx.portfolio_value(MASK, None, None, None, agg.data_ptr()))
+        extras["portfolio_totals_only"] = {"ms_per_step": ms, "trades_per_s_per_gpu": n / ms * 1e3,
+                                           "note": "PV+delta+gamma of the portfolio, no per-trade rows written"}
+        if rank == 0:
+            from adrates_b200.synthetic import shocked_rate_scenarios
+            S = args.scenarios
+            nt = min(n, 100_000)
+            shocked = shocked_rate_scenarios(curve, S)
+            sub = flatten_book(type(book)(curve, book.schedules, book.sched[:nt], book.coupon[:nt], book.notional[:nt],
+                                         book.fixed_sign[:nt], book.spread[:nt]), dedup=True)
+            ctx2 = _native.Context(local)
+            ctx2.set_stream(stream.cuda_stream)
+            ctx2.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
+            ctx2.portfolio_upload(sub)
+            pnl = torch.empty(S, nt, dtype=torch.float64, device=dev)
+            ms = timed(lambda: ctx2.scenarios(shocked, pnl.data_ptr()), reps=3)
+            extras["scenarios_config4"] = {"scenarios": S, "trades": nt, "ms": ms, "revaluations_per_s": S * nt / ms * 1e3,
+                                           "pnl_bytes": S * nt * 8,
+                                           "note": "shocked curves re-bootstrapped on device (DFs only) + full revaluation; "
+                                                   "includes H2D of the shocked rates"}
+            del pnl
+            ctx2.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -341,8 +392,9 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "extras": extras,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
