@@ -118,8 +118,21 @@ int units_rows() {
 
 int units_ctas_per_sm(int rows) { return rows == 32 ? 2 : (rows == 4 ? 4 : 3); }
 
+bool use_tile_kernel(const cav_ctx* ctx, bool gamma) {
+    static int mode = [] { const char* e = std::getenv("CAV_UNITS_TILE"); return e ? std::atoi(e) : 1; }();
+    return gamma && ctx->n_pairs == 2 && mode != 0;
+}
+
 // returns grid size; *slots = number of persistent unit slots (= partial rows)
 int units_grid(const cav_ctx* ctx, int64_t n_units, bool gamma, int64_t* slots) {
+    if (use_tile_kernel(ctx, gamma)) {
+        const int64_t n_tiles = (n_units + CAV_TU - 1) / CAV_TU;
+        int64_t want = (n_tiles + 1) / 2;                   // 2 teams per CTA
+        int64_t cap = (int64_t)ctx->sm_count * 2;           // __launch_bounds__(256, 2)
+        int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
+        *slots = (int64_t)grid * 2;
+        return grid;
+    }
     const int rows = gamma ? units_rows() : 32;
     const int wpu = 32 / rows;
     int64_t want = (n_units * wpu + 7) / 8;
@@ -469,7 +482,11 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         a.out_gamma = gamma ? ctx->u_gamma : nullptr;
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[0], ctx->stream));
-    if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
+    if (use_tile_kernel(ctx, want_g)) {
+        const size_t smem = a.partials ? (size_t)2 * CAV_NOUT * sizeof(double) : 0;
+        k_units_tile<<<grid, 256, smem, ctx->stream>>>(a);
+        ctx->launches++;
+    } else if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
     else launch_units<6>(ctx, a, want_d, want_g, grid);
     CK(cudaGetLastError());
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[1], ctx->stream));

@@ -247,6 +247,214 @@ k_units(UnitsArgs A)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tiled units kernel (single-DF terms, full Greeks).  A *team* of 4 warps owns a tile of
+// CAV_TU consecutive units; warp `part` of the team owns gamma rows 8*part .. 8*part+7 of ALL
+// units of the tile (lane = column).  The team walks term position jj = 0, 1, 2, ... of the
+// tile's units together: when the units' terms at that position use the same bracket nodes
+// (homogeneous tiles: the flattener orders units by schedule class) the table rows Hf/Cf and
+// the g rows are loaded ONCE and applied to all CAV_TU units from registers, which divides the
+// L1/L2 traffic of the table rows - the bound of the one-unit-per-warp kernel - by CAV_TU.
+// Heterogeneous positions fall back to per-unit loads (same arithmetic).
+// ------------------------------------------------------------------------------------------
+#define CAV_TU 4
+#define CAV_TROWS 8
+__global__ void __launch_bounds__(256, 2)
+k_units_tile(UnitsArgs A)
+{
+    constexpr int TU = CAV_TU, ROWS = CAV_TROWS, WPT = CAV_RW / ROWS;   // 4 warps per team
+    constexpr int TPC = 8 / WPT;                                          // teams per CTA
+    __shared__ double vbuf[8][TU][CAV_RW];
+    __shared__ double s_p[8][TU][32];                 // per-warp staging of the current 32-term batch
+    __shared__ double2 s_w[8][TU][32];
+    __shared__ int2 s_n[8][TU][32];
+    __shared__ int s_k[8][TU][32];
+    extern __shared__ double s_tot[];                 // [TPC][CAV_NOUT] when A.partials != null
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const int team_in_cta = wib / WPT;
+    const int part = wib % WPT;
+    const int r0 = part * ROWS;
+    const bool lead = (part == 0);
+    const int64_t team = (int64_t)blockIdx.x * TPC + team_in_cta;
+    const int64_t n_teams = (int64_t)gridDim.x * TPC;
+    const int64_t n_tiles = (A.n_units + TU - 1) / TU;
+    double* my_tot = s_tot + (size_t)team_in_cta * CAV_NOUT;
+    if (A.partials) {
+        for (int e = threadIdx.x; e < TPC * CAV_NOUT; e += 256) s_tot[e] = 0.0;
+        __syncthreads();
+    }
+
+    for (int64_t tile = team; tile < n_tiles; tile += n_teams) {
+        int64_t t0[TU], t1[TU];
+        int64_t maxlen = 0;
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+            const int64_t uid = tile * TU + u;
+            t0[u] = (uid < A.n_units) ? A.unit_offsets[uid] : 0;
+            t1[u] = (uid < A.n_units) ? A.unit_offsets[uid + 1] : 0;
+            maxlen = (t1[u] - t0[u]) > maxlen ? (t1[u] - t0[u]) : maxlen;
+        }
+        double pv[TU], delta[TU], acc[TU][ROWS];
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+            pv[u] = 0.0; delta[u] = 0.0;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) acc[u][r] = 0.0;
+        }
+        for (int64_t base = 0; base < maxlen; base += 32) {
+            int cnt[TU];
+            int maxcnt = 0;
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < TU; ++u) {
+                const int64_t i = t0[u] + base + lane;
+                const int64_t left = t1[u] - t0[u] - base;
+                cnt[u] = left < 0 ? 0 : (left < 32 ? (int)left : 32);
+                maxcnt = cnt[u] > maxcnt ? cnt[u] : maxcnt;
+                double p = 0.0;
+                if (i < t1[u]) {
+                    const double2 ww = reinterpret_cast<const double2*>(A.weight)[i];
+                    const int2 nn = reinterpret_cast<const int2*>(A.node)[i];
+                    p = A.amt[i] * exp(ww.x * A.L[nn.x] + ww.y * A.L[nn.y]);
+                    s_w[wib][u][lane] = ww;
+                    s_n[wib][u][lane] = nn;
+                    s_k[wib][u][lane] = (ww.x == 1.0 && ww.y == 0.0) ? 0 : (ww.y != 0.0 ? 2 : 1);
+                }
+                s_p[wib][u][lane] = p;
+                pv[u] += p;
+            }
+            __syncwarp();
+            for (int jj = 0; jj < maxcnt; ++jj) {
+                // pass 1 (integers only): do all live units use the same rows at this position?
+                int ref = -1, r_n0 = 0, r_n1 = 0, r_kind = 0;
+                bool same = true;
+#pragma unroll
+                for (int u = 0; u < TU; ++u) {
+                    if (jj >= cnt[u]) continue;
+                    const int2 nn = s_n[wib][u][jj];
+                    const int kind = s_k[wib][u][jj];      // 0 snap, 1 one node, 2 two nodes
+                    if (ref < 0) { ref = u; r_n0 = nn.x; r_n1 = nn.y; r_kind = kind; }
+                    else if (nn.x != r_n0 || kind != r_kind || (kind == 2 && nn.y != r_n1)) same = false;
+                }
+                if (same) {
+                    // ---- shared rows: one set of loads for the whole tile ----
+                    const double g0 = __ldg(A.g + (size_t)r_n0 * CAV_RW + lane);
+                    if (r_kind == 0) {
+                        const double* C = A.Cf + (size_t)r_n0 * CAV_RR + r0 * CAV_RW + lane;
+                        double c[ROWS];
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) c[r] = __ldg(C + r * CAV_RW);
+#pragma unroll
+                        for (int u = 0; u < TU; ++u) {
+                            if (jj >= cnt[u]) continue;
+                            const double pj = s_p[wib][u][jj];
+                            if (lead) delta[u] += pj * g0;
+#pragma unroll
+                            for (int r = 0; r < ROWS; ++r) acc[u][r] += pj * c[r];
+                        }
+                    } else {
+                        const bool two = (r_kind == 2);
+                        const double g1 = two ? __ldg(A.g + (size_t)r_n1 * CAV_RW + lane) : 0.0;
+                        const double* H0 = A.Hf + (size_t)r_n0 * CAV_RR + r0 * CAV_RW + lane;
+                        const double* H1 = A.Hf + (size_t)r_n1 * CAV_RR + r0 * CAV_RW + lane;
+                        double h0[ROWS], h1[ROWS];
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) { h0[r] = __ldg(H0 + r * CAV_RW); h1[r] = two ? __ldg(H1 + r * CAV_RW) : 0.0; }
+                        __syncwarp();
+#pragma unroll
+                        for (int u = 0; u < TU; ++u) {
+                            const double2 ww = s_w[wib][u][jj];
+                            vbuf[wib][u][lane] = ww.x * g0 + ww.y * g1;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int u = 0; u < TU; ++u) {
+                            if (jj >= cnt[u]) continue;
+                            const double pj = s_p[wib][u][jj];
+                            const double2 ww = s_w[wib][u][jj];
+                            const double v = vbuf[wib][u][lane];
+                            if (lead) delta[u] += pj * v;
+                            const double pvk = pj * v, pa = pj * ww.x, pb = pj * ww.y;
+                            const double2* vb = reinterpret_cast<const double2*>(&vbuf[wib][u][r0]);
+#pragma unroll
+                            for (int r = 0; r < ROWS; r += 2) {
+                                const double2 vv = vb[r >> 1];
+                                acc[u][r] += pvk * vv.x + pa * h0[r] + pb * h1[r];
+                                acc[u][r + 1] += pvk * vv.y + pa * h0[r + 1] + pb * h1[r + 1];
+                            }
+                        }
+                    }
+                } else {
+                    // ---- heterogeneous position: per-unit rows (same arithmetic) ----
+#pragma unroll
+                    for (int u = 0; u < TU; ++u) {
+                        if (jj >= cnt[u]) continue;
+                        const double pj = s_p[wib][u][jj];
+                        const double2 ww = s_w[wib][u][jj];
+                        const int2 nn = s_n[wib][u][jj];
+                        const int kind = s_k[wib][u][jj];
+                        double v = ww.x * __ldg(A.g + (size_t)nn.x * CAV_RW + lane);
+                        if (kind == 2) v += ww.y * __ldg(A.g + (size_t)nn.y * CAV_RW + lane);
+                        if (lead) delta[u] += pj * v;
+                        if (kind == 0) {
+                            const double* C = A.Cf + (size_t)nn.x * CAV_RR + r0 * CAV_RW + lane;
+#pragma unroll
+                            for (int r = 0; r < ROWS; ++r) acc[u][r] += pj * __ldg(C + r * CAV_RW);
+                        } else {
+                            __syncwarp();
+                            vbuf[wib][u][lane] = v;
+                            __syncwarp();
+                            const double pvk = pj * v, pa = pj * ww.x, pb = pj * ww.y;
+                            const double* H0 = A.Hf + (size_t)nn.x * CAV_RR + r0 * CAV_RW + lane;
+                            const double* H1 = A.Hf + (size_t)nn.y * CAV_RR + r0 * CAV_RW + lane;
+#pragma unroll
+                            for (int r = 0; r < ROWS; ++r) {
+                                double t = pvk * vbuf[wib][u][r0 + r] + pa * __ldg(H0 + r * CAV_RW);
+                                if (kind == 2) t += pb * __ldg(H1 + r * CAV_RW);
+                                acc[u][r] += t;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // ---- write the tile ----
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+            const int64_t uid = tile * TU + u;
+            if (uid >= A.n_units) continue;
+            double s = pv[u];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const int64_t row = A.out_index ? A.out_index[uid] : uid;
+            if (lead) {
+                if (A.out_pv && lane == 0) A.out_pv[row] = s;
+                if (A.out_delta) A.out_delta[row * CAV_RW + lane] = delta[u];
+            }
+            if (A.out_gamma) {
+                double* o = A.out_gamma + row * CAV_RR + r0 * CAV_RW + lane;
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) __stcs(o + r * CAV_RW, acc[u][r]);
+            }
+            if (A.partials) {
+                const double W = A.unit_weight ? A.unit_weight[uid] : 1.0;
+                if (lead) {
+                    if (lane == 0) my_tot[0] += W * s;
+                    my_tot[1 + lane] += W * delta[u];
+                }
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) my_tot[33 + (r0 + r) * CAV_RW + lane] += W * acc[u][r];
+            }
+        }
+    }
+    if (A.partials) {
+        __syncthreads();
+        double* P = A.partials + (size_t)blockIdx.x * TPC * CAV_NOUT;
+        for (int e = threadIdx.x; e < TPC * CAV_NOUT; e += 256) P[e] = s_tot[e];
+    }
+}
+
 // totals[e] = sum_rows partials[row][e]; one warp per entry, lane-strided partial sums combined
 // in a fixed butterfly order (bitwise reproducible for a given grid)
 __global__ void __launch_bounds__(256)

@@ -80,10 +80,11 @@ def flatten_book(book: Book, dedup: bool = True, max_group: int = 256) -> FlatPo
     wA = book.fixed_sign * book.notional * book.coupon
     wF = -book.fixed_sign * book.notional
     if dedup:
-        units = []
-        for c in comps:
-            units += [_merge_single_df_terms(c[0][1]), _merge_single_df_terms(c[1][1])]
-        ids = np.stack([2 * book.sched, 2 * book.sched + 1], axis=1).astype(np.int32)
+        # unit order = all annuity units (schedule order), then all floating units: neighbouring units then
+        # bracket the same grid nodes, which the tiled units kernel exploits (shared table rows per tile)
+        S = len(comps)
+        units = [_merge_single_df_terms(c[0][1]) for c in comps] + [_merge_single_df_terms(c[1][1]) for c in comps]
+        ids = np.stack([book.sched, S + book.sched], axis=1).astype(np.int32)
         ws = np.stack([wA, wF], axis=1)
         base = assemble(book.curve, units, [[(0, 1.0)]], 1, direct=True)   # plan the unit terms once
         return group_trades(len(units), base.unit_offsets, base.n_pairs, base.amt, base.weight, base.node, ids, ws,
@@ -105,17 +106,21 @@ def flatten_book(book: Book, dedup: bool = True, max_group: int = 256) -> FlatPo
         f_vecs.append(f)
     tm = assemble(book.curve, tmpl_units, [[(0, 1.0)]], 1, direct=True)
     a_all, f_all = np.concatenate(a_vecs), np.concatenate(f_vecs)
-    cnt = np.diff(tm.unit_offsets)[book.sched]
+    # units in schedule order (neighbours bracket the same nodes); rows go back to trade order via out_index
+    order = np.argsort(book.sched, kind="stable")
+    sched_sorted = book.sched[order]
+    wA, wF = wA[order], wF[order]
+    cnt = np.diff(tm.unit_offsets)[sched_sorted]
     unit_offsets = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(cnt, out=unit_offsets[1:])
     n_terms = int(unit_offsets[-1])
-    src = np.repeat(tm.unit_offsets[:-1][book.sched] - unit_offsets[:-1], cnt) + np.arange(n_terms, dtype=np.int64)
+    src = np.repeat(tm.unit_offsets[:-1][sched_sorted] - unit_offsets[:-1], cnt) + np.arange(n_terms, dtype=np.int64)
     amt = np.repeat(wA, cnt) * a_all[src] + np.repeat(wF, cnt) * f_all[src]
     weight = tm.weight.reshape(-1, 2)[src].reshape(-1)
     node = tm.node.reshape(-1, 2)[src].reshape(-1)
     return FlatPortfolio(n, n_terms, unit_offsets, 2, amt, np.ascontiguousarray(weight), np.ascontiguousarray(node),
-                         n, 1, np.ones(n), n, np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32), None,
-                         np.ones(n))
+                         n, 1, np.ones(n), n, np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32),
+                         order.astype(np.int64), np.ones(n))
 
 
 def reference_leg_tables(book: Book):

@@ -215,3 +215,31 @@ def test_error_behaviour():
     with pytest.raises(LibError):
         ctx.portfolio_value_host(MASK)          # no curve / portfolio yet
     ctx.close()
+
+
+@pytest.mark.parametrize("dedup", [True, False])
+def test_synthetic_book_matches_c_oracle(ref_curves, dedup):
+    """3000 trades of the BASELINE config-2/3 book (homogeneous tiles: exercises the shared-row path of the
+    tiled units kernel) against the C oracle, per trade and in total."""
+    from oracle import c_oracle
+    from adrates_b200.synthetic import make_book, flatten_book, reference_leg_tables
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    book = make_book(curve, 3000, seed=11, max_offset_bd=6)      # few offsets -> many trades per schedule
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+    trades = dict(sched=book.sched, coupon=book.coupon, notional=book.notional, spread=book.spread,
+                  fixed_sign=book.fixed_sign)
+    pv_c, dl_c, gm_c = c_oracle.ois_batch((plan["times"], d, J, C), METHOD[cv["interp"]], reference_leg_tables(book),
+                                          trades, dense=False)
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    pv, dl, gm, agg = _run_flat(ctx, flatten_book(book, dedup=dedup))
+    N = book.notional
+    assert np.max(np.abs(pv - pv_c) / np.maximum(np.abs(pv_c), N)) < TOL
+    assert np.max(np.abs(dl - dl_c) / np.maximum(np.abs(dl_c), (N * 1e-4)[:, None])) < TOL
+    assert np.max(np.abs(gm.reshape(-1, 32, 32) - gm_c) / np.maximum(np.abs(gm_c), (N * 1e-8)[:, None, None])) < TOL
+    tot = np.concatenate([[pv_c.sum()], dl_c.sum(0), gm_c.sum(0).reshape(-1)])
+    scale = np.concatenate([[np.abs(pv_c).sum()], np.abs(dl_c).sum(0), np.abs(gm_c).sum(0).reshape(-1)]) + 1e-300
+    assert np.max(np.abs(agg - tot) / scale) < 1e-11
+    ctx.close()
