@@ -119,7 +119,9 @@ int units_rows() {
 int units_ctas_per_sm(int rows) { return rows == 32 ? 2 : (rows == 4 ? 4 : 3); }
 
 bool use_tile_kernel(const cav_ctx* ctx, bool gamma) {
-    static int mode = [] { const char* e = std::getenv("CAV_UNITS_TILE"); return e ? std::atoi(e) : 1; }();
+    // experimental: measured no faster than the warp-per-unit kernel on B200 (both are bound by issue slots and
+    // latency, not by table-row traffic: profiles/r01_ncu_units_tile_private.txt), so it is opt-in
+    static int mode = [] { const char* e = std::getenv("CAV_UNITS_TILE"); return e ? std::atoi(e) : 0; }();
     return gamma && ctx->n_pairs == 2 && mode != 0;
 }
 
@@ -484,6 +486,8 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[0], ctx->stream));
     if (use_tile_kernel(ctx, want_g)) {
         const size_t smem = a.partials ? (size_t)2 * CAV_NOUT * sizeof(double) : 0;
+        // static (45 KB) + dynamic shared memory exceeds the 48 KB default: opt in
+        CK(cudaFuncSetAttribute(k_units_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CAV_NOUT * (int)sizeof(double)));
         k_units_tile<<<grid, 256, smem, ctx->stream>>>(a);
         ctx->launches++;
     } else if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
