@@ -38,6 +38,7 @@ _SIGS = {
                                        C.c_int64, _P, _P, _P, _P]),
     "cav_portfolio_value": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "cav_portfolio_value_host": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
+    "cav_portfolio_delta_gemm": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "cav_scenarios": (C.c_int, [_P, _P, C.c_int, _P]),
 }
 EXPORTS = tuple(_SIGS)
@@ -169,6 +170,12 @@ class Context:
         self._ck(self._dll.cav_portfolio_value_host(self._h, mask, _ptr(pv_dev), _ptr(delta_dev), _ptr(gamma_dev),
                                                     _ptr(agg_host)))
         return agg_host
+
+    def portfolio_delta_gemm(self, pv_dev, delta_dev):
+        """PV + delta with the chain rule as a DMMA GEMM; returns (gemm_ms, gemm_flops)."""
+        ms, fl = C.c_float(), C.c_double()
+        self._ck(self._dll.cav_portfolio_delta_gemm(self._h, _ptr(pv_dev), _ptr(delta_dev), C.byref(ms), C.byref(fl)))
+        return float(ms.value), float(fl.value)
 
     def scenarios(self, shocked_rates, pnl_dev):
         r = _f64(shocked_rates)

@@ -52,8 +52,11 @@ struct cav_ctx {
     double* comp_weight = nullptr;
     int64_t* group_offsets = nullptr;
     int* group_units = nullptr;
-    int* trade_units = nullptr;
-    bool trade_units_valid = false;
+    int* row_units = nullptr;
+    double* row_weight = nullptr;
+    bool row_tables_valid = false;
+    double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
+    double *sc_rates = nullptr, *sc_P = nullptr, *sc_L = nullptr, *sc_upv = nullptr;   // scenario scratch (grow-only)
     int64_t* out_index = nullptr;
     double* unit_weight = nullptr;
 
@@ -212,7 +215,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
-    dev_free(ctx, &ctx->trade_units); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
+    dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
     cudaEventDestroy(ctx->ev0);
@@ -439,7 +442,7 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     CK(cudaStreamSynchronize(ctx->stream));   // host buffers may be reused by the caller
     ctx->n_units = n_units; ctx->n_terms = n_terms; ctx->n_trades = n_trades; ctx->n_groups = n_groups;
     ctx->n_pairs = n_pairs; ctx->n_comp = n_comp; ctx->direct = direct;
-    ctx->trade_units_valid = false;
+    ctx->row_tables_valid = false;
     return CAV_OK;
 }
 
@@ -528,6 +531,54 @@ int cav_portfolio_value_host(cav_ctx* ctx, uint32_t request_mask, double* pv_dev
     return value_impl(ctx, request_mask, pv_dev, delta_dev, gamma_dev, nullptr, agg_host);
 }
 
+// ---------------------------------------------------------------------------- chain GEMM
+int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, float* gemm_ms, double* gemm_flops) {
+    if (!ctx) return CAV_E_INVALID;
+    if (ctx->order < 1) return fail(ctx, CAV_E_STATE, "cav_portfolio_delta_gemm: curve with jacobian first");
+    if (!ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_portfolio_delta_gemm: no portfolio uploaded");
+    if (!delta_dev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_delta_gemm: delta_dev is null");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_units == 0) return CAV_OK;
+    const int Gp = (ctx->G + 3) & ~3;
+    CK(dev_alloc(ctx, &ctx->Qmat, (size_t)ctx->n_units * Gp));
+    double* u_delta = delta_dev;
+    double* u_pv = pv_dev;
+    if (!ctx->direct) {
+        CK(dev_alloc(ctx, &ctx->u_pv, (size_t)ctx->n_units));
+        CK(dev_alloc(ctx, &ctx->u_delta, (size_t)ctx->n_units * CAV_RW));
+        u_delta = ctx->u_delta;
+        u_pv = ctx->u_pv;
+    } else if (ctx->out_index) {
+        return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_delta_gemm: private layout must be in output order");
+    }
+    const unsigned gb = (unsigned)((ctx->n_units + 7) / 8);
+    if (ctx->n_pairs == 2)
+        k_node_grad<2><<<gb, 256, 0, ctx->stream>>>(ctx->n_units, Gp, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->L, ctx->Qmat, u_pv);
+    else
+        k_node_grad<6><<<gb, 256, 0, ctx->stream>>>(ctx->n_units, Gp, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->L, ctx->Qmat, u_pv);
+    const size_t smem = (size_t)CAV_GEMM_KC * CAV_GEMM_LD * sizeof(double);
+    CK(cudaFuncSetAttribute(k_chain_gemm_dmma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaEventRecord(ctx->evk[0], ctx->stream));
+    k_chain_gemm_dmma<<<(unsigned)((ctx->n_units + 127) / 128), 256, smem, ctx->stream>>>(ctx->n_units, Gp, ctx->Qmat, ctx->g,
+                                                                                      ctx->G, u_delta);
+    CK(cudaEventRecord(ctx->evk[1], ctx->stream));
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    if (!ctx->direct && ctx->n_groups > 0) {
+        switch (ctx->n_comp) {
+            case 1: launch_expand<1>(ctx, pv_dev, delta_dev, nullptr); break;
+            case 2: launch_expand<2>(ctx, pv_dev, delta_dev, nullptr); break;
+            case 3: launch_expand<3>(ctx, pv_dev, delta_dev, nullptr); break;
+            default: launch_expand<4>(ctx, pv_dev, delta_dev, nullptr); break;
+        }
+        CK(cudaGetLastError());
+    }
+    CK(cudaEventSynchronize(ctx->evk[1]));
+    if (gemm_ms) CK(cudaEventElapsedTime(gemm_ms, ctx->evk[0], ctx->evk[1]));
+    if (gemm_flops) *gemm_flops = 2.0 * (double)ctx->n_units * Gp * CAV_RW;
+    return CAV_OK;
+}
+
 // ---------------------------------------------------------------------------- scenarios
 int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev) {
     if (!ctx) return CAV_E_INVALID;
@@ -535,41 +586,39 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
     if (ctx->order < 0 || !ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_scenarios: curve and portfolio first");
     CK(cudaSetDevice(ctx->device));
     const size_t S = (size_t)n_scen, G = (size_t)ctx->G;
-    double *rates = nullptr, *Pbuf = nullptr, *Ls = nullptr, *upv = nullptr;
-    cudaError_t e = upload(ctx, &rates, shocked_rates, S * ctx->R);
-    if (e == cudaSuccess) e = dev_alloc(ctx, &Pbuf, G * S);
-    if (e == cudaSuccess) e = dev_alloc(ctx, &Ls, G * S);
-    if (e == cudaSuccess) e = dev_alloc(ctx, &upv, (size_t)ctx->n_units * S);
-    if (e == cudaSuccess && !ctx->trade_units_valid) {
-        e = dev_alloc(ctx, &ctx->trade_units, (size_t)ctx->n_trades * ctx->n_comp);
-        if (e == cudaSuccess && ctx->n_groups > 0) {
-            k_trade_units<<<(unsigned)((ctx->n_groups + 127) / 128), 128, 0, ctx->stream>>>(
-                ctx->n_groups, ctx->n_comp, ctx->group_offsets, ctx->group_units, ctx->trade_units);
+    CK(upload(ctx, &ctx->sc_rates, shocked_rates, S * ctx->R));
+    CK(dev_alloc(ctx, &ctx->sc_P, G * S));
+    CK(dev_alloc(ctx, &ctx->sc_L, G * S));
+    CK(dev_alloc(ctx, &ctx->sc_upv, (size_t)ctx->n_units * S));
+    if (!ctx->row_tables_valid) {
+        CK(dev_alloc(ctx, &ctx->row_units, (size_t)ctx->n_trades * ctx->n_comp));
+        CK(dev_alloc(ctx, &ctx->row_weight, (size_t)ctx->n_trades * ctx->n_comp));
+        if (ctx->n_groups > 0) {
+            k_row_tables<<<(unsigned)((ctx->n_groups + 127) / 128), 128, 0, ctx->stream>>>(
+                ctx->n_groups, ctx->n_comp, ctx->group_offsets, ctx->group_units, ctx->comp_weight, ctx->out_index,
+                ctx->row_units, ctx->row_weight);
             ctx->launches++;
-            ctx->trade_units_valid = true;
         }
+        ctx->row_tables_valid = true;
     }
-    if (e == cudaSuccess) {
-        k_scen_bootstrap<<<(n_scen + 127) / 128, 128, 0, ctx->stream>>>(ctx->G, ctx->R, n_scen, rates, ctx->node_acc,
-                                                                      ctx->node_swap, ctx->node_prev, Pbuf, Ls);
-        dim3 gu((unsigned)ctx->n_units, (unsigned)((n_scen + 127) / 128));
-        if (ctx->n_pairs == 2)
-            k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, Ls, upv);
-        else
-            k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, Ls, upv);
-        dim3 ge((unsigned)((ctx->n_trades + 31) / 32), (unsigned)((n_scen + 31) / 32));
-        switch (ctx->n_comp) {
-            case 1: k_scen_expand<1><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
-            case 2: k_scen_expand<2><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
-            case 3: k_scen_expand<3><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
-            default: k_scen_expand<4><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->trade_units, ctx->comp_weight, ctx->out_index, upv, pnl_dev); break;
-        }
-        ctx->launches += 3;
-        e = cudaGetLastError();
+    if (ctx->n_units == 0 || ctx->n_trades == 0) return CAV_OK;
+    k_scen_bootstrap<<<(n_scen + 127) / 128, 128, 0, ctx->stream>>>(ctx->G, ctx->R, n_scen, ctx->sc_rates, ctx->node_acc,
+                                                                  ctx->node_swap, ctx->node_prev, ctx->sc_P, ctx->sc_L);
+    dim3 gu((unsigned)ctx->n_units, (unsigned)((n_scen + 127) / 128));
+    if (ctx->n_pairs == 2)
+        k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
+    else
+        k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
+    dim3 ge((unsigned)((ctx->n_trades + 31) / 32), (unsigned)((n_scen + 31) / 32));
+    switch (ctx->n_comp) {
+        case 1: k_scen_expand<1><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+        case 2: k_scen_expand<2><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+        case 3: k_scen_expand<3><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+        default: k_scen_expand<4><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    dev_free(ctx, &rates); dev_free(ctx, &Pbuf); dev_free(ctx, &Ls); dev_free(ctx, &upv);
-    if (e != cudaSuccess) return fail(ctx, CAV_E_CUDA, std::string("cav_scenarios: ") + cudaGetErrorString(e));
+    ctx->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));   // shocked_rates (host) may be reused by the caller
     return CAV_OK;
 }
 

@@ -542,6 +542,96 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
 }
 
 // ------------------------------------------------------------------------------------------
+// Chain rule as a batched FP64 tensor-core GEMM (the reference's `jnp.dot(grad_dfs, jac)`,
+// engine.py:2554/2912, for all units at once):
+//     delta[U][32] = Q[U][Gp] * g[Gp][32],   Q[u][n] = dPV_u / d ln d_n = sum_terms p * w
+// k_node_grad builds the dense node-gradient rows, k_chain_gemm_dmma contracts them with the
+// (1e-4-scaled) log-DF Jacobian using mma.sync.m8n8k4.f64 (DMMA; there is no FP64 tcgen05 kind).
+// This is the dense formulation (2*Gp*32 flops per unit, 2.6x the sparse per-cashflow chain of
+// k_units) and is kept as a measured alternative, not the default path.
+// ------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256)
+k_node_grad(int64_t n_units, int Gp, const int64_t* __restrict__ unit_offsets, const double* __restrict__ amt,
+            const double* __restrict__ weight, const int* __restrict__ node, const double* __restrict__ L,
+            double* Q, double* unit_pv)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t u = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (u >= n_units) return;
+    double* q = Q + (size_t)u * Gp;
+    for (int n = lane; n < Gp; n += 32) q[n] = 0.0;
+    __syncwarp();
+    double pv = 0.0;
+    for (int64_t i = unit_offsets[u] + lane; i < unit_offsets[u + 1]; i += 32) {
+        double ell = 0.0, w[NP];
+        int nn[NP];
+#pragma unroll
+        for (int m = 0; m < NP; ++m) { w[m] = weight[i * NP + m]; nn[m] = node[i * NP + m]; ell += w[m] * L[nn[m]]; }
+        const double p = amt[i] * exp(ell);
+        pv += p;
+#pragma unroll
+        for (int m = 0; m < NP; ++m)
+            if (w[m] != 0.0) atomicAdd(q + nn[m], p * w[m]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+    if (lane == 0 && unit_pv) unit_pv[u] = pv;
+}
+
+#define CAV_GEMM_KC 256          // nodes staged per shared-memory chunk
+#define CAV_GEMM_LD 36           // padded row stride of the staged g chunk (conflict-free B fragments)
+__global__ void __launch_bounds__(256)
+k_chain_gemm_dmma(int64_t n_units, int Gp, const double* __restrict__ Q, const double* __restrict__ g, int G,
+                  double* delta)
+{
+    extern __shared__ double s_g[];                     // [KC][LD]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t u0 = ((int64_t)blockIdx.x * 8 + wib) * 16;     // 16 units per warp (two m8 tiles)
+    const int ar = lane >> 2, ac = lane & 3;             // fragment coordinates
+    double c[2][4][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < 4; ++n) c[m][n][0] = c[m][n][1] = 0.0;
+    const int64_t ua = u0 + ar, ub = u0 + 8 + ar;
+    const double* qa = Q + (size_t)(ua < n_units ? ua : 0) * Gp;
+    const double* qb = Q + (size_t)(ub < n_units ? ub : 0) * Gp;
+    for (int k0 = 0; k0 < Gp; k0 += CAV_GEMM_KC) {
+        const int kc = (Gp - k0) < CAV_GEMM_KC ? (Gp - k0) : CAV_GEMM_KC;
+        __syncthreads();
+        for (int e = threadIdx.x; e < kc * 32; e += 256) {
+            const int r = e >> 5, col = e & 31;
+            s_g[r * CAV_GEMM_LD + col] = (k0 + r < G) ? g[(size_t)(k0 + r) * 32 + col] : 0.0;
+        }
+        __syncthreads();
+        if (u0 < n_units) {
+            for (int k = 0; k < kc; k += 4) {
+                const double a0 = (ua < n_units) ? __ldg(qa + k0 + k + ac) : 0.0;
+                const double a1 = (ub < n_units) ? __ldg(qb + k0 + k + ac) : 0.0;
+#pragma unroll
+                for (int n = 0; n < 4; ++n) {
+                    const double b = s_g[(k + ac) * CAV_GEMM_LD + n * 8 + ar];
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(b));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1), "d"(b));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int64_t u = u0 + m * 8 + ar;
+        if (u < n_units) {
+#pragma unroll
+            for (int n = 0; n < 4; ++n)
+                *reinterpret_cast<double2*>(delta + (size_t)u * 32 + n * 8 + 2 * ac) = make_double2(c[m][n][0], c[m][n][1]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // df_ad: fwd_k = -ln(d_{k+1}/d_k)/(x_{k+1}-x_k); f = interp(t, x[:-1], fwd);
 //        i0 = searchsorted(x, t, 'right') - 1; DF = d[i0] exp(-f (t - x[i0]))
 // ------------------------------------------------------------------------------------------
@@ -596,14 +686,21 @@ __global__ void k_scen_bootstrap(int G, int R, int n_scen, const double* __restr
     }
 }
 
-// per-trade unit ids from the group table (one thread per group)
-__global__ void k_trade_units(int64_t n_groups, int K, const int64_t* __restrict__ group_offsets,
-                              const int* __restrict__ group_units, int* trade_units)
+// unit ids and weights per OUTPUT ROW (original trade order) from the group table, so that the
+// scenario expansion writes the P&L matrix with fully coalesced rows (one thread per group)
+__global__ void k_row_tables(int64_t n_groups, int K, const int64_t* __restrict__ group_offsets,
+                             const int* __restrict__ group_units, const double* __restrict__ comp_weight,
+                             const int64_t* __restrict__ out_index, int* row_units, double* row_weight)
 {
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gi >= n_groups) return;
-    for (int64_t t = group_offsets[gi]; t < group_offsets[gi + 1]; ++t)
-        for (int k = 0; k < K; ++k) trade_units[t * K + k] = group_units[gi * K + k];
+    for (int64_t t = group_offsets[gi]; t < group_offsets[gi + 1]; ++t) {
+        const int64_t row = out_index ? out_index[t] : t;
+        for (int k = 0; k < K; ++k) {
+            row_units[row * K + k] = group_units[gi * K + k];
+            row_weight[row * K + k] = comp_weight[t * K + k];
+        }
+    }
 }
 
 // unit_pv[u][s]: block = 128 scenarios (threads) x loop over the unit's terms; grid (units, scen tiles)
@@ -630,39 +727,34 @@ k_scen_units(int n_scen, const int64_t* __restrict__ unit_offsets, const double*
     unit_pv[u * n_scen + s] = pv;
 }
 
-// pnl[s][row(t)] = sum_k w_tk unit_pv[u_k][s]; block handles 32 scenarios x 32 trades tile via smem transpose
+// pnl[s][row] = sum_k w_row,k unit_pv[u_row,k][s]; a 32x32 (rows x scenarios) tile is read with the
+// scenario index fastest (256-byte runs of unit_pv) and written transposed with the row index fastest
 template <int K>
 __global__ void __launch_bounds__(256)
-k_scen_expand(int n_scen, int64_t n_trades, const int* __restrict__ trade_units /*[T][K]*/,
-              const double* __restrict__ comp_weight, const int64_t* __restrict__ out_index,
-              const double* __restrict__ unit_pv, double* pnl)
+k_scen_expand(int n_scen, int64_t n_trades, const int* __restrict__ row_units /*[N][K]*/,
+              const double* __restrict__ row_weight, const double* __restrict__ unit_pv, double* pnl)
 {
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-    const int64_t tbase = (int64_t)blockIdx.x * 32;
+    const int64_t rbase = (int64_t)blockIdx.x * 32;
     const int sbase = blockIdx.y * 32;
-    // load: rows = trades (ty..), cols = scenarios (tx) -> coalesced reads of unit_pv[u][s]
     for (int r = ty; r < 32; r += 8) {
-        const int64_t t = tbase + r;
-        const int s = sbase + tx;
+        const int64_t row = rbase + r;
+        const int sc = sbase + tx;
         double v = 0.0;
-        if (t < n_trades && s < n_scen) {
+        if (row < n_trades && sc < n_scen) {
 #pragma unroll
             for (int k = 0; k < K; ++k) {
-                const double w = comp_weight[t * K + k];
-                if (w != 0.0) v += w * unit_pv[(size_t)trade_units[t * K + k] * n_scen + s];
+                const double w = row_weight[row * K + k];
+                if (w != 0.0) v += w * unit_pv[(size_t)row_units[row * K + k] * n_scen + sc];
             }
         }
         tile[r][tx] = v;
     }
     __syncthreads();
-    // store: rows = scenarios, cols = trades (tx) -> coalesced when out_index is near-identity
     for (int r = ty; r < 32; r += 8) {
-        const int s = sbase + r;
-        const int64_t t = tbase + tx;
-        if (t < n_trades && s < n_scen) {
-            const int64_t row = out_index ? out_index[t] : t;
-            pnl[(size_t)s * n_trades + row] = tile[tx][r];
-        }
+        const int sc = sbase + r;
+        const int64_t row = rbase + tx;
+        if (row < n_trades && sc < n_scen) __stcs(pnl + (size_t)sc * n_trades + row, tile[tx][r]);
     }
 }

@@ -67,7 +67,7 @@ def make_book(curve: OISCurve, n_trades: int, seed: int = 20240430, max_offset_b
     return Book(curve, schedules, sched.astype(np.int32), coupon, notional, fixed_sign, np.zeros(n_trades))
 
 
-def flatten_book(book: Book, dedup: bool = True, max_group: int = 256) -> FlatPortfolio:
+def flatten_book(book: Book, dedup: bool = True, max_group: int = 256, sort_units: bool = True) -> FlatPortfolio:
     vd = book.curve._value_dt
     comps = [ois_components(s, vd) for s in book.schedules]   # unit-notional, unit-coupon, PAY fixed
     for c in comps:
@@ -107,7 +107,7 @@ def flatten_book(book: Book, dedup: bool = True, max_group: int = 256) -> FlatPo
     tm = assemble(book.curve, tmpl_units, [[(0, 1.0)]], 1, direct=True)
     a_all, f_all = np.concatenate(a_vecs), np.concatenate(f_vecs)
     # units in schedule order (neighbours bracket the same nodes); rows go back to trade order via out_index
-    order = np.argsort(book.sched, kind="stable")
+    order = np.argsort(book.sched, kind="stable") if sort_units else np.arange(n)
     sched_sorted = book.sched[order]
     wA, wF = wA[order], wF[order]
     cnt = np.diff(tm.unit_offsets)[sched_sorted]
@@ -120,7 +120,7 @@ def flatten_book(book: Book, dedup: bool = True, max_group: int = 256) -> FlatPo
     node = tm.node.reshape(-1, 2)[src].reshape(-1)
     return FlatPortfolio(n, n_terms, unit_offsets, 2, amt, np.ascontiguousarray(weight), np.ascontiguousarray(node),
                          n, 1, np.ones(n), n, np.arange(n + 1, dtype=np.int64), np.arange(n, dtype=np.int32),
-                         order.astype(np.int64), np.ones(n))
+                         order.astype(np.int64) if sort_units else None, np.ones(n))
 
 
 def reference_leg_tables(book: Book):

@@ -123,6 +123,15 @@ int cav_portfolio_value(cav_ctx* ctx, uint32_t request_mask,
 int cav_portfolio_value_host(cav_ctx* ctx, uint32_t request_mask,
                              double* pv_dev, double* delta_dev, double* gamma_dev, double* agg_host);
 
+/* ---- chain rule as a batched FP64 tensor-core GEMM -----------------------------------
+ * Alternative delta path: replaces `jnp.dot(grad_dfs, jac) * 1e-4` (engine.py:2554-2555,
+ * 2912-2913) for the whole book with delta[U][32] = Q[U][G] * (1e-4 J/d)[G][32] on the FP64
+ * tensor pipe (mma.sync m8n8k4).  Writes per-trade pv[n_trades] (may be NULL) and
+ * delta[n_trades][32]; returns the GEMM kernel's CUDA-event time and its flop count so the
+ * caller can report tensor-pipe utilisation.  Private layouts must be uploaded in output
+ * order (out_index == NULL). */
+int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, float* gemm_ms, double* gemm_flops);
+
 /* ---- scenarios: replaces Model.scenario + rebuild + Position.compute([VALUE]) ------
  * (cavour/models/models.py:507-557, engine.py:2337-2349).  Each row of shocked_rates is a
  * full par-rate vector; every curve is re-bootstrapped (DFs only) and every trade

@@ -243,3 +243,25 @@ def test_synthetic_book_matches_c_oracle(ref_curves, dedup):
     scale = np.concatenate([[np.abs(pv_c).sum()], np.abs(dl_c).sum(0), np.abs(gm_c).sum(0).reshape(-1)]) + 1e-300
     assert np.max(np.abs(agg - tot) / scale) < 1e-11
     ctx.close()
+
+
+def test_delta_chain_gemm_matches_fused_path(ref_curves):
+    """The DMMA chain-rule GEMM (delta = Q * 1e-4 J/d) against the fused per-cashflow chain, both layouts."""
+    from adrates_b200.synthetic import make_book, flatten_book
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    book = make_book(curve, 2500, seed=3)
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    for flat in (flatten_book(book, dedup=True), flatten_book(book, dedup=False, sort_units=False)):
+        pv, dl, gm, agg = _run_flat(ctx, flat, _native.REQ_VALUE | _native.REQ_DELTA)
+        pv2 = torch.zeros(flat.n_trades, dtype=torch.float64, device="cuda")
+        dl2 = torch.zeros(flat.n_trades, 32, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        ms, flops = ctx.portfolio_delta_gemm(pv2.data_ptr(), dl2.data_ptr())
+        ctx.sync()
+        N = book.notional
+        assert flops == 2.0 * flat.n_units * 264 * 32 and ms > 0
+        assert np.max(np.abs(pv2.cpu().numpy() - pv) / np.maximum(np.abs(pv), N)) < TOL
+        assert np.max(np.abs(dl2.cpu().numpy() - dl) / np.maximum(np.abs(dl), (N * 1e-4)[:, None])) < TOL
+    ctx.close()

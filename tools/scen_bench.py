@@ -1,0 +1,28 @@
+"""Scenario revaluation timing (BASELINE config 4 slice): S shocked curves x T trades on one GPU."""
+import argparse, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from adrates_b200 import _native
+from adrates_b200.synthetic import make_book, flatten_book, shocked_rate_scenarios
+from bench import load_curve
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--scen", type=int, default=2000)
+ap.add_argument("--trades", type=int, default=100000)
+ap.add_argument("--reps", type=int, default=3)
+a = ap.parse_args()
+cv, curve = load_curve()
+book = make_book(curve, a.trades, seed=7)
+flat = flatten_book(book, dedup=True)
+ctx = _native.Context(0)
+ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
+ctx.portfolio_upload(flat)
+shocked = shocked_rate_scenarios(curve, a.scen)
+pnl = torch.empty(a.scen, a.trades, dtype=torch.float64, device="cuda")
+torch.cuda.synchronize()
+for r in range(a.reps):
+    t0 = time.perf_counter()
+    ctx.scenarios(shocked, pnl.data_ptr())
+    ctx.sync()
+    dt = time.perf_counter() - t0
+    print(f"rep {r}: {dt*1e3:.2f} ms  {a.scen*a.trades/dt/1e9:.2f} G revaluations/s  units={flat.n_units} terms={flat.n_terms}")
