@@ -539,7 +539,7 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
     if (!delta_dev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_delta_gemm: delta_dev is null");
     CK(cudaSetDevice(ctx->device));
     if (ctx->n_units == 0) return CAV_OK;
-    const int Gp = (ctx->G + 3) & ~3;
+    const int Gp = (ctx->G + 15) & ~15;        // row stride of Q: multiple of 16 nodes (32-byte A loads x 4 k-steps)
     CK(dev_alloc(ctx, &ctx->Qmat, (size_t)ctx->n_units * Gp));
     double* u_delta = delta_dev;
     double* u_pv = pv_dev;

@@ -579,8 +579,12 @@ k_node_grad(int64_t n_units, int Gp, const int64_t* __restrict__ unit_offsets, c
     if (lane == 0 && unit_pv) unit_pv[u] = pv;
 }
 
-#define CAV_GEMM_KC 256          // nodes staged per shared-memory chunk
-#define CAV_GEMM_LD 36           // padded row stride of the staged g chunk (conflict-free B fragments)
+#define CAV_GEMM_KC 256          // nodes staged per shared-memory chunk (multiple of 16)
+#define CAV_GEMM_LD 33           // padded row stride of the staged g chunk (conflict-free B fragments)
+// Each lane fetches its A operands with one 32-byte load per 16 nodes: lane (ar, ac) reads
+// Q[unit ar][16t + 4ac .. 4ac+3], a full 128-byte line per unit row per warp instruction.  The
+// K index of MMA step s is therefore the permuted node 16t + 4ac + s, and the B fragment is read
+// from the same permuted row, so the product is unchanged.  Gp (row stride of Q) is a multiple of 16.
 __global__ void __launch_bounds__(256)
 k_chain_gemm_dmma(int64_t n_units, int Gp, const double* __restrict__ Q, const double* __restrict__ g, int G,
                   double* delta)
@@ -595,8 +599,9 @@ k_chain_gemm_dmma(int64_t n_units, int Gp, const double* __restrict__ Q, const d
 #pragma unroll
         for (int n = 0; n < 4; ++n) c[m][n][0] = c[m][n][1] = 0.0;
     const int64_t ua = u0 + ar, ub = u0 + 8 + ar;
-    const double* qa = Q + (size_t)(ua < n_units ? ua : 0) * Gp;
-    const double* qb = Q + (size_t)(ub < n_units ? ub : 0) * Gp;
+    const bool va = ua < n_units, vb = ub < n_units;
+    const double* qa = Q + (size_t)(va ? ua : 0) * Gp + 4 * ac;
+    const double* qb = Q + (size_t)(vb ? ub : 0) * Gp + 4 * ac;
     for (int k0 = 0; k0 < Gp; k0 += CAV_GEMM_KC) {
         const int kc = (Gp - k0) < CAV_GEMM_KC ? (Gp - k0) : CAV_GEMM_KC;
         __syncthreads();
@@ -606,16 +611,24 @@ k_chain_gemm_dmma(int64_t n_units, int Gp, const double* __restrict__ Q, const d
         }
         __syncthreads();
         if (u0 < n_units) {
-            for (int k = 0; k < kc; k += 4) {
-                const double a0 = (ua < n_units) ? __ldg(qa + k0 + k + ac) : 0.0;
-                const double a1 = (ub < n_units) ? __ldg(qb + k0 + k + ac) : 0.0;
+#pragma unroll 2
+            for (int k = 0; k < kc; k += 16) {
+                double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+                if (va) asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                     : "=d"(a0[0]), "=d"(a0[1]), "=d"(a0[2]), "=d"(a0[3]) : "l"(qa + k0 + k));
+                if (vb) asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                     : "=d"(a1[0]), "=d"(a1[1]), "=d"(a1[2]), "=d"(a1[3]) : "l"(qb + k0 + k));
 #pragma unroll
-                for (int n = 0; n < 4; ++n) {
-                    const double b = s_g[(k + ac) * CAV_GEMM_LD + n * 8 + ar];
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                 : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(b));
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                 : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1), "d"(b));
+                for (int st = 0; st < 4; ++st) {
+                    const double* brow = s_g + (k + 4 * ac + st) * CAV_GEMM_LD + ar;
+#pragma unroll
+                    for (int n = 0; n < 4; ++n) {
+                        const double b = brow[n * 8];
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0[st]), "d"(b));
+                        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                     : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1[st]), "d"(b));
+                    }
                 }
             }
         }
