@@ -11,14 +11,15 @@ from .dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRul
 from .global_types import (SwapTypes, InstrumentTypes, RequestTypes, InterpTypes, CurveTypes,
                            CurrencyTypes, CollateralType)
 
-from .trades import OIS, SwapFixedLeg, SwapFloatLeg
+from .trades import OIS, SwapFixedLeg, SwapFloatLeg, XccyBasisSwap
+from .xccy_curve import XccyCurve
 from .curves import OISCurve, DiscountCurve
 from .models import Model
 from .position import Position, Portfolio, Engine
 from .results import Valuation, Delta, Gamma, Risk, AnalyticsResult
 
 __all__ = [
-    "OIS", "SwapFixedLeg", "SwapFloatLeg", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
+    "OIS", "SwapFixedLeg", "SwapFloatLeg", "XccyBasisSwap", "XccyCurve", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
     "Valuation", "Delta", "Gamma", "Risk", "AnalyticsResult",
     "LibError", "Date", "Calendar", "CalendarTypes", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
     "DayCountTypes", "FrequencyTypes", "Schedule", "to_tenor", "times_from_dates", "SwapTypes",

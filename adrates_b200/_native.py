@@ -33,6 +33,7 @@ _SIGS = {
     "cav_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cav_curve_build": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "cav_curve_read": (C.c_int, [_P, _P, _P, _P]),
+    "cav_curve_set_tables": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
     "cav_df_ad": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_portfolio_upload": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P,
                                        C.c_int64, _P, _P, _P, _P]),
@@ -136,6 +137,14 @@ class Context:
         self._ck(self._dll.cav_curve_build(self._h, int(interp_method), _ptr(r), r.shape[0], _ptr(t), _ptr(a),
                                            _ptr(s), _ptr(p), t.shape[0], int(order)))
         self._G, self._R = t.shape[0], r.shape[0]
+
+    def curve_set_tables(self, dfs, jac=None, hess=None):
+        d = _f64(dfs)
+        J = None if jac is None else _f64(jac)
+        H = None if hess is None else _f64(hess)
+        R = 1 if J is None else J.shape[1]
+        self._ck(self._dll.cav_curve_set_tables(self._h, _ptr(d), _ptr(J), _ptr(H), d.shape[0], R))
+        self._G, self._R = d.shape[0], R
 
     def curve_read(self, jac=True, hess=True):
         G, R = self._G, self._R

@@ -37,6 +37,7 @@ struct cav_ctx {
 
     // curve
     int G = 0, R = 0, interp = 0, order = -1;
+    bool has_plan = false;     // bootstrap plan present (needed by cav_scenarios)
     double *rates = nullptr, *node_time = nullptr, *node_acc = nullptr;
     int *node_swap = nullptr, *node_prev = nullptr;
     double *df = nullptr, *P = nullptr, *jac = nullptr, *dP = nullptr, *hess = nullptr, *d2P = nullptr;
@@ -327,6 +328,47 @@ int cav_curve_build(cav_ctx* ctx, int interp_method, const double* swap_rates, i
     ctx->R = n_rates;
     ctx->interp = interp_method;
     ctx->order = order;
+    ctx->has_plan = true;
+    return CAV_OK;
+}
+
+int cav_curve_set_tables(cav_ctx* ctx, const double* dfs, const double* jac, const double* hess, int n_nodes,
+                         int n_rates) {
+    if (!ctx) return CAV_E_INVALID;
+    if (!dfs || n_nodes < 1 || n_rates < 1 || (hess && !jac))
+        return fail(ctx, CAV_E_INVALID, "cav_curve_set_tables: null pointer or bad size");
+    if (n_rates > CAV_R) return fail(ctx, CAV_E_UNSUPPORTED, "cav_curve_set_tables: more than 32 pillars");
+    for (int i = 0; i < n_nodes; ++i)
+        if (!(dfs[i] > 0.0)) return fail(ctx, CAV_E_INVALID, "cav_curve_set_tables: discount factors must be positive");
+    CK(cudaSetDevice(ctx->device));
+    const size_t G = (size_t)n_nodes;
+    const int order = hess ? 2 : (jac ? 1 : 0);
+    std::vector<double> J, H;
+    if (jac) {
+        J.assign(G * CAV_RW, 0.0);
+        for (size_t i = 0; i < G; ++i)
+            for (int k = 0; k < n_rates; ++k) J[i * CAV_RW + k] = jac[i * n_rates + k];
+    }
+    if (hess) {
+        H.assign(G * CAV_RR, 0.0);
+        for (size_t i = 0; i < G; ++i)
+            for (int j = 0; j < n_rates; ++j)
+                for (int k = 0; k < n_rates; ++k) H[i * CAV_RR + j * CAV_RW + k] = hess[(i * n_rates + j) * n_rates + k];
+    }
+    CK(upload(ctx, &ctx->df, dfs, G));
+    CK(dev_alloc(ctx, &ctx->L, G));
+    if (jac) { CK(upload(ctx, &ctx->jac, J.data(), J.size())); CK(dev_alloc(ctx, &ctx->g, G * CAV_RW)); }
+    if (hess) {
+        CK(upload(ctx, &ctx->hess, H.data(), H.size()));
+        CK(dev_alloc(ctx, &ctx->Hf, G * CAV_RR));
+        CK(dev_alloc(ctx, &ctx->Cf, G * CAV_RR));
+    }
+    k_tables<<<n_nodes, 1024, 0, ctx->stream>>>(order, ctx->df, ctx->jac, ctx->hess, ctx->L, ctx->g, ctx->Hf, ctx->Cf);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->G = n_nodes; ctx->R = n_rates; ctx->order = order; ctx->interp = 0;
+    ctx->has_plan = false;
     return CAV_OK;
 }
 
@@ -584,6 +626,7 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
     if (!ctx) return CAV_E_INVALID;
     if (!shocked_rates || n_scen < 1 || !pnl_dev) return fail(ctx, CAV_E_INVALID, "cav_scenarios: bad arguments");
     if (ctx->order < 0 || !ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_scenarios: curve and portfolio first");
+    if (!ctx->has_plan) return fail(ctx, CAV_E_STATE, "cav_scenarios: the curve was set from tables, there is no bootstrap plan");
     CK(cudaSetDevice(ctx->device));
     const size_t S = (size_t)n_scen, G = (size_t)ctx->G;
     CK(upload(ctx, &ctx->sc_rates, shocked_rates, S * ctx->R));

@@ -67,8 +67,44 @@ class Model:
             self._fx_params_dict[pair] = {"base": base, "quote": quote, "ticker": f"{pair} Curncy",
                                           "price": float(price)}
 
-    def build_xccy_curve(self, *args, **kwargs):
-        raise LibError("XccyCurve construction is not part of the accelerated path yet (SURVEY section 8f rank 2)")
+    def build_xccy_curve(self, name: str, domestic_curve_name: str, foreign_curve_name: str,
+                         basis_spreads: List[float], tenor_list: List[str], spot_fx: float,
+                         domestic_notional: float = 100_000_000,
+                         domestic_freq_type=FrequencyTypes.ANNUAL, foreign_freq_type=FrequencyTypes.ANNUAL,
+                         domestic_dc_type=DayCountTypes.ACT_360, foreign_dc_type=DayCountTypes.ACT_365F,
+                         bus_day_type=BusDayAdjustTypes.MODIFIED_FOLLOWING,
+                         interp_type=InterpTypes.FLAT_FWD_RATES, use_ad: bool = True):
+        """Cross-currency basis curve from basis spreads in bp (models.py:267-391).  As in the reference the
+        calibration swaps use the XccyBasisSwap default business-day rule and XccyCurve receives 1/spot_fx."""
+        from .trades import XccyBasisSwap
+        from .xccy_curve import XccyCurve
+        for nm, what in ((domestic_curve_name, "Domestic"), (foreign_curve_name, "Foreign")):
+            if nm not in self._curves_dict:
+                raise ValueError(f"{what} curve '{nm}' not found in model. Build it first using build_curve() or "
+                                 f"prebuilt_curve().")
+        dom_ccy = CurrencyTypes[domestic_curve_name.split("_")[0]]
+        for_ccy = CurrencyTypes[foreign_curve_name.split("_")[0]]
+        foreign_notional = domestic_notional / spot_fx
+        swaps = [XccyBasisSwap(effective_dt=self.value_dt, term_dt_or_tenor=tenor, domestic_notional=domestic_notional,
+                               foreign_notional=foreign_notional, domestic_spread=0.0, foreign_spread=bps / 10000.0,
+                               domestic_freq_type=domestic_freq_type, foreign_freq_type=foreign_freq_type,
+                               domestic_dc_type=domestic_dc_type, foreign_dc_type=foreign_dc_type,
+                               domestic_floating_index=CurveTypes[domestic_curve_name],
+                               foreign_floating_index=CurveTypes[foreign_curve_name],
+                               domestic_currency=dom_ccy, foreign_currency=for_ccy)
+                 for tenor, bps in zip(tenor_list, basis_spreads)]
+        self._curves_dict[name] = XccyCurve(value_dt=self.value_dt, basis_swaps=swaps,
+                                            domestic_curve=self._curves_dict[domestic_curve_name],
+                                            foreign_curve=self._curves_dict[foreign_curve_name],
+                                            spot_fx=1 / spot_fx, interp_type=interp_type, use_ad=use_ad)
+        self._curve_params_dict[name] = {
+            "domestic_curve_name": domestic_curve_name, "foreign_curve_name": foreign_curve_name,
+            "basis_spreads": basis_spreads, "tenor_list": tenor_list, "spot_fx": spot_fx,
+            "domestic_notional": domestic_notional, "domestic_freq_type": domestic_freq_type,
+            "foreign_freq_type": foreign_freq_type, "domestic_dc_type": domestic_dc_type,
+            "foreign_dc_type": foreign_dc_type, "bus_day_type": bus_day_type, "interp_type": interp_type,
+            "use_ad": use_ad,
+        }
 
     def scenario(self, curve_name: str, shock, new_name: str = None) -> "Model":
         """New Model holding `curve_name` rebuilt from shocked quotes (float = parallel,

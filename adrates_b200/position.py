@@ -78,6 +78,9 @@ class Engine:
 
     def compute(self, derivative, request_list, collateral_type=None) -> AnalyticsResult:
         dtype = getattr(derivative, "derivative_type", None)
+        if dtype == InstrumentTypes.XCCY_SWAP:
+            from .xccy_engine import compute_xccy
+            return compute_xccy([derivative], self.model, request_list, self.device)
         if dtype != InstrumentTypes.OIS_SWAP:
             raise LibError(f"{dtype} not yet implemented")
         if collateral_type is not None:
@@ -136,6 +139,15 @@ class Portfolio:
         request_list = list(request_list)
         if not self._positions:
             return AnalyticsResult()
+        kinds = {getattr(p.derivative, "derivative_type", None) for p in self._positions}
+        if kinds == {InstrumentTypes.XCCY_SWAP}:
+            from .xccy_engine import compute_xccy
+            models = {id(p.model) for p in self._positions}
+            if len(models) != 1:
+                raise LibError("XCCY portfolio positions must share one Model")
+            return compute_xccy([p.derivative for p in self._positions], self._positions[0].model, request_list)
+        if InstrumentTypes.XCCY_SWAP in kinds:
+            raise LibError("mixed OIS / XCCY portfolios are not supported (the reference cannot add Risk to Delta)")
         buckets = {}
         for pos in self._positions:
             curve = pos._engine._curve_for(pos.derivative)

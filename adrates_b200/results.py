@@ -143,19 +143,34 @@ class Gamma(_Sensitivity):
 
 
 class Risk:
-    """Multi-curve container with attribute access by curve name (results.py:839-942)."""
+    """Multi-curve container: attribute access by curve name, call with a CurveTypes
+    (cavour/requests/results.py:839-942)."""
 
-    def __init__(self, items):
-        self._items = {it.curve_type.name: it for it in items}
+    def __init__(self, items, cross_gammas=None):
+        self._by_curve = {}
+        for it in items:
+            name = it.curve_type.name
+            if name in self._by_curve:
+                raise ValueError(f"Duplicate curve {name} in Risk")
+            self._by_curve[name] = it
+        self._cross_gammas = {}
+        for cg in cross_gammas or []:
+            self._cross_gammas[(cg.curve_type_1.name, cg.curve_type_2.name)] = cg
+
+    def __call__(self, curve_type: CurveTypes):
+        return self._by_curve[curve_type.name]
 
     def __getattr__(self, name):
         try:
-            return self.__dict__["_items"][name]
+            return self.__dict__["_by_curve"][name]
         except KeyError:
             raise AttributeError(f"No risk for curve {name}")
 
-    def __iter__(self):
-        return iter(self._items.values())
+    def cross_gamma(self, c1: CurveTypes, c2: CurveTypes):
+        return self._cross_gammas.get((c1.name, c2.name), None)
+
+    def __repr__(self):
+        return f"Risk({', '.join(f'{k}={v!r}' for k, v in self._by_curve.items())})"
 
 
 class AnalyticsResult:

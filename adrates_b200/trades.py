@@ -122,7 +122,7 @@ class SwapFloatLeg(_SwapLeg):
         self._roll_schedule()
 
     def value(self, value_dt: Date, discount_curve, index_curve=None, first_fixing_rate=None):
-        """Path-A PV of the floating leg without notional exchange (swap_float_leg.py:190-352)."""
+        """Path-A PV of the floating leg (swap_float_leg.py:190-352)."""
         if discount_curve is None:
             raise LibError("Discount curve is None")
         index_curve = index_curve or discount_curve
@@ -141,6 +141,13 @@ class SwapFloatLeg(_SwapLeg):
             first = False
             df_p = discount_curve.df(dt, self._dc_type) / df0
             pv += (fwd + self._spread) * self._year_fracs[i] * self._notional * df_p
+        if self._notional_exchange:
+            # -N at the effective date, +N at maturity, when not in the past (swap_float_leg.py:284-347);
+            # unlike the reference this does not insert the exchange into the leg's date lists
+            if self._effective_dt >= value_dt:
+                pv -= self._notional * discount_curve.df(self._effective_dt, self._dc_type) / df0
+            if self._maturity_dt >= value_dt and len(self._payment_dts) > 0:
+                pv += self._notional * discount_curve.df(self._maturity_dt, self._dc_type) / df0
         return -pv if self._leg_type == SwapTypes.PAY else pv
 
 
@@ -195,3 +202,59 @@ class OIS:
     def swap_rate(self, value_dt, ois_curve, first_fixing_rate=None):
         pv01 = self.pv01(value_dt, ois_curve)
         return self._float_leg.value(value_dt, ois_curve, ois_curve, first_fixing_rate) / pv01 / self._fixed_leg._notional
+
+
+class XccyBasisSwap:
+    """Cross-currency basis swap: receive domestic floating, pay foreign floating + basis spread,
+    notionals exchanged at start and maturity (cavour/trades/rates/xccy_basis_swap.py:67-205)."""
+
+    def __init__(self, effective_dt: Date, term_dt_or_tenor, domestic_notional: float, foreign_notional: float,
+                 domestic_spread: float, foreign_spread: float, domestic_freq_type: FrequencyTypes,
+                 foreign_freq_type: FrequencyTypes, domestic_dc_type: DayCountTypes, foreign_dc_type: DayCountTypes,
+                 domestic_floating_index: CurveTypes, foreign_floating_index: CurveTypes,
+                 domestic_currency: CurrencyTypes, foreign_currency: CurrencyTypes,
+                 domestic_payment_lag: int = 0, foreign_payment_lag: int = 0,
+                 domestic_cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 foreign_cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 domestic_bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 foreign_bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 domestic_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
+                 foreign_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
+                 domestic_end_of_month: bool = False, foreign_end_of_month: bool = False):
+        self.derivative_type = InstrumentTypes.XCCY_SWAP
+        self._termination_dt = _resolve_end(effective_dt, term_dt_or_tenor)
+        self._maturity_dt = Calendar(domestic_cal_type).adjust(self._termination_dt, domestic_bd_type)
+        if effective_dt > self._maturity_dt:
+            raise LibError("Start date after maturity date")
+        self._effective_dt = effective_dt
+        self._domestic_notional = domestic_notional
+        self._foreign_notional = foreign_notional
+        self._domestic_currency = domestic_currency
+        self._foreign_currency = foreign_currency
+        self._domestic_floating_index = domestic_floating_index
+        self._foreign_floating_index = foreign_floating_index
+        self._domestic_leg = SwapFloatLeg(effective_dt, self._termination_dt, SwapTypes.RECEIVE, domestic_spread,
+                                          domestic_freq_type, domestic_dc_type, domestic_floating_index,
+                                          domestic_currency, domestic_notional, 0.0, domestic_payment_lag,
+                                          domestic_cal_type, domestic_bd_type, domestic_dg_type,
+                                          domestic_end_of_month, True)
+        self._foreign_leg = SwapFloatLeg(effective_dt, self._termination_dt, SwapTypes.PAY, foreign_spread,
+                                         foreign_freq_type, foreign_dc_type, foreign_floating_index,
+                                         foreign_currency, foreign_notional, 0.0, foreign_payment_lag,
+                                         foreign_cal_type, foreign_bd_type, foreign_dg_type,
+                                         foreign_end_of_month, True)
+        self._domestic_spread = domestic_spread
+        self._foreign_spread = foreign_spread
+        self._adjusted_domestic_dts = self._domestic_leg._payment_dts
+        self._adjusted_foreign_dts = self._foreign_leg._payment_dts
+
+    def position(self, model):
+        from .position import Position
+        return Position(self, model)
+
+    def value(self, value_dt: Date, domestic_curve, foreign_curve, xccy_curve, spot_fx: float):
+        """Path-A PV in domestic currency: domestic leg on its own curve, foreign leg projected on the foreign
+        OIS curve and discounted on the XCCY curve, converted at spot (xccy_basis_swap.py:209-306)."""
+        pv_dom = self._domestic_leg.value(value_dt, domestic_curve, domestic_curve)
+        pv_for = self._foreign_leg.value(value_dt, xccy_curve, foreign_curve)
+        return pv_dom + spot_fx * pv_for

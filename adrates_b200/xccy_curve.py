@@ -1,0 +1,154 @@
+"""XccyCurve: foreign-in-domestic discount curve implied by cross-currency basis swaps.
+
+Mirror of cavour/trades/rates/xccy_curve.py for the part the valuation path consumes:
+`_times`, `_dfs`, `swap_times`, `basis_spreads`, `_spot_fx`, `_interp_type`, `_dc_type`, `df()` and
+`_jac_basis` = d(xccy DFs)/d(pillar basis spreads) (xccy_curve.py:594).  The curve is an input
+producer (built once per curve on the host, like OISCurve path A); its tables are uploaded to the
+device with cav_curve_set_tables.
+
+Bootstrap (xccy_curve.py:707-935 plan, :954-1206 recursion), per foreign-leg payment point in
+(time, swap) order:
+    cashflow      = N*(DF_s/DF_e - 1) [+N on the last payment]  or -+N for a notional exchange,
+                    + basis_swap * accrual * N          (DF_s, DF_e log-linear on the foreign OIS nodes)
+    DF_inter(t)   = DF_prev * DF_ois(t)/DF_ois(t_prev) * exp(-basis_swap * (t - t_prev))
+    at a maturity : DF(t) solves  PV_dom + spot * (-(known PV) - cashflow * DF(t)) = 0
+The reference differentiates this scan with jacrev; here the first-order tangents w.r.t. the pillar
+spreads are propagated alongside the values (exact forward mode).  Second-order tables
+(`_hess_basis`, `_mixed_hess_foreign_basis`) are not produced: the reference's XCCY GAMMA request
+fails inside its cross-gamma contraction (engine.py:1936-1939), so there is nothing to match.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .curves import DiscountCurve
+from .dates import Date, DayCountTypes, times_from_dates
+from .error import LibError
+from .global_types import InterpTypes
+
+
+class XccyCurve(DiscountCurve):
+    def __init__(self, value_dt: Date, basis_swaps: list, domestic_curve, foreign_curve, spot_fx: float,
+                 interp_type: InterpTypes = InterpTypes.FLAT_FWD_RATES, check_refit: bool = False,
+                 use_ad: bool = False):
+        if not basis_swaps:
+            raise LibError("XccyCurve needs at least one basis swap")
+        self._value_dt = value_dt
+        self._used_swaps = sorted(basis_swaps, key=lambda s: s._maturity_dt._n)
+        self._domestic_curve = domestic_curve
+        self._foreign_curve = foreign_curve
+        self._spot_fx = spot_fx
+        self._interp_type = interp_type
+        self._check_refit = check_refit
+        self._use_ad = use_ad
+        self._dc_type = DayCountTypes.ACT_365F
+        self.basis_spreads = [s._foreign_spread for s in self._used_swaps]
+        self.swap_times = [(s._maturity_dt - value_dt) / 365.0 for s in self._used_swaps]
+        self._bootstrap()
+
+    # ---------------------------------------------------------------------------------
+    def _points(self):
+        """Foreign-leg payment points of all calibration swaps (xccy_curve.py:720-806).  The
+        reference reads them off legs that `value()` has mutated (an effective-date exchange row
+        with zero accrual is inserted, swap_float_leg.py:306-318); here the row is built directly."""
+        vd, fc = self._value_dt, self._foreign_curve
+        pts = []
+        for k, swap in enumerate(self._used_swaps):
+            leg = swap._foreign_leg
+            pv_dom = swap._domestic_leg.value(vd, self._domestic_curve, self._domestic_curve)
+            rows = []
+            if leg._notional_exchange and leg._effective_dt >= vd:
+                rows.append((leg._effective_dt, 0.0, leg._effective_dt, leg._effective_dt))
+            rows += list(zip(leg._payment_dts, leg._year_fracs, leg._start_accrued_dts, leg._end_accrued_dts))
+            for pay, alpha, start, end in rows:
+                if not pay >= vd:
+                    continue
+                exch = abs(alpha) < 1e-10
+                pts.append(dict(
+                    time=(pay - vd) / 365.0, swap=k, is_mat=(pay == swap._maturity_dt), at_val=(pay == vd),
+                    alpha=alpha, notional=leg._notional, exch=exch,
+                    last=(pay == swap._maturity_dt) and leg._notional_exchange,
+                    spread_sens=0.0 if exch else alpha * leg._notional,
+                    t_start=times_from_dates(start, vd, fc._dc_type), t_end=times_from_dates(end, vd, fc._dc_type),
+                    df_ois=fc.df(pay, fc._dc_type), pv_dom=pv_dom))
+        pts.sort(key=lambda p: (p["time"], p["swap"]))
+        return pts
+
+    def _bootstrap(self):
+        pts = self._points()
+        nb = len(self._used_swaps)
+        fx, fd = np.asarray(self._foreign_curve._times, dtype=np.float64), np.asarray(self._foreign_curve._dfs, dtype=np.float64)
+        log_fd = np.log(fd)
+        n = len(pts)
+        df = np.zeros(n)
+        ddf = np.zeros((n, nb))                   # d df / d pillar spreads
+        pv_c = np.zeros(n)
+        dpv_c = np.zeros((n, nb))
+        prev = -1                                  # previous XCCY node (any swap), in time order
+        node_idx, seen = [], set()
+        for i, p in enumerate(pts):
+            k = p["swap"]
+            basis = self.basis_spreads[k]
+            e_k = np.zeros(nb)
+            e_k[k] = 1.0
+            if p["exch"]:
+                base = p["notional"] if p["last"] else -p["notional"]
+            else:
+                df_s = np.exp(np.interp(p["t_start"], fx, log_fd))
+                df_e = np.exp(np.interp(p["t_end"], fx, log_fd))
+                fwd = (df_s / df_e - 1.0) / max(p["alpha"], 1e-10) if p["alpha"] > 1e-10 else 0.0
+                base = fwd * p["alpha"] * p["notional"] + (p["notional"] if p["last"] else 0.0)
+            cash = base + basis * p["spread_sens"]
+            dcash = p["spread_sens"] * e_k
+            if prev < 0:
+                d_int = p["df_ois"] * np.exp(-basis * p["time"])
+                dd_int = -p["time"] * d_int * e_k
+            else:
+                q = pts[prev]
+                grow = (p["df_ois"] / q["df_ois"]) * np.exp(-basis * (p["time"] - q["time"]))
+                d_int = df[prev] * grow
+                dd_int = ddf[prev] * grow - (p["time"] - q["time"]) * d_int * e_k
+            if p["at_val"]:
+                pv_c[i], dpv_c[i] = cash, dcash
+            elif not p["is_mat"]:
+                pv_c[i] = cash * d_int
+                dpv_c[i] = dcash * d_int + cash * dd_int
+            if p["is_mat"]:
+                same = [j for j in range(i) if pts[j]["swap"] == k]
+                known = pv_c[same].sum() + pv_c[i]
+                dknown = dpv_c[same].sum(axis=0) + dpv_c[i]
+                # par: PV_dom + spot * (-(known) - cash * DF) = 0  (foreign legs pay)
+                num = -(p["pv_dom"] + self._spot_fx * (-known))
+                den = self._spot_fx * (-cash)
+                dnum = self._spot_fx * dknown
+                dden = -self._spot_fx * dcash
+                if abs(den) > 1e-12:
+                    df[i] = num / den
+                    ddf[i] = (dnum - df[i] * dden) / den
+                else:
+                    df[i], ddf[i] = d_int, dd_int
+            else:
+                df[i], ddf[i] = d_int, dd_int
+            if not p["at_val"]:
+                prev = i
+                key = round(p["time"], 4)
+                if key not in seen:
+                    seen.add(key)
+                    node_idx.append(i)
+        self._times = np.concatenate([[0.0], [pts[i]["time"] for i in node_idx]])
+        self._dfs = np.concatenate([[1.0], df[node_idx]])
+        self._repr_dfs = self._dfs
+        self._jac_basis = np.vstack([np.zeros((1, nb)), ddf[node_idx]])
+        if self._check_refit:
+            self._check_refits(1e-8)
+
+    # ---------------------------------------------------------------------------------
+    def df(self, dt, day_count=None):
+        """Always ACT/365F, whatever day count is passed (xccy_curve.py:1210-1234)."""
+        return DiscountCurve.df(self, dt, DayCountTypes.ACT_365F)
+
+    def _check_refits(self, swap_tol: float):
+        for swap in self._used_swaps:
+            v = swap.value(self._value_dt, self._domestic_curve, self._foreign_curve, self, self._spot_fx)
+            if abs(v / swap._domestic_notional) > swap_tol:
+                raise LibError("Basis swap not repriced.")

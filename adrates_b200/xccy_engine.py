@@ -1,0 +1,202 @@
+"""Cross-currency basis swap valuation on the CUDA path (VALUE + three delta ladders).
+
+Replaces Engine._compute_xccy (cavour/market/position/engine.py:1411-1765):
+    total = PV_dom(domestic OIS grid) + PV_for(foreign OIS grid for forwards, XCCY nodes for discounting)/spot_fx
+    delta_dom   = grad_dom_dfs  @ J_dom      * 1e-4
+    delta_for   = grad_for_dfs  @ J_for      * 1e-4 / spot_fx      (XCCY DFs held fixed)
+    delta_basis = grad_xccy_dfs @ J_basis    * 1e-4 / spot_fx      (both OIS curves held fixed)
+The domestic leg is an ordinary single-curve unit.  The foreign leg lives on a *stacked* node grid
+[foreign OIS engine grid ; XCCY curve nodes]: a coupon is the 3-bracket product term
+N*DF_f(s)/DF_f(e)*DF_x(p), and the two foreign-leg ladders are the same valuation run against two
+Jacobian blocks ([J_for ; 0] and [0 ; J_basis]) uploaded with cav_curve_set_tables.
+
+GAMMA: the reference's XCCY gamma request fails inside its cross-gamma contraction
+(engine.py:1936-1939: 65 path-A foreign nodes of `_mixed_hess_foreign_basis` against the 263-row engine
+Jacobian), so there is no reference behaviour to match; NotImplementedError is raised.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import _native
+from .curves import plan_queries
+from .dates import times_from_dates, to_tenor
+from .error import LibError
+from .flatten import FlatPortfolio, Flattener, _Unit
+from .global_types import CurveTypes, RequestTypes, SwapTypes
+from .results import AnalyticsResult, Delta, Risk, Valuation
+
+
+def _sign(leg) -> float:
+    return +1.0 if leg._leg_type == SwapTypes.RECEIVE else -1.0
+
+
+def domestic_leg_unit(swap, value_dt) -> _Unit:
+    """Floating leg with notional exchange on its own curve (engine.py:2675-2728), single-DF terms."""
+    leg = swap._domestic_leg
+    dc = leg._dc_type
+    sg, N = _sign(leg), leg._notional
+    t = lambda d: times_from_dates(d, value_dt, dc)  # noqa: E731
+    times, amts = [], []
+    for i, pay in enumerate(leg._payment_dts):
+        tp, ts, te, al = t(pay), t(leg._start_accrued_dts[i]), t(leg._end_accrued_dts[i]), leg._year_fracs[i]
+        if not tp >= 0.0:
+            continue
+        if al > 0:
+            if tp == te:
+                times += [((ts, 1.0),), ((te, 1.0),)]
+                amts += [sg * N, -sg * N]
+            else:
+                times += [((ts, 1.0), (te, -1.0), (tp, 1.0)), ((tp, 1.0),)]
+                amts += [sg * N, -sg * N]
+        if leg._spread != 0.0:
+            times.append(((tp, 1.0),))
+            amts.append(sg * leg._spread * al * N)
+    if leg._notional_exchange:
+        te_, tm_ = t(swap._effective_dt), t(swap._maturity_dt)
+        if te_ >= 0.0:
+            times.append(((te_, 1.0),))
+            amts.append(-sg * N)
+        if tm_ >= 0.0:
+            times.append(((tm_, 1.0),))
+            amts.append(sg * N)
+    return _Unit(times, amts)
+
+
+def foreign_leg_terms(swap, value_dt, xccy_curve):
+    """[(amount, t_start|None, t_end|None, t_pay)]: start/end on the foreign OIS grid (foreign leg day count),
+    pay on the XCCY nodes (XCCY day count), amounts in domestic currency (divided by the curve's spot_fx)."""
+    leg = swap._foreign_leg
+    fx = xccy_curve._spot_fx
+    sg, N = _sign(leg), leg._notional
+    tf = lambda d: times_from_dates(d, value_dt, leg._dc_type)          # noqa: E731
+    tx = lambda d: times_from_dates(d, value_dt, xccy_curve._dc_type)   # noqa: E731
+    out = []
+    for i, pay in enumerate(leg._payment_dts):
+        tp, al = tx(pay), leg._year_fracs[i]
+        if not tp >= 0.0:
+            continue
+        if al > 0:
+            out.append((sg * N / fx, tf(leg._start_accrued_dts[i]), tf(leg._end_accrued_dts[i]), tp))
+            out.append((-sg * N / fx, None, None, tp))
+        if leg._spread != 0.0:
+            out.append((sg * leg._spread * al * N / fx, None, None, tp))
+    if leg._notional_exchange:
+        te_, tm_ = tx(swap._effective_dt), tx(swap._maturity_dt)
+        if te_ >= 0.0:
+            out.append((-sg * N / fx, None, None, te_))
+        if tm_ >= 0.0:
+            out.append((sg * N / fx, None, None, tm_))
+    return out
+
+
+def flatten_foreign_legs(swaps, value_dt, foreign_curve, xccy_curve) -> FlatPortfolio:
+    """One private unit per trade on the stacked grid; 6 (node, weight) pairs per term:
+    [start bracket (+), end bracket (-), pay bracket (+ on XCCY nodes, offset by the foreign grid size)]."""
+    plan_f = foreign_curve.path_b_plan()
+    Gf = plan_f.n_nodes
+    terms, offsets = [], [0]
+    for sw in swaps:
+        terms += foreign_leg_terms(sw, value_dt, xccy_curve)
+        offsets.append(len(terms))
+    n = len(terms)
+    amt = np.array([t[0] for t in terms], dtype=np.float64)
+    has_fwd = np.array([t[1] is not None for t in terms], dtype=bool)
+    ts = np.array([t[1] if t[1] is not None else 0.0 for t in terms], dtype=np.float64)
+    te = np.array([t[2] if t[2] is not None else 0.0 for t in terms], dtype=np.float64)
+    tp = np.array([t[3] for t in terms], dtype=np.float64)
+    weight = np.zeros((n, 6))
+    node = np.zeros((n, 6), dtype=np.int32)
+    if n:
+        a, b, wa, wb = plan_queries(ts, plan_f.node_time, foreign_curve._interp_type)
+        weight[:, 0], weight[:, 1], node[:, 0], node[:, 1] = wa * has_fwd, wb * has_fwd, a, b
+        a, b, wa, wb = plan_queries(te, plan_f.node_time, foreign_curve._interp_type)
+        weight[:, 2], weight[:, 3], node[:, 2], node[:, 3] = -wa * has_fwd, -wb * has_fwd, a, b
+        a, b, wa, wb = plan_queries(tp, np.asarray(xccy_curve._times, dtype=np.float64), xccy_curve._interp_type)
+        weight[:, 4], weight[:, 5], node[:, 4], node[:, 5] = wa, wb, a + Gf, b + Gf
+        node[weight == 0.0] = 0
+    N = len(swaps)
+    return FlatPortfolio(N, n, np.array(offsets, dtype=np.int64), 6, amt, weight.reshape(-1), node.reshape(-1),
+                         N, 1, np.ones(N), N, np.arange(N + 1, dtype=np.int64), np.arange(N, dtype=np.int32), None,
+                         np.ones(N))
+
+
+class XccySession:
+    """Device tables of the stacked (foreign OIS + XCCY) grid, one context per Jacobian block."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, foreign_curve, xccy_curve, device=0):
+        key = (device, id(foreign_curve), id(xccy_curve))
+        if key not in cls._cache:
+            if len(cls._cache) >= 8:
+                old = cls._cache.pop(next(iter(cls._cache)))
+                old.ctx_for.close()
+                old.ctx_basis.close()
+            cls._cache[key] = XccySession(foreign_curve, xccy_curve, device)
+        return cls._cache[key]
+
+    def __init__(self, foreign_curve, xccy_curve, device):
+        from .position import CurveSession
+        fsess = CurveSession.get(foreign_curve, device)
+        d_f, J_f, _ = fsess.ctx.curve_read(jac=True, hess=False)       # engine grid of the foreign OIS curve
+        d_x = np.asarray(xccy_curve._dfs, dtype=np.float64)
+        J_b = np.asarray(xccy_curve._jac_basis, dtype=np.float64)
+        Gf, Rf, Gx, Rb = d_f.shape[0], J_f.shape[1], d_x.shape[0], J_b.shape[1]
+        d = np.concatenate([d_f, d_x])
+        self.ctx_for = _native.Context(device)
+        self.ctx_for.curve_set_tables(d, np.vstack([J_f, np.zeros((Gx, Rf))]))
+        self.ctx_basis = _native.Context(device)
+        self.ctx_basis.curve_set_tables(d, np.vstack([np.zeros((Gf, Rb)), J_b]))
+        self.n_for, self.n_basis = Rf, Rb
+
+
+def compute_xccy(derivatives, model, request_list, device=0) -> AnalyticsResult:
+    reqs = set(request_list)
+    if RequestTypes.GAMMA in reqs:
+        raise NotImplementedError("XCCY GAMMA: the reference raises in its cross-gamma contraction "
+                                  "(engine.py:1936-1939); there is no reference result to reproduce")
+    if RequestTypes.CASHFLOWS in reqs:
+        raise NotImplementedError("CASHFLOWS on XCCY swaps raises NameError in the reference (engine.py:1986)")
+    from .position import CurveSession
+    d0 = derivatives[0]
+    curves = model.curves
+    try:
+        dom = getattr(curves, d0._domestic_floating_index.name)
+        forn = getattr(curves, d0._foreign_floating_index.name)
+    except AttributeError as ex:
+        raise LibError(str(ex))
+    name = f"{d0._foreign_currency.name}_{d0._domestic_currency.name}_BASIS"
+    try:
+        xc = getattr(curves, name)
+    except AttributeError:
+        raise LibError(f"XCCY curve {name} not found in model.")
+    vd = model.value_dt
+    mask = (_native.REQ_VALUE if RequestTypes.VALUE in reqs else 0) | (_native.REQ_DELTA if RequestTypes.DELTA in reqs else 0)
+    want_delta = bool(mask & _native.REQ_DELTA)
+    # domestic legs: ordinary single-curve units on the domestic OIS curve
+    dsess = CurveSession.get(dom, device)
+    fl = Flattener(dom)
+    for sw in derivatives:
+        fl.add_components([(("XD", id(sw)), domestic_leg_unit(sw, vd), 1.0)])
+    dsess.ctx.portfolio_upload(fl.finalize(dedup=False))
+    agg_dom = dsess.ctx.portfolio_value_host(mask | _native.REQ_VALUE)
+    # foreign legs on the stacked grid
+    xs = XccySession.get(forn, xc, device)
+    flat = flatten_foreign_legs(derivatives, vd, forn, xc)
+    xs.ctx_for.portfolio_upload(flat)
+    agg_for = xs.ctx_for.portfolio_value_host(mask | _native.REQ_VALUE)
+    value = delta = None
+    ccy = d0._domestic_currency
+    if RequestTypes.VALUE in reqs:
+        value = Valuation(float(agg_dom[0] + agg_for[0]), ccy)
+    if want_delta:
+        xs.ctx_basis.portfolio_upload(flat)
+        agg_bas = xs.ctx_basis.portfolio_value_host(_native.REQ_VALUE | _native.REQ_DELTA)
+        Rd, Rf, Rb = len(dom.swap_rates), xs.n_for, xs.n_basis
+        delta = Risk([
+            Delta(np.array(agg_dom[1:1 + Rd]), to_tenor(dom.swap_times), ccy, d0._domestic_floating_index),
+            Delta(np.array(agg_for[1:1 + Rf]), to_tenor(forn.swap_times), ccy, d0._foreign_floating_index),
+            Delta(np.array(agg_bas[1:1 + Rb]), to_tenor(xc.swap_times), ccy, CurveTypes.USD_GBP_BASIS),
+        ])
+    return AnalyticsResult(value=value, risk=delta, gamma=None)

@@ -82,6 +82,13 @@ int cav_curve_build(cav_ctx* ctx, int interp_method,
  * hess is [G][n_rates][n_rates] - the shapes of the reference cache (engine.py:2405-2410) */
 int cav_curve_read(cav_ctx* ctx, double* dfs, double* jac, double* hess);
 
+/* Set the curve tables directly instead of bootstrapping them: dfs[G], jac[G][n_rates] (may be
+ * NULL), hess[G][n_rates][n_rates] (may be NULL).  Used for curves whose bootstrap lives on the
+ * host - XccyCurve._times/_dfs/_jac_basis (cavour/trades/rates/xccy_curve.py:529-703) - and for
+ * the stacked (foreign OIS + XCCY) node grid of Engine._compute_xccy (engine.py:1411-1765). */
+int cav_curve_set_tables(cav_ctx* ctx, const double* dfs, const double* jac, const double* hess, int n_nodes,
+                         int n_rates);
+
 /* ---- curve.df_ad: replaces DiscountCurve._linear_forward_interp -------------------
  * (cavour/market/curves/discount_curve.py:385-415) on the path-A nodes. */
 int cav_df_ad(cav_ctx* ctx, const double* node_time, const double* node_df, int n_nodes,

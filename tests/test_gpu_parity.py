@@ -265,3 +265,34 @@ def test_delta_chain_gemm_matches_fused_path(ref_curves):
         assert np.max(np.abs(pv2.cpu().numpy() - pv) / np.maximum(np.abs(pv), N)) < TOL
         assert np.max(np.abs(dl2.cpu().numpy() - dl) / np.maximum(np.abs(dl), (N * 1e-4)[:, None])) < TOL
     ctx.close()
+
+
+def test_xccy_position_and_portfolio_match_reference():
+    """Engine._compute_xccy VALUE + three delta ladders (goldens from the unmodified reference engine)."""
+    from tests.conftest import load_golden
+    from tests.util_xccy import build_xccy_model, make_xccy_trade
+    from adrates_b200 import Position, CurveTypes
+    g = load_golden("ref_xccy.json")
+    m = build_xccy_model(g)
+    trades = [make_xccy_trade(t) for t in g["trades"]]
+    tot_v, tot_b = 0.0, None
+    for sw, t in zip(trades, g["trades"]):
+        res = Position(sw, m).compute([RequestTypes.VALUE, RequestTypes.DELTA])
+        N, T = t["domestic_notional"], float(t["tenor"][:-1])
+        assert abs(res.value.amount - t["value"]) <= TOL * max(abs(t["value"]), N), t["id"]
+        for key, ct in (("USD_OIS_SOFR", CurveTypes.USD_OIS_SOFR), ("GBP_OIS_SONIA", CurveTypes.GBP_OIS_SONIA),
+                        ("USD_GBP_BASIS", CurveTypes.USD_GBP_BASIS)):
+            ref = np.array(t["deltas"][key]["ladder"])
+            got = res.risk(ct).risk_ladder
+            assert got.shape == ref.shape and res.risk(ct).tenors == t["deltas"][key]["tenors"]
+            assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), N * 1e-4 * T)) < TOL, (t["id"], key)
+        tot_v += t["value"]
+        b = np.array(t["deltas"]["USD_GBP_BASIS"]["ladder"])
+        tot_b = b if tot_b is None else tot_b + b
+        only_v = Position(sw, m).compute([RequestTypes.VALUE])
+        assert only_v.risk is None and abs(only_v.value.amount - t["value"]) <= TOL * max(abs(t["value"]), N)
+    port = Portfolio([Position(sw, m) for sw in trades]).compute([RequestTypes.VALUE, RequestTypes.DELTA])
+    assert abs(port.value.amount - tot_v) <= TOL * 1e8
+    assert np.max(np.abs(port.risk.USD_GBP_BASIS.risk_ladder - tot_b)) <= TOL * 1e8 * 1e-4 * 10
+    with pytest.raises(NotImplementedError):
+        Position(trades[0], m).compute([RequestTypes.GAMMA])

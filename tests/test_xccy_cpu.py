@@ -1,0 +1,72 @@
+"""Cross-currency path on CPU: XccyCurve bootstrap + Jacobian against the reference's AD tables, and the flattened
+legs (evaluated with the numpy restatement of the kernels) against the reference engine's VALUE and three deltas."""
+import numpy as np
+import pytest
+
+from oracle import cavour_oracle as orc
+from adrates_b200.flatten import Flattener
+from adrates_b200.xccy_engine import domestic_leg_unit, flatten_foreign_legs
+from tests.conftest import load_golden
+from tests.flat_eval import eval_flat
+from tests.util_xccy import build_xccy_model, make_xccy_trade
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def xg():
+    return load_golden("ref_xccy.json")
+
+
+def test_xccy_curve_matches_reference(xg):
+    m = build_xccy_model(xg)
+    xc = m.curves.GBP_USD_BASIS
+    assert np.array_equal(xc._times, np.array(xg["xccy_times"]))
+    assert np.max(np.abs(xc._dfs - np.array(xg["xccy_dfs"]))) < 1e-14
+    J = np.array(xg["xccy_jac_basis"])
+    assert np.max(np.abs(xc._jac_basis - J)) < 1e-12 * np.abs(J).max()
+    assert xc.swap_times == xg["xccy_swap_times"] and xc._spot_fx == xg["xccy_spot_fx_internal"]
+    assert xc._interp_type.name == xg["xccy_interp"]
+
+
+def test_calibration_basis_swaps_reprice(xg):
+    """tests/test_xccy_curve.py:213 / test_xccy_simple.py:131: abs(PV/N) < 1e-8 through the non-AD value().
+    Holds when the OIS curves interpolate flat-forward (the bootstrap projects forwards log-linearly)."""
+    from adrates_b200 import InterpTypes
+    import tests.util_xccy as ux
+    g = dict(xg)
+    m = ux.build_xccy_model(g, ois_interp=InterpTypes.FLAT_FWD_RATES)
+    m.curves.GBP_USD_BASIS._check_refits(1e-8)
+
+
+def test_flattened_xccy_trades_match_reference_engine(xg):
+    m = build_xccy_model(xg)
+    dom, forn, xc = m.curves.USD_OIS_SOFR, m.curves.GBP_OIS_SONIA, m.curves.GBP_USD_BASIS
+    vd = m.value_dt
+    tabs = {}
+    for c in (dom, forn):
+        plan = orc.plan_path_b(c.swap_times, c.year_fracs)
+        tabs[id(c)] = orc.bootstrap_tables(c.swap_rates, plan)
+    d_d, J_d, _ = tabs[id(dom)]
+    d_f, J_f, _ = tabs[id(forn)]
+    d_x, J_b = xc._dfs, xc._jac_basis
+    d_s = np.concatenate([d_f, d_x])
+    Gf, Gx, Rb = len(d_f), len(d_x), J_b.shape[1]
+    J_for = np.vstack([J_f, np.zeros((Gx, 32))])
+    J_bas = np.vstack([np.zeros((Gf, Rb)), J_b])
+    z = lambda G, R: np.zeros((G, R, R))  # noqa: E731
+    for t in xg["trades"]:
+        sw = make_xccy_trade(t)
+        fl = Flattener(dom)
+        fl.add_components([(("XD", 0), domestic_leg_unit(sw, vd), 1.0)])
+        pv_d, dl_d, _ = eval_flat(fl.finalize(dedup=False), d_d, J_d, z(len(d_d), 32))
+        flat = flatten_foreign_legs([sw], vd, forn, xc)
+        pv_f, dl_f, _ = eval_flat(flat, d_s, J_for, z(Gf + Gx, 32))
+        _, dl_b, _ = eval_flat(flat, d_s, J_bas, z(Gf + Gx, Rb))
+        N = t["domestic_notional"]
+        T = float(t["tenor"][:-1])
+        assert abs(pv_d[0] + pv_f[0] - t["value"]) <= TOL * max(abs(t["value"]), N), t["id"]
+        ref = t["deltas"]
+        for got, key in ((dl_d[0], "USD_OIS_SOFR"), (dl_f[0], "GBP_OIS_SONIA"), (dl_b[0], "USD_GBP_BASIS")):
+            r = np.array(ref[key]["ladder"])
+            assert np.max(np.abs(got[:len(r)] - r) / np.maximum(np.abs(r), N * 1e-4 * T)) < TOL, (t["id"], key)
