@@ -296,3 +296,36 @@ def test_xccy_position_and_portfolio_match_reference():
     assert np.max(np.abs(port.risk.USD_GBP_BASIS.risk_ladder - tot_b)) <= TOL * 1e8 * 1e-4 * 10
     with pytest.raises(NotImplementedError):
         Position(trades[0], m).compute([RequestTypes.GAMMA])
+
+
+def test_small_curve_seasoned_swap_and_empty_portfolio():
+    """Edge cases against the pinned oracle: a 6-pillar curve (ladders narrower than a warp), a seasoned swap whose
+    first accrual started before the value date (past cashflows masked, DF(t<0) = 1), and an empty portfolio."""
+    from adrates_b200 import (Model, OIS, Date, SwapTypes, FrequencyTypes, DayCountTypes, CurveTypes, CurrencyTypes,
+                              BusDayAdjustTypes, InterpTypes)
+    from adrates_b200.flatten import FlatPortfolio
+    vd = Date(17, 12, 2024)
+    m = Model(vd)
+    tenors, px = ["6M", "1Y", "2Y", "5Y", "10Y", "30Y"], [5.1, 5.0, 4.7, 4.3, 4.1, 4.0]
+    m.build_curve(name="GBP_OIS_SONIA", px_list=px, tenor_list=tenors, fixed_dcc_type=DayCountTypes.ACT_365F,
+                  float_dc_type=DayCountTypes.ACT_365F, interp_type=InterpTypes.FLAT_FWD_RATES)
+    curve = m.curves.GBP_OIS_SONIA
+    plan = orc.plan_path_b(curve.swap_times, curve.year_fracs)
+    d, J, C = orc.bootstrap_tables(curve.swap_rates, plan)
+    for eff, tenor in ((Date(17, 12, 2024), "7Y"), (Date(20, 3, 2023), "6Y"), (Date(3, 2, 2025), "18M")):
+        sw = OIS(eff, tenor, SwapTypes.RECEIVE, 0.043, FrequencyTypes.SEMI_ANNUAL, DayCountTypes.ACT_365F,
+                 CurveTypes.GBP_OIS_SONIA, CurrencyTypes.GBP, notional=3e6, float_spread=0.001,
+                 float_freq_type=FrequencyTypes.QUARTERLY, float_dc_type=DayCountTypes.ACT_365F,
+                 bd_type=BusDayAdjustTypes.MODIFIED_FOLLOWING)
+        res = sw.position(m).compute(ALL)
+        fixed, floating = leg_arrays(sw, vd)
+        v, dl, gm = orc.ois_analytics((plan["times"], d, J, C), 1, fixed, floating)
+        assert res.risk.risk_ladder.shape == (6,) and res.gamma.risk_ladder.shape == (6, 6)
+        assert rel_err(res.value.amount, v, 3e6) < TOL
+        assert rel_err(res.risk.risk_ladder, dl, 3e6 * 1e-4) < TOL
+        assert rel_err(res.gamma.risk_ladder, gm, 3e6 * 1e-8) < TOL
+    ctx = CurveSession.get(curve).ctx
+    z64, zf, zi = np.zeros(1, dtype=np.int64), np.zeros(0), np.zeros(0, dtype=np.int32)
+    ctx.portfolio_upload(FlatPortfolio(0, 0, z64, 2, zf, zf, zi, 0, 1, zf, 0, z64, zi, None, zf))
+    assert np.all(ctx.portfolio_value_host(MASK) == 0.0)
+    assert Portfolio([]).compute(ALL).value is None
