@@ -47,6 +47,7 @@ struct cav_ctx {
     int64_t n_units = 0, n_terms = 0, n_trades = 0, n_groups = 0;
     int n_pairs = 2, n_comp = 1;
     bool direct = false;
+    bool portfolio_valid = false;
     int64_t* unit_offsets = nullptr;
     double *amt = nullptr, *weight = nullptr;
     int* node = nullptr;
@@ -439,23 +440,6 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     if (unit_offsets[0] != 0 || unit_offsets[n_units] != n_terms || group_offsets[0] != 0 ||
         group_offsets[n_groups] != n_trades)
         return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: offsets do not cover the arrays");
-    {   // bounds of every index the kernels will dereference (branch-free scans)
-        int lo = 0, hi = 0;
-        for (int64_t i = 0; i < n_terms * n_pairs; ++i) { lo = node[i] < lo ? node[i] : lo; hi = node[i] > hi ? node[i] : hi; }
-        if (lo < 0 || hi >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: node index out of range");
-        lo = hi = 0;
-        for (int64_t i = 0; i < n_groups * n_comp; ++i) { lo = group_units[i] < lo ? group_units[i] : lo; hi = group_units[i] > hi ? group_units[i] : hi; }
-        if (lo < 0 || (n_groups && hi >= n_units)) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: unit id out of range");
-        int64_t bad = 0;
-        for (int64_t u = 0; u < n_units; ++u) bad |= (unit_offsets[u + 1] - unit_offsets[u]) >> 63;
-        for (int64_t gi = 0; gi < n_groups; ++gi) {
-            const int64_t c = group_offsets[gi + 1] - group_offsets[gi];
-            bad |= (c >> 63) | ((256 - c) >> 63);      // 0 <= group size <= 256
-        }
-        if (out_index)
-            for (int64_t t = 0; t < n_trades; ++t) bad |= (out_index[t] >> 63) | ((n_trades - 1 - out_index[t]) >> 63);
-        if (bad) return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: offsets not monotone, group larger than 256 trades or out_index out of range");
-    }
     bool direct = (n_comp == 1 && n_units == n_trades && n_groups == n_trades);
     if (direct) {
         int64_t bad = 0;
@@ -481,7 +465,32 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     if (!direct) CK(upload(ctx, &ctx->unit_weight, unit_weight, (size_t)n_units));
     if (out_index) CK(upload(ctx, &ctx->out_index, out_index, (size_t)n_trades));
     else dev_free(ctx, &ctx->out_index);
+    // Host-side validation of every index the kernels will dereference runs while the copies above are in
+    // flight (branch-free scans); a failure invalidates the uploaded portfolio.
+    const char* verr = nullptr;
+    {
+        int lo = 0, hi = 0;
+        for (int64_t i = 0; i < n_terms * n_pairs; ++i) { lo = node[i] < lo ? node[i] : lo; hi = node[i] > hi ? node[i] : hi; }
+        if (lo < 0 || hi >= ctx->G) verr = "cav_portfolio_upload: node index out of range";
+        lo = hi = 0;
+        for (int64_t i = 0; i < n_groups * n_comp; ++i) { lo = group_units[i] < lo ? group_units[i] : lo; hi = group_units[i] > hi ? group_units[i] : hi; }
+        if (lo < 0 || (n_groups && hi >= n_units)) verr = "cav_portfolio_upload: unit id out of range";
+        int64_t bad = 0;
+        for (int64_t u = 0; u < n_units; ++u) bad |= (unit_offsets[u + 1] - unit_offsets[u]) >> 63;
+        for (int64_t gi = 0; gi < n_groups; ++gi) {
+            const int64_t c = group_offsets[gi + 1] - group_offsets[gi];
+            bad |= (c >> 63) | ((256 - c) >> 63);      // 0 <= group size <= 256
+        }
+        if (out_index)
+            for (int64_t t = 0; t < n_trades; ++t) bad |= (out_index[t] >> 63) | ((n_trades - 1 - out_index[t]) >> 63);
+        if (bad) verr = "cav_portfolio_upload: offsets not monotone, group larger than 256 trades or out_index out of range";
+    }
     CK(cudaStreamSynchronize(ctx->stream));   // host buffers may be reused by the caller
+    if (verr) {
+        ctx->portfolio_valid = false;
+        return fail(ctx, CAV_E_INVALID, verr);
+    }
+    ctx->portfolio_valid = true;
     ctx->n_units = n_units; ctx->n_terms = n_terms; ctx->n_trades = n_trades; ctx->n_groups = n_groups;
     ctx->n_pairs = n_pairs; ctx->n_comp = n_comp; ctx->direct = direct;
     ctx->row_tables_valid = false;
@@ -492,7 +501,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
                       double* agg_host) {
     if (!ctx) return CAV_E_INVALID;
     if (ctx->order < 0) return fail(ctx, CAV_E_STATE, "cav_portfolio_value: no curve");
-    if (!ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_portfolio_value: no portfolio uploaded");
+    if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_value: no portfolio uploaded");
     const bool want_d = (mask & CAV_REQ_DELTA) != 0, want_g = (mask & CAV_REQ_GAMMA) != 0;
     if ((want_d || want_g) && ctx->order < 1) return fail(ctx, CAV_E_STATE, "curve built without jacobian");
     if (want_g && ctx->order < 2) return fail(ctx, CAV_E_STATE, "curve built without hessian");
@@ -577,7 +586,7 @@ int cav_portfolio_value_host(cav_ctx* ctx, uint32_t request_mask, double* pv_dev
 int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, float* gemm_ms, double* gemm_flops) {
     if (!ctx) return CAV_E_INVALID;
     if (ctx->order < 1) return fail(ctx, CAV_E_STATE, "cav_portfolio_delta_gemm: curve with jacobian first");
-    if (!ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_portfolio_delta_gemm: no portfolio uploaded");
+    if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_delta_gemm: no portfolio uploaded");
     if (!delta_dev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_delta_gemm: delta_dev is null");
     CK(cudaSetDevice(ctx->device));
     if (ctx->n_units == 0) return CAV_OK;
@@ -625,7 +634,7 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
 int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev) {
     if (!ctx) return CAV_E_INVALID;
     if (!shocked_rates || n_scen < 1 || !pnl_dev) return fail(ctx, CAV_E_INVALID, "cav_scenarios: bad arguments");
-    if (ctx->order < 0 || !ctx->unit_offsets) return fail(ctx, CAV_E_STATE, "cav_scenarios: curve and portfolio first");
+    if (ctx->order < 0 || !ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_scenarios: curve and portfolio first");
     if (!ctx->has_plan) return fail(ctx, CAV_E_STATE, "cav_scenarios: the curve was set from tables, there is no bootstrap plan");
     CK(cudaSetDevice(ctx->device));
     const size_t S = (size_t)n_scen, G = (size_t)ctx->G;

@@ -329,3 +329,20 @@ def test_small_curve_seasoned_swap_and_empty_portfolio():
     ctx.portfolio_upload(FlatPortfolio(0, 0, z64, 2, zf, zf, zi, 0, 1, zf, 0, z64, zi, None, zf))
     assert np.all(ctx.portfolio_value_host(MASK) == 0.0)
     assert Portfolio([]).compute(ALL).value is None
+
+
+def test_upload_rejects_bad_indices(ref_curves):
+    from adrates_b200.error import LibError
+    from adrates_b200.synthetic import make_book, flatten_book
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=1)
+    flat = flatten_book(make_book(curve, 50, seed=1), dedup=True)
+    flat.node = flat.node.copy()
+    flat.node[3] = 10_000                      # beyond the curve grid
+    with pytest.raises(LibError, match="node index out of range"):
+        ctx.portfolio_upload(flat)
+    with pytest.raises(LibError):
+        ctx.portfolio_value_host(_native.REQ_VALUE)     # the rejected portfolio must not be valued
+    ctx.close()
