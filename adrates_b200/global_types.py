@@ -83,4 +83,11 @@ class CollateralType(Enum):
     UNCOLLATERALIZED = 99
 
 
+def collateral_to_currency(collateral_type: CollateralType) -> CurrencyTypes:
+    """cavour/utils/global_types.py:157-190 (currency collateral only)."""
+    if collateral_type == CollateralType.UNCOLLATERALIZED or collateral_type.name not in CurrencyTypes.__members__:
+        raise ValueError(f"Cannot convert {collateral_type} to currency. Use is_currency_collateral() to check first.")
+    return CurrencyTypes[collateral_type.name]
+
+
 ONE_MILLION = 1000000

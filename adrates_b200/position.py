@@ -84,9 +84,11 @@ class Engine:
         if dtype != InstrumentTypes.OIS_SWAP:
             raise LibError(f"{dtype} not yet implemented")
         if collateral_type is not None:
-            from .global_types import CurrencyTypes
-            if CurrencyTypes[collateral_type.name] != derivative._currency:
-                raise NotImplementedError("cross-currency collateral needs the XCCY curve path (not built yet)")
+            from .global_types import collateral_to_currency
+            collateral_ccy = collateral_to_currency(collateral_type)
+            if collateral_ccy != derivative._currency:
+                from .xccy_engine import compute_ois_xccy_collateral
+                return compute_ois_xccy_collateral(derivative, self.model, request_list, collateral_ccy, self.device)
         return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
 
 

@@ -91,13 +91,17 @@ def foreign_leg_terms(swap, value_dt, xccy_curve):
 
 
 def flatten_foreign_legs(swaps, value_dt, foreign_curve, xccy_curve) -> FlatPortfolio:
+    return _flatten_stacked([foreign_leg_terms(sw, value_dt, xccy_curve) for sw in swaps], foreign_curve, xccy_curve)
+
+
+def _flatten_stacked(term_lists, foreign_curve, xccy_curve) -> FlatPortfolio:
     """One private unit per trade on the stacked grid; 6 (node, weight) pairs per term:
-    [start bracket (+), end bracket (-), pay bracket (+ on XCCY nodes, offset by the foreign grid size)]."""
+    [start bracket (+), end bracket (-), pay bracket (+ on XCCY nodes, offset by the OIS grid size)]."""
     plan_f = foreign_curve.path_b_plan()
     Gf = plan_f.n_nodes
     terms, offsets = [], [0]
-    for sw in swaps:
-        terms += foreign_leg_terms(sw, value_dt, xccy_curve)
+    for tl in term_lists:
+        terms += tl
         offsets.append(len(terms))
     n = len(terms)
     amt = np.array([t[0] for t in terms], dtype=np.float64)
@@ -115,7 +119,7 @@ def flatten_foreign_legs(swaps, value_dt, foreign_curve, xccy_curve) -> FlatPort
         a, b, wa, wb = plan_queries(tp, np.asarray(xccy_curve._times, dtype=np.float64), xccy_curve._interp_type)
         weight[:, 4], weight[:, 5], node[:, 4], node[:, 5] = wa, wb, a + Gf, b + Gf
         node[weight == 0.0] = 0
-    N = len(swaps)
+    N = len(term_lists)
     return FlatPortfolio(N, n, np.array(offsets, dtype=np.int64), 6, amt, weight.reshape(-1), node.reshape(-1),
                          N, 1, np.ones(N), N, np.arange(N + 1, dtype=np.int64), np.arange(N, dtype=np.int32), None,
                          np.ones(N))
@@ -198,5 +202,67 @@ def compute_xccy(derivatives, model, request_list, device=0) -> AnalyticsResult:
             Delta(np.array(agg_dom[1:1 + Rd]), to_tenor(dom.swap_times), ccy, d0._domestic_floating_index),
             Delta(np.array(agg_for[1:1 + Rf]), to_tenor(forn.swap_times), ccy, d0._foreign_floating_index),
             Delta(np.array(agg_bas[1:1 + Rb]), to_tenor(xc.swap_times), ccy, CurveTypes.USD_GBP_BASIS),
+        ])
+    return AnalyticsResult(value=value, risk=delta, gamma=None)
+
+
+# ======================================================================================
+# OIS discounted on an XCCY curve (cross-currency collateral)
+# ======================================================================================
+def ois_collateral_terms(swap, value_dt, fx):
+    """Engine._compute_ois_xccy_collateral (engine.py:217-345): fixed coupons discounted on the XCCY nodes,
+    floating coupons projected on the OIS engine grid and discounted on the XCCY nodes, everything divided by
+    the curve's spot_fx.  All times use the FIXED leg's day count, as the reference does (:263)."""
+    fl, ft = swap._fixed_leg, swap._float_leg
+    dc = fl._dc_type
+    t = lambda d: times_from_dates(d, value_dt, dc)  # noqa: E731
+    out = []
+    sg = _sign(fl)
+    for pay, al in zip(fl._payment_dts, fl._year_fracs):
+        tp = t(pay)
+        if tp > 0.0:
+            out.append((sg * fl._cpn * al * fl._notional / fx, None, None, tp))
+    if fl._principal != 0.0 and t(fl._payment_dts[-1]) > 0.0:
+        out.append((sg * fl._principal / fx, None, None, t(fl._payment_dts[-1])))
+    sg, N = _sign(ft), ft._notional
+    for i, pay in enumerate(ft._payment_dts):
+        tp, al = t(pay), ft._year_fracs[i]
+        if not tp >= 0.0:
+            continue
+        if al > 0:
+            out.append((sg * N / fx, t(ft._start_accrued_dts[i]), t(ft._end_accrued_dts[i]), tp))
+            out.append((-sg * N / fx, None, None, tp))
+        if ft._spread != 0.0:
+            out.append((sg * ft._spread * al * N / fx, None, None, tp))
+    return out
+
+
+def compute_ois_xccy_collateral(derivative, model, request_list, collateral_ccy, device=0) -> AnalyticsResult:
+    reqs = set(request_list)
+    if RequestTypes.GAMMA in reqs:
+        raise NotImplementedError("GAMMA not yet supported for OIS with cross-currency collateral. "
+                                  "Only VALUE and DELTA are currently implemented.")   # engine.py:491-495
+    curves = model.curves
+    ois = getattr(curves, derivative._floating_index.name)
+    name = f"{derivative._currency.name}_{collateral_ccy.name}_XCCY"
+    try:
+        xc = getattr(curves, name)
+    except AttributeError:
+        raise LibError(f"XCCY curve {name} not found in model. Required for cross-currency collateral valuation.")
+    vd = model.value_dt
+    xs = XccySession.get(ois, xc, device)
+    terms = ois_collateral_terms(derivative, vd, xc._spot_fx)
+    flat = _flatten_stacked([terms], ois, xc)
+    mask = _native.REQ_VALUE | (_native.REQ_DELTA if RequestTypes.DELTA in reqs else 0)
+    xs.ctx_for.portfolio_upload(flat)
+    agg_o = xs.ctx_for.portfolio_value_host(mask)
+    value = Valuation(float(agg_o[0]), collateral_ccy) if RequestTypes.VALUE in reqs else None
+    delta = None
+    if RequestTypes.DELTA in reqs:
+        xs.ctx_basis.portfolio_upload(flat)
+        agg_b = xs.ctx_basis.portfolio_value_host(mask)
+        delta = Risk([
+            Delta(np.array(agg_o[1:1 + xs.n_for]), to_tenor(ois.swap_times), collateral_ccy, derivative._floating_index),
+            Delta(np.array(agg_b[1:1 + xs.n_basis]), to_tenor(xc.swap_times), collateral_ccy, CurveTypes.USD_GBP_BASIS),
         ])
     return AnalyticsResult(value=value, risk=delta, gamma=None)

@@ -346,3 +346,27 @@ def test_upload_rejects_bad_indices(ref_curves):
     with pytest.raises(LibError):
         ctx.portfolio_value_host(_native.REQ_VALUE)     # the rejected portfolio must not be valued
     ctx.close()
+
+
+def test_ois_with_cross_currency_collateral_matches_reference():
+    from tests.conftest import load_golden
+    from tests.util_xccy import build_xccy_model
+    from tests.util_trades import make_trade
+    from adrates_b200 import CollateralType, CurveTypes
+    g, cg = load_golden("ref_xccy.json"), load_golden("ref_collateral.json")
+    m = build_xccy_model(g, xccy_name="GBP_USD_XCCY")
+    fx = m.curves.GBP_USD_XCCY._spot_fx
+    for t in cg["trades"]:
+        sw = make_trade(dict(t, payment_lag=0), {"name": "GBP_OIS_SONIA", "dc": "ACT_365F"})
+        res = sw.position(m).compute([RequestTypes.VALUE, RequestTypes.DELTA], collateral_type=CollateralType.USD)
+        N, T = t["notional"] / fx, float(t["tenor"][:-1])
+        assert res.value.currency.name == "USD"
+        assert abs(res.value.amount - t["value"]) <= TOL * max(abs(t["value"]), N), t["id"]
+        for key, ct in (("GBP_OIS_SONIA", CurveTypes.GBP_OIS_SONIA), ("USD_GBP_BASIS", CurveTypes.USD_GBP_BASIS)):
+            r = np.array(t["deltas"][key]["ladder"])
+            got = res.risk(ct).risk_ladder
+            assert np.max(np.abs(got - r) / np.maximum(np.abs(r), N * 1e-4 * T)) < TOL, (t["id"], key)
+        same = sw.position(m).compute([RequestTypes.VALUE], collateral_type=CollateralType.GBP)   # natural currency
+        assert same.value.currency.name == "GBP"
+        with pytest.raises(NotImplementedError):
+            sw.position(m).compute([RequestTypes.GAMMA], collateral_type=CollateralType.USD)

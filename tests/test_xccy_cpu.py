@@ -70,3 +70,29 @@ def test_flattened_xccy_trades_match_reference_engine(xg):
         for got, key in ((dl_d[0], "USD_OIS_SOFR"), (dl_f[0], "GBP_OIS_SONIA"), (dl_b[0], "USD_GBP_BASIS")):
             r = np.array(ref[key]["ladder"])
             assert np.max(np.abs(got[:len(r)] - r) / np.maximum(np.abs(r), N * 1e-4 * T)) < TOL, (t["id"], key)
+
+
+def test_ois_with_usd_collateral_matches_reference_engine(xg):
+    """Engine._compute_ois_xccy_collateral (engine.py:217-503): VALUE in collateral currency + OIS and basis ladders."""
+    from adrates_b200 import Date
+    from adrates_b200.xccy_engine import ois_collateral_terms, _flatten_stacked
+    from tests.util_trades import make_trade
+    cg = load_golden("ref_collateral.json")
+    m = build_xccy_model(xg, xccy_name="GBP_USD_XCCY")
+    ois, xc = m.curves.GBP_OIS_SONIA, m.curves.GBP_USD_XCCY
+    plan = orc.plan_path_b(ois.swap_times, ois.year_fracs)
+    d_o, J_o, _ = orc.bootstrap_tables(ois.swap_rates, plan)
+    d_s = np.concatenate([d_o, xc._dfs])
+    Go, Gx, Rb = len(d_o), len(xc._dfs), xc._jac_basis.shape[1]
+    cvspec = {"name": "GBP_OIS_SONIA", "dc": "ACT_365F"}
+    for t in cg["trades"]:
+        sw = make_trade(dict(t, payment_lag=0), cvspec)
+        flat = _flatten_stacked([ois_collateral_terms(sw, m.value_dt, xc._spot_fx)], ois, xc)
+        pv, dl_o, _ = eval_flat(flat, d_s, np.vstack([J_o, np.zeros((Gx, 32))]), np.zeros((Go + Gx, 32, 32)))
+        _, dl_b, _ = eval_flat(flat, d_s, np.vstack([np.zeros((Go, Rb)), xc._jac_basis]), np.zeros((Go + Gx, Rb, Rb)))
+        N, T = t["notional"] / xc._spot_fx, float(t["tenor"][:-1])
+        assert t["currency"] == "USD"
+        assert abs(pv[0] - t["value"]) <= TOL * max(abs(t["value"]), N), t["id"]
+        for got, key in ((dl_o[0], "GBP_OIS_SONIA"), (dl_b[0], "USD_GBP_BASIS")):
+            r = np.array(t["deltas"][key]["ladder"])
+            assert np.max(np.abs(got[:len(r)] - r) / np.maximum(np.abs(r), N * 1e-4 * T)) < TOL, (t["id"], key)

@@ -4,7 +4,7 @@ from adrates_b200 import (Date, DayCountTypes, FrequencyTypes, BusDayAdjustTypes
 from adrates_b200.models import Model
 
 
-def build_xccy_model(g, ois_interp=InterpTypes.LINEAR_ZERO_RATES):
+def build_xccy_model(g, ois_interp=InterpTypes.LINEAR_ZERO_RATES, xccy_name="GBP_USD_BASIS"):
     vd = Date(*g["value_dt"])
     m = Model(vd)
     for name, px, dc in (("GBP_OIS_SONIA", g["gbp_px"], DayCountTypes.ACT_365F),
@@ -13,7 +13,7 @@ def build_xccy_model(g, ois_interp=InterpTypes.LINEAR_ZERO_RATES):
                       fixed_dcc_type=dc, fixed_freq_type=FrequencyTypes.ANNUAL, float_freq_type=FrequencyTypes.ANNUAL,
                       float_dc_type=dc, bus_day_type=BusDayAdjustTypes.MODIFIED_FOLLOWING,
                       interp_type=ois_interp)
-    m.build_xccy_curve(name="GBP_USD_BASIS", domestic_curve_name="USD_OIS_SOFR", foreign_curve_name="GBP_OIS_SONIA",
+    m.build_xccy_curve(name=xccy_name, domestic_curve_name="USD_OIS_SOFR", foreign_curve_name="GBP_OIS_SONIA",
                        basis_spreads=g["basis_bps"], tenor_list=g["basis_tenors"], spot_fx=g["spot_fx"],
                        domestic_freq_type=FrequencyTypes.ANNUAL, foreign_freq_type=FrequencyTypes.QUARTERLY)
     return m
