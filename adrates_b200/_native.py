@@ -34,6 +34,7 @@ _SIGS = {
     "cav_curve_build": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "cav_curve_read": (C.c_int, [_P, _P, _P, _P]),
     "cav_curve_set_tables": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
+    "cav_curve_rebuild_dev": (C.c_int, [_P, _P]),
     "cav_df_ad": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_portfolio_upload": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P,
                                        C.c_int64, _P, _P, _P, _P]),
@@ -137,6 +138,9 @@ class Context:
         self._ck(self._dll.cav_curve_build(self._h, int(interp_method), _ptr(r), r.shape[0], _ptr(t), _ptr(a),
                                            _ptr(s), _ptr(p), t.shape[0], int(order)))
         self._G, self._R = t.shape[0], r.shape[0]
+
+    def curve_rebuild_dev(self, swap_rates_dev):
+        self._ck(self._dll.cav_curve_rebuild_dev(self._h, _ptr(swap_rates_dev)))
 
     def curve_set_tables(self, dfs, jac=None, hess=None):
         d = _f64(dfs)

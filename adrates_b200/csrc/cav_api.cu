@@ -333,6 +333,19 @@ int cav_curve_build(cav_ctx* ctx, int interp_method, const double* swap_rates, i
     return CAV_OK;
 }
 
+int cav_curve_rebuild_dev(cav_ctx* ctx, const double* swap_rates_dev) {
+    if (!ctx || !swap_rates_dev) return CAV_E_INVALID;
+    if (ctx->order < 0 || !ctx->has_plan) return fail(ctx, CAV_E_STATE, "cav_curve_rebuild_dev: build a curve from a plan first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->rates, swap_rates_dev, sizeof(double) * ctx->R, cudaMemcpyDeviceToDevice, ctx->stream));
+    k_bootstrap<<<1, 1024, 0, ctx->stream>>>(ctx->G, ctx->order, ctx->rates, ctx->node_acc, ctx->node_swap, ctx->node_prev,
+                                             ctx->df, ctx->P, ctx->jac, ctx->dP, ctx->hess, ctx->d2P);
+    k_tables<<<ctx->G, 1024, 0, ctx->stream>>>(ctx->order, ctx->df, ctx->jac, ctx->hess, ctx->L, ctx->g, ctx->Hf, ctx->Cf);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return CAV_OK;
+}
+
 int cav_curve_set_tables(cav_ctx* ctx, const double* dfs, const double* jac, const double* hess, int n_nodes,
                          int n_rates) {
     if (!ctx) return CAV_E_INVALID;

@@ -82,6 +82,11 @@ int cav_curve_build(cav_ctx* ctx, int interp_method,
  * hess is [G][n_rates][n_rates] - the shapes of the reference cache (engine.py:2405-2410) */
 int cav_curve_read(cav_ctx* ctx, double* dfs, double* jac, double* hess);
 
+/* Re-bootstrap the current plan from par rates that already live on the device (asynchronous on the
+ * context stream): what a jax.ffi handler calls when the rates are a traced device buffer, and what a
+ * scenario loop with full Greeks per scenario uses (Model.scenario, models.py:507-557). */
+int cav_curve_rebuild_dev(cav_ctx* ctx, const double* swap_rates_dev);
+
 /* Set the curve tables directly instead of bootstrapping them: dfs[G], jac[G][n_rates] (may be
  * NULL), hess[G][n_rates][n_rates] (may be NULL).  Used for curves whose bootstrap lives on the
  * host - XccyCurve._times/_dfs/_jac_basis (cavour/trades/rates/xccy_curve.py:529-703) - and for

@@ -370,3 +370,21 @@ def test_ois_with_cross_currency_collateral_matches_reference():
         assert same.value.currency.name == "GBP"
         with pytest.raises(NotImplementedError):
             sw.position(m).compute([RequestTypes.GAMMA], collateral_type=CollateralType.USD)
+
+
+def test_curve_rebuild_from_device_rates(ref_curves):
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    shocked = np.array(curve.swap_rates) + 1e-3
+    rd = torch.tensor(shocked, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.curve_rebuild_dev(rd.data_ptr())
+    d1, J1, H1 = ctx.curve_read()
+    ctx.curve_build(curve._interp_type.value, shocked, curve.path_b_plan(), order=2)
+    d2, J2, H2 = ctx.curve_read()
+    assert np.array_equal(d1, d2) and np.array_equal(J1, J2) and np.array_equal(H1, H2)
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    assert np.max(np.abs(d1 - orc.bootstrap_dfs(shocked, plan))) < 4e-16
+    ctx.close()
