@@ -38,6 +38,7 @@ _SIGS = {
     "cav_df_ad": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_portfolio_upload": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P,
                                        C.c_int64, _P, _P, _P, _P]),
+    "cav_portfolio_set_tiles": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, _P]),
     "cav_portfolio_value": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "cav_portfolio_value_host": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "cav_portfolio_delta_gemm": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
@@ -172,6 +173,18 @@ class Context:
             _ptr(flat.weight), _ptr(flat.node), flat.n_trades, flat.n_comp, _ptr(flat.comp_weight), flat.n_groups,
             _ptr(flat.group_offsets), _ptr(flat.group_units), _ptr(flat.out_index), _ptr(flat.unit_weight)))
         self._n_trades = flat.n_trades
+        tp = getattr(flat, "tile_plan", None)
+        if tp is not None:
+            self.portfolio_set_tiles(tp)
+
+    def portfolio_set_tiles(self, tp):
+        """tp: adrates_b200.tiles.TilePlan (all units covered)."""
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)  # noqa: E731
+        arrs = [i32(tp.tile_units), i32(tp.tile_kstart), i32(tp.tile_kcount), i32(tp.k_row), i32(tp.k_pos),
+                i32(tp.k_coef), i32(tp.pairs)]
+        self._ck(self._dll.cav_portfolio_set_tiles(self._h, tp.n_tiles, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
+                                                   arrs[3].shape[0], _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]),
+                                                   arrs[6].shape[0] // 2, _ptr(arrs[6])))
 
     def portfolio_value(self, mask: int, pv_dev=None, delta_dev=None, gamma_dev=None, agg_dev=None):
         self._ck(self._dll.cav_portfolio_value(self._h, mask, _ptr(pv_dev), _ptr(delta_dev), _ptr(gamma_dev),

@@ -57,6 +57,12 @@ struct cav_ctx {
     int* row_units = nullptr;
     double* row_weight = nullptr;
     bool row_tables_valid = false;
+    // tensor-core units path (tile plan + symmetric tables)
+    int n_tiles = 0, n_pair_rows = 0, tiles_max_k = 0;
+    int64_t n_krows = 0;
+    int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *k_row = nullptr, *k_pos = nullptr, *k_coef = nullptr, *pairs = nullptr;
+    double* Tsym = nullptr;
+    bool tiles_valid = false, tsym_valid = false;
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
     double *sc_rates = nullptr, *sc_P = nullptr, *sc_L = nullptr, *sc_upv = nullptr;   // scenario scratch (grow-only)
     int64_t* out_index = nullptr;
@@ -217,7 +223,8 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
-    dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
+    dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->tile_units); dev_free(ctx, &ctx->tile_kstart); dev_free(ctx, &ctx->tile_kcount);
+    dev_free(ctx, &ctx->k_row); dev_free(ctx, &ctx->k_pos); dev_free(ctx, &ctx->k_coef); dev_free(ctx, &ctx->pairs); dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
     cudaEventDestroy(ctx->ev0);
@@ -330,6 +337,7 @@ int cav_curve_build(cav_ctx* ctx, int interp_method, const double* swap_rates, i
     ctx->interp = interp_method;
     ctx->order = order;
     ctx->has_plan = true;
+    ctx->tsym_valid = false;
     return CAV_OK;
 }
 
@@ -342,6 +350,7 @@ int cav_curve_rebuild_dev(cav_ctx* ctx, const double* swap_rates_dev) {
                                              ctx->df, ctx->P, ctx->jac, ctx->dP, ctx->hess, ctx->d2P);
     k_tables<<<ctx->G, 1024, 0, ctx->stream>>>(ctx->order, ctx->df, ctx->jac, ctx->hess, ctx->L, ctx->g, ctx->Hf, ctx->Cf);
     ctx->launches += 2;
+    ctx->tsym_valid = false;
     CK(cudaGetLastError());
     return CAV_OK;
 }
@@ -383,6 +392,7 @@ int cav_curve_set_tables(cav_ctx* ctx, const double* dfs, const double* jac, con
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->G = n_nodes; ctx->R = n_rates; ctx->order = order; ctx->interp = 0;
     ctx->has_plan = false;
+    ctx->tsym_valid = false;
     return CAV_OK;
 }
 
@@ -507,6 +517,60 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     ctx->n_units = n_units; ctx->n_terms = n_terms; ctx->n_trades = n_trades; ctx->n_groups = n_groups;
     ctx->n_pairs = n_pairs; ctx->n_comp = n_comp; ctx->direct = direct;
     ctx->row_tables_valid = false;
+    ctx->tiles_valid = false;
+    return CAV_OK;
+}
+
+int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units, const int32_t* tile_kstart,
+                            const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
+                            const int32_t* k_coef, int n_pair_rows, const int32_t* pairs) {
+    if (!ctx) return CAV_E_INVALID;
+    if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_set_tiles: upload the portfolio first");
+    if (ctx->n_pairs != 2) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: single-DF terms (n_pairs == 2) only");
+    if (n_tiles < 0 || n_krows < 0 || n_pair_rows < 0 || (n_tiles && (!tile_units || !tile_kstart || !tile_kcount)) ||
+        (n_krows && (!k_row || !k_pos || !k_coef)) || (n_pair_rows && !pairs))
+        return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: null pointer or negative size");
+    const int n_rows = 3 * ctx->G + n_pair_rows;
+    int64_t covered = 0;
+    for (int64_t i = 0; i < (int64_t)n_tiles * GT_TM; ++i) {
+        if (tile_units[i] < -1 || tile_units[i] >= ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: unit id out of range");
+        covered += tile_units[i] >= 0;
+    }
+    if (covered != ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: every unit must belong to exactly one tile");
+    int max_k = 0;
+    for (int t = 0; t < n_tiles; ++t) {
+        if (tile_kstart[t] < 0 || tile_kcount[t] < 0 || (int64_t)tile_kstart[t] + tile_kcount[t] > n_krows)
+            return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K range out of bounds");
+        max_k = tile_kcount[t] > max_k ? tile_kcount[t] : max_k;
+    }
+    for (int64_t k = 0; k < n_krows; ++k)
+        if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_coef[k] < 0 || k_coef[k] > 5)
+            return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: bad K row");
+    for (int i = 0; i < 2 * n_pair_rows; ++i)
+        if (pairs[i] < 0 || pairs[i] >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: pair node out of range");
+    CK(cudaSetDevice(ctx->device));
+    CK(upload(ctx, &ctx->tile_units, (const int*)tile_units, (size_t)n_tiles * GT_TM));
+    CK(upload(ctx, &ctx->tile_kstart, (const int*)tile_kstart, (size_t)n_tiles));
+    CK(upload(ctx, &ctx->tile_kcount, (const int*)tile_kcount, (size_t)n_tiles));
+    CK(upload(ctx, &ctx->k_row, (const int*)k_row, (size_t)n_krows));
+    CK(upload(ctx, &ctx->k_pos, (const int*)k_pos, (size_t)n_krows));
+    CK(upload(ctx, &ctx->k_coef, (const int*)k_coef, (size_t)n_krows));
+    CK(upload(ctx, &ctx->pairs, (const int*)pairs, (size_t)2 * n_pair_rows));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_tiles = n_tiles; ctx->n_krows = n_krows; ctx->n_pair_rows = n_pair_rows; ctx->tiles_max_k = max_k;
+    ctx->tiles_valid = true; ctx->tsym_valid = false;
+    return CAV_OK;
+}
+
+static int build_sym_tables(cav_ctx* ctx) {
+    const size_t rows = (size_t)3 * ctx->G + ctx->n_pair_rows + 1;
+    CK(dev_alloc(ctx, &ctx->Tsym, rows * GT_NC));
+    k_sym_tables<<<3 * ctx->G, GT_NC, 0, ctx->stream>>>(ctx->G, ctx->g, ctx->Hf, ctx->Cf, ctx->Tsym);
+    k_pair_tables<<<ctx->n_pair_rows + 1, GT_NC, 0, ctx->stream>>>(ctx->n_pair_rows, ctx->pairs, ctx->g,
+                                                                    ctx->Tsym + (size_t)3 * ctx->G * GT_NC);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    ctx->tsym_valid = true;
     return CAV_OK;
 }
 
@@ -528,8 +592,12 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         return CAV_OK;
     }
     const bool need_agg = agg_dev || agg_host;
+    static int gemm_mode = [] { const char* e = std::getenv("CAV_UNITS_GEMM"); return e ? std::atoi(e) : 1; }();
+    const bool use_gemm = want_g && ctx->tiles_valid && gemm_mode != 0 && ctx->n_tiles > 0;
+    if (use_gemm && !ctx->tsym_valid) { int rc = build_sym_tables(ctx); if (rc) return rc; }
     int64_t rows = 0;
-    const int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
+    int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
+    if (use_gemm) { grid = ctx->n_tiles < ctx->sm_count ? ctx->n_tiles : ctx->sm_count; rows = grid; }
     if (need_agg) CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
     UnitsArgs a;
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
@@ -551,7 +619,19 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         a.out_gamma = gamma ? ctx->u_gamma : nullptr;
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[0], ctx->stream));
-    if (use_tile_kernel(ctx, want_g)) {
+    if (use_gemm) {
+        GemmArgs ga;
+        ga.n_tiles = ctx->n_tiles; ga.tile_units = ctx->tile_units; ga.tile_kstart = ctx->tile_kstart;
+        ga.tile_kcount = ctx->tile_kcount; ga.k_row = ctx->k_row; ga.k_pos = ctx->k_pos; ga.k_coef = ctx->k_coef;
+        ga.T = ctx->Tsym; ga.zero_row = 3 * ctx->G + ctx->n_pair_rows;
+        ga.unit_offsets = a.unit_offsets; ga.amt = a.amt; ga.weight = a.weight; ga.node = a.node; ga.L = a.L;
+        ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
+        ga.out_gamma = a.out_gamma; ga.partials = a.partials;
+        const size_t smem = (size_t)(GT_TM * GT_LDA + 16 * GT_LDS + GT_TM) * sizeof(double) + (3 * GT_KC + GT_TM) * sizeof(int);
+        CK(cudaFuncSetAttribute(k_units_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_units_gemm<<<grid, 256, smem, ctx->stream>>>(ga);
+        ctx->launches++;
+    } else if (use_tile_kernel(ctx, want_g)) {
         const size_t smem = a.partials ? (size_t)2 * CAV_NOUT * sizeof(double) : 0;
         // static (45 KB) + dynamic shared memory exceeds the 48 KB default: opt in
         CK(cudaFuncSetAttribute(k_units_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CAV_NOUT * (int)sizeof(double)));

@@ -455,6 +455,222 @@ k_units_tile(UnitsArgs A)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Tensor-core units kernel.  For units that bracket the same node pairs term by term,
+//   [gamma (528 packed lower-triangle entries) | delta (32)] [units x 560] = A[units x K] . B[K x 560]
+// where the K rows of B come from per-curve symmetric tables (built by k_sym_tables / k_pair_tables)
+//   H_n = hess(ln d_n)|g_n,  C_n = (H_n + g_n g_n^T)|g_n,  G_nn = g_n g_n^T|0,  G_ab = (g_a g_b^T + g_b g_a^T)|0
+// and only the coefficients A (p, p w0, p w1, p w0^2, p w1^2, p w0 w1) depend on the unit
+// (adrates_b200/tiles.py).  One CTA = one tile of 32 units x all 576 padded columns, FP64 DMMA
+// (mma.sync.m8n8k4): warp (mg, ng) owns m-tiles {2mg, 2mg+1} x n-tiles [18 ng, 18 ng + 18).  A is built
+// in shared memory (K chunked by 256), B fragments are read straight from the L2-resident tables
+// (each table row is read once per tile, not once per unit), the epilogue stages 8 units at a time in
+// shared memory and writes full symmetric 32x32 rows with 32-byte stores.
+// ------------------------------------------------------------------------------------------
+#define GT_TM 32
+#define GT_NC 576
+#define GT_NPACK 528
+#define GT_KC 256
+#define GT_LDA 268
+#define GT_LDS 584
+
+__device__ __forceinline__ int gt_packed(int j, int k) { return j >= k ? j * (j + 1) / 2 + k : k * (k + 1) / 2 + j; }
+
+// rows 0..G-1: H_n | g_n ; G..2G-1: C_n | g_n ; 2G..3G-1: g_n g_n^T | 0   (one CTA per row)
+__global__ void __launch_bounds__(GT_NC)
+k_sym_tables(int G, const double* __restrict__ g, const double* __restrict__ Hf, const double* __restrict__ Cf,
+             double* T)
+{
+    const int row = blockIdx.x, e = threadIdx.x;
+    const int type = row / G, n = row % G;
+    double v = 0.0;
+    if (e < GT_NPACK) {
+        int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (j * (j + 1) / 2 > e) --j;
+        while ((j + 1) * (j + 2) / 2 <= e) ++j;
+        const int k = e - j * (j + 1) / 2;
+        if (type == 0) v = Hf[(size_t)n * CAV_RR + j * CAV_RW + k];
+        else if (type == 1) v = Cf[(size_t)n * CAV_RR + j * CAV_RW + k];
+        else v = g[n * CAV_RW + j] * g[n * CAV_RW + k];
+    } else if (e < GT_NPACK + CAV_RW) {
+        if (type < 2) v = g[n * CAV_RW + (e - GT_NPACK)];
+    }
+    T[(size_t)row * GT_NC + e] = v;
+}
+
+// rows 3G + i: g_a g_b^T + g_b g_a^T | 0 for the node pairs the portfolio brackets; last row = zeros
+__global__ void __launch_bounds__(GT_NC)
+k_pair_tables(int n_pairs, const int* __restrict__ pairs, const double* __restrict__ g, double* Trows)
+{
+    const int i = blockIdx.x, e = threadIdx.x;
+    double v = 0.0;
+    if (i < n_pairs && e < GT_NPACK) {
+        int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (j * (j + 1) / 2 > e) --j;
+        while ((j + 1) * (j + 2) / 2 <= e) ++j;
+        const int k = e - j * (j + 1) / 2;
+        const int a = pairs[2 * i], b = pairs[2 * i + 1];
+        v = g[a * CAV_RW + j] * g[b * CAV_RW + k] + g[b * CAV_RW + j] * g[a * CAV_RW + k];
+    }
+    Trows[(size_t)i * GT_NC + e] = v;
+}
+
+struct GemmArgs {
+    int n_tiles;
+    const int* tile_units;     // [n_tiles][32], -1 = padding
+    const int* tile_kstart;
+    const int* tile_kcount;
+    const int* k_row;
+    const int* k_pos;
+    const int* k_coef;
+    const double* T;           // symmetric tables [rows][576]
+    int zero_row;
+    const int64_t* unit_offsets;
+    const double* amt;
+    const double* weight;      // [n_terms][2]
+    const int* node;           // [n_terms][2]
+    const double* L;
+    const double* unit_weight;
+    const int64_t* out_index;
+    double* out_pv;
+    double* out_delta;
+    double* out_gamma;
+    double* partials;          // [gridDim.x][1057] or null
+};
+
+__global__ void __launch_bounds__(256, 1)
+k_units_gemm(GemmArgs a)
+{
+    extern __shared__ double smem[];
+    double* sA = smem;                                   // [32][GT_LDA]
+    double* sStage = sA + GT_TM * GT_LDA;                // [2][8][GT_LDS]
+    double* sPv = sStage + 2 * 8 * GT_LDS;               // [32]
+    int* sRow = reinterpret_cast<int*>(sPv + GT_TM);     // [GT_KC]
+    int* sPos = sRow + GT_KC;
+    int* sCoef = sPos + GT_KC;
+    int* sUnit = sCoef + GT_KC;                          // [32]
+
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int mg = wib >> 2, ng = wib & 3;
+    const int ar = lane >> 2, ac = lane & 3;
+    const int oj = tid >> 3, ok4 = (tid & 7) * 4;        // epilogue: this thread owns gamma entries (oj, ok4..ok4+3)
+    int pk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) pk[q] = gt_packed(oj, ok4 + q);
+    double tg[4] = {0.0, 0.0, 0.0, 0.0}, td = 0.0, tp = 0.0;
+
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int K = a.tile_kcount[tile], ks = a.tile_kstart[tile];
+        __syncthreads();
+        if (tid < GT_TM) sUnit[tid] = a.tile_units[tile * GT_TM + tid];
+        __syncthreads();
+        // unit PVs: 8 threads per unit
+        {
+            const int u = tid >> 3, sub = tid & 7;
+            const int uid = sUnit[u];
+            double pv = 0.0;
+            if (uid >= 0) {
+                for (int64_t i = a.unit_offsets[uid] + sub; i < a.unit_offsets[uid + 1]; i += 8) {
+                    const double2 w = reinterpret_cast<const double2*>(a.weight)[i];
+                    const int2 n = reinterpret_cast<const int2*>(a.node)[i];
+                    pv += a.amt[i] * exp(w.x * a.L[n.x] + w.y * a.L[n.y]);
+                }
+            }
+            pv += __shfl_xor_sync(0xffffffffu, pv, 1);
+            pv += __shfl_xor_sync(0xffffffffu, pv, 2);
+            pv += __shfl_xor_sync(0xffffffffu, pv, 4);
+            if (sub == 0) sPv[u] = pv;
+        }
+        double c[2][18][2];
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < 18; ++n) c[m][n][0] = c[m][n][1] = 0.0;
+
+        for (int c0 = 0; c0 < K; c0 += GT_KC) {
+            const int kc = (K - c0) < GT_KC ? (K - c0) : GT_KC;
+            const int kc4 = (kc + 3) & ~3;
+            __syncthreads();                             // previous chunk's A fully consumed
+            for (int k = tid; k < kc4; k += 256) {
+                sRow[k] = (k < kc) ? a.k_row[ks + c0 + k] : a.zero_row;
+                sPos[k] = (k < kc) ? a.k_pos[ks + c0 + k] : 0;
+                sCoef[k] = (k < kc) ? a.k_coef[ks + c0 + k] : -1;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < GT_TM * kc4; idx += 256) {
+                const int u = idx / kc4, k = idx - u * kc4;
+                const int uid = sUnit[u];
+                const int cf = sCoef[k];
+                double v = 0.0;
+                if (uid >= 0 && cf >= 0) {
+                    const int64_t i = a.unit_offsets[uid] + sPos[k];
+                    const double2 w = reinterpret_cast<const double2*>(a.weight)[i];
+                    const int2 n = reinterpret_cast<const int2*>(a.node)[i];
+                    const double p = a.amt[i] * exp(w.x * a.L[n.x] + w.y * a.L[n.y]);
+                    v = cf == 0 ? p : cf == 1 ? p * w.x : cf == 2 ? p * w.y : cf == 3 ? p * w.x * w.x
+                      : cf == 4 ? p * w.y * w.y : p * w.x * w.y;
+                }
+                sA[u * GT_LDA + k] = v;
+            }
+            __syncthreads();
+            const double* A0 = sA + (mg * 16 + ar) * GT_LDA + ac;
+            const double* A1 = A0 + 8 * GT_LDA;
+            for (int k = 0; k < kc4; k += 4) {
+                const double a0 = A0[k], a1 = A1[k];
+                const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC + ng * 144 + ar;
+#pragma unroll
+                for (int n = 0; n < 18; ++n) {
+                    const double b = __ldg(rowp + n * 8);
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(b));
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1), "d"(b));
+                }
+            }
+        }
+        // ---- epilogue: stage 8 units per m-group, expand to full symmetric rows ----
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            __syncthreads();                             // stage buffers free
+            double* st = sStage + (size_t)(mg * 8 + ar) * GT_LDS + ng * 144 + 2 * ac;
+#pragma unroll
+            for (int n = 0; n < 18; ++n)
+                *reinterpret_cast<double2*>(st + n * 8) = make_double2(c[mt][n][0], c[mt][n][1]);
+            __syncthreads();
+            for (int s = 0; s < 16; ++s) {
+                const int u = (s >> 3) * 16 + mt * 8 + (s & 7);
+                const int uid = sUnit[u];
+                if (uid < 0) continue;
+                const double* row_s = sStage + (size_t)s * GT_LDS;
+                const int64_t row = a.out_index ? a.out_index[uid] : uid;
+                const double W = a.unit_weight ? a.unit_weight[uid] : 1.0;
+                const double g0 = row_s[pk[0]], g1 = row_s[pk[1]], g2 = row_s[pk[2]], g3 = row_s[pk[3]];
+                if (a.out_gamma) {
+                    double* dst = a.out_gamma + (size_t)row * CAV_RR + oj * CAV_RW + ok4;
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
+                }
+                tg[0] += W * g0; tg[1] += W * g1; tg[2] += W * g2; tg[3] += W * g3;
+                if (tid < CAV_RW) {
+                    const double dl = row_s[GT_NPACK + tid];
+                    if (a.out_delta) a.out_delta[(size_t)row * CAV_RW + tid] = dl;
+                    td += W * dl;
+                }
+                if (tid == 32) {
+                    if (a.out_pv) a.out_pv[row] = sPv[u];
+                    tp += W * sPv[u];
+                }
+            }
+        }
+    }
+    if (a.partials) {
+        double* P = a.partials + (size_t)blockIdx.x * CAV_NOUT;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) P[33 + oj * CAV_RW + ok4 + q] = tg[q];
+        if (tid < CAV_RW) P[1 + tid] = td;
+        if (tid == 32) P[0] = tp;
+    }
+}
+
 // totals[e] = sum_rows partials[row][e]; one warp per entry, lane-strided partial sums combined
 // in a fixed butterfly order (bitwise reproducible for a given grid)
 __global__ void __launch_bounds__(256)

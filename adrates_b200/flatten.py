@@ -51,11 +51,24 @@ class FlatPortfolio:
     group_units: np.ndarray       # i32 [n_groups*n_comp]
     out_index: Optional[np.ndarray]   # int64 [n_trades] or None
     unit_weight: np.ndarray       # f64 [n_units]
+    tile_plan: Optional[object] = None   # adrates_b200.tiles.TilePlan: enables the tensor-core Greeks kernel
 
     def h2d_bytes(self) -> int:
         arrs = [self.unit_offsets, self.amt, self.weight, self.node, self.comp_weight, self.group_offsets,
                 self.group_units, self.unit_weight] + ([self.out_index] if self.out_index is not None else [])
+        tp = self.tile_plan
+        if tp is not None:
+            arrs += [tp.tile_units, tp.tile_kstart, tp.tile_kcount, tp.k_row, tp.k_pos, tp.k_coef, tp.pairs]
         return int(sum(a.nbytes for a in arrs))
+
+    def with_tiles(self, n_nodes: int) -> "FlatPortfolio":
+        """Attach a tile plan (adrates_b200/tiles.py) when every unit consists of single-DF terms."""
+        from .tiles import plan_tiles
+        if self.n_pairs == 2 and self.n_units > 0:
+            tp = plan_tiles(self, n_nodes)
+            if len(tp.leftover_units) == 0:
+                self.tile_plan = tp
+        return self
 
 
 # a DF query list: times on the curve, each with an exponent (+1 / -1) inside one term

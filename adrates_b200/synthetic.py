@@ -67,7 +67,13 @@ def make_book(curve: OISCurve, n_trades: int, seed: int = 20240430, max_offset_b
     return Book(curve, schedules, sched.astype(np.int32), coupon, notional, fixed_sign, np.zeros(n_trades))
 
 
-def flatten_book(book: Book, dedup: bool = True, max_group: int = 256, sort_units: bool = True) -> FlatPortfolio:
+def flatten_book(book: Book, dedup: bool = True, max_group: int = 256, sort_units: bool = True,
+                 tiles: bool = True) -> FlatPortfolio:
+    flat = _flatten_book(book, dedup, max_group, sort_units)
+    return flat.with_tiles(book.curve.path_b_plan().n_nodes) if tiles else flat
+
+
+def _flatten_book(book: Book, dedup: bool, max_group: int, sort_units: bool) -> FlatPortfolio:
     vd = book.curve._value_dt
     comps = [ois_components(s, vd) for s in book.schedules]   # unit-notional, unit-coupon, PAY fixed
     for c in comps:

@@ -1,0 +1,124 @@
+"""Tile planner for the tensor-core units kernel (k_units_gemm).
+
+The Greeks of a unit are a linear combination of curve-only matrices.  With v = w0 g_a + w1 g_b and
+H_n = hess(ln d_n), a bracketed term contributes
+
+    p (v v^T + w0 H_a + w1 H_b) = p w0 H_a + p w1 H_b + p w0^2 G_aa + p w1^2 G_bb + p w0 w1 G_ab,
+    G_aa = g_a g_a^T,  G_ab = g_a g_b^T + g_b g_a^T                       (a grid snap: p (H_a + G_aa) = p C_a)
+
+so for units that bracket the same node pairs position by position ("same signature"),
+gamma[units x 528 packed entries | 32 delta columns] = A[units x K] . B[K x 560] with B rows taken from
+per-curve symmetric tables and only the K coefficients A depending on the unit.  That is a dense FP64 GEMM
+per tile of 32 units, which the kernel runs on the tensor pipe (mma.sync.m8n8k4.f64); each table row is read
+once per tile instead of once per unit.
+
+This module groups units by signature, cuts the groups into tiles of TM units and emits, per group, the list
+of K rows: (table row id, term position, coefficient kind).  Units whose terms are not single-DF brackets
+(6-pair product terms) are left to the generic warp-per-unit kernel.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+TM = 32            # units per tile (four m8 tiles)
+NCOL = 576         # padded row length: 528 packed gamma entries + 32 delta columns + 16 zeros
+NPACK = 528
+
+# coefficient kinds
+COEF_P, COEF_PW0, COEF_PW1, COEF_PW0SQ, COEF_PW1SQ, COEF_PW0W1 = range(6)
+
+
+@dataclass
+class TilePlan:
+    n_tiles: int
+    tile_units: np.ndarray    # i32 [n_tiles*TM], -1 = padding
+    tile_kstart: np.ndarray   # i32 [n_tiles] first K row of the tile's group
+    tile_kcount: np.ndarray   # i32 [n_tiles]
+    tile_npos: np.ndarray     # i32 [n_tiles] terms per unit in this tile
+    k_row: np.ndarray         # i32 [sum K over groups] table row id
+    k_pos: np.ndarray         # i32 term position the coefficient comes from
+    k_coef: np.ndarray        # i32 coefficient kind
+    pairs: np.ndarray         # i32 [n_pair_rows*2] (a, b) node pairs that need a G_ab row
+    n_table_rows: int         # 3*G + n_pair_rows (+1 zero row appended by the library)
+    leftover_units: np.ndarray  # i32 units not covered by tiles (generic kernel)
+
+    @property
+    def max_k(self) -> int:
+        return int(self.tile_kcount.max()) if self.n_tiles else 0
+
+
+def row_H(n, G):
+    return n
+
+
+def row_C(n, G):
+    return G + n
+
+
+def row_Gnn(n, G):
+    return 2 * G + n
+
+
+def plan_tiles(flat, G: int, min_group: int = 1) -> TilePlan:
+    """flat: FlatPortfolio with n_pairs == 2.  G: number of curve nodes."""
+    if flat.n_pairs != 2:
+        raise ValueError("tile planner handles single-DF terms only")
+    w = flat.weight.reshape(-1, 2)
+    nd = flat.node.reshape(-1, 2).astype(np.int64)
+    off = flat.unit_offsets
+    kind = np.where((w[:, 0] == 1.0) & (w[:, 1] == 0.0), 0, np.where(w[:, 1] == 0.0, 1, 2)).astype(np.int64)
+    a = nd[:, 0]
+    b = np.where(kind == 2, nd[:, 1], 0)
+    key = (kind << 40) | (a << 20) | b
+    groups = {}
+    for u in range(flat.n_units):
+        groups.setdefault(key[off[u]:off[u + 1]].tobytes(), []).append(u)
+    pair_index = {}
+    k_row, k_pos, k_coef = [], [], []
+    t_units, t_kstart, t_kcount, t_npos = [], [], [], []
+    leftover = []
+    for sig, units in groups.items():
+        if len(units) < min_group:
+            leftover += units
+            continue
+        ks = np.frombuffer(sig, dtype=np.int64)
+        kstart = len(k_row)
+        for j, kk in enumerate(ks):
+            knd, na, nb = int(kk >> 40), int((kk >> 20) & 0xFFFFF), int(kk & 0xFFFFF)
+            if knd == 0:
+                k_row.append(row_C(na, G)); k_pos.append(j); k_coef.append(COEF_P)
+            else:
+                k_row += [row_H(na, G), row_Gnn(na, G)]
+                k_pos += [j, j]
+                k_coef += [COEF_PW0, COEF_PW0SQ]
+                if knd == 2:
+                    pi = pair_index.setdefault((na, nb), len(pair_index))
+                    k_row += [row_H(nb, G), row_Gnn(nb, G), 3 * G + pi]
+                    k_pos += [j, j, j]
+                    k_coef += [COEF_PW1, COEF_PW1SQ, COEF_PW0W1]
+        kcount = len(k_row) - kstart
+        ua = np.array(units, dtype=np.int32)
+        pad = (-len(ua)) % TM
+        ua = np.concatenate([ua, np.full(pad, -1, dtype=np.int32)]).reshape(-1, TM)
+        for row in ua:
+            t_units.append(row)
+            t_kstart.append(kstart)
+            t_kcount.append(kcount)
+            t_npos.append(len(ks))
+    n_tiles = len(t_units)
+    pairs = np.zeros((len(pair_index), 2), dtype=np.int32)
+    for (na, nb), pi in pair_index.items():
+        pairs[pi] = (na, nb)
+    return TilePlan(
+        n_tiles,
+        np.concatenate(t_units).astype(np.int32) if n_tiles else np.zeros(0, dtype=np.int32),
+        np.array(t_kstart, dtype=np.int32), np.array(t_kcount, dtype=np.int32), np.array(t_npos, dtype=np.int32),
+        np.array(k_row, dtype=np.int32), np.array(k_pos, dtype=np.int32), np.array(k_coef, dtype=np.int32),
+        pairs.reshape(-1), 3 * G + len(pair_index), np.array(leftover, dtype=np.int32))
+
+
+def packed_index(j: int, k: int) -> int:
+    j, k = (j, k) if j >= k else (k, j)
+    return j * (j + 1) // 2 + k

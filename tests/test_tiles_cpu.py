@@ -1,0 +1,87 @@
+"""Tile planner for the tensor-core units kernel: the per-tile GEMM A[units x K] . B[K x (528 | 32)] built from the
+plan reproduces the per-term evaluation (tests/flat_eval.py) for both flat layouts."""
+import numpy as np
+import pytest
+
+from oracle import cavour_oracle as orc
+from adrates_b200.curves import OISCurve
+from adrates_b200.global_types import InterpTypes
+from adrates_b200.synthetic import make_book, flatten_book
+from adrates_b200.tiles import plan_tiles, packed_index, TM, NPACK
+from tests.flat_eval import eval_flat
+from tests.util_trades import make_calibration_swaps
+
+
+def sym_tables(d, J, C, pairs):
+    """Rows [H_n | C_n | G_nn | G_ab] x (528 packed entries + 32 delta columns), scalings as in k_tables."""
+    G, R = J.shape
+    g = 1e-4 * J / d[:, None]
+    Hf = 1e-8 * (C / d[:, None, None] - J[:, :, None] * J[:, None, :] / (d * d)[:, None, None])
+    Cf = 1e-8 * C / d[:, None, None]
+    idx = np.array([(j, k) for j in range(32) for k in range(j + 1)])
+    pk = lambda M: M[..., idx[:, 0], idx[:, 1]]  # noqa: E731
+    z = np.zeros((G, 32))
+    rows = [np.hstack([pk(Hf), g]), np.hstack([pk(Cf), g]), np.hstack([pk(g[:, :, None] * g[:, None, :]), z])]
+    if len(pairs):
+        ga, gb = g[pairs[:, 0]], g[pairs[:, 1]]
+        Gab = ga[:, :, None] * gb[:, None, :] + gb[:, :, None] * ga[:, None, :]
+        rows.append(np.hstack([pk(Gab), np.zeros((len(pairs), 32))]))
+    return np.vstack(rows)
+
+
+@pytest.mark.parametrize("dedup", [True, False])
+def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
+    cv = ref_curves["gbp_readme_lzr"]
+    vd, swaps = make_calibration_swaps(cv)
+    curve = OISCurve(vd, swaps, InterpTypes[cv["interp"]])
+    book = make_book(curve, 400, seed=9, max_offset_bd=40)
+    flat = flatten_book(book, dedup=dedup)
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+    tp = plan_tiles(flat, len(d))
+    assert len(tp.leftover_units) == 0
+    covered = np.sort(tp.tile_units[tp.tile_units >= 0])
+    assert np.array_equal(covered, np.arange(flat.n_units))
+    T = sym_tables(d, J, C, tp.pairs.reshape(-1, 2))
+    L = np.log(d)
+    w = flat.weight.reshape(-1, 2)
+    nd = flat.node.reshape(-1, 2)
+    u_pv, u_dl, u_gm = np.zeros(flat.n_units), np.zeros((flat.n_units, 32)), np.zeros((flat.n_units, 32, 32))
+    for t in range(tp.n_tiles):
+        ks, kc, P = tp.tile_kstart[t], tp.tile_kcount[t], tp.tile_npos[t]
+        rows, pos, coef = tp.k_row[ks:ks + kc], tp.k_pos[ks:ks + kc], tp.k_coef[ks:ks + kc]
+        A = np.zeros((TM, kc))
+        units = tp.tile_units[t * TM:(t + 1) * TM]
+        for s, u in enumerate(units):
+            if u < 0:
+                continue
+            i0 = flat.unit_offsets[u]
+            assert flat.unit_offsets[u + 1] - i0 == P
+            i = i0 + pos
+            p = flat.amt[i] * np.exp(w[i, 0] * L[nd[i, 0]] + w[i, 1] * L[nd[i, 1]])
+            table = np.stack([p, p * w[i, 0], p * w[i, 1], p * w[i, 0] ** 2, p * w[i, 1] ** 2, p * w[i, 0] * w[i, 1]])
+            A[s] = table[coef, np.arange(kc)]
+            u_pv[u] = (flat.amt[i0:i0 + P] * np.exp(w[i0:i0 + P, 0] * L[nd[i0:i0 + P, 0]] + w[i0:i0 + P, 1] * L[nd[i0:i0 + P, 1]])).sum()
+        Cm = A @ T[rows]
+        for s, u in enumerate(units):
+            if u < 0:
+                continue
+            u_dl[u] = Cm[s, NPACK:NPACK + 32]
+            for j in range(32):
+                for k in range(32):
+                    u_gm[u, j, k] = Cm[s, packed_index(j, k)]
+    # unit results -> trades, then compare with the per-term evaluation
+    K = flat.n_comp
+    cw = flat.comp_weight.reshape(-1, K)
+    pv, dl, gm = eval_flat(flat, d, J, C)
+    for gi in range(flat.n_groups):
+        ids = flat.group_units[gi * K:(gi + 1) * K]
+        for t in range(flat.group_offsets[gi], flat.group_offsets[gi + 1]):
+            row = t if flat.out_index is None else flat.out_index[t]
+            v = sum(cw[t, k] * u_pv[ids[k]] for k in range(K))
+            dd = sum(cw[t, k] * u_dl[ids[k]] for k in range(K))
+            gg = sum(cw[t, k] * u_gm[ids[k]] for k in range(K))
+            N = book.notional[row]
+            assert abs(v - pv[row]) <= 1e-12 * N
+            assert np.max(np.abs(dd - dl[row])) <= 1e-12 * N * 1e-4 * 50
+            assert np.max(np.abs(gg - gm[row])) <= 1e-12 * N * 1e-8 * 2500
