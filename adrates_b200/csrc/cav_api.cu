@@ -60,7 +60,7 @@ struct cav_ctx {
     // tensor-core units path (tile plan + symmetric tables)
     int n_tiles = 0, n_pair_rows = 0, tiles_max_k = 0;
     int64_t n_krows = 0;
-    int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *k_row = nullptr, *k_pos = nullptr, *k_coef = nullptr, *pairs = nullptr;
+    int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *k_row = nullptr, *k_pos = nullptr, *k_coef = nullptr, *pairs = nullptr;
     double* Tsym = nullptr;
     bool tiles_valid = false, tsym_valid = false;
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
@@ -223,7 +223,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
-    dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->tile_units); dev_free(ctx, &ctx->tile_kstart); dev_free(ctx, &ctx->tile_kcount);
+    dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->tile_units); dev_free(ctx, &ctx->tile_kstart); dev_free(ctx, &ctx->tile_kcount); dev_free(ctx, &ctx->tile_npos);
     dev_free(ctx, &ctx->k_row); dev_free(ctx, &ctx->k_pos); dev_free(ctx, &ctx->k_coef); dev_free(ctx, &ctx->pairs); dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
@@ -538,10 +538,30 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units
     }
     if (covered != ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: every unit must belong to exactly one tile");
     int max_k = 0;
+    std::vector<int64_t> h_off((size_t)ctx->n_units + 1);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(h_off.data(), ctx->unit_offsets, sizeof(int64_t) * h_off.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> npos((size_t)n_tiles, 0);
     for (int t = 0; t < n_tiles; ++t) {
         if (tile_kstart[t] < 0 || tile_kcount[t] < 0 || (int64_t)tile_kstart[t] + tile_kcount[t] > n_krows)
             return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K range out of bounds");
         max_k = tile_kcount[t] > max_k ? tile_kcount[t] : max_k;
+        int64_t len = -1;                                  // all units of a tile have the same number of terms
+        for (int s = 0; s < GT_TM; ++s) {
+            const int u = tile_units[(size_t)t * GT_TM + s];
+            if (u < 0) continue;
+            const int64_t l = h_off[u + 1] - h_off[u];
+            if (len >= 0 && l != len) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: units of a tile differ in length");
+            len = l;
+        }
+        npos[t] = (int)(len < 0 ? 0 : len);
+        int prev = 0;
+        for (int k = 0; k < tile_kcount[t]; ++k) {         // K rows ordered by position, positions inside the unit
+            const int p = k_pos[tile_kstart[t] + k];
+            if (p < prev || p >= npos[t]) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows not ordered by position or position out of range");
+            prev = p;
+        }
     }
     for (int64_t k = 0; k < n_krows; ++k)
         if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_coef[k] < 0 || k_coef[k] > 5)
@@ -552,6 +572,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units
     CK(upload(ctx, &ctx->tile_units, (const int*)tile_units, (size_t)n_tiles * GT_TM));
     CK(upload(ctx, &ctx->tile_kstart, (const int*)tile_kstart, (size_t)n_tiles));
     CK(upload(ctx, &ctx->tile_kcount, (const int*)tile_kcount, (size_t)n_tiles));
+    CK(upload(ctx, &ctx->tile_npos, npos.data(), (size_t)n_tiles));
     CK(upload(ctx, &ctx->k_row, (const int*)k_row, (size_t)n_krows));
     CK(upload(ctx, &ctx->k_pos, (const int*)k_pos, (size_t)n_krows));
     CK(upload(ctx, &ctx->k_coef, (const int*)k_coef, (size_t)n_krows));
@@ -622,12 +643,13 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (use_gemm) {
         GemmArgs ga;
         ga.n_tiles = ctx->n_tiles; ga.tile_units = ctx->tile_units; ga.tile_kstart = ctx->tile_kstart;
-        ga.tile_kcount = ctx->tile_kcount; ga.k_row = ctx->k_row; ga.k_pos = ctx->k_pos; ga.k_coef = ctx->k_coef;
+        ga.tile_kcount = ctx->tile_kcount; ga.tile_npos = ctx->tile_npos; ga.k_row = ctx->k_row; ga.k_pos = ctx->k_pos; ga.k_coef = ctx->k_coef;
         ga.T = ctx->Tsym; ga.zero_row = 3 * ctx->G + ctx->n_pair_rows;
         ga.unit_offsets = a.unit_offsets; ga.amt = a.amt; ga.weight = a.weight; ga.node = a.node; ga.L = a.L;
         ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
         ga.out_gamma = a.out_gamma; ga.partials = a.partials;
-        const size_t smem = (size_t)(GT_TM * GT_LDA + 16 * GT_LDS + GT_TM) * sizeof(double) + (3 * GT_KC + GT_TM) * sizeof(int);
+        const size_t smem = (size_t)(GT_TM * GT_LDA + 3 * GT_TM * GT_PC + 16 * GT_LDS + GT_TM) * sizeof(double) +
+                            (3 * GT_KC + GT_TM) * sizeof(int) + GT_TM * sizeof(int64_t);
         CK(cudaFuncSetAttribute(k_units_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_units_gemm<<<grid, 256, smem, ctx->stream>>>(ga);
         ctx->launches++;

@@ -520,6 +520,7 @@ struct GemmArgs {
     const int* tile_units;     // [n_tiles][32], -1 = padding
     const int* tile_kstart;
     const int* tile_kcount;
+    const int* tile_npos;
     const int* k_row;
     const int* k_pos;
     const int* k_coef;
@@ -538,17 +539,22 @@ struct GemmArgs {
     double* partials;          // [gridDim.x][1057] or null
 };
 
+#define GT_PC 48                 // term positions per chunk (<= 240 K rows <= GT_KC)
 __global__ void __launch_bounds__(256, 1)
 k_units_gemm(GemmArgs a)
 {
     extern __shared__ double smem[];
     double* sA = smem;                                   // [32][GT_LDA]
-    double* sStage = sA + GT_TM * GT_LDA;                // [2][8][GT_LDS]
-    double* sPv = sStage + 2 * 8 * GT_LDS;               // [32]
+    double* sTp = sA + GT_TM * GT_LDA;                   // [32][GT_PC] p
+    double* sTw0 = sTp + GT_TM * GT_PC;                  // [32][GT_PC] w0
+    double* sTw1 = sTw0 + GT_TM * GT_PC;                 // [32][GT_PC] w1
+    double* sStage = sTw1 + GT_TM * GT_PC;               // [16][GT_LDS]
+    double* sPv = sStage + 16 * GT_LDS;                  // [32]
     int* sRow = reinterpret_cast<int*>(sPv + GT_TM);     // [GT_KC]
     int* sPos = sRow + GT_KC;
     int* sCoef = sPos + GT_KC;
     int* sUnit = sCoef + GT_KC;                          // [32]
+    int64_t* sOff = reinterpret_cast<int64_t*>(sUnit + GT_TM);   // [32] first term of each unit
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
     const int mg = wib >> 2, ng = wib & 3;
@@ -560,26 +566,13 @@ k_units_gemm(GemmArgs a)
     double tg[4] = {0.0, 0.0, 0.0, 0.0}, td = 0.0, tp = 0.0;
 
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int K = a.tile_kcount[tile], ks = a.tile_kstart[tile];
+        const int K = a.tile_kcount[tile], ks = a.tile_kstart[tile], P = a.tile_npos[tile];
         __syncthreads();
-        if (tid < GT_TM) sUnit[tid] = a.tile_units[tile * GT_TM + tid];
-        __syncthreads();
-        // unit PVs: 8 threads per unit
-        {
-            const int u = tid >> 3, sub = tid & 7;
-            const int uid = sUnit[u];
-            double pv = 0.0;
-            if (uid >= 0) {
-                for (int64_t i = a.unit_offsets[uid] + sub; i < a.unit_offsets[uid + 1]; i += 8) {
-                    const double2 w = reinterpret_cast<const double2*>(a.weight)[i];
-                    const int2 n = reinterpret_cast<const int2*>(a.node)[i];
-                    pv += a.amt[i] * exp(w.x * a.L[n.x] + w.y * a.L[n.y]);
-                }
-            }
-            pv += __shfl_xor_sync(0xffffffffu, pv, 1);
-            pv += __shfl_xor_sync(0xffffffffu, pv, 2);
-            pv += __shfl_xor_sync(0xffffffffu, pv, 4);
-            if (sub == 0) sPv[u] = pv;
+        if (tid < GT_TM) {
+            const int uid = a.tile_units[tile * GT_TM + tid];
+            sUnit[tid] = uid;
+            sOff[tid] = uid >= 0 ? a.unit_offsets[uid] : 0;
+            sPv[tid] = 0.0;
         }
         double c[2][18][2];
 #pragma unroll
@@ -587,34 +580,63 @@ k_units_gemm(GemmArgs a)
 #pragma unroll
             for (int n = 0; n < 18; ++n) c[m][n][0] = c[m][n][1] = 0.0;
 
-        for (int c0 = 0; c0 < K; c0 += GT_KC) {
-            const int kc = (K - c0) < GT_KC ? (K - c0) : GT_KC;
-            const int kc4 = (kc + 3) & ~3;
-            __syncthreads();                             // previous chunk's A fully consumed
-            for (int k = tid; k < kc4; k += 256) {
-                sRow[k] = (k < kc) ? a.k_row[ks + c0 + k] : a.zero_row;
-                sPos[k] = (k < kc) ? a.k_pos[ks + c0 + k] : 0;
-                sCoef[k] = (k < kc) ? a.k_coef[ks + c0 + k] : -1;
-            }
-            __syncthreads();
-            for (int idx = tid; idx < GT_TM * kc4; idx += 256) {
-                const int u = idx / kc4, k = idx - u * kc4;
-                const int uid = sUnit[u];
-                const int cf = sCoef[k];
-                double v = 0.0;
-                if (uid >= 0 && cf >= 0) {
-                    const int64_t i = a.unit_offsets[uid] + sPos[k];
+        int kdone = 0;                                   // K rows are ordered by position
+        for (int p0 = 0; p0 < P; p0 += GT_PC) {
+            const int pc = (P - p0) < GT_PC ? (P - p0) : GT_PC;
+            __syncthreads();                             // previous chunk consumed; sUnit/sOff visible
+            // (1) term scalars of this chunk: p = amt * DF, w0, w1 for 32 units x pc positions
+            for (int idx = tid; idx < GT_TM * GT_PC; idx += 256) {
+                const int u = idx / GT_PC, j = idx - u * GT_PC;
+                double p = 0.0, w0 = 0.0, w1 = 0.0;
+                if (j < pc && sUnit[u] >= 0) {
+                    const int64_t i = sOff[u] + p0 + j;
                     const double2 w = reinterpret_cast<const double2*>(a.weight)[i];
                     const int2 n = reinterpret_cast<const int2*>(a.node)[i];
-                    const double p = a.amt[i] * exp(w.x * a.L[n.x] + w.y * a.L[n.y]);
-                    v = cf == 0 ? p : cf == 1 ? p * w.x : cf == 2 ? p * w.y : cf == 3 ? p * w.x * w.x
-                      : cf == 4 ? p * w.y * w.y : p * w.x * w.y;
+                    w0 = w.x; w1 = w.y;
+                    p = a.amt[i] * exp(w.x * a.L[n.x] + w.y * a.L[n.y]);
+                }
+                sTp[idx] = p; sTw0[idx] = w0; sTw1[idx] = w1;
+            }
+            // K rows of this chunk: [kdone, kend) with k_pos < p0 + pc
+            int kend;
+            {   // first K row with position >= p0 + pc (rows are ordered by position): binary search
+                int lo = kdone, hi = K;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (a.k_pos[ks + mid] < p0 + pc) lo = mid + 1; else hi = mid;
+                }
+                kend = lo;
+            }
+            const int kc = kend - kdone;
+            const int kc4 = (kc + 3) & ~3;
+            for (int k = tid; k < kc4; k += 256) {
+                sRow[k] = (k < kc) ? a.k_row[ks + kdone + k] : a.zero_row;
+                sPos[k] = (k < kc) ? a.k_pos[ks + kdone + k] - p0 : 0;
+                sCoef[k] = (k < kc) ? a.k_coef[ks + kdone + k] : -1;
+            }
+            __syncthreads();
+            // unit PVs (sum over positions) and the coefficient matrix A
+            if (tid < GT_TM) {
+                double pv = sPv[tid];
+                for (int j = 0; j < pc; ++j) pv += sTp[tid * GT_PC + j];
+                sPv[tid] = pv;
+            }
+            for (int idx = tid; idx < GT_TM * kc4; idx += 256) {
+                const int u = idx / kc4, k = idx - u * kc4;
+                const int cf = sCoef[k];
+                double v = 0.0;
+                if (cf >= 0) {
+                    const int t = u * GT_PC + sPos[k];
+                    const double p = sTp[t], w0 = sTw0[t], w1 = sTw1[t];
+                    v = cf == 0 ? p : cf == 1 ? p * w0 : cf == 2 ? p * w1 : cf == 3 ? p * w0 * w0
+                      : cf == 4 ? p * w1 * w1 : p * w0 * w1;
                 }
                 sA[u * GT_LDA + k] = v;
             }
             __syncthreads();
             const double* A0 = sA + (mg * 16 + ar) * GT_LDA + ac;
             const double* A1 = A0 + 8 * GT_LDA;
+#pragma unroll 2
             for (int k = 0; k < kc4; k += 4) {
                 const double a0 = A0[k], a1 = A1[k];
                 const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC + ng * 144 + ar;
@@ -627,6 +649,7 @@ k_units_gemm(GemmArgs a)
                                  : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1), "d"(b));
                 }
             }
+            kdone = kend;
         }
         // ---- epilogue: stage 8 units per m-group, expand to full symmetric rows ----
 #pragma unroll
