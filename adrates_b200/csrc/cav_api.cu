@@ -58,7 +58,7 @@ struct cav_ctx {
     double* row_weight = nullptr;
     bool row_tables_valid = false;
     // tensor-core units path (tile plan + symmetric tables)
-    int n_tiles = 0, n_pair_rows = 0, tiles_max_k = 0;
+    int n_tiles = 0, n_pair_rows = 0, tiles_max_k = 0, tile_tm = 32;
     int64_t n_krows = 0;
     int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *k_row = nullptr, *k_pos = nullptr, *k_coef = nullptr, *pairs = nullptr;
     double* Tsym = nullptr;
@@ -129,23 +129,8 @@ int units_rows() {
 
 int units_ctas_per_sm(int rows) { return rows == 32 ? 2 : (rows == 4 ? 4 : 3); }
 
-bool use_tile_kernel(const cav_ctx* ctx, bool gamma) {
-    // experimental: measured no faster than the warp-per-unit kernel on B200 (both are bound by issue slots and
-    // latency, not by table-row traffic: profiles/r01_ncu_units_tile_private.txt), so it is opt-in
-    static int mode = [] { const char* e = std::getenv("CAV_UNITS_TILE"); return e ? std::atoi(e) : 0; }();
-    return gamma && ctx->n_pairs == 2 && mode != 0;
-}
-
 // returns grid size; *slots = number of persistent unit slots (= partial rows)
 int units_grid(const cav_ctx* ctx, int64_t n_units, bool gamma, int64_t* slots) {
-    if (use_tile_kernel(ctx, gamma)) {
-        const int64_t n_tiles = (n_units + CAV_TU - 1) / CAV_TU;
-        int64_t want = (n_tiles + 1) / 2;                   // 2 teams per CTA
-        int64_t cap = (int64_t)ctx->sm_count * 2;           // __launch_bounds__(256, 2)
-        int grid = (int)(want < cap ? (want < 1 ? 1 : want) : cap);
-        *slots = (int64_t)grid * 2;
-        return grid;
-    }
     const int rows = gamma ? units_rows() : 32;
     const int wpu = 32 / rows;
     int64_t want = (n_units * wpu + 7) / 8;
@@ -521,18 +506,19 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     return CAV_OK;
 }
 
-int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units, const int32_t* tile_kstart,
+int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int32_t* tile_units, const int32_t* tile_kstart,
                             const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
                             const int32_t* k_coef, int n_pair_rows, const int32_t* pairs) {
     if (!ctx) return CAV_E_INVALID;
     if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_set_tiles: upload the portfolio first");
     if (ctx->n_pairs != 2) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: single-DF terms (n_pairs == 2) only");
+    if (tile_size != 16 && tile_size != 32) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: tile_size must be 16 or 32");
     if (n_tiles < 0 || n_krows < 0 || n_pair_rows < 0 || (n_tiles && (!tile_units || !tile_kstart || !tile_kcount)) ||
         (n_krows && (!k_row || !k_pos || !k_coef)) || (n_pair_rows && !pairs))
         return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: null pointer or negative size");
     const int n_rows = 3 * ctx->G + n_pair_rows;
     int64_t covered = 0;
-    for (int64_t i = 0; i < (int64_t)n_tiles * GT_TM; ++i) {
+    for (int64_t i = 0; i < (int64_t)n_tiles * tile_size; ++i) {
         if (tile_units[i] < -1 || tile_units[i] >= ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: unit id out of range");
         covered += tile_units[i] >= 0;
     }
@@ -548,8 +534,8 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units
             return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K range out of bounds");
         max_k = tile_kcount[t] > max_k ? tile_kcount[t] : max_k;
         int64_t len = -1;                                  // all units of a tile have the same number of terms
-        for (int s = 0; s < GT_TM; ++s) {
-            const int u = tile_units[(size_t)t * GT_TM + s];
+        for (int s = 0; s < tile_size; ++s) {
+            const int u = tile_units[(size_t)t * tile_size + s];
             if (u < 0) continue;
             const int64_t l = h_off[u + 1] - h_off[u];
             if (len >= 0 && l != len) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: units of a tile differ in length");
@@ -569,7 +555,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units
     for (int i = 0; i < 2 * n_pair_rows; ++i)
         if (pairs[i] < 0 || pairs[i] >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: pair node out of range");
     CK(cudaSetDevice(ctx->device));
-    CK(upload(ctx, &ctx->tile_units, (const int*)tile_units, (size_t)n_tiles * GT_TM));
+    CK(upload(ctx, &ctx->tile_units, (const int*)tile_units, (size_t)n_tiles * tile_size));
     CK(upload(ctx, &ctx->tile_kstart, (const int*)tile_kstart, (size_t)n_tiles));
     CK(upload(ctx, &ctx->tile_kcount, (const int*)tile_kcount, (size_t)n_tiles));
     CK(upload(ctx, &ctx->tile_npos, npos.data(), (size_t)n_tiles));
@@ -578,6 +564,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units
     CK(upload(ctx, &ctx->k_coef, (const int*)k_coef, (size_t)n_krows));
     CK(upload(ctx, &ctx->pairs, (const int*)pairs, (size_t)2 * n_pair_rows));
     CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tile_tm = tile_size;
     ctx->n_tiles = n_tiles; ctx->n_krows = n_krows; ctx->n_pair_rows = n_pair_rows; ctx->tiles_max_k = max_k;
     ctx->tiles_valid = true; ctx->tsym_valid = false;
     return CAV_OK;
@@ -618,7 +605,11 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (use_gemm && !ctx->tsym_valid) { int rc = build_sym_tables(ctx); if (rc) return rc; }
     int64_t rows = 0;
     int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
-    if (use_gemm) { grid = ctx->n_tiles < ctx->sm_count ? ctx->n_tiles : ctx->sm_count; rows = grid; }
+    if (use_gemm) {
+        const int cap = ctx->sm_count * (ctx->tile_tm == 16 ? 2 : 1);
+        grid = ctx->n_tiles < cap ? ctx->n_tiles : cap;
+        rows = grid;
+    }
     if (need_agg) CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
     UnitsArgs a;
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
@@ -648,16 +639,16 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         ga.unit_offsets = a.unit_offsets; ga.amt = a.amt; ga.weight = a.weight; ga.node = a.node; ga.L = a.L;
         ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
         ga.out_gamma = a.out_gamma; ga.partials = a.partials;
-        const size_t smem = (size_t)(GT_TM * GT_LDA + 3 * GT_TM * GT_PC + 16 * GT_LDS + GT_TM) * sizeof(double) +
-                            (3 * GT_KC + GT_TM) * sizeof(int) + GT_TM * sizeof(int64_t);
-        CK(cudaFuncSetAttribute(k_units_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_units_gemm<<<grid, 256, smem, ctx->stream>>>(ga);
-        ctx->launches++;
-    } else if (use_tile_kernel(ctx, want_g)) {
-        const size_t smem = a.partials ? (size_t)2 * CAV_NOUT * sizeof(double) : 0;
-        // static (45 KB) + dynamic shared memory exceeds the 48 KB default: opt in
-        CK(cudaFuncSetAttribute(k_units_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * CAV_NOUT * (int)sizeof(double)));
-        k_units_tile<<<grid, 256, smem, ctx->stream>>>(a);
+        const int tm = ctx->tile_tm, mgc = tm / 16;
+        const size_t smem = (size_t)(tm * GT_LDA + 3 * tm * GT_PC + 8 * mgc * GT_LDS + tm) * sizeof(double) +
+                            (3 * GT_KC + 32) * sizeof(int) + 2 * 32 * sizeof(int64_t) + 32 * sizeof(double);
+        if (mgc == 2) {
+            CK(cudaFuncSetAttribute(k_units_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_units_gemm<2><<<grid, 256, smem, ctx->stream>>>(ga);
+        } else {
+            CK(cudaFuncSetAttribute(k_units_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_units_gemm<1><<<grid, 256, smem, ctx->stream>>>(ga);
+        }
         ctx->launches++;
     } else if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
     else launch_units<6>(ctx, a, want_d, want_g, grid);

@@ -248,226 +248,18 @@ k_units(UnitsArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
-// Tiled units kernel (single-DF terms, full Greeks).  A *team* of 4 warps owns a tile of
-// CAV_TU consecutive units; warp `part` of the team owns gamma rows 8*part .. 8*part+7 of ALL
-// units of the tile (lane = column).  The team walks term position jj = 0, 1, 2, ... of the
-// tile's units together: when the units' terms at that position use the same bracket nodes
-// (homogeneous tiles: the flattener orders units by schedule class) the table rows Hf/Cf and
-// the g rows are loaded ONCE and applied to all CAV_TU units from registers, which divides the
-// L1/L2 traffic of the table rows - the bound of the one-unit-per-warp kernel - by CAV_TU.
-// Heterogeneous positions fall back to per-unit loads (same arithmetic).
-// ------------------------------------------------------------------------------------------
-#define CAV_TU 4
-#define CAV_TROWS 8
-__global__ void __launch_bounds__(256, 2)
-k_units_tile(UnitsArgs A)
-{
-    constexpr int TU = CAV_TU, ROWS = CAV_TROWS, WPT = CAV_RW / ROWS;   // 4 warps per team
-    constexpr int TPC = 8 / WPT;                                          // teams per CTA
-    __shared__ double vbuf[8][TU][CAV_RW];
-    __shared__ double s_p[8][TU][32];                 // per-warp staging of the current 32-term batch
-    __shared__ double2 s_w[8][TU][32];
-    __shared__ int2 s_n[8][TU][32];
-    __shared__ int s_k[8][TU][32];
-    extern __shared__ double s_tot[];                 // [TPC][CAV_NOUT] when A.partials != null
-    const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const int team_in_cta = wib / WPT;
-    const int part = wib % WPT;
-    const int r0 = part * ROWS;
-    const bool lead = (part == 0);
-    const int64_t team = (int64_t)blockIdx.x * TPC + team_in_cta;
-    const int64_t n_teams = (int64_t)gridDim.x * TPC;
-    const int64_t n_tiles = (A.n_units + TU - 1) / TU;
-    double* my_tot = s_tot + (size_t)team_in_cta * CAV_NOUT;
-    if (A.partials) {
-        for (int e = threadIdx.x; e < TPC * CAV_NOUT; e += 256) s_tot[e] = 0.0;
-        __syncthreads();
-    }
-
-    for (int64_t tile = team; tile < n_tiles; tile += n_teams) {
-        int64_t t0[TU], t1[TU];
-        int64_t maxlen = 0;
-#pragma unroll
-        for (int u = 0; u < TU; ++u) {
-            const int64_t uid = tile * TU + u;
-            t0[u] = (uid < A.n_units) ? A.unit_offsets[uid] : 0;
-            t1[u] = (uid < A.n_units) ? A.unit_offsets[uid + 1] : 0;
-            maxlen = (t1[u] - t0[u]) > maxlen ? (t1[u] - t0[u]) : maxlen;
-        }
-        double pv[TU], delta[TU], acc[TU][ROWS];
-#pragma unroll
-        for (int u = 0; u < TU; ++u) {
-            pv[u] = 0.0; delta[u] = 0.0;
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) acc[u][r] = 0.0;
-        }
-        for (int64_t base = 0; base < maxlen; base += 32) {
-            int cnt[TU];
-            int maxcnt = 0;
-            __syncwarp();
-#pragma unroll
-            for (int u = 0; u < TU; ++u) {
-                const int64_t i = t0[u] + base + lane;
-                const int64_t left = t1[u] - t0[u] - base;
-                cnt[u] = left < 0 ? 0 : (left < 32 ? (int)left : 32);
-                maxcnt = cnt[u] > maxcnt ? cnt[u] : maxcnt;
-                double p = 0.0;
-                if (i < t1[u]) {
-                    const double2 ww = reinterpret_cast<const double2*>(A.weight)[i];
-                    const int2 nn = reinterpret_cast<const int2*>(A.node)[i];
-                    p = A.amt[i] * exp(ww.x * A.L[nn.x] + ww.y * A.L[nn.y]);
-                    s_w[wib][u][lane] = ww;
-                    s_n[wib][u][lane] = nn;
-                    s_k[wib][u][lane] = (ww.x == 1.0 && ww.y == 0.0) ? 0 : (ww.y != 0.0 ? 2 : 1);
-                }
-                s_p[wib][u][lane] = p;
-                pv[u] += p;
-            }
-            __syncwarp();
-            for (int jj = 0; jj < maxcnt; ++jj) {
-                // pass 1 (integers only): do all live units use the same rows at this position?
-                int ref = -1, r_n0 = 0, r_n1 = 0, r_kind = 0;
-                bool same = true;
-#pragma unroll
-                for (int u = 0; u < TU; ++u) {
-                    if (jj >= cnt[u]) continue;
-                    const int2 nn = s_n[wib][u][jj];
-                    const int kind = s_k[wib][u][jj];      // 0 snap, 1 one node, 2 two nodes
-                    if (ref < 0) { ref = u; r_n0 = nn.x; r_n1 = nn.y; r_kind = kind; }
-                    else if (nn.x != r_n0 || kind != r_kind || (kind == 2 && nn.y != r_n1)) same = false;
-                }
-                if (same) {
-                    // ---- shared rows: one set of loads for the whole tile ----
-                    const double g0 = __ldg(A.g + (size_t)r_n0 * CAV_RW + lane);
-                    if (r_kind == 0) {
-                        const double* C = A.Cf + (size_t)r_n0 * CAV_RR + r0 * CAV_RW + lane;
-                        double c[ROWS];
-#pragma unroll
-                        for (int r = 0; r < ROWS; ++r) c[r] = __ldg(C + r * CAV_RW);
-#pragma unroll
-                        for (int u = 0; u < TU; ++u) {
-                            if (jj >= cnt[u]) continue;
-                            const double pj = s_p[wib][u][jj];
-                            if (lead) delta[u] += pj * g0;
-#pragma unroll
-                            for (int r = 0; r < ROWS; ++r) acc[u][r] += pj * c[r];
-                        }
-                    } else {
-                        const bool two = (r_kind == 2);
-                        const double g1 = two ? __ldg(A.g + (size_t)r_n1 * CAV_RW + lane) : 0.0;
-                        const double* H0 = A.Hf + (size_t)r_n0 * CAV_RR + r0 * CAV_RW + lane;
-                        const double* H1 = A.Hf + (size_t)r_n1 * CAV_RR + r0 * CAV_RW + lane;
-                        double h0[ROWS], h1[ROWS];
-#pragma unroll
-                        for (int r = 0; r < ROWS; ++r) { h0[r] = __ldg(H0 + r * CAV_RW); h1[r] = two ? __ldg(H1 + r * CAV_RW) : 0.0; }
-                        __syncwarp();
-#pragma unroll
-                        for (int u = 0; u < TU; ++u) {
-                            const double2 ww = s_w[wib][u][jj];
-                            vbuf[wib][u][lane] = ww.x * g0 + ww.y * g1;
-                        }
-                        __syncwarp();
-#pragma unroll
-                        for (int u = 0; u < TU; ++u) {
-                            if (jj >= cnt[u]) continue;
-                            const double pj = s_p[wib][u][jj];
-                            const double2 ww = s_w[wib][u][jj];
-                            const double v = vbuf[wib][u][lane];
-                            if (lead) delta[u] += pj * v;
-                            const double pvk = pj * v, pa = pj * ww.x, pb = pj * ww.y;
-                            const double2* vb = reinterpret_cast<const double2*>(&vbuf[wib][u][r0]);
-#pragma unroll
-                            for (int r = 0; r < ROWS; r += 2) {
-                                const double2 vv = vb[r >> 1];
-                                acc[u][r] += pvk * vv.x + pa * h0[r] + pb * h1[r];
-                                acc[u][r + 1] += pvk * vv.y + pa * h0[r + 1] + pb * h1[r + 1];
-                            }
-                        }
-                    }
-                } else {
-                    // ---- heterogeneous position: per-unit rows (same arithmetic) ----
-#pragma unroll
-                    for (int u = 0; u < TU; ++u) {
-                        if (jj >= cnt[u]) continue;
-                        const double pj = s_p[wib][u][jj];
-                        const double2 ww = s_w[wib][u][jj];
-                        const int2 nn = s_n[wib][u][jj];
-                        const int kind = s_k[wib][u][jj];
-                        double v = ww.x * __ldg(A.g + (size_t)nn.x * CAV_RW + lane);
-                        if (kind == 2) v += ww.y * __ldg(A.g + (size_t)nn.y * CAV_RW + lane);
-                        if (lead) delta[u] += pj * v;
-                        if (kind == 0) {
-                            const double* C = A.Cf + (size_t)nn.x * CAV_RR + r0 * CAV_RW + lane;
-#pragma unroll
-                            for (int r = 0; r < ROWS; ++r) acc[u][r] += pj * __ldg(C + r * CAV_RW);
-                        } else {
-                            __syncwarp();
-                            vbuf[wib][u][lane] = v;
-                            __syncwarp();
-                            const double pvk = pj * v, pa = pj * ww.x, pb = pj * ww.y;
-                            const double* H0 = A.Hf + (size_t)nn.x * CAV_RR + r0 * CAV_RW + lane;
-                            const double* H1 = A.Hf + (size_t)nn.y * CAV_RR + r0 * CAV_RW + lane;
-#pragma unroll
-                            for (int r = 0; r < ROWS; ++r) {
-                                double t = pvk * vbuf[wib][u][r0 + r] + pa * __ldg(H0 + r * CAV_RW);
-                                if (kind == 2) t += pb * __ldg(H1 + r * CAV_RW);
-                                acc[u][r] += t;
-                            }
-                        }
-                    }
-                }
-            }
-        }
-        // ---- write the tile ----
-#pragma unroll
-        for (int u = 0; u < TU; ++u) {
-            const int64_t uid = tile * TU + u;
-            if (uid >= A.n_units) continue;
-            double s = pv[u];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const int64_t row = A.out_index ? A.out_index[uid] : uid;
-            if (lead) {
-                if (A.out_pv && lane == 0) A.out_pv[row] = s;
-                if (A.out_delta) A.out_delta[row * CAV_RW + lane] = delta[u];
-            }
-            if (A.out_gamma) {
-                double* o = A.out_gamma + row * CAV_RR + r0 * CAV_RW + lane;
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) __stcs(o + r * CAV_RW, acc[u][r]);
-            }
-            if (A.partials) {
-                const double W = A.unit_weight ? A.unit_weight[uid] : 1.0;
-                if (lead) {
-                    if (lane == 0) my_tot[0] += W * s;
-                    my_tot[1 + lane] += W * delta[u];
-                }
-#pragma unroll
-                for (int r = 0; r < ROWS; ++r) my_tot[33 + (r0 + r) * CAV_RW + lane] += W * acc[u][r];
-            }
-        }
-    }
-    if (A.partials) {
-        __syncthreads();
-        double* P = A.partials + (size_t)blockIdx.x * TPC * CAV_NOUT;
-        for (int e = threadIdx.x; e < TPC * CAV_NOUT; e += 256) P[e] = s_tot[e];
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // Tensor-core units kernel.  For units that bracket the same node pairs term by term,
 //   [gamma (528 packed lower-triangle entries) | delta (32)] [units x 560] = A[units x K] . B[K x 560]
 // where the K rows of B come from per-curve symmetric tables (built by k_sym_tables / k_pair_tables)
 //   H_n = hess(ln d_n)|g_n,  C_n = (H_n + g_n g_n^T)|g_n,  G_nn = g_n g_n^T|0,  G_ab = (g_a g_b^T + g_b g_a^T)|0
 // and only the coefficients A (p, p w0, p w1, p w0^2, p w1^2, p w0 w1) depend on the unit
 // (adrates_b200/tiles.py).  One CTA = one tile of 32 units x all 576 padded columns, FP64 DMMA
-// (mma.sync.m8n8k4): warp (mg, ng) owns m-tiles {2mg, 2mg+1} x n-tiles [18 ng, 18 ng + 18).  A is built
-// in shared memory (K chunked by 256), B fragments are read straight from the L2-resident tables
-// (each table row is read once per tile, not once per unit), the epilogue stages 8 units at a time in
-// shared memory and writes full symmetric 32x32 rows with 32-byte stores.
+// (mma.sync.m8n8k4).  Per chunk of 48 term positions the CTA evaluates p = amt*DF once per term, builds A in
+// shared memory, then runs the K loop with B fragments read straight from the L2-resident tables (each table
+// row is read once per tile, not once per unit); the epilogue stages 8 units at a time in shared memory and
+// writes full symmetric 32x32 rows with 32-byte stores.
 // ------------------------------------------------------------------------------------------
-#define GT_TM 32
+#define GT_TM 32          // largest tile (MG = 2)
 #define GT_NC 576
 #define GT_NPACK 528
 #define GT_KC 256
@@ -540,24 +332,34 @@ struct GemmArgs {
 };
 
 #define GT_PC 48                 // term positions per chunk (<= 240 K rows <= GT_KC)
-__global__ void __launch_bounds__(256, 1)
+// MG = m-groups per CTA: a tile has TM = 16*MG units; warp (mg, ng) owns m-tiles {2mg, 2mg+1} x NT n-tiles.
+// MG = 2: one CTA per SM (254 registers).  MG = 1: half the accumulators per warp, two CTAs per SM whose
+// scalar / epilogue phases overlap each other's MMA phase (each table row is then read once per 16 units).
+template <int MG>
+__global__ void __launch_bounds__(256, 3 - MG)
 k_units_gemm(GemmArgs a)
 {
+    constexpr int TM = 16 * MG;            // units per tile
+    constexpr int NG = 8 / MG;             // n-groups (warps along N)
+    constexpr int NT = 72 / NG;            // n-tiles per warp
+    constexpr int NW = NT * 8;             // columns per warp
     extern __shared__ double smem[];
     double* sA = smem;                                   // [32][GT_LDA]
-    double* sTp = sA + GT_TM * GT_LDA;                   // [32][GT_PC] p
-    double* sTw0 = sTp + GT_TM * GT_PC;                  // [32][GT_PC] w0
-    double* sTw1 = sTw0 + GT_TM * GT_PC;                 // [32][GT_PC] w1
-    double* sStage = sTw1 + GT_TM * GT_PC;               // [16][GT_LDS]
-    double* sPv = sStage + 16 * GT_LDS;                  // [32]
-    int* sRow = reinterpret_cast<int*>(sPv + GT_TM);     // [GT_KC]
+    double* sTp = sA + TM * GT_LDA;                   // [32][GT_PC] p
+    double* sTw0 = sTp + TM * GT_PC;                  // [32][GT_PC] w0
+    double* sTw1 = sTw0 + TM * GT_PC;                 // [32][GT_PC] w1
+    double* sStage = sTw1 + TM * GT_PC;               // [16][GT_LDS]
+    double* sPv = sStage + 8 * MG * GT_LDS;              // [TM]
+    int* sRow = reinterpret_cast<int*>(sPv + TM);        // [GT_KC]
     int* sPos = sRow + GT_KC;
     int* sCoef = sPos + GT_KC;
     int* sUnit = sCoef + GT_KC;                          // [32]
-    int64_t* sOff = reinterpret_cast<int64_t*>(sUnit + GT_TM);   // [32] first term of each unit
+    int64_t* sOff = reinterpret_cast<int64_t*>(sUnit + 32);   // [32] first term of each unit
+    int64_t* sOut = sOff + 32;                                // [32] output row of each unit
+    double* sW = reinterpret_cast<double*>(sOut + 32);        // [32] portfolio weight of each unit
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const int mg = wib >> 2, ng = wib & 3;
+    const int mg = wib / NG, ng = wib % NG;
     const int ar = lane >> 2, ac = lane & 3;
     const int oj = tid >> 3, ok4 = (tid & 7) * 4;        // epilogue: this thread owns gamma entries (oj, ok4..ok4+3)
     int pk[4];
@@ -568,24 +370,26 @@ k_units_gemm(GemmArgs a)
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int K = a.tile_kcount[tile], ks = a.tile_kstart[tile], P = a.tile_npos[tile];
         __syncthreads();
-        if (tid < GT_TM) {
-            const int uid = a.tile_units[tile * GT_TM + tid];
+        if (tid < TM) {
+            const int uid = a.tile_units[tile * TM + tid];
             sUnit[tid] = uid;
             sOff[tid] = uid >= 0 ? a.unit_offsets[uid] : 0;
+            sOut[tid] = uid >= 0 ? (a.out_index ? a.out_index[uid] : uid) : 0;
+            sW[tid] = (uid >= 0 && a.unit_weight) ? a.unit_weight[uid] : 1.0;
             sPv[tid] = 0.0;
         }
-        double c[2][18][2];
+        double c[2][NT][2];
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
-            for (int n = 0; n < 18; ++n) c[m][n][0] = c[m][n][1] = 0.0;
+            for (int n = 0; n < NT; ++n) c[m][n][0] = c[m][n][1] = 0.0;
 
         int kdone = 0;                                   // K rows are ordered by position
         for (int p0 = 0; p0 < P; p0 += GT_PC) {
             const int pc = (P - p0) < GT_PC ? (P - p0) : GT_PC;
             __syncthreads();                             // previous chunk consumed; sUnit/sOff visible
             // (1) term scalars of this chunk: p = amt * DF, w0, w1 for 32 units x pc positions
-            for (int idx = tid; idx < GT_TM * GT_PC; idx += 256) {
+            for (int idx = tid; idx < TM * GT_PC; idx += 256) {
                 const int u = idx / GT_PC, j = idx - u * GT_PC;
                 double p = 0.0, w0 = 0.0, w1 = 0.0;
                 if (j < pc && sUnit[u] >= 0) {
@@ -598,8 +402,8 @@ k_units_gemm(GemmArgs a)
                 sTp[idx] = p; sTw0[idx] = w0; sTw1[idx] = w1;
             }
             // K rows of this chunk: [kdone, kend) with k_pos < p0 + pc
-            int kend;
-            {   // first K row with position >= p0 + pc (rows are ordered by position): binary search
+            int kend = K;
+            if (p0 + pc < P) {   // first K row with position >= p0 + pc (rows are ordered by position)
                 int lo = kdone, hi = K;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
@@ -616,22 +420,29 @@ k_units_gemm(GemmArgs a)
             }
             __syncthreads();
             // unit PVs (sum over positions) and the coefficient matrix A
-            if (tid < GT_TM) {
-                double pv = sPv[tid];
-                for (int j = 0; j < pc; ++j) pv += sTp[tid * GT_PC + j];
-                sPv[tid] = pv;
+            {   // 8 threads per unit, fixed order
+                const int u = (tid >> 3) % TM, sub = tid & 7;
+                double pv = 0.0;
+                for (int j = sub; j < pc; j += 8) pv += sTp[u * GT_PC + j];
+                pv += __shfl_xor_sync(0xffffffffu, pv, 1);
+                pv += __shfl_xor_sync(0xffffffffu, pv, 2);
+                pv += __shfl_xor_sync(0xffffffffu, pv, 4);
+                if (sub == 0 && (tid >> 3) < TM) sPv[u] += pv;
             }
-            for (int idx = tid; idx < GT_TM * kc4; idx += 256) {
-                const int u = idx / kc4, k = idx - u * kc4;
-                const int cf = sCoef[k];
-                double v = 0.0;
-                if (cf >= 0) {
-                    const int t = u * GT_PC + sPos[k];
-                    const double p = sTp[t], w0 = sTw0[t], w1 = sTw1[t];
-                    v = cf == 0 ? p : cf == 1 ? p * w0 : cf == 2 ? p * w1 : cf == 3 ? p * w0 * w0
-                      : cf == 4 ? p * w1 * w1 : p * w0 * w1;
+            for (int k = lane; k < kc4; k += 32) {
+                const int cf = sCoef[k], pos = sPos[k];
+#pragma unroll
+                for (int uu = 0; uu < TM / 8; ++uu) {
+                    const int u = wib + 8 * uu;
+                    double v = 0.0;
+                    if (cf >= 0) {
+                        const int t = u * GT_PC + pos;
+                        const double p = sTp[t], w0 = sTw0[t], w1 = sTw1[t];
+                        v = cf == 0 ? p : cf == 1 ? p * w0 : cf == 2 ? p * w1 : cf == 3 ? p * w0 * w0
+                          : cf == 4 ? p * w1 * w1 : p * w0 * w1;
+                    }
+                    sA[u * GT_LDA + k] = v;
                 }
-                sA[u * GT_LDA + k] = v;
             }
             __syncthreads();
             const double* A0 = sA + (mg * 16 + ar) * GT_LDA + ac;
@@ -639,9 +450,9 @@ k_units_gemm(GemmArgs a)
 #pragma unroll 2
             for (int k = 0; k < kc4; k += 4) {
                 const double a0 = A0[k], a1 = A1[k];
-                const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC + ng * 144 + ar;
+                const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC + ng * NW + ar;
 #pragma unroll
-                for (int n = 0; n < 18; ++n) {
+                for (int n = 0; n < NT; ++n) {
                     const double b = __ldg(rowp + n * 8);
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                  : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(b));
@@ -655,18 +466,18 @@ k_units_gemm(GemmArgs a)
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             __syncthreads();                             // stage buffers free
-            double* st = sStage + (size_t)(mg * 8 + ar) * GT_LDS + ng * 144 + 2 * ac;
+            double* st = sStage + (size_t)(mg * 8 + ar) * GT_LDS + ng * NW + 2 * ac;
 #pragma unroll
-            for (int n = 0; n < 18; ++n)
+            for (int n = 0; n < NT; ++n)
                 *reinterpret_cast<double2*>(st + n * 8) = make_double2(c[mt][n][0], c[mt][n][1]);
             __syncthreads();
-            for (int s = 0; s < 16; ++s) {
+            for (int s = 0; s < 8 * MG; ++s) {
                 const int u = (s >> 3) * 16 + mt * 8 + (s & 7);
                 const int uid = sUnit[u];
                 if (uid < 0) continue;
                 const double* row_s = sStage + (size_t)s * GT_LDS;
-                const int64_t row = a.out_index ? a.out_index[uid] : uid;
-                const double W = a.unit_weight ? a.unit_weight[uid] : 1.0;
+                const int64_t row = sOut[u];
+                const double W = sW[u];
                 const double g0 = row_s[pk[0]], g1 = row_s[pk[1]], g2 = row_s[pk[2]], g3 = row_s[pk[3]];
                 if (a.out_gamma) {
                     double* dst = a.out_gamma + (size_t)row * CAV_RR + oj * CAV_RW + ok4;

@@ -22,7 +22,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-TM = 32            # units per tile (four m8 tiles)
+TM = int(__import__("os").environ.get("CAV_TILE_SIZE", "16"))   # units per tile: 16 (two CTAs per SM) or 32
 NCOL = 576         # padded row length: 528 packed gamma entries + 32 delta columns + 16 zeros
 NPACK = 528
 
@@ -33,7 +33,8 @@ COEF_P, COEF_PW0, COEF_PW1, COEF_PW0SQ, COEF_PW1SQ, COEF_PW0W1 = range(6)
 @dataclass
 class TilePlan:
     n_tiles: int
-    tile_units: np.ndarray    # i32 [n_tiles*TM], -1 = padding
+    tile_size: int
+    tile_units: np.ndarray    # i32 [n_tiles*tile_size], -1 = padding
     tile_kstart: np.ndarray   # i32 [n_tiles] first K row of the tile's group
     tile_kcount: np.ndarray   # i32 [n_tiles]
     tile_npos: np.ndarray     # i32 [n_tiles] terms per unit in this tile
@@ -112,7 +113,7 @@ def plan_tiles(flat, G: int, min_group: int = 1) -> TilePlan:
     for (na, nb), pi in pair_index.items():
         pairs[pi] = (na, nb)
     return TilePlan(
-        n_tiles,
+        n_tiles, TM,
         np.concatenate(t_units).astype(np.int32) if n_tiles else np.zeros(0, dtype=np.int32),
         np.array(t_kstart, dtype=np.int32), np.array(t_kcount, dtype=np.int32), np.array(t_npos, dtype=np.int32),
         np.array(k_row, dtype=np.int32), np.array(k_pos, dtype=np.int32), np.array(k_coef, dtype=np.int32),

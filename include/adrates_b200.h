@@ -123,15 +123,15 @@ int cav_portfolio_upload(cav_ctx* ctx,
                          const int64_t* out_index, const double* unit_weight);
 
 /* Optional tile plan for the tensor-core Greeks kernel (host planner: adrates_b200/tiles.py).  Units that
- * bracket the same node pairs term by term are grouped into tiles of 32; their gamma/delta rows are then one
+ * bracket the same node pairs term by term are grouped into tiles of 16 or 32; their gamma/delta rows are then one
  * FP64 GEMM per tile, [32 x K] coefficients times K rows of per-curve symmetric tables (H_n, C_n, g_n g_n^T and,
  * for the node pairs listed in `pairs`, g_a g_b^T + g_b g_a^T), evaluated with mma.sync.m8n8k4.f64.
- * tile_units[n_tiles][32] (-1 = padding) must cover every unit exactly once; tile t uses K rows
+ * tile_units[n_tiles][tile_size] (tile_size 16 or 32, -1 = padding) must cover every unit exactly once; tile t uses K rows
  * [tile_kstart[t], tile_kstart[t] + tile_kcount[t]) of (k_row = table row id, k_pos = term position within the
  * unit, k_coef = 0:p 1:p*w0 2:p*w1 3:p*w0^2 4:p*w1^2 5:p*w0*w1).  Table row ids: n (H), G+n (C), 2G+n (g g^T),
  * 3G+i (pair i).  Replaces the same reference code as cav_portfolio_value; it only changes how it is computed.
  * Must be called after every cav_portfolio_upload (which clears the plan). */
-int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, const int32_t* tile_units, const int32_t* tile_kstart,
+int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int32_t* tile_units, const int32_t* tile_kstart,
                             const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
                             const int32_t* k_coef, int n_pair_rows, const int32_t* pairs);
 
