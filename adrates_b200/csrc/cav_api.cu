@@ -169,6 +169,13 @@ void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma) {
     ctx->launches++;
 }
 
+template <int K>
+void launch_expand_rows(cav_ctx* ctx, double* pv, double* delta) {
+    k_expand_rows<K><<<(unsigned)((ctx->n_trades + 7) / 8), 256, 0, ctx->stream>>>(
+        ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->u_pv, ctx->u_delta, pv, delta);
+    ctx->launches++;
+}
+
 }  // namespace
 
 extern "C" {
@@ -570,6 +577,21 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     return CAV_OK;
 }
 
+static int ensure_row_tables(cav_ctx* ctx) {
+    if (ctx->row_tables_valid) return CAV_OK;
+    CK(dev_alloc(ctx, &ctx->row_units, (size_t)ctx->n_trades * ctx->n_comp));
+    CK(dev_alloc(ctx, &ctx->row_weight, (size_t)ctx->n_trades * ctx->n_comp));
+    if (ctx->n_groups > 0) {
+        k_row_tables<<<(unsigned)((ctx->n_groups + 127) / 128), 128, 0, ctx->stream>>>(
+            ctx->n_groups, ctx->n_comp, ctx->group_offsets, ctx->group_units, ctx->comp_weight, ctx->out_index,
+            ctx->row_units, ctx->row_weight);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    ctx->row_tables_valid = true;
+    return CAV_OK;
+}
+
 static int build_sym_tables(cav_ctx* ctx) {
     const size_t rows = (size_t)3 * ctx->G + ctx->n_pair_rows + 1;
     CK(dev_alloc(ctx, &ctx->Tsym, rows * GT_NC));
@@ -655,13 +677,26 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     CK(cudaGetLastError());
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[1], ctx->stream));
     if (!ctx->direct && (pv || delta || gamma) && ctx->n_groups > 0) {
-        switch (ctx->n_comp) {
-            case 1: launch_expand<1>(ctx, pv, delta, gamma); break;
-            case 2: launch_expand<2>(ctx, pv, delta, gamma); break;
-            case 3: launch_expand<3>(ctx, pv, delta, gamma); break;
-            default: launch_expand<4>(ctx, pv, delta, gamma); break;
+        // gamma rows: group-ordered streaming kernel; PV / delta rows: row-ordered gather (coalesced small rows)
+        if (gamma) {
+            switch (ctx->n_comp) {
+                case 1: launch_expand<1>(ctx, nullptr, nullptr, gamma); break;
+                case 2: launch_expand<2>(ctx, nullptr, nullptr, gamma); break;
+                case 3: launch_expand<3>(ctx, nullptr, nullptr, gamma); break;
+                default: launch_expand<4>(ctx, nullptr, nullptr, gamma); break;
+            }
+            CK(cudaGetLastError());
         }
-        CK(cudaGetLastError());
+        if (pv || delta) {
+            { int rc = ensure_row_tables(ctx); if (rc) return rc; }
+            switch (ctx->n_comp) {
+                case 1: launch_expand_rows<1>(ctx, pv, delta); break;
+                case 2: launch_expand_rows<2>(ctx, pv, delta); break;
+                case 3: launch_expand_rows<3>(ctx, pv, delta); break;
+                default: launch_expand_rows<4>(ctx, pv, delta); break;
+            }
+            CK(cudaGetLastError());
+        }
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[2], ctx->stream));
     if (need_agg) {
@@ -748,17 +783,7 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
     CK(dev_alloc(ctx, &ctx->sc_P, G * S));
     CK(dev_alloc(ctx, &ctx->sc_L, G * S));
     CK(dev_alloc(ctx, &ctx->sc_upv, (size_t)ctx->n_units * S));
-    if (!ctx->row_tables_valid) {
-        CK(dev_alloc(ctx, &ctx->row_units, (size_t)ctx->n_trades * ctx->n_comp));
-        CK(dev_alloc(ctx, &ctx->row_weight, (size_t)ctx->n_trades * ctx->n_comp));
-        if (ctx->n_groups > 0) {
-            k_row_tables<<<(unsigned)((ctx->n_groups + 127) / 128), 128, 0, ctx->stream>>>(
-                ctx->n_groups, ctx->n_comp, ctx->group_offsets, ctx->group_units, ctx->comp_weight, ctx->out_index,
-                ctx->row_units, ctx->row_weight);
-            ctx->launches++;
-        }
-        ctx->row_tables_valid = true;
-    }
+    { int rc = ensure_row_tables(ctx); if (rc) return rc; }
     if (ctx->n_units == 0 || ctx->n_trades == 0) return CAV_OK;
     k_scen_bootstrap<<<(n_scen + 127) / 128, 128, 0, ctx->stream>>>(ctx->G, ctx->R, n_scen, ctx->sc_rates, ctx->node_acc,
                                                                   ctx->node_swap, ctx->node_prev, ctx->sc_P, ctx->sc_L);

@@ -591,6 +591,30 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
     }
 }
 
+// PV and delta rows of the expansion, gathered per OUTPUT row (warp = row, lane = pillar) from the
+// unit results with the row-ordered tables of k_row_tables: consecutive rows write consecutive
+// memory, instead of the 8-byte / 256-byte scatters the group-ordered k_expand would issue
+// (measured: 1M scattered 8-byte PV stores alone cost 0.1 ms).
+template <int K>
+__global__ void __launch_bounds__(256)
+k_expand_rows(int64_t n_trades, const int* __restrict__ row_units, const double* __restrict__ row_weight,
+              const double* __restrict__ u_pv, const double* __restrict__ u_delta, double* pv, double* delta)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_trades) return;
+    double d = 0.0, p = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const double w = row_weight[row * K + k];
+        const int u = row_units[row * K + k];
+        if (delta) d += w * u_delta[(size_t)u * CAV_RW + lane];
+        if (pv && lane == 0) p += w * u_pv[u];
+    }
+    if (delta) delta[row * CAV_RW + lane] = d;
+    if (pv && lane == 0) pv[row] = p;
+}
+
 // ------------------------------------------------------------------------------------------
 // Chain rule as a batched FP64 tensor-core GEMM (the reference's `jnp.dot(grad_dfs, jac)`,
 // engine.py:2554/2912, for all units at once):
