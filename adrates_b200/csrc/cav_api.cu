@@ -8,6 +8,16 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
+#define CAV_N_CLASSES 6
+// size class of a tile from its active-pillar mask: compact columns = na(na+3)/2, NI = ceil(columns / 32)
+static int cav_tile_class(unsigned mask) {
+    const int na = __builtin_popcount(mask);
+    const int ni = (na * (na + 3) / 2 + 31) / 32;
+    return ni <= 2 ? 0 : ni <= 4 ? 1 : ni <= 6 ? 2 : ni <= 8 ? 3 : ni <= 12 ? 4 : 5;
+}
+
 struct CapTable {
     std::vector<std::pair<void*, size_t>> v;
     size_t get(void* p) const {
@@ -58,9 +68,12 @@ struct cav_ctx {
     double* row_weight = nullptr;
     bool row_tables_valid = false;
     // tensor-core units path (tile plan + symmetric tables)
-    int n_tiles = 0, n_pair_rows = 0, tiles_max_k = 0, tile_tm = 32;
+    int n_tiles = 0, n_pair_rows = 0;
     int64_t n_krows = 0;
-    int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *k_row = nullptr, *k_pos = nullptr, *k_coef = nullptr, *pairs = nullptr;
+    int class_begin[CAV_N_CLASSES + 1] = {0};   // tiles are ordered by size class (compact columns / 32)
+    unsigned *tile_mask = nullptr, *row_masks = nullptr;
+    int* check_flag = nullptr;
+    int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *k_pack = nullptr, *pairs = nullptr;
     double* Tsym = nullptr;
     bool tiles_valid = false, tsym_valid = false;
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
@@ -169,6 +182,45 @@ void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma) {
     ctx->launches++;
 }
 
+// Size classes of the tiled units kernel: NI = compact columns / 32 (accumulators per lane and unit), U = units per
+// pass, MINB = CTAs per SM the register allocation is bounded for.
+#define SIMT_CLASSES(X) X(2, 4, 6) X(4, 4, 5) X(6, 4, 4) X(8, 4, 4) X(12, 2, 4) X(18, 2, 3)
+
+template <int NI, int U, int MINB>
+int simt_ctas_per_sm() {
+    static int n = [] {
+        int v = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_units_simt<NI, U, MINB>, 128, 0) != cudaSuccess || v < 1) v = 1;
+        return v;
+    }();
+    return n;
+}
+
+int simt_max_grid(const cav_ctx* ctx) {
+    int m = 1;
+#define X(NI, U, MINB) m = std::max(m, simt_ctas_per_sm<NI, U, MINB>());
+    SIMT_CLASSES(X)
+#undef X
+    return m * ctx->sm_count;
+}
+
+template <int NI, int U, int MINB>
+void launch_simt(cav_ctx* ctx, const SimtArgs& ga, int t0, int t1) {
+    if (t1 <= t0) return;
+    const int cap = simt_ctas_per_sm<NI, U, MINB>() * ctx->sm_count;
+    const int want = (t1 - t0 + 3) / 4;
+    k_units_simt<NI, U, MINB><<<want < cap ? want : cap, 128, 0, ctx->stream>>>(ga, t0, t1);
+    ctx->launches++;
+}
+
+void launch_simt_classes(cav_ctx* ctx, const SimtArgs& ga) {
+    const int* cb = ctx->class_begin;
+    int c = 0;
+#define X(NI, U, MINB) launch_simt<NI, U, MINB>(ctx, ga, cb[c], cb[c + 1]); ++c;
+    SIMT_CLASSES(X)
+#undef X
+}
+
 template <int K>
 void launch_expand_rows(cav_ctx* ctx, double* pv, double* delta) {
     k_expand_rows<K><<<(unsigned)((ctx->n_trades + 7) / 8), 256, 0, ctx->stream>>>(
@@ -215,8 +267,9 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
+    dev_free(ctx, &ctx->tile_mask); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag);
     dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->tile_units); dev_free(ctx, &ctx->tile_kstart); dev_free(ctx, &ctx->tile_kcount); dev_free(ctx, &ctx->tile_npos);
-    dev_free(ctx, &ctx->k_row); dev_free(ctx, &ctx->k_pos); dev_free(ctx, &ctx->k_coef); dev_free(ctx, &ctx->pairs); dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
+    dev_free(ctx, &ctx->k_pack); dev_free(ctx, &ctx->pairs); dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
     cudaEventDestroy(ctx->ev0);
@@ -515,31 +568,36 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
 
 int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int32_t* tile_units, const int32_t* tile_kstart,
                             const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
-                            const int32_t* k_coef, int n_pair_rows, const int32_t* pairs) {
+                            const int32_t* k_coef, int n_pair_rows, const int32_t* pairs, const uint32_t* tile_mask) {
     if (!ctx) return CAV_E_INVALID;
     if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_set_tiles: upload the portfolio first");
     if (ctx->n_pairs != 2) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: single-DF terms (n_pairs == 2) only");
-    if (tile_size != 16 && tile_size != 32) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: tile_size must be 16 or 32");
+    if (tile_size != GT_TM) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: tile_size must be 4");
     if (n_tiles < 0 || n_krows < 0 || n_pair_rows < 0 || (n_tiles && (!tile_units || !tile_kstart || !tile_kcount)) ||
         (n_krows && (!k_row || !k_pos || !k_coef)) || (n_pair_rows && !pairs))
         return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: null pointer or negative size");
     const int n_rows = 3 * ctx->G + n_pair_rows;
+    if (n_rows >= (1 << 20)) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 2^20 table rows");
     int64_t covered = 0;
     for (int64_t i = 0; i < (int64_t)n_tiles * tile_size; ++i) {
         if (tile_units[i] < -1 || tile_units[i] >= ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: unit id out of range");
         covered += tile_units[i] >= 0;
     }
     if (covered != ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: every unit must belong to exactly one tile");
-    int max_k = 0;
     std::vector<int64_t> h_off((size_t)ctx->n_units + 1);
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(h_off.data(), ctx->unit_offsets, sizeof(int64_t) * h_off.size(), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<int> npos((size_t)n_tiles, 0);
+    std::vector<unsigned> masks((size_t)n_tiles, 0xFFFFFFFFu);
+    if (tile_mask) std::memcpy(masks.data(), tile_mask, sizeof(unsigned) * n_tiles);
+    int cls_prev = 0;
+    int class_begin[CAV_N_CLASSES + 1];
+    for (int c = 0; c <= CAV_N_CLASSES; ++c) class_begin[c] = n_tiles;
+    class_begin[0] = 0;
     for (int t = 0; t < n_tiles; ++t) {
         if (tile_kstart[t] < 0 || tile_kcount[t] < 0 || (int64_t)tile_kstart[t] + tile_kcount[t] > n_krows)
             return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K range out of bounds");
-        max_k = tile_kcount[t] > max_k ? tile_kcount[t] : max_k;
         int64_t len = -1;                                  // all units of a tile have the same number of terms
         for (int s = 0; s < tile_size; ++s) {
             const int u = tile_units[(size_t)t * tile_size + s];
@@ -549,30 +607,41 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
             len = l;
         }
         npos[t] = (int)(len < 0 ? 0 : len);
-        int prev = 0;
-        for (int k = 0; k < tile_kcount[t]; ++k) {         // K rows ordered by position, positions inside the unit
-            const int p = k_pos[tile_kstart[t] + k];
-            if (p < prev || p >= npos[t]) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows not ordered by position or position out of range");
-            prev = p;
+        if (npos[t] > 255) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 255 terms per unit");
+        // K rows ordered by position and every position present (the kernel loads term scalars as it meets them)
+        if (t == 0 || tile_kstart[t] != tile_kstart[t - 1] || tile_kcount[t] != tile_kcount[t - 1] || npos[t] != npos[t - 1]) {
+            int prev = -1;
+            for (int k = 0; k < tile_kcount[t]; ++k) {
+                const int p = k_pos[tile_kstart[t] + k];
+                if (p < prev || p > prev + 1 || p >= npos[t])
+                    return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows must be ordered by position and cover every position");
+                prev = p;
+            }
+            if (prev != npos[t] - 1) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows do not cover every term position");
         }
+        const int cls = cav_tile_class(masks[t]);
+        if (cls < cls_prev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: tiles must be ordered by size class");
+        for (int c = cls_prev + 1; c <= cls; ++c) class_begin[c] = t;
+        cls_prev = cls;
     }
-    for (int64_t k = 0; k < n_krows; ++k)
-        if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_coef[k] < 0 || k_coef[k] > 5)
+    std::vector<int> pack((size_t)n_krows);
+    for (int64_t k = 0; k < n_krows; ++k) {
+        if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_pos[k] > 255 || k_coef[k] < 0 || k_coef[k] > 5)
             return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: bad K row");
+        pack[k] = k_row[k] | (k_pos[k] << 20) | (k_coef[k] << 28);
+    }
     for (int i = 0; i < 2 * n_pair_rows; ++i)
         if (pairs[i] < 0 || pairs[i] >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: pair node out of range");
-    CK(cudaSetDevice(ctx->device));
     CK(upload(ctx, &ctx->tile_units, (const int*)tile_units, (size_t)n_tiles * tile_size));
     CK(upload(ctx, &ctx->tile_kstart, (const int*)tile_kstart, (size_t)n_tiles));
     CK(upload(ctx, &ctx->tile_kcount, (const int*)tile_kcount, (size_t)n_tiles));
     CK(upload(ctx, &ctx->tile_npos, npos.data(), (size_t)n_tiles));
-    CK(upload(ctx, &ctx->k_row, (const int*)k_row, (size_t)n_krows));
-    CK(upload(ctx, &ctx->k_pos, (const int*)k_pos, (size_t)n_krows));
-    CK(upload(ctx, &ctx->k_coef, (const int*)k_coef, (size_t)n_krows));
+    CK(upload(ctx, &ctx->k_pack, pack.data(), (size_t)n_krows));
     CK(upload(ctx, &ctx->pairs, (const int*)pairs, (size_t)2 * n_pair_rows));
+    CK(upload(ctx, &ctx->tile_mask, masks.data(), (size_t)n_tiles));
     CK(cudaStreamSynchronize(ctx->stream));
-    ctx->tile_tm = tile_size;
-    ctx->n_tiles = n_tiles; ctx->n_krows = n_krows; ctx->n_pair_rows = n_pair_rows; ctx->tiles_max_k = max_k;
+    std::memcpy(ctx->class_begin, class_begin, sizeof(class_begin));
+    ctx->n_tiles = n_tiles; ctx->n_krows = n_krows; ctx->n_pair_rows = n_pair_rows;
     ctx->tiles_valid = true; ctx->tsym_valid = false;
     return CAV_OK;
 }
@@ -598,8 +667,21 @@ static int build_sym_tables(cav_ctx* ctx) {
     k_sym_tables<<<3 * ctx->G, GT_NC, 0, ctx->stream>>>(ctx->G, ctx->g, ctx->Hf, ctx->Cf, ctx->Tsym);
     k_pair_tables<<<ctx->n_pair_rows + 1, GT_NC, 0, ctx->stream>>>(ctx->n_pair_rows, ctx->pairs, ctx->g,
                                                                     ctx->Tsym + (size_t)3 * ctx->G * GT_NC);
-    ctx->launches += 2;
+    // the tiles' active-pillar masks must cover the support of every table row they use (a wrong mask would
+    // silently drop Greeks): checked on the device whenever the tables are rebuilt
+    CK(dev_alloc(ctx, &ctx->row_masks, rows));
+    CK(dev_alloc(ctx, &ctx->check_flag, (size_t)1));
+    CK(cudaMemsetAsync(ctx->check_flag, 0, sizeof(int), ctx->stream));
+    k_row_masks<<<(unsigned)rows, GT_NC, 0, ctx->stream>>>(ctx->Tsym, ctx->row_masks);
+    k_check_tile_masks<<<(ctx->n_tiles + 127) / 128, 128, 0, ctx->stream>>>(ctx->n_tiles, ctx->tile_kstart, ctx->tile_kcount,
+                                                                          ctx->tile_mask, ctx->k_pack, ctx->row_masks,
+                                                                          ctx->check_flag);
+    ctx->launches += 4;
     CK(cudaGetLastError());
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx->check_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag) return fail(ctx, CAV_E_INVALID, "tile plan: active-pillar masks do not cover the curve tables' support");
     ctx->tsym_valid = true;
     return CAV_OK;
 }
@@ -627,12 +709,11 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (use_gemm && !ctx->tsym_valid) { int rc = build_sym_tables(ctx); if (rc) return rc; }
     int64_t rows = 0;
     int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
-    if (use_gemm) {
-        const int cap = ctx->sm_count * (ctx->tile_tm == 16 ? 2 : 1);
-        grid = ctx->n_tiles < cap ? ctx->n_tiles : cap;
-        rows = grid;
+    if (use_gemm) rows = (int64_t)simt_max_grid(ctx) * 4;          // packed partial rows, one per persistent warp
+    if (need_agg) {
+        CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * (use_gemm ? GT_NC : CAV_NOUT)));
+        if (use_gemm) CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * rows * GT_NC, ctx->stream));
     }
-    if (need_agg) CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
     UnitsArgs a;
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
     a.node = ctx->node; a.L = ctx->L; a.g = ctx->g; a.Hf = ctx->Hf; a.Cf = ctx->Cf;
@@ -654,24 +735,13 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[0], ctx->stream));
     if (use_gemm) {
-        GemmArgs ga;
-        ga.n_tiles = ctx->n_tiles; ga.tile_units = ctx->tile_units; ga.tile_kstart = ctx->tile_kstart;
-        ga.tile_kcount = ctx->tile_kcount; ga.tile_npos = ctx->tile_npos; ga.k_row = ctx->k_row; ga.k_pos = ctx->k_pos; ga.k_coef = ctx->k_coef;
-        ga.T = ctx->Tsym; ga.zero_row = 3 * ctx->G + ctx->n_pair_rows;
+        SimtArgs ga;
+        ga.tile_units = ctx->tile_units; ga.tile_kstart = ctx->tile_kstart; ga.tile_kcount = ctx->tile_kcount;
+        ga.tile_npos = ctx->tile_npos; ga.tile_mask = ctx->tile_mask; ga.k_pack = ctx->k_pack; ga.T = ctx->Tsym;
         ga.unit_offsets = a.unit_offsets; ga.amt = a.amt; ga.weight = a.weight; ga.node = a.node; ga.L = a.L;
         ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
         ga.out_gamma = a.out_gamma; ga.partials = a.partials;
-        const int tm = ctx->tile_tm, mgc = tm / 16;
-        const size_t smem = (size_t)(tm * GT_LDA + 3 * tm * GT_PC + 8 * mgc * GT_LDS + tm) * sizeof(double) +
-                            (3 * GT_KC + 32) * sizeof(int) + 2 * 32 * sizeof(int64_t) + 32 * sizeof(double);
-        if (mgc == 2) {
-            CK(cudaFuncSetAttribute(k_units_gemm<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_units_gemm<2><<<grid, 256, smem, ctx->stream>>>(ga);
-        } else {
-            CK(cudaFuncSetAttribute(k_units_gemm<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_units_gemm<1><<<grid, 256, smem, ctx->stream>>>(ga);
-        }
-        ctx->launches++;
+        launch_simt_classes(ctx, ga);
     } else if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
     else launch_units<6>(ctx, a, want_d, want_g, grid);
     CK(cudaGetLastError());
@@ -701,7 +771,8 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[2], ctx->stream));
     if (need_agg) {
         double* dst = agg_dev ? agg_dev : ctx->agg;
-        k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
+        if (use_gemm) k_reduce_packed<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
+        else k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
         ctx->launches++;
         CK(cudaGetLastError());
         if (ctx->profile) { CK(cudaEventRecord(ctx->evk[3], ctx->stream)); ctx->evk_n = 4; }

@@ -248,23 +248,27 @@ k_units(UnitsArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
-// Tensor-core units kernel.  For units that bracket the same node pairs term by term,
+// Tiled units kernel (k_units_simt).  For units that bracket the same node pairs term by term,
 //   [gamma (528 packed lower-triangle entries) | delta (32)] [units x 560] = A[units x K] . B[K x 560]
 // where the K rows of B come from per-curve symmetric tables (built by k_sym_tables / k_pair_tables)
 //   H_n = hess(ln d_n)|g_n,  C_n = (H_n + g_n g_n^T)|g_n,  G_nn = g_n g_n^T|0,  G_ab = (g_a g_b^T + g_b g_a^T)|0
 // and only the coefficients A (p, p w0, p w1, p w0^2, p w1^2, p w0 w1) depend on the unit
-// (adrates_b200/tiles.py).  One CTA = one tile of 32 units x all 576 padded columns, FP64 DMMA
-// (mma.sync.m8n8k4).  Per chunk of 48 term positions the CTA evaluates p = amt*DF once per term, builds A in
-// shared memory, then runs the K loop with B fragments read straight from the L2-resident tables (each table
-// row is read once per tile, not once per unit); the epilogue stages 8 units at a time in shared memory and
-// writes full symmetric 32x32 rows with 32-byte stores.
+// (adrates_b200/tiles.py).  A tile is 4 units with the same K rows; one warp owns a tile end to end (no CTA
+// barriers: phases of different warps overlap freely and the SM hides latency with warps, not with a
+// hand-built pipeline).
+//
+// Column compaction: a tile's Greeks are non-zero only on its active pillars (tile_mask, na bits).  The
+// warp works on the na(na+1)/2 packed gamma columns of the active pillars plus their na delta columns instead
+// of all 528 + 32; lane l owns compact columns l, l+32, ... (NI of them, template parameter = size class of
+// the tile), each mapped to a table column cn[i].  Per K row: NI table loads and U*NI DFMAs, with the row's
+// coefficient of each unit broadcast by one shuffle from the lane that holds the term.
+// The epilogue scatters the compact accumulators back into full symmetric 32x32 rows (zeros elsewhere)
+// through a per-warp staging row and writes them with 32-byte stores.
 // ------------------------------------------------------------------------------------------
-#define GT_TM 32          // largest tile (MG = 2)
-#define GT_NC 576
+#define GT_NC 576          // table row length: 528 packed gamma entries + 32 delta columns + 16 zeros
 #define GT_NPACK 528
-#define GT_KC 256
-#define GT_LDA 268
-#define GT_LDS 584
+#define GT_TM 4            // units per tile
+#define GT_PV_COL (GT_NPACK + CAV_RW + 1)   // column of the packed partial rows that carries the PV total
 
 __device__ __forceinline__ int gt_packed(int j, int k) { return j >= k ? j * (j + 1) / 2 + k : k * (k + 1) / 2 + j; }
 
@@ -307,17 +311,51 @@ k_pair_tables(int n_pairs, const int* __restrict__ pairs, const double* __restri
     Trows[(size_t)i * GT_NC + e] = v;
 }
 
-struct GemmArgs {
-    int n_tiles;
-    const int* tile_units;     // [n_tiles][32], -1 = padding
+// pillar-support bit mask of every table row (bit r: the row has a non-zero in a column that involves pillar r)
+__global__ void __launch_bounds__(GT_NC)
+k_row_masks(const double* __restrict__ T, unsigned* masks)
+{
+    __shared__ unsigned s_m;
+    const int row = blockIdx.x, e = threadIdx.x;
+    if (e == 0) s_m = 0u;
+    __syncthreads();
+    const double v = T[(size_t)row * GT_NC + e];
+    unsigned m = 0u;
+    if (v != 0.0) {
+        if (e < GT_NPACK) {
+            int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+            while (j * (j + 1) / 2 > e) --j;
+            while ((j + 1) * (j + 2) / 2 <= e) ++j;
+            m = (1u << j) | (1u << (e - j * (j + 1) / 2));
+        } else if (e < GT_NPACK + CAV_RW) m = 1u << (e - GT_NPACK);
+    }
+    if (m) atomicOr(&s_m, m);
+    __syncthreads();
+    if (e == 0) masks[row] = s_m;
+}
+
+// every K row of every tile must live on the tile's active pillars; *flag != 0 otherwise
+__global__ void k_check_tile_masks(int n_tiles, const int* __restrict__ tile_kstart, const int* __restrict__ tile_kcount,
+                                   const unsigned* __restrict__ tile_mask, const int* __restrict__ k_pack,
+                                   const unsigned* __restrict__ row_masks, int* flag)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    if (t > 0 && tile_kstart[t] == tile_kstart[t - 1] && tile_mask[t] == tile_mask[t - 1]) return;   // same group
+    const unsigned allowed = tile_mask[t];
+    unsigned bad = 0u;
+    for (int k = 0; k < tile_kcount[t]; ++k) bad |= row_masks[k_pack[tile_kstart[t] + k] & 0xFFFFF] & ~allowed;
+    if (bad) atomicExch(flag, 1);
+}
+
+struct SimtArgs {
+    const int* tile_units;     // [n_tiles][GT_TM], -1 = padding
     const int* tile_kstart;
     const int* tile_kcount;
     const int* tile_npos;
-    const int* k_row;
-    const int* k_pos;
-    const int* k_coef;
-    const double* T;           // symmetric tables [rows][576]
-    int zero_row;
+    const unsigned* tile_mask; // [n_tiles] active par-rate pillars of the tile
+    const int* k_pack;         // per K row: table row (20 bits) | term position << 20 (8 bits) | coefficient kind << 28
+    const double* T;           // symmetric tables [rows][GT_NC]
     const int64_t* unit_offsets;
     const double* amt;
     const double* weight;      // [n_terms][2]
@@ -328,181 +366,208 @@ struct GemmArgs {
     double* out_pv;
     double* out_delta;
     double* out_gamma;
-    double* partials;          // [gridDim.x][1057] or null
+    double* partials;          // [warps of the largest grid][GT_NC] packed totals per persistent warp, or null
 };
 
-#define GT_PC 48                 // term positions per chunk (<= 240 K rows <= GT_KC)
-// MG = m-groups per CTA: a tile has TM = 16*MG units; warp (mg, ng) owns m-tiles {2mg, 2mg+1} x NT n-tiles.
-// MG = 2: one CTA per SM (254 registers).  MG = 1: half the accumulators per warp, two CTAs per SM whose
-// scalar / epilogue phases overlap each other's MMA phase (each table row is then read once per 16 units).
-template <int MG>
-__global__ void __launch_bounds__(256, 3 - MG)
-k_units_gemm(GemmArgs a)
+// per-warp shared memory (doubles): stage[32 NI + 8] | 1056 x u16 epilogue indices | 32 x int pillars |
+// term scalars p, w0, w1 [U][32] | unit PVs [U]
+template <int NI, int U>
+struct SimtSmem {
+    static constexpr int STAGE = 32 * NI + 8;
+    static constexpr int ZSLOT = 32 * NI;          // staging slot that is always zero
+    static constexpr int IDX = STAGE;               // u16 [1056]
+    static constexpr int PIL = IDX + 264;           // int [32]
+    static constexpr int TERM = PIL + 16;           // double [3][U][32]
+    static constexpr int PV = TERM + 3 * U * 32;    // double [U]
+    static constexpr int TOTAL = PV + ((U + 7) & ~7);
+};
+
+template <int NI, int U, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+k_units_simt(SimtArgs a, int tile_begin, int tile_end)
 {
-    constexpr int TM = 16 * MG;            // units per tile
-    constexpr int NG = 8 / MG;             // n-groups (warps along N)
-    constexpr int NT = 72 / NG;            // n-tiles per warp
-    constexpr int NW = NT * 8;             // columns per warp
-    extern __shared__ double smem[];
-    double* sA = smem;                                   // [32][GT_LDA]
-    double* sTp = sA + TM * GT_LDA;                   // [32][GT_PC] p
-    double* sTw0 = sTp + TM * GT_PC;                  // [32][GT_PC] w0
-    double* sTw1 = sTw0 + TM * GT_PC;                 // [32][GT_PC] w1
-    double* sStage = sTw1 + TM * GT_PC;               // [16][GT_LDS]
-    double* sPv = sStage + 8 * MG * GT_LDS;              // [TM]
-    int* sRow = reinterpret_cast<int*>(sPv + TM);        // [GT_KC]
-    int* sPos = sRow + GT_KC;
-    int* sCoef = sPos + GT_KC;
-    int* sUnit = sCoef + GT_KC;                          // [32]
-    int64_t* sOff = reinterpret_cast<int64_t*>(sUnit + 32);   // [32] first term of each unit
-    int64_t* sOut = sOff + 32;                                // [32] output row of each unit
-    double* sW = reinterpret_cast<double*>(sOut + 32);        // [32] portfolio weight of each unit
-
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    const int mg = wib / NG, ng = wib % NG;
-    const int ar = lane >> 2, ac = lane & 3;
-    const int oj = tid >> 3, ok4 = (tid & 7) * 4;        // epilogue: this thread owns gamma entries (oj, ok4..ok4+3)
-    int pk[4];
+    using SM = SimtSmem<NI, U>;
+    __shared__ double smem[4 * SM::TOTAL];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double* stage = smem + wib * SM::TOTAL;
+    unsigned short* sidx = reinterpret_cast<unsigned short*>(stage + SM::IDX);   // [1024] gamma entry -> stage slot, [32] delta
+    int* sPil = reinterpret_cast<int*>(stage + SM::PIL);                         // [32] active pillars, ascending
+    double* sP = stage + SM::TERM;                 // [U][32] p = amt * DF of the current 32 term positions
+    double* sW0 = sP + U * 32;
+    double* sW1 = sW0 + U * 32;
+    double* sPv = stage + SM::PV;
+    const int gw = blockIdx.x * 4 + wib, nw = gridDim.x * 4;
+    double* my_part = a.partials ? a.partials + (size_t)gw * GT_NC : nullptr;
+    unsigned cur_mask = 0u;
+    bool have_mask = false;
+    int cn[NI];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) pk[q] = gt_packed(oj, ok4 + q);
-    double tg[4] = {0.0, 0.0, 0.0, 0.0}, td = 0.0, tp = 0.0;
+    for (int i = 0; i < NI; ++i) cn[i] = GT_NPACK + CAV_RW;
+    if (lane == 0) stage[SM::ZSLOT] = 0.0;
 
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int tile = tile_begin + gw; tile < tile_end; tile += nw) {
         const int K = a.tile_kcount[tile], ks = a.tile_kstart[tile], P = a.tile_npos[tile];
-        __syncthreads();
-        if (tid < TM) {
-            const int uid = a.tile_units[tile * TM + tid];
-            sUnit[tid] = uid;
-            sOff[tid] = uid >= 0 ? a.unit_offsets[uid] : 0;
-            sOut[tid] = uid >= 0 ? (a.out_index ? a.out_index[uid] : uid) : 0;
-            sW[tid] = (uid >= 0 && a.unit_weight) ? a.unit_weight[uid] : 1.0;
-            sPv[tid] = 0.0;
+        const unsigned mask = a.tile_mask[tile];
+        if (!have_mask || mask != cur_mask) {
+            // column map of this lane and the epilogue index table of this warp
+            const int na = __popc(mask), nc = na * (na + 1) / 2, ncols = nc + na;
+            __syncwarp();
+            if ((mask >> lane) & 1u) sPil[__popc(mask & ((1u << lane) - 1u))] = lane;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int cc = lane + 32 * i;
+                int col = GT_NPACK + CAV_RW;                 // a zero column of the tables
+                if (cc < nc) {
+                    int j = (int)((sqrtf(8.0f * cc + 1.0f) - 1.0f) * 0.5f);
+                    while (j * (j + 1) / 2 > cc) --j;
+                    while ((j + 1) * (j + 2) / 2 <= cc) ++j;
+                    const int pj = sPil[j], pk2 = sPil[cc - j * (j + 1) / 2];
+                    col = pj * (pj + 1) / 2 + pk2;
+                } else if (cc < ncols) col = GT_NPACK + sPil[cc - nc];
+                cn[i] = col;
+            }
+            const int ik = ((mask >> lane) & 1u) ? __popc(mask & ((1u << lane) - 1u)) : -1;
+            for (int j = 0; j < CAV_RW; ++j) {
+                const int ij = ((mask >> j) & 1u) ? __popc(mask & ((1u << j) - 1u)) : -1;
+                sidx[j * CAV_RW + lane] = (unsigned short)((ij < 0 || ik < 0) ? SM::ZSLOT
+                                                           : (ij >= ik ? ij * (ij + 1) / 2 + ik : ik * (ik + 1) / 2 + ij));
+            }
+            sidx[CAV_RR + lane] = (unsigned short)(ik < 0 ? SM::ZSLOT : nc + ik);
+            cur_mask = mask;
+            have_mask = true;
+            __syncwarp();
         }
-        double c[2][NT][2];
-#pragma unroll
-        for (int m = 0; m < 2; ++m)
-#pragma unroll
-            for (int n = 0; n < NT; ++n) c[m][n][0] = c[m][n][1] = 0.0;
 
-        int kdone = 0;                                   // K rows are ordered by position
-        for (int p0 = 0; p0 < P; p0 += GT_PC) {
-            const int pc = (P - p0) < GT_PC ? (P - p0) : GT_PC;
-            __syncthreads();                             // previous chunk consumed; sUnit/sOff visible
-            // (1) term scalars of this chunk: p = amt * DF, w0, w1 for 32 units x pc positions
-            for (int idx = tid; idx < TM * GT_PC; idx += 256) {
-                const int u = idx / GT_PC, j = idx - u * GT_PC;
-                double p = 0.0, w0 = 0.0, w1 = 0.0;
-                if (j < pc && sUnit[u] >= 0) {
-                    const int64_t i = sOff[u] + p0 + j;
-                    const double2 w = reinterpret_cast<const double2*>(a.weight)[i];
-                    const int2 n = reinterpret_cast<const int2*>(a.node)[i];
-                    w0 = w.x; w1 = w.y;
-                    p = a.amt[i] * exp(w.x * a.L[n.x] + w.y * a.L[n.y]);
-                }
-                sTp[idx] = p; sTw0[idx] = w0; sTw1[idx] = w1;
-            }
-            // K rows of this chunk: [kdone, kend) with k_pos < p0 + pc
-            int kend = K;
-            if (p0 + pc < P) {   // first K row with position >= p0 + pc (rows are ordered by position)
-                int lo = kdone, hi = K;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (a.k_pos[ks + mid] < p0 + pc) lo = mid + 1; else hi = mid;
-                }
-                kend = lo;
-            }
-            const int kc = kend - kdone;
-            const int kc4 = (kc + 3) & ~3;
-            for (int k = tid; k < kc4; k += 256) {
-                sRow[k] = (k < kc) ? a.k_row[ks + kdone + k] : a.zero_row;
-                sPos[k] = (k < kc) ? a.k_pos[ks + kdone + k] - p0 : 0;
-                sCoef[k] = (k < kc) ? a.k_coef[ks + kdone + k] : -1;
-            }
-            __syncthreads();
-            // unit PVs (sum over positions) and the coefficient matrix A
-            {   // 8 threads per unit, fixed order
-                const int u = (tid >> 3) % TM, sub = tid & 7;
-                double pv = 0.0;
-                for (int j = sub; j < pc; j += 8) pv += sTp[u * GT_PC + j];
-                pv += __shfl_xor_sync(0xffffffffu, pv, 1);
-                pv += __shfl_xor_sync(0xffffffffu, pv, 2);
-                pv += __shfl_xor_sync(0xffffffffu, pv, 4);
-                if (sub == 0 && (tid >> 3) < TM) sPv[u] += pv;
-            }
-            for (int k = lane; k < kc4; k += 32) {
-                const int cf = sCoef[k], pos = sPos[k];
+#pragma unroll 1
+        for (int h = 0; h < GT_TM; h += U) {
+            const int* units = a.tile_units + tile * GT_TM + h;
+            double acc[U][NI];
 #pragma unroll
-                for (int uu = 0; uu < TM / 8; ++uu) {
-                    const int u = wib + 8 * uu;
-                    double v = 0.0;
-                    if (cf >= 0) {
-                        const int t = u * GT_PC + pos;
-                        const double p = sTp[t], w0 = sTw0[t], w1 = sTw1[t];
-                        v = cf == 0 ? p : cf == 1 ? p * w0 : cf == 2 ? p * w1 : cf == 3 ? p * w0 * w0
-                          : cf == 4 ? p * w1 * w1 : p * w0 * w1;
+            for (int u = 0; u < U; ++u)
+#pragma unroll
+                for (int i = 0; i < NI; ++i) acc[u][i] = 0.0;
+            if (lane < U) sPv[lane] = 0.0;
+            // K rows come in windows of 32 (lane = row of the window); term scalars in chunks of 32 positions
+            // (lane = position, kept in shared memory).  Rows are ordered by position, so the rows of a chunk
+            // are a prefix of what is left of the window.  Per (window, chunk) segment every lane first forms
+            // the coefficients of its own row for the U units; the row loop then only broadcasts them.
+            int r0 = 0, start = 0;
+            int mypack = (lane < K) ? __ldg(a.k_pack + ks + lane) : 0;
+            for (int c0 = 0; c0 < P; c0 += 32) {
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int uid = __ldg(units + u);
+                    double pp = 0.0, x0 = 0.0, x1 = 0.0;
+                    if (uid >= 0 && c0 + lane < P) {
+                        const int64_t i = __ldg(a.unit_offsets + uid) + c0 + lane;
+                        const double2 w = __ldg(reinterpret_cast<const double2*>(a.weight) + i);
+                        const int2 n = __ldg(reinterpret_cast<const int2*>(a.node) + i);
+                        x0 = w.x; x1 = w.y;
+                        pp = __ldg(a.amt + i) * exp(w.x * __ldg(a.L + n.x) + w.y * __ldg(a.L + n.y));
                     }
-                    sA[u * GT_LDA + k] = v;
+                    sP[u * 32 + lane] = pp; sW0[u * 32 + lane] = x0; sW1[u * 32 + lane] = x1;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) pp += __shfl_xor_sync(0xffffffffu, pp, o);
+                    if (lane == 0) sPv[u] += pp;
                 }
-            }
-            __syncthreads();
-            const double* A0 = sA + (mg * 16 + ar) * GT_LDA + ac;
-            const double* A1 = A0 + 8 * GT_LDA;
+                __syncwarp();
+                for (;;) {
+                    const int wn = (K - r0) < 32 ? (K - r0) : 32;
+                    const int pos = (mypack >> 20) & 0xFF, cf = (mypack >> 28) & 7;
+                    const bool mine = lane < wn && pos < c0 + 32;
+                    const int n_in = __popc(__ballot_sync(0xffffffffu, mine));
+                    const int mybase = (mypack & 0xFFFFF) * GT_NC;
+                    double cw[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int t = u * 32 + (pos & 31);
+                        const double x0 = sW0[t], x1 = sW1[t];
+                        const double f1 = (cf == 1 || cf == 3 || cf == 5) ? x0 : ((cf == 2 || cf == 4) ? x1 : 1.0);
+                        const double f2 = cf == 3 ? x0 : ((cf == 4 || cf == 5) ? x1 : 1.0);
+                        cw[u] = mine ? sP[t] * f1 * f2 : 0.0;
+                    }
 #pragma unroll 2
-            for (int k = 0; k < kc4; k += 4) {
-                const double a0 = A0[k], a1 = A1[k];
-                const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC + ng * NW + ar;
+                    for (int rr = start; rr < n_in; ++rr) {
+                        const int base = __shfl_sync(0xffffffffu, mybase, rr);
+                        double b[NI];
 #pragma unroll
-                for (int n = 0; n < NT; ++n) {
-                    const double b = __ldg(rowp + n * 8);
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                 : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(b));
-                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                 : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1), "d"(b));
+                        for (int i = 0; i < NI; ++i) b[i] = __ldg(a.T + (base + cn[i]));
+                        double c[U];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) c[u] = __shfl_sync(0xffffffffu, cw[u], rr);
+#pragma unroll
+                        for (int i = 0; i < NI; ++i)
+#pragma unroll
+                            for (int u = 0; u < U; ++u) acc[u][i] = fma(c[u], b[i], acc[u][i]);
+                    }
+                    start = n_in;
+                    if (n_in < wn || r0 + wn >= K) break;     // the chunk ends inside this window / no rows left
+                    r0 += 32;
+                    start = 0;
+                    mypack = (r0 + lane < K) ? __ldg(a.k_pack + ks + r0 + lane) : 0;
                 }
             }
-            kdone = kend;
-        }
-        // ---- epilogue: stage 8 units per m-group, expand to full symmetric rows ----
+            // ---- epilogue: one unit at a time through the staging row ----
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) {
-            __syncthreads();                             // stage buffers free
-            double* st = sStage + (size_t)(mg * 8 + ar) * GT_LDS + ng * NW + 2 * ac;
+            for (int u = 0; u < U; ++u) {
+                const int uid = __ldg(units + u);
+                if (uid < 0) continue;               // warp-uniform
+                __syncwarp();
 #pragma unroll
-            for (int n = 0; n < NT; ++n)
-                *reinterpret_cast<double2*>(st + n * 8) = make_double2(c[mt][n][0], c[mt][n][1]);
-            __syncthreads();
-            for (int s = 0; s < 8 * MG; ++s) {
-                const int u = (s >> 3) * 16 + mt * 8 + (s & 7);
-                const int uid = sUnit[u];
-                if (uid < 0) continue;
-                const double* row_s = sStage + (size_t)s * GT_LDS;
-                const int64_t row = sOut[u];
-                const double W = sW[u];
-                const double g0 = row_s[pk[0]], g1 = row_s[pk[1]], g2 = row_s[pk[2]], g3 = row_s[pk[3]];
+                for (int i = 0; i < NI; ++i) stage[lane + 32 * i] = acc[u][i];
+                __syncwarp();
+                const int64_t orow = a.out_index ? a.out_index[uid] : uid;
                 if (a.out_gamma) {
-                    double* dst = a.out_gamma + (size_t)row * CAV_RR + oj * CAV_RW + ok4;
-                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
+                    double* dst = a.out_gamma + (size_t)orow * CAV_RR + lane * 4;
+#pragma unroll
+                    for (int s8 = 0; s8 < 8; ++s8) {
+                        const uint2 ix = *reinterpret_cast<const uint2*>(sidx + (s8 * 32 + lane) * 4);
+                        const double g0 = stage[ix.x & 0xFFFFu], g1 = stage[ix.x >> 16];
+                        const double g2 = stage[ix.y & 0xFFFFu], g3 = stage[ix.y >> 16];
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
+                                     :: "l"(dst + s8 * 128), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
+                    }
                 }
-                tg[0] += W * g0; tg[1] += W * g1; tg[2] += W * g2; tg[3] += W * g3;
-                if (tid < CAV_RW) {
-                    const double dl = row_s[GT_NPACK + tid];
-                    if (a.out_delta) a.out_delta[(size_t)row * CAV_RW + tid] = dl;
-                    td += W * dl;
+                if (a.out_delta) a.out_delta[(size_t)orow * CAV_RW + lane] = stage[sidx[CAV_RR + lane]];
+                if (a.out_pv && lane == 0) a.out_pv[orow] = sPv[u];
+            }
+            if (my_part) {     // this warp owns its partial row: plain read-modify-write, fixed order
+                double W[U], tpv = 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int uid = __ldg(units + u);
+                    W[u] = uid < 0 ? 0.0 : (a.unit_weight ? a.unit_weight[uid] : 1.0);
+                    tpv = fma(W[u], sPv[u], tpv);
                 }
-                if (tid == 32) {
-                    if (a.out_pv) a.out_pv[row] = sPv[u];
-                    tp += W * sPv[u];
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    double t = 0.0;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) t = fma(W[u], acc[u][i], t);
+                    if (cn[i] < GT_NPACK + CAV_RW) my_part[cn[i]] += t;
                 }
+                if (lane == 0) my_part[GT_PV_COL] += tpv;
             }
         }
     }
-    if (a.partials) {
-        double* P = a.partials + (size_t)blockIdx.x * CAV_NOUT;
+}
+
+// totals[1057] = PV | delta[32] | gamma[32][32] from the packed per-warp partial rows [n_rows][GT_NC];
+// one warp per output entry, lane-strided sums combined in a fixed butterfly (bitwise reproducible for a grid)
+__global__ void __launch_bounds__(256)
+k_reduce_packed(const double* __restrict__ partials, int64_t n_rows, double* totals)
+{
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (e >= CAV_NOUT) return;
+    const int col = e == 0 ? GT_PV_COL : (e <= CAV_RW ? GT_NPACK + e - 1 : gt_packed((e - 33) >> 5, (e - 33) & 31));
+    double s = 0.0;
+    for (int64_t w = lane; w < n_rows; w += 32) s += partials[w * GT_NC + col];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) P[33 + oj * CAV_RW + ok4 + q] = tg[q];
-        if (tid < CAV_RW) P[1 + tid] = td;
-        if (tid == 32) P[0] = tp;
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) totals[e] = s;
 }
 
 // totals[e] = sum_rows partials[row][e]; one warp per entry, lane-strided partial sums combined

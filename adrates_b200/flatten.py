@@ -58,14 +58,17 @@ class FlatPortfolio:
                 self.group_units, self.unit_weight] + ([self.out_index] if self.out_index is not None else [])
         tp = self.tile_plan
         if tp is not None:
-            arrs += [tp.tile_units, tp.tile_kstart, tp.tile_kcount, tp.k_row, tp.k_pos, tp.k_coef, tp.pairs]
+            arrs += [tp.tile_units, tp.tile_kstart, tp.tile_kcount, tp.k_row, tp.k_pos, tp.k_coef, tp.pairs, tp.tile_mask]
         return int(sum(a.nbytes for a in arrs))
 
-    def with_tiles(self, n_nodes: int) -> "FlatPortfolio":
-        """Attach a tile plan (adrates_b200/tiles.py) when every unit consists of single-DF terms."""
-        from .tiles import plan_tiles
+    def with_tiles(self, n_nodes: int, plan=None) -> "FlatPortfolio":
+        """Attach a tile plan (adrates_b200/tiles.py) when every unit consists of single-DF terms.
+        plan: the curve's PathBPlan; its dependency structure gives the active par-rate pillars of each tile
+        (column compaction of the tile GEMM).  Without it every pillar is treated as active."""
+        from .tiles import plan_tiles, node_support_masks
         if self.n_pairs == 2 and self.n_units > 0:
-            tp = plan_tiles(self, n_nodes)
+            support = None if plan is None else node_support_masks(plan.node_swap, plan.node_prev, plan.node_acc)
+            tp = plan_tiles(self, n_nodes, support=support)
             if len(tp.leftover_units) == 0:
                 self.tile_plan = tp
         return self

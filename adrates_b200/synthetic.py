@@ -68,9 +68,12 @@ def make_book(curve: OISCurve, n_trades: int, seed: int = 20240430, max_offset_b
 
 
 def flatten_book(book: Book, dedup: bool = True, max_group: int = 256, sort_units: bool = True,
-                 tiles: bool = True) -> FlatPortfolio:
+                 tiles: bool = True, compact: bool = True) -> FlatPortfolio:
     flat = _flatten_book(book, dedup, max_group, sort_units)
-    return flat.with_tiles(book.curve.path_b_plan().n_nodes) if tiles else flat
+    if not tiles:
+        return flat
+    plan = book.curve.path_b_plan()
+    return flat.with_tiles(plan.n_nodes, plan if compact else None)
 
 
 def _flatten_book(book: Book, dedup: bool, max_group: int, sort_units: bool) -> FlatPortfolio:

@@ -1,4 +1,4 @@
-"""Tile planner for the tensor-core units kernel (k_units_gemm).
+"""Tile planner for the tiled units kernel (k_units_simt).
 
 The Greeks of a unit are a linear combination of curve-only matrices.  With v = w0 g_a + w1 g_b and
 H_n = hess(ln d_n), a bracketed term contributes
@@ -9,8 +9,10 @@ H_n = hess(ln d_n), a bracketed term contributes
 so for units that bracket the same node pairs position by position ("same signature"),
 gamma[units x 528 packed entries | 32 delta columns] = A[units x K] . B[K x 560] with B rows taken from
 per-curve symmetric tables and only the K coefficients A depending on the unit.  That is a dense FP64 GEMM
-per tile of 32 units, which the kernel runs on the tensor pipe (mma.sync.m8n8k4.f64); each table row is read
-once per tile instead of once per unit.
+per tile; the kernel gives each tile of TM units to one warp (lane = compact column, DFMA), so each table row is
+read once per tile instead of once per unit.  Only the columns of the tile's *active* par-rate pillars are
+computed (tile_mask, from the dependency structure of the bootstrap plan); tiles are ordered by size class
+(number of compact columns / 32) because the kernel is instantiated per class.
 
 This module groups units by signature, cuts the groups into tiles of TM units and emits, per group, the list
 of K rows: (table row id, term position, coefficient kind).  Units whose terms are not single-DF brackets
@@ -22,7 +24,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-TM = int(__import__("os").environ.get("CAV_TILE_SIZE", "16"))   # units per tile: 16 (two CTAs per SM) or 32
+TM = 4             # units per tile (one warp of k_units_simt owns a tile)
 NCOL = 576         # padded row length: 528 packed gamma entries + 32 delta columns + 16 zeros
 NPACK = 528
 
@@ -42,6 +44,7 @@ class TilePlan:
     k_pos: np.ndarray         # i32 term position the coefficient comes from
     k_coef: np.ndarray        # i32 coefficient kind
     pairs: np.ndarray         # i32 [n_pair_rows*2] (a, b) node pairs that need a G_ab row
+    tile_mask: np.ndarray     # u32 [n_tiles] bit r set = par-rate pillar r can be non-zero in this tile's Greeks
     n_table_rows: int         # 3*G + n_pair_rows (+1 zero row appended by the library)
     leftover_units: np.ndarray  # i32 units not covered by tiles (generic kernel)
 
@@ -62,10 +65,36 @@ def row_Gnn(n, G):
     return 2 * G + n
 
 
-def plan_tiles(flat, G: int, min_group: int = 1) -> TilePlan:
-    """flat: FlatPortfolio with n_pairs == 2.  G: number of curve nodes."""
+def node_support_masks(node_swap, node_prev, node_acc=None) -> np.ndarray:
+    """u32 [G]: bit r set when ln d_n can depend on par rate r.  From the bootstrap recursion
+    d_i = (1 - r_s P_p)/(1 + r_s a), P_i = P_p + a d_i (engine.py:2341-2347): supp(d_i) = {s} U supp(P_p),
+    supp(P_i) = supp(P_p) U supp(d_i).  The second-order tables H_n, C_n live on supp x supp."""
+    G = len(node_swap)
+    md = np.zeros(G, dtype=np.uint32)
+    mp = np.zeros(G, dtype=np.uint32)
+    for i in range(G):
+        p = int(node_prev[i])
+        base = mp[p] if p >= 0 else np.uint32(0)
+        if p < 0 and node_acc is not None and node_acc[i] == 0.0:
+            continue          # root node: d = 1/(1 + r*0) = 1, no dependence on any rate
+        md[i] = base | np.uint32(1 << int(node_swap[i]))
+        mp[i] = base | md[i]
+    return md
+
+
+def tile_class(mask: int) -> int:
+    """Size class of a tile (mirrors cav_tile_class in csrc/cav_api.cu)."""
+    na = bin(int(mask)).count("1")
+    ni = (na * (na + 3) // 2 + 31) // 32
+    return 0 if ni <= 2 else 1 if ni <= 4 else 2 if ni <= 6 else 3 if ni <= 8 else 4 if ni <= 12 else 5
+
+
+def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = None) -> TilePlan:
+    """flat: FlatPortfolio with n_pairs == 2.  G: number of curve nodes.  support: u32 [G] pillar masks of the
+    nodes (node_support_masks) or None = every pillar is active everywhere (no column compaction)."""
     if flat.n_pairs != 2:
         raise ValueError("tile planner handles single-DF terms only")
+    full = np.uint32(0xFFFFFFFF)
     w = flat.weight.reshape(-1, 2)
     nd = flat.node.reshape(-1, 2).astype(np.int64)
     off = flat.unit_offsets
@@ -78,7 +107,7 @@ def plan_tiles(flat, G: int, min_group: int = 1) -> TilePlan:
         groups.setdefault(key[off[u]:off[u + 1]].tobytes(), []).append(u)
     pair_index = {}
     k_row, k_pos, k_coef = [], [], []
-    t_units, t_kstart, t_kcount, t_npos = [], [], [], []
+    t_units, t_kstart, t_kcount, t_npos, t_mask = [], [], [], [], []
     leftover = []
     for sig, units in groups.items():
         if len(units) < min_group:
@@ -86,6 +115,14 @@ def plan_tiles(flat, G: int, min_group: int = 1) -> TilePlan:
             continue
         ks = np.frombuffer(sig, dtype=np.int64)
         kstart = len(k_row)
+        mask = full
+        if support is not None:
+            kn = (ks >> 40)
+            na_all = ((ks >> 20) & 0xFFFFF)
+            nb_all = (ks & 0xFFFFF)[kn == 2]
+            mask = np.bitwise_or.reduce(support[na_all]) if len(na_all) else np.uint32(0)
+            if len(nb_all):
+                mask = mask | np.bitwise_or.reduce(support[nb_all])
         for j, kk in enumerate(ks):
             knd, na, nb = int(kk >> 40), int((kk >> 20) & 0xFFFFF), int(kk & 0xFFFFF)
             if knd == 0:
@@ -108,7 +145,15 @@ def plan_tiles(flat, G: int, min_group: int = 1) -> TilePlan:
             t_kstart.append(kstart)
             t_kcount.append(kcount)
             t_npos.append(len(ks))
+            t_mask.append(mask)
     n_tiles = len(t_units)
+    if n_tiles:      # order tiles by size class (stable: neighbours keep sharing table rows)
+        order = np.argsort(np.array([tile_class(m) for m in t_mask]), kind="stable")
+        t_units = [t_units[i] for i in order]
+        t_kstart = [t_kstart[i] for i in order]
+        t_kcount = [t_kcount[i] for i in order]
+        t_npos = [t_npos[i] for i in order]
+        t_mask = [t_mask[i] for i in order]
     pairs = np.zeros((len(pair_index), 2), dtype=np.int32)
     for (na, nb), pi in pair_index.items():
         pairs[pi] = (na, nb)
@@ -117,7 +162,8 @@ def plan_tiles(flat, G: int, min_group: int = 1) -> TilePlan:
         np.concatenate(t_units).astype(np.int32) if n_tiles else np.zeros(0, dtype=np.int32),
         np.array(t_kstart, dtype=np.int32), np.array(t_kcount, dtype=np.int32), np.array(t_npos, dtype=np.int32),
         np.array(k_row, dtype=np.int32), np.array(k_pos, dtype=np.int32), np.array(k_coef, dtype=np.int32),
-        pairs.reshape(-1), 3 * G + len(pair_index), np.array(leftover, dtype=np.int32))
+        pairs.reshape(-1), np.array(t_mask, dtype=np.uint32), 3 * G + len(pair_index),
+        np.array(leftover, dtype=np.int32))
 
 
 def packed_index(j: int, k: int) -> int:

@@ -130,10 +130,14 @@ int cav_portfolio_upload(cav_ctx* ctx,
  * [tile_kstart[t], tile_kstart[t] + tile_kcount[t]) of (k_row = table row id, k_pos = term position within the
  * unit, k_coef = 0:p 1:p*w0 2:p*w1 3:p*w0^2 4:p*w1^2 5:p*w0*w1).  Table row ids: n (H), G+n (C), 2G+n (g g^T),
  * 3G+i (pair i).  Replaces the same reference code as cav_portfolio_value; it only changes how it is computed.
+ * tile_mask[n_tiles] (or NULL = all pillars): bit r set when par-rate pillar r can be non-zero in the tile's Greeks
+ * (union of the supports of the nodes its terms touch; adrates_b200/tiles.py::node_support_masks derives it from
+ * the bootstrap plan).  The tile GEMM then runs over the packed columns of the active pillars only; the masks are
+ * checked on the device against the tables (CAV_E_INVALID from the valuation call if a mask is too small).
  * Must be called after every cav_portfolio_upload (which clears the plan). */
 int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int32_t* tile_units, const int32_t* tile_kstart,
                             const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
-                            const int32_t* k_coef, int n_pair_rows, const int32_t* pairs);
+                            const int32_t* k_coef, int n_pair_rows, const int32_t* pairs, const uint32_t* tile_mask);
 
 /* ---- valuation: replaces Position.compute / Portfolio.compute ----------------------
  * (cavour/market/position/position.py:62-80, cavour/market/portfolio/portfolio.py:39-67,

@@ -217,8 +217,8 @@ def test_error_behaviour():
     ctx.close()
 
 
-@pytest.mark.parametrize("dedup", [True, False])
-def test_synthetic_book_matches_c_oracle(ref_curves, dedup):
+@pytest.mark.parametrize("dedup,compact", [(True, True), (False, True), (False, False)])
+def test_synthetic_book_matches_c_oracle(ref_curves, dedup, compact):
     """3000 trades of the BASELINE config-2/3 book (homogeneous tiles: exercises the shared-row path of the
     tiled units kernel) against the C oracle, per trade and in total."""
     from oracle import c_oracle
@@ -234,7 +234,9 @@ def test_synthetic_book_matches_c_oracle(ref_curves, dedup):
                                           trades, dense=False)
     ctx = _native.Context(0)
     ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
-    pv, dl, gm, agg = _run_flat(ctx, flatten_book(book, dedup=dedup))
+    flat = flatten_book(book, dedup=dedup, compact=compact)
+    assert flat.tile_plan is not None and (int(flat.tile_plan.tile_mask.min()) != 0xFFFFFFFF) == compact
+    pv, dl, gm, agg = _run_flat(ctx, flat)
     N = book.notional
     assert np.max(np.abs(pv - pv_c) / np.maximum(np.abs(pv_c), N)) < TOL
     assert np.max(np.abs(dl - dl_c) / np.maximum(np.abs(dl_c), (N * 1e-4)[:, None])) < TOL
@@ -242,6 +244,23 @@ def test_synthetic_book_matches_c_oracle(ref_curves, dedup):
     tot = np.concatenate([[pv_c.sum()], dl_c.sum(0), gm_c.sum(0).reshape(-1)])
     scale = np.concatenate([[np.abs(pv_c).sum()], np.abs(dl_c).sum(0), np.abs(gm_c).sum(0).reshape(-1)]) + 1e-300
     assert np.max(np.abs(agg - tot) / scale) < 1e-11
+    ctx.close()
+
+
+def test_tile_mask_too_small_is_rejected(ref_curves):
+    """A tile plan whose active-pillar masks miss part of the tables' support must fail loudly, not drop Greeks."""
+    from adrates_b200.error import LibError
+    from adrates_b200.synthetic import make_book, flatten_book
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    flat = flatten_book(make_book(curve, 200, seed=5, max_offset_bd=6), dedup=False)
+    # drop the highest active pillar of the first tile (it stays in the smallest size class: tiles remain ordered)
+    m0 = int(flat.tile_plan.tile_mask[0])
+    flat.tile_plan.tile_mask[0] = np.uint32(m0 & ~(1 << (m0.bit_length() - 1)))
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    with pytest.raises(LibError, match="active-pillar masks"):
+        _run_flat(ctx, flat)
     ctx.close()
 
 

@@ -7,7 +7,7 @@ from oracle import cavour_oracle as orc
 from adrates_b200.curves import OISCurve
 from adrates_b200.global_types import InterpTypes
 from adrates_b200.synthetic import make_book, flatten_book
-from adrates_b200.tiles import plan_tiles, packed_index, TM, NPACK
+from adrates_b200.tiles import plan_tiles, packed_index, node_support_masks, TM, NPACK
 from tests.flat_eval import eval_flat
 from tests.util_trades import make_calibration_swaps
 
@@ -38,8 +38,11 @@ def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
     flat = flatten_book(book, dedup=dedup)
     plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
     d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
-    tp = plan_tiles(flat, len(d))
-    assert len(tp.leftover_units) == 0
+    support = node_support_masks(plan["swap"], plan["prev"], plan["acc"])
+    for i in range(len(d)):      # the structural masks are exactly the non-zero pattern of the Jacobian rows
+        assert [int(support[i]) >> r & 1 for r in range(32)] == [int(x != 0.0) for x in np.pad(J[i], (0, 32 - J.shape[1]))]
+    tp = plan_tiles(flat, len(d), support=support)
+    assert len(tp.leftover_units) == 0 and tp.tile_mask.shape == (tp.n_tiles,)
     covered = np.sort(tp.tile_units[tp.tile_units >= 0])
     assert np.array_equal(covered, np.arange(flat.n_units))
     T = sym_tables(d, J, C, tp.pairs.reshape(-1, 2))
@@ -63,6 +66,10 @@ def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
             A[s] = table[coef, np.arange(kc)]
             u_pv[u] = (flat.amt[i0:i0 + P] * np.exp(w[i0:i0 + P, 0] * L[nd[i0:i0 + P, 0]] + w[i0:i0 + P, 1] * L[nd[i0:i0 + P, 1]])).sum()
         Cm = A @ T[rows]
+        # column compaction: everything outside the tile's active pillars is structurally zero
+        act = np.array([(int(tp.tile_mask[t]) >> r) & 1 for r in range(32)], dtype=bool)
+        dead = np.array([not (act[j] and act[k]) for j in range(32) for k in range(j + 1)] + list(~act))
+        assert not np.any(T[rows][:, :NPACK + 32][:, dead])
         for s, u in enumerate(units):
             if u < 0:
                 continue
