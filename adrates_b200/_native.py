@@ -38,7 +38,8 @@ _SIGS = {
     "cav_df_ad": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_portfolio_upload": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P,
                                        C.c_int64, _P, _P, _P, _P]),
-    "cav_portfolio_set_tiles": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, _P, _P]),
+    "cav_portfolio_set_tiles": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int, _P, _P,
+                                          _P]),
     "cav_portfolio_value": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "cav_portfolio_value_host": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "cav_portfolio_delta_gemm": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
@@ -183,9 +184,12 @@ class Context:
         mask = None if getattr(tp, "tile_mask", None) is None else np.ascontiguousarray(tp.tile_mask, dtype=np.uint32)
         arrs = [i32(tp.tile_units), i32(tp.tile_kstart), i32(tp.tile_kcount), i32(tp.k_row), i32(tp.k_pos),
                 i32(tp.k_coef), i32(tp.pairs)]
+        opt = lambda name: None if getattr(tp, name, None) is None else i32(getattr(tp, name))  # noqa: E731
+        pos2, coef2, perm = opt("k_pos2"), opt("k_coef2"), opt("perm")
         self._ck(self._dll.cav_portfolio_set_tiles(self._h, tp.n_tiles, tp.tile_size, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
                                                    arrs[3].shape[0], _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]),
-                                                   arrs[6].shape[0] // 2, _ptr(arrs[6]), _ptr(mask)))
+                                                   _ptr(pos2), _ptr(coef2), arrs[6].shape[0] // 2, _ptr(arrs[6]),
+                                                   _ptr(mask), _ptr(perm)))
 
     def portfolio_value(self, mask: int, pv_dev=None, delta_dev=None, gamma_dev=None, agg_dev=None):
         self._ck(self._dll.cav_portfolio_value(self._h, mask, _ptr(pv_dev), _ptr(delta_dev), _ptr(gamma_dev),

@@ -11,11 +11,11 @@
 #include <algorithm>
 
 #define CAV_N_CLASSES 6
-// size class of a tile from its active-pillar mask: compact columns = na(na+3)/2, NI = ceil(columns / 32)
+// size class of a tile from its active-pillar mask: compact columns = na(na+3)/2, 8 per n-tile, 8 warps
 static int cav_tile_class(unsigned mask) {
     const int na = __builtin_popcount(mask);
-    const int ni = (na * (na + 3) / 2 + 31) / 32;
-    return ni <= 2 ? 0 : ni <= 4 ? 1 : ni <= 6 ? 2 : ni <= 8 ? 3 : ni <= 12 ? 4 : 5;
+    const int nnt = (na * (na + 3) / 2 + 7) / 8;          // n-tiles of 8 compact columns
+    return nnt <= 8 ? 0 : nnt <= 16 ? 1 : nnt <= 24 ? 2 : nnt <= 32 ? 3 : nnt <= 48 ? 4 : 5;
 }
 
 struct CapTable {
@@ -73,7 +73,9 @@ struct cav_ctx {
     int class_begin[CAV_N_CLASSES + 1] = {0};   // tiles are ordered by size class (compact columns / 32)
     unsigned *tile_mask = nullptr, *row_masks = nullptr;
     int* check_flag = nullptr;
-    int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *k_pack = nullptr, *pairs = nullptr;
+    int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *pairs = nullptr;
+    int2* k_pack = nullptr;
+    PillarPerm pp;
     double* Tsym = nullptr;
     bool tiles_valid = false, tsym_valid = false;
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
@@ -182,15 +184,16 @@ void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma) {
     ctx->launches++;
 }
 
-// Size classes of the tiled units kernel: NI = compact columns / 32 (accumulators per lane and unit), U = units per
-// pass, MINB = CTAs per SM the register allocation is bounded for.
-#define SIMT_CLASSES(X) X(2, 4, 6) X(4, 4, 5) X(6, 4, 4) X(8, 4, 4) X(12, 2, 4) X(18, 2, 3)
+// Size classes of the tiled units kernel: NT = n-tiles (8 compact columns) per warp, MINB = CTAs per SM the register
+// allocation is bounded for.  A class holds tiles with at most 64 NT compact columns.
+#define MMA_CLASSES(X) X(1, 4) X(2, 4) X(3, 3) X(4, 3) X(6, 2) X(9, 2)
 
-template <int NI, int U, int MINB>
-int simt_ctas_per_sm() {
+template <int NT, int MINB>
+int mma_ctas_per_sm() {
     static int n = [] {
         int v = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_units_simt<NI, U, MINB>, 128, 0) != cudaSuccess || v < 1) v = 1;
+        cudaFuncSetAttribute(k_units_mma<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaSmem<NT>::BYTES);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_units_mma<NT, MINB>, 256, MmaSmem<NT>::BYTES) != cudaSuccess || v < 1) v = 1;
         return v;
     }();
     return n;
@@ -198,26 +201,27 @@ int simt_ctas_per_sm() {
 
 int simt_max_grid(const cav_ctx* ctx) {
     int m = 1;
-#define X(NI, U, MINB) m = std::max(m, simt_ctas_per_sm<NI, U, MINB>());
-    SIMT_CLASSES(X)
+#define X(NT, MINB) m = std::max(m, mma_ctas_per_sm<NT, MINB>());
+    MMA_CLASSES(X)
 #undef X
     return m * ctx->sm_count;
 }
 
-template <int NI, int U, int MINB>
-void launch_simt(cav_ctx* ctx, const SimtArgs& ga, int t0, int t1) {
+template <int NT, int MINB>
+void launch_mma(cav_ctx* ctx, const SimtArgs& ga, int t0, int t1) {
     if (t1 <= t0) return;
-    const int cap = simt_ctas_per_sm<NI, U, MINB>() * ctx->sm_count;
-    const int want = (t1 - t0 + 3) / 4;
-    k_units_simt<NI, U, MINB><<<want < cap ? want : cap, 128, 0, ctx->stream>>>(ga, t0, t1);
+    const int cap = mma_ctas_per_sm<NT, MINB>() * ctx->sm_count;
+    const int want = t1 - t0;
+    k_units_mma<NT, MINB><<<want < cap ? want : cap, 256, MmaSmem<NT>::BYTES, ctx->stream>>>(
+        ga, t0, t1, 3 * ctx->G + ctx->n_pair_rows);
     ctx->launches++;
 }
 
 void launch_simt_classes(cav_ctx* ctx, const SimtArgs& ga) {
     const int* cb = ctx->class_begin;
     int c = 0;
-#define X(NI, U, MINB) launch_simt<NI, U, MINB>(ctx, ga, cb[c], cb[c + 1]); ++c;
-    SIMT_CLASSES(X)
+#define X(NT, MINB) launch_mma<NT, MINB>(ctx, ga, cb[c], cb[c + 1]); ++c;
+    MMA_CLASSES(X)
 #undef X
 }
 
@@ -568,16 +572,27 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
 
 int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int32_t* tile_units, const int32_t* tile_kstart,
                             const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
-                            const int32_t* k_coef, int n_pair_rows, const int32_t* pairs, const uint32_t* tile_mask) {
+                            const int32_t* k_coef, const int32_t* k_pos2, const int32_t* k_coef2, int n_pair_rows,
+                            const int32_t* pairs, const uint32_t* tile_mask, const int32_t* pillar_perm) {
     if (!ctx) return CAV_E_INVALID;
     if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_set_tiles: upload the portfolio first");
     if (ctx->n_pairs != 2) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: single-DF terms (n_pairs == 2) only");
-    if (tile_size != GT_TM) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: tile_size must be 4");
+    if (tile_size != GT_TM) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: tile_size must be 16");
     if (n_tiles < 0 || n_krows < 0 || n_pair_rows < 0 || (n_tiles && (!tile_units || !tile_kstart || !tile_kcount)) ||
-        (n_krows && (!k_row || !k_pos || !k_coef)) || (n_pair_rows && !pairs))
+        (n_krows && (!k_row || !k_pos || !k_coef)) || (n_pair_rows && !pairs) || ((k_pos2 == nullptr) != (k_coef2 == nullptr)))
         return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: null pointer or negative size");
     const int n_rows = 3 * ctx->G + n_pair_rows;
-    if (n_rows >= (1 << 20)) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 2^20 table rows");
+    PillarPerm pp;
+    {
+        unsigned seen = 0u;
+        for (int q = 0; q < 32; ++q) {
+            const int r = pillar_perm ? pillar_perm[q] : q;
+            if (r < 0 || r > 31 || ((seen >> r) & 1u)) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: pillar_perm is not a permutation of 0..31");
+            seen |= 1u << r;
+            pp.perm[q] = (unsigned char)r;
+            pp.pos_of[r] = (unsigned char)q;
+        }
+    }
     int64_t covered = 0;
     for (int64_t i = 0; i < (int64_t)n_tiles * tile_size; ++i) {
         if (tile_units[i] < -1 || tile_units[i] >= ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: unit id out of range");
@@ -608,27 +623,36 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
         }
         npos[t] = (int)(len < 0 ? 0 : len);
         if (npos[t] > 255) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 255 terms per unit");
-        // K rows ordered by position and every position present (the kernel loads term scalars as it meets them)
+        // K rows ordered by position; a second contribution lives in the same chunk of 32 positions
         if (t == 0 || tile_kstart[t] != tile_kstart[t - 1] || tile_kcount[t] != tile_kcount[t - 1] || npos[t] != npos[t - 1]) {
-            int prev = -1;
+            int prev = 0, in_chunk = 0;
             for (int k = 0; k < tile_kcount[t]; ++k) {
                 const int p = k_pos[tile_kstart[t] + k];
-                if (p < prev || p > prev + 1 || p >= npos[t])
-                    return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows must be ordered by position and cover every position");
+                if (p < prev || p >= npos[t])
+                    return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows not ordered by position or position out of range");
+                in_chunk = (p >> 5) == (prev >> 5) ? in_chunk + 1 : 1;
+                if (in_chunk > GM_KC)
+                    return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 160 K rows in a chunk of 32 term positions");
                 prev = p;
+                if (k_pos2 && k_coef2[tile_kstart[t] + k] >= 0) {
+                    const int p2 = k_pos2[tile_kstart[t] + k];
+                    if (p2 < 0 || p2 >= npos[t] || (p2 >> 5) != (p >> 5))
+                        return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: second contribution outside the row's 32-position chunk");
+                }
             }
-            if (prev != npos[t] - 1) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows do not cover every term position");
         }
         const int cls = cav_tile_class(masks[t]);
         if (cls < cls_prev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: tiles must be ordered by size class");
         for (int c = cls_prev + 1; c <= cls; ++c) class_begin[c] = t;
         cls_prev = cls;
     }
-    std::vector<int> pack((size_t)n_krows);
+    std::vector<int2> pack((size_t)n_krows);
     for (int64_t k = 0; k < n_krows; ++k) {
-        if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_pos[k] > 255 || k_coef[k] < 0 || k_coef[k] > 5)
+        if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_pos[k] > 255 || k_coef[k] < 0 || k_coef[k] > 5 ||
+            (k_coef2 && k_coef2[k] > 5))
             return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: bad K row");
-        pack[k] = k_row[k] | (k_pos[k] << 20) | (k_coef[k] << 28);
+        const bool two = k_coef2 && k_coef2[k] >= 0;
+        pack[k] = make_int2(k_row[k], k_pos[k] | (k_coef[k] << 8) | ((two ? k_pos2[k] : 0) << 16) | ((two ? k_coef2[k] : 7) << 24));
     }
     for (int i = 0; i < 2 * n_pair_rows; ++i)
         if (pairs[i] < 0 || pairs[i] >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: pair node out of range");
@@ -641,6 +665,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     CK(upload(ctx, &ctx->tile_mask, masks.data(), (size_t)n_tiles));
     CK(cudaStreamSynchronize(ctx->stream));
     std::memcpy(ctx->class_begin, class_begin, sizeof(class_begin));
+    ctx->pp = pp;
     ctx->n_tiles = n_tiles; ctx->n_krows = n_krows; ctx->n_pair_rows = n_pair_rows;
     ctx->tiles_valid = true; ctx->tsym_valid = false;
     return CAV_OK;
@@ -664,9 +689,9 @@ static int ensure_row_tables(cav_ctx* ctx) {
 static int build_sym_tables(cav_ctx* ctx) {
     const size_t rows = (size_t)3 * ctx->G + ctx->n_pair_rows + 1;
     CK(dev_alloc(ctx, &ctx->Tsym, rows * GT_NC));
-    k_sym_tables<<<3 * ctx->G, GT_NC, 0, ctx->stream>>>(ctx->G, ctx->g, ctx->Hf, ctx->Cf, ctx->Tsym);
+    k_sym_tables<<<3 * ctx->G, GT_NC, 0, ctx->stream>>>(ctx->G, ctx->g, ctx->Hf, ctx->Cf, ctx->Tsym, ctx->pp);
     k_pair_tables<<<ctx->n_pair_rows + 1, GT_NC, 0, ctx->stream>>>(ctx->n_pair_rows, ctx->pairs, ctx->g,
-                                                                    ctx->Tsym + (size_t)3 * ctx->G * GT_NC);
+                                                                    ctx->Tsym + (size_t)3 * ctx->G * GT_NC, ctx->pp);
     // the tiles' active-pillar masks must cover the support of every table row they use (a wrong mask would
     // silently drop Greeks): checked on the device whenever the tables are rebuilt
     CK(dev_alloc(ctx, &ctx->row_masks, rows));
@@ -709,10 +734,10 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (use_gemm && !ctx->tsym_valid) { int rc = build_sym_tables(ctx); if (rc) return rc; }
     int64_t rows = 0;
     int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
-    if (use_gemm) rows = (int64_t)simt_max_grid(ctx) * 4;          // packed partial rows, one per persistent warp
+    if (use_gemm) rows = (int64_t)simt_max_grid(ctx);              // one partial row per persistent CTA
     if (need_agg) {
-        CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * (use_gemm ? GT_NC : CAV_NOUT)));
-        if (use_gemm) CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * rows * GT_NC, ctx->stream));
+        CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
+        if (use_gemm) CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * rows * CAV_NOUT, ctx->stream));
     }
     UnitsArgs a;
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
@@ -737,7 +762,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (use_gemm) {
         SimtArgs ga;
         ga.tile_units = ctx->tile_units; ga.tile_kstart = ctx->tile_kstart; ga.tile_kcount = ctx->tile_kcount;
-        ga.tile_npos = ctx->tile_npos; ga.tile_mask = ctx->tile_mask; ga.k_pack = ctx->k_pack; ga.T = ctx->Tsym;
+        ga.tile_npos = ctx->tile_npos; ga.tile_mask = ctx->tile_mask; ga.k_pack = ctx->k_pack; ga.T = ctx->Tsym; ga.pp = ctx->pp;
         ga.unit_offsets = a.unit_offsets; ga.amt = a.amt; ga.weight = a.weight; ga.node = a.node; ga.L = a.L;
         ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
         ga.out_gamma = a.out_gamma; ga.partials = a.partials;
@@ -771,8 +796,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[2], ctx->stream));
     if (need_agg) {
         double* dst = agg_dev ? agg_dev : ctx->agg;
-        if (use_gemm) k_reduce_packed<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
-        else k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
+        k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
         ctx->launches++;
         CK(cudaGetLastError());
         if (ctx->profile) { CK(cudaEventRecord(ctx->evk[3], ctx->stream)); ctx->evk_n = 4; }

@@ -248,34 +248,37 @@ k_units(UnitsArgs A)
 }
 
 // ------------------------------------------------------------------------------------------
-// Tiled units kernel (k_units_simt).  For units that bracket the same node pairs term by term,
+// Tiled units kernel (k_units_mma).  For units that bracket the same node pairs term by term,
 //   [gamma (528 packed lower-triangle entries) | delta (32)] [units x 560] = A[units x K] . B[K x 560]
 // where the K rows of B come from per-curve symmetric tables (built by k_sym_tables / k_pair_tables)
 //   H_n = hess(ln d_n)|g_n,  C_n = (H_n + g_n g_n^T)|g_n,  G_nn = g_n g_n^T|0,  G_ab = (g_a g_b^T + g_b g_a^T)|0
 // and only the coefficients A (p, p w0, p w1, p w0^2, p w1^2, p w0 w1) depend on the unit
-// (adrates_b200/tiles.py).  A tile is 4 units with the same K rows; one warp owns a tile end to end (no CTA
-// barriers: phases of different warps overlap freely and the SM hides latency with warps, not with a
-// hand-built pipeline).
+// (adrates_b200/tiles.py).  One CTA = one tile of 16 units, FP64 DMMA (mma.sync.m8n8k4): per chunk of 32 term
+// positions the CTA evaluates p = amt*DF once per term, builds A in shared memory, then runs the K loop with
+// B fragments read straight from the L2-resident tables (each table row is read once per tile, not once per
+// unit); the epilogue stages 8 units at a time in shared memory and writes full symmetric 32x32 rows with
+// 32-byte stores.
 //
-// Column compaction: a tile's Greeks are non-zero only on its active pillars (tile_mask, na bits).  The
-// warp works on the na(na+1)/2 packed gamma columns of the active pillars plus their na delta columns instead
-// of all 528 + 32; lane l owns compact columns l, l+32, ... (NI of them, template parameter = size class of
-// the tile), each mapped to a table column cn[i].  Per K row: NI table loads and U*NI DFMAs, with the row's
-// coefficient of each unit broadcast by one shuffle from the lane that holds the term.
-// The epilogue scatters the compact accumulators back into full symmetric 32x32 rows (zeros elsewhere)
-// through a per-warp staging row and writes them with 32-byte stores.
+// Column compaction: a tile's Greeks are non-zero only on its active pillars (tile_mask, na bits).  The GEMM
+// runs over the na(na+1)/2 packed gamma columns of the active pillars plus their na delta columns instead of
+// all 528 + 32: compact column c reads table column sCol[c]; n-tiles of 8 compact columns are dealt round-robin
+// to the 8 warps.  The kernel is instantiated per size class NT = n-tiles per warp (accumulator registers and
+// the staging rows scale with NT, so small classes run three or four CTAs per SM and their phases overlap).
+// Pillars are permuted (PillarPerm, chosen by the planner) so that the active sets are mostly prefixes and the
+// compact columns mostly contiguous in the tables.
 // ------------------------------------------------------------------------------------------
 #define GT_NC 576          // table row length: 528 packed gamma entries + 32 delta columns + 16 zeros
 #define GT_NPACK 528
-#define GT_TM 4            // units per tile
-#define GT_PV_COL (GT_NPACK + CAV_RW + 1)   // column of the packed partial rows that carries the PV total
+#define GT_TM 16           // units per tile
 
 __device__ __forceinline__ int gt_packed(int j, int k) { return j >= k ? j * (j + 1) / 2 + k : k * (k + 1) / 2 + j; }
 
 // rows 0..G-1: H_n | g_n ; G..2G-1: C_n | g_n ; 2G..3G-1: g_n g_n^T | 0   (one CTA per row)
+struct PillarPerm { unsigned char perm[32]; unsigned char pos_of[32]; };   // position -> pillar, pillar -> position
+
 __global__ void __launch_bounds__(GT_NC)
 k_sym_tables(int G, const double* __restrict__ g, const double* __restrict__ Hf, const double* __restrict__ Cf,
-             double* T)
+             double* T, PillarPerm pp)
 {
     const int row = blockIdx.x, e = threadIdx.x;
     const int type = row / G, n = row % G;
@@ -284,19 +287,20 @@ k_sym_tables(int G, const double* __restrict__ g, const double* __restrict__ Hf,
         int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
         while (j * (j + 1) / 2 > e) --j;
         while ((j + 1) * (j + 2) / 2 <= e) ++j;
-        const int k = e - j * (j + 1) / 2;
+        const int k = pp.perm[e - j * (j + 1) / 2];
+        j = pp.perm[j];
         if (type == 0) v = Hf[(size_t)n * CAV_RR + j * CAV_RW + k];
         else if (type == 1) v = Cf[(size_t)n * CAV_RR + j * CAV_RW + k];
         else v = g[n * CAV_RW + j] * g[n * CAV_RW + k];
     } else if (e < GT_NPACK + CAV_RW) {
-        if (type < 2) v = g[n * CAV_RW + (e - GT_NPACK)];
+        if (type < 2) v = g[n * CAV_RW + pp.perm[e - GT_NPACK]];
     }
     T[(size_t)row * GT_NC + e] = v;
 }
 
 // rows 3G + i: g_a g_b^T + g_b g_a^T | 0 for the node pairs the portfolio brackets; last row = zeros
 __global__ void __launch_bounds__(GT_NC)
-k_pair_tables(int n_pairs, const int* __restrict__ pairs, const double* __restrict__ g, double* Trows)
+k_pair_tables(int n_pairs, const int* __restrict__ pairs, const double* __restrict__ g, double* Trows, PillarPerm pp)
 {
     const int i = blockIdx.x, e = threadIdx.x;
     double v = 0.0;
@@ -304,7 +308,8 @@ k_pair_tables(int n_pairs, const int* __restrict__ pairs, const double* __restri
         int j = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
         while (j * (j + 1) / 2 > e) --j;
         while ((j + 1) * (j + 2) / 2 <= e) ++j;
-        const int k = e - j * (j + 1) / 2;
+        const int k = pp.perm[e - j * (j + 1) / 2];
+        j = pp.perm[j];
         const int a = pairs[2 * i], b = pairs[2 * i + 1];
         v = g[a * CAV_RW + j] * g[b * CAV_RW + k] + g[b * CAV_RW + j] * g[a * CAV_RW + k];
     }
@@ -336,7 +341,7 @@ k_row_masks(const double* __restrict__ T, unsigned* masks)
 
 // every K row of every tile must live on the tile's active pillars; *flag != 0 otherwise
 __global__ void k_check_tile_masks(int n_tiles, const int* __restrict__ tile_kstart, const int* __restrict__ tile_kcount,
-                                   const unsigned* __restrict__ tile_mask, const int* __restrict__ k_pack,
+                                   const unsigned* __restrict__ tile_mask, const int2* __restrict__ k_pack,
                                    const unsigned* __restrict__ row_masks, int* flag)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -344,7 +349,7 @@ __global__ void k_check_tile_masks(int n_tiles, const int* __restrict__ tile_kst
     if (t > 0 && tile_kstart[t] == tile_kstart[t - 1] && tile_mask[t] == tile_mask[t - 1]) return;   // same group
     const unsigned allowed = tile_mask[t];
     unsigned bad = 0u;
-    for (int k = 0; k < tile_kcount[t]; ++k) bad |= row_masks[k_pack[tile_kstart[t] + k] & 0xFFFFF] & ~allowed;
+    for (int k = 0; k < tile_kcount[t]; ++k) bad |= row_masks[k_pack[tile_kstart[t] + k].x] & ~allowed;
     if (bad) atomicExch(flag, 1);
 }
 
@@ -354,7 +359,8 @@ struct SimtArgs {
     const int* tile_kcount;
     const int* tile_npos;
     const unsigned* tile_mask; // [n_tiles] active par-rate pillars of the tile
-    const int* k_pack;         // per K row: table row (20 bits) | term position << 20 (8 bits) | coefficient kind << 28
+    const int2* k_pack;        // per K row: x = table row; y = pos | kind << 8 | pos2 << 16 | kind2 << 24 (kind2 = 7: none)
+    PillarPerm pp;             // the packed tables (and the tile masks) are in permuted pillar order
     const double* T;           // symmetric tables [rows][GT_NC]
     const int64_t* unit_offsets;
     const double* amt;
@@ -366,208 +372,231 @@ struct SimtArgs {
     double* out_pv;
     double* out_delta;
     double* out_gamma;
-    double* partials;          // [warps of the largest grid][GT_NC] packed totals per persistent warp, or null
+    double* partials;          // [CTAs of the largest grid][1057] totals per persistent CTA, or null
 };
 
-// per-warp shared memory (doubles): stage[32 NI + 8] | 1056 x u16 epilogue indices | 32 x int pillars |
-// term scalars p, w0, w1 [U][32] | unit PVs [U]
-template <int NI, int U>
-struct SimtSmem {
-    static constexpr int STAGE = 32 * NI + 8;
-    static constexpr int ZSLOT = 32 * NI;          // staging slot that is always zero
-    static constexpr int IDX = STAGE;               // u16 [1056]
-    static constexpr int PIL = IDX + 264;           // int [32]
-    static constexpr int TERM = PIL + 16;           // double [3][U][32]
-    static constexpr int PV = TERM + 3 * U * 32;    // double [U]
-    static constexpr int TOTAL = PV + ((U + 7) & ~7);
+#define GM_PC 32                 // term positions per chunk
+#define GM_KC 160                // K rows per chunk (at most 5 per position)
+#define GM_LDA 164               // row stride of the coefficient tile
+
+template <int NT>
+struct MmaSmem {                 // shared-memory layout (doubles first, then 8-byte and 4-byte integers)
+    static constexpr int NCS = 64 * NT;             // compact columns the class can hold
+    static constexpr int LDS_ = NCS + 8;            // staging row stride; slot NCS is always zero
+    static constexpr int A = 0;                     // [16][GM_LDA]
+    static constexpr int TP = A + GT_TM * GM_LDA;   // [16][32] p, then w0, w1
+    static constexpr int STAGE = TP + 3 * GT_TM * GM_PC;   // [8][LDS_]
+    static constexpr int PV = STAGE + 8 * LDS_;     // [16]
+    static constexpr int W = PV + GT_TM;            // [16]
+    static constexpr int TOT = W + GT_TM;           // [1058]
+    static constexpr int OFF = TOT + 1058;          // int64 [16]
+    static constexpr int OUT = OFF + GT_TM;         // int64 [16]
+    static constexpr int INTS = OUT + GT_TM;        // int: row[GM_KC] desc[GM_KC] col[NCS] pil[32] unit[16]
+    static constexpr size_t BYTES = (size_t)INTS * 8 + (size_t)(2 * GM_KC + NCS + 32 + GT_TM) * 4;
 };
 
-template <int NI, int U, int MINB>
-__global__ void __launch_bounds__(128, MINB)
-k_units_simt(SimtArgs a, int tile_begin, int tile_end)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
 {
-    using SM = SimtSmem<NI, U>;
-    __shared__ double smem[4 * SM::TOTAL];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double* stage = smem + wib * SM::TOTAL;
-    unsigned short* sidx = reinterpret_cast<unsigned short*>(stage + SM::IDX);   // [1024] gamma entry -> stage slot, [32] delta
-    int* sPil = reinterpret_cast<int*>(stage + SM::PIL);                         // [32] active pillars, ascending
-    double* sP = stage + SM::TERM;                 // [U][32] p = amt * DF of the current 32 term positions
-    double* sW0 = sP + U * 32;
-    double* sW1 = sW0 + U * 32;
-    double* sPv = stage + SM::PV;
-    const int gw = blockIdx.x * 4 + wib, nw = gridDim.x * 4;
-    double* my_part = a.partials ? a.partials + (size_t)gw * GT_NC : nullptr;
-    unsigned cur_mask = 0u;
-    bool have_mask = false;
-    int cn[NI];
-#pragma unroll
-    for (int i = 0; i < NI; ++i) cn[i] = GT_NPACK + CAV_RW;
-    if (lane == 0) stage[SM::ZSLOT] = 0.0;
+    using SM = MmaSmem<NT>;
+    extern __shared__ double smem[];
+    double* sA = smem + SM::A;
+    double* sTp = smem + SM::TP;
+    double* sTw0 = sTp + GT_TM * GM_PC;
+    double* sTw1 = sTw0 + GT_TM * GM_PC;
+    double* sStage = smem + SM::STAGE;
+    double* sPv = smem + SM::PV;
+    double* sW = smem + SM::W;
+    double* sTot = smem + SM::TOT;                 // portfolio partials of this CTA (each entry owned by one thread)
+    int64_t* sOff = reinterpret_cast<int64_t*>(smem + SM::OFF);
+    int64_t* sOut = reinterpret_cast<int64_t*>(smem + SM::OUT);
+    int* sRow = reinterpret_cast<int*>(smem + SM::INTS);
+    int* sDesc = sRow + GM_KC;
+    int* sCol = sDesc + GM_KC;
+    int* sPil = sCol + SM::NCS;
+    int* sUnit = sPil + 32;
 
-    for (int tile = tile_begin + gw; tile < tile_end; tile += nw) {
+    const int tid = threadIdx.x, lane = tid & 31, ng = tid >> 5;
+    const int ar = lane >> 2, ac = lane & 3;
+    const int oj = tid >> 3, ok4 = (tid & 7) * 4;        // epilogue: this thread owns gamma entries (oj, ok4..ok4+3)
+    if (tid < 8) sStage[tid * SM::LDS_ + SM::NCS] = 0.0;
+    double* my_tg = sTot + 33 + oj * CAV_RW + ok4;
+    my_tg[0] = my_tg[1] = my_tg[2] = my_tg[3] = 0.0;
+    if (tid <= CAV_RW) sTot[tid] = 0.0;
+
+    for (int tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
         const int K = a.tile_kcount[tile], ks = a.tile_kstart[tile], P = a.tile_npos[tile];
         const unsigned mask = a.tile_mask[tile];
-        if (!have_mask || mask != cur_mask) {
-            // column map of this lane and the epilogue index table of this warp
-            const int na = __popc(mask), nc = na * (na + 1) / 2, ncols = nc + na;
-            __syncwarp();
-            if ((mask >> lane) & 1u) sPil[__popc(mask & ((1u << lane) - 1u))] = lane;
-            __syncwarp();
+        const int na = __popc(mask), nc = na * (na + 1) / 2, ncols = nc + na, nnt = (ncols + 7) >> 3;
+        const int ntw = nnt > ng ? (nnt - ng + 7) >> 3 : 0;              // n-tiles of this warp: ng, ng+8, ...
+        __syncthreads();                                  // previous tile is done with shared memory
+        if (tid < GT_TM) {
+            const int uid = a.tile_units[tile * GT_TM + tid];
+            sUnit[tid] = uid;
+            sOff[tid] = uid >= 0 ? a.unit_offsets[uid] : 0;
+            sOut[tid] = uid >= 0 ? (a.out_index ? a.out_index[uid] : uid) : 0;
+            sW[tid] = (uid >= 0 && a.unit_weight) ? a.unit_weight[uid] : 1.0;
+            sPv[tid] = 0.0;
+        }
+        if (tid >= 32 && tid < 64 && ((mask >> (tid - 32)) & 1u)) sPil[__popc(mask & ((1u << (tid - 32)) - 1u))] = tid - 32;
+        __syncthreads();
+        for (int cc = tid; cc < nnt * 8; cc += 256) {
+            int col = GT_NPACK + CAV_RW;                 // a zero column of the tables
+            if (cc < nc) {
+                int j = (int)((sqrtf(8.0f * cc + 1.0f) - 1.0f) * 0.5f);
+                while (j * (j + 1) / 2 > cc) --j;
+                while ((j + 1) * (j + 2) / 2 <= cc) ++j;
+                const int pj = sPil[j], pk2 = sPil[cc - j * (j + 1) / 2];
+                col = pj * (pj + 1) / 2 + pk2;
+            } else if (cc < ncols) col = GT_NPACK + sPil[cc - nc];
+            sCol[cc] = col;
+        }
+        __syncthreads();
+        int cn[NT];
+        double c[2][NT][2];
 #pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const int cc = lane + 32 * i;
-                int col = GT_NPACK + CAV_RW;                 // a zero column of the tables
-                if (cc < nc) {
-                    int j = (int)((sqrtf(8.0f * cc + 1.0f) - 1.0f) * 0.5f);
-                    while (j * (j + 1) / 2 > cc) --j;
-                    while ((j + 1) * (j + 2) / 2 <= cc) ++j;
-                    const int pj = sPil[j], pk2 = sPil[cc - j * (j + 1) / 2];
-                    col = pj * (pj + 1) / 2 + pk2;
-                } else if (cc < ncols) col = GT_NPACK + sPil[cc - nc];
-                cn[i] = col;
-            }
-            const int ik = ((mask >> lane) & 1u) ? __popc(mask & ((1u << lane) - 1u)) : -1;
-            for (int j = 0; j < CAV_RW; ++j) {
-                const int ij = ((mask >> j) & 1u) ? __popc(mask & ((1u << j) - 1u)) : -1;
-                sidx[j * CAV_RW + lane] = (unsigned short)((ij < 0 || ik < 0) ? SM::ZSLOT
-                                                           : (ij >= ik ? ij * (ij + 1) / 2 + ik : ik * (ik + 1) / 2 + ij));
-            }
-            sidx[CAV_RR + lane] = (unsigned short)(ik < 0 ? SM::ZSLOT : nc + ik);
-            cur_mask = mask;
-            have_mask = true;
-            __syncwarp();
+        for (int n = 0; n < NT; ++n) {
+            cn[n] = (n < ntw) ? sCol[(ng + 8 * n) * 8 + ar] : (GT_NPACK + CAV_RW);
+            c[0][n][0] = c[0][n][1] = c[1][n][0] = c[1][n][1] = 0.0;
         }
 
-#pragma unroll 1
-        for (int h = 0; h < GT_TM; h += U) {
-            const int* units = a.tile_units + tile * GT_TM + h;
-            double acc[U][NI];
-#pragma unroll
-            for (int u = 0; u < U; ++u)
-#pragma unroll
-                for (int i = 0; i < NI; ++i) acc[u][i] = 0.0;
-            if (lane < U) sPv[lane] = 0.0;
-            // K rows come in windows of 32 (lane = row of the window); term scalars in chunks of 32 positions
-            // (lane = position, kept in shared memory).  Rows are ordered by position, so the rows of a chunk
-            // are a prefix of what is left of the window.  Per (window, chunk) segment every lane first forms
-            // the coefficients of its own row for the U units; the row loop then only broadcasts them.
-            int r0 = 0, start = 0;
-            int mypack = (lane < K) ? __ldg(a.k_pack + ks + lane) : 0;
-            for (int c0 = 0; c0 < P; c0 += 32) {
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int uid = __ldg(units + u);
-                    double pp = 0.0, x0 = 0.0, x1 = 0.0;
-                    if (uid >= 0 && c0 + lane < P) {
-                        const int64_t i = __ldg(a.unit_offsets + uid) + c0 + lane;
-                        const double2 w = __ldg(reinterpret_cast<const double2*>(a.weight) + i);
-                        const int2 n = __ldg(reinterpret_cast<const int2*>(a.node) + i);
-                        x0 = w.x; x1 = w.y;
-                        pp = __ldg(a.amt + i) * exp(w.x * __ldg(a.L + n.x) + w.y * __ldg(a.L + n.y));
-                    }
-                    sP[u * 32 + lane] = pp; sW0[u * 32 + lane] = x0; sW1[u * 32 + lane] = x1;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) pp += __shfl_xor_sync(0xffffffffu, pp, o);
-                    if (lane == 0) sPv[u] += pp;
+        int kdone = 0;                                   // K rows are ordered by (first) position
+        for (int p0 = 0; p0 < P; p0 += GM_PC) {
+            __syncthreads();                             // previous chunk consumed
+            // (1) term scalars of this chunk: p = amt * DF, w0, w1 for 16 units x 32 positions
+            for (int idx = tid; idx < GT_TM * GM_PC; idx += 256) {
+                const int u = idx >> 5, j = idx & 31;
+                double p = 0.0, w0 = 0.0, w1 = 0.0;
+                if (p0 + j < P && sUnit[u] >= 0) {
+                    const int64_t i = sOff[u] + p0 + j;
+                    const double2 w = __ldg(reinterpret_cast<const double2*>(a.weight) + i);
+                    const int2 n = __ldg(reinterpret_cast<const int2*>(a.node) + i);
+                    w0 = w.x; w1 = w.y;
+                    p = __ldg(a.amt + i) * exp(w.x * __ldg(a.L + n.x) + w.y * __ldg(a.L + n.y));
                 }
-                __syncwarp();
-                for (;;) {
-                    const int wn = (K - r0) < 32 ? (K - r0) : 32;
-                    const int pos = (mypack >> 20) & 0xFF, cf = (mypack >> 28) & 7;
-                    const bool mine = lane < wn && pos < c0 + 32;
-                    const int n_in = __popc(__ballot_sync(0xffffffffu, mine));
-                    const int mybase = (mypack & 0xFFFFF) * GT_NC;
-                    double cw[U];
+                sTp[idx] = p; sTw0[idx] = w0; sTw1[idx] = w1;
+            }
+            // (2) K rows of this chunk = the prefix of the remaining rows whose position lies in the chunk
+            int2 pk = make_int2(zero_row, 0);
+            bool in = false;
+            if (tid < GM_KC && kdone + tid < K) {
+                pk = __ldg(a.k_pack + ks + kdone + tid);
+                in = (pk.y & 0xFF) < p0 + GM_PC;
+            }
+            const int kc = __syncthreads_count(in);      // also publishes the term scalars
+            const int kc4 = (kc + 3) & ~3;
+            if (tid < kc4) { sRow[tid] = in ? pk.x : zero_row; sDesc[tid] = in ? pk.y : -1; }
+            __syncthreads();
+            // (3) unit PVs (fixed butterfly order) and the coefficient tile A: warp w owns units 2w, 2w+1
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int t = u * 32 + (pos & 31);
-                        const double x0 = sW0[t], x1 = sW1[t];
+            for (int uu = 0; uu < 2; ++uu) {
+                const int u = 2 * ng + uu;
+                double pv = sTp[u * GM_PC + lane];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+                if (lane == 0) sPv[u] += pv;
+                for (int k = lane; k < kc4; k += 32) {
+                    const int d = sDesc[k];
+                    double v = 0.0;
+                    if (d >= 0) {
+                        const int cf = (d >> 8) & 0xF, cf2 = (d >> 24) & 0xF;
+                        const int t = u * GM_PC + (d & 31);
+                        const double x0 = sTw0[t], x1 = sTw1[t];
                         const double f1 = (cf == 1 || cf == 3 || cf == 5) ? x0 : ((cf == 2 || cf == 4) ? x1 : 1.0);
                         const double f2 = cf == 3 ? x0 : ((cf == 4 || cf == 5) ? x1 : 1.0);
-                        cw[u] = mine ? sP[t] * f1 * f2 : 0.0;
+                        v = sTp[t] * f1 * f2;
+                        if (cf2 != 7) {                  // second term feeding the same table row (same chunk)
+                            const int t2 = u * GM_PC + ((d >> 16) & 31);
+                            const double y0 = sTw0[t2], y1 = sTw1[t2];
+                            const double h1 = (cf2 == 1 || cf2 == 3 || cf2 == 5) ? y0 : ((cf2 == 2 || cf2 == 4) ? y1 : 1.0);
+                            const double h2 = cf2 == 3 ? y0 : ((cf2 == 4 || cf2 == 5) ? y1 : 1.0);
+                            v = fma(sTp[t2] * h1, h2, v);
+                        }
                     }
+                    sA[u * GM_LDA + k] = v;
+                }
+            }
+            __syncthreads();
+            // (4) C += A . B on the tensor pipe
+            if (ntw > 0) {
+                const double* A0 = sA + ar * GM_LDA + ac;
+                const double* A1 = A0 + 8 * GM_LDA;
 #pragma unroll 2
-                    for (int rr = start; rr < n_in; ++rr) {
-                        const int base = __shfl_sync(0xffffffffu, mybase, rr);
-                        double b[NI];
+                for (int k = 0; k < kc4; k += 4) {
+                    const double a0 = A0[k], a1 = A1[k];
+                    const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC;
 #pragma unroll
-                        for (int i = 0; i < NI; ++i) b[i] = __ldg(a.T + (base + cn[i]));
-                        double c[U];
-#pragma unroll
-                        for (int u = 0; u < U; ++u) c[u] = __shfl_sync(0xffffffffu, cw[u], rr);
-#pragma unroll
-                        for (int i = 0; i < NI; ++i)
-#pragma unroll
-                            for (int u = 0; u < U; ++u) acc[u][i] = fma(c[u], b[i], acc[u][i]);
+                    for (int n = 0; n < NT; ++n) {
+                        if (n < ntw) {                    // warp-uniform
+                            const double b = __ldg(rowp + cn[n]);
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(b));
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1), "d"(b));
+                        }
                     }
-                    start = n_in;
-                    if (n_in < wn || r0 + wn >= K) break;     // the chunk ends inside this window / no rows left
-                    r0 += 32;
-                    start = 0;
-                    mypack = (r0 + lane < K) ? __ldg(a.k_pack + ks + r0 + lane) : 0;
                 }
             }
-            // ---- epilogue: one unit at a time through the staging row ----
+            kdone += kc;
+        }
+        // ---- epilogue: stage 8 units at a time, scatter to full symmetric rows ----
+        int pk4[4], pd = SM::NCS;
+        {   // real pillar r lives at position pos_of[r] of the permuted order the mask and the tables use
+            const int qj = a.pp.pos_of[oj];
+            const int ij = ((mask >> qj) & 1u) ? __popc(mask & ((1u << qj) - 1u)) : -1;
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int uid = __ldg(units + u);
-                if (uid < 0) continue;               // warp-uniform
-                __syncwarp();
+            for (int q = 0; q < 4; ++q) {
+                const int qk = a.pp.pos_of[ok4 + q];
+                const int ik = ((mask >> qk) & 1u) ? __popc(mask & ((1u << qk) - 1u)) : -1;
+                pk4[q] = (ij < 0 || ik < 0) ? SM::NCS : (ij >= ik ? ij * (ij + 1) / 2 + ik : ik * (ik + 1) / 2 + ij);
+            }
+            if (tid < CAV_RW) {
+                const int qd = a.pp.pos_of[tid];
+                if ((mask >> qd) & 1u) pd = nc + __popc(mask & ((1u << qd) - 1u));
+            }
+        }
 #pragma unroll
-                for (int i = 0; i < NI; ++i) stage[lane + 32 * i] = acc[u][i];
-                __syncwarp();
-                const int64_t orow = a.out_index ? a.out_index[uid] : uid;
+        for (int mt = 0; mt < 2; ++mt) {
+            __syncthreads();                             // stage rows free
+            double* st = sStage + (size_t)ar * SM::LDS_ + 2 * ac;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                if (n < ntw)
+                    *reinterpret_cast<double2*>(st + (ng + 8 * n) * 8) = make_double2(c[mt][n][0], c[mt][n][1]);
+            __syncthreads();
+            for (int s8 = 0; s8 < 8; ++s8) {
+                const int u = mt * 8 + s8;
+                const int uid = sUnit[u];
+                if (uid < 0) continue;
+                const double* row_s = sStage + (size_t)s8 * SM::LDS_;
+                const int64_t row = sOut[u];
+                const double W = sW[u];
+                const double g0 = row_s[pk4[0]], g1 = row_s[pk4[1]], g2 = row_s[pk4[2]], g3 = row_s[pk4[3]];
                 if (a.out_gamma) {
-                    double* dst = a.out_gamma + (size_t)orow * CAV_RR + lane * 4;
-#pragma unroll
-                    for (int s8 = 0; s8 < 8; ++s8) {
-                        const uint2 ix = *reinterpret_cast<const uint2*>(sidx + (s8 * 32 + lane) * 4);
-                        const double g0 = stage[ix.x & 0xFFFFu], g1 = stage[ix.x >> 16];
-                        const double g2 = stage[ix.y & 0xFFFFu], g3 = stage[ix.y >> 16];
-                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};"
-                                     :: "l"(dst + s8 * 128), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
-                    }
+                    double* dst = a.out_gamma + (size_t)row * CAV_RR + oj * CAV_RW + ok4;
+                    asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
                 }
-                if (a.out_delta) a.out_delta[(size_t)orow * CAV_RW + lane] = stage[sidx[CAV_RR + lane]];
-                if (a.out_pv && lane == 0) a.out_pv[orow] = sPv[u];
-            }
-            if (my_part) {     // this warp owns its partial row: plain read-modify-write, fixed order
-                double W[U], tpv = 0.0;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int uid = __ldg(units + u);
-                    W[u] = uid < 0 ? 0.0 : (a.unit_weight ? a.unit_weight[uid] : 1.0);
-                    tpv = fma(W[u], sPv[u], tpv);
+                if (a.partials) { my_tg[0] += W * g0; my_tg[1] += W * g1; my_tg[2] += W * g2; my_tg[3] += W * g3; }
+                if (tid < CAV_RW) {
+                    const double dl = row_s[pd];
+                    if (a.out_delta) a.out_delta[(size_t)row * CAV_RW + tid] = dl;
+                    sTot[1 + tid] += W * dl;
                 }
-#pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    double t = 0.0;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) t = fma(W[u], acc[u][i], t);
-                    if (cn[i] < GT_NPACK + CAV_RW) my_part[cn[i]] += t;
+                if (tid == 32) {
+                    if (a.out_pv) a.out_pv[row] = sPv[u];
+                    sTot[0] += W * sPv[u];
                 }
-                if (lane == 0) my_part[GT_PV_COL] += tpv;
             }
         }
     }
-}
-
-// totals[1057] = PV | delta[32] | gamma[32][32] from the packed per-warp partial rows [n_rows][GT_NC];
-// one warp per output entry, lane-strided sums combined in a fixed butterfly (bitwise reproducible for a grid)
-__global__ void __launch_bounds__(256)
-k_reduce_packed(const double* __restrict__ partials, int64_t n_rows, double* totals)
-{
-    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (e >= CAV_NOUT) return;
-    const int col = e == 0 ? GT_PV_COL : (e <= CAV_RW ? GT_NPACK + e - 1 : gt_packed((e - 33) >> 5, (e - 33) & 31));
-    double s = 0.0;
-    for (int64_t w = lane; w < n_rows; w += 32) s += partials[w * GT_NC + col];
+    if (a.partials) {     // accumulate into this CTA's partial row (zeroed by the host before the first class launch)
+        double* Pr = a.partials + (size_t)blockIdx.x * CAV_NOUT;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) totals[e] = s;
+        for (int q = 0; q < 4; ++q) Pr[33 + oj * CAV_RW + ok4 + q] += my_tg[q];
+        if (tid < CAV_RW) Pr[1 + tid] += sTot[1 + tid];
+        if (tid == 32) Pr[0] += sTot[0];
+    }
 }
 
 // totals[e] = sum_rows partials[row][e]; one warp per entry, lane-strided partial sums combined

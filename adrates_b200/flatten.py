@@ -58,7 +58,7 @@ class FlatPortfolio:
                 self.group_units, self.unit_weight] + ([self.out_index] if self.out_index is not None else [])
         tp = self.tile_plan
         if tp is not None:
-            arrs += [tp.tile_units, tp.tile_kstart, tp.tile_kcount, tp.k_row, tp.k_pos, tp.k_coef, tp.pairs, tp.tile_mask]
+            arrs += [tp.tile_units, tp.tile_kstart, tp.tile_kcount, tp.k_row, tp.k_pos, tp.k_coef, tp.k_pos2, tp.k_coef2, tp.pairs, tp.tile_mask]
         return int(sum(a.nbytes for a in arrs))
 
     def with_tiles(self, n_nodes: int, plan=None) -> "FlatPortfolio":

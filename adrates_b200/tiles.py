@@ -1,4 +1,4 @@
-"""Tile planner for the tiled units kernel (k_units_simt).
+"""Tile planner for the tiled units kernel (k_units_mma).
 
 The Greeks of a unit are a linear combination of curve-only matrices.  With v = w0 g_a + w1 g_b and
 H_n = hess(ln d_n), a bracketed term contributes
@@ -9,8 +9,8 @@ H_n = hess(ln d_n), a bracketed term contributes
 so for units that bracket the same node pairs position by position ("same signature"),
 gamma[units x 528 packed entries | 32 delta columns] = A[units x K] . B[K x 560] with B rows taken from
 per-curve symmetric tables and only the K coefficients A depending on the unit.  That is a dense FP64 GEMM
-per tile; the kernel gives each tile of TM units to one warp (lane = compact column, DFMA), so each table row is
-read once per tile instead of once per unit.  Only the columns of the tile's *active* par-rate pillars are
+per tile of TM units, which the kernel runs on the tensor pipe (mma.sync.m8n8k4.f64); each table row is read
+once per tile instead of once per unit.  Only the columns of the tile's *active* par-rate pillars are
 computed (tile_mask, from the dependency structure of the bootstrap plan); tiles are ordered by size class
 (number of compact columns / 32) because the kernel is instantiated per class.
 
@@ -24,7 +24,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-TM = 4             # units per tile (one warp of k_units_simt owns a tile)
+TM = 16            # units per tile (one CTA of k_units_mma owns a tile)
 NCOL = 576         # padded row length: 528 packed gamma entries + 32 delta columns + 16 zeros
 NPACK = 528
 
@@ -43,8 +43,11 @@ class TilePlan:
     k_row: np.ndarray         # i32 [sum K over groups] table row id
     k_pos: np.ndarray         # i32 term position the coefficient comes from
     k_coef: np.ndarray        # i32 coefficient kind
+    k_pos2: np.ndarray        # i32 second contribution to the same table row (same 32-position chunk), -1 = none
+    k_coef2: np.ndarray       # i32
+    perm: np.ndarray          # i32 [32] pillar permutation: position q of the packed tables holds pillar perm[q]
     pairs: np.ndarray         # i32 [n_pair_rows*2] (a, b) node pairs that need a G_ab row
-    tile_mask: np.ndarray     # u32 [n_tiles] bit r set = par-rate pillar r can be non-zero in this tile's Greeks
+    tile_mask: np.ndarray     # u32 [n_tiles] bit q set = pillar perm[q] can be non-zero in this tile's Greeks
     n_table_rows: int         # 3*G + n_pair_rows (+1 zero row appended by the library)
     leftover_units: np.ndarray  # i32 units not covered by tiles (generic kernel)
 
@@ -85,11 +88,12 @@ def node_support_masks(node_swap, node_prev, node_acc=None) -> np.ndarray:
 def tile_class(mask: int) -> int:
     """Size class of a tile (mirrors cav_tile_class in csrc/cav_api.cu)."""
     na = bin(int(mask)).count("1")
-    ni = (na * (na + 3) // 2 + 31) // 32
-    return 0 if ni <= 2 else 1 if ni <= 4 else 2 if ni <= 6 else 3 if ni <= 8 else 4 if ni <= 12 else 5
+    nnt = (na * (na + 3) // 2 + 7) // 8
+    return 0 if nnt <= 8 else 1 if nnt <= 16 else 2 if nnt <= 24 else 3 if nnt <= 32 else 4 if nnt <= 48 else 5
 
 
-def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = None) -> TilePlan:
+def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = None, merge: bool = True,
+               permute: bool = True) -> TilePlan:
     """flat: FlatPortfolio with n_pairs == 2.  G: number of curve nodes.  support: u32 [G] pillar masks of the
     nodes (node_support_masks) or None = every pillar is active everywhere (no column compaction)."""
     if flat.n_pairs != 2:
@@ -106,9 +110,21 @@ def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = No
     for u in range(flat.n_units):
         groups.setdefault(key[off[u]:off[u + 1]].tobytes(), []).append(u)
     pair_index = {}
-    k_row, k_pos, k_coef = [], [], []
-    t_units, t_kstart, t_kcount, t_npos, t_mask = [], [], [], [], []
+    k_row, k_pos, k_coef, k_pos2, k_coef2 = [], [], [], [], []
+    t_units, t_kstart, t_kcount, t_npos, t_mask, t_work = [], [], [], [], [], []
     leftover = []
+
+    def emit(open_rows, row, pos, cf):
+        """A table row met twice inside one 32-position chunk (consecutive terms bracket a common node) becomes
+        ONE K row whose coefficient is the sum of both contributions."""
+        hit = open_rows.get(row) if merge else None
+        if hit is not None and k_pos2[hit] < 0 and (k_pos[hit] >> 5) == (pos >> 5):
+            k_pos2[hit] = pos
+            k_coef2[hit] = cf
+            return
+        open_rows[row] = len(k_row)
+        k_row.append(row); k_pos.append(pos); k_coef.append(cf); k_pos2.append(-1); k_coef2.append(-1)
+
     for sig, units in groups.items():
         if len(units) < min_group:
             leftover += units
@@ -123,19 +139,19 @@ def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = No
             mask = np.bitwise_or.reduce(support[na_all]) if len(na_all) else np.uint32(0)
             if len(nb_all):
                 mask = mask | np.bitwise_or.reduce(support[nb_all])
+        open_rows = {}
         for j, kk in enumerate(ks):
             knd, na, nb = int(kk >> 40), int((kk >> 20) & 0xFFFFF), int(kk & 0xFFFFF)
             if knd == 0:
-                k_row.append(row_C(na, G)); k_pos.append(j); k_coef.append(COEF_P)
+                emit(open_rows, row_C(na, G), j, COEF_P)
             else:
-                k_row += [row_H(na, G), row_Gnn(na, G)]
-                k_pos += [j, j]
-                k_coef += [COEF_PW0, COEF_PW0SQ]
+                emit(open_rows, row_H(na, G), j, COEF_PW0)
+                emit(open_rows, row_Gnn(na, G), j, COEF_PW0SQ)
                 if knd == 2:
                     pi = pair_index.setdefault((na, nb), len(pair_index))
-                    k_row += [row_H(nb, G), row_Gnn(nb, G), 3 * G + pi]
-                    k_pos += [j, j, j]
-                    k_coef += [COEF_PW1, COEF_PW1SQ, COEF_PW0W1]
+                    emit(open_rows, row_H(nb, G), j, COEF_PW1)
+                    emit(open_rows, row_Gnn(nb, G), j, COEF_PW1SQ)
+                    emit(open_rows, 3 * G + pi, j, COEF_PW0W1)
         kcount = len(k_row) - kstart
         ua = np.array(units, dtype=np.int32)
         pad = (-len(ua)) % TM
@@ -146,7 +162,23 @@ def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = No
             t_kcount.append(kcount)
             t_npos.append(len(ks))
             t_mask.append(mask)
+            t_work.append(kcount)
     n_tiles = len(t_units)
+    # Pillar permutation: pillars that are active in most of the work come first, so that the active sets (which
+    # are nested: every pillar up to the maturity, plus a few short-end ones) are prefixes of the permuted order
+    # and the compact columns of a tile are mostly CONTIGUOUS in the packed tables (coalesced table-row loads).
+    perm = np.arange(32, dtype=np.int32)
+    if n_tiles and support is not None and permute:
+        m = np.array(t_mask, dtype=np.uint64)
+        wk = np.array(t_work, dtype=np.float64)
+        freq = np.array([float(np.sum(wk[((m >> np.uint64(r)) & np.uint64(1)) == 1])) for r in range(32)])
+        perm = np.argsort(-freq, kind="stable").astype(np.int32)
+        pos_of = np.empty(32, dtype=np.int64)
+        pos_of[perm] = np.arange(32)
+        pm = np.zeros(n_tiles, dtype=np.uint64)
+        for r in range(32):
+            pm |= ((m >> np.uint64(r)) & np.uint64(1)) << np.uint64(pos_of[r])
+        t_mask = [np.uint32(x) for x in pm]
     if n_tiles:      # order tiles by size class (stable: neighbours keep sharing table rows)
         order = np.argsort(np.array([tile_class(m) for m in t_mask]), kind="stable")
         t_units = [t_units[i] for i in order]
@@ -157,11 +189,11 @@ def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = No
     pairs = np.zeros((len(pair_index), 2), dtype=np.int32)
     for (na, nb), pi in pair_index.items():
         pairs[pi] = (na, nb)
+    i32 = lambda x: np.array(x, dtype=np.int32)  # noqa: E731
     return TilePlan(
         n_tiles, TM,
         np.concatenate(t_units).astype(np.int32) if n_tiles else np.zeros(0, dtype=np.int32),
-        np.array(t_kstart, dtype=np.int32), np.array(t_kcount, dtype=np.int32), np.array(t_npos, dtype=np.int32),
-        np.array(k_row, dtype=np.int32), np.array(k_pos, dtype=np.int32), np.array(k_coef, dtype=np.int32),
+        i32(t_kstart), i32(t_kcount), i32(t_npos), i32(k_row), i32(k_pos), i32(k_coef), i32(k_pos2), i32(k_coef2), perm,
         pairs.reshape(-1), np.array(t_mask, dtype=np.uint32), 3 * G + len(pair_index),
         np.array(leftover, dtype=np.int32))
 

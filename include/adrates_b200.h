@@ -137,7 +137,8 @@ int cav_portfolio_upload(cav_ctx* ctx,
  * Must be called after every cav_portfolio_upload (which clears the plan). */
 int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int32_t* tile_units, const int32_t* tile_kstart,
                             const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
-                            const int32_t* k_coef, int n_pair_rows, const int32_t* pairs, const uint32_t* tile_mask);
+                            const int32_t* k_coef, const int32_t* k_pos2, const int32_t* k_coef2, int n_pair_rows,
+                            const int32_t* pairs, const uint32_t* tile_mask, const int32_t* pillar_perm);
 
 /* ---- valuation: replaces Position.compute / Portfolio.compute ----------------------
  * (cavour/market/position/position.py:62-80, cavour/market/portfolio/portfolio.py:39-67,

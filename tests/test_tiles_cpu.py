@@ -53,6 +53,9 @@ def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
     for t in range(tp.n_tiles):
         ks, kc, P = tp.tile_kstart[t], tp.tile_kcount[t], tp.tile_npos[t]
         rows, pos, coef = tp.k_row[ks:ks + kc], tp.k_pos[ks:ks + kc], tp.k_coef[ks:ks + kc]
+        pos2, coef2 = tp.k_pos2[ks:ks + kc], tp.k_coef2[ks:ks + kc]
+        two = coef2 >= 0
+        assert np.all((pos2[two] >> 5) == (pos[two] >> 5))     # both contributions in one 32-position chunk
         A = np.zeros((TM, kc))
         units = tp.tile_units[t * TM:(t + 1) * TM]
         for s, u in enumerate(units):
@@ -64,10 +67,15 @@ def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
             p = flat.amt[i] * np.exp(w[i, 0] * L[nd[i, 0]] + w[i, 1] * L[nd[i, 1]])
             table = np.stack([p, p * w[i, 0], p * w[i, 1], p * w[i, 0] ** 2, p * w[i, 1] ** 2, p * w[i, 0] * w[i, 1]])
             A[s] = table[coef, np.arange(kc)]
+            i2 = i0 + np.where(two, pos2, 0)
+            p2 = flat.amt[i2] * np.exp(w[i2, 0] * L[nd[i2, 0]] + w[i2, 1] * L[nd[i2, 1]])
+            table2 = np.stack([p2, p2 * w[i2, 0], p2 * w[i2, 1], p2 * w[i2, 0] ** 2, p2 * w[i2, 1] ** 2, p2 * w[i2, 0] * w[i2, 1]])
+            A[s] += np.where(two, table2[np.where(two, coef2, 0), np.arange(kc)], 0.0)
             u_pv[u] = (flat.amt[i0:i0 + P] * np.exp(w[i0:i0 + P, 0] * L[nd[i0:i0 + P, 0]] + w[i0:i0 + P, 1] * L[nd[i0:i0 + P, 1]])).sum()
         Cm = A @ T[rows]
         # column compaction: everything outside the tile's active pillars is structurally zero
-        act = np.array([(int(tp.tile_mask[t]) >> r) & 1 for r in range(32)], dtype=bool)
+        pos_of = np.argsort(tp.perm)              # the masks are in permuted pillar order
+        act = np.array([(int(tp.tile_mask[t]) >> int(pos_of[r])) & 1 for r in range(32)], dtype=bool)
         dead = np.array([not (act[j] and act[k]) for j in range(32) for k in range(j + 1)] + list(~act))
         assert not np.any(T[rows][:, :NPACK + 32][:, dead])
         for s, u in enumerate(units):
