@@ -41,6 +41,8 @@ struct cav_ctx {
     bool own_stream = true;
     bool profile = false;
     cudaEvent_t evk[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t aux[CAV_N_CLASSES] = {nullptr};      // size classes of the tiled units kernel run side by side
+    cudaEvent_t ev_fork = nullptr, ev_join[CAV_N_CLASSES] = {nullptr};
     int evk_n = 0;
     std::string err;
     int64_t launches = 0;
@@ -199,30 +201,56 @@ int mma_ctas_per_sm() {
     return n;
 }
 
-int simt_max_grid(const cav_ctx* ctx) {
-    int m = 1;
-#define X(NT, MINB) m = std::max(m, mma_ctas_per_sm<NT, MINB>());
+// grid of one class launch (persistent CTAs, at most the resident capacity of the class)
+template <int NT, int MINB>
+int mma_grid(const cav_ctx* ctx, int n_tiles) {
+    const int cap = mma_ctas_per_sm<NT, MINB>() * ctx->sm_count;
+    return n_tiles < cap ? n_tiles : cap;
+}
+
+// Rows of the partial-totals buffer: every class launch owns a contiguous block of rows, one per CTA, and
+// overwrites it (no zero fill, no accumulation across launches), so the classes can run concurrently.
+int64_t mma_partial_rows(const cav_ctx* ctx) {
+    const int* cb = ctx->class_begin;
+    int64_t rows = 0;
+    int c = 0;
+#define X(NT, MINB) rows += mma_grid<NT, MINB>(ctx, cb[c + 1] - cb[c]); ++c;
     MMA_CLASSES(X)
 #undef X
-    return m * ctx->sm_count;
+    return rows;
 }
 
 template <int NT, int MINB>
-void launch_mma(cav_ctx* ctx, const SimtArgs& ga, int t0, int t1) {
+void launch_mma(cav_ctx* ctx, SimtArgs ga, int t0, int t1, cudaStream_t st, int64_t* row0) {
     if (t1 <= t0) return;
-    const int cap = mma_ctas_per_sm<NT, MINB>() * ctx->sm_count;
-    const int want = t1 - t0;
-    k_units_mma<NT, MINB><<<want < cap ? want : cap, 256, MmaSmem<NT>::BYTES, ctx->stream>>>(
-        ga, t0, t1, 3 * ctx->G + ctx->n_pair_rows);
+    const int grid = mma_grid<NT, MINB>(ctx, t1 - t0);
+    if (ga.partials) ga.partials += (size_t)(*row0) * CAV_NOUT;
+    *row0 += grid;
+    k_units_mma<NT, MINB><<<grid, 256, MmaSmem<NT>::BYTES, st>>>(ga, t0, t1, 3 * ctx->G + ctx->n_pair_rows);
     ctx->launches++;
 }
 
-void launch_simt_classes(cav_ctx* ctx, const SimtArgs& ga) {
+// The size classes are independent: fork them onto side streams (a small book leaves each class far below the
+// machine's capacity, so the launches overlap instead of queueing) and join back on the context's stream.
+int launch_mma_classes(cav_ctx* ctx, const SimtArgs& ga) {
     const int* cb = ctx->class_begin;
+    int n_active = 0;
+    for (int c = 0; c < CAV_N_CLASSES; ++c) n_active += cb[c + 1] > cb[c];
+    const bool fork = n_active > 1;
+    if (fork) CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+    int64_t row0 = 0;
     int c = 0;
-#define X(NT, MINB) launch_mma<NT, MINB>(ctx, ga, cb[c], cb[c + 1]); ++c;
+#define X(NT, MINB)                                                                           \
+    if (cb[c + 1] > cb[c]) {                                                                  \
+        cudaStream_t st = fork ? ctx->aux[c] : ctx->stream;                                   \
+        if (fork) CK(cudaStreamWaitEvent(st, ctx->ev_fork, 0));                               \
+        launch_mma<NT, MINB>(ctx, ga, cb[c], cb[c + 1], st, &row0);                           \
+        if (fork) { CK(cudaEventRecord(ctx->ev_join[c], st)); CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[c], 0)); } \
+    }                                                                                         \
+    ++c;
     MMA_CLASSES(X)
 #undef X
+    return CAV_OK;
 }
 
 template <int K>
@@ -256,6 +284,10 @@ int cav_create(cav_ctx** out, int device) {
     }
     for (int i = 0; i < 5; ++i)
         if (cudaEventCreate(&ctx->evk[i]) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
+    for (int i = 0; i < CAV_N_CLASSES; ++i)
+        if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     *out = ctx;
     return CAV_OK;
 }
@@ -279,6 +311,8 @@ void cav_destroy(cav_ctx* ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     for (int i = 0; i < 5; ++i) cudaEventDestroy(ctx->evk[i]);
+    cudaEventDestroy(ctx->ev_fork);
+    for (int i = 0; i < CAV_N_CLASSES; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -734,11 +768,8 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (use_gemm && !ctx->tsym_valid) { int rc = build_sym_tables(ctx); if (rc) return rc; }
     int64_t rows = 0;
     int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
-    if (use_gemm) rows = (int64_t)simt_max_grid(ctx);              // one partial row per persistent CTA
-    if (need_agg) {
-        CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
-        if (use_gemm) CK(cudaMemsetAsync(ctx->partials, 0, sizeof(double) * rows * CAV_NOUT, ctx->stream));
-    }
+    if (use_gemm) rows = mma_partial_rows(ctx);                   // one partial row per persistent CTA of every class
+    if (need_agg) CK(dev_alloc(ctx, &ctx->partials, (size_t)rows * CAV_NOUT));
     UnitsArgs a;
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
     a.node = ctx->node; a.L = ctx->L; a.g = ctx->g; a.Hf = ctx->Hf; a.Cf = ctx->Cf;
@@ -766,7 +797,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         ga.unit_offsets = a.unit_offsets; ga.amt = a.amt; ga.weight = a.weight; ga.node = a.node; ga.L = a.L;
         ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
         ga.out_gamma = a.out_gamma; ga.partials = a.partials;
-        launch_simt_classes(ctx, ga);
+        { int rc = launch_mma_classes(ctx, ga); if (rc) return rc; }
     } else if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
     else launch_units<6>(ctx, a, want_d, want_g, grid);
     CK(cudaGetLastError());

@@ -372,7 +372,7 @@ struct SimtArgs {
     double* out_pv;
     double* out_delta;
     double* out_gamma;
-    double* partials;          // [CTAs of the largest grid][1057] totals per persistent CTA, or null
+    double* partials;          // [CTAs of this launch][1057] totals per persistent CTA, or null
 };
 
 #define GM_PC 32                 // term positions per chunk
@@ -590,12 +590,12 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
             }
         }
     }
-    if (a.partials) {     // accumulate into this CTA's partial row (zeroed by the host before the first class launch)
+    if (a.partials) {     // this CTA's partial row (every launch owns its own block of rows and overwrites it)
         double* Pr = a.partials + (size_t)blockIdx.x * CAV_NOUT;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) Pr[33 + oj * CAV_RW + ok4 + q] += my_tg[q];
-        if (tid < CAV_RW) Pr[1 + tid] += sTot[1 + tid];
-        if (tid == 32) Pr[0] += sTot[0];
+        for (int q = 0; q < 4; ++q) Pr[33 + oj * CAV_RW + ok4 + q] = my_tg[q];
+        if (tid < CAV_RW) Pr[1 + tid] = sTot[1 + tid];
+        if (tid == 32) Pr[0] = sTot[0];
     }
 }
 
