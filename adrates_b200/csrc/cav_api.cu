@@ -255,7 +255,7 @@ int launch_mma_classes(cav_ctx* ctx, const SimtArgs& ga) {
 
 template <int K>
 void launch_expand_rows(cav_ctx* ctx, double* pv, double* delta) {
-    k_expand_rows<K><<<(unsigned)((ctx->n_trades + 7) / 8), 256, 0, ctx->stream>>>(
+    k_expand_rows<K><<<(unsigned)((ctx->n_trades + 8 * XR_ROWS - 1) / (8 * XR_ROWS)), 256, 0, ctx->stream>>>(
         ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->u_pv, ctx->u_delta, pv, delta);
     ctx->launches++;
 }

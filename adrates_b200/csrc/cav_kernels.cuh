@@ -685,28 +685,45 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
     }
 }
 
-// PV and delta rows of the expansion, gathered per OUTPUT row (warp = row, lane = pillar) from the
-// unit results with the row-ordered tables of k_row_tables: consecutive rows write consecutive
-// memory, instead of the 8-byte / 256-byte scatters the group-ordered k_expand would issue
-// (measured: 1M scattered 8-byte PV stores alone cost 0.1 ms).
+// PV and delta rows of the expansion, gathered per OUTPUT row (lane = pillar) from the unit results with the
+// row-ordered tables of k_row_tables: consecutive rows write consecutive memory, instead of the 8-byte /
+// 256-byte scatters the group-ordered k_expand would issue (measured: 1M scattered 8-byte PV stores alone cost
+// 0.1 ms).  A warp owns 8 consecutive rows: it fetches their (unit, weight) pairs with one coalesced load,
+// issues all unit-row gathers before the first store (the kernel is latency-, not bandwidth-bound otherwise)
+// and writes the 8 PVs as one 64-byte run.
+#define XR_ROWS 8
 template <int K>
 __global__ void __launch_bounds__(256)
 k_expand_rows(int64_t n_trades, const int* __restrict__ row_units, const double* __restrict__ row_weight,
               const double* __restrict__ u_pv, const double* __restrict__ u_delta, double* pv, double* delta)
 {
     const int lane = threadIdx.x & 31;
-    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= n_trades) return;
-    double d = 0.0, p = 0.0;
+    const int64_t row0 = ((int64_t)blockIdx.x * 8 + (threadIdx.x >> 5)) * XR_ROWS;
+    if (row0 >= n_trades) return;
+    const int nr = (n_trades - row0) < XR_ROWS ? (int)(n_trades - row0) : XR_ROWS;
+    int my_u = 0;
+    double my_w = 0.0;
+    if (lane < nr * K) { my_u = __ldg(row_units + row0 * K + lane); my_w = __ldg(row_weight + row0 * K + lane); }
+    double d[XR_ROWS], p = 0.0;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-        const double w = row_weight[row * K + k];
-        const int u = row_units[row * K + k];
-        if (delta) d += w * u_delta[(size_t)u * CAV_RW + lane];
-        if (pv && lane == 0) p += w * u_pv[u];
+    for (int r = 0; r < XR_ROWS; ++r) {
+        d[r] = 0.0;
+        double pr = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int u = __shfl_sync(0xffffffffu, my_u, r * K + k);
+            const double w = __shfl_sync(0xffffffffu, my_w, r * K + k);
+            if (delta) d[r] = fma(w, __ldg(u_delta + (size_t)u * CAV_RW + lane), d[r]);
+            if (pv) pr = fma(w, __ldg(u_pv + u), pr);
+        }
+        if (lane == r) p = pr;
     }
-    if (delta) delta[row * CAV_RW + lane] = d;
-    if (pv && lane == 0) pv[row] = p;
+    if (delta) {
+#pragma unroll
+        for (int r = 0; r < XR_ROWS; ++r)
+            if (r < nr) delta[(row0 + r) * CAV_RW + lane] = d[r];
+    }
+    if (pv && lane < nr) pv[row0 + lane] = p;
 }
 
 // ------------------------------------------------------------------------------------------
