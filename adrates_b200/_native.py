@@ -44,6 +44,8 @@ _SIGS = {
     "cav_portfolio_value_host": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "cav_portfolio_delta_gemm": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "cav_scenarios": (C.c_int, [_P, _P, C.c_int, _P]),
+    "cav_curve_df": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_int64, _P]),
+    "cav_cashflow_pv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
 }
 EXPORTS = tuple(_SIGS)
 
@@ -165,6 +167,24 @@ class Context:
         out = np.empty_like(tt)
         self._ck(self._dll.cav_df_ad(self._h, _ptr(x), _ptr(d), x.shape[0], _ptr(tt), tt.shape[0], _ptr(out)))
         return out
+
+    def curve_df(self, interp_method: int, node_time, node_df, t):
+        """DiscountCurve.df / Interpolator._uinterpolate on the path-A nodes."""
+        x, d, tt = _f64(node_time), _f64(node_df), _f64(t)
+        out = np.empty_like(tt)
+        self._ck(self._dll.cav_curve_df(self._h, int(interp_method), _ptr(x), _ptr(d), x.shape[0], _ptr(tt),
+                                        tt.shape[0], _ptr(out)))
+        return out
+
+    def cashflow_pv(self, interp_method: int, node_time, node_df, t_value: float, offsets, t, amt):
+        """PV per trade of explicit cashflows on the path-A nodes; returns (pv[n_trades], total)."""
+        x, d, tt, aa = _f64(node_time), _f64(node_df), _f64(t), _f64(amt)
+        off = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = off.shape[0] - 1
+        pv, tot = np.zeros(n), C.c_double()
+        self._ck(self._dll.cav_cashflow_pv(self._h, int(interp_method), _ptr(x), _ptr(d), x.shape[0], float(t_value), n,
+                                           _ptr(off), _ptr(tt), _ptr(aa), _ptr(pv), C.byref(tot)))
+        return pv, float(tot.value)
 
     # ---- portfolio
     def portfolio_upload(self, flat):

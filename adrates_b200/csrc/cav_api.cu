@@ -82,6 +82,8 @@ struct cav_ctx {
     bool tiles_valid = false, tsym_valid = false;
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
     double *sc_rates = nullptr, *sc_P = nullptr, *sc_L = nullptr, *sc_upv = nullptr;   // scenario scratch (grow-only)
+    double *cf_x = nullptr, *cf_d = nullptr, *cf_t = nullptr, *cf_amt = nullptr, *cf_pv = nullptr;   // cashflow PV scratch (grow-only)
+    int64_t* cf_off = nullptr;
     int64_t* out_index = nullptr;
     double* unit_weight = nullptr;
 
@@ -303,6 +305,8 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
+    dev_free(ctx, &ctx->cf_x); dev_free(ctx, &ctx->cf_d); dev_free(ctx, &ctx->cf_t); dev_free(ctx, &ctx->cf_amt);
+    dev_free(ctx, &ctx->cf_pv); dev_free(ctx, &ctx->cf_off);
     dev_free(ctx, &ctx->tile_mask); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag);
     dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->tile_units); dev_free(ctx, &ctx->tile_kstart); dev_free(ctx, &ctx->tile_kcount); dev_free(ctx, &ctx->tile_npos);
     dev_free(ctx, &ctx->k_pack); dev_free(ctx, &ctx->pairs); dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
@@ -528,6 +532,74 @@ int cav_df_ad(cav_ctx* ctx, const double* node_time, const double* node_df, int 
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     dev_free(ctx, &x); dev_free(ctx, &d); dev_free(ctx, &tt); dev_free(ctx, &o);
     if (e != cudaSuccess) return fail(ctx, CAV_E_CUDA, std::string("cav_df_ad: ") + cudaGetErrorString(e));
+    return CAV_OK;
+}
+
+// ---------------------------------------------------------------------------- path-A curve queries / cashflow PV
+static int check_path_a_curve(cav_ctx* ctx, const char* who, int interp_method, const double* node_time,
+                              const double* node_df, int n_nodes) {
+    if (!node_time || !node_df || n_nodes < 2 || n_nodes > CF_MAX_NODES)
+        return fail(ctx, CAV_E_INVALID, std::string(who) + ": null pointer, fewer than 2 or more than 1024 nodes");
+    if (interp_method != CAV_INTERP_FLAT_FWD_RATES && interp_method != CAV_INTERP_LINEAR_ZERO_RATES)
+        return fail(ctx, CAV_E_UNSUPPORTED, "Invalid interpolation scheme.");
+    for (int i = 0; i < n_nodes; ++i) {
+        if (!(node_df[i] > 0.0)) return fail(ctx, CAV_E_INVALID, std::string(who) + ": discount factors must be positive");
+    }
+    return CAV_OK;
+}
+
+int cav_curve_df(cav_ctx* ctx, int interp_method, const double* node_time, const double* node_df, int n_nodes,
+                 const double* t, int64_t n, double* out) {
+    if (!ctx) return CAV_E_INVALID;
+    { int rc = check_path_a_curve(ctx, "cav_curve_df", interp_method, node_time, node_df, n_nodes); if (rc) return rc; }
+    if (n < 0 || (n && (!t || !out))) return fail(ctx, CAV_E_INVALID, "cav_curve_df: null pointer or negative size");
+    for (int64_t i = 0; i < n; ++i)
+        if (!(t[i] >= 0.0)) return fail(ctx, CAV_E_INVALID, "Interpolate times must all be >= 0");
+    if (n == 0) return CAV_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(upload(ctx, &ctx->cf_x, node_time, (size_t)n_nodes));
+    CK(upload(ctx, &ctx->cf_d, node_df, (size_t)n_nodes));
+    CK(upload(ctx, &ctx->cf_t, t, (size_t)n));
+    CK(dev_alloc(ctx, &ctx->cf_pv, (size_t)n));
+    k_curve_df<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(interp_method, ctx->cf_x, ctx->cf_d, n_nodes, ctx->cf_t, n, ctx->cf_pv);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, ctx->cf_pv, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return CAV_OK;
+}
+
+int cav_cashflow_pv(cav_ctx* ctx, int interp_method, const double* node_time, const double* node_df, int n_nodes,
+                    double t_value, int64_t n_trades, const int64_t* offsets, const double* t, const double* amt,
+                    double* pv, double* total) {
+    if (!ctx) return CAV_E_INVALID;
+    { int rc = check_path_a_curve(ctx, "cav_cashflow_pv", interp_method, node_time, node_df, n_nodes); if (rc) return rc; }
+    if (n_trades < 0 || !offsets || (n_trades && !pv) || !(t_value >= 0.0))
+        return fail(ctx, CAV_E_INVALID, "cav_cashflow_pv: null pointer, negative size or negative valuation time");
+    if (offsets[0] != 0) return fail(ctx, CAV_E_INVALID, "cav_cashflow_pv: offsets must start at 0");
+    for (int64_t i = 0; i < n_trades; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(ctx, CAV_E_INVALID, "cav_cashflow_pv: offsets not monotone");
+    const int64_t n_cf = offsets[n_trades];
+    if (n_cf && (!t || !amt)) return fail(ctx, CAV_E_INVALID, "cav_cashflow_pv: null cashflow arrays");
+    for (int64_t i = 0; i < n_cf; ++i)
+        if (!(t[i] >= 0.0)) return fail(ctx, CAV_E_INVALID, "Interpolate times must all be >= 0");
+    if (total) *total = 0.0;
+    if (n_trades == 0) return CAV_OK;
+    CK(cudaSetDevice(ctx->device));
+    CK(upload(ctx, &ctx->cf_x, node_time, (size_t)n_nodes));
+    CK(upload(ctx, &ctx->cf_d, node_df, (size_t)n_nodes));
+    CK(upload(ctx, &ctx->cf_off, offsets, (size_t)n_trades + 1));
+    CK(upload(ctx, &ctx->cf_t, t, (size_t)n_cf));
+    CK(upload(ctx, &ctx->cf_amt, amt, (size_t)n_cf));
+    CK(dev_alloc(ctx, &ctx->cf_pv, (size_t)n_trades + 1));
+    k_cashflow_pv<<<(unsigned)((n_trades + 7) / 8), 256, 2 * n_nodes * sizeof(double), ctx->stream>>>(
+        interp_method, ctx->cf_x, ctx->cf_d, n_nodes, t_value, n_trades, ctx->cf_off, ctx->cf_t, ctx->cf_amt, ctx->cf_pv);
+    k_sum_fixed<<<1, 1024, 0, ctx->stream>>>(ctx->cf_pv, n_trades, ctx->cf_pv + n_trades);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(pv, ctx->cf_pv, sizeof(double) * n_trades, cudaMemcpyDeviceToHost, ctx->stream));
+    if (total) CK(cudaMemcpyAsync(total, ctx->cf_pv + n_trades, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     return CAV_OK;
 }
 

@@ -864,6 +864,87 @@ __global__ void k_df_ad(const double* __restrict__ x, const double* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// Path-A discount factors (Interpolator._uinterpolate, interpolator.py:69-170): exact hit on node 0; i = first
+// node with x[i] >= t (n when t lies beyond the last node); LINEAR_ZERO_RATES interpolates the zero rates
+// (the first segment and the extrapolation are flat in the zero rate), FLAT_FWD_RATES interpolates ln DF
+// (extrapolation continues the last segment).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double node_df_path_a(int method, const double* __restrict__ x, const double* __restrict__ d,
+                                                 int n, double t)
+{
+    if (t == x[0]) return d[0];
+    // the reference scans linearly (`while times[i] < t and i < n - 1`); its own OIS curves carry duplicate node
+    // times that differ in the last ulp, so a binary search is not equivalent
+    int i = 0;
+    while (x[i] < t && i < n - 1) ++i;
+    if (t > x[i]) i = n;
+    if (method == 4) {                            // LINEAR_ZERO_RATES
+        double z1, z2;
+        int lo, hi;
+        if (i == 1) { z1 = z2 = -log(d[1]) / x[1]; lo = 0; hi = 1; }
+        else if (i < n) { z1 = -log(d[i - 1]) / x[i - 1]; z2 = -log(d[i]) / x[i]; lo = i - 1; hi = i; }
+        else { z1 = z2 = -log(d[n - 1]) / x[n - 1]; lo = n - 2; hi = n - 1; }
+        const double z = ((x[hi] - t) * z1 + (t - x[lo]) * z2) / (x[hi] - x[lo]);
+        return exp(-z * t);
+    }
+    const int lo = i < n ? i - 1 : n - 2, hi = i < n ? i : n - 1;      // FLAT_FWD_RATES
+    const double y1 = -log(d[lo]), y2 = -log(d[hi]);
+    const double y = ((x[hi] - t) * y1 + (t - x[lo]) * y2) / (x[hi] - x[lo]);
+    return exp(-y);
+}
+
+__global__ void k_curve_df(int method, const double* __restrict__ x, const double* __restrict__ d, int n,
+                           const double* __restrict__ t, int64_t m, double* out)
+{
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < m) out[q] = node_df_path_a(method, x, d, n, t[q]);
+}
+
+// pv[i] = sum over the trade's cashflows of amt * DF(t) / DF(t_value); warp per trade, lanes stride the
+// cashflows, fixed butterfly.  The curve nodes (<= 128 typical) are staged in shared memory.
+#define CF_MAX_NODES 1024
+__global__ void __launch_bounds__(256)
+k_cashflow_pv(int method, const double* __restrict__ x, const double* __restrict__ d, int n, double t_value,
+              int64_t n_trades, const int64_t* __restrict__ offsets, const double* __restrict__ t,
+              const double* __restrict__ amt, double* pv)
+{
+    extern __shared__ double s_nodes[];           // x[n] | d[n]
+    double* sx = s_nodes;
+    double* sd = s_nodes + n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { sx[i] = x[i]; sd[i] = d[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t tr = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (tr >= n_trades) return;
+    const double inv0 = 1.0 / node_df_path_a(method, sx, sd, n, t_value);
+    double acc = 0.0;
+    for (int64_t c = offsets[tr] + lane; c < offsets[tr + 1]; c += 32)
+        acc += (amt[c] * node_df_path_a(method, sx, sd, n, t[c])) * inv0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) pv[tr] = acc;
+}
+
+// total = sum pv[i]: one CTA, fixed strides and butterfly (bitwise reproducible)
+__global__ void __launch_bounds__(1024)
+k_sum_fixed(const double* __restrict__ v, int64_t n, double* out)
+{
+    __shared__ double s[32];
+    double a = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) a += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        a = s[threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (threadIdx.x == 0) *out = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Scenarios: thread per scenario re-bootstraps the grid (DFs only) and stores ln DF;
 // then unit PVs per scenario, then trades.
 // ------------------------------------------------------------------------------------------

@@ -151,6 +151,30 @@ class DiscountCurve:
     _dfs: np.ndarray
     _interp_type: InterpTypes
 
+    def __init__(self, value_dt: Date, df_dts: list, df_values, interp_type: InterpTypes = InterpTypes.FLAT_FWD_RATES):
+        """Curve from year offsets and discount factors (discount_curve.py:40-93): offsets become dates with
+        `add_years`, times are ACT/365 from the value date, (0, 1) is prepended unless the first date is the
+        value date."""
+        if len(df_dts) < 1:
+            raise LibError("Times has zero length")
+        if len(df_dts) != len(df_values):
+            raise LibError("Times and Values are not the same")
+        times, dfs = [0.0], [1.0]
+        dts = value_dt.add_years(list(df_dts))
+        start = 0
+        if dts[0] == value_dt:
+            dfs[0] = float(df_values[0])
+            start = 1
+        for i in range(start, len(dts)):
+            times.append((dts[i] - value_dt) / 365.0)
+            dfs.append(float(df_values[i]))
+        self._times = np.array(times)
+        if np.any(np.diff(self._times) <= 0.0):
+            raise LibError("Times are not sorted in increasing order")
+        self._value_dt = value_dt
+        self._dfs = np.array(dfs)
+        self._interp_type = interp_type
+
     def df(self, dt, day_count=DayCountTypes.ACT_ACT_ISDA):
         times = times_from_dates(dt, self._value_dt, day_count)
         if isinstance(times, np.ndarray):
@@ -169,9 +193,8 @@ class DiscountCurve:
         n = x.shape[0]
         if t == x[0]:
             return float(d[0])
-        i = int(np.searchsorted(x, t, side="left"))   # first node with x[i] >= t
-        if i > n - 1:
-            i = n - 1
+        ge = x >= t                                   # first node with x[i] >= t, scanning from the front like the
+        i = int(np.argmax(ge)) if ge.any() else n - 1 # reference (its OIS curves have duplicate times off by an ulp)
         if t > x[i]:
             i = n
         if self._interp_type == InterpTypes.LINEAR_ZERO_RATES:

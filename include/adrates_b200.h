@@ -140,6 +140,21 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
                             const int32_t* k_coef, const int32_t* k_pos2, const int32_t* k_coef2, int n_pair_rows,
                             const int32_t* pairs, const uint32_t* tile_mask, const int32_t* pillar_perm);
 
+/* ---- explicit-cashflow PV on a path-A curve: replaces DiscountCurve.df / _df and Interpolator._uinterpolate
+ * (cavour/market/curves/discount_curve.py:300-436, cavour/market/curves/interpolator.py:35-170) and the discounting
+ * inside ZeroCouponInflationSwap.value / SwapInflationLeg.value (cavour/trades/rates/zcis.py:176-238,
+ * cavour/trades/rates/swap_inflation_leg.py:166-236).
+ * node_time[n_nodes] (scanned from the front like the reference, whose OIS curves carry duplicate node times) / node_df[n_nodes] are the
+ * curve's `_times` / `_dfs`; interp_method is CAV_INTERP_FLAT_FWD_RATES or CAV_INTERP_LINEAR_ZERO_RATES.
+ * cav_curve_df: out[i] = DF(t[i]); every t must be >= 0 (CAV_E_INVALID otherwise, like the reference's LibError).
+ * cav_cashflow_pv: trade i owns cashflows [offsets[i], offsets[i+1]) at times t[] with signed amounts amt[];
+ * pv[i] = sum amt * DF(t) / DF(t_value); *total = sum_i pv[i] (fixed-order reduction).  All pointers are host memory. */
+int cav_curve_df(cav_ctx* ctx, int interp_method, const double* node_time, const double* node_df, int n_nodes,
+                 const double* t, int64_t n, double* out);
+int cav_cashflow_pv(cav_ctx* ctx, int interp_method, const double* node_time, const double* node_df, int n_nodes,
+                    double t_value, int64_t n_trades, const int64_t* offsets, const double* t, const double* amt,
+                    double* pv, double* total);
+
 /* ---- valuation: replaces Position.compute / Portfolio.compute ----------------------
  * (cavour/market/position/position.py:62-80, cavour/market/portfolio/portfolio.py:39-67,
  * engine.py:153-189, 2541-2574, 2899-2932).
