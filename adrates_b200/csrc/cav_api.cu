@@ -190,7 +190,10 @@ void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma) {
 
 // Size classes of the tiled units kernel: NT = n-tiles (8 compact columns) per warp, MINB = CTAs per SM the register
 // allocation is bounded for.  A class holds tiles with at most 64 NT compact columns.
-#define MMA_CLASSES(X) X(1, 4) X(2, 4) X(3, 3) X(4, 3) X(6, 2) X(9, 2)
+#ifndef MMA_MINB34
+#define MMA_MINB34 3
+#endif
+#define MMA_CLASSES(X) X(1, 4) X(2, 4) X(3, MMA_MINB34) X(4, MMA_MINB34) X(6, 2) X(9, 2)
 
 template <int NT, int MINB>
 int mma_ctas_per_sm() {

@@ -378,6 +378,10 @@ struct SimtArgs {
 #define GM_PC 32                 // term positions per chunk
 #define GM_KC 160                // K rows per chunk (at most 5 per position)
 #define GM_LDA 164               // row stride of the coefficient tile
+#ifndef MMA_UNROLL
+#define MMA_UNROLL 2
+#endif
+constexpr int kMmaUnroll = MMA_UNROLL;   // k-steps (4 table rows each) in flight per warp in the K loop
 
 template <int NT>
 struct MmaSmem {                 // shared-memory layout (doubles first, then 8-byte and 4-byte integers)
@@ -522,7 +526,7 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
             if (ntw > 0) {
                 const double* A0 = sA + ar * GM_LDA + ac;
                 const double* A1 = A0 + 8 * GM_LDA;
-#pragma unroll 2
+#pragma unroll kMmaUnroll
                 for (int k = 0; k < kc4; k += 4) {
                     const double a0 = A0[k], a1 = A1[k];
                     const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC;
