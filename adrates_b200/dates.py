@@ -502,13 +502,18 @@ def times_from_dates(dt, value_dt: Date, day_count_type: DayCountTypes = None):
     """Date(s) -> year fraction(s) from value_dt (helpers.py:154-197)."""
     if not isinstance(value_dt, Date):
         raise LibError("Valuation date is not a Date")
-    dc = None if day_count_type is None else DayCount(day_count_type)
+    # day counts that are a plain day difference over a constant: one vectorised division on the serials
+    # (same floating-point operation as DayCount.year_frac: num / den)
+    den = {None: 365.0, DayCountTypes.ACT_365F: 365, DayCountTypes.ACT_360: 360, DayCountTypes.SIMPLE: 365.0}.get(day_count_type)
+    dc = None if (day_count_type is None or den is not None) else DayCount(day_count_type)
 
     def one(d):
-        return (d - value_dt) / 365.0 if dc is None else dc.year_frac(value_dt, d)[0]
+        return (d._n - value_dt._n) / den if dc is None else dc.year_frac(value_dt, d)[0]
     if isinstance(dt, Date):
         return one(dt)
     if isinstance(dt, list) and len(dt) and isinstance(dt[0], Date):
         import numpy as np
+        if dc is None:
+            return (np.array([d._n for d in dt], dtype=np.int64) - value_dt._n) / den
         return np.array([one(d) for d in dt])
     raise LibError("Discount factor must take dates.")

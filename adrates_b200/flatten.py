@@ -85,6 +85,11 @@ def _leg_sign(leg) -> float:
     return +1.0 if leg._leg_type == SwapTypes.RECEIVE else -1.0
 
 
+def _times(dts, value_dt, dc_type):
+    """Year fractions of a list of dates as a list of Python floats (one vectorised call for the simple day counts)."""
+    return [float(x) for x in times_from_dates(list(dts), value_dt, dc_type)] if len(dts) else []
+
+
 def ois_components(swap, value_dt):
     """[(key, unit, weight)] for one OIS (engine.py:153-189 = fixed leg + floating leg)."""
     if getattr(swap, "derivative_type", None) != InstrumentTypes.OIS_SWAP:
@@ -93,7 +98,7 @@ def ois_components(swap, value_dt):
     fl, ft = swap._fixed_leg, swap._float_leg
     # ---- fixed leg: sum_{t_i > t_val} alpha_i N c DF(t_i) (+ principal, 0 for OIS) ----
     val_t = times_from_dates(value_dt, value_dt, fl._dc_type)
-    t_pay = [times_from_dates(d, value_dt, fl._dc_type) for d in fl._payment_dts]
+    t_pay = _times(fl._payment_dts, value_dt, fl._dc_type)
     live = [i for i, t in enumerate(t_pay) if t > val_t]
     if live:
         times = tuple(t_pay[i] for i in live)
@@ -105,9 +110,9 @@ def ois_components(swap, value_dt):
             out.append((("P", times[-1]), unit_p, _leg_sign(fl) * fl._principal))
     # ---- floating leg ----
     val_t = times_from_dates(value_dt, value_dt, ft._dc_type)
-    tp = [times_from_dates(d, value_dt, ft._dc_type) for d in ft._payment_dts]
-    ts = [times_from_dates(d, value_dt, ft._dc_type) for d in ft._start_accrued_dts]
-    te = [times_from_dates(d, value_dt, ft._dc_type) for d in ft._end_accrued_dts]
+    tp = _times(ft._payment_dts, value_dt, ft._dc_type)
+    ts = _times(ft._start_accrued_dts, value_dt, ft._dc_type)
+    te = _times(ft._end_accrued_dts, value_dt, ft._dc_type)
     al = list(ft._year_fracs)
     live = [i for i, t in enumerate(tp) if t >= val_t]
     notional = ft._notional

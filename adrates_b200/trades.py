@@ -46,25 +46,38 @@ class _SwapLeg:
         self._dg_type = dg_type
         self._end_of_month = end_of_month
 
+    # Rolled schedules are a pure function of these arguments and Dates are immutable: books hold many legs on the
+    # same dates (both legs of a vanilla OIS, every trade of one maturity bucket), so the roll is memoised.
+    _ROLL_CACHE: dict = {}
+    _ROLL_CACHE_MAX = 200_000
+
     def _roll_schedule(self):
-        dts = Schedule(self._effective_dt, self._termination_dt, self._freq_type, self._cal_type,
-                       self._bd_type, self._dg_type, end_of_month=self._end_of_month)._adjusted_dts
-        if len(dts) < 2:
-            raise LibError("Schedule has none or only one date")
-        dc = DayCount(self._dc_type)
-        cal = Calendar(self._cal_type)
-        self._start_accrued_dts, self._end_accrued_dts = [], []
-        self._payment_dts, self._payment_dts_ad = [], []
-        self._year_fracs, self._accrued_days = [], []
-        for start, end in zip(dts[:-1], dts[1:]):
-            self._start_accrued_dts.append(start)
-            self._end_accrued_dts.append(end)
-            pay = end if self._payment_lag == 0 else cal.add_business_days(end, self._payment_lag)
-            self._payment_dts.append(pay)
-            self._payment_dts_ad.append(dc.year_frac(self._effective_dt, end)[0])
-            alpha, num, _ = dc.year_frac(start, end)
-            self._year_fracs.append(alpha)
-            self._accrued_days.append(num)
+        key = (self._effective_dt._n, self._termination_dt._n, self._freq_type, self._cal_type, self._bd_type,
+               self._dg_type, self._end_of_month, self._dc_type, self._payment_lag)
+        hit = _SwapLeg._ROLL_CACHE.get(key)
+        if hit is None:
+            dts = Schedule(self._effective_dt, self._termination_dt, self._freq_type, self._cal_type,
+                           self._bd_type, self._dg_type, end_of_month=self._end_of_month)._adjusted_dts
+            if len(dts) < 2:
+                raise LibError("Schedule has none or only one date")
+            dc = DayCount(self._dc_type)
+            cal = Calendar(self._cal_type)
+            starts, ends, pays, pays_ad, fracs, days = [], [], [], [], [], []
+            for start, end in zip(dts[:-1], dts[1:]):
+                starts.append(start)
+                ends.append(end)
+                pays.append(end if self._payment_lag == 0 else cal.add_business_days(end, self._payment_lag))
+                pays_ad.append(dc.year_frac(self._effective_dt, end)[0])
+                alpha, num, _ = dc.year_frac(start, end)
+                fracs.append(alpha)
+                days.append(num)
+            hit = (starts, ends, pays, pays_ad, fracs, days)
+            if len(_SwapLeg._ROLL_CACHE) < _SwapLeg._ROLL_CACHE_MAX:
+                _SwapLeg._ROLL_CACHE[key] = hit
+        # per-leg lists (the reference's legs own theirs and some callers edit them)
+        self._start_accrued_dts, self._end_accrued_dts = list(hit[0]), list(hit[1])
+        self._payment_dts, self._payment_dts_ad = list(hit[2]), list(hit[3])
+        self._year_fracs, self._accrued_days = list(hit[4]), list(hit[5])
 
 
 class SwapFixedLeg(_SwapLeg):
