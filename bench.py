@@ -369,12 +369,12 @@ def main():
                 az = rz.uniform(-1e6, 1e6, 2 * nz)
                 oz = np.arange(0, 2 * nz + 1, 2, dtype=np.int64)
                 ctxz = _native.Context(local)
-                args = (curve._interp_type.value, curve._times, curve._dfs, 0.0, oz, tz, az)
+                zargs = (curve._interp_type.value, curve._times, curve._dfs, 0.0, oz, tz, az)
                 for _ in range(2):
-                    pvz, totz = ctxz.cashflow_pv(*args)
+                    pvz, totz = ctxz.cashflow_pv(*zargs)
                 t1 = time.perf_counter()
                 for _ in range(5):
-                    pvz, totz = ctxz.cashflow_pv(*args)
+                    pvz, totz = ctxz.cashflow_pv(*zargs)
                 dtz = (time.perf_counter() - t1) / 5
                 ref = np.array([curve._node_df(float(x)) for x in tz[:64]])
                 errz = float(np.max(np.abs(pvz[:32] - (az[:64] * ref).reshape(-1, 2).sum(1)) / 1e6))
