@@ -107,11 +107,15 @@ def cpu_oracle_rate(cv, curve, book, sample, dense, threads=0):
     lt = reference_leg_tables(book)
     tr = dict(sched=book.sched[:sample], coupon=book.coupon[:sample], notional=book.notional[:sample],
               spread=book.spread[:sample], fixed_sign=book.fixed_sign[:sample])
+    if not threads:
+        # all the host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would
+        # silently turn the CPU baseline into a single-thread number
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     t0 = time.perf_counter()
     out = c_oracle.ois_batch((plan["times"], d, J, C), curve._interp_type.value, lt, tr, want=7, dense=dense,
                              n_threads=threads)
     dt = time.perf_counter() - t0
-    return sample / dt, (threads or c_oracle.max_threads()), out
+    return sample / dt, threads, out
 
 
 def run_reference(args):
