@@ -364,6 +364,24 @@ def main():
                                                    "includes H2D of the shocked rates"}
             del pnl
             ctx2.close()
+            # XCCY basis swaps (BASELINE config 5, cross-currency half): 500k GBP/USD swaps on SONIA + SOFR + the
+            # GBP/USD basis curve, PV + domestic / foreign / basis ladders per trade (VALUE + DELTA, like the reference)
+            try:
+                from adrates_b200.synthetic_xccy import make_xccy_book, XccyBookValuer
+                from tests.conftest import load_golden
+                from tests.util_xccy import build_xccy_model
+                gx = load_golden("ref_xccy.json")
+                t1 = time.perf_counter()
+                xbook = make_xccy_book(build_xccy_model(gx), 500_000, seed=11, spot=gx["spot_fx"])
+                xval = XccyBookValuer(xbook, device=local, stream=stream.cuda_stream)
+                x_prep = time.perf_counter() - t1
+                ms = timed(lambda: xval.value(), reps=10)
+                extras["xccy_config5"] = {"trades": xbook.n_trades, "ms_per_step": ms, "trades_per_s": xbook.n_trades / ms * 1e3,
+                                          "units": int(xval.flat_for.n_units), "flatten_seconds_untimed": x_prep,
+                                          "note": "per-trade PV + three 32-wide ladder rows written (776 B/trade); parity of "
+                                                  "this path against the per-trade engine path: tests/test_gpu_xccy_book.py"}
+            except Exception as ex:  # noqa: BLE001
+                extras["xccy_config5"] = {"error": str(ex)}
             # ZCIS leg PVs (BASELINE config 5, inflation half): 500k swaps = 1M cashflows on the path-A nodes of the
             # same curve, host buffers in, per-trade PVs + total out (cav_cashflow_pv)
             try:
