@@ -154,6 +154,30 @@ def _merge_single_df_terms(unit: _Unit):
     return _Unit([((t, 1.0),) for t in ts] + multi_t, [single[t] for t in ts] + multi_a)
 
 
+def bond_components(bond, value_dt):
+    """Engine._compute_bond (engine.py:505-575): `_price_fixed_leg_jax` with payments = coupon payments, principal =
+    face value on the LAST payment date, leg_sign = +1 (investor side), times in the bond's day count; flows on or
+    before the value date are worth 0."""
+    ts = _times(bond._payment_dts, value_dt, bond._dc_type)
+    live = [i for i, t in enumerate(ts) if t > 0.0]
+    terms = [((ts[i], 1.0),) for i in live]
+    amts = [float(bond._coupon_payments[i]) for i in live]
+    if ts and ts[-1] > 0.0:
+        terms.append(((ts[-1], 1.0),))
+        amts.append(float(bond._face_value))
+    if not terms:
+        return []
+    key = ("B", tuple(t[0][0] for t in terms), tuple(amts))
+    return [(key, _Unit(terms, amts), 1.0)]
+
+
+def trade_components(derivative, value_dt):
+    kind = getattr(derivative, "derivative_type", None)
+    if kind == InstrumentTypes.BOND:
+        return bond_components(derivative, value_dt)
+    return ois_components(derivative, value_dt)
+
+
 class Flattener:
     """Collects trades on one curve and emits a FlatPortfolio."""
 
@@ -163,7 +187,7 @@ class Flattener:
         self._trades = []   # list of [(key, unit, weight)]
 
     def add_trade(self, swap):
-        self._trades.append(ois_components(swap, self.value_dt))
+        self._trades.append(trade_components(swap, self.value_dt))
 
     def add_components(self, comps):
         self._trades.append(comps)

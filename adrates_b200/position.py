@@ -81,6 +81,8 @@ class Engine:
         if dtype == InstrumentTypes.XCCY_SWAP:
             from .xccy_engine import compute_xccy
             return compute_xccy([derivative], self.model, request_list, self.device)
+        if dtype == InstrumentTypes.BOND:      # Engine._compute_bond (engine.py:505-640): OIS curve of the currency
+            return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
         if dtype != InstrumentTypes.OIS_SWAP:
             raise LibError(f"{dtype} not yet implemented")
         if collateral_type is not None:

@@ -1,0 +1,46 @@
+"""Bonds through Position.compute / Portfolio.compute on the GPU against Engine._compute_bond of the unmodified
+reference (tests/golden/ref_bonds.json)."""
+import numpy as np
+import pytest
+
+from adrates_b200 import Portfolio, RequestTypes
+from tests.conftest import load_golden
+from tests.util_bonds import build_bond_model, make_bond
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+REQ = [RequestTypes.VALUE, RequestTypes.DELTA, RequestTypes.GAMMA]
+
+
+def _scales(b):
+    T = max(len(b["payment_dts"]) / {"ANNUAL": 1, "SEMI_ANNUAL": 2, "QUARTERLY": 4}[b["freq"]], 1.0)
+    return b["face"], b["face"] * 1e-4 * T, b["face"] * 1e-8 * T * T
+
+
+def test_bond_positions_match_reference():
+    g = load_golden("ref_bonds.json")
+    m = build_bond_model(g)
+    for b in g["bonds"]:
+        res = make_bond(b).position(m).compute(REQ)
+        s_pv, s_d, s_g = _scales(b)
+        assert abs(res.value.amount - b["value"]) <= TOL * max(abs(b["value"]), s_pv), b["id"]
+        assert res.risk.tenors == b["tenors"] and res.value.currency.name == b["currency"]
+        ref_d, ref_g = np.array(b["delta"]), np.array(b["gamma"])
+        assert np.max(np.abs(res.risk.risk_ladder - ref_d) / np.maximum(np.abs(ref_d), s_d)) < TOL, b["id"]
+        assert np.max(np.abs(res.gamma.risk_ladder - ref_g) / np.maximum(np.abs(ref_g), s_g)) < TOL, b["id"]
+        only_v = make_bond(b).position(m).compute([RequestTypes.VALUE])
+        assert only_v.risk is None and only_v.gamma is None
+
+
+def test_bond_portfolio_is_one_batched_valuation():
+    g = load_golden("ref_bonds.json")
+    m = build_bond_model(g)
+    gbp = [b for b in g["bonds"] if b["currency"] == "GBP"]
+    res = Portfolio([make_bond(b).position(m) for b in gbp]).compute(REQ)
+    v = sum(b["value"] for b in gbp)
+    d = np.sum([b["delta"] for b in gbp], axis=0)
+    G = np.sum([b["gamma"] for b in gbp], axis=0)
+    scale = sum(abs(b["value"]) for b in gbp)
+    assert abs(res.value.amount - v) <= TOL * scale
+    assert np.max(np.abs(res.risk.risk_ladder - d)) <= TOL * scale * 1e-4 * 30
+    assert np.max(np.abs(res.gamma.risk_ladder - G)) <= TOL * scale * 1e-8 * 900
