@@ -17,14 +17,14 @@ from .curves import OISCurve, DiscountCurve
 from .models import Model
 from .position import Position, Portfolio, Engine
 from .results import Valuation, Delta, Gamma, Risk, AnalyticsResult
-from .credit import Bond
+from .credit import Bond, FRN
 from .inflation import (InflationIndex, InflationCurve, InflationIndexTypes, InflationInterpTypes, SwapInflationLeg,
                         ZeroCouponInflationSwap)
 
 __all__ = [
     "OIS", "SwapFixedLeg", "SwapFloatLeg", "XccyBasisSwap", "XccyCurve", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
     "Valuation", "Delta", "Gamma", "Risk", "AnalyticsResult", "InflationIndex", "InflationCurve", "InflationIndexTypes",
-    "InflationInterpTypes", "SwapInflationLeg", "ZeroCouponInflationSwap", "Bond",
+    "InflationInterpTypes", "SwapInflationLeg", "ZeroCouponInflationSwap", "Bond", "FRN",
     "LibError", "Date", "Calendar", "CalendarTypes", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
     "DayCountTypes", "FrequencyTypes", "Schedule", "to_tenor", "times_from_dates", "SwapTypes",
     "InstrumentTypes", "RequestTypes", "InterpTypes", "CurveTypes", "CurrencyTypes", "CollateralType",

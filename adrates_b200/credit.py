@@ -1,11 +1,15 @@
-"""Bonds on the CUDA valuation path.
+"""Bonds and floating-rate notes on the CUDA valuation path.
 
 Reference: cavour/trades/credit/bond.py:80-247 (constructor and coupon schedule) and Engine._compute_bond
 (cavour/market/position/engine.py:505-640): a bond is priced with the engine's fixed-leg pricer on the OIS curve of
 its currency - coupons `year_frac x coupon x outstanding principal` on the payment dates plus the face value on the
 last payment date, from the investor's side - so VALUE / DELTA / GAMMA come from the same kernels as an OIS fixed leg.
-Yield, spread and duration analytics of the reference's Bond class (bond.py:264-875) are path-A host code outside
-this path and are not mirrored.
+An FRN (cavour/trades/credit/frn.py:80-220, Engine._compute_frn engine.py:700-925) is the engine's floating-leg pricer
+on the same curve: coupons (forward + quoted margin) x accrual x face, an optional known first fixing, the face value
+at maturity; caps and floors are ignored by the engine (and here).  Like the reference, DELTA / GAMMA exist only when
+the index curve is the discount curve of the currency.
+Yield, spread, discount-margin and duration analytics of the reference's classes (bond.py:264-875, frn.py:222-640)
+are path-A host code outside this path and are not mirrored.
 """
 from __future__ import annotations
 
@@ -89,6 +93,53 @@ class Bond:
         if self._currency not in BOND_CURVE:
             raise LibError(f"No default OIS curve for currency {self._currency}")
         return BOND_CURVE[self._currency]
+
+    def position(self, model):
+        from .position import Position
+        return Position(self, model)
+
+
+class FRN:
+    def __init__(self, issue_dt: Date, maturity_dt_or_tenor, quoted_margin: float, freq_type: FrequencyTypes,
+                 dc_type: DayCountTypes, currency: CurrencyTypes, floating_index: CurveTypes, face_value: float = 100.0,
+                 payment_lag: int = 0, cap_rate=None, floor_rate=None, first_fixing_rate=None,
+                 cal_type: CalendarTypes = CalendarTypes.WEEKEND, bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False):
+        self._issue_dt = issue_dt
+        self._quoted_margin = quoted_margin
+        self._freq_type = freq_type
+        self._dc_type = dc_type
+        self._currency = currency
+        self._floating_index = floating_index
+        self._face_value = face_value
+        self._payment_lag = payment_lag
+        self._cap_rate = cap_rate
+        self._floor_rate = floor_rate
+        self._first_fixing_rate = first_fixing_rate
+        self._cal_type = cal_type
+        self._bd_type = bd_type
+        self._dg_type = dg_type
+        self._end_of_month = end_of_month
+        mat = maturity_dt_or_tenor if isinstance(maturity_dt_or_tenor, Date) else issue_dt.add_tenor(maturity_dt_or_tenor)
+        calendar = Calendar(cal_type)
+        self._maturity_dt = calendar.adjust(mat, bd_type)
+        if issue_dt >= self._maturity_dt:
+            raise LibError("Issue date must be before maturity date")
+        self.derivative_type = InstrumentTypes.FRN
+        dts = Schedule(issue_dt, self._maturity_dt, freq_type, cal_type, bd_type, dg_type,
+                       end_of_month=end_of_month)._adjusted_dts
+        if len(dts) < 2:
+            raise LibError("Schedule must have at least two dates")
+        dc = DayCount(dc_type)
+        self._payment_dts, self._start_accrued_dts, self._end_accrued_dts = [], [], []
+        self._year_fracs, self._accrued_days = [], []
+        for prev, nxt in zip(dts[:-1], dts[1:]):
+            self._start_accrued_dts.append(prev)
+            self._end_accrued_dts.append(nxt)
+            self._payment_dts.append(nxt if payment_lag == 0 else calendar.add_business_days(nxt, payment_lag))
+            yf, days, _ = dc.year_frac(prev, nxt)
+            self._year_fracs.append(yf)
+            self._accrued_days.append(days)
 
     def position(self, model):
         from .position import Position

@@ -171,10 +171,47 @@ def bond_components(bond, value_dt):
     return [(key, _Unit(terms, amts), 1.0)]
 
 
+def frn_components(frn, value_dt):
+    """Engine._compute_frn, single-curve case (engine.py:763-860): `_float_leg_jax` with spreads = quoted margin,
+    notionals = face value, leg_sign = +1, an optional known first fixing on coupon 0, plus the face value
+    discounted from the (adjusted) maturity date; times in the FRN's day count, coupons with payment time >= 0."""
+    dc = frn._dc_type
+    tp = _times(frn._payment_dts, value_dt, dc)
+    ts = _times(frn._start_accrued_dts, value_dt, dc)
+    te = _times(frn._end_accrued_dts, value_dt, dc)
+    N, m = float(frn._face_value), float(frn._quoted_margin)
+    terms, amts = [], []
+    for i, al in enumerate(frn._year_fracs):
+        if not tp[i] >= 0.0:
+            continue
+        if i == 0 and frn._first_fixing_rate is not None:
+            terms.append(((tp[i], 1.0),))
+            amts.append((float(frn._first_fixing_rate) + m) * al * N)
+            continue
+        if al > 0:
+            if tp[i] == te[i]:
+                terms += [((ts[i], 1.0),), ((te[i], 1.0),)]
+            else:
+                terms += [((ts[i], 1.0), (te[i], -1.0), (tp[i], 1.0)), ((tp[i], 1.0),)]
+            amts += [N, -N]
+        if m != 0.0:
+            terms.append(((tp[i], 1.0),))
+            amts.append(m * al * N)
+    tm = float(times_from_dates(frn._maturity_dt, value_dt, dc))
+    if tm > 0.0:
+        terms.append(((tm, 1.0),))
+        amts.append(N)
+    if not terms:
+        return []
+    return [(("N", id(frn)), _Unit(terms, amts), 1.0)]
+
+
 def trade_components(derivative, value_dt):
     kind = getattr(derivative, "derivative_type", None)
     if kind == InstrumentTypes.BOND:
         return bond_components(derivative, value_dt)
+    if kind == InstrumentTypes.FRN:
+        return frn_components(derivative, value_dt)
     return ois_components(derivative, value_dt)
 
 

@@ -83,6 +83,16 @@ class Engine:
             return compute_xccy([derivative], self.model, request_list, self.device)
         if dtype == InstrumentTypes.BOND:      # Engine._compute_bond (engine.py:505-640): OIS curve of the currency
             return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
+        if dtype == InstrumentTypes.FRN:       # Engine._compute_frn (engine.py:700-925)
+            from .credit import BOND_CURVE
+            if derivative._currency not in BOND_CURVE:
+                raise LibError(f"No default OIS curve for currency {derivative._currency}")
+            if BOND_CURVE[derivative._currency] != derivative._floating_index:
+                # the reference values dual-curve FRNs but has no Greeks for them; the dual-curve VALUE needs a
+                # second (index) grid in one term, which the single-grid flat layout does not carry yet
+                raise LibError("Dual-curve FRN delta/gamma not yet implemented. "
+                               "Use same curve for discounting and projection.")
+            return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
         if dtype != InstrumentTypes.OIS_SWAP:
             raise LibError(f"{dtype} not yet implemented")
         if collateral_type is not None:

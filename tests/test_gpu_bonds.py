@@ -5,7 +5,7 @@ import pytest
 
 from adrates_b200 import Portfolio, RequestTypes
 from tests.conftest import load_golden
-from tests.util_bonds import build_bond_model, make_bond
+from tests.util_bonds import build_bond_model, make_bond, make_frn
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
@@ -44,3 +44,22 @@ def test_bond_portfolio_is_one_batched_valuation():
     assert abs(res.value.amount - v) <= TOL * scale
     assert np.max(np.abs(res.risk.risk_ladder - d)) <= TOL * scale * 1e-4 * 30
     assert np.max(np.abs(res.gamma.risk_ladder - G)) <= TOL * scale * 1e-8 * 900
+
+
+def test_frn_positions_match_reference():
+    """Engine._compute_frn, single-curve case, incl. known first fixing, payment lag (product terms) and a seasoned note."""
+    from adrates_b200 import LibError, FRN, Date, FrequencyTypes, DayCountTypes, CurrencyTypes, CurveTypes
+    g = load_golden("ref_frn.json")
+    m = build_bond_model(g)
+    for f in g["frns"]:
+        res = make_frn(f).position(m).compute(REQ)
+        T = max(len(f["payment_dts"]) / {"ANNUAL": 1, "SEMI_ANNUAL": 2, "QUARTERLY": 4}[f["freq"]], 1.0)
+        N = f["face"]
+        assert abs(res.value.amount - f["value"]) <= TOL * max(abs(f["value"]), N), f["id"]
+        ref_d, ref_g = np.array(f["delta"]), np.array(f["gamma"])
+        assert np.max(np.abs(res.risk.risk_ladder - ref_d) / np.maximum(np.abs(ref_d), N * 1e-4 * T)) < TOL, f["id"]
+        assert np.max(np.abs(res.gamma.risk_ladder - ref_g) / np.maximum(np.abs(ref_g), N * 1e-8 * T * T)) < TOL, f["id"]
+    dual = FRN(Date(30, 4, 2024), "2Y", 0.003, FrequencyTypes.QUARTERLY, DayCountTypes.ACT_365F, CurrencyTypes.GBP,
+               CurveTypes.USD_OIS_SOFR)
+    with pytest.raises(LibError, match="Dual-curve FRN"):
+        dual.position(m).compute(REQ)

@@ -1,6 +1,6 @@
 """Builders for the bond goldens (tests/golden/ref_bonds.json, produced by the unmodified reference engine)."""
 from adrates_b200 import (Date, DayCountTypes, FrequencyTypes, BusDayAdjustTypes, SwapTypes, InterpTypes, CurrencyTypes,
-                          Bond)
+                          Bond, FRN, CurveTypes)
 from adrates_b200.models import Model
 
 
@@ -19,3 +19,10 @@ def make_bond(b):
     return Bond(Date(*b["issue"]), mat, b["coupon"], FrequencyTypes[b["freq"]], DayCountTypes[b["dc"]],
                 CurrencyTypes[b["currency"]], face_value=b["face"], payment_lag=b["payment_lag"],
                 amortization_schedule=b["amortization"])
+
+
+def make_frn(f):
+    mat = f["maturity"] if isinstance(f["maturity"], str) else Date(*f["maturity"])
+    return FRN(Date(*f["issue"]), mat, f["margin"], FrequencyTypes[f["freq"]], DayCountTypes[f["dc"]],
+               CurrencyTypes[f["currency"]], CurveTypes[f["index"]], face_value=f["face"], payment_lag=f["payment_lag"],
+               first_fixing_rate=f["first_fixing"])
