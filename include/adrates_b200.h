@@ -123,17 +123,23 @@ int cav_portfolio_upload(cav_ctx* ctx,
                          const int64_t* out_index, const double* unit_weight);
 
 /* Optional tile plan for the tensor-core Greeks kernel (host planner: adrates_b200/tiles.py).  Units that
- * bracket the same node pairs term by term are grouped into tiles of 16 or 32; their gamma/delta rows are then one
- * FP64 GEMM per tile, [32 x K] coefficients times K rows of per-curve symmetric tables (H_n, C_n, g_n g_n^T and,
+ * bracket the same node pairs term by term are grouped into tiles of 16; their gamma/delta rows are then one
+ * FP64 GEMM per tile, [16 x K] coefficients times K rows of per-curve symmetric tables (H_n, C_n, g_n g_n^T and,
  * for the node pairs listed in `pairs`, g_a g_b^T + g_b g_a^T), evaluated with mma.sync.m8n8k4.f64.
- * tile_units[n_tiles][tile_size] (tile_size 16 or 32, -1 = padding) must cover every unit exactly once; tile t uses K rows
+ * tile_units[n_tiles][tile_size] (tile_size 16, -1 = padding) must cover every unit exactly once; tile t uses K rows
  * [tile_kstart[t], tile_kstart[t] + tile_kcount[t]) of (k_row = table row id, k_pos = term position within the
- * unit, k_coef = 0:p 1:p*w0 2:p*w1 3:p*w0^2 4:p*w1^2 5:p*w0*w1).  Table row ids: n (H), G+n (C), 2G+n (g g^T),
+ * unit, k_coef = 0:p 1:p*w0 2:p*w1 3:p*w0^2 4:p*w1^2 5:p*w0*w1), ordered by k_pos, at most 160 per chunk of 32
+ * positions.  k_pos2 / k_coef2 (both NULL, or k_coef2 = -1 per row for none): a second term of the same 32-position
+ * chunk that feeds the same table row (its coefficient is added).  Table row ids: n (H), G+n (C), 2G+n (g g^T),
  * 3G+i (pair i).  Replaces the same reference code as cav_portfolio_value; it only changes how it is computed.
- * tile_mask[n_tiles] (or NULL = all pillars): bit r set when par-rate pillar r can be non-zero in the tile's Greeks
- * (union of the supports of the nodes its terms touch; adrates_b200/tiles.py::node_support_masks derives it from
- * the bootstrap plan).  The tile GEMM then runs over the packed columns of the active pillars only; the masks are
- * checked on the device against the tables (CAV_E_INVALID from the valuation call if a mask is too small).
+ * tile_mask[n_tiles] (or NULL = all pillars): bit q set when the pillar at position q of the permuted order can be
+ * non-zero in the tile's Greeks (union of the supports of the nodes its terms touch;
+ * adrates_b200/tiles.py::node_support_masks derives it from the bootstrap plan).  The tile GEMM then runs over the
+ * packed columns of the active pillars only; the masks are checked on the device against the tables
+ * (CAV_E_INVALID from the valuation call if a mask is too small).  Tiles must be ordered by size class
+ * (compact columns na(na+3)/2 in steps of 64: <= 64, 128, 192, 256, 384, 576), one kernel instantiation per class.
+ * pillar_perm[32] (or NULL = identity): position q of the packed tables holds par-rate pillar pillar_perm[q]; the
+ * planner orders pillars by how much work uses them so that active sets are prefixes (contiguous table columns).
  * Must be called after every cav_portfolio_upload (which clears the plan). */
 int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int32_t* tile_units, const int32_t* tile_kstart,
                             const int32_t* tile_kcount, int64_t n_krows, const int32_t* k_row, const int32_t* k_pos,
