@@ -26,6 +26,9 @@ from .global_types import InstrumentTypes, RequestTypes
 from .results import AnalyticsResult, Delta, Gamma, Valuation
 
 
+TILE_MIN_UNITS = 64     # below this the warp-per-unit kernel is as fast and the tile plan is pure overhead
+
+
 def request_mask(request_list) -> int:
     reqs = set(request_list)
     unknown = [r for r in reqs if not isinstance(r, RequestTypes)]
@@ -112,6 +115,9 @@ def value_positions(derivatives, curve: OISCurve, request_list, device: int = 0,
     for d in derivatives:
         fl.add_trade(d)
     flat = fl.finalize(dedup=(len(derivatives) > 1) if dedup is None else dedup)
+    if (mask & _native.REQ_GAMMA) and flat.n_units >= TILE_MIN_UNITS:
+        plan = curve.path_b_plan()          # books of any size get the tensor-core Greeks kernel (tiles.py)
+        flat.with_tiles(plan.n_nodes, plan)
     sess.ctx.portfolio_upload(flat)
     agg = sess.ctx.portfolio_value_host(mask)
     return _result_from_totals(agg, mask, curve, derivatives[0])

@@ -114,6 +114,41 @@ def test_portfolio_compute_sums_positions(ref_curves, ref_trades):
     assert rel_err(res.gamma.risk_ladder, np.sum([s["gamma"] for s in specs], axis=0), 1e1) < TOL
 
 
+def test_portfolio_of_objects_uses_tile_plan_and_matches_oracle(ref_curves):
+    """Portfolio.compute over 300 OIS objects on ~150 distinct schedules: the public path attaches a tile plan
+    (tensor-core Greeks kernel) above position.TILE_MIN_UNITS; totals against the C oracle."""
+    from oracle import c_oracle
+    from adrates_b200 import OIS, SwapTypes, FrequencyTypes, DayCountTypes, CurveTypes, CurrencyTypes, BusDayAdjustTypes
+    from adrates_b200 import position as pos_mod
+    from adrates_b200.synthetic import make_book, reference_leg_tables
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    curve = model.curves.GBP_OIS_SONIA
+    book = make_book(curve, 300, seed=21, max_offset_bd=40)
+    swaps = []
+    for i in range(book.n_trades):
+        t = book.schedules[book.sched[i]]
+        swaps.append(OIS(t._effective_dt, t._termination_dt, SwapTypes.RECEIVE if book.fixed_sign[i] > 0 else SwapTypes.PAY,
+                         float(book.coupon[i]), FrequencyTypes.ANNUAL, DayCountTypes.ACT_365F, CurveTypes.GBP_OIS_SONIA,
+                         CurrencyTypes.GBP, notional=float(book.notional[i]), float_freq_type=FrequencyTypes.ANNUAL,
+                         float_dc_type=DayCountTypes.ACT_365F, bd_type=BusDayAdjustTypes.MODIFIED_FOLLOWING))
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+    trades = dict(sched=book.sched, coupon=book.coupon, notional=book.notional, spread=book.spread, fixed_sign=book.fixed_sign)
+    pv_c, dl_c, gm_c = c_oracle.ois_batch((plan["times"], d, J, C), METHOD[cv["interp"]], reference_leg_tables(book),
+                                          trades, dense=False)
+    results = []
+    for min_units in (64, 10 ** 9):          # with and without the tile plan
+        pos_mod.TILE_MIN_UNITS = min_units
+        results.append(Portfolio([s.position(model) for s in swaps]).compute(ALL))
+    pos_mod.TILE_MIN_UNITS = 64
+    scale = np.abs(pv_c).sum()
+    for res in results:
+        assert abs(res.value.amount - pv_c.sum()) <= 1e-11 * scale
+        assert np.max(np.abs(res.risk.risk_ladder - dl_c.sum(0))) <= 1e-11 * np.abs(dl_c).sum()
+        assert np.max(np.abs(res.gamma.risk_ladder - gm_c.sum(0))) <= 1e-11 * np.abs(gm_c).sum()
+
+
 def test_reference_property_tests_hold(ref_curves):
     """tests/test_refit_curves.py:152-231 (every calibration swap reprices to |PV| <= 1e-5 through
     Position.compute) and tests/test_ois_request_types.py:841-905 (PAY + RECEIVE = 0 within 1e-10)."""
