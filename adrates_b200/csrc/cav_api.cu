@@ -9,6 +9,7 @@
 #include <vector>
 
 #include <algorithm>
+#include <unordered_map>
 
 #define CAV_N_CLASSES 6
 // size class of a tile from its active-pillar mask: compact columns = na(na+3)/2, 8 per n-tile, 8 warps
@@ -82,6 +83,13 @@ struct cav_ctx {
     bool tiles_valid = false, tsym_valid = false;
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
     double *sc_rates = nullptr, *sc_P = nullptr, *sc_L = nullptr, *sc_upv = nullptr;   // scenario scratch (grow-only)
+    // scenario DF cache: distinct (bracket, weights) queries of the uploaded terms
+    int2* sq_node = nullptr;
+    double2* sq_w = nullptr;
+    int* sq_term = nullptr;
+    double* sc_dfq = nullptr;
+    int64_t sq_n = 0;
+    bool sq_valid = false;
     double *cf_x = nullptr, *cf_d = nullptr, *cf_t = nullptr, *cf_amt = nullptr, *cf_pv = nullptr;   // cashflow PV scratch (grow-only)
     int64_t* cf_off = nullptr;
     int64_t* out_index = nullptr;
@@ -317,6 +325,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
+    dev_free(ctx, &ctx->sq_node); dev_free(ctx, &ctx->sq_w); dev_free(ctx, &ctx->sq_term); dev_free(ctx, &ctx->sc_dfq);
     dev_free(ctx, &ctx->cf_x); dev_free(ctx, &ctx->cf_d); dev_free(ctx, &ctx->cf_t); dev_free(ctx, &ctx->cf_amt);
     dev_free(ctx, &ctx->cf_pv); dev_free(ctx, &ctx->cf_off);
     dev_free(ctx, &ctx->tile_mask); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag);
@@ -685,6 +694,7 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     ctx->n_pairs = n_pairs; ctx->n_comp = n_comp; ctx->direct = direct;
     ctx->row_tables_valid = false;
     ctx->tiles_valid = false;
+    ctx->sq_valid = false;
     return CAV_OK;
 }
 
@@ -982,6 +992,47 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
 }
 
 // ---------------------------------------------------------------------------- scenarios
+// Distinct DF queries of the uploaded single-DF terms (host hash over the term arrays, once per upload).
+static int ensure_scen_queries(cav_ctx* ctx) {
+    if (ctx->sq_valid) return CAV_OK;
+    const size_t nt = (size_t)ctx->n_terms;
+    std::vector<int> node(2 * nt);
+    std::vector<double> w(2 * nt);
+    CK(cudaMemcpyAsync(node.data(), ctx->node, sizeof(int) * 2 * nt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(w.data(), ctx->weight, sizeof(double) * 2 * nt, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    struct Key { int a, b; uint64_t w0, w1; bool operator==(const Key& o) const { return a == o.a && b == o.b && w0 == o.w0 && w1 == o.w1; } };
+    struct Hash { size_t operator()(const Key& k) const {
+        uint64_t h = (uint64_t)(uint32_t)k.a * 0x9E3779B97F4A7C15ull ^ ((uint64_t)(uint32_t)k.b << 32);
+        h ^= k.w0 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        h ^= k.w1 + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+        return (size_t)h; } };
+    std::unordered_map<Key, int, Hash> ids;
+    ids.reserve(nt / 4 + 16);
+    std::vector<int> term_q(nt);
+    std::vector<int2> qn;
+    std::vector<double2> qw;
+    for (size_t i = 0; i < nt; ++i) {
+        Key k;
+        k.a = node[2 * i]; k.b = node[2 * i + 1];
+        std::memcpy(&k.w0, &w[2 * i], 8); std::memcpy(&k.w1, &w[2 * i + 1], 8);
+        auto it = ids.find(k);
+        if (it == ids.end()) {
+            it = ids.emplace(k, (int)qn.size()).first;
+            qn.push_back(make_int2(k.a, k.b));
+            qw.push_back(make_double2(w[2 * i], w[2 * i + 1]));
+        }
+        term_q[i] = it->second;
+    }
+    ctx->sq_n = (int64_t)qn.size();
+    CK(upload(ctx, &ctx->sq_node, qn.data(), qn.size()));
+    CK(upload(ctx, &ctx->sq_w, qw.data(), qw.size()));
+    CK(upload(ctx, &ctx->sq_term, term_q.data(), nt));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->sq_valid = true;
+    return CAV_OK;
+}
+
 int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev) {
     if (!ctx) return CAV_E_INVALID;
     if (!shocked_rates || n_scen < 1 || !pnl_dev) return fail(ctx, CAV_E_INVALID, "cav_scenarios: bad arguments");
@@ -998,7 +1049,22 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
     k_scen_bootstrap<<<(n_scen + 127) / 128, 128, 0, ctx->stream>>>(ctx->G, ctx->R, n_scen, ctx->sc_rates, ctx->node_acc,
                                                                   ctx->node_swap, ctx->node_prev, ctx->sc_P, ctx->sc_L);
     dim3 gu((unsigned)ctx->n_units, (unsigned)((n_scen + 127) / 128));
-    if (ctx->n_pairs == 2)
+    // DF cache when the terms share enough queries (and the cache fits): see k_scen_df
+    bool cached = false;
+    {
+        const char* e = std::getenv("CAV_SCEN_DFCACHE");
+        if (ctx->n_pairs == 2 && ctx->n_terms > 0 && ctx->n_terms <= ((int64_t)8 << 20) && !(e && std::atoi(e) == 0)) {
+            { int rc = ensure_scen_queries(ctx); if (rc) return rc; }
+            cached = ctx->sq_n * 2 <= ctx->n_terms && (size_t)ctx->sq_n * S * sizeof(double) <= ((size_t)4 << 30);
+        }
+    }
+    if (cached) {
+        CK(dev_alloc(ctx, &ctx->sc_dfq, (size_t)ctx->sq_n * S));
+        dim3 gq((unsigned)ctx->sq_n, (unsigned)((n_scen + 127) / 128));
+        k_scen_df<<<gq, 128, 0, ctx->stream>>>(n_scen, ctx->sq_node, ctx->sq_w, ctx->sc_L, ctx->sc_dfq);
+        k_scen_units_q<<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->sq_term, ctx->sc_dfq, ctx->sc_upv);
+        ctx->launches++;
+    } else if (ctx->n_pairs == 2)
         k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
     else
         k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);

@@ -1010,6 +1010,44 @@ k_scen_units(int n_scen, const int64_t* __restrict__ unit_offsets, const double*
     unit_pv[u * n_scen + s] = pv;
 }
 
+// Books with shared dates ask for the same discount factor many times per scenario (the 345k terms of the 100k-trade
+// dedup book are 12.6k distinct (bracket, weights) queries).  DF cache path: every distinct query is evaluated once
+// per scenario (k_scen_df, one exp each), the units then only gather and sum (k_scen_units_q).  dfq is [J][S] with the
+// scenario index fastest; the grid runs query / unit fastest, so the 128-scenario slab of dfq a wave of CTAs reads
+// (J x 1 KB) stays in L2.
+__global__ void __launch_bounds__(128)
+k_scen_df(int n_scen, const int2* __restrict__ q_node, const double2* __restrict__ q_w, const double* __restrict__ Ls,
+          double* dfq)
+{
+    const int64_t j = blockIdx.x;
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= n_scen) return;
+    const int2 n = q_node[j];
+    const double2 w = q_w[j];
+    double ell = w.x * Ls[(size_t)n.x * n_scen + s];
+    if (w.y != 0.0) ell += w.y * Ls[(size_t)n.y * n_scen + s];
+    dfq[j * n_scen + s] = exp(ell);
+}
+
+__global__ void __launch_bounds__(128)
+k_scen_units_q(int n_scen, const int64_t* __restrict__ unit_offsets, const double* __restrict__ amt,
+               const int* __restrict__ term_q, const double* __restrict__ dfq, double* unit_pv /*[U][S]*/)
+{
+    const int64_t u = blockIdx.x;
+    const int s = blockIdx.y * blockDim.x + threadIdx.x;
+    if (s >= n_scen) return;
+    const int64_t t0 = unit_offsets[u], t1 = unit_offsets[u + 1];
+    double pv = 0.0;
+    int64_t i = t0;
+    for (; i + 4 <= t1; i += 4) {                 // four gathers in flight; summed in term order
+        const double d0 = dfq[(size_t)term_q[i] * n_scen + s], d1 = dfq[(size_t)term_q[i + 1] * n_scen + s];
+        const double d2 = dfq[(size_t)term_q[i + 2] * n_scen + s], d3 = dfq[(size_t)term_q[i + 3] * n_scen + s];
+        pv += amt[i] * d0; pv += amt[i + 1] * d1; pv += amt[i + 2] * d2; pv += amt[i + 3] * d3;
+    }
+    for (; i < t1; ++i) pv += amt[i] * dfq[(size_t)term_q[i] * n_scen + s];
+    unit_pv[u * n_scen + s] = pv;
+}
+
 // pnl[s][row] = sum_k w_row,k unit_pv[u_row,k][s]; a 32x32 (rows x scenarios) tile is read with the
 // scenario index fastest (256-byte runs of unit_pv) and written transposed with the row index fastest
 template <int K>

@@ -360,8 +360,8 @@ def main():
             ms = timed(lambda: ctx2.scenarios(shocked, pnl.data_ptr()), reps=3)
             extras["scenarios_config4"] = {"scenarios": S, "trades": nt, "ms": ms, "revaluations_per_s": S * nt / ms * 1e3,
                                            "pnl_bytes": S * nt * 8,
-                                           "note": "shocked curves re-bootstrapped on device (DFs only) + full revaluation; "
-                                                   "includes H2D of the shocked rates"}
+                                           "note": "shocked curves re-bootstrapped on device (DFs only) + full revaluation (one exp per "
+                                                   "distinct DF query and scenario, units gather them); includes H2D of the shocked rates"}
             del pnl
             ctx2.close()
             # XCCY basis swaps (BASELINE config 5, cross-currency half): 500k GBP/USD swaps on SONIA + SOFR + the

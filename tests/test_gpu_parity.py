@@ -244,6 +244,42 @@ def test_scenarios_match_oracle_rebootstrap(ref_curves, ref_trades):
     ctx.close()
 
 
+def test_scenario_df_cache_matches_direct_path(ref_curves, monkeypatch):
+    """The DF-cache scenario path (one exp per distinct query and scenario) against the direct path (one exp per
+    term and scenario) on a book with shared dates, and against the oracle's re-bootstrap for a few cells."""
+    from adrates_b200.synthetic import make_book, flatten_book, shocked_rate_scenarios
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    book = make_book(curve, 1500, seed=5, max_offset_bd=30)
+    flat = flatten_book(book, dedup=True)
+    S = 37
+    shocked = shocked_rate_scenarios(curve, S)
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CAV_SCEN_DFCACHE", flag)
+        ctx = _native.Context(0)
+        ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
+        ctx.portfolio_upload(flat)
+        pnl = torch.zeros(S, flat.n_trades, dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.scenarios(shocked, pnl.data_ptr())
+        ctx.sync()
+        out.append(pnl.cpu().numpy())
+        ctx.close()
+    assert np.array_equal(out[0], out[1])          # same arithmetic in the same order
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    vd = Date(*cv["value_dt"])
+    for s_, i in ((0, 0), (11, 700), (36, 1499)):
+        d = orc.bootstrap_dfs(shocked[s_], plan)
+        tmpl = book.schedules[book.sched[i]]
+        fixed, floating = leg_arrays(tmpl, vd)       # unit-notional, unit-coupon, PAY-fixed template
+        fixed["payments"] = np.asarray(fixed["payments"]) * book.coupon[i] * book.notional[i]
+        floating["notionals"] = np.asarray(floating["notionals"]) * book.notional[i]
+        sign = -book.fixed_sign[i]                   # template pays fixed
+        ref = sign * orc.ois_value_only(plan["times"], d, METHOD[cv["interp"]], fixed, floating)
+        assert abs(out[1][s_, i] - ref) <= TOL * max(abs(ref), book.notional[i]), (s_, i)
+
+
 def test_error_behaviour():
     ctx = _native.Context(0)
     from adrates_b200.error import LibError
