@@ -80,7 +80,9 @@ struct cav_ctx {
     int2* k_pack = nullptr;
     PillarPerm pp;
     double* Tsym = nullptr;
-    bool tiles_valid = false, tsym_valid = false;
+    bool tiles_valid = false;
+    bool tables_ok = false;     // Tsym / row_masks hold the tables of the current curve, pair rows and permutation
+    bool tsym_valid = false;    // ... and the current tile plan's masks have been checked against them
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
     double *sc_rates = nullptr, *sc_P = nullptr, *sc_L = nullptr, *sc_upv = nullptr;   // scenario scratch (grow-only)
     // scenario DF cache: distinct (bracket, weights) queries of the uploaded terms
@@ -94,6 +96,8 @@ struct cav_ctx {
     int64_t* cf_off = nullptr;
     int64_t* out_index = nullptr;
     double* unit_weight = nullptr;
+    std::vector<int64_t> h_unit_offsets;      // host copy (tile-plan validation)
+    std::vector<int> h_pairs;                 // pair rows and permutation of the tables currently on the device
 
     // scratch
     double *u_pv = nullptr, *u_delta = nullptr, *u_gamma = nullptr;
@@ -446,6 +450,7 @@ int cav_curve_build(cav_ctx* ctx, int interp_method, const double* swap_rates, i
     ctx->order = order;
     ctx->has_plan = true;
     ctx->tsym_valid = false;
+    ctx->tables_ok = false;
     return CAV_OK;
 }
 
@@ -459,6 +464,7 @@ int cav_curve_rebuild_dev(cav_ctx* ctx, const double* swap_rates_dev) {
     k_tables<<<ctx->G, 1024, 0, ctx->stream>>>(ctx->order, ctx->df, ctx->jac, ctx->hess, ctx->L, ctx->g, ctx->Hf, ctx->Cf);
     ctx->launches += 2;
     ctx->tsym_valid = false;
+    ctx->tables_ok = false;
     CK(cudaGetLastError());
     return CAV_OK;
 }
@@ -501,6 +507,7 @@ int cav_curve_set_tables(cav_ctx* ctx, const double* dfs, const double* jac, con
     ctx->G = n_nodes; ctx->R = n_rates; ctx->order = order; ctx->interp = 0;
     ctx->has_plan = false;
     ctx->tsym_valid = false;
+    ctx->tables_ok = false;
     return CAV_OK;
 }
 
@@ -654,6 +661,7 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
         unit_weight = W.data();
     }
     CK(cudaSetDevice(ctx->device));
+    ctx->h_unit_offsets.assign(unit_offsets, unit_offsets + n_units + 1);
     CK(upload(ctx, &ctx->unit_offsets, unit_offsets, (size_t)n_units + 1));
     CK(upload(ctx, &ctx->amt, amt, (size_t)n_terms));
     CK(upload(ctx, &ctx->weight, weight, (size_t)n_terms * n_pairs));
@@ -727,10 +735,8 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
         covered += tile_units[i] >= 0;
     }
     if (covered != ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: every unit must belong to exactly one tile");
-    std::vector<int64_t> h_off((size_t)ctx->n_units + 1);
+    const std::vector<int64_t>& h_off = ctx->h_unit_offsets;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(h_off.data(), ctx->unit_offsets, sizeof(int64_t) * h_off.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
     std::vector<int> npos((size_t)n_tiles, 0);
     std::vector<unsigned> masks((size_t)n_tiles, 0xFFFFFFFFu);
     if (tile_mask) std::memcpy(masks.data(), tile_mask, sizeof(unsigned) * n_tiles);
@@ -793,9 +799,17 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     CK(upload(ctx, &ctx->tile_mask, masks.data(), (size_t)n_tiles));
     CK(cudaStreamSynchronize(ctx->stream));
     std::memcpy(ctx->class_begin, class_begin, sizeof(class_begin));
+    // the symmetric tables depend on the curve, the pair rows and the permutation only: keep them (and the mask
+    // check's row masks) when a new plan asks for the same ones
+    std::vector<int> sig(pairs, pairs + 2 * (size_t)n_pair_rows);
+    for (int q = 0; q < 32; ++q) sig.push_back(pp.perm[q]);
+    const bool same_tables = ctx->tables_ok && sig == ctx->h_pairs;
+    ctx->h_pairs.swap(sig);
     ctx->pp = pp;
     ctx->n_tiles = n_tiles; ctx->n_krows = n_krows; ctx->n_pair_rows = n_pair_rows;
-    ctx->tiles_valid = true; ctx->tsym_valid = false;
+    ctx->tiles_valid = true;
+    ctx->tsym_valid = false;
+    if (!same_tables) ctx->tables_ok = false;
     return CAV_OK;
 }
 
@@ -804,7 +818,7 @@ static int ensure_row_tables(cav_ctx* ctx) {
     CK(dev_alloc(ctx, &ctx->row_units, (size_t)ctx->n_trades * ctx->n_comp));
     CK(dev_alloc(ctx, &ctx->row_weight, (size_t)ctx->n_trades * ctx->n_comp));
     if (ctx->n_groups > 0) {
-        k_row_tables<<<(unsigned)((ctx->n_groups + 127) / 128), 128, 0, ctx->stream>>>(
+        k_row_tables<<<(unsigned)((ctx->n_groups + 7) / 8), 256, 0, ctx->stream>>>(
             ctx->n_groups, ctx->n_comp, ctx->group_offsets, ctx->group_units, ctx->comp_weight, ctx->out_index,
             ctx->row_units, ctx->row_weight);
         ctx->launches++;
@@ -816,20 +830,25 @@ static int ensure_row_tables(cav_ctx* ctx) {
 
 static int build_sym_tables(cav_ctx* ctx) {
     const size_t rows = (size_t)3 * ctx->G + ctx->n_pair_rows + 1;
-    CK(dev_alloc(ctx, &ctx->Tsym, rows * GT_NC));
-    k_sym_tables<<<3 * ctx->G, GT_NC, 0, ctx->stream>>>(ctx->G, ctx->g, ctx->Hf, ctx->Cf, ctx->Tsym, ctx->pp);
-    k_pair_tables<<<ctx->n_pair_rows + 1, GT_NC, 0, ctx->stream>>>(ctx->n_pair_rows, ctx->pairs, ctx->g,
-                                                                    ctx->Tsym + (size_t)3 * ctx->G * GT_NC, ctx->pp);
+    if (!ctx->tables_ok) {
+        CK(dev_alloc(ctx, &ctx->Tsym, rows * GT_NC));
+        CK(dev_alloc(ctx, &ctx->row_masks, rows));
+        k_sym_tables<<<3 * ctx->G, GT_NC, 0, ctx->stream>>>(ctx->G, ctx->g, ctx->Hf, ctx->Cf, ctx->Tsym, ctx->pp);
+        k_pair_tables<<<ctx->n_pair_rows + 1, GT_NC, 0, ctx->stream>>>(ctx->n_pair_rows, ctx->pairs, ctx->g,
+                                                                        ctx->Tsym + (size_t)3 * ctx->G * GT_NC, ctx->pp);
+        k_row_masks<<<(unsigned)rows, GT_NC, 0, ctx->stream>>>(ctx->Tsym, ctx->row_masks);
+        ctx->launches += 3;
+        CK(cudaGetLastError());
+        ctx->tables_ok = true;
+    }
     // the tiles' active-pillar masks must cover the support of every table row they use (a wrong mask would
-    // silently drop Greeks): checked on the device whenever the tables are rebuilt
-    CK(dev_alloc(ctx, &ctx->row_masks, rows));
+    // silently drop Greeks): checked on the device for every new plan / new tables
     CK(dev_alloc(ctx, &ctx->check_flag, (size_t)1));
     CK(cudaMemsetAsync(ctx->check_flag, 0, sizeof(int), ctx->stream));
-    k_row_masks<<<(unsigned)rows, GT_NC, 0, ctx->stream>>>(ctx->Tsym, ctx->row_masks);
     k_check_tile_masks<<<(ctx->n_tiles + 127) / 128, 128, 0, ctx->stream>>>(ctx->n_tiles, ctx->tile_kstart, ctx->tile_kcount,
                                                                           ctx->tile_mask, ctx->k_pack, ctx->row_masks,
                                                                           ctx->check_flag);
-    ctx->launches += 4;
+    ctx->launches++;
     CK(cudaGetLastError());
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx->check_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

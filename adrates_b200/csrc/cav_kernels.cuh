@@ -969,15 +969,17 @@ __global__ void k_scen_bootstrap(int G, int R, int n_scen, const double* __restr
     }
 }
 
-// unit ids and weights per OUTPUT ROW (original trade order) from the group table, so that the
-// scenario expansion writes the P&L matrix with fully coalesced rows (one thread per group)
-__global__ void k_row_tables(int64_t n_groups, int K, const int64_t* __restrict__ group_offsets,
-                             const int* __restrict__ group_units, const double* __restrict__ comp_weight,
-                             const int64_t* __restrict__ out_index, int* row_units, double* row_weight)
+// unit ids and weights per OUTPUT ROW (original trade order) from the group table, so that the row-ordered
+// expansions write coalesced rows.  Warp per group, lanes stride its trades (a group has at most 256).
+__global__ void __launch_bounds__(256)
+k_row_tables(int64_t n_groups, int K, const int64_t* __restrict__ group_offsets,
+             const int* __restrict__ group_units, const double* __restrict__ comp_weight,
+             const int64_t* __restrict__ out_index, int* row_units, double* row_weight)
 {
-    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gi = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
     if (gi >= n_groups) return;
-    for (int64_t t = group_offsets[gi]; t < group_offsets[gi + 1]; ++t) {
+    const int64_t t0 = group_offsets[gi], t1 = group_offsets[gi + 1];
+    for (int64_t t = t0 + (threadIdx.x & 31); t < t1; t += 32) {
         const int64_t row = out_index ? out_index[t] : t;
         for (int k = 0; k < K; ++k) {
             row_units[row * K + k] = group_units[gi * K + k];
