@@ -319,10 +319,10 @@ def group_trades(n_units, unit_offsets, n_pairs, amt, weight, node, ids, ws, max
         new_run[1:] = np.any(ids_s[1:] != ids_s[:-1], axis=1)
         run_start = np.flatnonzero(new_run)
         run_end = np.append(run_start[1:], n_trades)
-        starts = []
-        for s, e in zip(run_start, run_end):
-            starts.append(np.arange(s, e, max_group))
-        starts = np.concatenate(starts)
+        per_run = -(-(run_end - run_start) // max_group)            # groups per run of equal unit ids
+        first = np.cumsum(per_run) - per_run
+        owner = np.repeat(np.arange(run_start.shape[0]), per_run)
+        starts = run_start[owner] + (np.arange(int(per_run.sum())) - first[owner]) * max_group
         group_offsets = np.append(starts, n_trades).astype(np.int64)
         group_units = ids_s[starts].astype(np.int32).reshape(-1)
     else:

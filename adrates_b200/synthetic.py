@@ -67,6 +67,26 @@ def make_book(curve: OISCurve, n_trades: int, seed: int = 20240430, max_offset_b
     return Book(curve, schedules, sched.astype(np.int32), coupon, notional, fixed_sign, np.zeros(n_trades))
 
 
+def make_array_book(curve: OISCurve, n_trades: int, seed: int = 20240430, max_offset_bd: int = 250,
+                    dc=DayCountTypes.ACT_365F):
+    """The same book as make_book (identical random draws) as an array-based batch.OISBook: no trade or schedule
+    objects at all - effective dates by closed-form weekday stepping, schedules rolled as arrays."""
+    from .batch import OISBook, add_weekdays
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tenor = rng.integers(1, 51, n_trades)
+    on_grid = rng.random(n_trades) < 0.5
+    offset = np.where(on_grid, 0, rng.integers(1, max_offset_bd + 1, n_trades))
+    par = np.interp(tenor.astype(np.float64), np.array(curve.swap_times), np.array(curve.swap_rates))
+    coupon = np.clip(par + rng.normal(0.0, 0.005, n_trades), 0.005, 0.09)
+    notional = np.exp(rng.uniform(np.log(1e5), np.log(1e8), n_trades))
+    fixed_sign = np.where(rng.random(n_trades) < 0.5, 1.0, -1.0)
+    eff = add_weekdays(np.full(n_trades, curve._value_dt._n), offset)
+    return OISBook.from_arrays(curve, eff, tenor_years=tenor, fixed_sign=fixed_sign, fixed_coupon=coupon,
+                               notional=notional, fixed_freq_type=FrequencyTypes.ANNUAL, fixed_dc_type=dc,
+                               float_freq_type=FrequencyTypes.ANNUAL, float_dc_type=dc,
+                               bd_type=BusDayAdjustTypes.MODIFIED_FOLLOWING)
+
+
 def flatten_book(book: Book, dedup: bool = True, max_group: int = 256, sort_units: bool = True,
                  tiles: bool = True, compact: bool = True) -> FlatPortfolio:
     flat = _flatten_book(book, dedup, max_group, sort_units)

@@ -1,0 +1,107 @@
+"""Array-based books on the GPU: OISBook.compute (batch.py -> C ABI) against the object-based Portfolio.compute,
+the numpy evaluation of the same flat arrays, and the C oracle on the bench book."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import cavour_oracle as orc  # noqa: E402
+from adrates_b200 import RequestTypes, batch as B  # noqa: E402
+from adrates_b200.curves import OISCurve  # noqa: E402
+from adrates_b200.dates import Date  # noqa: E402
+from adrates_b200.global_types import CurrencyTypes, CurveTypes, InterpTypes, SwapTypes  # noqa: E402
+from adrates_b200.position import Portfolio  # noqa: E402
+from adrates_b200.trades import OIS  # noqa: E402
+from tests.flat_eval import eval_flat  # noqa: E402
+from tests.test_batch_cpu import CONVS, _random_book  # noqa: E402
+from tests.util_trades import build_model  # noqa: E402
+
+ALL = [RequestTypes.VALUE, RequestTypes.DELTA, RequestTypes.GAMMA]
+TOL = 1e-10
+
+
+def _scaled(got, ref, scale):
+    return float(np.max(np.abs(got - ref) / np.maximum(np.abs(ref), scale)))
+
+
+@pytest.mark.parametrize("conv", list(CONVS))
+def test_book_compute_matches_flat_arrays_and_portfolio(ref_curves, conv):
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    curve = model.curves.GBP_OIS_SONIA
+    rng = np.random.default_rng(23)
+    n = 150
+    spec = _random_book(curve, n, rng, spread=(conv != "annual_act365"))
+    book = B.OISBook.from_arrays(curve, **spec, **CONVS[conv])
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+    c = CONVS[conv]
+    sp = np.broadcast_to(spec["float_spread"], (n,))
+    positions = []
+    for i in range(n):
+        eff = Date._of(int(spec["effective"][i]))
+        positions.append(OIS(eff, eff.add_tenor(f"{int(spec['tenor_months'][i])}M"),
+                             SwapTypes.RECEIVE if spec["fixed_sign"][i] > 0 else SwapTypes.PAY,
+                             float(spec["fixed_coupon"][i]), c["fixed_freq_type"], c["fixed_dc_type"],
+                             CurveTypes.GBP_OIS_SONIA, CurrencyTypes.GBP, float(spec["notional"][i]),
+                             c.get("payment_lag", 0), float(sp[i]), c["float_freq_type"], c["float_dc_type"],
+                             bd_type=c["bd_type"]).position(model))
+    ref_tot = Portfolio(positions).compute(ALL)
+    for dedup in ((True,) if conv == "lagged" else (True, False)):
+        res, rows = book.compute(ALL, dedup=dedup)
+        exp = eval_flat(book.flatten(dedup=dedup, tiles=False), d, J, C)
+        N = 1e8
+        assert _scaled(rows["pv"].cpu().numpy(), exp[0], N) < TOL
+        assert _scaled(rows["delta"].cpu().numpy(), exp[1], N * 1e-4 * 40) < TOL
+        assert _scaled(rows["gamma"].cpu().numpy(), exp[2], N * 1e-8 * 1600) < TOL
+        assert abs(res.value.amount - ref_tot.value.amount) <= TOL * n * N
+        assert _scaled(res.risk.risk_ladder, ref_tot.risk.risk_ladder, n * N * 1e-4) < TOL
+        assert _scaled(res.gamma.risk_ladder, ref_tot.gamma.risk_ladder, n * N * 1e-8 * 40) < TOL
+        assert res.value.currency == CurrencyTypes.GBP and res.risk.tenors == ref_tot.risk.tenors
+
+
+def test_array_bench_book_matches_c_oracle_and_object_book(ref_curves):
+    """200k trades of the BASELINE book built without any trade object: rows equal those of the object-built book
+    (same draws), a sample equals the C oracle."""
+    from adrates_b200 import _native
+    from adrates_b200.position import CurveSession
+    from adrates_b200.synthetic import flatten_book, make_array_book, make_book, reference_leg_tables
+    from oracle import c_oracle
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    curve = model.curves.GBP_OIS_SONIA
+    n = 200_000
+    arr = make_array_book(curve, n)
+    res, rows = arr.compute(ALL)
+    obj = make_book(curve, n)
+    sess = CurveSession.get(curve, 0)
+    sess.ctx.portfolio_upload(flatten_book(obj, dedup=True))
+    pv = torch.empty(n, dtype=torch.float64, device="cuda")
+    dl = torch.empty(n, 32, dtype=torch.float64, device="cuda")
+    gm = torch.empty(n, 32, 32, dtype=torch.float64, device="cuda")
+    agg = sess.ctx.portfolio_value_host(7, pv.data_ptr(), dl.data_ptr(), gm.data_ptr())
+    sess.ctx.sync()
+    # same trades, different unit order (tile composition differs): equal up to FP64 reassociation
+    assert float(((rows["pv"] - pv).abs() / pv.abs().clamp_min(1e5)).max()) < 1e-12
+    assert float(((rows["delta"] - dl).abs() / dl.abs().clamp_min(1e5 * 1e-4)).max()) < 1e-12
+    assert float(((rows["gamma"] - gm).abs() / gm.abs().clamp_min(1e5 * 1e-8)).max()) < 1e-12
+    assert abs(res.value.amount - agg[0]) <= 1e-12 * float(pv.abs().sum())
+    # private layout of the array book: same rows to 1e-10
+    res_p, rows_p = arr.compute(ALL, dedup=False)
+    N = 1e8
+    assert _scaled(rows_p["pv"].cpu().numpy(), pv.cpu().numpy(), N) < TOL
+    assert _scaled(rows_p["delta"][:20000].cpu().numpy(), dl[:20000].cpu().numpy(), N * 1e-4 * 50) < TOL
+    assert _scaled(rows_p["gamma"][:4000].cpu().numpy(), gm[:4000].cpu().numpy(), N * 1e-8 * 2500) < TOL
+    # C oracle on a sample of the same trades (inputs from the OBJECT schedules, i.e. an independent date path)
+    m = 300
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+    tr = dict(sched=obj.sched[:m], coupon=obj.coupon[:m], notional=obj.notional[:m], spread=obj.spread[:m],
+              fixed_sign=obj.fixed_sign[:m])
+    o_pv, o_dl, o_gm = c_oracle.ois_batch((plan["times"], d, J, C), 4 if cv["interp"] == "LINEAR_ZERO_RATES" else 1,
+                                          reference_leg_tables(obj), tr, dense=False)
+    assert _scaled(rows["pv"][:m].cpu().numpy(), o_pv, N) < TOL
+    assert _scaled(rows["delta"][:m].cpu().numpy(), o_dl, N * 1e-4 * 50) < TOL
+    assert _scaled(rows["gamma"][:m].cpu().numpy(), o_gm, N * 1e-8 * 2500) < TOL
