@@ -30,6 +30,7 @@ _SIGS = {
     "cav_launch_count": (C.c_int64, [_P]),
     "cav_set_stream": (C.c_int, [_P, _P]),
     "cav_profile": (C.c_int, [_P, C.c_int]),
+    "cav_set_async_upload": (C.c_int, [_P, C.c_int]),
     "cav_last_kernel_ms": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "cav_curve_build": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int]),
     "cav_curve_read": (C.c_int, [_P, _P, _P, _P]),
@@ -122,6 +123,11 @@ class Context:
     def set_stream(self, cuda_stream: int):
         self._ck(self._dll.cav_set_stream(self._h, int(cuda_stream)))
 
+    def set_async_upload(self, enable: bool):
+        """Pipeline the per-trade arrays of portfolio_upload behind the units kernel (see the header for the
+        lifetime contract of the host buffers)."""
+        self._ck(self._dll.cav_set_async_upload(self._h, 1 if enable else 0))
+
     def profile(self, enable: bool):
         self._ck(self._dll.cav_profile(self._h, 1 if enable else 0))
 
@@ -194,6 +200,7 @@ class Context:
             _ptr(flat.weight), _ptr(flat.node), flat.n_trades, flat.n_comp, _ptr(flat.comp_weight), flat.n_groups,
             _ptr(flat.group_offsets), _ptr(flat.group_units), _ptr(flat.out_index), _ptr(flat.unit_weight)))
         self._n_trades = flat.n_trades
+        self._flat_in_flight = flat          # async upload: the host arrays must outlive the copies
         tp = getattr(flat, "tile_plan", None)
         if tp is not None:
             self.portfolio_set_tiles(tp)

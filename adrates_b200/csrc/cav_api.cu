@@ -33,6 +33,8 @@ struct CapTable {
         for (size_t i = 0; i < v.size(); ++i) if (v[i].first == p) { v.erase(v.begin() + i); return; }
     }
 };
+#define CAV_UP_CHUNKS 4
+
 struct cav_ctx {
     CapTable caps;
     int device = 0;
@@ -45,6 +47,13 @@ struct cav_ctx {
     cudaStream_t aux[CAV_N_CLASSES] = {nullptr};      // size classes of the tiled units kernel run side by side
     cudaEvent_t ev_fork = nullptr, ev_join[CAV_N_CLASSES] = {nullptr};
     int evk_n = 0;
+    // pipelined upload (cav_set_async_upload): the per-trade arrays travel on `copy` in CAV_UP_CHUNKS group-aligned
+    // chunks while the unit arrays, the tile plan and the units kernel proceed on `stream`
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_up = nullptr, ev_chunk[CAV_UP_CHUNKS] = {nullptr};
+    bool async_upload = false;
+    int up_chunks = 0;                              // > 0: chunk events of the current portfolio are valid
+    int64_t up_group[CAV_UP_CHUNKS + 1] = {0};      // group range of every chunk
     std::string err;
     int64_t launches = 0;
 
@@ -193,11 +202,21 @@ void launch_units(cav_ctx* ctx, const UnitsArgs& a, bool delta, bool gamma, int 
 }
 
 template <int K>
-void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma) {
-    k_expand<K><<<(unsigned)ctx->n_groups, 256, 0, ctx->stream>>>(
-        ctx->group_offsets, ctx->group_units, ctx->comp_weight, ctx->out_index, ctx->u_pv, ctx->u_delta,
+void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma, int64_t g0, int64_t g1) {
+    if (g1 <= g0) return;
+    k_expand<K><<<(unsigned)(g1 - g0), 256, 0, ctx->stream>>>(
+        ctx->group_offsets + g0, ctx->group_units + g0 * K, ctx->comp_weight, ctx->out_index, ctx->u_pv, ctx->u_delta,
         ctx->u_gamma, pv, delta, gamma);
     ctx->launches++;
+}
+
+// every chunk of a pipelined upload has landed before anything later on the context's stream runs
+cudaError_t wait_trade_arrays(cav_ctx* ctx) {
+    for (int c = 0; c < ctx->up_chunks; ++c) {
+        cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 // Size classes of the tiled units kernel: NT = n-tiles (8 compact columns) per warp, MINB = CTAs per SM the register
@@ -314,6 +333,10 @@ int cav_create(cav_ctx** out, int device) {
     for (int i = 0; i < CAV_N_CLASSES; ++i)
         if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
+    for (int i = 0; i < CAV_UP_CHUNKS; ++i)
+        if (cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     *out = ctx;
     return CAV_OK;
 }
@@ -322,6 +345,7 @@ void cav_destroy(cav_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy);
     dev_free(ctx, &ctx->rates); dev_free(ctx, &ctx->node_time); dev_free(ctx, &ctx->node_acc);
     dev_free(ctx, &ctx->node_swap); dev_free(ctx, &ctx->node_prev);
     dev_free(ctx, &ctx->df); dev_free(ctx, &ctx->P); dev_free(ctx, &ctx->jac); dev_free(ctx, &ctx->dP);
@@ -342,6 +366,9 @@ void cav_destroy(cav_ctx* ctx) {
     for (int i = 0; i < 5; ++i) cudaEventDestroy(ctx->evk[i]);
     cudaEventDestroy(ctx->ev_fork);
     for (int i = 0; i < CAV_N_CLASSES; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    cudaStreamDestroy(ctx->copy);
+    cudaEventDestroy(ctx->ev_up);
+    for (int i = 0; i < CAV_UP_CHUNKS; ++i) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -354,7 +381,14 @@ int cav_sync(cav_ctx* ctx) {
     if (!ctx) return CAV_E_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamSynchronize(ctx->copy));
     CK(cudaGetLastError());
+    return CAV_OK;
+}
+
+int cav_set_async_upload(cav_ctx* ctx, int enable) {
+    if (!ctx) return CAV_E_INVALID;
+    ctx->async_upload = enable != 0;
     return CAV_OK;
 }
 
@@ -666,12 +700,41 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     CK(upload(ctx, &ctx->amt, amt, (size_t)n_terms));
     CK(upload(ctx, &ctx->weight, weight, (size_t)n_terms * n_pairs));
     CK(upload(ctx, &ctx->node, (const int*)node, (size_t)n_terms * n_pairs));
-    CK(upload(ctx, &ctx->comp_weight, comp_weight, (size_t)n_trades * n_comp));
+    // A previous portfolio's copies may still be in flight on the copy stream: the buffers below are reused
+    CK(cudaStreamSynchronize(ctx->copy));
+    ctx->up_chunks = 0;
+    const bool piped = ctx->async_upload && !direct && n_groups >= 4 * CAV_UP_CHUNKS;
+    if (piped) {
+        // per-trade arrays on the copy stream, in group-aligned chunks with one event each: the expansion kernel
+        // of a chunk starts when its weights have landed, while the unit arrays (below, on `stream`), the tile
+        // plan and the units kernel do not wait for them at all.  The copy stream first waits for whatever the
+        // context's stream still runs on the old buffers.
+        CK(dev_alloc(ctx, &ctx->comp_weight, (size_t)n_trades * n_comp));
+        if (out_index) CK(dev_alloc(ctx, &ctx->out_index, (size_t)n_trades));
+        else dev_free(ctx, &ctx->out_index);
+        CK(cudaEventRecord(ctx->ev_up, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_up, 0));
+        for (int c = 0; c <= CAV_UP_CHUNKS; ++c) ctx->up_group[c] = n_groups * c / CAV_UP_CHUNKS;
+        for (int c = 0; c < CAV_UP_CHUNKS; ++c) {
+            const int64_t t0 = group_offsets[ctx->up_group[c]], t1 = group_offsets[ctx->up_group[c + 1]];
+            if (t1 > t0 && t0 >= 0 && t1 <= n_trades) {
+                CK(cudaMemcpyAsync(ctx->comp_weight + t0 * n_comp, comp_weight + t0 * n_comp,
+                                   sizeof(double) * (size_t)(t1 - t0) * n_comp, cudaMemcpyHostToDevice, ctx->copy));
+                if (out_index)
+                    CK(cudaMemcpyAsync(ctx->out_index + t0, out_index + t0, sizeof(int64_t) * (size_t)(t1 - t0),
+                                       cudaMemcpyHostToDevice, ctx->copy));
+            }
+            CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy));
+        }
+        ctx->up_chunks = CAV_UP_CHUNKS;
+    } else {
+        CK(upload(ctx, &ctx->comp_weight, comp_weight, (size_t)n_trades * n_comp));
+        if (out_index) CK(upload(ctx, &ctx->out_index, out_index, (size_t)n_trades));
+        else dev_free(ctx, &ctx->out_index);
+    }
     CK(upload(ctx, &ctx->group_offsets, group_offsets, (size_t)n_groups + 1));
     CK(upload(ctx, &ctx->group_units, (const int*)group_units, (size_t)n_groups * n_comp));
     if (!direct) CK(upload(ctx, &ctx->unit_weight, unit_weight, (size_t)n_units));
-    if (out_index) CK(upload(ctx, &ctx->out_index, out_index, (size_t)n_trades));
-    else dev_free(ctx, &ctx->out_index);
     // Host-side validation of every index the kernels will dereference runs while the copies above are in
     // flight (branch-free scans); a failure invalidates the uploaded portfolio.
     const char* verr = nullptr;
@@ -694,6 +757,8 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     }
     CK(cudaStreamSynchronize(ctx->stream));   // host buffers may be reused by the caller
     if (verr) {
+        cudaStreamSynchronize(ctx->copy);
+        ctx->up_chunks = 0;
         ctx->portfolio_valid = false;
         return fail(ctx, CAV_E_INVALID, verr);
     }
@@ -815,6 +880,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
 
 static int ensure_row_tables(cav_ctx* ctx) {
     if (ctx->row_tables_valid) return CAV_OK;
+    CK(wait_trade_arrays(ctx));
     CK(dev_alloc(ctx, &ctx->row_units, (size_t)ctx->n_trades * ctx->n_comp));
     CK(dev_alloc(ctx, &ctx->row_weight, (size_t)ctx->n_trades * ctx->n_comp));
     if (ctx->n_groups > 0) {
@@ -918,11 +984,17 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (!ctx->direct && (pv || delta || gamma) && ctx->n_groups > 0) {
         // gamma rows: group-ordered streaming kernel; PV / delta rows: row-ordered gather (coalesced small rows)
         if (gamma) {
-            switch (ctx->n_comp) {
-                case 1: launch_expand<1>(ctx, nullptr, nullptr, gamma); break;
-                case 2: launch_expand<2>(ctx, nullptr, nullptr, gamma); break;
-                case 3: launch_expand<3>(ctx, nullptr, nullptr, gamma); break;
-                default: launch_expand<4>(ctx, nullptr, nullptr, gamma); break;
+            const int chunks = ctx->up_chunks > 0 ? ctx->up_chunks : 1;
+            for (int c = 0; c < chunks; ++c) {
+                const int64_t g0 = ctx->up_chunks > 0 ? ctx->up_group[c] : 0;
+                const int64_t g1 = ctx->up_chunks > 0 ? ctx->up_group[c + 1] : ctx->n_groups;
+                if (ctx->up_chunks > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+                switch (ctx->n_comp) {
+                    case 1: launch_expand<1>(ctx, nullptr, nullptr, gamma, g0, g1); break;
+                    case 2: launch_expand<2>(ctx, nullptr, nullptr, gamma, g0, g1); break;
+                    case 3: launch_expand<3>(ctx, nullptr, nullptr, gamma, g0, g1); break;
+                    default: launch_expand<4>(ctx, nullptr, nullptr, gamma, g0, g1); break;
+                }
             }
             CK(cudaGetLastError());
         }
@@ -996,11 +1068,12 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
     ctx->launches += 2;
     CK(cudaGetLastError());
     if (!ctx->direct && ctx->n_groups > 0) {
+        CK(wait_trade_arrays(ctx));
         switch (ctx->n_comp) {
-            case 1: launch_expand<1>(ctx, pv_dev, delta_dev, nullptr); break;
-            case 2: launch_expand<2>(ctx, pv_dev, delta_dev, nullptr); break;
-            case 3: launch_expand<3>(ctx, pv_dev, delta_dev, nullptr); break;
-            default: launch_expand<4>(ctx, pv_dev, delta_dev, nullptr); break;
+            case 1: launch_expand<1>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
+            case 2: launch_expand<2>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
+            case 3: launch_expand<3>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
+            default: launch_expand<4>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
         }
         CK(cudaGetLastError());
     }

@@ -280,6 +280,9 @@ def main():
 
     # ---- e2e: host buffers -> H2D -> valuation -> D2H of portfolio totals, every step ----
     agg_host = np.empty(_native.NOUT)
+    agg_resident = agg.cpu().numpy().copy() if world == 1 else None
+    gm_check = float(gm[:: max(1, n // 4096)].sum().item())
+    ctx.set_async_upload(True)       # per-trade arrays stream in behind the units kernel (pinned buffers stay alive)
     for _ in range(2):
         ctx.portfolio_upload(flat_pinned)
         ctx.portfolio_value_host(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg_host)
@@ -298,6 +301,12 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * args.steps / float(e2e_s.item())
+    ctx.set_async_upload(False)
+    # the pipelined path must reproduce the resident-input results exactly (same kernels, same order)
+    if agg_resident is not None and not np.array_equal(agg_host, agg_resident):
+        raise SystemExit("e2e (pipelined upload) totals differ from the device-resident totals")
+    if float(gm[:: max(1, n // 4096)].sum().item()) != gm_check:
+        raise SystemExit("e2e (pipelined upload) gamma rows differ from the device-resident run")
 
     # ---- secondary measurements (same book, device-resident inputs; reported under "extras") ----
     extras = {}
