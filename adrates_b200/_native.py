@@ -213,6 +213,7 @@ class Context:
                 i32(tp.k_coef), i32(tp.pairs)]
         opt = lambda name: None if getattr(tp, name, None) is None else i32(getattr(tp, name))  # noqa: E731
         pos2, coef2, perm = opt("k_pos2"), opt("k_coef2"), opt("perm")
+        self._tiles_in_flight = (arrs, pos2, coef2, perm, mask)     # async upload: outlive the copies
         self._ck(self._dll.cav_portfolio_set_tiles(self._h, tp.n_tiles, tp.tile_size, _ptr(arrs[0]), _ptr(arrs[1]), _ptr(arrs[2]),
                                                    arrs[3].shape[0], _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]),
                                                    _ptr(pos2), _ptr(coef2), arrs[6].shape[0] // 2, _ptr(arrs[6]),

@@ -8,7 +8,7 @@ SRC = os.path.join(HERE, "csrc", "cav_api.cu")
 DEPS = [SRC, os.path.join(HERE, "csrc", "cav_kernels.cuh"), os.path.join(HERE, "..", "include", "adrates_b200.h")]
 LIB = os.path.join(HERE, "libadrates_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC,-fopenmp"]
 
 
 def needs_build() -> bool:

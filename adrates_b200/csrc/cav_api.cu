@@ -6,6 +6,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <algorithm>
@@ -50,10 +51,17 @@ struct cav_ctx {
     // pipelined upload (cav_set_async_upload): the per-trade arrays travel on `copy` in CAV_UP_CHUNKS group-aligned
     // chunks while the unit arrays, the tile plan and the units kernel proceed on `stream`
     cudaStream_t copy = nullptr;
-    cudaEvent_t ev_up = nullptr, ev_chunk[CAV_UP_CHUNKS] = {nullptr};
+    cudaEvent_t ev_up = nullptr, ev_tiles = nullptr, ev_chunk[CAV_UP_CHUNKS] = {nullptr};
     bool async_upload = false;
     int up_chunks = 0;                              // > 0: chunk events of the current portfolio are valid
     int64_t up_group[CAV_UP_CHUNKS + 1] = {0};      // group range of every chunk
+    int64_t up_trade[CAV_UP_CHUNKS + 1] = {0};      // ... and its trade range
+    int up_n = CAV_UP_CHUNKS;                       // chunks of the pending / current upload
+    bool chunks_pending = false;                    // chunk copies not issued yet (host pointers below still needed)
+    const double* pend_weight = nullptr;
+    const int64_t* pend_index = nullptr;
+    int pend_comp = 0;
+    int64_t pend_trades = 0;
     std::string err;
     int64_t launches = 0;
 
@@ -107,6 +115,9 @@ struct cav_ctx {
     double* unit_weight = nullptr;
     std::vector<int64_t> h_unit_offsets;      // host copy (tile-plan validation)
     std::vector<int> h_pairs;                 // pair rows and permutation of the tables currently on the device
+    std::vector<int> h_npos;                  // staging of the tile plan (see cav_portfolio_set_tiles)
+    std::vector<unsigned> h_masks;
+    std::vector<int2> h_pack;
 
     // scratch
     double *u_pv = nullptr, *u_delta = nullptr, *u_gamma = nullptr;
@@ -148,6 +159,18 @@ cudaError_t upload(cav_ctx* ctx, T** p, const T* host, size_t n) {
     cudaError_t e = dev_alloc(ctx, p, n);
     if (e != cudaSuccess || n == 0) return e;
     return cudaMemcpyAsync(*p, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+}
+
+// Threads for the host-side scans of an upload: explicit (torchrun pins OMP_NUM_THREADS=1, and one rank per GPU
+// shares the host), a few are enough to hide the scans behind the copies; CAV_HOST_THREADS overrides.
+int host_threads(int64_t work) {
+    static int cap = [] {
+        const char* e = std::getenv("CAV_HOST_THREADS");
+        int n = e ? std::atoi(e) : 0;
+        if (n <= 0) { n = (int)std::thread::hardware_concurrency() / 2; n = n > 8 ? 8 : n; }
+        return n < 1 ? 1 : n;
+    }();
+    return work < 200000 ? 1 : cap;
 }
 
 template <typename T>
@@ -210,8 +233,31 @@ void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma, int64
     ctx->launches++;
 }
 
+// enqueue the per-trade chunk copies of a pipelined upload (after whatever the context's stream still runs on the
+// old buffers, and behind every copy issued so far)
+cudaError_t issue_trade_chunks(cav_ctx* ctx) {
+    if (!ctx->chunks_pending) return cudaSuccess;
+    ctx->chunks_pending = false;
+    cudaError_t e = cudaEventRecord(ctx->ev_up, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->copy, ctx->ev_up, 0);
+    for (int c = 0; c < ctx->up_n && e == cudaSuccess; ++c) {
+        const int64_t t0 = ctx->up_trade[c], t1 = ctx->up_trade[c + 1];
+        if (t1 > t0 && t0 >= 0 && t1 <= ctx->pend_trades) {
+            e = cudaMemcpyAsync(ctx->comp_weight + t0 * ctx->pend_comp, ctx->pend_weight + t0 * ctx->pend_comp,
+                                sizeof(double) * (size_t)(t1 - t0) * ctx->pend_comp, cudaMemcpyHostToDevice, ctx->copy);
+            if (e == cudaSuccess && ctx->pend_index)
+                e = cudaMemcpyAsync(ctx->out_index + t0, ctx->pend_index + t0, sizeof(int64_t) * (size_t)(t1 - t0),
+                                    cudaMemcpyHostToDevice, ctx->copy);
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_chunk[c], ctx->copy);
+    }
+    if (e == cudaSuccess) ctx->up_chunks = ctx->up_n;
+    return e;
+}
+
 // every chunk of a pipelined upload has landed before anything later on the context's stream runs
 cudaError_t wait_trade_arrays(cav_ctx* ctx) {
+    { cudaError_t e = issue_trade_chunks(ctx); if (e != cudaSuccess) return e; }
     for (int c = 0; c < ctx->up_chunks; ++c) {
         cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0);
         if (e != cudaSuccess) return e;
@@ -334,7 +380,8 @@ int cav_create(cav_ctx** out, int device) {
         if (cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
+        cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_tiles, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     for (int i = 0; i < CAV_UP_CHUNKS; ++i)
         if (cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     *out = ctx;
@@ -368,6 +415,7 @@ void cav_destroy(cav_ctx* ctx) {
     for (int i = 0; i < CAV_N_CLASSES; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
     cudaStreamDestroy(ctx->copy);
     cudaEventDestroy(ctx->ev_up);
+    cudaEventDestroy(ctx->ev_tiles);
     for (int i = 0; i < CAV_UP_CHUNKS; ++i) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -380,6 +428,7 @@ int64_t cav_launch_count(const cav_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int cav_sync(cav_ctx* ctx) {
     if (!ctx) return CAV_E_INVALID;
     CK(cudaSetDevice(ctx->device));
+    CK(issue_trade_chunks(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy));
     CK(cudaGetLastError());
@@ -696,69 +745,92 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     }
     CK(cudaSetDevice(ctx->device));
     ctx->h_unit_offsets.assign(unit_offsets, unit_offsets + n_units + 1);
+    // A previous portfolio's copies may still be in flight on the copy stream: the buffers below are reused
+    CK(cudaStreamSynchronize(ctx->copy));
+    ctx->up_chunks = 0;
+    ctx->chunks_pending = false;
+    const bool piped = ctx->async_upload && !direct && n_groups >= 4 * CAV_UP_CHUNKS;
     CK(upload(ctx, &ctx->unit_offsets, unit_offsets, (size_t)n_units + 1));
     CK(upload(ctx, &ctx->amt, amt, (size_t)n_terms));
     CK(upload(ctx, &ctx->weight, weight, (size_t)n_terms * n_pairs));
     CK(upload(ctx, &ctx->node, (const int*)node, (size_t)n_terms * n_pairs));
-    // A previous portfolio's copies may still be in flight on the copy stream: the buffers below are reused
-    CK(cudaStreamSynchronize(ctx->copy));
-    ctx->up_chunks = 0;
-    const bool piped = ctx->async_upload && !direct && n_groups >= 4 * CAV_UP_CHUNKS;
+    CK(upload(ctx, &ctx->group_offsets, group_offsets, (size_t)n_groups + 1));
+    CK(upload(ctx, &ctx->group_units, (const int*)group_units, (size_t)n_groups * n_comp));
+    if (!direct) CK(upload(ctx, &ctx->unit_weight, unit_weight, (size_t)n_units));
+    // (the host->device copy engine serves copies in issue order whatever their stream: the unit arrays above go
+    // first so that the units kernel is not held up by the bulk of the per-trade data)
     if (piped) {
-        // per-trade arrays on the copy stream, in group-aligned chunks with one event each: the expansion kernel
-        // of a chunk starts when its weights have landed, while the unit arrays (below, on `stream`), the tile
-        // plan and the units kernel do not wait for them at all.  The copy stream first waits for whatever the
-        // context's stream still runs on the old buffers.
+        // per-trade arrays go on the copy stream in group-aligned chunks with one event each, so the expansion
+        // kernel of a chunk starts when its weights have landed.  They are ISSUED later (issue_trade_chunks: at the
+        // end of cav_portfolio_set_tiles or at the first use) so that the tile plan, which the units kernel needs,
+        // is ahead of them in the copy engine's queue.
         CK(dev_alloc(ctx, &ctx->comp_weight, (size_t)n_trades * n_comp));
         if (out_index) CK(dev_alloc(ctx, &ctx->out_index, (size_t)n_trades));
         else dev_free(ctx, &ctx->out_index);
-        CK(cudaEventRecord(ctx->ev_up, ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_up, 0));
-        for (int c = 0; c <= CAV_UP_CHUNKS; ++c) ctx->up_group[c] = n_groups * c / CAV_UP_CHUNKS;
-        for (int c = 0; c < CAV_UP_CHUNKS; ++c) {
-            const int64_t t0 = group_offsets[ctx->up_group[c]], t1 = group_offsets[ctx->up_group[c + 1]];
-            if (t1 > t0 && t0 >= 0 && t1 <= n_trades) {
-                CK(cudaMemcpyAsync(ctx->comp_weight + t0 * n_comp, comp_weight + t0 * n_comp,
-                                   sizeof(double) * (size_t)(t1 - t0) * n_comp, cudaMemcpyHostToDevice, ctx->copy));
-                if (out_index)
-                    CK(cudaMemcpyAsync(ctx->out_index + t0, out_index + t0, sizeof(int64_t) * (size_t)(t1 - t0),
-                                       cudaMemcpyHostToDevice, ctx->copy));
-            }
-            CK(cudaEventRecord(ctx->ev_chunk[c], ctx->copy));
+        // chunk sizes grow quadratically: a small first chunk lets the expansion start early, large later chunks
+        // keep the number of partial waves (kernel tails) down
+        static const int n_chunks = [] {
+            const char* e = std::getenv("CAV_UP_CHUNKS");
+            const int n = e ? std::atoi(e) : 2;
+            return n < 1 ? 1 : (n > CAV_UP_CHUNKS ? CAV_UP_CHUNKS : n);
+        }();
+        ctx->up_n = n_chunks;
+        for (int c = 0; c <= n_chunks; ++c) {
+            ctx->up_group[c] = n_groups * c * c / (n_chunks * n_chunks);
+            ctx->up_trade[c] = group_offsets[ctx->up_group[c]];
         }
-        ctx->up_chunks = CAV_UP_CHUNKS;
+        ctx->pend_weight = comp_weight;
+        ctx->pend_index = out_index;
+        ctx->pend_comp = n_comp;
+        ctx->pend_trades = n_trades;
+        ctx->chunks_pending = true;
     } else {
         CK(upload(ctx, &ctx->comp_weight, comp_weight, (size_t)n_trades * n_comp));
         if (out_index) CK(upload(ctx, &ctx->out_index, out_index, (size_t)n_trades));
         else dev_free(ctx, &ctx->out_index);
     }
-    CK(upload(ctx, &ctx->group_offsets, group_offsets, (size_t)n_groups + 1));
-    CK(upload(ctx, &ctx->group_units, (const int*)group_units, (size_t)n_groups * n_comp));
-    if (!direct) CK(upload(ctx, &ctx->unit_weight, unit_weight, (size_t)n_units));
+
     // Host-side validation of every index the kernels will dereference runs while the copies above are in
-    // flight (branch-free scans); a failure invalidates the uploaded portfolio.
+    // flight; a failure invalidates the uploaded portfolio.  The scans are OR-reductions (x | (limit - x) has its
+    // sign bit set iff x < 0 or x > limit): branch-free, vectorisable and split over a few host threads - at 1M
+    // trades a single-threaded scan (11 MB) costs as much as the copies themselves.
     const char* verr = nullptr;
     {
-        int lo = 0, hi = 0;
-        for (int64_t i = 0; i < n_terms * n_pairs; ++i) { lo = node[i] < lo ? node[i] : lo; hi = node[i] > hi ? node[i] : hi; }
-        if (lo < 0 || hi >= ctx->G) verr = "cav_portfolio_upload: node index out of range";
-        lo = hi = 0;
-        for (int64_t i = 0; i < n_groups * n_comp; ++i) { lo = group_units[i] < lo ? group_units[i] : lo; hi = group_units[i] > hi ? group_units[i] : hi; }
-        if (lo < 0 || (n_groups && hi >= n_units)) verr = "cav_portfolio_upload: unit id out of range";
-        int64_t bad = 0;
-        for (int64_t u = 0; u < n_units; ++u) bad |= (unit_offsets[u + 1] - unit_offsets[u]) >> 63;
-        for (int64_t gi = 0; gi < n_groups; ++gi) {
-            const int64_t c = group_offsets[gi + 1] - group_offsets[gi];
-            bad |= (c >> 63) | ((256 - c) >> 63);      // 0 <= group size <= 256
+        const int nth = host_threads(n_trades + n_terms);
+        const int64_t n_node = n_terms * n_pairs, n_gu = n_groups * n_comp;
+        const int g_hi = ctx->G - 1, u_hi = (int)(n_units - 1);
+        const int64_t t_hi = n_trades - 1;
+        int a_node = 0, a_gu = 0;
+        int64_t a_off = 0, a_grp = 0, a_out = 0;
+#pragma omp parallel num_threads(nth) reduction(| : a_node, a_gu, a_off, a_grp, a_out)
+        {
+#pragma omp for nowait schedule(static)
+            for (int64_t i = 0; i < n_node; ++i) a_node |= node[i] | (g_hi - node[i]);
+#pragma omp for nowait schedule(static)
+            for (int64_t i = 0; i < n_gu; ++i) a_gu |= group_units[i] | (u_hi - group_units[i]);
+#pragma omp for nowait schedule(static)
+            for (int64_t u = 0; u < n_units; ++u) a_off |= unit_offsets[u + 1] - unit_offsets[u];
+#pragma omp for nowait schedule(static)
+            for (int64_t gi = 0; gi < n_groups; ++gi) {
+                const int64_t c = group_offsets[gi + 1] - group_offsets[gi];
+                a_grp |= c | (256 - c);                      // 0 <= group size <= 256
+            }
+            if (out_index) {
+#pragma omp for nowait schedule(static)
+                for (int64_t t = 0; t < n_trades; ++t) a_out |= out_index[t] | (t_hi - out_index[t]);
+            }
         }
-        if (out_index)
-            for (int64_t t = 0; t < n_trades; ++t) bad |= (out_index[t] >> 63) | ((n_trades - 1 - out_index[t]) >> 63);
-        if (bad) verr = "cav_portfolio_upload: offsets not monotone, group larger than 256 trades or out_index out of range";
+        if (a_node < 0) verr = "cav_portfolio_upload: node index out of range";
+        else if (a_gu < 0) verr = "cav_portfolio_upload: unit id out of range";
+        else if ((a_off | a_grp | a_out) < 0)
+            verr = "cav_portfolio_upload: offsets not monotone, group larger than 256 trades or out_index out of range";
     }
-    CK(cudaStreamSynchronize(ctx->stream));   // host buffers may be reused by the caller
+    // host buffers may be reused by the caller (and W is a local) unless the pipelined contract holds
+    if (!ctx->async_upload || verr || !W.empty()) CK(cudaStreamSynchronize(ctx->stream));
     if (verr) {
         cudaStreamSynchronize(ctx->copy);
         ctx->up_chunks = 0;
+        ctx->chunks_pending = false;
         ctx->portfolio_valid = false;
         return fail(ctx, CAV_E_INVALID, verr);
     }
@@ -802,8 +874,13 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     if (covered != ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: every unit must belong to exactly one tile");
     const std::vector<int64_t>& h_off = ctx->h_unit_offsets;
     CK(cudaSetDevice(ctx->device));
-    std::vector<int> npos((size_t)n_tiles, 0);
-    std::vector<unsigned> masks((size_t)n_tiles, 0xFFFFFFFFu);
+    // staging vectors live in the context: with the pipelined upload their copies may still be in flight when this
+    // call returns, so wait for the previous plan's copies (ev_tiles) before overwriting them
+    CK(cudaEventSynchronize(ctx->ev_tiles));
+    std::vector<int>& npos = ctx->h_npos;
+    std::vector<unsigned>& masks = ctx->h_masks;
+    npos.assign((size_t)n_tiles, 0);
+    masks.assign((size_t)n_tiles, 0xFFFFFFFFu);
     if (tile_mask) std::memcpy(masks.data(), tile_mask, sizeof(unsigned) * n_tiles);
     int cls_prev = 0;
     int class_begin[CAV_N_CLASSES + 1];
@@ -845,7 +922,8 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
         for (int c = cls_prev + 1; c <= cls; ++c) class_begin[c] = t;
         cls_prev = cls;
     }
-    std::vector<int2> pack((size_t)n_krows);
+    std::vector<int2>& pack = ctx->h_pack;
+    pack.resize((size_t)n_krows);
     for (int64_t k = 0; k < n_krows; ++k) {
         if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_pos[k] > 255 || k_coef[k] < 0 || k_coef[k] > 5 ||
             (k_coef2 && k_coef2[k] > 5))
@@ -862,7 +940,9 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     CK(upload(ctx, &ctx->k_pack, pack.data(), (size_t)n_krows));
     CK(upload(ctx, &ctx->pairs, (const int*)pairs, (size_t)2 * n_pair_rows));
     CK(upload(ctx, &ctx->tile_mask, masks.data(), (size_t)n_tiles));
-    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaEventRecord(ctx->ev_tiles, ctx->stream));
+    CK(issue_trade_chunks(ctx));
+    if (!ctx->async_upload) CK(cudaStreamSynchronize(ctx->stream));
     std::memcpy(ctx->class_begin, class_begin, sizeof(class_begin));
     // the symmetric tables depend on the curve, the pair rows and the permutation only: keep them (and the mask
     // check's row masks) when a new plan asks for the same ones
@@ -941,6 +1021,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         if (agg_host) std::memset(agg_host, 0, sizeof(double) * CAV_NOUT);
         return CAV_OK;
     }
+    CK(issue_trade_chunks(ctx));
     const bool need_agg = agg_dev || agg_host;
     static int gemm_mode = [] { const char* e = std::getenv("CAV_UNITS_GEMM"); return e ? std::atoi(e) : 1; }();
     const bool use_gemm = want_g && ctx->tiles_valid && gemm_mode != 0 && ctx->n_tiles > 0;

@@ -63,10 +63,11 @@ int         cav_set_stream(cav_ctx* ctx, void* cuda_stream);
  * rebuilds every Position's inputs on the host before it values it (position.py:55, engine.py:2519-2539); here
  * the per-trade arrays (comp_weight, out_index) travel on a side copy stream in 4 group-aligned chunks while the
  * unit arrays, the tile plan and the units kernel proceed, and the expansion kernel of a chunk starts as soon as
- * its weights have landed.  Contract when enabled: the comp_weight / out_index HOST buffers handed to
- * cav_portfolio_upload must stay valid and unmodified until the next cav_portfolio_value*, cav_scenarios or
- * cav_sync call on this context has returned (every other buffer may be reused as soon as upload returns).
- * Off by default.  Results are bit-identical either way. */
+ * its weights have landed; neither cav_portfolio_upload nor cav_portfolio_set_tiles waits for its copies (the
+ * host-side validation still runs, concurrently with them).  Contract when enabled: every HOST buffer handed to
+ * cav_portfolio_upload / cav_portfolio_set_tiles must stay valid and unmodified until the next
+ * cav_portfolio_value_host or cav_sync call on this context has returned.  Off by default.  Results are
+ * bit-identical either way. */
 int         cav_set_async_upload(cav_ctx* ctx, int enable);
 /* per-kernel CUDA-event timing of cav_portfolio_value: ms[0] units kernel, ms[1] per-trade
  * expansion kernel, ms[2] portfolio-total reduction (needs agg output) */

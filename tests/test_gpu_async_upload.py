@@ -61,7 +61,10 @@ def test_async_upload_is_bit_identical_and_race_free(ref_curves):
             assert np.array_equal(got[3], r[3])
     # PV + delta only (row-table path waits for every chunk), then totals only (no per-trade rows)
     pv, dl, _, agg = _value(ctx, flats[0], n, _native.REQ_VALUE | _native.REQ_DELTA)
-    assert torch.equal(pv, ref[0][0]) and torch.equal(dl, ref[0][1])
+    ctx.set_async_upload(False)
+    pv_s, dl_s, _, agg_s = _value(ctx, flats[0], n, _native.REQ_VALUE | _native.REQ_DELTA)
+    ctx.set_async_upload(True)
+    assert torch.equal(pv, pv_s) and torch.equal(dl, dl_s) and np.array_equal(agg, agg_s)
     ctx.portfolio_upload(flats[1])
     agg = ctx.portfolio_value_host(MASK)
     assert np.array_equal(agg, ref[1][3])
