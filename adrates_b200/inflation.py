@@ -298,6 +298,87 @@ class ZeroCouponInflationSwap:
         return ((1.0 + ret) ** (1.0 / yf)) - 1.0
 
 
+class SwapYoYInflationLeg:
+    """Periodic payments notional x alpha_i x [I(end_i)/I(end_i - 12M) - 1 + spread]
+    (cavour/trades/rates/swap_yoy_inflation_leg.py:95-262).  Schedule only; valuation and Greeks go through
+    Position.compute -> yoy_engine (Engine._compute_yoy_iis)."""
+
+    def __init__(self, effective_dt: Date, end_dt, leg_type: SwapTypes, inflation_index: InflationIndex,
+                 freq_type, dc_type: DayCountTypes, notional: float = ONE_MILLION, spread: float = 0.0,
+                 payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING, dg_type=None, end_of_month: bool = False):
+        from .dates import DateGenRuleTypes, Schedule
+        self.instrument_type = InstrumentTypes.SWAP_YOY_INFLATION_LEG
+        self._termination_dt = end_dt if isinstance(end_dt, Date) else effective_dt.add_tenor(end_dt)
+        cal = Calendar(cal_type)
+        self._maturity_dt = cal.adjust(self._termination_dt, bd_type)
+        if effective_dt > self._maturity_dt:
+            raise LibError("Start date after maturity date")
+        self._effective_dt, self._end_dt, self._leg_type = effective_dt, end_dt, leg_type
+        self._inflation_index, self._freq_type, self._dc_type = inflation_index, freq_type, dc_type
+        self._notional, self._spread, self._payment_lag = notional, spread, payment_lag
+        self._cal_type, self._bd_type = cal_type, bd_type
+        self._dg_type = dg_type or DateGenRuleTypes.BACKWARD
+        self._end_of_month = end_of_month
+        dts = Schedule(effective_dt, self._termination_dt, freq_type, cal_type, bd_type, self._dg_type,
+                       end_of_month=end_of_month)._adjusted_dts
+        if len(dts) < 2:
+            raise LibError("Schedule has none or only one date")
+        dc = DayCount(dc_type)
+        self._start_accrued_dts, self._end_accrued_dts, self._payment_dts = [], [], []
+        self._year_fracs, self._accrued_days, self._yoy_start_dts, self._yoy_end_dts = [], [], [], []
+        for start, end in zip(dts[:-1], dts[1:]):
+            alpha, days, _ = dc.year_frac(start, end)
+            self._start_accrued_dts.append(start)
+            self._end_accrued_dts.append(end)
+            self._payment_dts.append(end if payment_lag == 0 else cal.add_business_days(end, payment_lag))
+            self._year_fracs.append(alpha)
+            self._accrued_days.append(days)
+            self._yoy_end_dts.append(end)                     # CPI reference dates: period end and one year before
+            self._yoy_start_dts.append(end.add_months(-12))
+
+
+class YoYInflationSwap:
+    """Fixed coupons against year-on-year inflation coupons on one schedule
+    (cavour/trades/rates/yoy_inflation_swap.py:85-220)."""
+
+    def __init__(self, effective_dt: Date, term_dt_or_tenor, fixed_leg_type: SwapTypes, fixed_rate: float,
+                 inflation_index: InflationIndex, freq_type, notional: float = ONE_MILLION,
+                 inflation_spread: float = 0.0, dc_type: DayCountTypes = DayCountTypes.ACT_365F, payment_lag: int = 0,
+                 cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING, dg_type=None, end_of_month: bool = False):
+        from .dates import DateGenRuleTypes
+        from .global_types import CurveTypes
+        from .trades import SwapFixedLeg
+        dg_type = dg_type or DateGenRuleTypes.BACKWARD
+        self.instrument_type = InstrumentTypes.YOY_INFLATION_SWAP
+        self.derivative_type = InstrumentTypes.YOY_INFLATION_SWAP
+        self._termination_dt = term_dt_or_tenor if isinstance(term_dt_or_tenor, Date) else effective_dt.add_tenor(term_dt_or_tenor)
+        self._maturity_dt = Calendar(cal_type).adjust(self._termination_dt, bd_type)
+        if effective_dt > self._maturity_dt:
+            raise LibError("Start date after maturity date")
+        self._effective_dt, self._fixed_leg_type, self._fixed_rate = effective_dt, fixed_leg_type, fixed_rate
+        self._inflation_index, self._freq_type, self._notional = inflation_index, freq_type, notional
+        self._inflation_spread, self._dc_type, self._payment_lag = inflation_spread, dc_type, payment_lag
+        self._cal_type, self._bd_type, self._dg_type, self._end_of_month = cal_type, bd_type, dg_type, end_of_month
+        infl_type = SwapTypes.RECEIVE if fixed_leg_type == SwapTypes.PAY else SwapTypes.PAY
+        currency = inflation_index._currency
+        floating_index = {CurrencyTypes.GBP: CurveTypes.GBP_OIS_SONIA, CurrencyTypes.USD: CurveTypes.USD_OIS_SOFR,
+                          CurrencyTypes.EUR: CurveTypes.EUR_OIS_ESTR}.get(currency, CurveTypes.USD_OIS_SOFR)
+        self._fixed_leg = SwapFixedLeg(effective_dt, self._termination_dt, fixed_leg_type, fixed_rate, freq_type, dc_type,
+                                       floating_index, currency, notional, 0.0, payment_lag, cal_type, bd_type, dg_type,
+                                       end_of_month)
+        self._inflation_leg = SwapYoYInflationLeg(effective_dt, self._termination_dt, infl_type, inflation_index,
+                                                  freq_type, dc_type, notional, inflation_spread, payment_lag, cal_type,
+                                                  bd_type, dg_type, end_of_month)
+        self._fixed_pv = self._inflation_pv = None
+
+    def position(self, model):
+        """Convenience the reference lacks (its YoYInflationSwap has no .position); Position(swap, model) works too."""
+        from .position import Position
+        return Position(self, model)
+
+
 def cashflow_pv(discount_curve: DiscountCurve, value_dt: Date, trades, device: int = 0) -> np.ndarray:
     """PV per trade of explicit cashflows [(date, signed amount), ...] on the path-A discount curve:
     sum amt * DF(date)/DF(value_dt), cashflows on or before the value date are worth 0

@@ -84,6 +84,9 @@ class Engine:
         if dtype == InstrumentTypes.XCCY_SWAP:
             from .xccy_engine import compute_xccy
             return compute_xccy([derivative], self.model, request_list, self.device)
+        if dtype == InstrumentTypes.YOY_INFLATION_SWAP:      # Engine._compute_yoy_iis (engine.py:120-122, 986-1408)
+            from .yoy_engine import compute_yoy
+            return compute_yoy([derivative], self.model, request_list, self.device)
         if dtype == InstrumentTypes.BOND:      # Engine._compute_bond (engine.py:505-640): OIS curve of the currency
             return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
         if dtype == InstrumentTypes.FRN:       # Engine._compute_frn (engine.py:700-925)
@@ -166,6 +169,13 @@ class Portfolio:
             if len(models) != 1:
                 raise LibError("XCCY portfolio positions must share one Model")
             return compute_xccy([p.derivative for p in self._positions], self._positions[0].model, request_list)
+        if kinds == {InstrumentTypes.YOY_INFLATION_SWAP}:
+            from .yoy_engine import compute_yoy
+            if len({id(p.model) for p in self._positions}) != 1:
+                raise LibError("YoY inflation swap positions must share one Model")
+            return compute_yoy([p.derivative for p in self._positions], self._positions[0].model, request_list)
+        if InstrumentTypes.YOY_INFLATION_SWAP in kinds:
+            raise LibError("mixed OIS / YoY inflation portfolios are not supported (the reference cannot add Risk to Delta)")
         if InstrumentTypes.XCCY_SWAP in kinds:
             raise LibError("mixed OIS / XCCY portfolios are not supported (the reference cannot add Risk to Delta)")
         buckets = {}
