@@ -560,6 +560,9 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                 if ((mask >> qd) & 1u) pd = nc + __popc(mask & ((1u << qd) - 1u));
             }
         }
+        // portfolio partials of this tile accumulate in registers and touch shared memory once per tile: as a
+        // read-modify-write per unit they were half of the kernel's shared-memory wavefronts (ncu source counters)
+        double tg0 = 0.0, tg1 = 0.0, tg2 = 0.0, tg3 = 0.0, tdl = 0.0, tpv = 0.0;
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
             __syncthreads();                             // stage rows free
@@ -581,17 +584,22 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                     double* dst = a.out_gamma + (size_t)row * CAV_RR + oj * CAV_RW + ok4;
                     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
                 }
-                if (a.partials) { my_tg[0] += W * g0; my_tg[1] += W * g1; my_tg[2] += W * g2; my_tg[3] += W * g3; }
+                if (a.partials) { tg0 = fma(W, g0, tg0); tg1 = fma(W, g1, tg1); tg2 = fma(W, g2, tg2); tg3 = fma(W, g3, tg3); }
                 if (tid < CAV_RW) {
                     const double dl = row_s[pd];
                     if (a.out_delta) a.out_delta[(size_t)row * CAV_RW + tid] = dl;
-                    sTot[1 + tid] += W * dl;
+                    tdl = fma(W, dl, tdl);
                 }
                 if (tid == 32) {
                     if (a.out_pv) a.out_pv[row] = sPv[u];
-                    sTot[0] += W * sPv[u];
+                    tpv = fma(W, sPv[u], tpv);
                 }
             }
+        }
+        if (a.partials) {
+            my_tg[0] += tg0; my_tg[1] += tg1; my_tg[2] += tg2; my_tg[3] += tg3;
+            if (tid < CAV_RW) sTot[1 + tid] += tdl;
+            if (tid == 32) sTot[0] += tpv;
         }
     }
     if (a.partials) {     // this CTA's partial row (every launch owns its own block of rows and overwrites it)
