@@ -110,10 +110,60 @@ class Engine:
         return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
 
 
+ARRAY_ROUTE_MIN = 512   # object books at least this large are flattened as arrays (batch.OISBook)
+
+
+def _ois_conventions(d):
+    """Convention tuple of a vanilla OIS whose legs batch.OISBook reproduces exactly, else None."""
+    if getattr(d, "derivative_type", None) != InstrumentTypes.OIS_SWAP:
+        return None
+    fl, ft = d._fixed_leg, d._float_leg
+    same = ("_effective_dt", "_termination_dt", "_payment_lag", "_cal_type", "_bd_type", "_dg_type", "_notional")
+    if any(getattr(fl, a) != getattr(ft, a) for a in same) or fl._end_of_month or ft._end_of_month:
+        return None
+    if fl._principal != 0.0 or ft._principal != 0.0 or ft._notional_array or ft._notional_exchange:
+        return None
+    if fl._leg_type == ft._leg_type:
+        return None
+    return (fl._freq_type, fl._dc_type, ft._freq_type, ft._dc_type, fl._payment_lag, fl._cal_type, fl._bd_type, fl._dg_type)
+
+
+def _value_as_arrays(derivatives, curve: OISCurve, mask: int, sess) -> np.ndarray | None:
+    """Large books of vanilla OIS: the legs' dates are re-rolled as arrays (batch.py, identical rules) instead of
+    walking ~100 Python objects per trade; one valuation per convention set, totals added.  None = not applicable."""
+    from .batch import OISBook
+    from .global_types import SwapTypes
+    groups = {}
+    for d in derivatives:
+        conv = _ois_conventions(d)
+        if conv is None:
+            return None
+        groups.setdefault(conv, []).append(d)
+    total = np.zeros(_native.NOUT)
+    for conv, ds in groups.items():
+        n = len(ds)
+        book = OISBook(curve,
+                       np.fromiter((d._fixed_leg._effective_dt._n for d in ds), dtype=np.int64, count=n),
+                       np.fromiter((d._fixed_leg._termination_dt._n for d in ds), dtype=np.int64, count=n),
+                       np.fromiter((1.0 if d._fixed_leg._leg_type == SwapTypes.RECEIVE else -1.0 for d in ds), dtype=np.float64, count=n),
+                       np.fromiter((d._fixed_leg._cpn for d in ds), dtype=np.float64, count=n),
+                       np.fromiter((d._fixed_leg._notional for d in ds), dtype=np.float64, count=n),
+                       np.fromiter((d._float_leg._spread for d in ds), dtype=np.float64, count=n),
+                       conv[0], conv[1], conv[2], conv[3], conv[4], conv[5], conv[6], conv[7])
+        flat = book.flatten(dedup=True, tiles=bool(mask & _native.REQ_GAMMA))
+        sess.ctx.portfolio_upload(flat)
+        total += sess.ctx.portfolio_value_host(mask)
+    return total
+
+
 def value_positions(derivatives, curve: OISCurve, request_list, device: int = 0, dedup=None) -> AnalyticsResult:
     """Flatten -> upload -> one batched valuation; returns the summed AnalyticsResult."""
     mask = request_mask(request_list)
     sess = CurveSession.get(curve, device)
+    if dedup is None and len(derivatives) >= ARRAY_ROUTE_MIN:
+        agg = _value_as_arrays(derivatives, curve, mask, sess)
+        if agg is not None:
+            return _result_from_totals(agg, mask, curve, derivatives[0])
     fl = Flattener(curve)
     for d in derivatives:
         fl.add_trade(d)

@@ -105,3 +105,36 @@ def test_array_bench_book_matches_c_oracle_and_object_book(ref_curves):
     assert _scaled(rows["pv"][:m].cpu().numpy(), o_pv, N) < TOL
     assert _scaled(rows["delta"][:m].cpu().numpy(), o_dl, N * 1e-4 * 50) < TOL
     assert _scaled(rows["gamma"][:m].cpu().numpy(), o_gm, N * 1e-8 * 2500) < TOL
+
+
+def test_portfolio_compute_array_route_equals_object_route(ref_curves):
+    """Portfolio.compute over >= 512 vanilla OIS objects takes the array route (position._value_as_arrays); the
+    totals equal those of the object flattener, for a book mixing two convention sets."""
+    from adrates_b200 import position as P
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    curve = model.curves.GBP_OIS_SONIA
+    rng = np.random.default_rng(5)
+    derivs = []
+    for conv in ("annual_act365", "semi_vs_quarterly"):
+        c = CONVS[conv]
+        n = 330
+        spec = _random_book(curve, n, rng, spread=(conv != "annual_act365"))
+        sp = np.broadcast_to(spec["float_spread"], (n,))
+        for i in range(n):
+            eff = Date._of(int(spec["effective"][i]))
+            derivs.append(OIS(eff, eff.add_tenor(f"{int(spec['tenor_months'][i])}M"),
+                              SwapTypes.RECEIVE if spec["fixed_sign"][i] > 0 else SwapTypes.PAY,
+                              float(spec["fixed_coupon"][i]), c["fixed_freq_type"], c["fixed_dc_type"],
+                              CurveTypes.GBP_OIS_SONIA, CurrencyTypes.GBP, float(spec["notional"][i]), 0, float(sp[i]),
+                              c["float_freq_type"], c["float_dc_type"], bd_type=c["bd_type"]))
+    assert len(derivs) >= P.ARRAY_ROUTE_MIN and all(P._ois_conventions(d) is not None for d in derivs)
+    fast = Portfolio([d.position(model) for d in derivs]).compute(ALL)
+    slow = P.value_positions(derivs, curve, ALL, dedup=True)          # explicit dedup -> object flattener
+    S = len(derivs) * 1e8
+    assert abs(fast.value.amount - slow.value.amount) <= TOL * S
+    assert _scaled(fast.risk.risk_ladder, slow.risk.risk_ladder, S * 1e-4) < TOL
+    assert _scaled(fast.gamma.risk_ladder, slow.gamma.risk_ladder, S * 1e-8 * 40) < TOL
+    # anything the array route cannot express exactly falls back to objects
+    derivs[7]._float_leg._notional_array = [1.0]
+    assert P._ois_conventions(derivs[7]) is None
