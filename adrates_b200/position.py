@@ -94,10 +94,12 @@ class Engine:
             if derivative._currency not in BOND_CURVE:
                 raise LibError(f"No default OIS curve for currency {derivative._currency}")
             if BOND_CURVE[derivative._currency] != derivative._floating_index:
-                # the reference values dual-curve FRNs but has no Greeks for them; the dual-curve VALUE needs a
-                # second (index) grid in one term, which the single-grid flat layout does not carry yet
-                raise LibError("Dual-curve FRN delta/gamma not yet implemented. "
-                               "Use same curve for discounting and projection.")
+                # the reference values dual-curve FRNs but has no Greeks for them (engine.py:921-924)
+                if set(request_list) - {RequestTypes.VALUE}:
+                    raise LibError("Dual-curve FRN delta/gamma not yet implemented. "
+                                   "Use same curve for discounting and projection.")
+                from .xccy_engine import value_frn_dual_curve
+                return value_frn_dual_curve(derivative, self.model, self.device)
             return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
         if dtype != InstrumentTypes.OIS_SWAP:
             raise LibError(f"{dtype} not yet implemented")

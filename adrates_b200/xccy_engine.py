@@ -266,3 +266,79 @@ def compute_ois_xccy_collateral(derivative, model, request_list, collateral_ccy,
             Delta(np.array(agg_b[1:1 + xs.n_basis]), to_tenor(xc.swap_times), collateral_ccy, CurveTypes.USD_GBP_BASIS),
         ])
     return AnalyticsResult(value=value, risk=delta, gamma=None)
+
+
+# ======================================================================================
+# Dual-curve floating-rate notes (VALUE only, like the reference)
+# ======================================================================================
+class _EngineGrid:
+    """The path-B grid of an OIS curve in the shape _flatten_stacked expects of its second (discounting) grid."""
+
+    def __init__(self, curve, d):
+        self._times = curve.path_b_plan().node_time
+        self._dfs = d
+        self._interp_type = curve._interp_type
+
+
+_dual_sessions = {}
+
+
+def value_frn_dual_curve(frn, model, device=0) -> AnalyticsResult:
+    """Engine._compute_frn with an index curve that is not the currency's discount curve (engine.py:700-866):
+    coupons N a_i ((DF_idx(s)/DF_idx(e) - 1)/a_i + margin) DF_disc(p) plus the face value at maturity, as product
+    terms on the stacked grid [index engine grid ; discount engine grid].
+
+    Reference quirk kept: the engine caches curve tables under tuple(swap_times) alone (engine.py:2362-2376) and
+    fetches the discount curve first, so an index curve quoting the SAME pillar dates resolves to the discount
+    curve's tables and the note is valued single-curve."""
+    from .credit import BOND_CURVE
+    from .position import CurveSession, value_positions
+    try:
+        disc = getattr(model.curves, BOND_CURVE[frn._currency].name)
+        idx = getattr(model.curves, frn._floating_index.name)
+    except AttributeError as ex:
+        raise LibError(str(ex))
+    if tuple(idx.swap_times) == tuple(disc.swap_times):
+        return value_positions([frn], disc, [RequestTypes.VALUE], device)
+    key = (device, id(idx), id(disc))
+    sess = _dual_sessions.get(key)
+    if sess is None:
+        if len(_dual_sessions) >= 8:
+            _dual_sessions.pop(next(iter(_dual_sessions)))[0].close()
+        d_i, _, _ = CurveSession.get(idx, device).ctx.curve_read(jac=False, hess=False)
+        d_d, _, _ = CurveSession.get(disc, device).ctx.curve_read(jac=False, hess=False)
+        ctx = _native.Context(device)
+        ctx.curve_set_tables(np.concatenate([d_i, d_d]))
+        sess = _dual_sessions[key] = (ctx, _EngineGrid(disc, d_d), idx, disc)     # curves kept: ids stay unique
+    ctx, grid = sess[0], sess[1]
+    vd = model.value_dt
+    flat = _flatten_stacked([_dual_frn_terms(frn, vd)], idx, grid)
+    ctx.portfolio_upload(flat)
+    agg = ctx.portfolio_value_host(_native.REQ_VALUE)
+    return AnalyticsResult(value=Valuation(float(agg[0]), frn._currency), risk=None, gamma=None)
+
+
+def _dual_frn_terms(frn, value_dt):
+    """[(amount, t_start|None, t_end|None, t_pay)] of a dual-curve note: the cashflow rules of flatten.frn_components
+    (engine.py:763-866), but every forward keeps its own product term - DF(s) - DF(e) only collapses when projection
+    and discounting share a curve."""
+    dc = frn._dc_type
+    t = lambda d: float(times_from_dates(d, value_dt, dc))  # noqa: E731
+    N, m = float(frn._face_value), float(frn._quoted_margin)
+    out = []
+    for i, al in enumerate(frn._year_fracs):
+        tp = t(frn._payment_dts[i])
+        if not tp >= 0.0:
+            continue
+        if i == 0 and frn._first_fixing_rate is not None:
+            out.append(((float(frn._first_fixing_rate) + m) * al * N, None, None, tp))
+            continue
+        if al > 0:
+            out.append((N, t(frn._start_accrued_dts[i]), t(frn._end_accrued_dts[i]), tp))
+            out.append((-N, None, None, tp))
+        if m != 0.0:
+            out.append((m * al * N, None, None, tp))
+    tm = t(frn._maturity_dt)
+    if tm > 0.0:
+        out.append((N, None, None, tm))
+    return out

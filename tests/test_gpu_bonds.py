@@ -63,3 +63,31 @@ def test_frn_positions_match_reference():
                CurveTypes.USD_OIS_SOFR)
     with pytest.raises(LibError, match="Dual-curve FRN"):
         dual.position(m).compute(REQ)
+
+
+def test_dual_curve_frn_value_matches_reference():
+    """Index curve != discount curve: VALUE only (DELTA / GAMMA raise like the reference).  With identical pillar dates
+    the reference's curve cache resolves the index curve to the discount curve (single-curve value); a SOFR curve
+    quoting fewer pillars exercises the genuine two-grid product terms."""
+    from adrates_b200 import LibError, Date, DayCountTypes, FrequencyTypes, BusDayAdjustTypes, SwapTypes, InterpTypes
+    from adrates_b200.models import Model
+    g = load_golden("ref_frn.json")
+    m = build_bond_model(g)
+    for f in g["dual"]:
+        note = make_frn(f)
+        res = note.position(m).compute([RequestTypes.VALUE])
+        assert abs(res.value.amount - f["value"]) <= 1e-10 * f["face"], f["id"]
+        assert res.risk is None and res.gamma is None
+        with pytest.raises(LibError, match="Dual-curve FRN delta/gamma not yet implemented"):
+            note.position(m).compute([RequestTypes.VALUE, RequestTypes.DELTA])
+    m2 = Model(Date(*g["value_dt"]))
+    keep = g["dual_distinct_usd_keep"]
+    for name, px, tn in (("GBP_OIS_SONIA", g["gbp_px"], g["tenors"]),
+                         ("USD_OIS_SOFR", [g["usd_px"][i] for i in keep], [g["tenors"][i] for i in keep])):
+        m2.build_curve(name=name, px_list=px, tenor_list=tn, spot_days=0, swap_type=SwapTypes.PAY,
+                       fixed_dcc_type=DayCountTypes.ACT_365F, fixed_freq_type=FrequencyTypes.ANNUAL,
+                       float_freq_type=FrequencyTypes.ANNUAL, float_dc_type=DayCountTypes.ACT_365F,
+                       bus_day_type=BusDayAdjustTypes.MODIFIED_FOLLOWING, interp_type=InterpTypes.LINEAR_ZERO_RATES)
+    for f in g["dual_distinct"]:
+        res = make_frn(f).position(m2).compute([RequestTypes.VALUE])
+        assert abs(res.value.amount - f["value"]) <= 1e-10 * f["face"], f["id"]
