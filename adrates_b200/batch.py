@@ -24,7 +24,6 @@ the two dates (ACT/365F, ACT/360, SIMPLE, the four 30/360 variants, ACT/ACT ISDA
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import Optional
 
 import numpy as np
 

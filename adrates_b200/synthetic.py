@@ -17,7 +17,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .curves import OISCurve, plan_queries
+from .curves import OISCurve
 from .dates import BusDayAdjustTypes, DayCountTypes, FrequencyTypes, times_from_dates
 from .flatten import FlatPortfolio, assemble, group_trades, ois_components, _merge_single_df_terms, _Unit
 from .global_types import CurrencyTypes, CurveTypes, SwapTypes

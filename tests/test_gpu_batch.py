@@ -9,9 +9,8 @@ torch = pytest.importorskip("torch")
 
 from oracle import cavour_oracle as orc  # noqa: E402
 from adrates_b200 import RequestTypes, batch as B  # noqa: E402
-from adrates_b200.curves import OISCurve  # noqa: E402
 from adrates_b200.dates import Date  # noqa: E402
-from adrates_b200.global_types import CurrencyTypes, CurveTypes, InterpTypes, SwapTypes  # noqa: E402
+from adrates_b200.global_types import CurrencyTypes, CurveTypes, SwapTypes  # noqa: E402
 from adrates_b200.position import Portfolio  # noqa: E402
 from adrates_b200.trades import OIS  # noqa: E402
 from tests.flat_eval import eval_flat  # noqa: E402
@@ -65,7 +64,6 @@ def test_book_compute_matches_flat_arrays_and_portfolio(ref_curves, conv):
 def test_array_bench_book_matches_c_oracle_and_object_book(ref_curves):
     """200k trades of the BASELINE book built without any trade object: rows equal those of the object-built book
     (same draws), a sample equals the C oracle."""
-    from adrates_b200 import _native
     from adrates_b200.position import CurveSession
     from adrates_b200.synthetic import flatten_book, make_array_book, make_book, reference_leg_tables
     from oracle import c_oracle
