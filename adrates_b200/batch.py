@@ -615,13 +615,11 @@ class OISBook:
                             np.stack(wcols, axis=1), max_group)
 
     # ---- valuation -----------------------------------------------------------------------
-    def compute(self, request_list, device: int = 0, dedup: bool = True, per_trade: bool = True):
-        """One batched device valuation.  Returns (AnalyticsResult of the book totals, rows) where rows is a dict
-        of torch CUDA tensors {"pv": [N], "delta": [N,32], "gamma": [N,32,32]} in trade order (per_trade=True)."""
+    def _value(self, mask: int, device: int, dedup: bool, per_trade: bool):
+        """(totals [1057] on the host, {"pv", "delta", "gamma"} device rows in trade order)."""
         import torch
         from . import _native
-        from .position import CurveSession, request_mask, _result_from_totals
-        mask = request_mask(request_list)
+        from .position import CurveSession
         sess = CurveSession.get(self.curve, device)
         flat = self.flatten(dedup=dedup, tiles=bool(mask & _native.REQ_GAMMA))
         sess.ctx.portfolio_upload(flat)
@@ -636,7 +634,52 @@ class OISBook:
             if mask & _native.REQ_GAMMA:
                 rows["gamma"] = torch.empty(n, 32, 32, dtype=torch.float64, device=dev)
         ptr = lambda k: rows[k].data_ptr() if k in rows else None  # noqa: E731
-        agg = sess.ctx.portfolio_value_host(mask, ptr("pv"), ptr("delta"), ptr("gamma"))
+        agg = sess.ctx.portfolio_value_host(mask, ptr("pv"), ptr("delta"), ptr("gamma")) if n else np.zeros(_native.NOUT)
+        return np.array(agg, dtype=np.float64), rows
 
+    def compute(self, request_list, device: int = 0, dedup: bool = True, per_trade: bool = True):
+        """One batched device valuation.  Returns (AnalyticsResult of the book totals, rows) where rows is a dict
+        of torch CUDA tensors {"pv": [N], "delta": [N,32], "gamma": [N,32,32]} in trade order (per_trade=True)."""
+        from .position import request_mask, _result_from_totals
+        mask = request_mask(request_list)
+        agg, rows = self._value(mask, device, dedup, per_trade)
         # currency / index of the totals: those of the curve's calibration swaps (books are single-curve)
         return _result_from_totals(agg, mask, self.curve, self.curve._used_swaps[0]), rows
+
+    # ---- multi-GPU: one process per GPU, trades shard by rank, totals all-reduced (SURVEY 8e) ----
+    def shard(self, rank: int, world: int) -> "OISBook":
+        """The contiguous slice of this book rank `rank` of `world` owns, balanced by coupon count."""
+        from .parallel import shard_bounds
+        per_year = annual_frequency(self.fixed_freq_type) + annual_frequency(self.float_freq_type)
+        cost = np.maximum((self.termination - self.effective) / 365.25 * per_year, 1.0)
+        lo, hi = shard_bounds(cost, world)[rank]
+        sl = slice(lo, hi)
+        return OISBook(self.curve, self.effective[sl], self.termination[sl], self.fixed_sign[sl], self.coupon[sl],
+                       self.notional[sl], self.spread[sl], self.fixed_freq_type, self.fixed_dc_type, self.float_freq_type,
+                       self.float_dc_type, self.payment_lag, self.cal_type, self.bd_type, self.dg_type)
+
+    def compute_distributed(self, request_list, device: int | None = None, dedup: bool = True, per_trade: bool = True):
+        """Every rank of the initialised torch.distributed group calls this with the SAME book: each values its own
+        shard on its GPU (no data-path collective), the 1057 totals are summed with one all-reduce (NCCL over NVLink
+        for CUDA groups).  Returns (AnalyticsResult of the WHOLE book, rows of this rank's shard, (lo, hi))."""
+        import os
+        import torch
+        import torch.distributed as dist
+        from .parallel import all_reduce_totals, shard_bounds
+        from .position import request_mask, _result_from_totals
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", rank))
+        mask = request_mask(request_list)
+        mine = self.shard(rank, world)
+        agg, rows = mine._value(mask, device, dedup, per_trade)
+        backend = dist.get_backend() if dist.is_initialized() else None
+        tot = torch.from_numpy(agg)
+        if backend == "nccl":
+            tot = tot.to(torch.device("cuda", device))
+        all_reduce_totals(tot)
+        per_year = annual_frequency(self.fixed_freq_type) + annual_frequency(self.float_freq_type)
+        cost = np.maximum((self.termination - self.effective) / 365.25 * per_year, 1.0)
+        return (_result_from_totals(tot.cpu().numpy(), mask, self.curve, self.curve._used_swaps[0]), rows,
+                shard_bounds(cost, world)[rank])

@@ -136,3 +136,41 @@ def test_portfolio_compute_array_route_equals_object_route(ref_curves):
     # anything the array route cannot express exactly falls back to objects
     derivs[7]._float_leg._notional_array = [1.0]
     assert P._ois_conventions(derivs[7]) is None
+
+
+def _dist_worker(rank, world, port, out):
+    import os
+    import sys
+    import json
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from adrates_b200.synthetic import make_array_book
+    from tests.util_trades import build_model as bm
+    cv = json.load(open(os.path.join(root, "tests", "golden", "ref_curves.json")))["gbp_readme_lzr"]
+    curve = bm(cv).curves.GBP_OIS_SONIA
+    book = make_array_book(curve, 5000, seed=21)
+    res, rows, (lo, hi) = book.compute_distributed(ALL, device=0)       # both ranks share the one test GPU
+    np.save(f"{out}_{rank}.npy", np.concatenate([[res.value.amount], res.risk.risk_ladder, res.gamma.risk_ladder.reshape(-1),
+                                                 [lo, hi, float(rows["pv"].sum())]]))
+    dist.destroy_process_group()
+
+
+def test_compute_distributed_two_ranks_equal_single_process(ref_curves, tmp_path):
+    """OISBook.compute_distributed: two processes (gloo group, one GPU) value their shards and all-reduce the totals;
+    every rank returns the totals of the whole book."""
+    import torch.multiprocessing as mp
+    from adrates_b200.synthetic import make_array_book
+    out = str(tmp_path / "dist")
+    mp.spawn(_dist_worker, args=(2, 29533, out), nprocs=2, join=True)
+    curve = build_model(ref_curves["gbp_readme_lzr"]).curves.GBP_OIS_SONIA
+    book = make_array_book(curve, 5000, seed=21)
+    res, rows = book.compute(ALL)
+    ref = np.concatenate([[res.value.amount], res.risk.risk_ladder, res.gamma.risk_ladder.reshape(-1)])
+    a, b = np.load(out + "_0.npy"), np.load(out + "_1.npy")
+    assert np.array_equal(a[:-3], b[:-3])                                 # same totals on every rank
+    assert np.max(np.abs(a[:-3] - ref) / np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))) < 1e-10
+    assert (a[-3], b[-2]) == (0, 5000) and a[-2] == b[-3]                 # shards are contiguous and cover the book
+    assert abs(a[-1] + b[-1] - float(rows["pv"].sum())) <= 1e-10 * float(rows["pv"].abs().sum())

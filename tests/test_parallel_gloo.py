@@ -63,3 +63,35 @@ def test_two_rank_gloo_totals_match_single_process(tmp_path):
     got, ref = np.load(out)
     scale = np.abs(ref).max()
     assert np.max(np.abs(got - ref)) <= 1e-12 * scale
+
+
+def test_array_book_shards_cover_the_book_and_add_up():
+    """OISBook.shard: contiguous, covering, balanced by coupon count; the shards' totals (numpy evaluation of their
+    flat layouts) add up to the totals of the whole book."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import cavour_oracle as orc
+    from adrates_b200.curves import OISCurve
+    from adrates_b200.global_types import InterpTypes
+    from adrates_b200.synthetic import make_array_book
+    from tests.flat_eval import eval_flat
+    from tests.util_trades import make_calibration_swaps
+    cv = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_curves.json")))["gbp_readme_lzr"]
+    vd, swaps = make_calibration_swaps(cv)
+    curve = OISCurve(vd, swaps, InterpTypes[cv["interp"]])
+    book = make_array_book(curve, 300, seed=3)
+    plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
+    d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+
+    def totals(b):
+        pv, dl, gm = eval_flat(b.flatten(tiles=False), d, J, C)
+        return np.concatenate([[pv.sum()], dl.sum(0), gm.sum(0).reshape(-1)])
+    ref = totals(book)
+    for world in (2, 3, 8):
+        shards = [book.shard(r, world) for r in range(world)]
+        assert sum(s.n_trades for s in shards) == 300
+        assert np.array_equal(np.concatenate([s.notional for s in shards]), book.notional)
+        costs = [float(np.sum(s.termination - s.effective)) for s in shards]
+        assert max(costs) - min(costs) <= 2 * 51 * 366
+        tot = sum(totals(s) for s in shards)
+        assert np.max(np.abs(tot - ref)) <= 1e-12 * np.max(np.abs(ref))
