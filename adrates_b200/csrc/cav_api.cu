@@ -167,7 +167,13 @@ int host_threads(int64_t work) {
     static int cap = [] {
         const char* e = std::getenv("CAV_HOST_THREADS");
         int n = e ? std::atoi(e) : 0;
-        if (n <= 0) { n = (int)std::thread::hardware_concurrency() / 2; n = n > 8 ? 8 : n; }
+        if (n <= 0) {
+            const int hw = (int)std::thread::hardware_concurrency();
+            n = hw / 2; n = n > 8 ? 8 : n;
+            const char* lws = std::getenv("LOCAL_WORLD_SIZE");          // one rank per GPU shares the host cores
+            const int ranks = lws ? std::atoi(lws) : 1;
+            if (ranks > 1 && n > hw / ranks) n = hw / ranks;
+        }
         return n < 1 ? 1 : n;
     }();
     return work < 200000 ? 1 : cap;
