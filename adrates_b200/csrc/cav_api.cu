@@ -1069,7 +1069,30 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     CK(cudaGetLastError());
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[1], ctx->stream));
     if (!ctx->direct && (pv || delta || gamma) && ctx->n_groups > 0) {
-        // gamma rows: group-ordered streaming kernel; PV / delta rows: row-ordered gather (coalesced small rows)
+        // gamma rows: group-ordered streaming kernel; PV / delta rows: row-ordered gather (coalesced small rows).
+        // With both requested the small, latency-bound row gather runs on a side stream next to the DRAM-bound gamma
+        // expansion instead of after it.
+        const bool rows_aside = gamma && (pv || delta);
+        if (rows_aside) {
+            cudaStream_t main_stream = ctx->stream;
+            CK(cudaEventRecord(ctx->ev_fork, main_stream));
+            CK(cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+            ctx->stream = ctx->aux[0];
+            int rc = ensure_row_tables(ctx);
+            if (rc == CAV_OK) {
+                switch (ctx->n_comp) {
+                    case 1: launch_expand_rows<1>(ctx, pv, delta); break;
+                    case 2: launch_expand_rows<2>(ctx, pv, delta); break;
+                    case 3: launch_expand_rows<3>(ctx, pv, delta); break;
+                    default: launch_expand_rows<4>(ctx, pv, delta); break;
+                }
+            }
+            cudaError_t e = cudaEventRecord(ctx->ev_join[0], ctx->aux[0]);
+            ctx->stream = main_stream;
+            if (rc) return rc;
+            CK(e);
+            CK(cudaGetLastError());
+        }
         if (gamma) {
             const int chunks = ctx->up_chunks > 0 ? ctx->up_chunks : 1;
             for (int c = 0; c < chunks; ++c) {
@@ -1085,7 +1108,8 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
             }
             CK(cudaGetLastError());
         }
-        if (pv || delta) {
+        if (rows_aside) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[0], 0));
+        else if (pv || delta) {
             { int rc = ensure_row_tables(ctx); if (rc) return rc; }
             switch (ctx->n_comp) {
                 case 1: launch_expand_rows<1>(ctx, pv, delta); break;
