@@ -100,6 +100,8 @@ struct cav_ctx {
     bool tiles_valid = false;
     bool tables_ok = false;     // Tsym / row_masks hold the tables of the current curve, pair rows and permutation
     bool tsym_valid = false;    // ... and the current tile plan's masks have been checked against them
+    bool mask_check_pending = false;   // k_check_tile_masks launched, verdict not read yet
+    int h_check_flag = 0;
     double* Qmat = nullptr;   // dense node gradients for the DMMA chain GEMM
     double *sc_rates = nullptr, *sc_P = nullptr, *sc_L = nullptr, *sc_upv = nullptr;   // scenario scratch (grow-only)
     // scenario DF cache: distinct (bracket, weights) queries of the uploaded terms
@@ -115,9 +117,11 @@ struct cav_ctx {
     double* unit_weight = nullptr;
     std::vector<int64_t> h_unit_offsets;      // host copy (tile-plan validation)
     std::vector<int> h_pairs;                 // pair rows and permutation of the tables currently on the device
-    std::vector<int> h_npos;                  // staging of the tile plan (see cav_portfolio_set_tiles)
-    std::vector<unsigned> h_masks;
-    std::vector<int2> h_pack;
+    // staging of the tile plan (see cav_portfolio_set_tiles): one pinned, grow-only arena, so that the copies are truly
+    // asynchronous whatever memory the caller's arrays live in (a pageable source makes cudaMemcpyAsync wait for the
+    // stream - here: for the 10 MB of unit arrays the upload has just queued)
+    char* tile_stage = nullptr;
+    size_t tile_stage_cap = 0;
 
     // scratch
     double *u_pv = nullptr, *u_delta = nullptr, *u_gamma = nullptr;
@@ -419,6 +423,7 @@ void cav_destroy(cav_ctx* ctx) {
     for (int i = 0; i < 5; ++i) cudaEventDestroy(ctx->evk[i]);
     cudaEventDestroy(ctx->ev_fork);
     for (int i = 0; i < CAV_N_CLASSES; ++i) { cudaStreamDestroy(ctx->aux[i]); cudaEventDestroy(ctx->ev_join[i]); }
+    if (ctx->tile_stage) cudaFreeHost(ctx->tile_stage);
     cudaStreamDestroy(ctx->copy);
     cudaEventDestroy(ctx->ev_up);
     cudaEventDestroy(ctx->ev_tiles);
@@ -883,11 +888,31 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     // staging vectors live in the context: with the pipelined upload their copies may still be in flight when this
     // call returns, so wait for the previous plan's copies (ev_tiles) before overwriting them
     CK(cudaEventSynchronize(ctx->ev_tiles));
-    std::vector<int>& npos = ctx->h_npos;
-    std::vector<unsigned>& masks = ctx->h_masks;
-    npos.assign((size_t)n_tiles, 0);
-    masks.assign((size_t)n_tiles, 0xFFFFFFFFu);
-    if (tile_mask) std::memcpy(masks.data(), tile_mask, sizeof(unsigned) * n_tiles);
+    auto up8 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t b_units = up8(sizeof(int) * (size_t)n_tiles * tile_size), b_tile = up8(sizeof(int) * (size_t)n_tiles),
+                 b_pack = up8(sizeof(int2) * (size_t)n_krows), b_pairs = up8(sizeof(int) * 2 * (size_t)n_pair_rows);
+    const size_t need = b_units + 5 * b_tile + b_pack + b_pairs;
+    if (need > ctx->tile_stage_cap) {
+        if (ctx->tile_stage) cudaFreeHost(ctx->tile_stage);
+        ctx->tile_stage = nullptr; ctx->tile_stage_cap = 0;
+        CK(cudaHostAlloc((void**)&ctx->tile_stage, need + need / 4, cudaHostAllocDefault));
+        ctx->tile_stage_cap = need + need / 4;
+    }
+    char* sp = ctx->tile_stage;
+    int* st_units = (int*)sp; sp += b_units;
+    int* st_kstart = (int*)sp; sp += b_tile;
+    int* st_kcount = (int*)sp; sp += b_tile;
+    int* npos = (int*)sp; sp += b_tile;
+    unsigned* masks = (unsigned*)sp; sp += b_tile;
+    sp += b_tile;                                   // spare
+    int2* pack = (int2*)sp; sp += b_pack;
+    int* st_pairs = (int*)sp;
+    std::memcpy(st_units, tile_units, sizeof(int) * (size_t)n_tiles * tile_size);
+    std::memcpy(st_kstart, tile_kstart, sizeof(int) * (size_t)n_tiles);
+    std::memcpy(st_kcount, tile_kcount, sizeof(int) * (size_t)n_tiles);
+    if (n_pair_rows) std::memcpy(st_pairs, pairs, sizeof(int) * 2 * (size_t)n_pair_rows);
+    for (int t = 0; t < n_tiles; ++t) { npos[t] = 0; masks[t] = 0xFFFFFFFFu; }
+    if (tile_mask) std::memcpy(masks, tile_mask, sizeof(unsigned) * n_tiles);
     int cls_prev = 0;
     int class_begin[CAV_N_CLASSES + 1];
     for (int c = 0; c <= CAV_N_CLASSES; ++c) class_begin[c] = n_tiles;
@@ -905,47 +930,57 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
         }
         npos[t] = (int)(len < 0 ? 0 : len);
         if (npos[t] > 255) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 255 terms per unit");
-        // K rows ordered by position; a second contribution lives in the same chunk of 32 positions
-        if (t == 0 || tile_kstart[t] != tile_kstart[t - 1] || tile_kcount[t] != tile_kcount[t - 1] || npos[t] != npos[t - 1]) {
-            int prev = 0, in_chunk = 0;
-            for (int k = 0; k < tile_kcount[t]; ++k) {
-                const int p = k_pos[tile_kstart[t] + k];
-                if (p < prev || p >= npos[t])
-                    return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows not ordered by position or position out of range");
-                in_chunk = (p >> 5) == (prev >> 5) ? in_chunk + 1 : 1;
-                if (in_chunk > GM_KC)
-                    return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 160 K rows in a chunk of 32 term positions");
-                prev = p;
-                if (k_pos2 && k_coef2[tile_kstart[t] + k] >= 0) {
-                    const int p2 = k_pos2[tile_kstart[t] + k];
-                    if (p2 < 0 || p2 >= npos[t] || (p2 >> 5) != (p >> 5))
-                        return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: second contribution outside the row's 32-position chunk");
-                }
-            }
-        }
         const int cls = cav_tile_class(masks[t]);
         if (cls < cls_prev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: tiles must be ordered by size class");
         for (int c = cls_prev + 1; c <= cls; ++c) class_begin[c] = t;
         cls_prev = cls;
     }
-    std::vector<int2>& pack = ctx->h_pack;
-    pack.resize((size_t)n_krows);
-    for (int64_t k = 0; k < n_krows; ++k) {
-        if (k_row[k] < 0 || k_row[k] >= n_rows || k_pos[k] < 0 || k_pos[k] > 255 || k_coef[k] < 0 || k_coef[k] > 5 ||
-            (k_coef2 && k_coef2[k] > 5))
-            return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: bad K row");
-        const bool two = k_coef2 && k_coef2[k] >= 0;
-        pack[k] = make_int2(k_row[k], k_pos[k] | (k_coef[k] << 8) | ((two ? k_pos2[k] : 0) << 16) | ((two ? k_coef2[k] : 7) << 24));
+    // K rows of every distinct group: ordered by position, at most GM_KC per chunk of 32 positions, a second contribution
+    // lives in the same chunk (groups are independent: checked by a few host threads)
+    {
+        int err = 0;
+#pragma omp parallel for num_threads(host_threads(4 * n_krows)) schedule(dynamic, 64) reduction(max : err)
+        for (int t = 0; t < n_tiles; ++t) {
+            if (t > 0 && tile_kstart[t] == tile_kstart[t - 1] && tile_kcount[t] == tile_kcount[t - 1] && npos[t] == npos[t - 1]) continue;
+            int prev = 0, in_chunk = 0, e = 0;
+            for (int k = 0; k < tile_kcount[t]; ++k) {
+                const int p = k_pos[tile_kstart[t] + k];
+                if (p < prev || p >= npos[t]) e = e > 1 ? e : 1;
+                in_chunk = (p >> 5) == (prev >> 5) ? in_chunk + 1 : 1;
+                if (in_chunk > GM_KC) e = e > 2 ? e : 2;
+                prev = p;
+                if (k_pos2 && k_coef2[tile_kstart[t] + k] >= 0) {
+                    const int p2 = k_pos2[tile_kstart[t] + k];
+                    if (p2 < 0 || p2 >= npos[t] || (p2 >> 5) != (p >> 5)) e = e > 3 ? e : 3;
+                }
+            }
+            err = err > e ? err : e;
+        }
+        if (err == 1) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K rows not ordered by position or position out of range");
+        if (err == 2) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 160 K rows in a chunk of 32 term positions");
+        if (err == 3) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: second contribution outside the row's 32-position chunk");
+    }
+    {
+        int bad_row = 0;
+        int2* pk = pack;
+#pragma omp parallel for num_threads(host_threads(4 * n_krows)) schedule(static) reduction(| : bad_row)
+        for (int64_t k = 0; k < n_krows; ++k) {
+            bad_row |= (k_row[k] < 0) | (k_row[k] >= n_rows) | (k_pos[k] < 0) | (k_pos[k] > 255) | (k_coef[k] < 0) |
+                       (k_coef[k] > 5) | (k_coef2 && k_coef2[k] > 5);
+            const bool two = k_coef2 && k_coef2[k] >= 0;
+            pk[k] = make_int2(k_row[k], k_pos[k] | (k_coef[k] << 8) | ((two ? k_pos2[k] : 0) << 16) | ((two ? k_coef2[k] : 7) << 24));
+        }
+        if (bad_row) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: bad K row");
     }
     for (int i = 0; i < 2 * n_pair_rows; ++i)
         if (pairs[i] < 0 || pairs[i] >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: pair node out of range");
-    CK(upload(ctx, &ctx->tile_units, (const int*)tile_units, (size_t)n_tiles * tile_size));
-    CK(upload(ctx, &ctx->tile_kstart, (const int*)tile_kstart, (size_t)n_tiles));
-    CK(upload(ctx, &ctx->tile_kcount, (const int*)tile_kcount, (size_t)n_tiles));
-    CK(upload(ctx, &ctx->tile_npos, npos.data(), (size_t)n_tiles));
-    CK(upload(ctx, &ctx->k_pack, pack.data(), (size_t)n_krows));
-    CK(upload(ctx, &ctx->pairs, (const int*)pairs, (size_t)2 * n_pair_rows));
-    CK(upload(ctx, &ctx->tile_mask, masks.data(), (size_t)n_tiles));
+    CK(upload(ctx, &ctx->tile_units, (const int*)st_units, (size_t)n_tiles * tile_size));
+    CK(upload(ctx, &ctx->tile_kstart, (const int*)st_kstart, (size_t)n_tiles));
+    CK(upload(ctx, &ctx->tile_kcount, (const int*)st_kcount, (size_t)n_tiles));
+    CK(upload(ctx, &ctx->tile_npos, (const int*)npos, (size_t)n_tiles));
+    CK(upload(ctx, &ctx->k_pack, (const int2*)pack, (size_t)n_krows));
+    CK(upload(ctx, &ctx->pairs, (const int*)st_pairs, (size_t)2 * n_pair_rows));
+    CK(upload(ctx, &ctx->tile_mask, (const unsigned*)masks, (size_t)n_tiles));
     CK(cudaEventRecord(ctx->ev_tiles, ctx->stream));
     CK(issue_trade_chunks(ctx));
     if (!ctx->async_upload) CK(cudaStreamSynchronize(ctx->stream));
@@ -980,7 +1015,22 @@ static int ensure_row_tables(cav_ctx* ctx) {
     return CAV_OK;
 }
 
-static int build_sym_tables(cav_ctx* ctx) {
+// result of k_check_tile_masks: read the flag (synchronising if asked to) and validate or reject the plan
+static int finish_mask_check(cav_ctx* ctx, bool sync) {
+    if (sync) {
+        CK(cudaMemcpyAsync(&ctx->h_check_flag, ctx->check_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->mask_check_pending = false;
+    if (ctx->h_check_flag) {
+        ctx->tiles_valid = false;
+        return fail(ctx, CAV_E_INVALID, "tile plan: active-pillar masks do not cover the curve tables' support");
+    }
+    ctx->tsym_valid = true;
+    return CAV_OK;
+}
+
+static int build_sym_tables(cav_ctx* ctx, bool defer_check) {
     const size_t rows = (size_t)3 * ctx->G + ctx->n_pair_rows + 1;
     if (!ctx->tables_ok) {
         CK(dev_alloc(ctx, &ctx->Tsym, rows * GT_NC));
@@ -1002,12 +1052,11 @@ static int build_sym_tables(cav_ctx* ctx) {
                                                                           ctx->check_flag);
     ctx->launches++;
     CK(cudaGetLastError());
-    int flag = 0;
-    CK(cudaMemcpyAsync(&flag, ctx->check_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    if (flag) return fail(ctx, CAV_E_INVALID, "tile plan: active-pillar masks do not cover the curve tables' support");
-    ctx->tsym_valid = true;
-    return CAV_OK;
+    if (defer_check) {       // the caller reads the flag together with its own device->host copy (no extra round trip)
+        ctx->mask_check_pending = true;
+        return CAV_OK;
+    }
+    return finish_mask_check(ctx, true);
 }
 
 static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, double* gamma, double* agg_dev,
@@ -1031,7 +1080,9 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     const bool need_agg = agg_dev || agg_host;
     static int gemm_mode = [] { const char* e = std::getenv("CAV_UNITS_GEMM"); return e ? std::atoi(e) : 1; }();
     const bool use_gemm = want_g && ctx->tiles_valid && gemm_mode != 0 && ctx->n_tiles > 0;
-    if (use_gemm && !ctx->tsym_valid) { int rc = build_sym_tables(ctx); if (rc) return rc; }
+    // a new tile plan is checked against the tables on the device; with a host-side totals read at the end of this call
+    // the verdict travels with it (a rejected plan's results are discarded: error return, plan invalidated)
+    if (use_gemm && !ctx->tsym_valid) { int rc = build_sym_tables(ctx, agg_host != nullptr); if (rc) return rc; }
     int64_t rows = 0;
     int grid = units_grid(ctx, ctx->n_units, want_g, &rows);
     if (use_gemm) rows = mma_partial_rows(ctx);                   // one partial row per persistent CTA of every class
@@ -1128,10 +1179,13 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         CK(cudaGetLastError());
         if (ctx->profile) { CK(cudaEventRecord(ctx->evk[3], ctx->stream)); ctx->evk_n = 4; }
         if (agg_host) {
+            if (ctx->mask_check_pending)
+                CK(cudaMemcpyAsync(&ctx->h_check_flag, ctx->check_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaMemcpyAsync(agg_host, dst, sizeof(double) * CAV_NOUT, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
         }
     }
+    if (ctx->mask_check_pending) { int rc = finish_mask_check(ctx, agg_host == nullptr); if (rc) return rc; }
     return CAV_OK;
 }
 

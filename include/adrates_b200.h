@@ -65,9 +65,9 @@ int         cav_set_stream(cav_ctx* ctx, void* cuda_stream);
  * unit arrays, the tile plan and the units kernel proceed, and the expansion kernel of a chunk starts as soon as
  * its weights have landed; neither cav_portfolio_upload nor cav_portfolio_set_tiles waits for its copies (the
  * host-side validation still runs, concurrently with them).  Contract when enabled: every HOST buffer handed to
- * cav_portfolio_upload / cav_portfolio_set_tiles must stay valid and unmodified until the next
- * cav_portfolio_value_host or cav_sync call on this context has returned.  Off by default.  Results are
- * bit-identical either way. */
+ * cav_portfolio_upload must stay valid and unmodified until the next cav_portfolio_value_host or cav_sync call on
+ * this context has returned (the tile plan is staged through a pinned arena of the library and may be reused at
+ * once).  Off by default.  Results are bit-identical either way. */
 int         cav_set_async_upload(cav_ctx* ctx, int enable);
 /* per-kernel CUDA-event timing of cav_portfolio_value: ms[0] units kernel, ms[1] per-trade
  * expansion kernel, ms[2] portfolio-total reduction (needs agg output) */
