@@ -186,7 +186,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the valuation path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
     if world > 1:
+        # one rank per GPU: keep the rank (its pinned upload buffers and the library's host threads) on the CPUs next to
+        # its GPU, so that eight end-to-end uploads do not all cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ
+                                                  else int(os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local]))
+            pynvml.nvmlDeviceSetCpuAffinity(h)
+            numa = len(os.sched_getaffinity(0))
+        except Exception as ex:          # noqa: BLE001  (placement is an optimisation, never a requirement)
+            numa = f"unbound ({type(ex).__name__})"
         dist.init_process_group("nccl", device_id=dev)
 
     cv, curve = load_curve()
@@ -472,6 +484,7 @@ def main():
                    "parity_gate_scaled_err": gate, "flatten_seconds_untimed": flatten_s,
                    "wall_seconds_timed_region": wall},
         "clocks": clocks,
+        "host_cpus_per_rank": numa,
         "e2e": {"value": e2e_value, "unit": "trades/s", "h2d_bytes_per_step": flat.h2d_bytes(),
                 "d2h_bytes_per_step": _native.NOUT * 8,
                 "note": "cav_portfolio_upload from pinned host arrays + cav_portfolio_value(_host) + totals D2H; "
