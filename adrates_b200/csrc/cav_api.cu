@@ -34,7 +34,7 @@ struct CapTable {
         for (size_t i = 0; i < v.size(); ++i) if (v[i].first == p) { v.erase(v.begin() + i); return; }
     }
 };
-#define CAV_UP_CHUNKS 4
+#define CAV_UP_CHUNKS 8
 
 struct cav_ctx {
     CapTable caps;
@@ -51,7 +51,7 @@ struct cav_ctx {
     // pipelined upload (cav_set_async_upload): the per-trade arrays travel on `copy` in CAV_UP_CHUNKS group-aligned
     // chunks while the unit arrays, the tile plan and the units kernel proceed on `stream`
     cudaStream_t copy = nullptr;
-    cudaEvent_t ev_up = nullptr, ev_tiles = nullptr, ev_chunk[CAV_UP_CHUNKS] = {nullptr};
+    cudaEvent_t ev_up = nullptr, ev_tiles = nullptr, ev_units = nullptr, ev_chunk[CAV_UP_CHUNKS] = {nullptr};
     bool async_upload = false;
     int up_chunks = 0;                              // > 0: chunk events of the current portfolio are valid
     int64_t up_group[CAV_UP_CHUNKS + 1] = {0};      // group range of every chunk
@@ -62,6 +62,11 @@ struct cav_ctx {
     const int64_t* pend_index = nullptr;
     int pend_comp = 0;
     int64_t pend_trades = 0;
+    // ... and their host-side validation is deferred until the units kernel has been launched (settle_trade_checks)
+    bool trade_check_pending = false;
+    const int64_t* chk_group_offsets = nullptr;
+    const int32_t* chk_group_units = nullptr;
+    int64_t chk_groups = 0, chk_units = 0;
     std::string err;
     int64_t launches = 0;
 
@@ -130,7 +135,6 @@ struct cav_ctx {
 };
 
 namespace {
-
 int fail(cav_ctx* c, int code, const std::string& msg) {
     if (c) c->err = msg;
     return code;
@@ -167,7 +171,7 @@ cudaError_t upload(cav_ctx* ctx, T** p, const T* host, size_t n) {
 
 // Threads for the host-side scans of an upload: explicit (torchrun pins OMP_NUM_THREADS=1, and one rank per GPU
 // shares the host), a few are enough to hide the scans behind the copies; CAV_HOST_THREADS overrides.
-int host_threads(int64_t work) {
+int host_threads(int64_t work, int64_t min_work = 200000) {
     static int cap = [] {
         const char* e = std::getenv("CAV_HOST_THREADS");
         int n = e ? std::atoi(e) : 0;
@@ -180,7 +184,7 @@ int host_threads(int64_t work) {
         }
         return n < 1 ? 1 : n;
     }();
-    return work < 200000 ? 1 : cap;
+    return work < min_work ? 1 : cap;
 }
 
 template <typename T>
@@ -235,9 +239,9 @@ void launch_units(cav_ctx* ctx, const UnitsArgs& a, bool delta, bool gamma, int 
 }
 
 template <int K>
-void launch_expand(cav_ctx* ctx, double* pv, double* delta, double* gamma, int64_t g0, int64_t g1) {
+void launch_expand(cav_ctx* ctx, cudaStream_t st, double* pv, double* delta, double* gamma, int64_t g0, int64_t g1) {
     if (g1 <= g0) return;
-    k_expand<K><<<(unsigned)(g1 - g0), 256, 0, ctx->stream>>>(
+    k_expand<K><<<(unsigned)(g1 - g0), 256, 0, st>>>(
         ctx->group_offsets + g0, ctx->group_units + g0 * K, ctx->comp_weight, ctx->out_index, ctx->u_pv, ctx->u_delta,
         ctx->u_gamma, pv, delta, gamma);
     ctx->launches++;
@@ -263,6 +267,52 @@ cudaError_t issue_trade_chunks(cav_ctx* ctx) {
     }
     if (e == cudaSuccess) ctx->up_chunks = ctx->up_n;
     return e;
+}
+
+// Range checks of the per-trade arrays of a portfolio (what the expansion kernels dereference): OR-reductions
+// (x | (limit - x) has its sign bit set iff x < 0 or x > limit), branch-free, vectorisable, split over a few host threads.
+const char* check_trade_arrays(int64_t n_trades, int64_t n_units, int64_t n_groups, int n_comp,
+                               const int64_t* group_offsets, const int32_t* group_units, const int64_t* out_index) {
+    const int nth = host_threads(n_trades);
+    const int64_t n_gu = n_groups * n_comp;
+    const int u_hi = (int)(n_units - 1);
+    const int64_t t_hi = n_trades - 1;
+    int a_gu = 0;
+    int64_t a_grp = 0, a_out = 0;
+#pragma omp parallel num_threads(nth) reduction(| : a_gu, a_grp, a_out)
+    {
+#pragma omp for nowait schedule(static)
+        for (int64_t i = 0; i < n_gu; ++i) a_gu |= group_units[i] | (u_hi - group_units[i]);
+#pragma omp for nowait schedule(static)
+        for (int64_t gi = 0; gi < n_groups; ++gi) {
+            const int64_t c = group_offsets[gi + 1] - group_offsets[gi];
+            a_grp |= c | (256 - c);                      // 0 <= group size <= 256
+        }
+        if (out_index) {
+#pragma omp for nowait schedule(static)
+            for (int64_t t = 0; t < n_trades; ++t) a_out |= out_index[t] | (t_hi - out_index[t]);
+        }
+    }
+    if (a_gu < 0) return "cav_portfolio_upload: unit id out of range";
+    if ((a_grp | a_out) < 0) return "cav_portfolio_upload: group larger than 256 trades, offsets not monotone or out_index out of range";
+    return nullptr;
+}
+
+// Pipelined upload: the per-trade arrays are checked on the host while the units kernel (which does not read them) runs;
+// nothing that dereferences them on the device is launched before this returns CAV_OK.  A failure discards the portfolio.
+int settle_trade_checks(cav_ctx* ctx) {
+    if (!ctx->trade_check_pending) return CAV_OK;
+    ctx->trade_check_pending = false;
+    const char* verr = check_trade_arrays(ctx->pend_trades, ctx->chk_units, ctx->chk_groups, ctx->pend_comp,
+                                          ctx->chk_group_offsets, ctx->chk_group_units, ctx->pend_index);
+    if (!verr) return CAV_OK;
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy);
+    ctx->up_chunks = 0;
+    ctx->chunks_pending = false;
+    ctx->portfolio_valid = false;
+    ctx->tiles_valid = false;
+    return fail(ctx, CAV_E_INVALID, verr);
 }
 
 // every chunk of a pipelined upload has landed before anything later on the context's stream runs
@@ -391,7 +441,8 @@ int cav_create(cav_ctx** out, int device) {
             cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     if (cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_up, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_tiles, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
+        cudaEventCreateWithFlags(&ctx->ev_tiles, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_units, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     for (int i = 0; i < CAV_UP_CHUNKS; ++i)
         if (cudaEventCreateWithFlags(&ctx->ev_chunk[i], cudaEventDisableTiming) != cudaSuccess) { delete ctx; return CAV_E_CUDA; }
     *out = ctx;
@@ -427,6 +478,7 @@ void cav_destroy(cav_ctx* ctx) {
     cudaStreamDestroy(ctx->copy);
     cudaEventDestroy(ctx->ev_up);
     cudaEventDestroy(ctx->ev_tiles);
+    cudaEventDestroy(ctx->ev_units);
     for (int i = 0; i < CAV_UP_CHUNKS; ++i) cudaEventDestroy(ctx->ev_chunk[i]);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -439,6 +491,8 @@ int64_t cav_launch_count(const cav_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int cav_sync(cav_ctx* ctx) {
     if (!ctx) return CAV_E_INVALID;
     CK(cudaSetDevice(ctx->device));
+    const int chk = settle_trade_checks(ctx);          // the caller may release the host arrays after this call
+    if (chk) return chk;
     CK(issue_trade_chunks(ctx));
     CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaStreamSynchronize(ctx->copy));
@@ -751,7 +805,12 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
         W.assign((size_t)n_units, 0.0);
         for (int64_t gi = 0; gi < n_groups; ++gi)
             for (int64_t t = group_offsets[gi]; t < group_offsets[gi + 1]; ++t)
-                for (int k = 0; k < n_comp; ++k) W[group_units[gi * n_comp + k]] += comp_weight[t * n_comp + k];
+                for (int k = 0; k < n_comp; ++k) {
+                    const int32_t u = group_units[gi * n_comp + k];
+                    if (u < 0 || u >= n_units || t < 0 || t >= n_trades)
+                        return fail(ctx, CAV_E_INVALID, "cav_portfolio_upload: unit id or group offsets out of range");
+                    W[u] += comp_weight[t * n_comp + k];
+                }
         unit_weight = W.data();
     }
     CK(cudaSetDevice(ctx->device));
@@ -780,14 +839,15 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
         else dev_free(ctx, &ctx->out_index);
         // chunk sizes grow quadratically: a small first chunk lets the expansion start early, large later chunks
         // keep the number of partial waves (kernel tails) down
-        static const int n_chunks = [] {
+        const int n_chunks = [] {
             const char* e = std::getenv("CAV_UP_CHUNKS");
             const int n = e ? std::atoi(e) : 2;
             return n < 1 ? 1 : (n > CAV_UP_CHUNKS ? CAV_UP_CHUNKS : n);
         }();
         ctx->up_n = n_chunks;
+        const int growth = [] { const char* e = std::getenv("CAV_UP_GROWTH"); return e ? std::atoi(e) : 2; }();
         for (int c = 0; c <= n_chunks; ++c) {
-            ctx->up_group[c] = n_groups * c * c / (n_chunks * n_chunks);
+            ctx->up_group[c] = growth == 1 ? n_groups * c / n_chunks : n_groups * c * c / (n_chunks * n_chunks);
             ctx->up_trade[c] = group_offsets[ctx->up_group[c]];
         }
         ctx->pend_weight = comp_weight;
@@ -802,39 +862,31 @@ int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const i
     }
 
     // Host-side validation of every index the kernels will dereference runs while the copies above are in
-    // flight; a failure invalidates the uploaded portfolio.  The scans are OR-reductions (x | (limit - x) has its
-    // sign bit set iff x < 0 or x > limit): branch-free, vectorisable and split over a few host threads - at 1M
-    // trades a single-threaded scan (11 MB) costs as much as the copies themselves.
+    // flight; a failure invalidates the uploaded portfolio.  With the pipelined upload only what the units kernel reads
+    // (nodes, unit offsets) is checked here; the per-trade arrays are checked after that kernel has been launched
+    // (settle_trade_checks), off the critical path - at 1M trades their scan costs as much as the unit-array copies.
     const char* verr = nullptr;
+    ctx->trade_check_pending = false;
     {
-        const int nth = host_threads(n_trades + n_terms);
-        const int64_t n_node = n_terms * n_pairs, n_gu = n_groups * n_comp;
-        const int g_hi = ctx->G - 1, u_hi = (int)(n_units - 1);
-        const int64_t t_hi = n_trades - 1;
-        int a_node = 0, a_gu = 0;
-        int64_t a_off = 0, a_grp = 0, a_out = 0;
-#pragma omp parallel num_threads(nth) reduction(| : a_node, a_gu, a_off, a_grp, a_out)
+        const int64_t n_node = n_terms * n_pairs;
+        const int nth = host_threads(n_node);
+        const int g_hi = ctx->G - 1;
+        int a_node = 0;
+        int64_t a_off = 0;
+#pragma omp parallel num_threads(nth) reduction(| : a_node, a_off)
         {
 #pragma omp for nowait schedule(static)
             for (int64_t i = 0; i < n_node; ++i) a_node |= node[i] | (g_hi - node[i]);
 #pragma omp for nowait schedule(static)
-            for (int64_t i = 0; i < n_gu; ++i) a_gu |= group_units[i] | (u_hi - group_units[i]);
-#pragma omp for nowait schedule(static)
             for (int64_t u = 0; u < n_units; ++u) a_off |= unit_offsets[u + 1] - unit_offsets[u];
-#pragma omp for nowait schedule(static)
-            for (int64_t gi = 0; gi < n_groups; ++gi) {
-                const int64_t c = group_offsets[gi + 1] - group_offsets[gi];
-                a_grp |= c | (256 - c);                      // 0 <= group size <= 256
-            }
-            if (out_index) {
-#pragma omp for nowait schedule(static)
-                for (int64_t t = 0; t < n_trades; ++t) a_out |= out_index[t] | (t_hi - out_index[t]);
-            }
         }
         if (a_node < 0) verr = "cav_portfolio_upload: node index out of range";
-        else if (a_gu < 0) verr = "cav_portfolio_upload: unit id out of range";
-        else if ((a_off | a_grp | a_out) < 0)
-            verr = "cav_portfolio_upload: offsets not monotone, group larger than 256 trades or out_index out of range";
+        else if (a_off < 0) verr = "cav_portfolio_upload: unit offsets not monotone";
+        else if (piped && W.empty()) {
+            ctx->trade_check_pending = true;
+            ctx->chk_group_offsets = group_offsets; ctx->chk_group_units = group_units;
+            ctx->chk_groups = n_groups; ctx->chk_units = n_units;
+        } else verr = check_trade_arrays(n_trades, n_units, n_groups, n_comp, group_offsets, group_units, out_index);
     }
     // host buffers may be reused by the caller (and W is a local) unless the pipelined contract holds
     if (!ctx->async_upload || verr || !W.empty()) CK(cudaStreamSynchronize(ctx->stream));
@@ -877,10 +929,20 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
             pp.pos_of[r] = (unsigned char)q;
         }
     }
+    // the plan's own checks are short loops (tens of microseconds each at 25k units); a few threads keep this call shorter
+    // than the unit-array copies it runs beside
+    const int nth_plan = std::min(4, host_threads(n_krows + (int64_t)n_tiles * tile_size, 32768));
     int64_t covered = 0;
-    for (int64_t i = 0; i < (int64_t)n_tiles * tile_size; ++i) {
-        if (tile_units[i] < -1 || tile_units[i] >= ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: unit id out of range");
-        covered += tile_units[i] >= 0;
+    {
+        int64_t bad_unit = 0;
+        const int64_t hi = ctx->n_units - 1;
+#pragma omp parallel for num_threads(nth_plan) schedule(static) reduction(+ : covered) reduction(| : bad_unit)
+        for (int64_t i = 0; i < (int64_t)n_tiles * tile_size; ++i) {
+            const int64_t u = tile_units[i];
+            bad_unit |= (u + 1) | (hi - u);                  // -1 <= u <= n_units - 1
+            covered += u >= 0;
+        }
+        if (bad_unit < 0) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: unit id out of range");
     }
     if (covered != ctx->n_units) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: every unit must belong to exactly one tile");
     const std::vector<int64_t>& h_off = ctx->h_unit_offsets;
@@ -913,23 +975,33 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     if (n_pair_rows) std::memcpy(st_pairs, pairs, sizeof(int) * 2 * (size_t)n_pair_rows);
     for (int t = 0; t < n_tiles; ++t) { npos[t] = 0; masks[t] = 0xFFFFFFFFu; }
     if (tile_mask) std::memcpy(masks, tile_mask, sizeof(unsigned) * n_tiles);
+    {
+        int err = 0;
+#pragma omp parallel for num_threads(nth_plan) schedule(static) reduction(max : err)
+        for (int t = 0; t < n_tiles; ++t) {
+            int e = 0;
+            if (tile_kstart[t] < 0 || tile_kcount[t] < 0 || (int64_t)tile_kstart[t] + tile_kcount[t] > n_krows) e = 3;
+            int64_t len = -1;                                  // all units of a tile have the same number of terms
+            for (int s = 0; s < tile_size; ++s) {
+                const int u = tile_units[(size_t)t * tile_size + s];
+                if (u < 0) continue;
+                const int64_t l = h_off[u + 1] - h_off[u];
+                if (len >= 0 && l != len) e = e > 2 ? e : 2;
+                len = l;
+            }
+            npos[t] = (int)(len < 0 ? 0 : (len > 256 ? 256 : len));
+            if (len > 255) e = e > 1 ? e : 1;
+            err = err > e ? err : e;
+        }
+        if (err == 3) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K range out of bounds");
+        if (err == 2) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: units of a tile differ in length");
+        if (err == 1) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 255 terms per unit");
+    }
     int cls_prev = 0;
     int class_begin[CAV_N_CLASSES + 1];
     for (int c = 0; c <= CAV_N_CLASSES; ++c) class_begin[c] = n_tiles;
     class_begin[0] = 0;
     for (int t = 0; t < n_tiles; ++t) {
-        if (tile_kstart[t] < 0 || tile_kcount[t] < 0 || (int64_t)tile_kstart[t] + tile_kcount[t] > n_krows)
-            return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: K range out of bounds");
-        int64_t len = -1;                                  // all units of a tile have the same number of terms
-        for (int s = 0; s < tile_size; ++s) {
-            const int u = tile_units[(size_t)t * tile_size + s];
-            if (u < 0) continue;
-            const int64_t l = h_off[u + 1] - h_off[u];
-            if (len >= 0 && l != len) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: units of a tile differ in length");
-            len = l;
-        }
-        npos[t] = (int)(len < 0 ? 0 : len);
-        if (npos[t] > 255) return fail(ctx, CAV_E_UNSUPPORTED, "cav_portfolio_set_tiles: more than 255 terms per unit");
         const int cls = cav_tile_class(masks[t]);
         if (cls < cls_prev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: tiles must be ordered by size class");
         for (int c = cls_prev + 1; c <= cls; ++c) class_begin[c] = t;
@@ -939,7 +1011,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     // lives in the same chunk (groups are independent: checked by a few host threads)
     {
         int err = 0;
-#pragma omp parallel for num_threads(host_threads(4 * n_krows)) schedule(dynamic, 64) reduction(max : err)
+#pragma omp parallel for num_threads(nth_plan) schedule(dynamic, 64) reduction(max : err)
         for (int t = 0; t < n_tiles; ++t) {
             if (t > 0 && tile_kstart[t] == tile_kstart[t - 1] && tile_kcount[t] == tile_kcount[t - 1] && npos[t] == npos[t - 1]) continue;
             int prev = 0, in_chunk = 0, e = 0;
@@ -963,7 +1035,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     {
         int bad_row = 0;
         int2* pk = pack;
-#pragma omp parallel for num_threads(host_threads(4 * n_krows)) schedule(static) reduction(| : bad_row)
+#pragma omp parallel for num_threads(nth_plan) schedule(static) reduction(| : bad_row)
         for (int64_t k = 0; k < n_krows; ++k) {
             bad_row |= (k_row[k] < 0) | (k_row[k] >= n_rows) | (k_pos[k] < 0) | (k_pos[k] > 255) | (k_coef[k] < 0) |
                        (k_coef[k] > 5) | (k_coef2 && k_coef2[k] > 5);
@@ -1001,6 +1073,7 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
 
 static int ensure_row_tables(cav_ctx* ctx) {
     if (ctx->row_tables_valid) return CAV_OK;
+    { int rc = settle_trade_checks(ctx); if (rc) return rc; }
     CK(wait_trade_arrays(ctx));
     CK(dev_alloc(ctx, &ctx->row_units, (size_t)ctx->n_trades * ctx->n_comp));
     CK(dev_alloc(ctx, &ctx->row_weight, (size_t)ctx->n_trades * ctx->n_comp));
@@ -1119,6 +1192,8 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     else launch_units<6>(ctx, a, want_d, want_g, grid);
     CK(cudaGetLastError());
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[1], ctx->stream));
+    // pipelined upload: the per-trade arrays are checked now, while the units kernel runs
+    { int rc = settle_trade_checks(ctx); if (rc) return rc; }
     if (!ctx->direct && (pv || delta || gamma) && ctx->n_groups > 0) {
         // gamma rows: group-ordered streaming kernel; PV / delta rows: row-ordered gather (coalesced small rows).
         // With both requested the small, latency-bound row gather runs on a side stream next to the DRAM-bound gamma
@@ -1145,17 +1220,32 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
             CK(cudaGetLastError());
         }
         if (gamma) {
+            // The chunks of a pipelined upload are expanded as they land.  Odd chunks go to a side stream so that the
+            // partial last wave of one chunk's kernel overlaps the first waves of the next instead of draining the
+            // machine between them (the kernels write disjoint rows).
             const int chunks = ctx->up_chunks > 0 ? ctx->up_chunks : 1;
+            const int n_streams = [] { const char* e = std::getenv("CAV_EXPAND_STREAMS"); return e ? std::atoi(e) : 2; }();
+            const bool alt = chunks > 1 && n_streams > 1;
+            cudaStream_t side = ctx->aux[1];
+            if (alt) {
+                CK(cudaEventRecord(ctx->ev_units, ctx->stream));
+                CK(cudaStreamWaitEvent(side, ctx->ev_units, 0));
+            }
             for (int c = 0; c < chunks; ++c) {
                 const int64_t g0 = ctx->up_chunks > 0 ? ctx->up_group[c] : 0;
                 const int64_t g1 = ctx->up_chunks > 0 ? ctx->up_group[c + 1] : ctx->n_groups;
-                if (ctx->up_chunks > 0) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[c], 0));
+                cudaStream_t st = (alt && (c & 1)) ? side : ctx->stream;
+                if (ctx->up_chunks > 0) CK(cudaStreamWaitEvent(st, ctx->ev_chunk[c], 0));
                 switch (ctx->n_comp) {
-                    case 1: launch_expand<1>(ctx, nullptr, nullptr, gamma, g0, g1); break;
-                    case 2: launch_expand<2>(ctx, nullptr, nullptr, gamma, g0, g1); break;
-                    case 3: launch_expand<3>(ctx, nullptr, nullptr, gamma, g0, g1); break;
-                    default: launch_expand<4>(ctx, nullptr, nullptr, gamma, g0, g1); break;
+                    case 1: launch_expand<1>(ctx, st, nullptr, nullptr, gamma, g0, g1); break;
+                    case 2: launch_expand<2>(ctx, st, nullptr, nullptr, gamma, g0, g1); break;
+                    case 3: launch_expand<3>(ctx, st, nullptr, nullptr, gamma, g0, g1); break;
+                    default: launch_expand<4>(ctx, st, nullptr, nullptr, gamma, g0, g1); break;
                 }
+            }
+            if (alt) {
+                CK(cudaEventRecord(ctx->ev_join[1], side));
+                CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join[1], 0));
             }
             CK(cudaGetLastError());
         }
@@ -1206,6 +1296,7 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
     if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_delta_gemm: no portfolio uploaded");
     if (!delta_dev) return fail(ctx, CAV_E_INVALID, "cav_portfolio_delta_gemm: delta_dev is null");
     CK(cudaSetDevice(ctx->device));
+    { int rc = settle_trade_checks(ctx); if (rc) return rc; }
     if (ctx->n_units == 0) return CAV_OK;
     const int Gp = (ctx->G + 15) & ~15;        // row stride of Q: multiple of 16 nodes (32-byte A loads x 4 k-steps)
     CK(dev_alloc(ctx, &ctx->Qmat, (size_t)ctx->n_units * Gp));
@@ -1235,10 +1326,10 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
     if (!ctx->direct && ctx->n_groups > 0) {
         CK(wait_trade_arrays(ctx));
         switch (ctx->n_comp) {
-            case 1: launch_expand<1>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
-            case 2: launch_expand<2>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
-            case 3: launch_expand<3>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
-            default: launch_expand<4>(ctx, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
+            case 1: launch_expand<1>(ctx, ctx->stream, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
+            case 2: launch_expand<2>(ctx, ctx->stream, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
+            case 3: launch_expand<3>(ctx, ctx->stream, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
+            default: launch_expand<4>(ctx, ctx->stream, pv_dev, delta_dev, nullptr, 0, ctx->n_groups); break;
         }
         CK(cudaGetLastError());
     }

@@ -61,10 +61,15 @@ int         cav_timer_stop(cav_ctx* ctx, float* elapsed_ms);   /* synchronises *
 int         cav_set_stream(cav_ctx* ctx, void* cuda_stream);
 /* Pipelined host->device upload for the end-to-end call sequence upload -> [set_tiles] -> value.  The reference
  * rebuilds every Position's inputs on the host before it values it (position.py:55, engine.py:2519-2539); here
- * the per-trade arrays (comp_weight, out_index) travel on a side copy stream in 4 group-aligned chunks while the
+ * the per-trade arrays (comp_weight, out_index) travel on a side copy stream in group-aligned chunks while the
  * unit arrays, the tile plan and the units kernel proceed, and the expansion kernel of a chunk starts as soon as
- * its weights have landed; neither cav_portfolio_upload nor cav_portfolio_set_tiles waits for its copies (the
- * host-side validation still runs, concurrently with them).  Contract when enabled: every HOST buffer handed to
+ * its weights have landed (chunks alternate between two streams so that one chunk's last wave overlaps the next
+ * chunk's first); neither cav_portfolio_upload nor cav_portfolio_set_tiles waits for its copies.  Host-side
+ * validation still covers every index a kernel dereferences, but is split: cav_portfolio_upload checks what the
+ * units kernel reads (node indices, unit offsets) and fails as usual; the per-trade arrays (group_offsets,
+ * group_units, out_index) are checked by the next valuation call after it has launched the units kernel and
+ * before it launches anything that reads them, or by cav_sync - that call then returns CAV_E_INVALID with the
+ * same message and the portfolio is discarded.  Contract when enabled: every HOST buffer handed to
  * cav_portfolio_upload must stay valid and unmodified until the next cav_portfolio_value_host or cav_sync call on
  * this context has returned (the tile plan is staged through a pinned arena of the library and may be reused at
  * once).  Off by default.  Results are bit-identical either way. */

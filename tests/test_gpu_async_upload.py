@@ -80,3 +80,41 @@ def test_async_upload_is_bit_identical_and_race_free(ref_curves):
     b = _value(ctx, small, 40)
     assert torch.equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     ctx.close()
+
+
+def test_bad_per_trade_indices_are_rejected_before_any_kernel_reads_them(ref_curves):
+    """Synchronous upload: the upload call itself fails.  Pipelined upload: the per-trade arrays are checked on the
+    host after the units kernel has been launched, so the error comes from the valuation (or cav_sync) and the
+    portfolio is discarded - no expansion kernel ever sees the bad index."""
+    from adrates_b200.error import LibError
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = build_model(cv).curves.GBP_OIS_SONIA
+    n = 60_000
+    good = _pinned(flatten_book(make_book(curve, n, seed=4), dedup=True))
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    ref = _value(ctx, good, n)
+    for field, value, msg in (("out_index", n, "out_index"), ("out_index", -1, "out_index"),
+                              ("group_units", good.n_units, "unit id")):
+        bad = copy.copy(good)
+        arr = getattr(good, field).copy()
+        arr[len(arr) // 2] = value
+        setattr(bad, field, arr)
+        ctx.set_async_upload(False)
+        with pytest.raises(LibError, match=msg):
+            ctx.portfolio_upload(bad)
+        with pytest.raises(LibError):
+            ctx.portfolio_value_host(MASK)
+        ctx.set_async_upload(True)
+        bad = _pinned(bad)
+        ctx.portfolio_upload(bad)                       # accepted: only the unit arrays are checked here
+        with pytest.raises(LibError, match=msg):
+            ctx.portfolio_value_host(MASK)
+        with pytest.raises(LibError):
+            ctx.portfolio_value_host(MASK)              # ... and the portfolio is gone
+        ctx.portfolio_upload(bad)
+        with pytest.raises(LibError, match=msg):
+            ctx.sync()                                  # cav_sync settles the check too
+        got = _value(ctx, good, n)                      # the context is still usable
+        assert torch.equal(got[2], ref[2]) and np.array_equal(got[3], ref[3])
+    ctx.close()

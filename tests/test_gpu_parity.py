@@ -335,6 +335,55 @@ def test_tile_mask_too_small_is_rejected(ref_curves):
     ctx.close()
 
 
+def test_malformed_tile_plans_are_rejected(ref_curves):
+    """cav_portfolio_set_tiles checks everything the tiled kernel dereferences; each defect has its own message."""
+    import copy
+    from adrates_b200.error import LibError
+    from adrates_b200.synthetic import make_book, flatten_book
+    cv = ref_curves["gbp_readme_lzr"]
+    curve = _curve(cv)
+    flat = flatten_book(make_book(curve, 4000, seed=6), dedup=True)
+    tp0 = flat.tile_plan
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    flat_nt = copy.copy(flat)
+    flat_nt.tile_plan = None
+    ctx.portfolio_upload(flat_nt)
+
+    def broken(field, fn):
+        tp = copy.copy(tp0)
+        a = np.array(getattr(tp0, field), copy=True)
+        fn(a)
+        setattr(tp, field, a)
+        return tp
+
+    lens = np.diff(flat.unit_offsets)
+    full = int(np.flatnonzero(np.asarray(tp0.tile_units).reshape(-1, 16)[:, 1] >= 0)[0])   # a tile with >= 2 units
+    first = int(tp0.tile_units[16 * full])
+    other = int(np.flatnonzero(lens != lens[first])[0])          # a unit with another number of terms
+    cases = [
+        (broken("tile_units", lambda a: a.__setitem__(0, flat.n_units)), "unit id out of range"),
+        (broken("tile_units", lambda a: a.__setitem__(0, -2)), "unit id out of range"),
+        (broken("tile_units", lambda a: a.__setitem__(0, -1)), "exactly one tile"),
+        (broken("tile_units", lambda a: a.__setitem__(16 * full + 1, other)), "differ in length"),
+        (broken("tile_kcount", lambda a: a.__setitem__(len(a) - 1, len(tp0.k_row) + 1)), "K range out of bounds"),
+        (broken("tile_kstart", lambda a: a.__setitem__(0, -1)), "K range out of bounds"),
+        (broken("k_row", lambda a: a.__setitem__(0, 10 ** 6)), "bad K row"),
+        (broken("k_coef", lambda a: a.__setitem__(0, 6)), "bad K row"),
+        (broken("perm", lambda a: a.__setitem__(0, a[1])), "not a permutation"),
+    ]
+    for tp, msg in cases:
+        with pytest.raises(LibError, match=msg):
+            ctx.portfolio_set_tiles(tp)
+    ctx.portfolio_set_tiles(tp0)                                  # the context still takes the good plan
+    agg = ctx.portfolio_value_host(MASK)
+    ctx.portfolio_upload(flat_nt)                                 # ... which gives what the plan-less kernel gives
+    agg0 = ctx.portfolio_value_host(MASK)
+    scale = np.abs(agg0) + 1e-6 * np.abs(agg0).max()
+    assert np.max(np.abs(agg - agg0) / scale) < 1e-10
+    ctx.close()
+
+
 def test_delta_chain_gemm_matches_fused_path(ref_curves):
     """The DMMA chain-rule GEMM (delta = Q * 1e-4 J/d) against the fused per-cashflow chain, both layouts."""
     from adrates_b200.synthetic import make_book, flatten_book
