@@ -100,6 +100,7 @@ struct cav_ctx {
     int* check_flag = nullptr;
     int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *pairs = nullptr;
     int2* k_pack = nullptr;
+    char* tile_arena = nullptr;        // the tile plan's device arrays are slices of one arena: one host->device copy per plan
     PillarPerm pp;
     double* Tsym = nullptr;
     bool tiles_valid = false;
@@ -464,9 +465,9 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->sq_node); dev_free(ctx, &ctx->sq_w); dev_free(ctx, &ctx->sq_term); dev_free(ctx, &ctx->sc_dfq);
     dev_free(ctx, &ctx->cf_x); dev_free(ctx, &ctx->cf_d); dev_free(ctx, &ctx->cf_t); dev_free(ctx, &ctx->cf_amt);
     dev_free(ctx, &ctx->cf_pv); dev_free(ctx, &ctx->cf_off);
-    dev_free(ctx, &ctx->tile_mask); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag);
-    dev_free(ctx, &ctx->Qmat); dev_free(ctx, &ctx->tile_units); dev_free(ctx, &ctx->tile_kstart); dev_free(ctx, &ctx->tile_kcount); dev_free(ctx, &ctx->tile_npos);
-    dev_free(ctx, &ctx->k_pack); dev_free(ctx, &ctx->pairs); dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
+    dev_free(ctx, &ctx->tile_arena); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag);
+    dev_free(ctx, &ctx->Qmat);
+    dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
     cudaEventDestroy(ctx->ev0);
@@ -529,7 +530,10 @@ int cav_last_kernel_ms(cav_ctx* ctx, float* ms /* [3]: units, expand, totals */)
     if (ctx->evk_n < 4) return fail(ctx, CAV_E_STATE, "cav_last_kernel_ms: no profiled valuation");
     CK(cudaSetDevice(ctx->device));
     CK(cudaEventSynchronize(ctx->evk[3]));
-    for (int i = 0; i < 3; ++i) CK(cudaEventElapsedTime(&ms[i], ctx->evk[i], ctx->evk[i + 1]));
+    // stream order of a valuation: units | totals | expansion
+    CK(cudaEventElapsedTime(&ms[0], ctx->evk[0], ctx->evk[1]));
+    CK(cudaEventElapsedTime(&ms[2], ctx->evk[1], ctx->evk[2]));
+    CK(cudaEventElapsedTime(&ms[1], ctx->evk[2], ctx->evk[3]));
     return CAV_OK;
 }
 
@@ -1046,13 +1050,15 @@ int cav_portfolio_set_tiles(cav_ctx* ctx, int n_tiles, int tile_size, const int3
     }
     for (int i = 0; i < 2 * n_pair_rows; ++i)
         if (pairs[i] < 0 || pairs[i] >= ctx->G) return fail(ctx, CAV_E_INVALID, "cav_portfolio_set_tiles: pair node out of range");
-    CK(upload(ctx, &ctx->tile_units, (const int*)st_units, (size_t)n_tiles * tile_size));
-    CK(upload(ctx, &ctx->tile_kstart, (const int*)st_kstart, (size_t)n_tiles));
-    CK(upload(ctx, &ctx->tile_kcount, (const int*)st_kcount, (size_t)n_tiles));
-    CK(upload(ctx, &ctx->tile_npos, (const int*)npos, (size_t)n_tiles));
-    CK(upload(ctx, &ctx->k_pack, (const int2*)pack, (size_t)n_krows));
-    CK(upload(ctx, &ctx->pairs, (const int*)st_pairs, (size_t)2 * n_pair_rows));
-    CK(upload(ctx, &ctx->tile_mask, (const unsigned*)masks, (size_t)n_tiles));
+    // one copy of the staged plan; the device pointers are the same slices of the device arena
+    CK(dev_alloc(ctx, &ctx->tile_arena, need));
+    if (need) CK(cudaMemcpyAsync(ctx->tile_arena, ctx->tile_stage, need, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        auto dev = [&](const void* staged) { return ctx->tile_arena + ((const char*)staged - ctx->tile_stage); };
+        ctx->tile_units = (int*)dev(st_units); ctx->tile_kstart = (int*)dev(st_kstart); ctx->tile_kcount = (int*)dev(st_kcount);
+        ctx->tile_npos = (int*)dev(npos); ctx->tile_mask = (unsigned*)dev(masks); ctx->k_pack = (int2*)dev(pack);
+        ctx->pairs = (int*)dev(st_pairs);
+    }
     CK(cudaEventRecord(ctx->ev_tiles, ctx->stream));
     CK(issue_trade_chunks(ctx));
     if (!ctx->async_upload) CK(cudaStreamSynchronize(ctx->stream));
@@ -1120,7 +1126,7 @@ static int build_sym_tables(cav_ctx* ctx, bool defer_check) {
     // silently drop Greeks): checked on the device for every new plan / new tables
     CK(dev_alloc(ctx, &ctx->check_flag, (size_t)1));
     CK(cudaMemsetAsync(ctx->check_flag, 0, sizeof(int), ctx->stream));
-    k_check_tile_masks<<<(ctx->n_tiles + 127) / 128, 128, 0, ctx->stream>>>(ctx->n_tiles, ctx->tile_kstart, ctx->tile_kcount,
+    k_check_tile_masks<<<(ctx->n_tiles + 3) / 4, 128, 0, ctx->stream>>>(ctx->n_tiles, ctx->tile_kstart, ctx->tile_kcount,
                                                                           ctx->tile_mask, ctx->k_pack, ctx->row_masks,
                                                                           ctx->check_flag);
     ctx->launches++;
@@ -1192,6 +1198,15 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     else launch_units<6>(ctx, a, want_d, want_g, grid);
     CK(cudaGetLastError());
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[1], ctx->stream));
+    // the portfolio totals depend on the units stage only: reduced here, ahead of the long expansion, so that nothing but
+    // the read-back is left behind it
+    double* const agg_dst = agg_dev ? agg_dev : ctx->agg;
+    if (need_agg) {
+        k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, agg_dst);
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    if (ctx->profile) CK(cudaEventRecord(ctx->evk[2], ctx->stream));
     // pipelined upload: the per-trade arrays are checked now, while the units kernel runs
     { int rc = settle_trade_checks(ctx); if (rc) return rc; }
     if (!ctx->direct && (pv || delta || gamma) && ctx->n_groups > 0) {
@@ -1261,19 +1276,12 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
             CK(cudaGetLastError());
         }
     }
-    if (ctx->profile) CK(cudaEventRecord(ctx->evk[2], ctx->stream));
-    if (need_agg) {
-        double* dst = agg_dev ? agg_dev : ctx->agg;
-        k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, dst);
-        ctx->launches++;
-        CK(cudaGetLastError());
-        if (ctx->profile) { CK(cudaEventRecord(ctx->evk[3], ctx->stream)); ctx->evk_n = 4; }
-        if (agg_host) {
-            if (ctx->mask_check_pending)
-                CK(cudaMemcpyAsync(&ctx->h_check_flag, ctx->check_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaMemcpyAsync(agg_host, dst, sizeof(double) * CAV_NOUT, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-        }
+    if (ctx->profile) { CK(cudaEventRecord(ctx->evk[3], ctx->stream)); if (need_agg) ctx->evk_n = 4; }
+    if (agg_host) {
+        if (ctx->mask_check_pending)
+            CK(cudaMemcpyAsync(&ctx->h_check_flag, ctx->check_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(agg_host, agg_dst, sizeof(double) * CAV_NOUT, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
     }
     if (ctx->mask_check_pending) { int rc = finish_mask_check(ctx, agg_host == nullptr); if (rc) return rc; }
     return CAV_OK;

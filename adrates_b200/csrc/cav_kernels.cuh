@@ -344,13 +344,17 @@ __global__ void k_check_tile_masks(int n_tiles, const int* __restrict__ tile_kst
                                    const unsigned* __restrict__ tile_mask, const int2* __restrict__ k_pack,
                                    const unsigned* __restrict__ row_masks, int* flag)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    // warp per tile, lanes stride over its K rows (a thread per tile walked ~100 dependent loads: tens of microseconds
+    // in front of the units kernel on every new plan)
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (t >= n_tiles) return;
-    if (t > 0 && tile_kstart[t] == tile_kstart[t - 1] && tile_mask[t] == tile_mask[t - 1]) return;   // same group
+    if (t > 0 && tile_kstart[t] == tile_kstart[t - 1] && tile_kcount[t] == tile_kcount[t - 1] && tile_mask[t] == tile_mask[t - 1])
+        return;                                                                                          // same group
     const unsigned allowed = tile_mask[t];
+    const int k0 = tile_kstart[t], kc = tile_kcount[t];
     unsigned bad = 0u;
-    for (int k = 0; k < tile_kcount[t]; ++k) bad |= row_masks[k_pack[tile_kstart[t] + k].x] & ~allowed;
-    if (bad) atomicExch(flag, 1);
+    for (int k = lane; k < kc; k += 32) bad |= row_masks[k_pack[k0 + k].x] & ~allowed;
+    if (__any_sync(0xFFFFFFFFu, bad != 0u) && lane == 0) atomicExch(flag, 1);
 }
 
 struct SimtArgs {
