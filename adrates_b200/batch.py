@@ -646,6 +646,29 @@ class OISBook:
         # currency / index of the totals: those of the curve's calibration swaps (books are single-curve)
         return _result_from_totals(agg, mask, self.curve, self.curve._used_swaps[0]), rows
 
+    # ---- scenario revaluation (BASELINE config 4) ------------------------------------------------
+    def scenario_values(self, rates, device: int = 0, dedup: bool = True, pnl: bool = False, out=None):
+        """Trade values under S shocked curves in one device pass: `rates` is [S, R] decimal par rates
+        (`Model.scenario_rates(curve_name, shocks)`), the result a torch CUDA tensor [S, n_trades] in trade order
+        (pnl=True: minus the values on this book's own curve).  Row s equals the per-trade VALUE of this book built on
+        `model.scenario(curve_name, shocks[s])`."""
+        from .scenarios import scenario_values_flat
+        return scenario_values_flat(self.curve, self.flatten(dedup=dedup, tiles=False), rates, device, pnl, out)
+
+    def scenario_values_distributed(self, rates, device: int | None = None, dedup: bool = True, pnl: bool = False):
+        """Every rank of the initialised torch.distributed group calls this with the SAME book and rates; rank r values
+        its contiguous slice of the scenarios on its GPU.  No collective: returns (rows [S_r, n_trades], (lo, hi))."""
+        import os
+        import torch.distributed as dist
+        from .scenarios import check_rates, scenario_bounds
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        world = dist.get_world_size() if dist.is_initialized() else 1
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", rank))
+        rates = check_rates(self.curve, rates)
+        lo, hi = scenario_bounds(rates.shape[0], world)[rank]
+        return self.scenario_values(rates[lo:hi], device, dedup, pnl), (lo, hi)
+
     # ---- multi-GPU: one process per GPU, trades shard by rank, totals all-reduced (SURVEY 8e) ----
     def shard(self, rank: int, world: int) -> "OISBook":
         """The contiguous slice of this book rank `rank` of `world` owns, balanced by coupon count."""

@@ -7,6 +7,7 @@ curve builder are outside this path.
 """
 from __future__ import annotations
 
+import numpy as np
 from typing import Dict, List
 
 from .curves import OISCurve
@@ -120,6 +121,32 @@ class Model:
         new = Model(self.value_dt)   # like the reference, the copy holds only the shocked curve
         new.build_curve(name=new_name or curve_name, px_list=shocked, tenor_list=tenors, **params)
         return new
+
+    def scenario_rates(self, curve_name: str, shocks) -> np.ndarray:
+        """Par rates (decimal) of `curve_name` under a batch of shocks: row s is what
+        `self.scenario(curve_name, shocks[s]).curves[curve_name].swap_rates` would hold, without rebuilding S curves on
+        the host (models.py:507-557 applied S times).  `shocks`: a sequence whose items are floats (parallel) or
+        dicts tenor -> shock, or an array [S] (parallel) / [S, R] (per pillar, quote order); percentage points
+        (1bp = 0.01).  Input of the batched revaluation (`OISBook.scenario_values`, `Portfolio.scenario_values`)."""
+        if curve_name not in self._curve_params_dict:
+            raise ValueError(f"No stored parameters found for curve '{curve_name}'")
+        params = self._curve_params_dict[curve_name]
+        tenors, px = list(params["tenor_list"]), np.asarray(params["px_list"], dtype=np.float64)
+        if isinstance(shocks, np.ndarray) and shocks.dtype != object:
+            sh = np.asarray(shocks, dtype=np.float64)
+            if sh.ndim == 1:
+                sh = sh[:, None]
+            if sh.ndim != 2 or sh.shape[1] not in (1, len(px)):
+                raise ValueError(f"shocks must be [S] or [S, {len(px)}], got {shocks.shape}")
+            shocked = px[None, :] + sh
+        else:
+            shocked = np.empty((len(shocks), len(px)))
+            for s, shock in enumerate(shocks):
+                if isinstance(shock, dict):
+                    shocked[s] = [p + shock.get(t, 0.0) for t, p in zip(tenors, px)]
+                else:
+                    shocked[s] = px + float(shock)
+        return shocked / 100
 
     @property
     def curves(self) -> CurveAccessor:

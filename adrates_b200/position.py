@@ -245,3 +245,31 @@ class Portfolio:
                     risk=None if res.risk is None else total.risk + res.risk,
                     gamma=None if res.gamma is None else total.gamma + res.gamma)
         return total
+
+    def scenario_values(self, curve_name: str, shocks, pnl: bool = False, device: int = 0):
+        """Values of every position under a batch of shocks of `curve_name` in one device pass: what the loop
+        `[p.derivative.position(model.scenario(curve_name, s)).compute([VALUE]).value.amount for s in shocks for p in
+        positions]` returns, as a torch CUDA tensor [S, n_positions] (pnl=True: minus the unshocked values).  `shocks` as
+        in `Model.scenario_rates`.  All positions must share one Model and be valued on `curve_name` (OIS, bonds and
+        single-curve FRNs; the reference has no batched counterpart, models.py:507-557 + position.py:62-80)."""
+        from .scenarios import scenario_values_flat
+        import torch
+        if not self._positions:
+            return torch.empty(len(shocks), 0, dtype=torch.float64, device=torch.device("cuda", device))
+        if len({id(p.model) for p in self._positions}) != 1:
+            raise LibError("scenario_values: positions must share one Model")
+        model = self._positions[0].model
+        curve = model.curves[curve_name]
+        from .credit import BOND_CURVE
+        for p in self._positions:
+            d = p.derivative
+            kind = getattr(d, "derivative_type", None)
+            ok = kind in (InstrumentTypes.OIS_SWAP, InstrumentTypes.BOND) or (
+                kind == InstrumentTypes.FRN and BOND_CURVE.get(d._currency) == d._floating_index)
+            if not ok or p._engine._curve_for(d) is not curve:
+                raise LibError(f"scenario_values: every position must be an OIS / bond / single-curve FRN valued on {curve_name}")
+        fl = Flattener(curve)
+        for p in self._positions:
+            fl.add_trade(p.derivative)
+        flat = fl.finalize(dedup=len(self._positions) > 1)
+        return scenario_values_flat(curve, flat, model.scenario_rates(curve_name, shocks), device, pnl)

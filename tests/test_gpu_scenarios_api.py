@@ -1,0 +1,70 @@
+"""Public scenario-revaluation calls against the reference's own way of doing it: Model.scenario (rebuilt curve,
+models.py:507-557) + Position.compute([VALUE]) per trade and scenario (position.py:62-80)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from adrates_b200 import RequestTypes, batch as B  # noqa: E402
+from adrates_b200.error import LibError  # noqa: E402
+from adrates_b200.position import Portfolio  # noqa: E402
+from tests.test_batch_cpu import CONVS, _random_book  # noqa: E402
+from tests.util_trades import build_model, make_trade  # noqa: E402
+
+TOL = 1e-10
+SHOCKS = [0.01, -0.25, {"10Y": 0.05, "2Y": -0.03}, {"1W": 0.2, "50Y": -0.1}, 0.0]
+
+
+def test_portfolio_scenario_values_match_the_scenario_loop(ref_curves, ref_trades):
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    specs = [s for s in ref_trades if s["curve"] == "gbp_readme_lzr"]
+    swaps = [make_trade(s, cv) for s in specs]
+    pf = Portfolio([sw.position(model) for sw in swaps])
+    got = pf.scenario_values(cv["name"], SHOCKS).cpu().numpy()
+    assert got.shape == (len(SHOCKS), len(swaps))
+    for s, shock in enumerate(SHOCKS):
+        shocked = model.scenario(cv["name"], shock)
+        for i, sw in enumerate(swaps):
+            ref = sw.position(shocked).compute([RequestTypes.VALUE]).value.amount
+            assert abs(got[s, i] - ref) <= TOL * max(abs(ref), specs[i]["notional"]), (shock, specs[i]["id"])
+    pnl = pf.scenario_values(cv["name"], SHOCKS, pnl=True).cpu().numpy()
+    base = got[-1]                                              # the 0.0 shock
+    scale = np.maximum(np.abs(got), np.array([s["notional"] for s in specs])[None, :])
+    assert np.max(np.abs(pnl - (got - base[None, :])) / scale) < TOL
+    assert np.max(np.abs(pnl[-1]) / scale[-1]) < 1e-13          # zero shock: the two kernels differ by summation order only
+    assert Portfolio([]).scenario_values(cv["name"], SHOCKS).shape == (len(SHOCKS), 0)
+    other = build_model(cv)
+    with pytest.raises(LibError, match="share one Model"):
+        Portfolio([swaps[0].position(model), swaps[1].position(other)]).scenario_values(cv["name"], SHOCKS)
+
+
+@pytest.mark.parametrize("conv", ["annual_act365", "lagged"])
+def test_array_book_scenario_values_match_books_on_rebuilt_curves(ref_curves, conv):
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    curve = model.curves[cv["name"]]
+    rng = np.random.default_rng(5)
+    n = 400
+    spec = _random_book(curve, n, rng, spread=(conv != "annual_act365"))
+    book = B.OISBook.from_arrays(curve, **spec, **CONVS[conv])
+    rates = model.scenario_rates(cv["name"], SHOCKS)
+    for dedup in ((True,) if conv == "lagged" else (True, False)):
+        got = book.scenario_values(rates, dedup=dedup).cpu().numpy()
+        assert got.shape == (len(SHOCKS), n)
+        for s, shock in enumerate(SHOCKS):
+            shocked_curve = model.scenario(cv["name"], shock).curves[cv["name"]]
+            _, rows = B.OISBook.from_arrays(shocked_curve, **spec, **CONVS[conv]).compute([RequestTypes.VALUE], dedup=dedup)
+            ref = rows["pv"].cpu().numpy()
+            assert np.max(np.abs(got[s] - ref) / np.maximum(np.abs(ref), spec["notional"])) < TOL, (shock, dedup)
+    # no process group: the distributed call values every scenario on this rank
+    rows, (lo, hi) = book.scenario_values_distributed(rates, device=0)
+    assert (lo, hi) == (0, len(SHOCKS)) and np.array_equal(rows.cpu().numpy(), book.scenario_values(rates).cpu().numpy())
+    out = torch.empty(len(SHOCKS), n, dtype=torch.float64, device="cuda")
+    assert book.scenario_values(rates, out=out) is out
+    with pytest.raises(LibError):
+        book.scenario_values(rates[:, :5])
+    with pytest.raises(LibError):
+        book.scenario_values(rates, out=torch.empty(2, n, dtype=torch.float64, device="cuda"))
