@@ -1424,13 +1424,24 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
         k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
     else
         k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
-    dim3 ge((unsigned)((ctx->n_trades + SX_T - 1) / SX_T), (unsigned)((n_scen + SX_T - 1) / SX_T));
-    const size_t sx_smem = (size_t)SX_T * (SX_T + 1) * sizeof(double);
-    switch (ctx->n_comp) {
-        case 1: k_scen_expand<1><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
-        case 2: k_scen_expand<2><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
-        case 3: k_scen_expand<3><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
-        default: k_scen_expand<4><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+    const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 2; }();
+    if (expand_variant == 2 && n_scen % 2 == 0) {       // 16-byte reads of the unit values need an even row length
+        dim3 ge((unsigned)((ctx->n_trades + SX2_R - 1) / SX2_R), (unsigned)((n_scen + SX2_S - 1) / SX2_S));
+        switch (ctx->n_comp) {
+            case 1: k_scen_expand2<1><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            case 2: k_scen_expand2<2><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            case 3: k_scen_expand2<3><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            default: k_scen_expand2<4><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+        }
+    } else {
+        dim3 ge((unsigned)((ctx->n_trades + SX_T - 1) / SX_T), (unsigned)((n_scen + SX_T - 1) / SX_T));
+        const size_t sx_smem = (size_t)SX_T * (SX_T + 1) * sizeof(double);
+        switch (ctx->n_comp) {
+            case 1: k_scen_expand<1><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            case 2: k_scen_expand<2><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            case 3: k_scen_expand<3><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            default: k_scen_expand<4><<<ge, 256, sx_smem, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+        }
     }
     ctx->launches += 3;
     CK(cudaGetLastError());

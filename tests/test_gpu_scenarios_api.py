@@ -68,3 +68,25 @@ def test_array_book_scenario_values_match_books_on_rebuilt_curves(ref_curves, co
         book.scenario_values(rates[:, :5])
     with pytest.raises(LibError):
         book.scenario_values(rates, out=torch.empty(2, n, dtype=torch.float64, device="cuda"))
+
+
+@pytest.mark.parametrize("n_scen", [2, 38, 130, 256])
+def test_scenario_expansion_kernels_agree_bitwise(ref_curves, monkeypatch, n_scen):
+    """Even scenario counts take the 32x128 expansion kernel with 16-byte reads, odd ones (and CAV_SCEN_EXPAND=1) the
+    64x64 kernel: same sums in the same order, so the matrices are identical, ragged tile edges included."""
+    from adrates_b200.synthetic import make_book, shocked_rate_scenarios
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    curve = model.curves[cv["name"]]
+    rng = np.random.default_rng(8)
+    n = 1237                                                    # not a multiple of 32: ragged last row tile
+    spec = _random_book(curve, n, rng)
+    book = B.OISBook.from_arrays(curve, **spec, **CONVS["annual_act365"])
+    rates = shocked_rate_scenarios(curve, n_scen)
+    out = {}
+    for variant in ("1", "2"):
+        monkeypatch.setenv("CAV_SCEN_EXPAND", variant)
+        out[variant] = book.scenario_values(rates).cpu().numpy()
+    assert np.array_equal(out["1"], out["2"])
+    odd = book.scenario_values(rates[: n_scen - 1]).cpu().numpy()     # odd count: always the 64x64 kernel
+    assert np.array_equal(odd, out["2"][: n_scen - 1])

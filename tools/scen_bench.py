@@ -20,9 +20,16 @@ ctx.portfolio_upload(flat)
 shocked = shocked_rate_scenarios(curve, a.scen)
 pnl = torch.empty(a.scen, a.trades, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
-for r in range(a.reps):
+ref = None
+for variant in ("1", "2", "1", "2"):
+  os.environ["CAV_SCEN_EXPAND"] = variant
+  for r in range(a.reps):
     t0 = time.perf_counter()
     ctx.scenarios(shocked, pnl.data_ptr())
     ctx.sync()
     dt = time.perf_counter() - t0
-    print(f"rep {r}: {dt*1e3:.2f} ms  {a.scen*a.trades/dt/1e9:.2f} G revaluations/s  units={flat.n_units} terms={flat.n_terms}")
+    if r == 0:
+        chk = pnl.sum().item()
+        ref = chk if ref is None else ref
+        assert chk == ref
+    print(f"expand variant {variant} rep {r}: {dt*1e3:.2f} ms  {a.scen*a.trades/dt/1e9:.2f} G revaluations/s  units={flat.n_units} terms={flat.n_terms}")
