@@ -1418,7 +1418,12 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
         CK(dev_alloc(ctx, &ctx->sc_dfq, (size_t)ctx->sq_n * S));
         dim3 gq((unsigned)ctx->sq_n, (unsigned)((n_scen + 127) / 128));
         k_scen_df<<<gq, 128, 0, ctx->stream>>>(n_scen, ctx->sq_node, ctx->sq_w, ctx->sc_L, ctx->sc_dfq);
-        k_scen_units_q<<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->sq_term, ctx->sc_dfq, ctx->sc_upv);
+        const int units_variant = [] { const char* e = std::getenv("CAV_SCEN_UNITS"); return e ? std::atoi(e) : 2; }();
+        if (units_variant == 2 && n_scen % 2 == 0) {    // two scenarios per thread, 16-byte gathers
+            dim3 gu2((unsigned)ctx->n_units, (unsigned)((n_scen / 2 + 127) / 128));
+            k_scen_units_q2<<<gu2, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->sq_term, ctx->sc_dfq, ctx->sc_upv);
+        } else
+            k_scen_units_q<<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->sq_term, ctx->sc_dfq, ctx->sc_upv);
         ctx->launches++;
     } else if (ctx->n_pairs == 2)
         k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);

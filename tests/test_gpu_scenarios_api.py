@@ -86,6 +86,7 @@ def test_scenario_expansion_kernels_agree_bitwise(ref_curves, monkeypatch, n_sce
     out = {}
     for variant in ("1", "2"):
         monkeypatch.setenv("CAV_SCEN_EXPAND", variant)
+        monkeypatch.setenv("CAV_SCEN_UNITS", variant)             # ... and the unit sums with two scenarios per thread
         out[variant] = book.scenario_values(rates).cpu().numpy()
     assert np.array_equal(out["1"], out["2"])
     odd = book.scenario_values(rates[: n_scen - 1]).cpu().numpy()     # odd count: always the 64x64 kernel

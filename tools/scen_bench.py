@@ -21,8 +21,8 @@ shocked = shocked_rate_scenarios(curve, a.scen)
 pnl = torch.empty(a.scen, a.trades, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
 ref = None
-for variant in ("1", "2", "1", "2"):
-  os.environ["CAV_SCEN_EXPAND"] = variant
+for variant in ("11", "21", "22", "11", "22"):
+  os.environ["CAV_SCEN_EXPAND"], os.environ["CAV_SCEN_UNITS"] = variant[0], variant[1]
   for r in range(a.reps):
     t0 = time.perf_counter()
     ctx.scenarios(shocked, pnl.data_ptr())
@@ -32,4 +32,4 @@ for variant in ("1", "2", "1", "2"):
         chk = pnl.sum().item()
         ref = chk if ref is None else ref
         assert chk == ref
-    print(f"expand variant {variant} rep {r}: {dt*1e3:.2f} ms  {a.scen*a.trades/dt/1e9:.2f} G revaluations/s  units={flat.n_units} terms={flat.n_terms}")
+    print(f"expand/units variant {variant} rep {r}: {dt*1e3:.2f} ms  {a.scen*a.trades/dt/1e9:.2f} G revaluations/s  units={flat.n_units} terms={flat.n_terms}")
