@@ -322,11 +322,19 @@ def main():
 
     # ---- secondary measurements (same book, device-resident inputs; reported under "extras") ----
     extras = {}
-    if not args.no_extra:
-        def timed(fn, reps=10):
+    if world > 1 and not args.no_extra:
+        # per-GPU side measurements: the N=1 run reports them; a multi-rank run keeps to the contract line (and to code
+        # every rank executes - a rank-0-only measurement must never sit behind a collective)
+        extras = {"skipped": "secondary per-GPU measurements are reported by the single-GPU run"}
+    if not args.no_extra and world == 1:
+        def timed(fn, reps=10, all_ranks=True):
+            # all_ranks=False: measurements only rank 0 takes - no collective there (the other ranks have left)
             for _ in range(3):
                 fn()
-            barrier()
+            if all_ranks:
+                barrier()
+            else:
+                torch.cuda.synchronize(dev)
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             for _ in range(reps):
@@ -356,7 +364,7 @@ def main():
                 for _ in range(5):
                     g_ms, g_fl = ctx3.portfolio_delta_gemm(pv.data_ptr(), dl.data_ptr())
                     best = g_ms if best is None else min(best, g_ms)
-                tot_ms = timed(lambda: ctx3.portfolio_delta_gemm(pv.data_ptr(), dl.data_ptr()), reps=5)
+                tot_ms = timed(lambda: ctx3.portfolio_delta_gemm(pv.data_ptr(), dl.data_ptr()), reps=5, all_ranks=False)
                 extras["chain_gemm_dmma"] = {
                     "units": ng, "gemm_ms": best, "gemm_tflops": g_fl / (best * 1e-3) / 1e12,
                     "dmma_peak_tflops_measured": 37.13, "tensor_pipe_frac": g_fl / (best * 1e-3) / 1e12 / 37.13,
@@ -378,7 +386,7 @@ def main():
             ctx2.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
             ctx2.portfolio_upload(sub)
             pnl = torch.empty(S, nt, dtype=torch.float64, device=dev)
-            ms = timed(lambda: ctx2.scenarios(shocked, pnl.data_ptr()), reps=3)
+            ms = timed(lambda: ctx2.scenarios(shocked, pnl.data_ptr()), reps=3, all_ranks=False)
             extras["scenarios_config4"] = {"scenarios": S, "trades": nt, "ms": ms, "revaluations_per_s": S * nt / ms * 1e3,
                                            "pnl_bytes": S * nt * 8,
                                            "note": "shocked curves re-bootstrapped on device (DFs only) + full revaluation (one exp per "
@@ -396,7 +404,7 @@ def main():
                 xbook = make_xccy_book(build_xccy_model(gx), 500_000, seed=11, spot=gx["spot_fx"])
                 xval = XccyBookValuer(xbook, device=local, stream=stream.cuda_stream)
                 x_prep = time.perf_counter() - t1
-                ms = timed(lambda: xval.value(), reps=10)
+                ms = timed(lambda: xval.value(), reps=10, all_ranks=False)
                 extras["xccy_config5"] = {"trades": xbook.n_trades, "ms_per_step": ms, "trades_per_s": xbook.n_trades / ms * 1e3,
                                           "units": int(xval.flat_for.n_units), "flatten_seconds_untimed": x_prep,
                                           "note": "per-trade PV + three 32-wide ladder rows written (776 B/trade); parity of "
