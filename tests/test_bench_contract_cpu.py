@@ -1,0 +1,61 @@
+"""Static checks of bench.py's multi-rank control flow (no GPU needed).
+
+One process per GPU: every collective (dist.barrier / all_reduce, and the helpers that wrap them) must be reached by
+every rank.  A collective inside an `if rank == 0:` block deadlocks the job - which is what the default multi-GPU
+command did while only `--no-extra` had been run on more than one GPU."""
+import ast
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _src():
+    with open(os.path.join(ROOT, "bench.py")) as f:
+        return f.read()
+
+
+def _is_rank0_test(node):
+    return (isinstance(node, ast.Compare) and isinstance(node.left, ast.Name) and node.left.id == "rank"
+            and len(node.ops) == 1 and isinstance(node.ops[0], ast.Eq)
+            and isinstance(node.comparators[0], ast.Constant) and node.comparators[0].value == 0)
+
+
+def _collective_calls(body):
+    bad = []
+    for stmt in body:
+        for n in ast.walk(stmt):
+            if not isinstance(n, ast.Call):
+                continue
+            f = n.func
+            if isinstance(f, ast.Name) and f.id == "barrier":
+                bad.append((n.lineno, "barrier()"))
+            if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "dist" \
+                    and f.attr in ("barrier", "all_reduce", "all_gather", "broadcast", "reduce"):
+                bad.append((n.lineno, f"dist.{f.attr}"))
+            if isinstance(f, ast.Name) and f.id == "timed":
+                kw = {k.arg: k.value for k in n.keywords}
+                v = kw.get("all_ranks")
+                if not (isinstance(v, ast.Constant) and v.value is False):
+                    bad.append((n.lineno, "timed(...) without all_ranks=False"))
+    return bad
+
+
+def test_no_collective_inside_rank0_only_blocks():
+    tree = ast.parse(_src())
+    found, bad = 0, []
+    for n in ast.walk(tree):
+        if isinstance(n, ast.If) and _is_rank0_test(n.test):
+            found += 1
+            bad += _collective_calls(n.body)
+    assert found >= 1
+    assert not bad, f"collectives only rank 0 would reach: {bad}"
+
+
+def test_contract_keys_and_flags_are_present():
+    src = _src()
+    for key in ('"metric"', '"value"', '"unit"', '"n_gpus"', '"steps"', '"warmup"', '"ms_per_step"', '"higher_is_better"',
+                '"scaling"', '"vs_baseline"', '"dtype"', '"data"', '"config"', '"clocks"', '"e2e"', '"gpu_launches"',
+                '"roofline"', '"cpu_baseline"', '"impl"'):
+        assert key in src, key
+    for flag in ("--gpus", "--steps", "--warmup", "--impl"):
+        assert flag in src, flag
