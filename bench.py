@@ -162,6 +162,19 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
     ap.add_argument("--scenarios", type=int, default=2000, help="shocked curves for the config-4 extra")
     args = ap.parse_args()
+    # A benchmark must never hold a GPU box hostage: if anything (a lost rank, a collective only some ranks reach)
+    # stalls the run, leave with an error instead of waiting for the launcher's limit.
+    deadline = float(os.environ.get("BENCH_DEADLINE_S", "1500"))
+    if deadline > 0:
+        import threading
+
+        def _expired():
+            sys.stderr.write(f"bench.py: no result after {deadline:.0f} s (BENCH_DEADLINE_S) - aborting this rank\n")
+            sys.stderr.flush()
+            os._exit(124)
+        t = threading.Timer(deadline, _expired)
+        t.daemon = True
+        t.start()
     if args.impl == "reference":
         return run_reference(args)
 

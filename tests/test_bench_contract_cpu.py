@@ -59,3 +59,17 @@ def test_contract_keys_and_flags_are_present():
         assert key in src, key
     for flag in ("--gpus", "--steps", "--warmup", "--impl"):
         assert flag in src, flag
+
+
+def test_deadline_watchdog_ends_a_stalled_run():
+    """BENCH_DEADLINE_S: a run that produces no result in time exits with 124 instead of hanging its launcher (checked
+    on the CPU arm with an absurd step count)."""
+    import subprocess
+    import sys
+    import time
+    env = dict(os.environ, BENCH_DEADLINE_S="2")
+    t0 = time.time()
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "100000000",
+                        "--warmup", "0"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=120)
+    assert r.returncode == 124 and time.time() - t0 < 60
+    assert "BENCH_DEADLINE_S" in r.stderr
