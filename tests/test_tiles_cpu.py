@@ -36,6 +36,26 @@ def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
     curve = OISCurve(vd, swaps, InterpTypes[cv["interp"]])
     book = make_book(curve, 400, seed=9, max_offset_bd=40)
     flat = flatten_book(book, dedup=dedup)
+    check_tile_gemm(flat, cv, book.notional)
+
+
+@pytest.mark.parametrize("dedup", [True, False])
+def test_tile_gemm_on_bond_books(ref_curves, dedup):
+    """The tile plan of an array-built bond book (annuity + one-term redemption units) through the same emulation."""
+    from adrates_b200.bond_book import BondBook
+    from tests.test_bond_book_cpu import BOND_CONVS, _random_bonds
+    cv = ref_curves["gbp_readme_lzr"]
+    vd, swaps = make_calibration_swaps(cv)
+    curve = OISCurve(vd, swaps, InterpTypes[cv["interp"]])
+    spec = _random_bonds(curve, 150, np.random.default_rng(4))
+    book = BondBook.from_arrays(curve, **spec, **BOND_CONVS["semi_act365"])
+    flat = book.flatten(dedup=dedup, tiles=False)
+    check_tile_gemm(flat, cv, spec["face_value"])
+
+
+def check_tile_gemm(flat, cv, notional):
+    """numpy emulation of the tiled Greeks kernel (coefficient tile x symmetric tables) on `flat` with the plan
+    `plan_tiles` gives it, against the per-term evaluation of the same flat arrays."""
     plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
     d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
     support = node_support_masks(plan["swap"], plan["prev"], plan["acc"])
@@ -96,7 +116,7 @@ def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
             v = sum(cw[t, k] * u_pv[ids[k]] for k in range(K))
             dd = sum(cw[t, k] * u_dl[ids[k]] for k in range(K))
             gg = sum(cw[t, k] * u_gm[ids[k]] for k in range(K))
-            N = book.notional[row]
+            N = notional[row]
             assert abs(v - pv[row]) <= 1e-12 * N
             assert np.max(np.abs(dd - dl[row])) <= 1e-12 * N * 1e-4 * 50
             assert np.max(np.abs(gg - gm[row])) <= 1e-12 * N * 1e-8 * 2500
