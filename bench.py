@@ -164,7 +164,7 @@ def main():
     args = ap.parse_args()
     # A benchmark must never hold a GPU box hostage: if anything (a lost rank, a collective only some ranks reach)
     # stalls the run, leave with an error instead of waiting for the launcher's limit.
-    deadline = float(os.environ.get("BENCH_DEADLINE_S", "1500"))
+    deadline = float(os.environ.get("BENCH_DEADLINE_S", "900"))
     if deadline > 0:
         import threading
 
