@@ -165,6 +165,8 @@ def main():
     # A benchmark must never hold a GPU box hostage: if anything (a lost rank, a collective only some ranks reach)
     # stalls the run, leave with an error instead of waiting for the launcher's limit.
     deadline = float(os.environ.get("BENCH_DEADLINE_S", "900"))
+    if "BENCH_DEADLINE_S" not in os.environ and args.impl == "reference":
+        deadline = max(deadline, 300.0 + 0.6 * (args.steps + args.warmup))    # ~0.2 s of CPU work per step
     if deadline > 0:
         import threading
 
