@@ -120,3 +120,53 @@ def check_tile_gemm(flat, cv, notional):
             assert abs(v - pv[row]) <= 1e-12 * N
             assert np.max(np.abs(dd - dl[row])) <= 1e-12 * N * 1e-4 * 50
             assert np.max(np.abs(gg - gm[row])) <= 1e-12 * N * 1e-8 * 2500
+
+
+def abi_plan_checks(flat, n_nodes):
+    """The host-side checks of cav_portfolio_set_tiles (csrc/cav_api.cu), restated: returns the largest number of K rows
+    any tile has inside one chunk of 32 term positions (limit 160)."""
+    from adrates_b200.tiles import tile_class
+    tp, off = flat.tile_plan, flat.unit_offsets
+    n_rows = 3 * n_nodes + len(tp.pairs) // 2
+    tu = tp.tile_units.reshape(-1, TM)
+    assert np.all((tu >= -1) & (tu < flat.n_units)) and int((tu >= 0).sum()) == flat.n_units
+    cls_prev, worst = 0, 0
+    for t in range(tp.n_tiles):
+        ks, kc = int(tp.tile_kstart[t]), int(tp.tile_kcount[t])
+        assert ks >= 0 and kc >= 0 and ks + kc <= len(tp.k_row)
+        lens = {int(off[u + 1] - off[u]) for u in tu[t] if u >= 0}
+        assert len(lens) == 1                                    # units of a tile have the same number of terms
+        npos = lens.pop()
+        assert npos <= 255
+        c = tile_class(tp.tile_mask[t])
+        assert c >= cls_prev                                     # tiles ordered by size class
+        cls_prev = c
+        prev, in_chunk = 0, 0
+        for k in range(kc):
+            p = int(tp.k_pos[ks + k])
+            assert prev <= p < npos                              # K rows ordered by position
+            in_chunk = in_chunk + 1 if (p >> 5) == (prev >> 5) else 1
+            worst = max(worst, in_chunk)
+            prev = p
+            if tp.k_coef2[ks + k] >= 0:
+                p2 = int(tp.k_pos2[ks + k])
+                assert 0 <= p2 < npos and (p2 >> 5) == (p >> 5)  # second contribution in the same chunk
+    assert worst <= 160
+    assert np.all((tp.k_row >= 0) & (tp.k_row < n_rows) & (tp.k_coef >= 0) & (tp.k_coef <= 5) & (tp.k_coef2 <= 5))
+    assert np.all((tp.pairs >= 0) & (tp.pairs < n_nodes)) and sorted(tp.perm.tolist()) == list(range(32))
+    return worst
+
+
+@pytest.mark.parametrize("dedup", [True, False])
+def test_plans_pass_the_abi_checks(ref_curves, dedup):
+    """Plans of OIS and bond books (annual books reach the 160-row limit exactly) satisfy what the C ABI verifies."""
+    from adrates_b200.bond_book import BondBook
+    from tests.test_bond_book_cpu import BOND_CONVS, _random_bonds
+    cv = ref_curves["gbp_readme_lzr"]
+    vd, swaps = make_calibration_swaps(cv)
+    curve = OISCurve(vd, swaps, InterpTypes[cv["interp"]])
+    G = curve.path_b_plan().n_nodes
+    assert abi_plan_checks(flatten_book(make_book(curve, 600, seed=3), dedup=dedup), G) <= 160
+    for conv in BOND_CONVS.values():
+        spec = _random_bonds(curve, 160, np.random.default_rng(31))
+        abi_plan_checks(BondBook.from_arrays(curve, **spec, **conv).flatten(dedup=dedup, tiles=True), G)
