@@ -47,7 +47,21 @@ _SIGS = {
     "cav_scenarios": (C.c_int, [_P, _P, C.c_int, _P]),
     "cav_curve_df": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_cashflow_pv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
+    "cav_book_from_arrays": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_uint32]),
+    "cav_book_info": (C.c_int, [_P, _P]),
+    "cav_book_read": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "cav_book_read_tiles": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
+E_INVALID, E_CUDA, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4
+TENOR_YEARS, TENOR_MONTHS = 0, 1
+
+
+class BookConv(C.Structure):
+    """cav_book_conv (include/adrates_b200.h)."""
+    _fields_ = [("value_dt", C.c_int64), ("fixed_freq_months", C.c_int32), ("float_freq_months", C.c_int32),
+                ("fixed_dc", C.c_int32), ("float_dc", C.c_int32), ("cal_type", C.c_int32), ("bd_type", C.c_int32),
+                ("dg_type", C.c_int32), ("end_of_month", C.c_int32), ("payment_lag", C.c_int32)]
+
 EXPORTS = tuple(_SIGS)
 
 _dll = None
@@ -106,7 +120,7 @@ class Context:
 
     def _ck(self, rc):
         if rc != 0:
-            raise LibError(f"adrates_b200 native error {rc}: {self._dll.cav_last_error(self._h).decode()}")
+            raise LibError(f"adrates_b200 native error {rc}: {self._dll.cav_last_error(self._h).decode()}", rc)
 
     # ---- misc
     def sync(self):
@@ -193,14 +207,36 @@ class Context:
         return pv, float(tot.value)
 
     # ---- portfolio
+    @staticmethod
+    def _checked_flat(flat):
+        """The arrays of a FlatPortfolio with the dtypes / lengths the C ABI reads (raw pointers cross it): arrays of the
+        right dtype and layout pass through untouched, anything else (an int64 node array, a strided view) is converted;
+        wrong lengths raise."""
+        def arr(a, dtype, n, name):
+            if a is None:
+                return None
+            b = np.ascontiguousarray(a, dtype=dtype)
+            if b.ndim != 1 or b.shape[0] != n:
+                raise LibError(f"FlatPortfolio.{name}: expected {n} entries of {np.dtype(dtype).name}, got shape {np.shape(a)}")
+            return b
+        U, T, N, G, P, K = flat.n_units, flat.n_terms, flat.n_trades, flat.n_groups, flat.n_pairs, flat.n_comp
+        return dict(unit_offsets=arr(flat.unit_offsets, np.int64, U + 1, "unit_offsets"), amt=arr(flat.amt, np.float64, T, "amt"),
+                    weight=arr(flat.weight, np.float64, T * P, "weight"), node=arr(flat.node, np.int32, T * P, "node"),
+                    comp_weight=arr(flat.comp_weight, np.float64, N * K, "comp_weight"),
+                    group_offsets=arr(flat.group_offsets, np.int64, G + 1, "group_offsets"),
+                    group_units=arr(flat.group_units, np.int32, G * K, "group_units"),
+                    out_index=arr(flat.out_index, np.int64, N, "out_index"),
+                    unit_weight=arr(flat.unit_weight, np.float64, U, "unit_weight"))
+
     def portfolio_upload(self, flat):
         """flat: adrates_b200.flatten.FlatPortfolio (numpy or pinned torch-backed arrays)."""
+        a = self._checked_flat(flat)
         self._ck(self._dll.cav_portfolio_upload(
-            self._h, flat.n_units, flat.n_terms, _ptr(flat.unit_offsets), flat.n_pairs, _ptr(flat.amt),
-            _ptr(flat.weight), _ptr(flat.node), flat.n_trades, flat.n_comp, _ptr(flat.comp_weight), flat.n_groups,
-            _ptr(flat.group_offsets), _ptr(flat.group_units), _ptr(flat.out_index), _ptr(flat.unit_weight)))
+            self._h, flat.n_units, flat.n_terms, _ptr(a["unit_offsets"]), flat.n_pairs, _ptr(a["amt"]),
+            _ptr(a["weight"]), _ptr(a["node"]), flat.n_trades, flat.n_comp, _ptr(a["comp_weight"]), flat.n_groups,
+            _ptr(a["group_offsets"]), _ptr(a["group_units"]), _ptr(a["out_index"]), _ptr(a["unit_weight"])))
         self._n_trades = flat.n_trades
-        self._flat_in_flight = flat          # async upload: the host arrays must outlive the copies
+        self._flat_in_flight = (flat, a)     # async upload: the host arrays must outlive the copies
         tp = getattr(flat, "tile_plan", None)
         if tp is not None:
             self.portfolio_set_tiles(tp)
@@ -218,6 +254,54 @@ class Context:
                                                    arrs[3].shape[0], _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]),
                                                    _ptr(pos2), _ptr(coef2), arrs[6].shape[0] // 2, _ptr(arrs[6]),
                                                    _ptr(mask), _ptr(perm)))
+
+    # ---- device-side flattening of array books
+    def book_from_arrays(self, conv: "BookConv", effective, termination=None, tenor=None, tenor_unit: int = TENOR_YEARS,
+                         fixed_sign=None, coupon=None, notional=None, spread=None, tiles: bool = True):
+        """cav_book_from_arrays: per-trade arrays -> flat book + tile plan in HBM (no flat arrays cross PCIe)."""
+        def arr(a, dtype):
+            return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+        eff = arr(effective, np.int64)
+        n = eff.shape[0]
+        term, ten = arr(termination, np.int64), arr(tenor, np.int32)
+        sg, cp, no, sp = (arr(a, np.float64) for a in (fixed_sign, coupon, notional, spread))
+        for name, a in (("termination", term), ("tenor", ten), ("fixed_sign", sg), ("coupon", cp), ("notional", no), ("spread", sp)):
+            if a is not None and a.shape != (n,):
+                raise LibError(f"book_from_arrays: {name} must have one entry per trade")
+        self._ck(self._dll.cav_book_from_arrays(self._h, C.addressof(conv), n, _ptr(eff), _ptr(term), _ptr(ten), int(tenor_unit),
+                                                _ptr(sg), _ptr(cp), _ptr(no), _ptr(sp), 1 if tiles else 0))
+        self._n_trades = n
+
+    def book_info(self) -> dict:
+        out = np.zeros(10, dtype=np.int64)
+        self._ck(self._dll.cav_book_info(self._h, _ptr(out)))
+        keys = ("n_units", "n_terms", "n_trades", "n_groups", "n_pairs", "n_comp", "n_tiles", "n_krows", "n_pair_rows", "built")
+        return {k: int(v) for k, v in zip(keys, out)}
+
+    def book_read(self):
+        """The flat arrays of the portfolio on the device as a FlatPortfolio (tests / inspection)."""
+        from .flatten import FlatPortfolio
+        i = self.book_info()
+        U, T, N, G, P, K = (i[k] for k in ("n_units", "n_terms", "n_trades", "n_groups", "n_pairs", "n_comp"))
+        off, amt, w = np.empty(U + 1, dtype=np.int64), np.empty(T), np.empty(T * P)
+        node, cw = np.empty(T * P, dtype=np.int32), np.empty(N * K)
+        go, gu = np.empty(G + 1, dtype=np.int64), np.empty(G * K, dtype=np.int32)
+        oi, uw = np.empty(N, dtype=np.int64), np.empty(U)
+        self._ck(self._dll.cav_book_read(self._h, _ptr(off), _ptr(amt), _ptr(w), _ptr(node), _ptr(cw), _ptr(go), _ptr(gu),
+                                         _ptr(oi), _ptr(uw)))
+        return FlatPortfolio(U, T, off, P, amt, w, node, N, K, cw, G, go, gu, oi, uw)
+
+    def book_read_tiles(self) -> dict:
+        i = self.book_info()
+        nt, nk, npr = i["n_tiles"], i["n_krows"], i["n_pair_rows"]
+        i32 = lambda n: np.empty(n, dtype=np.int32)  # noqa: E731
+        out = dict(tile_units=i32(nt * 16), tile_kstart=i32(nt), tile_kcount=i32(nt), tile_npos=i32(nt),
+                   tile_mask=np.empty(nt, dtype=np.uint32), k_row=i32(nk), k_desc=i32(nk), pairs=i32(2 * npr), perm=i32(32),
+                   class_begin=i32(7))
+        self._ck(self._dll.cav_book_read_tiles(self._h, *(_ptr(out[k]) for k in (
+            "tile_units", "tile_kstart", "tile_kcount", "tile_npos", "tile_mask", "k_row", "k_desc", "pairs", "perm", "class_begin"))))
+        out["n_tiles"] = nt
+        return out
 
     def portfolio_value(self, mask: int, pv_dev=None, delta_dev=None, gamma_dev=None, agg_dev=None):
         self._ck(self._dll.cav_portfolio_value(self._h, mask, _ptr(pv_dev), _ptr(delta_dev), _ptr(gamma_dev),

@@ -336,27 +336,53 @@ def _merge_terms(owner, time, amt, n_units):
     return off, time, s
 
 
-@dataclass
+EAGER_CHECK_MAX = 4096     # books up to this size are validated in from_arrays; larger ones by the device flattener
+
+
 class OISBook:
     """A book of vanilla OIS on one curve, held as arrays (one entry per trade).
 
     Conventions (frequencies, day counts, calendar, roll rules, payment lag) are per book, as they are per
-    currency in practice; effective date, termination date, side, coupon, notional and spread are per trade."""
-    curve: OISCurve
-    effective: np.ndarray            # int64 serials
-    termination: np.ndarray          # int64 serials (unadjusted)
-    fixed_sign: np.ndarray           # f64: +1 receive fixed, -1 pay fixed
-    coupon: np.ndarray
-    notional: np.ndarray
-    spread: np.ndarray
-    fixed_freq_type: FrequencyTypes = FrequencyTypes.ANNUAL
-    fixed_dc_type: DayCountTypes = DayCountTypes.ACT_365F
-    float_freq_type: FrequencyTypes = FrequencyTypes.ANNUAL
-    float_dc_type: DayCountTypes = DayCountTypes.THIRTY_E_360
-    payment_lag: int = 0
-    cal_type: CalendarTypes = CalendarTypes.WEEKEND
-    bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING
-    dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD
+    currency in practice; effective date, termination date (or tenor), side, coupon, notional and spread are per trade.
+    `termination` and `spread` are materialised on the host only when host code asks for them: `compute()` hands the
+    arrays to the device flattener (cav_book_from_arrays), which applies the tenor rules itself."""
+
+    def __init__(self, curve: OISCurve, effective, termination, fixed_sign, coupon, notional, spread=None,
+                 fixed_freq_type: FrequencyTypes = FrequencyTypes.ANNUAL, fixed_dc_type: DayCountTypes = DayCountTypes.ACT_365F,
+                 float_freq_type: FrequencyTypes = FrequencyTypes.ANNUAL, float_dc_type: DayCountTypes = DayCountTypes.THIRTY_E_360,
+                 payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING, dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
+                 tenor=None, tenor_unit: str = "Y"):
+        self.curve = curve
+        self.effective = effective            # int64 serials
+        self._termination = termination       # int64 serials (unadjusted) or None while only the tenor is known
+        self._tenor = tenor                   # int32 counts in `tenor_unit` ('Y' / 'M') or None
+        self._tenor_unit = tenor_unit
+        self.fixed_sign = fixed_sign          # f64: +1 receive fixed, -1 pay fixed
+        self.coupon = coupon
+        self.notional = notional
+        self._spread = spread                 # f64 per trade, or None = no spreads
+        self.fixed_freq_type = fixed_freq_type
+        self.fixed_dc_type = fixed_dc_type
+        self.float_freq_type = float_freq_type
+        self.float_dc_type = float_dc_type
+        self.payment_lag = payment_lag
+        self.cal_type = cal_type
+        self.bd_type = bd_type
+        self.dg_type = dg_type
+        self._validated = False
+
+    @property
+    def termination(self) -> np.ndarray:
+        if self._termination is None:
+            self._termination = add_tenor(self.effective, self._tenor, self._tenor_unit)
+        return self._termination
+
+    @property
+    def spread(self) -> np.ndarray:
+        if self._spread is None:
+            return np.zeros(self.n_trades)
+        return self._spread
 
     @property
     def n_trades(self) -> int:
@@ -368,16 +394,20 @@ class OISBook:
                     **conventions) -> "OISBook":
         """effective: list[Date] or serials.  Maturity: `termination` (dates / serials), or `tenor_years` /
         `tenor_months` (integers, applied like Date.add_tenor('nY' / 'nM')).  Side: `fixed_leg_type` (SwapTypes per
-        trade) or `fixed_sign` (+1 receive / -1 pay)."""
+        trade) or `fixed_sign` (+1 receive / -1 pay).  Arrays of the right dtype are kept as they are (no copies)."""
         from .global_types import SwapTypes
         eff = serials(effective)
         n = eff.shape[0]
+        term = tenor = None
+        unit = "Y"
         if termination is not None:
             term = serials(termination)
-        elif tenor_years is not None:
-            term = add_tenor(eff, tenor_years, "Y")
-        elif tenor_months is not None:
-            term = add_tenor(eff, tenor_months, "M")
+            if term.shape[0] != n:
+                raise LibError("effective and termination arrays differ in length")
+        elif tenor_years is not None or tenor_months is not None:
+            unit = "Y" if tenor_years is not None else "M"
+            tenor = np.ascontiguousarray(np.broadcast_to(np.asarray(tenor_years if tenor_years is not None else tenor_months),
+                                                         (n,)), dtype=np.int32)
         else:
             raise LibError("OISBook needs termination dates or tenors")
         if fixed_sign is None:
@@ -391,13 +421,20 @@ class OISBook:
         vec = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=np.float64), (n,)))  # noqa: E731
         if fixed_coupon is None:
             raise LibError("fixed_coupon is required")
-        book = cls(curve, eff, term, vec(fixed_sign), vec(fixed_coupon), vec(notional), vec(float_spread), **conventions)
-        if term.shape[0] != n:
-            raise LibError("effective and termination arrays differ in length")
-        mat = adjust(term, book.bd_type, book.cal_type)
-        if np.any(eff > mat):
-            raise LibError("Start date after maturity date")
+        no_spread = np.ndim(float_spread) == 0 and float(float_spread) == 0.0
+        book = cls(curve, eff, term, vec(fixed_sign), vec(fixed_coupon), vec(notional), None if no_spread else vec(float_spread),
+                   tenor=tenor, tenor_unit=unit, **conventions)
+        if n <= EAGER_CHECK_MAX:
+            book._validate()
         return book
+
+    def _validate(self):
+        """Start date after (adjusted) maturity date: the reference raises when the trade is built (ois.py:127-128).  Small
+        books are checked in from_arrays, large ones where they are flattened (on the device: cav_book_from_arrays)."""
+        if not self._validated:
+            if np.any(self.effective > adjust(self.termination, self.bd_type, self.cal_type)):
+                raise LibError("Start date after maturity date")
+            self._validated = True
 
     # ---- schedule classes: trades that share (effective, termination) share both leg schedules
     def schedule_classes(self):
@@ -421,6 +458,7 @@ class OISBook:
 
         dedup=True: one annuity / floating (/ spread-annuity) unit per schedule class, trades carry weights.
         dedup=False: one private unit per trade (payment_lag 0 only)."""
+        self._validate()
         curve = self.curve
         vd = curve._value_dt._n
         eff, term, cls_of = self.schedule_classes()
@@ -491,7 +529,7 @@ class OISBook:
             ids.append(np.where(has[cls_of], uid[cls_of], 0))
             wcols.append(np.where(has[cls_of], w, 0.0))
             base += int(has.sum())
-        n_units = base
+        n_units = n_units_real = base
         if n_units == 0:       # every trade has matured: one zero unit keeps the layout valid
             offs, ts, amts, n_units = [np.array([1], dtype=I64)], [np.array([0.0])], [np.array([0.0])], 1
         counts = np.concatenate(offs)
@@ -499,7 +537,8 @@ class OISBook:
         np.cumsum(counts, out=unit_offsets[1:])
         weight, node = self._plan(np.concatenate(ts))
         return group_trades(n_units, unit_offsets, 2, np.concatenate(amts), weight.reshape(-1), node.reshape(-1),
-                            np.stack(ids, axis=1).astype(np.int32), np.stack(wcols, axis=1), max_group)
+                            np.stack(ids, axis=1).astype(np.int32), np.stack(wcols, axis=1), max_group,
+                            run_key=cls_of if n_units_real else None)
 
     # -- private units -------------------------------------------------------------------
     def _flatten_private(self, S, cls_of, A, F, Sp, wA, wF, wS) -> FlatPortfolio:
@@ -612,19 +651,59 @@ class OISBook:
         node[weight == 0.0] = 0
         return group_trades(base, unit_offsets, 6, np.concatenate(amts), np.ascontiguousarray(weight.reshape(-1)),
                             np.ascontiguousarray(node.reshape(-1)), np.stack(ids, axis=1).astype(np.int32),
-                            np.stack(wcols, axis=1), max_group)
+                            np.stack(wcols, axis=1), max_group, run_key=cls_of)
 
     # ---- valuation -----------------------------------------------------------------------
-    def _value(self, mask: int, device: int, dedup: bool, per_trade: bool):
+    # ---- device flattening ------------------------------------------------------------------
+    def device_conv(self):
+        """cav_book_conv of this book, or None when only the host flattener handles its conventions."""
+        from . import _native
+        if self.payment_lag != 0 or self.cal_type not in (CalendarTypes.WEEKEND, CalendarTypes.NONE):
+            return None
+        supported = set(_FIXED_DEN) | set(_THIRTY) | {DayCountTypes.ACT_ACT_ISDA, DayCountTypes.ZERO}
+        if self.fixed_dc_type not in supported or self.float_dc_type not in supported:
+            return None
+        try:
+            steps = [int(12 / annual_frequency(f)) for f in (self.fixed_freq_type, self.float_freq_type)]
+        except (LibError, ZeroDivisionError):
+            return None
+        if any(st < 1 or st > 12 for st in steps):
+            return None
+        return _native.BookConv(self.curve._value_dt._n, steps[0], steps[1], self.fixed_dc_type.value, self.float_dc_type.value,
+                                self.cal_type.value, self.bd_type.value, self.dg_type.value, 0, 0)
+
+    def upload(self, ctx, tiles: bool = True, dedup: bool = True, device_flatten: bool = True) -> str:
+        """Make this book the portfolio of `ctx` (a _native.Context whose curve is this book's).  Shared-unit books with
+        conventions the device flattener knows are flattened on the GPU from the per-trade arrays (cav_book_from_arrays: no
+        flat arrays are built on the host or cross PCIe); everything else goes through flatten() + cav_portfolio_upload.
+        Returns "device" or "host"."""
+        from . import _native
+        conv = self.device_conv() if (dedup and device_flatten and self.n_trades > 0) else None
+        if conv is not None:
+            try:
+                unit = _native.TENOR_YEARS if self._tenor_unit == "Y" else _native.TENOR_MONTHS
+                ctx.book_from_arrays(conv, self.effective, self._termination, None if self._termination is not None else self._tenor,
+                                     unit, self.fixed_sign, self.coupon, self.notional, self._spread, tiles=tiles)
+                self._validated = True
+                return "device"
+            except LibError as ex:
+                if ex.code != _native.E_UNSUPPORTED:
+                    # the reference's own message for invalid trades (the native prefix stays in __cause__)
+                    msg = str(ex).split(": ", 1)[-1]
+                    raise LibError(msg, ex.code) from ex
+        ctx.portfolio_upload(self.flatten(dedup=dedup, tiles=tiles))
+        return "host"
+
+    def _value(self, mask: int, device: int, dedup: bool, per_trade: bool, device_flatten: bool = True):
         """(totals [1057] on the host, {"pv", "delta", "gamma"} device rows in trade order)."""
         import torch
         from . import _native
         from .position import CurveSession
         sess = CurveSession.get(self.curve, device)
-        flat = self.flatten(dedup=dedup, tiles=bool(mask & _native.REQ_GAMMA))
-        sess.ctx.portfolio_upload(flat)
-        rows = {}
         n = self.n_trades
+        if n:
+            self.upload(sess.ctx, tiles=bool(mask & _native.REQ_GAMMA), dedup=dedup, device_flatten=device_flatten)
+        rows = {}
         if per_trade:
             dev = torch.device("cuda", device)
             if mask & _native.REQ_VALUE:
@@ -637,12 +716,13 @@ class OISBook:
         agg = sess.ctx.portfolio_value_host(mask, ptr("pv"), ptr("delta"), ptr("gamma")) if n else np.zeros(_native.NOUT)
         return np.array(agg, dtype=np.float64), rows
 
-    def compute(self, request_list, device: int = 0, dedup: bool = True, per_trade: bool = True):
+    def compute(self, request_list, device: int = 0, dedup: bool = True, per_trade: bool = True, device_flatten: bool = True):
         """One batched device valuation.  Returns (AnalyticsResult of the book totals, rows) where rows is a dict
-        of torch CUDA tensors {"pv": [N], "delta": [N,32], "gamma": [N,32,32]} in trade order (per_trade=True)."""
+        of torch CUDA tensors {"pv": [N], "delta": [N,32], "gamma": [N,32,32]} in trade order (per_trade=True).
+        device_flatten=False forces the host flattener (same results; used by the parity tests)."""
         from .position import request_mask, _result_from_totals
         mask = request_mask(request_list)
-        agg, rows = self._value(mask, device, dedup, per_trade)
+        agg, rows = self._value(mask, device, dedup, per_trade, device_flatten)
         # currency / index of the totals: those of the curve's calibration swaps (books are single-curve)
         return _result_from_totals(agg, mask, self.curve, self.curve._used_swaps[0]), rows
 
@@ -652,8 +732,9 @@ class OISBook:
         (`Model.scenario_rates(curve_name, shocks)`), the result a torch CUDA tensor [S, n_trades] in trade order
         (pnl=True: minus the values on this book's own curve).  Row s equals the per-trade VALUE of this book built on
         `model.scenario(curve_name, shocks[s])`."""
-        from .scenarios import scenario_values_flat
-        return scenario_values_flat(self.curve, self.flatten(dedup=dedup, tiles=False), rates, device, pnl, out)
+        from .scenarios import scenario_values_uploaded
+        return scenario_values_uploaded(self.curve, self.n_trades, lambda ctx: self.upload(ctx, tiles=False, dedup=dedup),
+                                        rates, device, pnl, out)
 
     def scenario_values_distributed(self, rates, device: int | None = None, dedup: bool = True, pnl: bool = False):
         """Every rank of the initialised torch.distributed group calls this with the SAME book and rates; rank r values
@@ -678,8 +759,9 @@ class OISBook:
         lo, hi = shard_bounds(cost, world)[rank]
         sl = slice(lo, hi)
         return OISBook(self.curve, self.effective[sl], self.termination[sl], self.fixed_sign[sl], self.coupon[sl],
-                       self.notional[sl], self.spread[sl], self.fixed_freq_type, self.fixed_dc_type, self.float_freq_type,
-                       self.float_dc_type, self.payment_lag, self.cal_type, self.bd_type, self.dg_type)
+                       self.notional[sl], None if self._spread is None else self._spread[sl], self.fixed_freq_type,
+                       self.fixed_dc_type, self.float_freq_type, self.float_dc_type, self.payment_lag, self.cal_type,
+                       self.bd_type, self.dg_type)
 
     def compute_distributed(self, request_list, device: int | None = None, dedup: bool = True, per_trade: bool = True):
         """Every rank of the initialised torch.distributed group calls this with the SAME book: each values its own

@@ -2,13 +2,16 @@
 import os
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "cav_api.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "cav_kernels.cuh"), os.path.join(HERE, "..", "include", "adrates_b200.h")]
+CSRC = os.path.join(HERE, "csrc")
+SOURCES = [os.path.join(CSRC, "cav_api.cu"), os.path.join(CSRC, "cav_book.cu")]
+DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("cav_kernels.cuh", "cav_ctx.h", "cav_book_core.h")] + \
+    [os.path.join(HERE, "..", "include", "adrates_b200.h")]
 LIB = os.path.join(HERE, "libadrates_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC,-fopenmp"]
+              "-Xcompiler", "-fPIC,-fopenmp"]
 
 
 def needs_build() -> bool:
@@ -23,12 +26,24 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("CAV_NVCC_EXTRA", "").split()          # experiment switches (-DNAME=value)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, SRC]
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objs = [os.path.join(HERE, os.path.basename(s)[:-3] + ".o") for s in SOURCES]
+
+    def compile_one(pair):
+        src, obj = pair
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        return subprocess.run(cmd, capture_output=True, text=True)
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:       # one nvcc per translation unit, side by side
+        results = list(ex.map(compile_one, zip(SOURCES, objs)))
+    for res in results:
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        if verbose:
+            sys.stderr.write(res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC,-fopenmp", "-gencode", "arch=compute_100a,code=sm_100a",
+                          "-o", LIB] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        sys.stderr.write(res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB
 
 

@@ -12,12 +12,8 @@
 //   k_df_ad          DiscountCurve._linear_forward_interp (discount_curve.py:385-415)
 //   k_scen_*         scenario re-bootstrap + revaluation (Model.scenario loop, models.py:507-557)
 #pragma once
-#include <cuda_runtime.h>
-#include <stdint.h>
+#include "cav_ctx.h"
 
-#define CAV_RW 32           // ladder width == warp size
-#define CAV_RR 1024         // gamma entries per trade
-#define CAV_NOUT 1057       // 1 + 32 + 1024
 
 // ------------------------------------------------------------------------------------------
 // Bootstrap with tangents.  One CTA of 1024 threads; thread (j,k) owns Hessian entry [j][k],
@@ -269,12 +265,11 @@ k_units(UnitsArgs A)
 // ------------------------------------------------------------------------------------------
 #define GT_NC 576          // table row length: 528 packed gamma entries + 32 delta columns + 16 zeros
 #define GT_NPACK 528
-#define GT_TM 16           // units per tile
 
 __device__ __forceinline__ int gt_packed(int j, int k) { return j >= k ? j * (j + 1) / 2 + k : k * (k + 1) / 2 + j; }
 
 // rows 0..G-1: H_n | g_n ; G..2G-1: C_n | g_n ; 2G..3G-1: g_n g_n^T | 0   (one CTA per row)
-struct PillarPerm { unsigned char perm[32]; unsigned char pos_of[32]; };   // position -> pillar, pillar -> position
+// (struct PillarPerm: cav_ctx.h)
 
 __global__ void __launch_bounds__(GT_NC)
 k_sym_tables(int G, const double* __restrict__ g, const double* __restrict__ Hf, const double* __restrict__ Cf,

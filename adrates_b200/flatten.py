@@ -308,15 +308,27 @@ def layout_trades(n_units, unit_offsets, n_pairs, amt, weight, node, trade_comps
     return group_trades(n_units, unit_offsets, n_pairs, amt, weight, node, ids, ws, max_group)
 
 
-def group_trades(n_units, unit_offsets, n_pairs, amt, weight, node, ids, ws, max_group=256) -> FlatPortfolio:
-    """Sort trades by their unit ids so that a CTA of the expansion kernel serves one run."""
+def group_trades(n_units, unit_offsets, n_pairs, amt, weight, node, ids, ws, max_group=256, run_key=None) -> FlatPortfolio:
+    """Sort trades by their unit ids so that a CTA of the expansion kernel serves one run.
+    run_key (int array per trade, optional): trades are ordered by this key instead (stable) and a run is a stretch of equal
+    keys - the schedule class of array books, which is also how the device flattener (cav_book_from_arrays) lays trades out;
+    every trade of a run must carry the same unit ids."""
     n_trades, n_comp = ids.shape
     n_terms = int(unit_offsets[-1])
-    order = np.lexsort(tuple(ids[:, k] for k in reversed(range(n_comp)))) if n_trades else np.zeros(0, dtype=np.int64)
+    if not n_trades:
+        order = np.zeros(0, dtype=np.int64)
+    elif run_key is not None:
+        order = np.argsort(run_key, kind="stable")
+    else:
+        order = np.lexsort(tuple(ids[:, k] for k in reversed(range(n_comp))))
     ids_s, ws_s = ids[order], ws[order]
     if n_trades:
         new_run = np.ones(n_trades, dtype=bool)
-        new_run[1:] = np.any(ids_s[1:] != ids_s[:-1], axis=1)
+        if run_key is not None:
+            key_s = np.asarray(run_key)[order]
+            new_run[1:] = key_s[1:] != key_s[:-1]
+        else:
+            new_run[1:] = np.any(ids_s[1:] != ids_s[:-1], axis=1)
         run_start = np.flatnonzero(new_run)
         run_end = np.append(run_start[1:], n_trades)
         per_run = -(-(run_end - run_start) // max_group)            # groups per run of equal unit ids

@@ -55,11 +55,14 @@ class CurveSession:
     def get(cls, curve: OISCurve, device: int = 0) -> "CurveSession":
         key = (device, tuple(curve.swap_rates), tuple(curve.swap_times), tuple(map(tuple, curve.year_fracs)),
                curve._interp_type)
-        sess = cls._cache.get(key)
+        sess = cls._cache.pop(key, None)
         if sess is None:
             if len(cls._cache) >= 16:
-                cls._cache.pop(next(iter(cls._cache))).ctx.close()
-            sess = cls._cache[key] = CurveSession(curve, device)
+                # least recently used goes; its context is NOT closed here - a caller may still hold the session (the
+                # XCCY / YoY engines keep two at a time); Context.__del__ frees the device memory with the last reference
+                cls._cache.pop(next(iter(cls._cache)))
+            sess = CurveSession(curve, device)
+        cls._cache[key] = sess          # (re)inserted at the end: dict order is the LRU order
         return sess
 
     def __init__(self, curve: OISCurve, device: int):
@@ -231,12 +234,25 @@ class Portfolio:
         if InstrumentTypes.XCCY_SWAP in kinds:
             raise LibError("mixed OIS / XCCY portfolios are not supported (the reference cannot add Risk to Delta)")
         buckets = {}
+        singles = []          # positions the batched single-curve valuation must not take: valued like Position.compute
         for pos in self._positions:
-            curve = pos._engine._curve_for(pos.derivative)
-            buckets.setdefault(id(curve), (curve, []))[1].append(pos.derivative)
+            d = pos.derivative
+            if getattr(d, "derivative_type", None) == InstrumentTypes.FRN:
+                # Engine._compute_frn (engine.py:700-925): the note is discounted on the OIS curve of its currency; when
+                # its index curve is another one it is a dual-curve valuation (VALUE only, Greeks raise), never the
+                # single-curve unit the flattener would build on the index curve
+                from .credit import BOND_CURVE
+                if d._currency not in BOND_CURVE:
+                    raise LibError(f"No default OIS curve for currency {d._currency}")
+                if BOND_CURVE[d._currency] != d._floating_index:
+                    singles.append(pos)
+                    continue
+            curve = pos._engine._curve_for(d)
+            buckets.setdefault(id(curve), (curve, []))[1].append(d)
         total = None
-        for curve, derivs in buckets.values():
-            res = value_positions(derivs, curve, request_list)
+        results = [value_positions(derivs, curve, request_list) for curve, derivs in buckets.values()]
+        results += [pos.compute(request_list) for pos in singles]
+        for res in results:
             if total is None:
                 total = res
             else:   # same semantics as the reference's running sums (portfolio.py:48-65)

@@ -39,11 +39,17 @@ def scenario_values_flat(curve: OISCurve, flat, rates, device: int = 0, pnl: boo
     """Values of the trades of `flat` (a FlatPortfolio on `curve`) under every row of `rates` [S, R]: torch CUDA tensor
     [S, n_trades], FP64.  pnl=True subtracts the values on the unshocked curve.  `out` (optional) is a preallocated
     contiguous [S, n_trades] CUDA tensor."""
+    return scenario_values_uploaded(curve, flat.n_trades, lambda ctx: ctx.portfolio_upload(flat), rates, device, pnl, out)
+
+
+def scenario_values_uploaded(curve: OISCurve, n_trades: int, upload, rates, device: int = 0, pnl: bool = False, out=None):
+    """As scenario_values_flat, with the portfolio put on the device by `upload(ctx)` (a host upload of a FlatPortfolio or
+    the device flattener of an array book)."""
     import torch
     from . import _native
     from .position import CurveSession
     rates = check_rates(curve, rates)
-    S, n = rates.shape[0], flat.n_trades
+    S, n = rates.shape[0], n_trades
     dev = torch.device("cuda", device)
     if out is None:
         out = torch.empty(S, n, dtype=torch.float64, device=dev)
@@ -52,7 +58,7 @@ def scenario_values_flat(curve: OISCurve, flat, rates, device: int = 0, pnl: boo
     if S == 0 or n == 0:
         return out
     sess = CurveSession.get(curve, device)
-    sess.ctx.portfolio_upload(flat)
+    upload(sess.ctx)
     sess.ctx.scenarios(rates, out.data_ptr())
     if pnl:
         base = torch.empty(n, dtype=torch.float64, device=dev)

@@ -204,6 +204,51 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
  * revalued.  pnl_dev[s][trade] = PV under scenario s (device, [n_scen][n_trades]). */
 int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev);
 
+/* ---- device-side book flattener: replaces the per-trade object layer in front of the valuation ------------------
+ * The reference turns every OIS into a Schedule, two legs and ~50 Date objects before it values a cashflow
+ * (cavour/utils/schedule.py:163-270, calendar.py:139-217, day_count.py:122-330, date.py:529-879, helpers.py:154-197,
+ * cavour/trades/rates/swap_fixed_leg.py:130-196, swap_float_leg.py:130-186, engine.py:2519-2539, 2858-2897) and plans
+ * every DF query at valuation time (cavour/market/curves/interpolator_ad.py:210-243).  cav_book_from_arrays takes a book
+ * of vanilla OIS as per-trade ARRAYS and builds, on the device, exactly the layout cav_portfolio_upload +
+ * cav_portfolio_set_tiles would have been given by the host flattener (adrates_b200/batch.py + tiles.py): dates are int64
+ * day serials (days since 0000-03-01, adrates_b200.dates.Date._n); trades with equal (effective, termination) dates share
+ * their schedule units (annuity, floating, spread annuity).  Afterwards cav_portfolio_value* / cav_scenarios work as after
+ * an upload.  All pointers are HOST memory (pinned memory is copied without staging); the call returns when the book is
+ * resident (the inputs may be reused).  Conventions are book-wide (per currency in practice).
+ * maturity: `termination` (serials), or tenor[] counts in tenor_unit (Date.add_tenor 'nY' / 'nM' rules).
+ * fixed_sign: +1 receive fixed / -1 pay fixed.  spread: floating spread per trade or NULL.
+ * flags: CAV_BOOK_TILES also plans the tiles of the tensor-core Greeks kernel.
+ * Errors: CAV_E_INVALID with the reference's LibError text ("Start date after maturity date", "Effective date must be
+ * before termination date.", "Dates are not monotonic", "Schedule has none or only one date"); CAV_E_UNSUPPORTED for what
+ * only the host flattener handles (payment lag, three-date day counts, holiday calendars, a fully matured book). */
+#define CAV_TENOR_YEARS  0
+#define CAV_TENOR_MONTHS 1
+#define CAV_BOOK_TILES   1u
+typedef struct cav_book_conv {
+    int64_t value_dt;            /* curve value date (serial) */
+    int32_t fixed_freq_months;   /* 12 / annual_frequency(fixed_freq_type) */
+    int32_t float_freq_months;
+    int32_t fixed_dc, float_dc;  /* DayCountTypes values (cavour/utils/day_count.py:91-120) */
+    int32_t cal_type;            /* CalendarTypes: 1 NONE, 2 WEEKEND */
+    int32_t bd_type;             /* BusDayAdjustTypes 1..5 */
+    int32_t dg_type;             /* DateGenRuleTypes: 1 FORWARD, 2 BACKWARD */
+    int32_t end_of_month;
+    int32_t payment_lag;         /* must be 0 on this path */
+} cav_book_conv;
+int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trades, const int64_t* effective,
+                         const int64_t* termination, const int32_t* tenor, int tenor_unit, const double* fixed_sign,
+                         const double* coupon, const double* notional, const double* spread, uint32_t flags);
+/* sizes of the portfolio on the device: out[10] = n_units, n_terms, n_trades, n_groups, n_pairs, n_comp, n_tiles, n_krows,
+ * n_pair_rows, built_on_device */
+int cav_book_info(cav_ctx* ctx, int64_t* out);
+/* copy the flat arrays / the tile plan of the portfolio on the device to the host (any pointer may be NULL; shapes as in
+ * cav_portfolio_upload / cav_portfolio_set_tiles; k_desc = k_pos | k_coef << 8 | k_pos2 << 16 | k_coef2 << 24 with
+ * k_coef2 = 7 for none; perm[32]; class_begin[7]) */
+int cav_book_read(cav_ctx* ctx, int64_t* unit_offsets, double* amt, double* weight, int32_t* node, double* comp_weight,
+                  int64_t* group_offsets, int32_t* group_units, int64_t* out_index, double* unit_weight);
+int cav_book_read_tiles(cav_ctx* ctx, int32_t* tile_units, int32_t* tile_kstart, int32_t* tile_kcount, int32_t* tile_npos,
+                        uint32_t* tile_mask, int32_t* k_row, int32_t* k_desc, int32_t* pairs, int32_t* perm, int32_t* class_begin);
+
 #ifdef __cplusplus
 }
 #endif

@@ -132,13 +132,14 @@ static void chain(const double* grad, const double* hess, const double* J, const
  *   trade i: coupon, notional, spread, fixed_sign (+1 receive fixed, -1 pay fixed)
  * want: bit0 value, bit1 delta, bit2 gamma.  Outputs: pv[n], delta[n*R], gamma[n*R*R].
  */
-void oracle_ois_batch(int G, int R, int method, const double* x, const double* d, const double* J, const double* C,
-                      const int64_t* fo, const double* f_pay_t, const double* f_alpha,
-                      const int64_t* lo, const double* l_start_t, const double* l_end_t, const double* l_pay_t,
-                      const double* l_alpha,
-                      int64_t n, const int32_t* sched, const double* coupon, const double* notional,
-                      const double* spread, const double* fixed_sign,
-                      int want, int dense, int n_threads, double* pv, double* delta, double* gamma)
+void oracle_ois_batch_legs(int G, int R, int method, const double* x, const double* d, const double* J, const double* C,
+                           const int64_t* fo, const double* f_pay_t, const double* f_alpha,
+                           const int64_t* lo, const double* l_start_t, const double* l_end_t, const double* l_pay_t,
+                           const double* l_alpha,
+                           int64_t n, const int32_t* sched, const double* coupon, const double* notional,
+                           const double* spread, const double* fixed_sign,
+                           int want, int dense, int n_threads, int legs /* bit0 fixed, bit1 floating */,
+                           double* pv, double* delta, double* gamma)
 {
 #ifdef _OPENMP
     if (n_threads > 0) omp_set_num_threads(n_threads);
@@ -158,7 +159,7 @@ void oracle_ois_batch(int G, int R, int method, const double* x, const double* d
             if (gm) memset(gm, 0, sizeof(double) * R * R);
             double value = 0.0;
             /* ---- fixed leg: sign * sum_{t > 0} alpha N c DF(t)  (value_time = 0, DF(0) = d[0] = 1) */
-            {
+            if (legs & 1) {
                 if (want & 6) memset(grad, 0, sizeof(double) * G);
                 if (hess) memset(hess, 0, sizeof(double) * G * G);
                 double leg = 0.0;
@@ -172,7 +173,7 @@ void oracle_ois_batch(int G, int R, int method, const double* x, const double* d
                 if (want & 6) chain(grad, hess, J, C, G, R, dense, dl, gm, tmp);
             }
             /* ---- floating leg: -sign * sum_{p >= 0} ((DF(s)/DF(e) - 1)/a + spread) a N DF(p) */
-            {
+            if (legs & 2) {
                 if (want & 6) memset(grad, 0, sizeof(double) * G);
                 if (hess) memset(hess, 0, sizeof(double) * G * G);
                 double leg = 0.0;
@@ -197,6 +198,42 @@ void oracle_ois_batch(int G, int R, int method, const double* x, const double* d
             if (want & 1) pv[i] = value;
         }
         free(grad); free(hess); free(tmp);
+    }
+}
+
+void oracle_ois_batch(int G, int R, int method, const double* x, const double* d, const double* J, const double* C,
+                      const int64_t* fo, const double* f_pay_t, const double* f_alpha,
+                      const int64_t* lo, const double* l_start_t, const double* l_end_t, const double* l_pay_t,
+                      const double* l_alpha,
+                      int64_t n, const int32_t* sched, const double* coupon, const double* notional,
+                      const double* spread, const double* fixed_sign,
+                      int want, int dense, int n_threads, double* pv, double* delta, double* gamma)
+{
+    oracle_ois_batch_legs(G, R, method, x, d, J, C, fo, f_pay_t, f_alpha, lo, l_start_t, l_end_t, l_pay_t, l_alpha, n, sched,
+                          coupon, notional, spread, fixed_sign, want, dense, n_threads, 3, pv, delta, gamma);
+}
+
+/*
+ * CPU baseline WITH the unit factorisation the GPU path uses (bench.py cpu_baseline.value_units_port): a vanilla OIS is
+ * linear in (coupon x notional, notional) once its schedule is fixed, so the legs of every distinct schedule are valued
+ * once (oracle_ois_batch_legs on unit trades) and every trade is a weighted sum of two unit rows.  This is the expansion:
+ *   out[i] = wa[i] * unit[ua[i]] + wf[i] * unit[uf[i]],   rows of 1 (pv) / R (delta) / R*R (gamma) doubles.
+ */
+void oracle_expand_units(int64_t n, int R, const int32_t* ua, const int32_t* uf, const double* wa, const double* wf,
+                         const double* u_pv, const double* u_delta, const double* u_gamma, int n_threads,
+                         double* pv, double* delta, double* gamma)
+{
+#ifdef _OPENMP
+    if (n_threads > 0) omp_set_num_threads(n_threads);
+#endif
+    const int RR = R * R;
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        const double a = wa[i], f = wf[i];
+        const int64_t x = ua[i], y = uf[i];
+        if (pv) pv[i] = a * u_pv[x] + f * u_pv[y];
+        if (delta) for (int r = 0; r < R; ++r) delta[i * R + r] = a * u_delta[x * R + r] + f * u_delta[y * R + r];
+        if (gamma) for (int e = 0; e < RR; ++e) gamma[i * RR + e] = a * u_gamma[x * RR + e] + f * u_gamma[y * RR + e];
     }
 }
 

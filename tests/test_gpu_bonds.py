@@ -91,3 +91,20 @@ def test_dual_curve_frn_value_matches_reference():
     for f in g["dual_distinct"]:
         res = make_frn(f).position(m2).compute([RequestTypes.VALUE])
         assert abs(res.value.amount - f["value"]) <= 1e-10 * f["face"], f["id"]
+
+
+def test_portfolio_with_dual_curve_frn_equals_sum_of_positions():
+    """Portfolio.compute == sum of Position.compute (reference portfolio.py:39-67) also when a book holds a dual-curve FRN:
+    the note is valued on index + discount curves (VALUE), never as a single-curve unit on its index curve, and Greeks
+    raise like Position.compute does."""
+    from adrates_b200 import LibError
+    from adrates_b200.position import Portfolio
+    g = load_golden("ref_frn.json")
+    m = build_bond_model(g)
+    notes = [make_frn(f) for f in g["dual"][:2]] + [make_frn(f) for f in g["frns"][:2]]
+    pos = [n.position(m) for n in notes]
+    total = Portfolio(pos).compute([RequestTypes.VALUE])
+    each = sum(p.compute([RequestTypes.VALUE]).value.amount for p in pos)
+    assert abs(total.value.amount - each) <= 1e-10 * sum(f["face"] for f in g["dual"][:2] + g["frns"][:2])
+    with pytest.raises(LibError, match="Dual-curve FRN delta/gamma not yet implemented"):
+        Portfolio(pos).compute([RequestTypes.VALUE, RequestTypes.DELTA])

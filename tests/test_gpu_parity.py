@@ -366,6 +366,7 @@ def test_malformed_tile_plans_are_rejected(ref_curves):
         (broken("tile_units", lambda a: a.__setitem__(0, -2)), "unit id out of range"),
         (broken("tile_units", lambda a: a.__setitem__(0, -1)), "exactly one tile"),
         (broken("tile_units", lambda a: a.__setitem__(16 * full + 1, other)), "differ in length"),
+        (broken("tile_units", lambda a: a.__setitem__(16 * full + 1, first)), "exactly one tile"),     # listed twice, one omitted
         (broken("tile_kcount", lambda a: a.__setitem__(len(a) - 1, len(tp0.k_row) + 1)), "K range out of bounds"),
         (broken("tile_kstart", lambda a: a.__setitem__(0, -1)), "K range out of bounds"),
         (broken("k_row", lambda a: a.__setitem__(0, 10 ** 6)), "bad K row"),
