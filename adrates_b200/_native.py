@@ -15,7 +15,8 @@ from .error import LibError
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libadrates_b200.so")
 
-REQ_VALUE, REQ_DELTA, REQ_GAMMA = 1, 2, 4
+REQ_VALUE, REQ_DELTA, REQ_GAMMA, REQ_ALLREDUCE = 1, 2, 4, 8
+COMM_HANDLE_BYTES = 96
 NOUT = 1057
 
 _P = C.c_void_p
@@ -49,6 +50,9 @@ _SIGS = {
     "cav_cashflow_pv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
     "cav_book_from_arrays": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_uint32]),
     "cav_book_info": (C.c_int, [_P, _P]),
+    "cav_comm_local_handle": (C.c_int, [_P, _P]),
+    "cav_comm_init": (C.c_int, [_P, C.c_int, C.c_int, _P]),
+    "cav_comm_status": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "cav_book_read": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "cav_book_read_tiles": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
 }
@@ -254,6 +258,25 @@ class Context:
                                                    arrs[3].shape[0], _ptr(arrs[3]), _ptr(arrs[4]), _ptr(arrs[5]),
                                                    _ptr(pos2), _ptr(coef2), arrs[6].shape[0] // 2, _ptr(arrs[6]),
                                                    _ptr(mask), _ptr(perm)))
+
+    # ---- multi-GPU totals (one process per GPU)
+    def comm_local_handle(self) -> bytes:
+        buf = C.create_string_buffer(COMM_HANDLE_BYTES)
+        self._ck(self._dll.cav_comm_local_handle(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, rank: int, world: int, handles):
+        """handles: the comm_local_handle() blobs of all ranks in rank order."""
+        blob = b"".join(handles)
+        if len(blob) != world * COMM_HANDLE_BYTES:
+            raise LibError(f"comm_init: expected {world} handles of {COMM_HANDLE_BYTES} bytes")
+        self._ck(self._dll.cav_comm_init(self._h, int(rank), int(world), blob))
+        self._comm_world = world
+
+    def comm_status(self):
+        r, w, lost = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self._dll.cav_comm_status(self._h, C.byref(r), C.byref(w), C.byref(lost)))
+        return int(r.value), int(w.value), bool(lost.value)
 
     # ---- device-side flattening of array books
     def book_from_arrays(self, conv: "BookConv", effective, termination=None, tenor=None, tenor_unit: int = TENOR_YEARS,

@@ -694,7 +694,7 @@ class OISBook:
         ctx.portfolio_upload(self.flatten(dedup=dedup, tiles=tiles))
         return "host"
 
-    def _value(self, mask: int, device: int, dedup: bool, per_trade: bool, device_flatten: bool = True):
+    def _value(self, mask: int, device: int, dedup: bool, per_trade: bool, device_flatten: bool = True, out=None):
         """(totals [1057] on the host, {"pv", "delta", "gamma"} device rows in trade order)."""
         import torch
         from . import _native
@@ -703,26 +703,45 @@ class OISBook:
         n = self.n_trades
         if n:
             self.upload(sess.ctx, tiles=bool(mask & _native.REQ_GAMMA), dedup=dedup, device_flatten=device_flatten)
+        elif mask & _native.REQ_ALLREDUCE:      # an empty shard: whatever book the context held before must not be valued again
+            z64, zf = np.zeros(1, dtype=np.int64), np.zeros(0)
+            sess.ctx.portfolio_upload(FlatPortfolio(0, 0, z64, 2, zf, zf, np.zeros(0, dtype=np.int32), 0, 1, zf, 0, z64,
+                                                    np.zeros(0, dtype=np.int32), None, zf))
         rows = {}
         if per_trade:
             dev = torch.device("cuda", device)
-            if mask & _native.REQ_VALUE:
-                rows["pv"] = torch.empty(n, dtype=torch.float64, device=dev)
-            if mask & _native.REQ_DELTA:
-                rows["delta"] = torch.empty(n, 32, dtype=torch.float64, device=dev)
-            if mask & _native.REQ_GAMMA:
-                rows["gamma"] = torch.empty(n, 32, 32, dtype=torch.float64, device=dev)
+            want = [(k, shape) for k, bit, shape in (("pv", _native.REQ_VALUE, (n,)), ("delta", _native.REQ_DELTA, (n, 32)),
+                                                     ("gamma", _native.REQ_GAMMA, (n, 32, 32))) if mask & bit]
+            for k, shape in want:
+                if out is not None and k in out:        # caller-owned result rows (reused across valuations)
+                    t = out[k]
+                    if tuple(t.shape) != shape or t.dtype != torch.float64 or not t.is_contiguous() or t.device != dev:
+                        raise LibError(f"out[{k!r}] must be a contiguous float64 {shape} tensor on {dev}")
+                    rows[k] = t
+                else:
+                    rows[k] = torch.empty(shape, dtype=torch.float64, device=dev)
         ptr = lambda k: rows[k].data_ptr() if k in rows else None  # noqa: E731
-        agg = sess.ctx.portfolio_value_host(mask, ptr("pv"), ptr("delta"), ptr("gamma")) if n else np.zeros(_native.NOUT)
+        if n or (mask & _native.REQ_ALLREDUCE):        # an empty shard still takes part in the exchange of the totals
+            agg = sess.ctx.portfolio_value_host(mask, ptr("pv"), ptr("delta"), ptr("gamma"))
+        else:
+            agg = np.zeros(_native.NOUT)
         return np.array(agg, dtype=np.float64), rows
 
-    def compute(self, request_list, device: int = 0, dedup: bool = True, per_trade: bool = True, device_flatten: bool = True):
+    def compute(self, request_list, device: int = 0, dedup: bool = True, per_trade: bool = True, device_flatten: bool = True,
+                all_ranks: bool = False, out=None):
         """One batched device valuation.  Returns (AnalyticsResult of the book totals, rows) where rows is a dict
-        of torch CUDA tensors {"pv": [N], "delta": [N,32], "gamma": [N,32,32]} in trade order (per_trade=True).
-        device_flatten=False forces the host flattener (same results; used by the parity tests)."""
-        from .position import request_mask, _result_from_totals
+        of torch CUDA tensors {"pv": [N], "delta": [N,32], "gamma": [N,32,32]} in trade order (per_trade=True; `out` may
+        supply preallocated tensors under the same keys).  device_flatten=False forces the host flattener (same results;
+        used by the parity tests).  all_ranks=True: every rank of the torch.distributed group (one process per GPU) calls
+        this with ITS OWN book and gets the totals of all books, summed inside the totals kernel over NVLink."""
+        from . import _native
+        from .position import CurveSession, request_mask, _result_from_totals
         mask = request_mask(request_list)
-        agg, rows = self._value(mask, device, dedup, per_trade, device_flatten)
+        if all_ranks:
+            from .parallel import init_device_allreduce
+            if init_device_allreduce(CurveSession.get(self.curve, device).ctx):
+                mask |= _native.REQ_ALLREDUCE
+        agg, rows = self._value(mask, device, dedup, per_trade, device_flatten, out)
         # currency / index of the totals: those of the curve's calibration swaps (books are single-curve)
         return _result_from_totals(agg, mask, self.curve, self.curve._used_swaps[0]), rows
 
@@ -765,26 +784,30 @@ class OISBook:
 
     def compute_distributed(self, request_list, device: int | None = None, dedup: bool = True, per_trade: bool = True):
         """Every rank of the initialised torch.distributed group calls this with the SAME book: each values its own
-        shard on its GPU (no data-path collective), the 1057 totals are summed with one all-reduce (NCCL over NVLink
-        for CUDA groups).  Returns (AnalyticsResult of the WHOLE book, rows of this rank's shard, (lo, hi))."""
+        shard on its GPU (no data-path collective) and the 1057 totals are summed over the ranks.  With an NCCL group (one
+        process per GPU) the sum happens inside the totals kernel over NVLink peer memory (REQ_ALLREDUCE, csrc/cav_comm.cu):
+        no collective call, one device->host read.  Other groups (gloo) all-reduce the host totals.
+        Returns (AnalyticsResult of the WHOLE book, rows of this rank's shard, (lo, hi))."""
         import os
         import torch
         import torch.distributed as dist
-        from .parallel import all_reduce_totals, shard_bounds
-        from .position import request_mask, _result_from_totals
+        from . import _native
+        from .parallel import all_reduce_totals, init_device_allreduce, shard_bounds
+        from .position import CurveSession, request_mask, _result_from_totals
         rank = dist.get_rank() if dist.is_initialized() else 0
         world = dist.get_world_size() if dist.is_initialized() else 1
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", rank))
         mask = request_mask(request_list)
         mine = self.shard(rank, world)
-        agg, rows = mine._value(mask, device, dedup, per_trade)
         backend = dist.get_backend() if dist.is_initialized() else None
-        tot = torch.from_numpy(agg)
-        if backend == "nccl":
-            tot = tot.to(torch.device("cuda", device))
-        all_reduce_totals(tot)
+        if backend == "nccl" and world > 1:
+            init_device_allreduce(CurveSession.get(self.curve, device).ctx, rank, world)
+            agg, rows = mine._value(mask | _native.REQ_ALLREDUCE, device, dedup, per_trade)
+            tot = agg
+        else:
+            agg, rows = mine._value(mask, device, dedup, per_trade)
+            tot = all_reduce_totals(torch.from_numpy(agg)).numpy()
         per_year = annual_frequency(self.fixed_freq_type) + annual_frequency(self.float_freq_type)
         cost = np.maximum((self.termination - self.effective) / 365.25 * per_year, 1.0)
-        return (_result_from_totals(tot.cpu().numpy(), mask, self.curve, self.curve._used_swaps[0]), rows,
-                shard_bounds(cost, world)[rank])
+        return (_result_from_totals(tot, mask, self.curve, self.curve._used_swaps[0]), rows, shard_bounds(cost, world)[rank])

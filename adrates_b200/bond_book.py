@@ -116,6 +116,11 @@ class BondBook:
     _plan = OISBook._plan
     _flatten_shared = OISBook._flatten_shared
     _flatten_private = OISBook._flatten_private
+    def upload(self, ctx, tiles: bool = True, dedup: bool = True, device_flatten: bool = True) -> str:
+        """Bond books are flattened on the host (the device flattener covers vanilla OIS)."""
+        ctx.portfolio_upload(self.flatten(dedup=dedup, tiles=tiles))
+        return "host"
+
     _value = OISBook._value
     compute = OISBook.compute
     scenario_values = OISBook.scenario_values

@@ -6,7 +6,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = [os.path.join(CSRC, "cav_api.cu"), os.path.join(CSRC, "cav_book.cu")]
+SOURCES = [os.path.join(CSRC, "cav_api.cu"), os.path.join(CSRC, "cav_book.cu"), os.path.join(CSRC, "cav_comm.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, h) for h in ("cav_kernels.cuh", "cav_ctx.h", "cav_book_core.h")] + \
     [os.path.join(HERE, "..", "include", "adrates_b200.h")]
 LIB = os.path.join(HERE, "libadrates_b200.so")

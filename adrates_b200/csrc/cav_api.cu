@@ -5,6 +5,8 @@
 #include <unordered_map>
 
 void cav_book_free(cav_ctx* ctx);      // cav_book.cu
+void cav_comm_free(cav_ctx* ctx);      // cav_comm.cu
+int cav_comm_reduce(cav_ctx* ctx, const double* partials, int64_t rows, double* totals);
 extern "C" void cav_book_set_plan(cav_ctx* ctx, const int32_t* node_swap, const int32_t* node_prev, const double* node_acc, int n_nodes);
 
 namespace {
@@ -270,6 +272,7 @@ void cav_destroy(cav_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy);
     cav_book_free(ctx);
+    cav_comm_free(ctx);
     dev_free(ctx, &ctx->rates); dev_free(ctx, &ctx->node_time); dev_free(ctx, &ctx->node_acc);
     dev_free(ctx, &ctx->node_swap); dev_free(ctx, &ctx->node_prev);
     dev_free(ctx, &ctx->df); dev_free(ctx, &ctx->P); dev_free(ctx, &ctx->jac); dev_free(ctx, &ctx->dP);
@@ -976,6 +979,17 @@ static int build_sym_tables(cav_ctx* ctx, bool defer_check) {
 static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, double* gamma, double* agg_dev,
                       double* agg_host) {
     if (!ctx) return CAV_E_INVALID;
+    if ((mask & CAV_REQ_ALLREDUCE) && (agg_dev || agg_host) && (!ctx->unit_offsets || !ctx->portfolio_valid || ctx->n_units == 0)) {
+        // a rank whose shard is empty (or that holds no portfolio at all) still takes part in the exchange, with zeros
+        CK(cudaSetDevice(ctx->device));
+        double* dst = agg_dev ? agg_dev : ctx->agg;
+        { int rc = cav_comm_reduce(ctx, nullptr, 0, dst); if (rc) return rc; }
+        if (agg_host) {
+            CK(cudaMemcpyAsync(agg_host, dst, sizeof(double) * CAV_NOUT, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        return CAV_OK;
+    }
     if (ctx->order < 0) return fail(ctx, CAV_E_STATE, "cav_portfolio_value: no curve");
     if (!ctx->unit_offsets || !ctx->portfolio_valid) return fail(ctx, CAV_E_STATE, "cav_portfolio_value: no portfolio uploaded");
     const bool want_d = (mask & CAV_REQ_DELTA) != 0, want_g = (mask & CAV_REQ_GAMMA) != 0;
@@ -985,6 +999,8 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     if (!want_g) gamma = nullptr;
     if (!(mask & CAV_REQ_VALUE)) pv = nullptr;
     CK(cudaSetDevice(ctx->device));
+    const bool all_ranks = (mask & CAV_REQ_ALLREDUCE) != 0;
+    if (all_ranks && !(agg_dev || agg_host)) return fail(ctx, CAV_E_INVALID, "CAV_REQ_ALLREDUCE needs a totals output");
     if (ctx->n_units == 0) {
         if (agg_dev) CK(cudaMemsetAsync(agg_dev, 0, sizeof(double) * CAV_NOUT, ctx->stream));
         if (agg_host) std::memset(agg_host, 0, sizeof(double) * CAV_NOUT);
@@ -1036,7 +1052,10 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     // the portfolio totals depend on the units stage only: reduced here, ahead of the long expansion, so that nothing but
     // the read-back is left behind it
     double* const agg_dst = agg_dev ? agg_dev : ctx->agg;
-    if (need_agg) {
+    if (need_agg && all_ranks) {       // this rank's totals, pushed to every peer and summed over ranks in the same kernel
+        int rc = cav_comm_reduce(ctx, ctx->partials, rows, agg_dst);
+        if (rc) return rc;
+    } else if (need_agg) {
         k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, agg_dst);
         ctx->launches++;
         CK(cudaGetLastError());

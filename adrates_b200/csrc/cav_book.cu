@@ -21,6 +21,8 @@
 #include "cav_ctx.h"
 #include "cav_book_core.h"
 
+#include <chrono>
+
 using namespace cavb;
 
 #define BK_KEY_SPAN_BITS 22
@@ -56,6 +58,7 @@ struct BookScratch {
     uint64_t* cls_key = nullptr;
     int32_t *cls_spread = nullptr, *cnt3 = nullptr, *has3 = nullptr, *uid3 = nullptr, *ng = nullptr, *gstart = nullptr;
     int32_t* unit_cnt = nullptr;
+    int2* sched3 = nullptr;                  // (dates before the duplicate filter - 1, dropped head dates) per (part, class)
     // tile plan
     unsigned* support = nullptr;             // [G] pillar-support masks of the curve nodes
     uint64_t* tab_key = nullptr;
@@ -72,6 +75,7 @@ struct BookScratch {
     BookStats *d_stats = nullptr, *h_stats = nullptr;
     char* stage = nullptr;                   // pinned staging for pageable inputs
     size_t stage_cap = 0;
+    cudaEvent_t ev_spread = nullptr, ev_inputs = nullptr;     // per-trade inputs that travel on the copy stream have landed
     std::vector<unsigned> h_support;         // host copy, rebuilt per curve
     int support_G = -1;
 };
@@ -86,7 +90,7 @@ void cav_book_free(cav_ctx* ctx) {
     { char* p = (char*)b->scan_sums; dev_free(ctx, &p); b->scan_sums = nullptr; }
     dev_free(ctx, &b->flag); dev_free(ctx, &b->cls); dev_free(ctx, &b->cls_start); dev_free(ctx, &b->cls_key);
     dev_free(ctx, &b->cls_spread); dev_free(ctx, &b->cnt3); dev_free(ctx, &b->has3); dev_free(ctx, &b->uid3); dev_free(ctx, &b->ng);
-    dev_free(ctx, &b->gstart); dev_free(ctx, &b->unit_cnt); dev_free(ctx, &b->support); dev_free(ctx, &b->tab_key);
+    dev_free(ctx, &b->gstart); dev_free(ctx, &b->unit_cnt); dev_free(ctx, &b->sched3); dev_free(ctx, &b->support); dev_free(ctx, &b->tab_key);
     dev_free(ctx, &b->tab_leader); dev_free(ctx, &b->unit_slot); dev_free(ctx, &b->is_leader); dev_free(ctx, &b->lead_rank);
     dev_free(ctx, &b->unit_gid); dev_free(ctx, &b->unit_mask); dev_free(ctx, &b->grp_cnt); dev_free(ctx, &b->grp_start);
     dev_free(ctx, &b->kcount); dev_free(ctx, &b->kstart); dev_free(ctx, &b->gtiles); dev_free(ctx, &b->tstart);
@@ -94,6 +98,8 @@ void cav_book_free(cav_ctx* ctx) {
     dev_free(ctx, &b->t_npos); dev_free(ctx, &b->t_mask); dev_free(ctx, &b->tile_units); dev_free(ctx, &b->tile_kstart);
     dev_free(ctx, &b->tile_kcount); dev_free(ctx, &b->tile_npos); dev_free(ctx, &b->pairs); dev_free(ctx, &b->tile_mask);
     dev_free(ctx, &b->k_pack); dev_free(ctx, &b->d_stats);
+    if (b->ev_spread) cudaEventDestroy(b->ev_spread);
+    if (b->ev_inputs) cudaEventDestroy(b->ev_inputs);
     if (b->h_stats) cudaFreeHost(b->h_stats);
     if (b->stage) cudaFreeHost(b->stage);
     delete b;
@@ -279,7 +285,7 @@ __global__ void __launch_bounds__(256) k_bk_keys(Conv cv, int64_t n, const int64
         if (e > adjust(t, cv.bd, cv.cal)) err |= E_START_AFTER_MAT;
         if (span < 0 || span >= ((int64_t)1 << BK_KEY_SPAN_BITS)) err |= E_START_AFTER_MAT;
         else if (e >= t) err |= E_EFF_GE_TERM;
-        if (e < 0 || e >= ((int64_t)1 << 40)) err |= E_KEY_RANGE;
+        if (e < 0 || e >= ((int64_t)1 << 30)) err |= E_KEY_RANGE;
         if (!err) { k = ((unsigned long long)e << BK_KEY_SPAN_BITS) | (unsigned long long)span; kmn = k; kmx = k; }
         key[i] = k;
     }
@@ -346,31 +352,39 @@ struct FillSink {
     }
 };
 
-__device__ __forceinline__ void class_scheds(const Conv& cv, uint64_t key, Sched& fx, Sched& fl) {
-    const int64_t eff = (int64_t)(key >> BK_KEY_SPAN_BITS);
-    const int64_t term = eff + (int64_t)(key & (((uint64_t)1 << BK_KEY_SPAN_BITS) - 1));
-    fx = make_sched(eff, term, cv.fixed_step, cv.cal, cv.bd, cv.dg, cv.eom, BK_MAX_DATES);
-    if (cv.float_step == cv.fixed_step) fl = fx;
-    else fl = make_sched(eff, term, cv.float_step, cv.cal, cv.bd, cv.dg, cv.eom, BK_MAX_DATES);
+__device__ __forceinline__ void class_dates(uint64_t key, int64_t& eff, int64_t& term) {
+    eff = (int64_t)(key >> BK_KEY_SPAN_BITS);
+    term = eff + (int64_t)(key & (((uint64_t)1 << BK_KEY_SPAN_BITS) - 1));
 }
 
+// one thread per (class, part): part 0 walks the fixed-leg schedule, parts 1 and 2 the floating-leg schedule.  The schedule
+// shape (dates before the duplicate filter, dropped head dates) is verified here and stored for the fill pass.
 __global__ void __launch_bounds__(128) k_bk_class_count(Conv cv, int64_t S, const uint64_t* __restrict__ cls_key,
                                                         const int64_t* __restrict__ cls_start, const int32_t* __restrict__ cls_spread,
-                                                        int32_t* cnt3, int32_t* has3, int32_t* ng, BookStats* st) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= S) return;
-    Sched fx, fl;
-    class_scheds(cv, cls_key[c], fx, fl);
-    int err = fx.err | fl.err;
-    CountSink sink;
-    sink.c[0] = sink.c[1] = sink.c[2] = 0;
-    if (!err) err |= walk_class(cv, fx, fl, cls_spread && cls_spread[c] != 0, sink);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { cnt3[k * S + c] = sink.c[k]; has3[k * S + c] = sink.c[k] > 0; }
-    ng[c] = (int32_t)((cls_start[c + 1] - cls_start[c] + 255) / 256);
+                                                        int32_t* cnt3, int32_t* has3, int32_t* ng, int2* sched3, BookStats* st) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * S) return;
+    const int part = (int)(i / S);
+    const int64_t c = i - (int64_t)part * S;
+    int n = 0, err = 0;
+    int2 shape = make_int2(0, 0);
+    if (part < 2 || (cls_spread && cls_spread[c] != 0)) {
+        int64_t eff, term;
+        class_dates(cls_key[c], eff, term);
+        const Sched sc = make_sched(eff, term, part == 0 ? cv.fixed_step : cv.float_step, cv.cal, cv.bd, cv.dg, cv.eom, BK_MAX_DATES);
+        err = sc.err;
+        shape = make_int2(sc.cnt, sc.dup);
+        CountSink sink;
+        sink.c[0] = sink.c[1] = sink.c[2] = 0;
+        if (!err) err |= part == 0 ? walk_annuity(cv, sc, sink) : (part == 1 ? walk_float(cv, sc, sink) : walk_spread(cv, sc, sink));
+        n = sink.c[part];
+    }
+    cnt3[i] = n;
+    has3[i] = n > 0;
+    sched3[i] = shape;
+    if (part == 0) ng[c] = (int32_t)((cls_start[c + 1] - cls_start[c] + 255) / 256);
     if (err) atomicOr(&st->err, err);
-    const int mx = max(sink.c[0], max(sink.c[1], sink.c[2]));
-    if (mx > 255) atomicMax(&st->max_terms, mx);
+    if (n > 255) atomicMax(&st->max_terms, n);
 }
 
 // unit_cnt[uid] = terms of the unit that (part, class) maps to
@@ -381,18 +395,24 @@ __global__ void __launch_bounds__(256) k_bk_unit_counts(int64_t S3, const int32_
 }
 
 __global__ void __launch_bounds__(128) k_bk_class_fill(Conv cv, int64_t S, const uint64_t* __restrict__ cls_key,
-                                                       const int32_t* __restrict__ cls_spread, const int32_t* __restrict__ has3,
-                                                       const int32_t* __restrict__ uid3, const int64_t* __restrict__ unit_offsets,
+                                                       const int32_t* __restrict__ has3, const int32_t* __restrict__ uid3,
+                                                       const int2* __restrict__ sched3, const int64_t* __restrict__ unit_offsets,
                                                        const double* __restrict__ x, int G, int lzr, double* amt, double* weight, int* node) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= S) return;
-    Sched fx, fl;
-    class_scheds(cv, cls_key[c], fx, fl);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * S || !has3[i]) return;
+    const int part = (int)(i / S);
+    const int64_t c = i - (int64_t)part * S;
+    int64_t eff, term;
+    class_dates(cls_key[c], eff, term);
+    const int2 shape = sched3[i];
+    const Sched sc = sched_from(eff, term, part == 0 ? cv.fixed_step : cv.float_step, cv.cal, cv.bd, cv.dg, cv.eom, shape.x, shape.y);
     FillSink sink;
     sink.x = x; sink.G = G; sink.lzr = lzr != 0; sink.amt = amt; sink.weight = weight; sink.node = node;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { sink.n[k] = 0; sink.base[k] = has3[k * S + c] ? unit_offsets[uid3[k * S + c]] : 0; }
-    walk_class(cv, fx, fl, cls_spread && cls_spread[c] != 0, sink);
+    sink.n[0] = sink.n[1] = sink.n[2] = 0;
+    sink.base[0] = sink.base[1] = sink.base[2] = unit_offsets[uid3[i]];
+    if (part == 0) walk_annuity(cv, sc, sink);
+    else if (part == 1) walk_float(cv, sc, sink);
+    else walk_spread(cv, sc, sink);
 }
 
 __global__ void __launch_bounds__(128) k_bk_groups_fill(int64_t S, int K, int64_t n_trades, int64_t n_groups,
@@ -429,17 +449,21 @@ __global__ void __launch_bounds__(256) k_bk_trades_fill(int64_t n, int64_t S, in
     out_index[i] = (int64_t)t;
 }
 
-// unit_weight[u] = sum of the trade weights on unit u, in trade order (the order np.bincount adds them)
-__global__ void __launch_bounds__(128) k_bk_unit_weight(int64_t S, int K, const int64_t* __restrict__ cls_start,
+// unit_weight[u] = sum of the trade weights on unit u: a warp per (part, class), lane-strided partial sums in trade order
+// combined in a fixed butterfly (bitwise reproducible; a book with 10k trades on one schedule would otherwise serialise)
+__global__ void __launch_bounds__(256) k_bk_unit_weight(int64_t S, int K, const int64_t* __restrict__ cls_start,
                                                         const int32_t* __restrict__ has3, const int32_t* __restrict__ uid3,
                                                         const double* __restrict__ comp_weight, double* unit_weight) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (i >= S * K) return;
     const int64_t k = i / S, c = i - k * S;
     if (!has3[i]) return;
     double s = 0.0;
-    for (int64_t t = cls_start[c]; t < cls_start[c + 1]; ++t) s += comp_weight[t * K + k];
-    unit_weight[uid3[i]] = s;
+    for (int64_t t = cls_start[c] + lane; t < cls_start[c + 1]; t += 32) s += comp_weight[t * K + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) unit_weight[uid3[i]] = s;
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -509,32 +533,81 @@ __global__ void k_bk_set_nsig(const int32_t* __restrict__ lead_rank, const int32
     if (threadIdx.x == 0 && blockIdx.x == 0) st->n_sig = lead_rank[U - 1] + is_leader[U - 1];
 }
 
-// per signature group: number of K rows, tiles, active-pillar mask; pair rows it needs; work per pillar for the permutation
-__global__ void __launch_bounds__(64) k_bk_group_plan(int G, const uint32_t* __restrict__ sorted_units,
+// K-row sink of cav_book_core.h with the backward search of find() spread over the lanes of a warp: the emission of a group
+// is sequential (a row may merge into the latest row of the same table row), the search for that row is not.  All lanes call
+// every method with the same arguments; the ring of the current 32-position chunk lives in shared memory.
+struct WarpRowSink {
+    int2* pack;
+    int n, chunk_first, chunk, lane;
+    int* ring_row;
+    unsigned char* ring_full;
+    __device__ WarpRowSink(int2* p, int* rr, unsigned char* rf, int ln) : pack(p), n(0), chunk_first(0), chunk(-1), lane(ln), ring_row(rr), ring_full(rf) {}
+    __device__ __forceinline__ void roll(int pos) {
+        if ((pos >> 5) != chunk) { chunk = pos >> 5; chunk_first = n; }
+    }
+    __device__ __forceinline__ int find(int row, int pos) {
+        roll(pos);
+        int best = -1;
+        for (int base = chunk_first; base < n; base += 32) {
+            const int k = base + lane;
+            const unsigned hit = __ballot_sync(0xffffffffu, k < n && ring_row[k - chunk_first] == row);
+            if (hit) best = base + 31 - __clz(hit);
+        }
+        if (best < 0) return -1;
+        return ring_full[best - chunk_first] ? -1 : best;
+    }
+    __device__ __forceinline__ void merge(int k, int pos, int coef) {
+        if (lane == 0) {
+            ring_full[k - chunk_first] = 1;
+            if (pack) pack[k].y = (pack[k].y & 0xFFFF) | (pos << 16) | (coef << 24);
+        }
+        __syncwarp();
+    }
+    __device__ __forceinline__ void emit(int row, int pos, int coef) {
+        roll(pos);
+        if (lane == 0) {
+            const int s = n - chunk_first;
+            if (s < 160) { ring_row[s] = row; ring_full[s] = 0; }
+            if (pack) { pack[n].x = row; pack[n].y = pos | (coef << 8) | (7 << 24); }
+        }
+        ++n;
+        __syncwarp();
+    }
+};
+
+#define BK_GROUP_WARPS 4
+
+// per signature group (a warp each): number of K rows, tiles, active-pillar mask; pair rows it needs; work per pillar for
+// the permutation
+__global__ void __launch_bounds__(32 * BK_GROUP_WARPS) k_bk_group_plan(int G, const uint32_t* __restrict__ sorted_units,
                                                       const int32_t* __restrict__ grp_start, const int32_t* __restrict__ grp_cnt,
                                                       const int64_t* __restrict__ unit_offsets, const double* __restrict__ weight,
                                                       const int* __restrict__ node, const unsigned* __restrict__ unit_mask,
                                                       int32_t* kcount, int32_t* gtiles, BookStats* st) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_row[BK_GROUP_WARPS][160];
+    __shared__ unsigned char s_full[BK_GROUP_WARPS][160];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * BK_GROUP_WARPS + w;
     if (g >= st->n_sig) return;
     const int L = (int)sorted_units[grp_start[g]];
     const int64_t t0 = unit_offsets[L], n = unit_offsets[L + 1] - t0;
-    KRowSink sink(nullptr);
+    WarpRowSink sink(nullptr, s_row[w], s_full[w], lane);
     for (int64_t j = 0; j < n; ++j) {
         const int64_t k = term_key(weight[2 * (t0 + j)], weight[2 * (t0 + j) + 1], node[2 * (t0 + j)], node[2 * (t0 + j) + 1]);
-        if ((k >> 40) == 2) {
+        if ((k >> 40) == 2 && lane == 0) {
             const int a = (int)((k >> 20) & 0xFFFFF);
             atomicOr(&st->pair_bits[a >> 5], 1u << (a & 31));
         }
         emit_term_rows(sink, k, (int)j, G, nullptr);      // pair row ids are not known yet: node-indexed stand-ins
     }
     const int nt = (grp_cnt[g] + GT_TM - 1) / GT_TM;
-    kcount[g] = sink.n;
-    gtiles[g] = nt;
     const unsigned m = unit_mask[L];
-    for (int r = 0; r < 32; ++r)
-        if ((m >> r) & 1u) atomicAdd(&st->freq[r], (unsigned long long)nt * (unsigned long long)sink.n);
-    atomicAdd(&st->class_cnt[bk_tile_class(m)], nt);
+    if (lane == 0) {
+        kcount[g] = sink.n;
+        gtiles[g] = nt;
+        atomicAdd(&st->class_cnt[bk_tile_class(m)], nt);
+    }
+    if ((m >> lane) & 1u) atomicAdd(&st->freq[lane], (unsigned long long)nt * (unsigned long long)sink.n);
 }
 
 // pair rows (a, a+1) in node order; pillar permutation by work (stable argsort of -freq, tiles.plan_tiles)
@@ -557,8 +630,8 @@ __global__ void k_bk_pairs_perm(int G, BookStats* st, int32_t* pair_index, int32
     }
 }
 
-// K rows of every group and its tiles (in group order)
-__global__ void __launch_bounds__(64) k_bk_group_fill(int64_t n_sig, int G, const uint32_t* __restrict__ sorted_units,
+// K rows of every group and its tiles (in group order); a warp per group
+__global__ void __launch_bounds__(32 * BK_GROUP_WARPS) k_bk_group_fill(int64_t n_sig, int G, const uint32_t* __restrict__ sorted_units,
                                                       const int32_t* __restrict__ grp_start, const int32_t* __restrict__ grp_cnt,
                                                       const int64_t* __restrict__ unit_offsets, const double* __restrict__ weight,
                                                       const int* __restrict__ node, const unsigned* __restrict__ unit_mask,
@@ -567,26 +640,28 @@ __global__ void __launch_bounds__(64) k_bk_group_fill(int64_t n_sig, int G, cons
                                                       const int32_t* __restrict__ pair_index, const BookStats* __restrict__ st,
                                                       int2* k_pack, int32_t* t_units, int32_t* t_kstart, int32_t* t_kcount,
                                                       int32_t* t_npos, unsigned* t_mask, uint64_t* t_key) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int s_row[BK_GROUP_WARPS][160];
+    __shared__ unsigned char s_full[BK_GROUP_WARPS][160];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t g = (int64_t)blockIdx.x * BK_GROUP_WARPS + w;
     if (g >= n_sig) return;
     const int L = (int)sorted_units[grp_start[g]];
     const int64_t t0 = unit_offsets[L], n = unit_offsets[L + 1] - t0;
-    KRowSink sink(k_pack + kstart[g]);
+    WarpRowSink sink(k_pack + kstart[g], s_row[w], s_full[w], lane);
     for (int64_t j = 0; j < n; ++j)
         emit_term_rows(sink, term_key(weight[2 * (t0 + j)], weight[2 * (t0 + j) + 1], node[2 * (t0 + j)], node[2 * (t0 + j) + 1]),
                        (int)j, G, pair_index);
     // mask in permuted pillar order
     const unsigned m = unit_mask[L];
-    unsigned pm = 0u;
-    for (int q = 0; q < 32; ++q) pm |= ((m >> st->perm[q]) & 1u) << q;
+    unsigned pm = ((m >> st->perm[lane]) & 1u) << lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pm |= __shfl_xor_sync(0xffffffffu, pm, o);
     const int cls = bk_tile_class(pm);
-    const int cnt = grp_cnt[g];
-    for (int j = 0; j < gtiles[g]; ++j) {
-        const int t = tstart[g] + j;
-        for (int s = 0; s < GT_TM; ++s) {
-            const int q = j * GT_TM + s;
-            t_units[(size_t)t * GT_TM + s] = q < cnt ? (int)sorted_units[grp_start[g] + q] : -1;
-        }
+    const int cnt = grp_cnt[g], nt = gtiles[g], ts = tstart[g];
+    for (int q = lane; q < nt * GT_TM; q += 32)
+        t_units[(size_t)ts * GT_TM + q] = q < cnt ? (int)sorted_units[grp_start[g] + q] : -1;
+    for (int j = lane; j < nt; j += 32) {
+        const int t = ts + j;
         t_kstart[t] = kstart[g]; t_kcount[t] = kcount[g]; t_npos[t] = (int)(n > 256 ? 256 : n); t_mask[t] = pm;
         t_key[t] = (uint64_t)cls;
     }
@@ -618,23 +693,23 @@ inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 
 
 // host -> device copy of one input array: pinned sources go straight to the copy engine; pageable ones are staged through
 // the library's pinned arena by a few host threads (a pageable cudaMemcpyAsync would be staged by the driver on one thread)
-cudaError_t h2d_input(cav_ctx* ctx, BookScratch* bk, void* dst, const void* src, size_t bytes, size_t* stage_off) {
+cudaError_t h2d_input(cav_ctx* ctx, BookScratch* bk, void* dst, const void* src, size_t bytes, size_t* stage_off, cudaStream_t st) {
     if (bytes == 0) return cudaSuccess;
     cudaPointerAttributes at;
     const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess &&
                         (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged || at.type == cudaMemoryTypeDevice);
     cudaGetLastError();
-    if (pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream);
-    char* st = bk->stage + *stage_off;
+    if (pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, st);
+    char* stg = bk->stage + *stage_off;
     *stage_off += (bytes + 255) & ~(size_t)255;
     const int nth = host_threads((int64_t)bytes, 1 << 20);
     const size_t chunk = (bytes + nth - 1) / nth;
 #pragma omp parallel for num_threads(nth) schedule(static)
     for (int t = 0; t < nth; ++t) {
         const size_t o = (size_t)t * chunk;
-        if (o < bytes) std::memcpy(st + o, (const char*)src + o, std::min(chunk, bytes - o));
+        if (o < bytes) std::memcpy(stg + o, (const char*)src + o, std::min(chunk, bytes - o));
     }
-    return cudaMemcpyAsync(dst, st, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    return cudaMemcpyAsync(dst, stg, bytes, cudaMemcpyHostToDevice, st);
 }
 
 // support masks of the curve nodes (adrates_b200/tiles.py::node_support_masks): which par rates ln d_n can depend on
@@ -651,6 +726,25 @@ void node_support_masks(const std::vector<int>& node_swap, const std::vector<int
         mp[i] = base | md[i];
     }
 }
+
+// CAV_BOOK_TRACE=1: host wall-clock of the phases of cav_book_from_arrays on stderr (each mark follows a stream sync)
+struct BookTrace {
+    bool on;
+    std::chrono::steady_clock::time_point t0, last;
+    BookTrace() {
+        static const bool env = [] { const char* e = std::getenv("CAV_BOOK_TRACE"); return e && std::atoi(e) != 0; }();
+        on = env;
+        t0 = last = std::chrono::steady_clock::now();
+    }
+    void mark(const char* what) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[cav_book] %-28s +%8.1f us   (%8.1f us)\n", what,
+                     std::chrono::duration<double, std::micro>(now - last).count(),
+                     std::chrono::duration<double, std::micro>(now - t0).count());
+        last = now;
+    }
+};
 
 int sync_stats(cav_ctx* ctx, BookScratch* bk) {
     CK(cudaMemcpyAsync(bk->h_stats, bk->d_stats, sizeof(BookStats), cudaMemcpyDeviceToHost, ctx->stream));
@@ -702,6 +796,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     ctx->up_chunks = 0; ctx->chunks_pending = false; ctx->trade_check_pending = false;
     ctx->portfolio_valid = false; ctx->tiles_valid = false; ctx->book_built = false;
 
+    BookTrace trace;
     const int64_t N = n_trades;
     const int G = ctx->G;
     Conv cv;
@@ -710,6 +805,8 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     cv.dg = conv->dg_type; cv.eom = conv->end_of_month;
     // the two legs share one schedule when their frequencies agree; the day count only enters the fractions
     if (!bk->d_stats) {
+        CK(cudaEventCreateWithFlags(&bk->ev_spread, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&bk->ev_inputs, cudaEventDisableTiming));
         CK(dev_alloc(ctx, &bk->d_stats, (size_t)1));
         CK(cudaHostAlloc((void**)&bk->h_stats, sizeof(BookStats), cudaHostAllocDefault));
     }
@@ -728,16 +825,26 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
             CK(cudaHostAlloc((void**)&bk->stage, need, cudaHostAllocDefault));
             bk->stage_cap = need;
         }
+        // dates first, on the context's stream: the keys, the sort and the schedule classes need nothing else.  Sides, coupons
+        // and notionals (two thirds of the bytes) follow on the copy stream and are awaited by k_bk_trades_fill only.
         size_t off = 0;
         CK(dev_alloc(ctx, &bk->eff, (size_t)N));
-        CK(h2d_input(ctx, bk, bk->eff, effective, sizeof(int64_t) * N, &off));
-        if (termination) { CK(dev_alloc(ctx, &bk->term_in, (size_t)N)); CK(h2d_input(ctx, bk, bk->term_in, termination, sizeof(int64_t) * N, &off)); }
-        else { CK(dev_alloc(ctx, &bk->tenor, (size_t)N)); CK(h2d_input(ctx, bk, bk->tenor, tenor, sizeof(int32_t) * N, &off)); }
-        CK(dev_alloc(ctx, &bk->sign, (size_t)N)); CK(h2d_input(ctx, bk, bk->sign, fixed_sign, sizeof(double) * N, &off));
-        CK(dev_alloc(ctx, &bk->cpn, (size_t)N)); CK(h2d_input(ctx, bk, bk->cpn, coupon, sizeof(double) * N, &off));
-        CK(dev_alloc(ctx, &bk->notl, (size_t)N)); CK(h2d_input(ctx, bk, bk->notl, notional, sizeof(double) * N, &off));
-        if (spread) { CK(dev_alloc(ctx, &bk->spread, (size_t)N)); CK(h2d_input(ctx, bk, bk->spread, spread, sizeof(double) * N, &off)); }
+        CK(h2d_input(ctx, bk, bk->eff, effective, sizeof(int64_t) * N, &off, ctx->stream));
+        if (termination) { CK(dev_alloc(ctx, &bk->term_in, (size_t)N)); CK(h2d_input(ctx, bk, bk->term_in, termination, sizeof(int64_t) * N, &off, ctx->stream)); }
+        else { CK(dev_alloc(ctx, &bk->tenor, (size_t)N)); CK(h2d_input(ctx, bk, bk->tenor, tenor, sizeof(int32_t) * N, &off, ctx->stream)); }
+        CK(dev_alloc(ctx, &bk->sign, (size_t)N)); CK(dev_alloc(ctx, &bk->cpn, (size_t)N)); CK(dev_alloc(ctx, &bk->notl, (size_t)N));
+        if (spread) CK(dev_alloc(ctx, &bk->spread, (size_t)N));
+        // (the copy stream must not run ahead of work still reading the old buffers on the context's stream)
+        CK(cudaEventRecord(ctx->ev_up, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_up, 0));
+        if (spread) CK(h2d_input(ctx, bk, bk->spread, spread, sizeof(double) * N, &off, ctx->copy));     // class flags need it first
+        CK(cudaEventRecord(bk->ev_spread, ctx->copy));
+        CK(h2d_input(ctx, bk, bk->sign, fixed_sign, sizeof(double) * N, &off, ctx->copy));
+        CK(h2d_input(ctx, bk, bk->cpn, coupon, sizeof(double) * N, &off, ctx->copy));
+        CK(h2d_input(ctx, bk, bk->notl, notional, sizeof(double) * N, &off, ctx->copy));
+        CK(cudaEventRecord(bk->ev_inputs, ctx->copy));
     }
+    trace.mark("inputs staged / queued");
     CK(dev_alloc(ctx, &bk->term, (size_t)N));
     CK(dev_alloc(ctx, &bk->key[0], (size_t)N)); CK(dev_alloc(ctx, &bk->key[1], (size_t)N));
     CK(dev_alloc(ctx, &bk->idx[0], (size_t)N)); CK(dev_alloc(ctx, &bk->idx[1], (size_t)N));
@@ -750,6 +857,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     ctx->launches++;
     CK(cudaGetLastError());
     { int rc = sync_stats(ctx, bk); if (rc) return rc; }
+    trace.mark("keys (sync 1)");
     if (bk->h_stats->err) return book_error(ctx, bk->h_stats->err);
     const uint64_t kmin = bk->h_stats->kmin, krange = bk->h_stats->kmax - kmin;
     int bits = 0;
@@ -772,6 +880,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     CK(cudaMemcpyAsync(&last_cls, bk->cls + (N - 1), sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     const int64_t S = (int64_t)last_cls + 1;
+    trace.mark("sort + classes (sync 2)");
 
     // ---- classes: term counts, unit ids, offsets ----
     CK(dev_alloc(ctx, &bk->cls_spread, (size_t)S));
@@ -779,12 +888,14 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     CK(dev_alloc(ctx, &bk->ng, (size_t)S)); CK(dev_alloc(ctx, &bk->gstart, (size_t)S + 1));
     CK(dev_alloc(ctx, &bk->unit_cnt, (size_t)3 * S + 1));
     if (spread) {
+        CK(cudaStreamWaitEvent(ctx->stream, bk->ev_spread, 0));
         CK(cudaMemsetAsync(bk->cls_spread, 0, sizeof(int32_t) * S, ctx->stream));
         k_bk_spread_flags<<<grid_for(N, 256), 256, 0, ctx->stream>>>(N, sidx, bk->cls, bk->spread, bk->cls_spread, bk->d_stats);
         ctx->launches++;
     }
-    k_bk_class_count<<<grid_for(S, 128), 128, 0, ctx->stream>>>(cv, S, bk->cls_key, bk->cls_start, spread ? bk->cls_spread : nullptr,
-                                                               bk->cnt3, bk->has3, bk->ng, bk->d_stats);
+    CK(dev_alloc(ctx, &bk->sched3, (size_t)3 * S));
+    k_bk_class_count<<<grid_for(3 * S, 128), 128, 0, ctx->stream>>>(cv, S, bk->cls_key, bk->cls_start, spread ? bk->cls_spread : nullptr,
+                                                                   bk->cnt3, bk->has3, bk->ng, bk->sched3, bk->d_stats);
     ctx->launches++;
     CK(cudaGetLastError());
     BookStats* ds = bk->d_stats;
@@ -806,6 +917,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
         bk->h_stats->n_units = (long long)tail[0] + tail[1];
         bk->h_stats->n_groups = (long long)tail[2] + tail[3];
     }
+    trace.mark("class counts (sync 3)");
     if (bk->h_stats->err) return book_error(ctx, bk->h_stats->err);
     const int64_t U = bk->h_stats->n_units, T = bk->h_stats->n_terms, NG = bk->h_stats->n_groups;
     const int K = (spread && bk->h_stats->any_spread) ? 3 : 2;
@@ -817,15 +929,16 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     CK(dev_alloc(ctx, &ctx->comp_weight, (size_t)N * K)); CK(dev_alloc(ctx, &ctx->out_index, (size_t)N));
     CK(dev_alloc(ctx, &ctx->group_offsets, (size_t)NG + 1)); CK(dev_alloc(ctx, &ctx->group_units, (size_t)NG * K));
     CK(dev_alloc(ctx, &ctx->unit_weight, (size_t)U));
-    k_bk_class_fill<<<grid_for(S, 128), 128, 0, ctx->stream>>>(cv, S, bk->cls_key, spread ? bk->cls_spread : nullptr, bk->has3, bk->uid3,
-                                                              ctx->unit_offsets, ctx->node_time, G,
-                                                              ctx->interp == CAV_INTERP_LINEAR_ZERO_RATES, ctx->amt, ctx->weight, ctx->node);
+    k_bk_class_fill<<<grid_for(3 * S, 128), 128, 0, ctx->stream>>>(cv, S, bk->cls_key, bk->has3, bk->uid3, bk->sched3, ctx->unit_offsets,
+                                                                  ctx->node_time, G, ctx->interp == CAV_INTERP_LINEAR_ZERO_RATES,
+                                                                  ctx->amt, ctx->weight, ctx->node);
     k_bk_groups_fill<<<grid_for(S, 128), 128, 0, ctx->stream>>>(S, K, N, NG, bk->cls_start, bk->ng, bk->gstart, bk->has3, bk->uid3,
                                                                ctx->group_offsets, ctx->group_units);
+    CK(cudaStreamWaitEvent(ctx->stream, bk->ev_inputs, 0));
     k_bk_trades_fill<<<grid_for(N, 256), 256, 0, ctx->stream>>>(N, S, K, sidx, bk->cls, bk->has3, bk->sign, bk->cpn, bk->notl,
                                                                spread ? bk->spread : nullptr, ctx->comp_weight, ctx->out_index);
-    k_bk_unit_weight<<<grid_for(S * K, 128), 128, 0, ctx->stream>>>(S, K, bk->cls_start, bk->has3, bk->uid3, ctx->comp_weight,
-                                                                   ctx->unit_weight);
+    k_bk_unit_weight<<<grid_for(S * K * 32, 256), 256, 0, ctx->stream>>>(S, K, bk->cls_start, bk->has3, bk->uid3, ctx->comp_weight,
+                                                                        ctx->unit_weight);
     ctx->launches += 4;
     CK(cudaGetLastError());
 
@@ -839,7 +952,10 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
 
     // ---- tile plan ----
     const bool want_tiles = (flags & CAV_BOOK_TILES) != 0 && bk->h_stats->max_terms <= 255;
-    if (!want_tiles) return CAV_OK;
+    if (!want_tiles) {
+        CK(cudaEventSynchronize(bk->ev_inputs));      // the caller's arrays may be reused when this call returns
+        return CAV_OK;
+    }
     if (bk->support_G != G || bk->h_support.size() != (size_t)G)
         return fail(ctx, CAV_E_STATE, "cav_book_from_arrays: node support masks missing (rebuild the curve)");
     CK(upload(ctx, &bk->support, bk->h_support.data(), (size_t)G));
@@ -877,7 +993,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     k_bk_set_nsig<<<1, 32, 0, ctx->stream>>>(bk->lead_rank, bk->is_leader, U, bk->d_stats);
     CK(cudaMemsetAsync(bk->kcount, 0, sizeof(int32_t) * (U + 1), ctx->stream));
     CK(cudaMemsetAsync(bk->gtiles, 0, sizeof(int32_t) * (U + 1), ctx->stream));
-    k_bk_group_plan<<<grid_for(U, 64), 64, 0, ctx->stream>>>(G, sorted_units, bk->grp_start, bk->grp_cnt, ctx->unit_offsets, ctx->weight,
+    k_bk_group_plan<<<grid_for(U, BK_GROUP_WARPS), 32 * BK_GROUP_WARPS, 0, ctx->stream>>>(G, sorted_units, bk->grp_start, bk->grp_cnt, ctx->unit_offsets, ctx->weight,
                                                             ctx->node, bk->unit_mask, bk->kcount, bk->gtiles, bk->d_stats);
     ctx->launches += 2;
     CK((scan_exclusive<int32_t, int32_t>(ctx, bk, bk->kcount, bk->kstart, U + 1, &ds->n_krows)));
@@ -886,6 +1002,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     ctx->launches++;
     CK(cudaGetLastError());
     { int rc = sync_stats(ctx, bk); if (rc) return rc; }
+    trace.mark("fill + tile groups (sync 4)");
     const BookStats& hs = *bk->h_stats;
     if (hs.err & E_SIG_COLLISION) return CAV_OK;      // (never seen) keep the book, leave the Greeks to the generic kernel
     const int64_t n_sig = hs.n_sig, n_tiles = hs.n_tiles, n_krows = hs.n_krows;
@@ -896,7 +1013,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     CK(dev_alloc(ctx, &bk->tile_kcount, (size_t)n_tiles)); CK(dev_alloc(ctx, &bk->tile_npos, (size_t)n_tiles));
     CK(dev_alloc(ctx, &bk->tile_mask, (size_t)n_tiles));
     // tiles in group order, their size class as sort key (the unit sort's key buffer is free again)
-    k_bk_group_fill<<<grid_for(n_sig, 64), 64, 0, ctx->stream>>>(n_sig, G, sorted_units, bk->grp_start, bk->grp_cnt, ctx->unit_offsets,
+    k_bk_group_fill<<<grid_for(n_sig, BK_GROUP_WARPS), 32 * BK_GROUP_WARPS, 0, ctx->stream>>>(n_sig, G, sorted_units, bk->grp_start, bk->grp_cnt, ctx->unit_offsets,
                                                                 ctx->weight, ctx->node, bk->unit_mask, bk->kstart, bk->kcount, bk->gtiles,
                                                                 bk->tstart, bk->pair_index, bk->d_stats, bk->k_pack, bk->t_units,
                                                                 bk->t_kstart, bk->t_kcount, bk->t_npos, bk->t_mask, bk->key[0]);
@@ -928,6 +1045,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     ctx->tiles_valid = n_tiles > 0;
     ctx->tsym_valid = false;
     if (!same_tables) ctx->tables_ok = false;
+    if (trace.on) { cudaStreamSynchronize(ctx->stream); trace.mark("tiles filled (traced sync)"); }
     return CAV_OK;
 }
 

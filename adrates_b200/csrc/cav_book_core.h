@@ -49,32 +49,36 @@ struct Conv {                 // book-wide conventions (per currency in practice
     int eom;                      // end-of-month roll
 };
 
-CAVB_HD int64_t fdiv(int64_t a, int64_t b) {          // Python's floor division
-    const int64_t q = a / b;
+// Day serials, years and month counts fit 32 bits with room to spare (a serial is < 2^30 until the year 2.9 million; the
+// entry point rejects anything larger): the date arithmetic runs in int, which matters on the GPU where 64-bit integer
+// division is an order of magnitude slower.
+CAVB_HD int fdiv(int a, int b) {                      // Python's floor division
+    const int q = a / b;
     return ((a % b != 0) && ((a < 0) != (b < 0))) ? q - 1 : q;
 }
 
-CAVB_HD void ymd(int64_t n, int& d, int& m, int64_t& y) {
-    const int64_t era = fdiv(n, 146097);
-    const int64_t doe = n - era * 146097;
-    const int64_t yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
-    const int64_t doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
-    const int64_t mp = (5 * doy + 2) / 153;
-    d = (int)(doy - (153 * mp + 2) / 5 + 1);
-    m = (int)(mp < 10 ? mp + 3 : mp - 9);
+CAVB_HD void ymd(int64_t n64, int& d, int& m, int64_t& y) {
+    const int n = (int)n64;
+    const int era = fdiv(n, 146097);
+    const int doe = n - era * 146097;
+    const int yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const int doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const int mp = (5 * doy + 2) / 153;
+    d = doy - (153 * mp + 2) / 5 + 1;
+    m = mp < 10 ? mp + 3 : mp - 9;
     y = yoe + era * 400 + (m <= 2);
 }
 
-CAVB_HD int64_t ordinal(int d, int m, int64_t y) {
-    const int64_t yy = y - (m <= 2);
-    const int64_t era = fdiv(yy, 400);
-    const int64_t yoe = yy - era * 400;
-    const int64_t mp = (m + 9) % 12;
-    const int64_t doy = (153 * mp + 2) / 5 + d - 1;
-    return era * 146097 + yoe * 365 + yoe / 4 - yoe / 100 + doy;
+CAVB_HD int64_t ordinal(int d, int m, int64_t y64) {
+    const int yy = (int)y64 - (m <= 2);
+    const int era = fdiv(yy, 400);
+    const int yoe = yy - era * 400;
+    const int mp = (m + 9) % 12;
+    const int doy = (153 * mp + 2) / 5 + d - 1;
+    return (int64_t)(era * 146097 + yoe * 365 + yoe / 4 - yoe / 100 + doy);
 }
 
-CAVB_HD bool is_leap(int64_t y) { return ((y % 4 == 0) && (y % 100 != 0)) || (y % 400 == 0); }
+CAVB_HD bool is_leap(int64_t y64) { const int y = (int)y64; return ((y % 4 == 0) && (y % 100 != 0)) || (y % 400 == 0); }
 
 CAVB_HD int days_in_month(int m, int64_t y) {
     const int base = (m == 2) ? 28 : ((m == 4 || m == 6 || m == 9 || m == 11) ? 30 : 31);
@@ -82,8 +86,8 @@ CAVB_HD int days_in_month(int m, int64_t y) {
 }
 
 CAVB_HD int weekday(int64_t n) {                     // 0 = Monday (0000-03-01 is a Wednesday)
-    const int64_t w = (n + 2) % 7;
-    return (int)(w < 0 ? w + 7 : w);
+    const int w = ((int)n + 2) % 7;
+    return w < 0 ? w + 7 : w;
 }
 
 // Date.add_months: same day of month (or `day` >= 1), clipped to the month length; eom -> month end
@@ -91,9 +95,9 @@ CAVB_HD int64_t add_months(int64_t n, int64_t mm, bool eom, int day = -1) {
     int d, m;
     int64_t y;
     ymd(n, d, m, y);
-    const int64_t k = y * 12 + (m - 1) + mm;
-    const int64_t y2 = fdiv(k, 12);
-    const int m2 = (int)(k - y2 * 12 + 1);
+    const int k = (int)y * 12 + (m - 1) + (int)mm;
+    const int y2 = fdiv(k, 12);
+    const int m2 = k - y2 * 12 + 1;
     const int dim = days_in_month(m2, y2);
     const int want = day < 0 ? d : day;
     const int d2 = eom ? dim : (want < dim ? want : dim);
@@ -151,7 +155,7 @@ CAVB_HD double year_frac(int64_t n1, int64_t n2, int dc) {
         else if (dc == DC_30E_360) { if (d2 == 31) d2 = 30; }
         else if (dc == DC_30E_360_ISDA) { if (feb1) d1 = 30; if (d2 == 31 || feb2) d2 = 30; }
         else { if (d2 == 31) { m2 += 1; d2 = 1; } }
-        return (double)(360 * (y2 - y1) + 30 * (int64_t)(m2 - m1) + (int64_t)(d2 - d1)) / 360.0;
+        return (double)(360 * (int)(y2 - y1) + 30 * (m2 - m1) + (d2 - d1)) / 360.0;
     }
     // ACT/ACT ISDA (and ZERO, which the reference routes the same way)
     const double den1 = is_leap(y1) ? 366.0 : 365.0, den2 = is_leap(y2) ? 366.0 : 365.0;
@@ -194,6 +198,14 @@ CAVB_HD int64_t sched_raw_date(const Sched& s, int pos) {     // position before
 
 CAVB_HD int64_t sched_date(const Sched& s, int pos) { return sched_raw_date(s, pos + s.dup); }
 
+// a schedule whose (cnt, dup) an earlier make_sched has already derived and verified
+CAVB_HD Sched sched_from(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int cnt, int dup) {
+    Sched s;
+    s.eff = eff; s.term = term; s.step = step; s.cal = cal; s.bd = bd; s.dg = dg; s.eom = eom;
+    s.cnt = cnt; s.dup = dup; s.err = 0;
+    return s;
+}
+
 CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int max_dates) {
     Sched s;
     s.eff = eff; s.term = term; s.step = step; s.cal = cal; s.bd = bd; s.dg = dg; s.eom = eom;
@@ -203,9 +215,9 @@ CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, int cal, int bd, i
     int64_t ye, yt;
     ymd(eff, de, me, ye);
     ymd(term, dt, mt, yt);
-    const int64_t M = (yt * 12 + mt) - (ye * 12 + me);
-    const int64_t q = fdiv(M, step), r = M - q * step;
-    int64_t cnt = q + (r != 0);
+    const int M = ((int)yt * 12 + mt) - ((int)ye * 12 + me);
+    const int q = fdiv(M, step), r = M - q * step;
+    int cnt = q + (r != 0);
     if (dg == DG_BACKWARD) {
         const int64_t same_month = (q == 0) ? term : add_months(term, -(int64_t)step * q, eom != 0);
         cnt += (r == 0) && (same_month > eff);
@@ -214,7 +226,7 @@ CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, int cal, int bd, i
         cnt += (r == 0) && (same_month < term);
     }
     if (cnt + 1 > max_dates) { s.err = E_TOO_MANY_DATES; return s; }
-    s.cnt = (int)cnt;
+    s.cnt = cnt;
     int64_t prev = sched_raw_date(s, 0);
     for (int pos = 1; pos <= s.cnt; ++pos) {
         const int64_t cur = sched_raw_date(s, pos);
@@ -241,19 +253,19 @@ CAVB_HD void flush_run(Sink& sink, int part, bool& open, double t, double sum) {
     open = false;
 }
 
+// part 0: annuity on the fixed-leg schedule
 template <class Sink>
-CAVB_HD int walk_class(const Conv& cv, const Sched& fx, const Sched& fl, bool with_spread, Sink& sink) {
+CAVB_HD int walk_annuity(const Conv& cv, const Sched& fx, Sink& sink) {
+    if (fx.n_dates() < 2) return E_SHORT_SCHEDULE;          // a leg needs at least one accrual period
     int err = 0;
-    if (fx.n_dates() < 2 || fl.n_dates() < 2) return E_SHORT_SCHEDULE;      // a leg needs at least one accrual period
-    // ---- part 0: annuity on the fixed-leg schedule
-    {
-        bool open = false;
-        double rt = 0.0, rs = 0.0;
-        const int np = fx.n_dates() - 1;
-        for (int i = 0; i < np; ++i) {
-            const int64_t s = sched_date(fx, i), e = sched_date(fx, i + 1);
-            const double t = year_frac(cv.value_dt, e, cv.fixed_dc);
-            if (!(t > 0.0)) continue;
+    bool open = false;
+    double rt = 0.0, rs = 0.0;
+    const int np = fx.n_dates() - 1;
+    int64_t s = sched_date(fx, 0);
+    for (int i = 0; i < np; ++i) {
+        const int64_t e = sched_date(fx, i + 1);
+        const double t = year_frac(cv.value_dt, e, cv.fixed_dc);
+        if (t > 0.0) {
             const double alpha = year_frac(s, e, cv.fixed_dc);
             if (open && t == rt) rs += alpha;
             else {
@@ -262,56 +274,69 @@ CAVB_HD int walk_class(const Conv& cv, const Sched& fx, const Sched& fl, bool wi
                 open = true; rt = t; rs = alpha;
             }
         }
-        flush_run(sink, 0, open, rt, rs);
+        s = e;
     }
-    // ---- part 1: floating leg, +1 at the accrual start and -1 at the accrual end of every live coupon, merged by time
-    // (ties: starts before ends, as the stable sort of [starts | ends] orders them; the sums are sums of +-1, exact in any order)
-    {
-        const int np = fl.n_dates() - 1;
-        int i = 0, j = 0;                       // next start / next end candidate (period indices)
-        bool open = false;
-        double rt = 0.0, rs = 0.0;
-        double ts_i = 0.0, te_j = 0.0, last_s = 0.0, last_e = 0.0;
-        bool have_s = false, have_e = false, seen_s = false, seen_e = false;
-        for (;;) {
-            while (!have_s && i < np) {         // advance the start stream to the next live coupon
-                const int64_t s = sched_date(fl, i), e = sched_date(fl, i + 1);
-                const double tp = year_frac(cv.value_dt, e, cv.float_dc);
-                if (tp >= 0.0 && year_frac(s, e, cv.float_dc) > 0.0) {
-                    ts_i = year_frac(cv.value_dt, s, cv.float_dc);
-                    if (seen_s && ts_i < last_s) err |= E_TIME_ORDER;
-                    last_s = ts_i; seen_s = true; have_s = true;
-                }
-                ++i;
-            }
-            while (!have_e && j < np) {
-                const int64_t s = sched_date(fl, j), e = sched_date(fl, j + 1);
-                const double tp = year_frac(cv.value_dt, e, cv.float_dc);
-                if (tp >= 0.0 && year_frac(s, e, cv.float_dc) > 0.0) {
-                    te_j = tp;
-                    if (seen_e && te_j < last_e) err |= E_TIME_ORDER;
-                    last_e = te_j; seen_e = true; have_e = true;
-                }
-                ++j;
-            }
-            if (!have_s && !have_e) break;
-            const bool take_s = have_s && (!have_e || ts_i <= te_j);
-            const double t = take_s ? ts_i : te_j, a = take_s ? 1.0 : -1.0;
-            if (take_s) have_s = false; else have_e = false;
-            if (open && t == rt) rs += a;
-            else { flush_run(sink, 1, open, rt, rs); open = true; rt = t; rs = a; }
-        }
-        flush_run(sink, 1, open, rt, rs);
-    }
-    // ---- part 2: spread annuity on the floating-leg schedule
-    if (with_spread) {
-        bool open = false;
-        double rt = 0.0, rs = 0.0;
-        const int np = fl.n_dates() - 1;
-        for (int i = 0; i < np; ++i) {
+    flush_run(sink, 0, open, rt, rs);
+    return err;
+}
+
+// part 1: floating leg, +1 at the accrual start and -1 at the accrual end of every live coupon, merged by time (ties: starts
+// before ends, as the stable sort of [starts | ends] orders them; the sums are sums of +-1, exact in any order)
+template <class Sink>
+CAVB_HD int walk_float(const Conv& cv, const Sched& fl, Sink& sink) {
+    if (fl.n_dates() < 2) return E_SHORT_SCHEDULE;
+    int err = 0;
+    const int np = fl.n_dates() - 1;
+    int i = 0, j = 0;                       // next start / next end candidate (period indices)
+    bool open = false;
+    double rt = 0.0, rs = 0.0;
+    double ts_i = 0.0, te_j = 0.0, last_s = 0.0, last_e = 0.0;
+    bool have_s = false, have_e = false, seen_s = false, seen_e = false;
+    for (;;) {
+        while (!have_s && i < np) {         // advance the start stream to the next live coupon
             const int64_t s = sched_date(fl, i), e = sched_date(fl, i + 1);
-            const double t = year_frac(cv.value_dt, e, cv.float_dc);
-            if (!(t >= 0.0)) continue;
+            const double tp = year_frac(cv.value_dt, e, cv.float_dc);
+            if (tp >= 0.0 && year_frac(s, e, cv.float_dc) > 0.0) {
+                ts_i = year_frac(cv.value_dt, s, cv.float_dc);
+                if (seen_s && ts_i < last_s) err |= E_TIME_ORDER;
+                last_s = ts_i; seen_s = true; have_s = true;
+            }
+            ++i;
+        }
+        while (!have_e && j < np) {
+            const int64_t s = sched_date(fl, j), e = sched_date(fl, j + 1);
+            const double tp = year_frac(cv.value_dt, e, cv.float_dc);
+            if (tp >= 0.0 && year_frac(s, e, cv.float_dc) > 0.0) {
+                te_j = tp;
+                if (seen_e && te_j < last_e) err |= E_TIME_ORDER;
+                last_e = te_j; seen_e = true; have_e = true;
+            }
+            ++j;
+        }
+        if (!have_s && !have_e) break;
+        const bool take_s = have_s && (!have_e || ts_i <= te_j);
+        const double t = take_s ? ts_i : te_j, a = take_s ? 1.0 : -1.0;
+        if (take_s) have_s = false; else have_e = false;
+        if (open && t == rt) rs += a;
+        else { flush_run(sink, 1, open, rt, rs); open = true; rt = t; rs = a; }
+    }
+    flush_run(sink, 1, open, rt, rs);
+    return err;
+}
+
+// part 2: spread annuity on the floating-leg schedule
+template <class Sink>
+CAVB_HD int walk_spread(const Conv& cv, const Sched& fl, Sink& sink) {
+    if (fl.n_dates() < 2) return E_SHORT_SCHEDULE;
+    int err = 0;
+    bool open = false;
+    double rt = 0.0, rs = 0.0;
+    const int np = fl.n_dates() - 1;
+    int64_t s = sched_date(fl, 0);
+    for (int i = 0; i < np; ++i) {
+        const int64_t e = sched_date(fl, i + 1);
+        const double t = year_frac(cv.value_dt, e, cv.float_dc);
+        if (t >= 0.0) {
             const double alpha = year_frac(s, e, cv.float_dc);
             if (open && t == rt) rs += alpha;
             else {
@@ -320,8 +345,17 @@ CAVB_HD int walk_class(const Conv& cv, const Sched& fx, const Sched& fl, bool wi
                 open = true; rt = t; rs = alpha;
             }
         }
-        flush_run(sink, 2, open, rt, rs);
+        s = e;
     }
+    flush_run(sink, 2, open, rt, rs);
+    return err;
+}
+
+template <class Sink>
+CAVB_HD int walk_class(const Conv& cv, const Sched& fx, const Sched& fl, bool with_spread, Sink& sink) {
+    if (fx.n_dates() < 2 || fl.n_dates() < 2) return E_SHORT_SCHEDULE;
+    int err = walk_annuity(cv, fx, sink) | walk_float(cv, fl, sink);
+    if (with_spread) err |= walk_spread(cv, fl, sink);
     return err;
 }
 

@@ -19,6 +19,7 @@ struct PillarPerm { unsigned char perm[32]; unsigned char pos_of[32]; };   // po
 #include <algorithm>
 
 struct BookScratch;           // device-side flattener state (cav_book.cu)
+struct CommState;             // NVLink all-reduce of the totals (cav_comm.cu)
 
 #define CAV_N_CLASSES 6
 // size class of a tile from its active-pillar mask: compact columns = na(na+3)/2, 8 per n-tile, 8 warps
@@ -138,6 +139,7 @@ struct cav_ctx {
     size_t tile_stage_cap = 0;
 
     BookScratch* book = nullptr;     // cav_book_from_arrays scratch (grow-only), freed by cav_destroy
+    CommState* comm = nullptr;       // peer-mapped buffers of the multi-GPU totals reduction
     bool book_built = false;         // the current portfolio was flattened on the device (no host copy of its arrays)
 
     // scratch

@@ -4,16 +4,19 @@
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun)
     python bench.py --impl reference ...                      (CPU arm: the oracle port of the reference)
 
-Workload (BASELINE.json configs[2]): 1M synthetic SONIA OIS (1Y-50Y, annual) per GPU on the
-README 32-pillar LINEAR_ZERO_RATES curve; every step values the whole book: per-trade PV,
-delta[32] and gamma[32x32] written to HBM plus the portfolio totals (the Portfolio.compute
-result), all-reduced over ranks when N > 1 (weak scaling: each rank owns its own 1M trades).
+Workload (BASELINE.json configs[2]): 1M synthetic SONIA OIS (1Y-50Y, annual) per GPU on the README 32-pillar
+LINEAR_ZERO_RATES curve; every step values the whole book: per-trade PV, delta[32] and gamma[32x32] written to HBM plus the
+portfolio totals (the Portfolio.compute result), summed over the ranks inside the totals kernel over NVLink when N > 1 (weak
+scaling: each rank owns its own 1M trades).
 
 Printed JSON keys follow the driver contract; additionally
-  roofline      dominant kernel (per-trade expansion, HBM-write bound) against MEASURED_PEAKS.json
+  roofline      dominant kernel (per-trade expansion, HBM-write bound) against MEASURED_PEAKS.json; `frac` is on the bytes the
+                kernel must physically move, `frac_algorithmic` on SURVEY 8(d)'s 9 712 B/trade
   cpu_baseline  oracle/liboracle.so (C port of the reference algorithm) on this box's host cores
-  e2e           same metric through the reference-facing call with HOST buffers: H2D of the flattened
-                book from pinned memory + valuation + D2H of the portfolio totals, every step
+  e2e           the same metric through the public call `OISBook.from_arrays(host arrays).compute([VALUE, DELTA, GAMMA])`:
+                H2D of the per-trade arrays from pinned memory, device-side flattening (schedules, day counts, brackets, tile
+                plan), valuation and D2H of the portfolio totals, every step
+  extras        secondary measurements (config 2 / 4 / 5, strong scaling, the pre-flattened upload path, ...)
 """
 import argparse
 import json
@@ -29,20 +32,18 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 BYTES_PER_TRADE = 9712          # 1256 B explicit-cashflow input + 8 + 256 + 8192 B output
-FLOPS_NOTE = "see DESIGN.md section 5"
 METRIC = "OIS trades/sec PV+delta+gamma FP64"
 WORKLOAD = ("BASELINE configs[2]: 1M synthetic SONIA OIS (1Y-50Y annual, 50% forward-starting) per GPU, "
             "PV + 32-pillar delta + full 32x32 gamma incl. par-rate Jacobian chain, per-trade outputs written")
 
 
 def load_curve():
-    from adrates_b200.curves import OISCurve
-    from adrates_b200.global_types import InterpTypes
-    from tests.util_trades import make_calibration_swaps
-    with open(os.path.join(ROOT, "tests", "golden", "ref_curves.json")) as f:
-        cv = json.load(f)["gbp_readme_lzr"]
-    vd, swaps = make_calibration_swaps(cv)
-    return cv, OISCurve(vd, swaps, InterpTypes[cv["interp"]])
+    """(cv, curve): the README SONIA curve and the dict of engine inputs the oracle takes."""
+    from adrates_b200.market_data import readme_gbp_curve
+    curve = readme_gbp_curve()
+    cv = {"swap_rates": list(curve.swap_rates), "swap_times": list(curve.swap_times), "year_fracs": [list(f) for f in curve.year_fracs],
+          "interp": curve._interp_type.name}
+    return cv, curve
 
 
 class ClockSampler(threading.Thread):
@@ -98,29 +99,58 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_oracle_rate(cv, curve, book, sample, dense, threads=0):
-    """trades/s of the C oracle on `sample` trades of the book (all host threads by default)."""
-    from oracle import cavour_oracle as orc, c_oracle
-    from adrates_b200.synthetic import reference_leg_tables
+def host_threads():
+    # all the host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would silently turn
+    # the CPU baseline into a single-thread number
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def oracle_tables(cv):
+    from oracle import cavour_oracle as orc
     plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
     d, J, C = orc.bootstrap_tables(cv["swap_rates"], plan)
+    return (plan["times"], d, J, C)
+
+
+def book_trades(book, lo, hi):
+    return dict(sched=book.sched[lo:hi], coupon=book.coupon[lo:hi], notional=book.notional[lo:hi], spread=book.spread[lo:hi],
+                fixed_sign=book.fixed_sign[lo:hi])
+
+
+def cpu_oracle_rate(cv, curve, book, sample, dense, threads=0):
+    """trades/s of the C oracle on `sample` trades of the book (all host threads by default)."""
+    from oracle import c_oracle
+    from adrates_b200.synthetic import reference_leg_tables
     lt = reference_leg_tables(book)
-    tr = dict(sched=book.sched[:sample], coupon=book.coupon[:sample], notional=book.notional[:sample],
-              spread=book.spread[:sample], fixed_sign=book.fixed_sign[:sample])
-    if not threads:
-        # all the host cores this process may use: torchrun exports OMP_NUM_THREADS=1 to every rank, which would
-        # silently turn the CPU baseline into a single-thread number
-        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = threads or host_threads()
     t0 = time.perf_counter()
-    out = c_oracle.ois_batch((plan["times"], d, J, C), curve._interp_type.value, lt, tr, want=7, dense=dense,
+    out = c_oracle.ois_batch(oracle_tables(cv), curve._interp_type.value, lt, book_trades(book, 0, sample), want=7, dense=dense,
                              n_threads=threads)
     dt = time.perf_counter() - t0
     return sample / dt, threads, out
 
 
+def cpu_units_rate(cv, curve, book, sample, threads=0):
+    """trades/s of the CPU port WITH the unit factorisation the GPU path uses: both legs of every distinct schedule of the
+    sample valued once (sparse chain rule), every trade expanded as a weighted sum of two unit rows."""
+    from oracle import c_oracle
+    from adrates_b200.synthetic import reference_leg_tables
+    lt = reference_leg_tables(book)
+    threads = threads or host_threads()
+    R = len(cv["swap_rates"])
+    out = (np.empty(sample), np.empty((sample, R)), np.empty((sample, R, R)))     # allocated (and touched by numpy) untimed
+    for a in out:
+        a.fill(0.0)
+    t0 = time.perf_counter()
+    pv, dl, gm, t_units, t_expand = c_oracle.ois_batch_units(oracle_tables(cv), curve._interp_type.value, lt,
+                                                             book_trades(book, 0, sample), want=7, n_threads=threads, out=out)
+    dt = time.perf_counter() - t0
+    return sample / dt, t_units, t_expand, (pv, dl, gm)
+
+
 def run_reference(args):
-    """CPU arm: the reference's algorithm (oracle port; the reference itself needs JAX, which is not
-    installed) on a bounded sample of the same workload, all host threads."""
+    """CPU arm: the reference's algorithm (oracle port; the reference itself needs JAX, which is not installed) on a
+    bounded sample of the same workload, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -148,6 +178,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def git_commit():
+    try:
+        return subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=5).stdout.strip() or None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,7 +197,7 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=2000)
     ap.add_argument("--cpu-sample", type=int, default=4000)
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
-    ap.add_argument("--scenarios", type=int, default=2000, help="shocked curves for the config-4 extra")
+    ap.add_argument("--scenarios", type=int, default=10_000, help="shocked curves of the config-4 extra (whole job)")
     args = ap.parse_args()
     # A benchmark must never hold a GPU box hostage: if anything (a lost rank, a collective only some ranks reach)
     # stalls the run, leave with an error instead of waiting for the launcher's limit.
@@ -168,8 +205,6 @@ def main():
     if "BENCH_DEADLINE_S" not in os.environ and args.impl == "reference":
         deadline = max(deadline, 300.0 + 0.6 * (args.steps + args.warmup))    # ~0.2 s of CPU work per step
     if deadline > 0:
-        import threading
-
         def _expired():
             sys.stderr.write(f"bench.py: no result after {deadline:.0f} s (BENCH_DEADLINE_S) - aborting this rank\n")
             sys.stderr.flush()
@@ -191,8 +226,11 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from adrates_b200 import _native
-    from adrates_b200.synthetic import make_book, flatten_book
+    from adrates_b200 import RequestTypes, _native
+    from adrates_b200.batch import OISBook
+    from adrates_b200.parallel import init_device_allreduce
+    from adrates_b200.position import CurveSession
+    from adrates_b200.synthetic import make_array_book, make_book, flatten_book
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -216,42 +254,42 @@ def main():
             numa = f"unbound ({type(ex).__name__})"
         dist.init_process_group("nccl", device_id=dev)
 
+    ALL = [RequestTypes.VALUE, RequestTypes.DELTA, RequestTypes.GAMMA]
+    MASK = _native.REQ_VALUE | _native.REQ_DELTA | _native.REQ_GAMMA
     cv, curve = load_curve()
     n = args.trades
+    seed = 20240430 + rank                                  # weak scaling: every rank has its own book
     t0 = time.perf_counter()
-    book = make_book(curve, n, seed=20240430 + rank)       # weak scaling: every rank has its own book
-    flat = flatten_book(book, dedup=(args.layout == "dedup"))
-    flatten_s = time.perf_counter() - t0
+    abook = make_array_book(curve, n, seed=seed)            # per-trade arrays (what a user holds)
+    arrays_s = time.perf_counter() - t0
+    book = make_book(curve, n, seed=seed)                   # the same trades over schedule objects: input of the CPU oracle
 
-    # pinned host copies of the flattened book (the e2e arm uploads from these every step)
-    def pin(a):
-        if a is None:
-            return None
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
-    pinned = {k: pin(getattr(flat, k)) for k in ("unit_offsets", "amt", "weight", "node", "comp_weight",
-                                                 "group_offsets", "group_units", "out_index", "unit_weight")}
-    import copy
-    flat_pinned = copy.copy(flat)
-    for k, t in pinned.items():
-        setattr(flat_pinned, k, None if t is None else t.numpy())
-
-    ctx = _native.Context(local)
     stream = torch.cuda.current_stream(dev)
-    ctx.set_stream(stream.cuda_stream)                     # kernels, events and NCCL order on one stream
+    ctx = _native.Context(local)
+    ctx.set_stream(stream.cuda_stream)                      # kernels and events order on one stream
     ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
-    ctx.portfolio_upload(flat_pinned)
+    all_ranks = world > 1 and init_device_allreduce(ctx, rank, world)
+    VMASK = MASK | (_native.REQ_ALLREDUCE if all_ranks else 0)
+    t0 = time.perf_counter()
+    flat = None
+    if args.layout == "dedup":
+        where = abook.upload(ctx)                           # device-side flattening (cav_book_from_arrays)
+        ctx.sync()
+    else:
+        flat = flatten_book(book, dedup=False)
+        ctx.portfolio_upload(flat)
+        where = "host"
+    flatten_s = time.perf_counter() - t0
+    info = ctx.book_info()
     pv = torch.empty(n, dtype=torch.float64, device=dev)
     dl = torch.empty(n, 32, dtype=torch.float64, device=dev)
     gm = torch.empty(n, 32, 32, dtype=torch.float64, device=dev)
     agg = torch.zeros(_native.NOUT, dtype=torch.float64, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    MASK = _native.REQ_VALUE | _native.REQ_DELTA | _native.REQ_GAMMA
 
     def step():
-        ctx.portfolio_value(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr())
-        if world > 1:
-            dist.all_reduce(agg)          # portfolio PV / ladder / gamma: 1057 doubles over NVLink
+        # portfolio PV / ladder / gamma of ALL ranks: summed inside the totals kernel over NVLink peer memory
+        ctx.portfolio_value(VMASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr())
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -304,214 +342,335 @@ def main():
     total_ms = float(total_ms.item())
     ms_per_step = total_ms / args.steps
     value = world * n / (ms_per_step * 1e-3)
-
-    # ---- e2e: host buffers -> H2D -> valuation -> D2H of portfolio totals, every step ----
-    agg_host = np.empty(_native.NOUT)
-    agg_resident = agg.cpu().numpy().copy() if world == 1 else None
+    agg_resident = agg.cpu().numpy().copy()
     gm_check = float(gm[:: max(1, n // 4096)].sum().item())
-    ctx.set_async_upload(True)       # per-trade arrays stream in behind the units kernel (pinned buffers stay alive)
-    for _ in range(2):
-        ctx.portfolio_upload(flat_pinned)
-        ctx.portfolio_value_host(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg_host)
+
+    # ---- e2e: the public call from HOST arrays, every step:  OISBook.from_arrays(...).compute([VALUE, DELTA, GAMMA]) ----
+    # H2D of the per-trade arrays (pinned), device-side flattening, valuation, D2H of the totals (summed over the ranks in the
+    # totals kernel).  Result rows stay in HBM (caller-owned tensors, reused).
+    def pin(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
+    h_eff, h_tenor, h_sign, h_cpn, h_notl = (pin(a) for a in (abook.effective, abook._tenor, abook.fixed_sign, abook.coupon, abook.notional))
+    conv = dict(fixed_freq_type=abook.fixed_freq_type, fixed_dc_type=abook.fixed_dc_type, float_freq_type=abook.float_freq_type,
+                float_dc_type=abook.float_dc_type, bd_type=abook.bd_type)
+    out_rows = {"pv": pv, "delta": dl, "gamma": gm}
+    e2e_dedup = args.layout == "dedup"
+
+    def e2e_step():
+        b = OISBook.from_arrays(curve, h_eff, tenor_years=h_tenor, fixed_sign=h_sign, fixed_coupon=h_cpn, notional=h_notl, **conv)
+        return b.compute(ALL, device=local, dedup=e2e_dedup, all_ranks=world > 1, out=out_rows)[0]
+
+    e2e_steps = args.steps if e2e_dedup else min(args.steps, 3)      # private units are flattened on the host: seconds per step
+    for _ in range(2 if e2e_dedup else 1):
+        res = e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        ctx.portfolio_upload(flat_pinned)
-        if world > 1:
-            ctx.portfolio_value(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr())
-            dist.all_reduce(agg)
-            agg_host[:] = agg.cpu().numpy()
-        else:
-            ctx.portfolio_value_host(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg_host)
+    for _ in range(e2e_steps):
+        res = e2e_step()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * args.steps / float(e2e_s.item())
-    ctx.set_async_upload(False)
-    # the pipelined path must reproduce the resident-input results exactly (same kernels, same order)
-    if agg_resident is not None and not np.array_equal(agg_host, agg_resident):
-        raise SystemExit("e2e (pipelined upload) totals differ from the device-resident totals")
-    if float(gm[:: max(1, n // 4096)].sum().item()) != gm_check:
-        raise SystemExit("e2e (pipelined upload) gamma rows differ from the device-resident run")
+    e2e_value = world * n * e2e_steps / float(e2e_s.item())
+    e2e_h2d = int(sum(a.nbytes for a in (h_eff, h_tenor, h_sign, h_cpn, h_notl)))
+    # the public path must reproduce the resident-input results (same kernels; totals differ only in summation order)
+    tot_scale = float(np.sum(np.abs(book.notional))) * world
+    if abs(res.value.amount - agg_resident[0]) > 1e-12 * tot_scale:
+        raise SystemExit("e2e (from_arrays) portfolio PV differs from the device-resident run")
+    if e2e_dedup and float(gm[:: max(1, n // 4096)].sum().item()) != gm_check:
+        raise SystemExit("e2e (from_arrays) gamma rows differ from the device-resident run")
 
-    # ---- secondary measurements (same book, device-resident inputs; reported under "extras") ----
+    # ---- secondary measurements ----
     extras = {}
-    if world > 1 and not args.no_extra:
-        # per-GPU side measurements: the N=1 run reports them; a multi-rank run keeps to the contract line (and to code
-        # every rank executes - a rank-0-only measurement must never sit behind a collective)
-        extras = {"skipped": "secondary per-GPU measurements are reported by the single-GPU run"}
-    if not args.no_extra and world == 1:
-        def timed(fn, reps=10, all_ranks=True):
-            # all_ranks=False: measurements only rank 0 takes - no collective there (the other ranks have left)
-            for _ in range(3):
-                fn()
-            if all_ranks:
-                barrier()
-            else:
-                torch.cuda.synchronize(dev)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            for _ in range(reps):
-                fn()
-            b.record(stream)
-            b.synchronize()
-            return a.elapsed_time(b) / reps
-        M_PD = _native.REQ_VALUE | _native.REQ_DELTA
-        ms = timed(lambda: ctx.portfolio_value(M_PD, pv.data_ptr(), dl.data_ptr(), None, agg.data_ptr()))
-        extras["pv_delta_config2"] = {"ms_per_step": ms, "trades_per_s_per_gpu": n / ms * 1e3,
-                                      "hbm_frac_algorithmic_1520B": n * 1520 / (ms * 1e-3) / 1e9 / measured_peak()[0]}
-        ms = timed(lambda: ctx.portfolio_value(MASK, None, None, None, agg.data_ptr()))
-        extras["portfolio_totals_only"] = {"ms_per_step": ms, "trades_per_s_per_gpu": n / ms * 1e3,
-                                           "note": "PV+delta+gamma of the portfolio, no per-trade rows written"}
-        if rank == 0:
-            # chain rule as a DMMA GEMM on the private layout (one node-gradient row per trade)
-            try:
-                ng = min(n, 1_000_000)
-                sub_b = type(book)(curve, book.schedules, book.sched[:ng], book.coupon[:ng], book.notional[:ng],
-                                   book.fixed_sign[:ng], book.spread[:ng])
-                priv = flatten_book(sub_b, dedup=False, sort_units=False)
-                ctx3 = _native.Context(local)
-                ctx3.set_stream(stream.cuda_stream)
-                ctx3.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=1)
-                ctx3.portfolio_upload(priv)
-                best = None
-                for _ in range(5):
-                    g_ms, g_fl = ctx3.portfolio_delta_gemm(pv.data_ptr(), dl.data_ptr())
-                    best = g_ms if best is None else min(best, g_ms)
-                tot_ms = timed(lambda: ctx3.portfolio_delta_gemm(pv.data_ptr(), dl.data_ptr()), reps=5, all_ranks=False)
-                extras["chain_gemm_dmma"] = {
-                    "units": ng, "gemm_ms": best, "gemm_tflops": g_fl / (best * 1e-3) / 1e12,
-                    "dmma_peak_tflops_measured": 37.13, "tensor_pipe_frac": g_fl / (best * 1e-3) / 1e12 / 37.13,
-                    "pv_delta_total_ms": tot_ms,
-                    "note": "delta[U][32] = Q[U][264] x (1e-4 J/d)[264][32], mma.sync.m8n8k4.f64; dense formulation "
-                            "(2.6x the flops of the fused sparse chain), reported as an alternative, not the default path"}
-                ctx3.close()
-                del priv
-            except Exception as ex:  # noqa: BLE001
-                extras["chain_gemm_dmma"] = {"error": str(ex)}
+
+    def timed(fn, reps=10, sync_all=False):
+        for _ in range(3):
+            fn()
+        if sync_all:
+            barrier()
+        else:
+            torch.cuda.synchronize(dev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        b.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, peak_src = measured_peak()
+    if not args.no_extra:
+        # ---- measurements EVERY rank takes (multi-rank runs execute exactly this code on every rank) ----
+        # (1) strong scaling of the north-star target: ONE 1M-trade book over all ranks (compute_distributed: shards balanced
+        # by coupon count, totals summed in the totals kernel), per-trade rows of the shard written
+        try:
+            sbook = make_array_book(curve, n, seed=20240430)        # the same book on every rank
+            shard = sbook.shard(rank, world)
+            sctx = CurveSession.get(curve, local).ctx
+            shard.upload(sctx)
+            if world > 1:
+                init_device_allreduce(sctx, rank, world)
+            ns = shard.n_trades
+            smask = MASK | (_native.REQ_ALLREDUCE if world > 1 else 0)
+            sagg = torch.zeros(_native.NOUT, dtype=torch.float64, device=dev)
+            sctx.set_stream(stream.cuda_stream)
+            ms = timed(lambda: sctx.portfolio_value(smask, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), sagg.data_ptr()),
+                       reps=10, sync_all=True)
+            ms = max_over_ranks(ms)
+            extras["strong_scaling_1m_book"] = {
+                "ranks": world, "trades_total": n, "trades_this_rank": ns, "ms_per_step": ms, "trades_per_s": n / ms * 1e3,
+                "note": "one 1M-trade book sharded over the ranks (OISBook.shard, balanced by coupon count), per-trade rows of "
+                        "the shard written, totals of the WHOLE book on every rank via the in-kernel NVLink all-reduce; "
+                        "back-to-back steps without an L2 flush, max over ranks"}
+        except Exception as ex:  # noqa: BLE001
+            extras["strong_scaling_1m_book"] = {"error": repr(ex)}
+        if world > 1:
+            barrier()
+        # (2) BASELINE config 4 in full: 10 000 shocked curves x 100 000 trades, scenarios sharded over the ranks (no collective)
+        try:
+            from adrates_b200.scenarios import scenario_bounds
             from adrates_b200.synthetic import shocked_rate_scenarios
             S = args.scenarios
             nt = min(n, 100_000)
             shocked = shocked_rate_scenarios(curve, S)
-            sub = flatten_book(type(book)(curve, book.schedules, book.sched[:nt], book.coupon[:nt], book.notional[:nt],
-                                         book.fixed_sign[:nt], book.spread[:nt]), dedup=True)
+            lo, hi = scenario_bounds(S, world)[rank]
+            sub = make_array_book(curve, nt, seed=20240430)
             ctx2 = _native.Context(local)
             ctx2.set_stream(stream.cuda_stream)
             ctx2.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
-            ctx2.portfolio_upload(sub)
-            pnl = torch.empty(S, nt, dtype=torch.float64, device=dev)
-            ms = timed(lambda: ctx2.scenarios(shocked, pnl.data_ptr()), reps=3, all_ranks=False)
-            extras["scenarios_config4"] = {"scenarios": S, "trades": nt, "ms": ms, "revaluations_per_s": S * nt / ms * 1e3,
-                                           "pnl_bytes": S * nt * 8,
-                                           "note": "shocked curves re-bootstrapped on device (DFs only) + full revaluation (one exp per "
-                                                   "distinct DF query and scenario, units gather them); includes H2D of the shocked rates"}
+            sub.upload(ctx2, tiles=False)
+            mine = np.ascontiguousarray(shocked[lo:hi])
+            pnl = torch.empty(hi - lo, nt, dtype=torch.float64, device=dev)
+            ms = max_over_ranks(timed(lambda: ctx2.scenarios(mine, pnl.data_ptr()), reps=3, sync_all=True))
+            extras["scenarios_config4"] = {
+                "scenarios_total": S, "scenarios_this_rank": hi - lo, "trades": nt, "ranks": world, "ms": ms,
+                "revaluations_per_s": S * nt / ms * 1e3, "pnl_bytes_total": S * nt * 8,
+                "note": "BASELINE config 4: every shocked curve re-bootstrapped on the device (DFs only) + full revaluation (one "
+                        "exp per distinct DF query and scenario); scenarios sharded over the ranks, no collective; includes the "
+                        "H2D of the shocked rates; max over ranks"}
             del pnl
             ctx2.close()
-            # XCCY basis swaps (BASELINE config 5, cross-currency half): 500k GBP/USD swaps on SONIA + SOFR + the
-            # GBP/USD basis curve, PV + domestic / foreign / basis ladders per trade (VALUE + DELTA, like the reference)
-            try:
-                from adrates_b200.synthetic_xccy import make_xccy_book, XccyBookValuer
-                from tests.conftest import load_golden
-                from tests.util_xccy import build_xccy_model
-                gx = load_golden("ref_xccy.json")
-                t1 = time.perf_counter()
-                xbook = make_xccy_book(build_xccy_model(gx), 500_000, seed=11, spot=gx["spot_fx"])
-                xval = XccyBookValuer(xbook, device=local, stream=stream.cuda_stream)
-                x_prep = time.perf_counter() - t1
-                ms = timed(lambda: xval.value(), reps=10, all_ranks=False)
-                extras["xccy_config5"] = {"trades": xbook.n_trades, "ms_per_step": ms, "trades_per_s": xbook.n_trades / ms * 1e3,
-                                          "units": int(xval.flat_for.n_units), "flatten_seconds_untimed": x_prep,
-                                          "note": "per-trade PV + three 32-wide ladder rows written (776 B/trade); parity of "
-                                                  "this path against the per-trade engine path: tests/test_gpu_xccy_book.py"}
-            except Exception as ex:  # noqa: BLE001
-                extras["xccy_config5"] = {"error": str(ex)}
-            # ZCIS leg PVs (BASELINE config 5, inflation half): 500k swaps = 1M cashflows on the path-A nodes of the
-            # same curve, host buffers in, per-trade PVs + total out (cav_cashflow_pv)
-            try:
-                nz = 500_000
-                rz = np.random.Generator(np.random.PCG64(11))
-                tz = np.repeat(rz.integers(1, 31, nz).astype(np.float64) + rz.uniform(0.0, 0.02, nz), 2)
-                az = rz.uniform(-1e6, 1e6, 2 * nz)
-                oz = np.arange(0, 2 * nz + 1, 2, dtype=np.int64)
-                ctxz = _native.Context(local)
-                zargs = (curve._interp_type.value, curve._times, curve._dfs, 0.0, oz, tz, az)
-                for _ in range(2):
-                    pvz, totz = ctxz.cashflow_pv(*zargs)
-                t1 = time.perf_counter()
-                for _ in range(5):
-                    pvz, totz = ctxz.cashflow_pv(*zargs)
-                dtz = (time.perf_counter() - t1) / 5
-                ref = np.array([curve._node_df(float(x)) for x in tz[:64]])
-                errz = float(np.max(np.abs(pvz[:32] - (az[:64] * ref).reshape(-1, 2).sum(1)) / 1e6))
-                extras["zcis_cashflow_pv_config5"] = {"trades": nz, "cashflows": 2 * nz, "ms_e2e_host_buffers": dtz * 1e3,
-                                                      "trades_per_s": nz / dtz, "check_scaled_err_vs_host_df": errz,
-                                                      "note": "discounting of the ZCIS legs on the path-A curve; the CPI index "
-                                                              "arithmetic that produces the amounts is host logic"}
-                ctxz.close()
-            except Exception as ex:  # noqa: BLE001
-                extras["zcis_cashflow_pv_config5"] = {"error": str(ex)}
+        except Exception as ex:  # noqa: BLE001
+            extras["scenarios_config4"] = {"error": repr(ex)}
+        if world > 1:
+            barrier()
+        # (3) BASELINE config 5, XCCY half: 500k GBP/USD basis swaps over the ranks, PV + the three ladders per trade
+        try:
+            from adrates_b200.market_data import SPOT_FX, readme_model
+            from adrates_b200.synthetic_xccy import make_xccy_book, XccyBookValuer
+            nx = 500_000 // world
+            t1 = time.perf_counter()
+            xbook = make_xccy_book(readme_model(with_basis=True), nx, seed=11 + rank, spot=SPOT_FX)
+            xval = XccyBookValuer(xbook, device=local, stream=stream.cuda_stream)
+            x_prep = time.perf_counter() - t1
+            ms = max_over_ranks(timed(lambda: xval.value(), reps=10, sync_all=True))
+            extras["xccy_config5"] = {"trades_total": nx * world, "ranks": world, "ms_per_step": ms,
+                                      "trades_per_s": nx * world / ms * 1e3, "units": int(xval.flat_for.n_units),
+                                      "flatten_seconds_untimed": x_prep,
+                                      "note": "per-trade PV + three 32-wide ladder rows written (776 B/trade), VALUE + DELTA; trades "
+                                              "sharded over the ranks, no collective in the step; parity against the per-trade "
+                                              "engine path: tests/test_gpu_xccy_book.py"}
+        except Exception as ex:  # noqa: BLE001
+            extras["xccy_config5"] = {"error": repr(ex)}
+        if world > 1:
+            barrier()
+
+    if not args.no_extra and world == 1:
+        # ---- single-GPU side measurements (device-resident inputs) ----
+        M_PD = _native.REQ_VALUE | _native.REQ_DELTA
+        ms = timed(lambda: ctx.portfolio_value(M_PD, pv.data_ptr(), dl.data_ptr(), None, agg.data_ptr()))
+        U, T = info["n_units"], info["n_terms"]
+        pd_bytes = n * 264 + n * (2 * 8 + 8 + 2 * 4) + U * 264 + T * 28        # rows out, per-trade weights / ids in, unit rows, terms
+        extras["pv_delta_config2"] = {
+            "ms_per_step": ms, "trades_per_s_per_gpu": n / ms * 1e3, "physical_bytes_model": pd_bytes,
+            "hbm_frac_physical": pd_bytes / (ms * 1e-3) / 1e9 / peak,
+            "hbm_frac_algorithmic_1520B": n * 1520 / (ms * 1e-3) / 1e9 / peak,
+            "note": "BASELINE config 2 (PV + 32-pillar ladder per trade).  The dedup layout reads shared schedule units, so the "
+                    "algorithmic figure (every trade charged its own 1 256 B of cashflows) overstates what moves; the physical "
+                    "fraction is the honest one: this step is latency-bound, not bandwidth-bound"}
+        ms = timed(lambda: ctx.portfolio_value(MASK, None, None, None, agg.data_ptr()))
+        extras["portfolio_totals_only"] = {"ms_per_step": ms, "trades_per_s_per_gpu": n / ms * 1e3,
+                                           "note": "PV+delta+gamma of the portfolio, no per-trade rows written"}
+        # the pre-flattened upload path (round 1's e2e): host flat arrays + tile plan -> pipelined upload -> valuation
+        try:
+            hflat = abook.flatten(dedup=True, tiles=True) if args.layout == "dedup" else flat
+            import copy
+            fp = copy.copy(hflat)
+            for k in ("unit_offsets", "amt", "weight", "node", "comp_weight", "group_offsets", "group_units", "out_index", "unit_weight"):
+                a = getattr(hflat, k)
+                setattr(fp, k, None if a is None else pin(a))
+            agg_host = np.empty(_native.NOUT)
+            ctx.set_async_upload(True)
+            for _ in range(2):
+                ctx.portfolio_upload(fp)
+                ctx.portfolio_value_host(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg_host)
+            torch.cuda.synchronize(dev)
+            t1 = time.perf_counter()
+            reps = max(5, min(args.steps, 30))
+            for _ in range(reps):
+                ctx.portfolio_upload(fp)
+                ctx.portfolio_value_host(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg_host)
+            dt = (time.perf_counter() - t1) / reps
+            ctx.set_async_upload(False)
+            extras["e2e_flat_upload"] = {"ms_per_step": dt * 1e3, "trades_per_s": n / dt, "h2d_bytes_per_step": fp.h2d_bytes(),
+                                         "note": "cav_portfolio_upload of host-flattened arrays (+ tile plan) from pinned memory + "
+                                                 "valuation + totals D2H; the flattening itself (seconds on the host) is NOT in it"}
+            if args.layout == "dedup":
+                abook.upload(ctx)        # back to the device-built book
+                ctx.sync()
+        except Exception as ex:  # noqa: BLE001
+            extras["e2e_flat_upload"] = {"error": repr(ex)}
+        # chain rule as a DMMA GEMM on the private layout (one node-gradient row per trade)
+        try:
+            ng = min(n, 1_000_000)
+            sub_b = type(book)(curve, book.schedules, book.sched[:ng], book.coupon[:ng], book.notional[:ng],
+                               book.fixed_sign[:ng], book.spread[:ng])
+            priv = flatten_book(sub_b, dedup=False, sort_units=False)
+            ctx3 = _native.Context(local)
+            ctx3.set_stream(stream.cuda_stream)
+            ctx3.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+            ctx3.portfolio_upload(priv)
+            best = None
+            for _ in range(5):
+                g_ms, g_fl = ctx3.portfolio_delta_gemm(pv.data_ptr(), dl.data_ptr())
+                best = g_ms if best is None else min(best, g_ms)
+            tot_ms = timed(lambda: ctx3.portfolio_delta_gemm(pv.data_ptr(), dl.data_ptr()), reps=5)
+            extras["chain_gemm_dmma"] = {
+                "units": ng, "gemm_ms": best, "gemm_tflops": g_fl / (best * 1e-3) / 1e12,
+                "dmma_peak_tflops_measured": 37.13, "tensor_pipe_frac": g_fl / (best * 1e-3) / 1e12 / 37.13,
+                "pv_delta_total_ms": tot_ms,
+                "note": "delta[U][32] = Q[U][264] x (1e-4 J/d)[264][32], mma.sync.m8n8k4.f64; dense formulation "
+                        "(2.6x the flops of the fused sparse chain), reported as an alternative, not the default path"}
+            # the irregular-book layout (one private unit per trade) through the full PV + delta + gamma valuation
+            if args.layout == "dedup":
+                privs = flatten_book(sub_b, dedup=False)
+                ctx3.portfolio_upload(privs)
+                pagg = torch.zeros(_native.NOUT, dtype=torch.float64, device=dev)
+
+                def pstep():
+                    flush.zero_()
+                    ctx3.portfolio_value(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), pagg.data_ptr())
+                fl_ms = timed(lambda: flush.zero_(), reps=10)
+                p_ms = timed(pstep, reps=10) - fl_ms
+                extras["private_layout"] = {
+                    "units": ng, "ms_per_step": p_ms, "trades_per_s": ng / p_ms * 1e3,
+                    "roofline": {"bound": "hbm", "frac": ng * BYTES_PER_TRADE / (p_ms * 1e-3) / 1e9 / peak,
+                                 "achieved": ng * BYTES_PER_TRADE / (p_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s"},
+                    "note": "one private unit per trade (the form irregular trades take): no sharing, every trade's terms are "
+                            "read and its Greeks computed by k_units_mma; L2 flushed between steps (flush time subtracted)"}
+                del privs
+            ctx3.close()
+            del priv
+        except Exception as ex:  # noqa: BLE001
+            extras["chain_gemm_dmma"] = {"error": repr(ex)}
+        # ZCIS leg PVs (BASELINE config 5, inflation half): 500k swaps = 1M cashflows on the path-A nodes of the same curve
+        try:
+            nz = 500_000
+            rz = np.random.Generator(np.random.PCG64(11))
+            tz = np.repeat(rz.integers(1, 31, nz).astype(np.float64) + rz.uniform(0.0, 0.02, nz), 2)
+            az = rz.uniform(-1e6, 1e6, 2 * nz)
+            oz = np.arange(0, 2 * nz + 1, 2, dtype=np.int64)
+            ctxz = _native.Context(local)
+            zargs = (curve._interp_type.value, curve._times, curve._dfs, 0.0, oz, tz, az)
+            for _ in range(2):
+                pvz, totz = ctxz.cashflow_pv(*zargs)
+            t1 = time.perf_counter()
+            for _ in range(5):
+                pvz, totz = ctxz.cashflow_pv(*zargs)
+            dtz = (time.perf_counter() - t1) / 5
+            ref = np.array([curve._node_df(float(x)) for x in tz[:64]])
+            errz = float(np.max(np.abs(pvz[:32] - (az[:64] * ref).reshape(-1, 2).sum(1)) / 1e6))
+            extras["zcis_cashflow_pv_config5"] = {"trades": nz, "cashflows": 2 * nz, "ms_e2e_host_buffers": dtz * 1e3,
+                                                  "trades_per_s": nz / dtz, "check_scaled_err_vs_host_df": errz,
+                                                  "note": "discounting of the ZCIS legs on the path-A curve; the CPI index "
+                                                          "arithmetic that produces the amounts is host logic"}
+            ctxz.close()
+        except Exception as ex:  # noqa: BLE001
+            extras["zcis_cashflow_pv_config5"] = {"error": repr(ex)}
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak()
     k = np.array(kern_ms)                      # [steps, 3] units / expand / totals
     dom = int(np.argmax(k.mean(0)))
     dom_name = ["k_units_mma (fused interpolation + PV + delta + gamma per schedule unit, FP64 DMMA tiles)",
                 "k_expand (per-trade PV/delta/gamma rows from unit results, streaming stores)",
                 "k_reduce_partials"][dom]
     dom_ms = float(k[:, dom].mean())
-    achieved = n * BYTES_PER_TRADE / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
+    U, T, K = info["n_units"], info["n_terms"], info["n_comp"]
+    if dom == 1:      # what the expansion stage must move: rows out; unit rows, per-trade weights and row ids in
+        phys = n * 8456 + U * 8456 + n * (K * 8 + 8)
+    else:             # the units stage: terms in, unit rows (or, private layout, the trade rows) out
+        phys = T * 28 + (n if args.layout == "private" else U) * 8456
+    achieved_alg = n * BYTES_PER_TRADE / (dom_ms * 1e-3) / 1e9
+    achieved_phys = phys / (dom_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved_phys, "peak": peak, "unit": "GB/s",
+                "frac": achieved_phys / peak, "traffic": None, "peak_source": peak_src,
+                "bytes_basis": "physical: bytes the dominant stage must move per launch (rows written + unit rows, weights and row "
+                               "ids read; model from the array sizes, see `traffic` for the ncu capture)",
+                "physical_bytes_per_launch": phys,
+                "achieved_algorithmic": achieved_alg, "frac_algorithmic": achieved_alg / peak,
                 "algorithmic_bytes_per_launch": n * BYTES_PER_TRADE,
-                "step_frac": (n * BYTES_PER_TRADE / (ms_per_step * 1e-3) / 1e9) / peak,
+                "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
+                "step_frac_physical": ((n * 8456 + U * 8456 * 2 + T * 28 + n * (K * 8 + 8)) / (ms_per_step * 1e-3) / 1e9) / peak,
+                "step_frac_algorithmic": (n * BYTES_PER_TRADE / (ms_per_step * 1e-3) / 1e9) / peak,
                 "all_kernels_ms": {"k_units": float(k[:, 0].mean()), "k_expand": float(k[:, 1].mean()),
                                    "k_reduce_partials": float(k[:, 2].mean())}}
-    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as f:
-                roofline["traffic"] = json.load(f).get(args.layout)
+                tr = json.load(f)
+            roofline["traffic"] = tr.get(args.layout)
+            roofline["traffic_source"] = {"file": "profiles/r02_traffic.json", "captured_at_commit": tr.get("commit"),
+                                          "note": tr.get("note"), "bench_commit": git_commit()}
         except Exception:  # noqa: BLE001
             pass
-    if roofline["traffic"]:
-        # DRAM bytes actually moved per launch (ncu) over the live kernel time.  The algorithmic figure above
-        # charges every trade its own 1 256 B of cashflow input; the dedup layout reads shared schedule units
-        # once, so `frac` can exceed the physical rate (and 1.0) there - both are reported.
-        roofline["physical_gbs"] = roofline["traffic"] * (n / 1_000_000) / (dom_ms * 1e-3) / 1e9
-        roofline["physical_frac"] = roofline["physical_gbs"] / peak
 
     cpu_dense, cores, _ = cpu_oracle_rate(cv, curve, book, min(args.cpu_sample, n), dense=True)
     cpu_sparse, _, _ = cpu_oracle_rate(cv, curve, book, min(20 * args.cpu_sample, n), dense=False)
+    us = min(200_000, n)
+    cpu_units, t_units, t_expand, _ = cpu_units_rate(cv, curve, book, us)
     cpu_baseline = {"value": cpu_dense, "unit": "trades/s", "cores": cores, "kind": "port",
                     "sample": f"first {min(args.cpu_sample, n)} trades of the same book, oracle/liboracle.so with the "
                               "reference's dense chain rule (J^T H J + sum g_k C_k per leg), curve tables built once, "
                               "OpenMP over all host threads",
                     "value_sparse_port": cpu_sparse,
-                    "sparse_note": "same arithmetic skipping structurally-zero rows (fastest CPU port we have)"}
+                    "sparse_note": "same arithmetic skipping structurally-zero rows",
+                    "value_units_port": cpu_units,
+                    "units_note": f"first {us} trades with the SAME unit factorisation as the GPU path (legs of every distinct "
+                                  f"schedule valued once: {t_units:.2f} s; per-trade rows expanded as weighted sums of two unit rows: "
+                                  f"{t_expand:.2f} s, memory-bound); the fastest CPU formulation we have - the GPU/CPU ratio against "
+                                  "this one is the hardware ratio, against `value` it also contains the algorithm"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "trades/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "trades_per_gpu": n, "layout": args.layout,
-                   "units": flat.n_units, "terms": flat.n_terms, "groups": flat.n_groups,
+        "config": {"workload": WORKLOAD, "trades_per_gpu": n, "layout": args.layout, "flattened_on": where,
+                   "units": info["n_units"], "terms": info["n_terms"], "groups": info["n_groups"], "tiles": info["n_tiles"],
                    "l2": "flushed (256 MiB memset) before every timed step; each step also streams "
                          f"{n * 8456 / 1e9:.2f} GB of outputs (>> 126 MB L2)",
                    "timing": "per-step CUDA events on the launch stream, summed over K steps, max over ranks",
-                   "parity_gate_scaled_err": gate, "flatten_seconds_untimed": flatten_s,
+                   "collective": ("portfolio totals summed over ranks inside k_reduce_partials_ar (NVLink peer stores + flags), "
+                                  "no NCCL call in the step") if all_ranks else "none (single rank)",
+                   "parity_gate_scaled_err": gate, "flatten_seconds_untimed": flatten_s, "array_book_seconds_untimed": arrays_s,
                    "wall_seconds_timed_region": wall},
         "clocks": clocks,
         "host_cpus_per_rank": numa,
-        "e2e": {"value": e2e_value, "unit": "trades/s", "h2d_bytes_per_step": flat.h2d_bytes(),
-                "d2h_bytes_per_step": _native.NOUT * 8,
-                "note": "cav_portfolio_upload from pinned host arrays + cav_portfolio_value(_host) + totals D2H; "
-                        "per-trade rows stay in HBM"},
+        "e2e": {"value": e2e_value, "unit": "trades/s", "h2d_bytes_per_step": e2e_h2d,
+                "d2h_bytes_per_step": _native.NOUT * 8, "ms_per_step": 1e3 * float(e2e_s.item()) / e2e_steps, "steps": e2e_steps,
+                "note": "OISBook.from_arrays(pinned per-trade arrays).compute([VALUE, DELTA, GAMMA]): H2D of effective date / "
+                        "tenor / side / coupon / notional, device-side flattening (cav_book_from_arrays: schedules, day counts, "
+                        "brackets, units, tile plan), valuation, D2H of the totals; per-trade rows stay in HBM"},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,

@@ -44,6 +44,8 @@ extern "C" {
 #define CAV_REQ_VALUE 1u
 #define CAV_REQ_DELTA 2u
 #define CAV_REQ_GAMMA 4u
+/* multi-GPU: the portfolio totals the valuation returns are the sum over all ranks of cav_comm_init (see below) */
+#define CAV_REQ_ALLREDUCE 8u
 
 typedef struct cav_ctx cav_ctx;
 
@@ -248,6 +250,21 @@ int cav_book_read(cav_ctx* ctx, int64_t* unit_offsets, double* amt, double* weig
                   int64_t* group_offsets, int32_t* group_units, int64_t* out_index, double* unit_weight);
 int cav_book_read_tiles(cav_ctx* ctx, int32_t* tile_units, int32_t* tile_kstart, int32_t* tile_kcount, int32_t* tile_npos,
                         uint32_t* tile_mask, int32_t* k_row, int32_t* k_desc, int32_t* pairs, int32_t* perm, int32_t* class_begin);
+
+/* ---- multi-GPU: portfolio totals over the GPUs of one box -------------------------------------------------------
+ * Replaces the running sums of Portfolio.compute (cavour/market/portfolio/portfolio.py:48-65) when the book is sharded
+ * over one process per GPU: the only exchange is the sum of the 1057 totals.  It is done inside the totals kernel over
+ * peer memory (NVLink stores into symmetric buffers + sequence flags, csrc/cav_comm.cu), not by a collective library.
+ * Setup: every rank calls cav_comm_local_handle, the ranks exchange the CAV_COMM_HANDLE_BYTES blobs by any means
+ * (torch.distributed all_gather, MPI, a file), then every rank calls cav_comm_init with all blobs in rank order.
+ * Afterwards cav_portfolio_value / cav_portfolio_value_host with CAV_REQ_ALLREDUCE in the request mask return the
+ * whole-job totals on every rank (bit-identical across ranks); every rank must make the same sequence of such calls.
+ * At most 8 ranks, one process per GPU (two ranks on one device are refused: a waiting kernel must never share a GPU
+ * with the kernel it waits for).  A peer that never arrives yields NaN totals and lost != 0 in cav_comm_status. */
+#define CAV_COMM_HANDLE_BYTES 96
+int cav_comm_local_handle(cav_ctx* ctx, void* handle_out);
+int cav_comm_init(cav_ctx* ctx, int rank, int world, const void* handles);
+int cav_comm_status(cav_ctx* ctx, int* rank, int* world, int* lost);
 
 #ifdef __cplusplus
 }

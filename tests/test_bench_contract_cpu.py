@@ -32,11 +32,13 @@ def _collective_calls(body):
             if isinstance(f, ast.Attribute) and isinstance(f.value, ast.Name) and f.value.id == "dist" \
                     and f.attr in ("barrier", "all_reduce", "all_gather", "broadcast", "reduce"):
                 bad.append((n.lineno, f"dist.{f.attr}"))
+            if isinstance(f, ast.Name) and f.id in ("max_over_ranks", "init_device_allreduce"):
+                bad.append((n.lineno, f"{f.id}()"))
             if isinstance(f, ast.Name) and f.id == "timed":
                 kw = {k.arg: k.value for k in n.keywords}
-                v = kw.get("all_ranks")
-                if not (isinstance(v, ast.Constant) and v.value is False):
-                    bad.append((n.lineno, "timed(...) without all_ranks=False"))
+                v = kw.get("sync_all")
+                if v is not None and not (isinstance(v, ast.Constant) and v.value is False):
+                    bad.append((n.lineno, "timed(..., sync_all=True) calls barrier()"))
     return bad
 
 
@@ -49,6 +51,16 @@ def test_no_collective_inside_rank0_only_blocks():
             bad += _collective_calls(n.body)
     assert found >= 1
     assert not bad, f"collectives only rank 0 would reach: {bad}"
+
+
+def test_bench_does_not_import_the_test_package():
+    """bench.py is product measurement: its inputs come from adrates_b200.market_data, never from tests/."""
+    tree = ast.parse(_src())
+    for n in ast.walk(tree):
+        if isinstance(n, ast.ImportFrom):
+            assert not (n.module or "").startswith("tests"), n.lineno
+        if isinstance(n, ast.Import):
+            assert not any(a.name.startswith("tests") for a in n.names), n.lineno
 
 
 def test_contract_keys_and_flags_are_present():

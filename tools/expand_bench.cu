@@ -320,6 +320,41 @@ __global__ void __launch_bounds__(256) k_p(const double* __restrict__ units, con
     }
 }
 
+// ---- Q: k_a (v4.f64 stores) + hints in isolation, units from DRAM (index 2g, 2g+1 as in the product)
+// MODE 0: evict_first stores only   1: L2 prefetch of the unit rows of group g + AHEAD issued by CTA g (fire and forget)
+// 2: both   3: evict_last unit loads + evict_first stores
+template <int MODE>
+__global__ void __launch_bounds__(256) k_q(const double* __restrict__ units, const double* __restrict__ w,
+                                           const long long* __restrict__ rows, int gsz, double* out, int G, int ahead) {
+    __shared__ double sw[256][2];
+    __shared__ long long sr[256];
+    int g = blockIdx.x, tid = threadIdx.x;
+    long long t0 = (long long)g * gsz;
+    if (tid < gsz) { sw[tid][0] = w[(t0 + tid) * 2]; sw[tid][1] = w[(t0 + tid) * 2 + 1]; sr[tid] = rows[t0 + tid]; }
+    unsigned long long pol = 0, keep = 0;
+    if (MODE != 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (MODE == 3) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+    if ((MODE == 1 || MODE == 2) && g + ahead < G && tid < 128) {
+        const char* p = (const char*)(units + (size_t)(2 * (g + ahead)) * RR) + (size_t)tid * 128;     // 16 KB = 128 lines
+        asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+    }
+    double4 u0, u1;
+    const double* p0 = units + (size_t)(2 * g) * RR + tid * 4;
+    const double* p1 = units + (size_t)(2 * g + 1) * RR + tid * 4;
+    if (MODE == 3) {
+        asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(u0.x), "=d"(u0.y), "=d"(u0.z), "=d"(u0.w) : "l"(p0), "l"(keep));
+        asm volatile("ld.global.L2::cache_hint.v4.f64 {%0,%1,%2,%3}, [%4], %5;" : "=d"(u1.x), "=d"(u1.y), "=d"(u1.z), "=d"(u1.w) : "l"(p1), "l"(keep));
+    } else { u0 = *(const double4*)p0; u1 = *(const double4*)p1; }
+    __syncthreads();
+    for (int i = 0; i < gsz; ++i) {
+        double a = sw[i][0], b = sw[i][1];
+        double* dst = out + (size_t)sr[i] * RR + tid * 4;
+        double x0 = a * u0.x + b * u1.x, x1 = a * u0.y + b * u1.y, x2 = a * u0.z + b * u1.z, x3 = a * u0.w + b * u1.w;
+        if (MODE != 1) asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" :: "l"(dst), "d"(x0), "d"(x1), "d"(x2), "d"(x3), "l"(pol) : "memory");
+        else asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(dst), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
+    }
+}
+
 int main() {
     const long long N = 1000000; const int gsz = 64; const int G = (int)(N / gsz);
     double *units, *w, *out; long long* rows;
@@ -374,6 +409,17 @@ int main() {
 
 
     cudaMemcpy(rows, rnd.data(), sizeof(long long) * N, cudaMemcpyHostToDevice);
+
+    cudaMemcpy(rows, rnd.data(), sizeof(long long) * N, cudaMemcpyHostToDevice);
+    run("Q evict_first stores", [&] { k_q<0><<<G, 256>>>(units, w, rows, gsz, out, G, 0); });
+    for (int ahead : {1200, 2400, 4800}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "Q L2 prefetch ahead=%d", ahead);
+        run(nm, [&] { k_q<1><<<G, 256>>>(units, w, rows, gsz, out, G, ahead); });
+        snprintf(nm, sizeof nm, "Q prefetch+evict_first %d", ahead);
+        run(nm, [&] { k_q<2><<<G, 256>>>(units, w, rows, gsz, out, G, ahead); });
+    }
+    run("Q evict_last ld+evict_first st", [&] { k_q<3><<<G, 256>>>(units, w, rows, gsz, out, G, 0); });
     for (int mult : {4, 6, 8}) {
         char nm[64];
         snprintf(nm, sizeof nm, "P persistent prefetch 148x%d", mult);
