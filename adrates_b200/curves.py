@@ -255,8 +255,15 @@ class OISCurve(DiscountCurve):
         """d = (1 - r*annuity_prev)/(1 + r*acc); coupon dates that are not quoted
         maturities are filled in on demand with exp(interp(ln r)) par rates; annuities are
         memoised by round(t, 2) (ois_curve.py:156-212)."""
+        times, dfs = self._path_a_scan([float(r) for r in self.swap_rates])
+        self._times = np.array(times, dtype=np.float64)
+        self._dfs = np.array(dfs, dtype=np.float64)
+
+    def _path_a_scan(self, rates):
+        """The path-A recursion on generic numbers (floats, or dual2.D2 for the node Jacobian)."""
+        from .dual2 import exp, interp, log
         st = np.array(self.swap_times, dtype=np.float64)
-        log_r = np.log(np.array(self.swap_rates, dtype=np.float64))
+        log_r = [log(r) for r in rates]
         annuity = {}
         times, dfs = [0.0], [1.0]
 
@@ -264,26 +271,37 @@ class OISCurve(DiscountCurve):
             fracs = self.year_fracs[i]
             if len(fracs) == 1:
                 acc = fracs[0]
-                d = 1.0 / (acc * rate + 1.0)
-                a = acc * d
+                d = 1.0 / (rate * acc + 1.0)
+                a = d * acc
             else:
                 acc = fracs[-1 - drop]
                 t_prev = sum(fracs[:-1 - drop])
                 key = round(t_prev, 2)
                 if key not in annuity:
-                    r_prev = float(np.exp(np.interp(t_prev, st, log_r)))
+                    r_prev = exp(interp(t_prev, st, log_r))
                     annuity[key] = node(i, t_prev, r_prev, drop + 1)
-                d = (1.0 - rate * annuity[key]) / (acc * rate + 1.0)
-                a = annuity[key] + acc * d
+                d = (1.0 - rate * annuity[key]) / (rate * acc + 1.0)
+                a = annuity[key] + d * acc
             times.append(t_mat)
             dfs.append(d)
             annuity[round(t_mat, 2)] = a
             return a
 
         for i in range(len(self._used_swaps)):
-            node(i, self.swap_times[i], self.swap_rates[i], 0)
-        self._times = np.array(times, dtype=np.float64)
-        self._dfs = np.array(dfs, dtype=np.float64)
+            node(i, self.swap_times[i], rates[i], 0)
+        return times, dfs
+
+    def path_a_jacobian(self) -> np.ndarray:
+        """d(path-A node DFs `_dfs`) / d(par rates), [nodes, R]: the map from this curve's quotes to the node DFs other
+        curves are built on (XccyCurve reads the foreign curve through them), by first-order forward mode through the
+        path-A recursion.  The reference has no such table - it chains `_mixed_hess_foreign_basis` (path-A nodes) with the
+        engine-grid Jacobian and fails on the shape mismatch (engine.py:1936-1939)."""
+        if getattr(self, "_jac_path_a", None) is None:
+            from .dual2 import D2
+            R = len(self.swap_rates)
+            _, dfs = self._path_a_scan([D2.var(float(r), k, R) for k, r in enumerate(self.swap_rates)])
+            self._jac_path_a = np.vstack([d.g if isinstance(d, D2) else np.zeros(R) for d in dfs])
+        return self._jac_path_a
 
     # -- path B plan (cached; depends on dates only) --------------------------------------
     def path_b_plan(self) -> PathBPlan:

@@ -142,6 +142,81 @@ class Gamma(_Sensitivity):
         return {rt: {ct: float(g[i, j]) for j, ct in enumerate(self.tenors)} for i, rt in enumerate(self.tenors)}
 
 
+@dataclass(frozen=True, repr=False)
+class CrossGamma:
+    """Cross-curve second-order sensitivity: risk_matrix[i, j] = 1e-8 * d2PV / d(curve-1 rate i) d(curve-2 rate j)
+    (cavour/requests/results.py:608-836: value, to_dict, df, addition, JSON / CSV export; plotting helpers are not
+    part of the valuation path)."""
+    risk_matrix: np.ndarray
+    tenors_curve1: List[str]
+    tenors_curve2: List[str]
+    curve_type_1: CurveTypes
+    curve_type_2: CurveTypes
+    currency: CurrencyTypes
+
+    def __post_init__(self):
+        arr = np.asarray(self.risk_matrix, dtype=np.float64)
+        object.__setattr__(self, "risk_matrix", arr)
+        if arr.ndim != 2:
+            raise ValueError(f"CrossGamma risk_matrix must be 2D, got {arr.ndim}D")
+        n1, n2 = arr.shape
+        if n1 != len(self.tenors_curve1):
+            raise ValueError(f"Expected {n1} tenors for curve 1, got {len(self.tenors_curve1)}")
+        if n2 != len(self.tenors_curve2):
+            raise ValueError(f"Expected {n2} tenors for curve 2, got {len(self.tenors_curve2)}")
+        if not isinstance(self.currency, CurrencyTypes):
+            raise TypeError(f"currency must be CurrencyTypes, got {type(self.currency)}")
+        if not isinstance(self.curve_type_1, CurveTypes):
+            raise TypeError(f"curve_type_1 must be CurveTypes, got {type(self.curve_type_1)}")
+        if not isinstance(self.curve_type_2, CurveTypes):
+            raise TypeError(f"curve_type_2 must be CurveTypes, got {type(self.curve_type_2)}")
+
+    @property
+    def value(self) -> Valuation:
+        return Valuation(float(np.sum(self.risk_matrix)), self.currency)
+
+    @property
+    def to_dict(self) -> dict:
+        g = self.risk_matrix
+        return {rt: {ct: float(g[i, j]) for j, ct in enumerate(self.tenors_curve2)} for i, rt in enumerate(self.tenors_curve1)}
+
+    @property
+    def df(self):
+        import pandas as pd
+        out = pd.DataFrame(self.risk_matrix, index=self.tenors_curve1, columns=self.tenors_curve2)
+        out.index.name = f"{self.curve_type_1.name}_Tenors"
+        out.columns.name = f"{self.curve_type_2.name}_Tenors"
+        return out
+
+    def to_json(self, indent: Optional[int] = 2) -> str:
+        import json
+        return json.dumps({"matrix": self.to_dict, "tenors_curve1": self.tenors_curve1, "tenors_curve2": self.tenors_curve2,
+                           "curve_type_1": self.curve_type_1.name, "curve_type_2": self.curve_type_2.name,
+                           "currency": self.currency.name, "total": float(np.sum(self.risk_matrix))}, indent=indent)
+
+    def to_csv(self, filepath: Optional[str] = None):
+        if filepath:
+            self.df.to_csv(filepath)
+            return None
+        return self.df.to_csv()
+
+    def __add__(self, other: Any) -> "CrossGamma":
+        if not isinstance(other, CrossGamma):
+            return NotImplemented
+        if (self.curve_type_1 != other.curve_type_1 or self.curve_type_2 != other.curve_type_2 or self.currency != other.currency
+                or self.tenors_curve1 != other.tenors_curve1 or self.tenors_curve2 != other.tenors_curve2):
+            raise ValueError("Cannot add CrossGamma with mismatched curves, currency, or tenors")
+        return CrossGamma(self.risk_matrix + other.risk_matrix, self.tenors_curve1, self.tenors_curve2, self.curve_type_1,
+                          self.curve_type_2, self.currency)
+
+    __radd__ = __add__
+
+    def __repr__(self):
+        n1, n2 = len(self.tenors_curve1), len(self.tenors_curve2)
+        return (f"CrossGamma({self.curve_type_1.name} x {self.curve_type_2.name}: {self.value.amount:.6g} "
+                f"{self.currency.name}, shape=[{n1}, {n2}])")
+
+
 class Risk:
     """Multi-curve container: attribute access by curve name, call with a CurveTypes
     (cavour/requests/results.py:839-942)."""
@@ -155,10 +230,16 @@ class Risk:
             self._by_curve[name] = it
         self._cross_gammas = {}
         for cg in cross_gammas or []:
-            self._cross_gammas[(cg.curve_type_1.name, cg.curve_type_2.name)] = cg
+            key = (cg.curve_type_1.name, cg.curve_type_2.name)
+            if key in self._cross_gammas:
+                raise ValueError(f"Duplicate cross-gamma for {key}")
+            self._cross_gammas[key] = cg
 
     def __call__(self, curve_type: CurveTypes):
-        return self._by_curve[curve_type.name]
+        try:
+            return self._by_curve[curve_type.name]
+        except KeyError:
+            raise ValueError(f"No risk data for curve: {curve_type.name}")
 
     def __getattr__(self, name):
         try:

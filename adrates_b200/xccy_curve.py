@@ -13,9 +13,14 @@ Bootstrap (xccy_curve.py:707-935 plan, :954-1206 recursion), per foreign-leg pay
     DF_inter(t)   = DF_prev * DF_ois(t)/DF_ois(t_prev) * exp(-basis_swap * (t - t_prev))
     at a maturity : DF(t) solves  PV_dom + spot * (-(known PV) - cashflow * DF(t)) = 0
 The reference differentiates this scan with jacrev; here the first-order tangents w.r.t. the pillar
-spreads are propagated alongside the values (exact forward mode).  Second-order tables
-(`_hess_basis`, `_mixed_hess_foreign_basis`) are not produced: the reference's XCCY GAMMA request
-fails inside its cross-gamma contraction (engine.py:1936-1939), so there is nothing to match.
+spreads are propagated alongside the values (exact forward mode).  The second-order tables the GAMMA
+request needs (xccy_curve.py:594-690) are produced on first use by running the same scan on second-order
+forward-mode numbers (dual2.D2):
+    _hess_basis                 d2(xccy DFs) / d(pillar spreads)^2                    [nodes, nb, nb]
+    _jac_foreign_curve_dfs      d(xccy DFs) / d(foreign curve node DFs)               [nodes, nf]
+    _mixed_hess_foreign_basis   d2(xccy DFs) / d(pillar spreads) d(foreign node DFs)  [nodes, nb, nf]
+For the last two the reference re-derives the payment-time foreign DFs from the foreign curve's node DFs by
+log-linear interpolation inside the differentiated function (xccy_curve.py:640-660); so does `_scan`.
 """
 from __future__ import annotations
 
@@ -139,8 +144,93 @@ class XccyCurve(DiscountCurve):
         self._dfs = np.concatenate([[1.0], df[node_idx]])
         self._repr_dfs = self._dfs
         self._jac_basis = np.vstack([np.zeros((1, nb)), ddf[node_idx]])
+        self._pts, self._node_idx = pts, node_idx
+        self._second = None                       # second-order tables, built on first use
         if self._check_refit:
             self._check_refits(1e-8)
+
+    # ---------------------------------------------------------------------------------
+    def _scan(self, basis, df_ois):
+        """The bootstrap recursion of `_bootstrap` on generic numbers (floats or dual2.D2): basis[k] = spread of pillar k,
+        df_ois[i] = foreign OIS discount factor at payment point i.  Returns the XCCY discount factor of every point."""
+        from .dual2 import exp
+        pts, spot = self._pts, self._spot_fx
+        fx, fd = np.asarray(self._foreign_curve._times, dtype=np.float64), np.asarray(self._foreign_curve._dfs, dtype=np.float64)
+        log_fd = np.log(fd)
+        df, pv_c = [None] * len(pts), [0.0] * len(pts)
+        prev = -1
+        for i, p in enumerate(pts):
+            k = p["swap"]
+            b = basis[k]
+            if p["exch"]:
+                base = p["notional"] if p["last"] else -p["notional"]
+            else:       # forward rates are payment-level constants of the differentiated function (xccy_curve.py:636-639)
+                df_s = np.exp(np.interp(p["t_start"], fx, log_fd))
+                df_e = np.exp(np.interp(p["t_end"], fx, log_fd))
+                fwd = (df_s / df_e - 1.0) / max(p["alpha"], 1e-10) if p["alpha"] > 1e-10 else 0.0
+                base = fwd * p["alpha"] * p["notional"] + (p["notional"] if p["last"] else 0.0)
+            cash = b * p["spread_sens"] + base
+            if prev < 0:
+                d_int = df_ois[i] * exp(-(b * p["time"]))
+            else:
+                q = pts[prev]
+                d_int = df[prev] * (df_ois[i] / df_ois[prev]) * exp(-(b * (p["time"] - q["time"])))
+            if p["at_val"]:
+                pv_c[i] = cash
+            elif not p["is_mat"]:
+                pv_c[i] = cash * d_int
+            if p["is_mat"]:
+                known = pv_c[i]
+                for j in range(i):
+                    if pts[j]["swap"] == k:
+                        known = known + pv_c[j]
+                num = -(-(known * spot) + p["pv_dom"])
+                den = -(cash * spot)
+                from .dual2 import value
+                df[i] = num / den if abs(value(den)) > 1e-12 else d_int
+            else:
+                df[i] = d_int
+            if not p["at_val"]:
+                prev = i
+        return df
+
+    def _second_order(self):
+        """(_hess_basis, _jac_foreign_curve_dfs, _mixed_hess_foreign_basis); row 0 is the (0, 1.0) node."""
+        if self._second is None:
+            from .dual2 import D2, exp, interp, log
+            pts, idx = self._pts, self._node_idx
+            nb = len(self._used_swaps)
+            # (a) w.r.t. the pillar spreads, payment-time foreign DFs held at their stored values (xccy_curve.py:578-606)
+            basis = [D2.var(s, k, nb) for k, s in enumerate(self.basis_spreads)]
+            dfa = self._scan(basis, [p["df_ois"] for p in pts])
+            jac = np.vstack([np.zeros((1, nb))] + [dfa[i].g[None, :] for i in idx])
+            hess = np.concatenate([np.zeros((1, nb, nb))] + [dfa[i].h[None, :, :] for i in idx])
+            if not np.allclose(jac, self._jac_basis, rtol=1e-10, atol=1e-14):
+                raise LibError("XccyCurve: second-order scan disagrees with the first-order tangents")
+            # (b) w.r.t. (pillar spreads, foreign curve node DFs): payment-time DFs by log-linear interpolation of the node DFs
+            fx = np.asarray(self._foreign_curve._times, dtype=np.float64)
+            fd = np.asarray(self._foreign_curve._dfs, dtype=np.float64)
+            nf = fd.shape[0]
+            n = nb + nf
+            basis = [D2.var(s, k, n) for k, s in enumerate(self.basis_spreads)]
+            log_nodes = [log(D2.var(d, nb + j, n)) for j, d in enumerate(fd)]
+            dfb = self._scan(basis, [exp(interp(p["time"], fx, log_nodes)) for p in pts])
+            jac_f = np.vstack([np.zeros((1, nf))] + [dfb[i].g[None, nb:] for i in idx])
+            mixed = np.concatenate([np.zeros((1, nb, nf))] + [dfb[i].h[None, :nb, nb:] for i in idx])
+            self._second = (hess, jac_f, mixed)
+        return self._second
+
+    @property
+    def _hess_basis(self):
+        return self._second_order()[0]
+
+    @property
+    def _jac_foreign_curve_dfs(self):
+        return self._second_order()[1]
+
+    @property
+    def _mixed_hess_foreign_basis(self):
+        return self._second_order()[2]
 
     # ---------------------------------------------------------------------------------
     def df(self, dt, day_count=None):

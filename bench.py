@@ -316,7 +316,10 @@ def main():
     # ---- timed region: K steps, per-step CUDA events, L2 flushed between steps ----
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.3)
+    t_wait = time.perf_counter()
+    while not sampler.rows and time.perf_counter() - t_wait < 5.0:      # nvidia-smi needs a moment before its first sample
+        time.sleep(0.05)
+    sampler.rows.clear()                                                # keep only samples taken under load
     ctx.profile(True)
     launches0 = ctx.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -334,7 +337,6 @@ def main():
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count() - launches0
     ctx.profile(False)
-    clocks = sampler.finish()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -372,6 +374,13 @@ def main():
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(e2e_s.item())
+    if len(sampler.rows) < 3:              # a short timed region: keep the GPU under the same load until there are samples
+        t_wait = time.perf_counter()
+        while len(sampler.rows) < 3 and time.perf_counter() - t_wait < 3.0:
+            # (rank-local filler: no exchange - the ranks do not run the same number of these)
+            ctx.portfolio_value(MASK, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr())
+            torch.cuda.synchronize(dev)
+    clocks = sampler.finish()              # sampled over the device-timed steps and the end-to-end steps (both under load)
     e2e_h2d = int(sum(a.nbytes for a in (h_eff, h_tenor, h_sign, h_cpn, h_notl)))
     # the public path must reproduce the resident-input results (same kernels; totals differ only in summation order)
     tot_scale = float(np.sum(np.abs(book.notional))) * world

@@ -101,10 +101,12 @@ def test_portfolio_with_dual_curve_frn_equals_sum_of_positions():
     from adrates_b200.position import Portfolio
     g = load_golden("ref_frn.json")
     m = build_bond_model(g)
-    notes = [make_frn(f) for f in g["dual"][:2]] + [make_frn(f) for f in g["frns"][:2]]
-    pos = [n.position(m) for n in notes]
+    specs = [f for f in g["dual"] + g["frns"] if f["currency"] == "GBP"][:6]         # sterling notes: dual- and single-curve
+    assert any(f["index"] != "GBP_OIS_SONIA" for f in specs) and any(f["index"] == "GBP_OIS_SONIA" for f in specs)
+    pos = [make_frn(f).position(m) for f in specs]
     total = Portfolio(pos).compute([RequestTypes.VALUE])
     each = sum(p.compute([RequestTypes.VALUE]).value.amount for p in pos)
-    assert abs(total.value.amount - each) <= 1e-10 * sum(f["face"] for f in g["dual"][:2] + g["frns"][:2])
+    assert abs(total.value.amount - each) <= 1e-10 * sum(f["face"] for f in specs)
+    assert abs(total.value.amount - sum(f["value"] for f in specs)) <= 1e-10 * sum(f["face"] for f in specs)
     with pytest.raises(LibError, match="Dual-curve FRN delta/gamma not yet implemented"):
         Portfolio(pos).compute([RequestTypes.VALUE, RequestTypes.DELTA])
