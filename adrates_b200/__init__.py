@@ -16,14 +16,14 @@ from .xccy_curve import XccyCurve
 from .curves import OISCurve, DiscountCurve
 from .models import Model
 from .position import Position, Portfolio, Engine
-from .results import Valuation, Delta, Gamma, Risk, AnalyticsResult
+from .results import Valuation, Delta, Gamma, CrossGamma, Risk, AnalyticsResult
 from .credit import Bond, FRN
 from .inflation import (InflationIndex, InflationCurve, InflationIndexTypes, InflationInterpTypes, SwapInflationLeg,
                         ZeroCouponInflationSwap, SwapYoYInflationLeg, YoYInflationSwap)
 
 __all__ = [
     "OIS", "SwapFixedLeg", "SwapFloatLeg", "XccyBasisSwap", "XccyCurve", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
-    "Valuation", "Delta", "Gamma", "Risk", "AnalyticsResult", "InflationIndex", "InflationCurve", "InflationIndexTypes",
+    "Valuation", "Delta", "Gamma", "CrossGamma", "Risk", "AnalyticsResult", "InflationIndex", "InflationCurve", "InflationIndexTypes",
     "InflationInterpTypes", "SwapInflationLeg", "ZeroCouponInflationSwap", "SwapYoYInflationLeg", "YoYInflationSwap", "Bond", "FRN",
     "LibError", "Date", "Calendar", "CalendarTypes", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
     "DayCountTypes", "FrequencyTypes", "Schedule", "to_tenor", "times_from_dates", "SwapTypes",

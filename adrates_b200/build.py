@@ -47,5 +47,37 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+JAX_ADAPTER = os.path.join(HERE, "libadrates_b200_jax.so")
+
+
+def jax_ffi_include():
+    """Directory holding xla/ffi/api/ffi.h (shipped inside jaxlib), or None."""
+    try:
+        import jaxlib
+    except ImportError:
+        return None
+    inc = os.path.join(os.path.dirname(jaxlib.__file__), "include")
+    return inc if os.path.exists(os.path.join(inc, "xla", "ffi", "api", "ffi.h")) else None
+
+
+def build_jax_ffi(force: bool = False):
+    """The XLA FFI adapter (csrc/jax_ffi_adapter.cc -> libadrates_b200_jax.so, linked against libadrates_b200.so next to
+    it).  Returns the path, or None where jaxlib's headers are not installed (this image)."""
+    inc = jax_ffi_include()
+    if inc is None:
+        return None
+    src = os.path.join(CSRC, "jax_ffi_adapter.cc")
+    if not force and os.path.exists(JAX_ADAPTER) and os.path.getmtime(JAX_ADAPTER) > os.path.getmtime(src):
+        return JAX_ADAPTER
+    build()
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-std=c++17", "-O2", "-shared", "-Xcompiler", "-fPIC", "-I", inc, "-o", JAX_ADAPTER, src,
+           "-L", HERE, "-ladrates_b200", "-Xlinker", "-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("jax ffi adapter build failed:\n" + res.stdout + res.stderr)
+    return JAX_ADAPTER
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -327,6 +327,7 @@ int cav_set_async_upload(cav_ctx* ctx, int enable) {
 
 int cav_set_stream(cav_ctx* ctx, void* stream) {
     if (!ctx) return CAV_E_INVALID;
+    if (!ctx->own_stream && ctx->stream == (cudaStream_t)stream) return CAV_OK;      // already there (a per-call FFI handler asks every time)
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

@@ -127,34 +127,48 @@ def flatten_xccy_book(book: XccyBook, max_group: int = 256):
 
 
 class XccyBookValuer:
-    """Uploads a flattened XCCY book once and revalues it: per-trade PV and the three delta ladders on the device."""
+    """Uploads a flattened XCCY book once and revalues it: per-trade PV and the three delta ladders on the device, and with
+    gamma=True also the three per-curve gamma matrices and the foreign x basis cross-gamma matrix of every trade
+    (engine.py:1769-1967; four more 32x32 rows per trade)."""
 
-    def __init__(self, book: XccyBook, device: int = 0, stream=None):
+    def __init__(self, book: XccyBook, device: int = 0, stream=None, gamma: bool = False):
         import torch
         from .position import CurveSession
         self.flat_dom, self.flat_for, (dom, forn, xc) = flatten_xccy_book(book)
         self.n = book.n_trades
+        self.gamma = gamma
         self.dsess = CurveSession.get(dom, device)
         self.xs = XccySession.get(forn, xc, device)
-        self.ctxs = (self.dsess.ctx, self.xs.ctx_for, self.xs.ctx_basis)
+        if gamma:
+            self.ctx_for, self.ctx_basis, self.ctx_cross = self.xs.second_order()
+        else:
+            self.ctx_for, self.ctx_basis, self.ctx_cross = self.xs.ctx_for, self.xs.ctx_basis, None
+        self.ctxs = tuple(c for c in (self.dsess.ctx, self.ctx_for, self.ctx_basis, self.ctx_cross) if c is not None)
         if stream is not None:
             for c in self.ctxs:
                 c.set_stream(stream)
         self.dsess.ctx.portfolio_upload(self.flat_dom)
-        self.xs.ctx_for.portfolio_upload(self.flat_for)
-        self.xs.ctx_basis.portfolio_upload(self.flat_for)
+        for c in self.ctxs[1:]:
+            c.portfolio_upload(self.flat_for)
         dev = torch.device("cuda", device)
         f64 = dict(dtype=torch.float64, device=dev)
         self.pv_dom, self.pv_for, self.pv_tmp = (torch.empty(self.n, **f64) for _ in range(3))
         self.delta_dom, self.delta_for, self.delta_basis = (torch.empty(self.n, 32, **f64) for _ in range(3))
-        self.agg = [torch.zeros(_native.NOUT, **f64) for _ in range(3)]
+        self.agg = [torch.zeros(_native.NOUT, **f64) for _ in range(4)]
+        if gamma:
+            self.delta_tmp = torch.empty(self.n, 32, **f64)
+            self.gamma_dom, self.gamma_for, self.gamma_basis, self.gamma_cross = (torch.empty(self.n, 32, 32, **f64) for _ in range(4))
 
     def value(self):
-        """PV (domestic + foreign/spot) and the domestic / foreign / basis ladders of every trade."""
-        M = _native.REQ_VALUE | _native.REQ_DELTA
-        self.dsess.ctx.portfolio_value(M, self.pv_dom.data_ptr(), self.delta_dom.data_ptr(), None, self.agg[0].data_ptr())
-        self.xs.ctx_for.portfolio_value(M, self.pv_for.data_ptr(), self.delta_for.data_ptr(), None, self.agg[1].data_ptr())
-        self.xs.ctx_basis.portfolio_value(M, self.pv_tmp.data_ptr(), self.delta_basis.data_ptr(), None, self.agg[2].data_ptr())
+        """PV (domestic + foreign/spot) and the domestic / foreign / basis ladders (and gammas) of every trade."""
+        M = _native.REQ_VALUE | _native.REQ_DELTA | (_native.REQ_GAMMA if self.gamma else 0)
+        gp = (lambda t: t.data_ptr()) if self.gamma else (lambda t: None)
+        g = (self.gamma_dom, self.gamma_for, self.gamma_basis, self.gamma_cross) if self.gamma else (None,) * 4
+        self.dsess.ctx.portfolio_value(M, self.pv_dom.data_ptr(), self.delta_dom.data_ptr(), gp(g[0]), self.agg[0].data_ptr())
+        self.ctx_for.portfolio_value(M, self.pv_for.data_ptr(), self.delta_for.data_ptr(), gp(g[1]), self.agg[1].data_ptr())
+        self.ctx_basis.portfolio_value(M, self.pv_tmp.data_ptr(), self.delta_basis.data_ptr(), gp(g[2]), self.agg[2].data_ptr())
+        if self.gamma:
+            self.ctx_cross.portfolio_value(M, self.pv_tmp.data_ptr(), self.delta_tmp.data_ptr(), gp(g[3]), self.agg[3].data_ptr())
 
     def sync(self):
         for c in self.ctxs:

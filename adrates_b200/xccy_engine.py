@@ -10,9 +10,17 @@ The domestic leg is an ordinary single-curve unit.  The foreign leg lives on a *
 N*DF_f(s)/DF_f(e)*DF_x(p), and the two foreign-leg ladders are the same valuation run against two
 Jacobian blocks ([J_for ; 0] and [0 ; J_basis]) uploaded with cav_curve_set_tables.
 
-GAMMA: the reference's XCCY gamma request fails inside its cross-gamma contraction
-(engine.py:1936-1939: 65 path-A foreign nodes of `_mixed_hess_foreign_basis` against the 263-row engine
-Jacobian), so there is no reference behaviour to match; NotImplementedError is raised.
+GAMMA (engine.py:1769-1967): three diagonal blocks, each `J^T H_pv J + sum_k grad_k C_k` of one curve with the other two
+held fixed - the domestic leg on the domestic OIS grid, the foreign leg on the stacked grid against the second-order
+blocks ([J_for ; 0], [C_for ; 0]) and ([0 ; J_basis], [0 ; H_basis]) - i.e. the same GAMMA valuation the OIS path runs,
+three times.  `H_basis` = XccyCurve._hess_basis (second-order forward mode through the XCCY bootstrap).
+Cross-gamma foreign OIS x basis (engine.py:1884-1955): `sum_i grad_xccy[i] * mixed[i, k, j] * d(foreign node DF j)/d(rate l)`.
+The reference contracts `_mixed_hess_foreign_basis` (indexed by the foreign curve's 65 path-A nodes) with the ENGINE-grid
+Jacobian (263 rows) and raises on the shape mismatch (reproduced when the goldens were generated), so its XCCY GAMMA request
+never returns.  Here the contraction uses the Jacobian of those same path-A nodes (OISCurve.path_a_jacobian), which is what
+the formula calls for; the result is flagged `beyond_reference` and validated by finite differences instead of goldens.
+The contraction itself is a fourth GAMMA valuation with J = 0 and the per-node matrices `sum_j mixed[i,k,j] J_A[j,l]` in
+place of the curve Hessian.
 """
 from __future__ import annotations
 
@@ -24,7 +32,7 @@ from .dates import times_from_dates, to_tenor
 from .error import LibError
 from .flatten import FlatPortfolio, Flattener, _Unit
 from .global_types import CurveTypes, RequestTypes, SwapTypes
-from .results import AnalyticsResult, Delta, Risk, Valuation
+from .results import AnalyticsResult, CrossGamma, Delta, Gamma, Risk, Valuation
 
 
 def _sign(leg) -> float:
@@ -153,13 +161,39 @@ class XccySession:
         self.ctx_basis = _native.Context(device)
         self.ctx_basis.curve_set_tables(d, np.vstack([np.zeros((Gf, Rb)), J_b]))
         self.n_for, self.n_basis = Rf, Rb
+        self._foreign_curve, self._xccy_curve, self._device = foreign_curve, xccy_curve, device
+        self._stacked = (d, J_f, J_b, Gf, Gx)
+        self.ctx_for2 = self.ctx_basis2 = self.ctx_cross = None
+
+    def second_order(self):
+        """Contexts with second-order tables (built on the first GAMMA request): foreign OIS block, basis block, and the
+        cross block (J = 0, per-node matrices of the foreign x basis contraction: rows = foreign par rates, columns = basis
+        pillars)."""
+        if self.ctx_for2 is None:
+            from .position import CurveSession
+            d, J_f, J_b, Gf, Gx = self._stacked
+            Rf, Rb = self.n_for, self.n_basis
+            _, _, C_f = CurveSession.get(self._foreign_curve, self._device).ctx.curve_read(jac=False, hess=True)
+            xc = self._xccy_curve
+            H_b = np.asarray(xc._hess_basis, dtype=np.float64)
+            self.ctx_for2 = _native.Context(self._device)
+            self.ctx_for2.curve_set_tables(d, np.vstack([J_f, np.zeros((Gx, Rf))]), np.concatenate([C_f, np.zeros((Gx, Rf, Rf))]))
+            self.ctx_basis2 = _native.Context(self._device)
+            self.ctx_basis2.curve_set_tables(d, np.vstack([np.zeros((Gf, Rb)), J_b]), np.concatenate([np.zeros((Gf, Rb, Rb)), H_b]))
+            # cross block: A[i, l, k] = sum_j mixed[i, k, j] * J_A[j, l]   (i: XCCY node, k: basis pillar, l: foreign par rate)
+            J_A = self._foreign_curve.path_a_jacobian()                         # [nf, Rf]
+            mixed = np.asarray(xc._mixed_hess_foreign_basis, dtype=np.float64)   # [Gx, Rb, nf]
+            A = np.einsum("ikj,jl->ilk", mixed, J_A)                             # [Gx, Rf, Rb]
+            R = max(Rf, Rb)
+            Apad = np.zeros((Gf + Gx, R, R))
+            Apad[Gf:, :Rf, :Rb] = A
+            self.ctx_cross = _native.Context(self._device)
+            self.ctx_cross.curve_set_tables(d, np.zeros((Gf + Gx, R)), Apad)
+        return self.ctx_for2, self.ctx_basis2, self.ctx_cross
 
 
 def compute_xccy(derivatives, model, request_list, device=0) -> AnalyticsResult:
     reqs = set(request_list)
-    if RequestTypes.GAMMA in reqs:
-        raise NotImplementedError("XCCY GAMMA: the reference raises in its cross-gamma contraction "
-                                  "(engine.py:1936-1939); there is no reference result to reproduce")
     if RequestTypes.CASHFLOWS in reqs:
         raise NotImplementedError("CASHFLOWS on XCCY swaps raises NameError in the reference (engine.py:1986)")
     from .position import CurveSession
@@ -176,34 +210,53 @@ def compute_xccy(derivatives, model, request_list, device=0) -> AnalyticsResult:
     except AttributeError:
         raise LibError(f"XCCY curve {name} not found in model.")
     vd = model.value_dt
-    mask = (_native.REQ_VALUE if RequestTypes.VALUE in reqs else 0) | (_native.REQ_DELTA if RequestTypes.DELTA in reqs else 0)
-    want_delta = bool(mask & _native.REQ_DELTA)
+    want_delta, want_gamma = RequestTypes.DELTA in reqs, RequestTypes.GAMMA in reqs
+    mask = _native.REQ_VALUE | (_native.REQ_DELTA if want_delta else 0)
+    gmask = mask | (_native.REQ_GAMMA if want_gamma else 0)
     # domestic legs: ordinary single-curve units on the domestic OIS curve
     dsess = CurveSession.get(dom, device)
     fl = Flattener(dom)
     for sw in derivatives:
         fl.add_components([(("XD", id(sw)), domestic_leg_unit(sw, vd), 1.0)])
     dsess.ctx.portfolio_upload(fl.finalize(dedup=False))
-    agg_dom = dsess.ctx.portfolio_value_host(mask | _native.REQ_VALUE)
+    agg_dom = dsess.ctx.portfolio_value_host(gmask)
     # foreign legs on the stacked grid
     xs = XccySession.get(forn, xc, device)
     flat = flatten_foreign_legs(derivatives, vd, forn, xc)
-    xs.ctx_for.portfolio_upload(flat)
-    agg_for = xs.ctx_for.portfolio_value_host(mask | _native.REQ_VALUE)
-    value = delta = None
+    if want_gamma:
+        ctx_for, ctx_basis, ctx_cross = xs.second_order()
+    else:
+        ctx_for, ctx_basis, ctx_cross = xs.ctx_for, xs.ctx_basis, None
+    ctx_for.portfolio_upload(flat)
+    agg_for = ctx_for.portfolio_value_host(gmask)
+    value = delta = gamma = None
     ccy = d0._domestic_currency
+    Rd, Rf, Rb = len(dom.swap_rates), xs.n_for, xs.n_basis
+    t_dom, t_for, t_bas = to_tenor(dom.swap_times), to_tenor(forn.swap_times), to_tenor(xc.swap_times)
     if RequestTypes.VALUE in reqs:
         value = Valuation(float(agg_dom[0] + agg_for[0]), ccy)
+    if want_delta or want_gamma:
+        ctx_basis.portfolio_upload(flat)
+        agg_bas = ctx_basis.portfolio_value_host(gmask)
     if want_delta:
-        xs.ctx_basis.portfolio_upload(flat)
-        agg_bas = xs.ctx_basis.portfolio_value_host(_native.REQ_VALUE | _native.REQ_DELTA)
-        Rd, Rf, Rb = len(dom.swap_rates), xs.n_for, xs.n_basis
         delta = Risk([
-            Delta(np.array(agg_dom[1:1 + Rd]), to_tenor(dom.swap_times), ccy, d0._domestic_floating_index),
-            Delta(np.array(agg_for[1:1 + Rf]), to_tenor(forn.swap_times), ccy, d0._foreign_floating_index),
-            Delta(np.array(agg_bas[1:1 + Rb]), to_tenor(xc.swap_times), ccy, CurveTypes.USD_GBP_BASIS),
+            Delta(np.array(agg_dom[1:1 + Rd]), t_dom, ccy, d0._domestic_floating_index),
+            Delta(np.array(agg_for[1:1 + Rf]), t_for, ccy, d0._foreign_floating_index),
+            Delta(np.array(agg_bas[1:1 + Rb]), t_bas, ccy, CurveTypes.USD_GBP_BASIS),
         ])
-    return AnalyticsResult(value=value, risk=delta, gamma=None)
+    if want_gamma:
+        ctx_cross.portfolio_upload(flat)
+        agg_x = ctx_cross.portfolio_value_host(_native.REQ_VALUE | _native.REQ_DELTA | _native.REQ_GAMMA)
+        block = lambda agg, r, c: np.array(agg[33:].reshape(32, 32)[:r, :c])      # noqa: E731
+        cross = CrossGamma(block(agg_x, Rf, Rb), t_for, t_bas, d0._foreign_floating_index, CurveTypes.USD_GBP_BASIS, ccy)
+        gamma = Risk([
+            Gamma(block(agg_dom, Rd, Rd), t_dom, ccy, d0._domestic_floating_index),
+            Gamma(block(agg_for, Rf, Rf), t_for, ccy, d0._foreign_floating_index),
+            Gamma(block(agg_bas, Rb, Rb), t_bas, ccy, CurveTypes.USD_GBP_BASIS),
+        ], cross_gammas=[cross])
+        gamma.beyond_reference = ("cross_gamma(foreign OIS, basis): the reference raises in this contraction "
+                                  "(engine.py:1936-1939); computed on the foreign curve's path-A nodes")
+    return AnalyticsResult(value=value, risk=delta, gamma=gamma)
 
 
 # ======================================================================================

@@ -479,12 +479,19 @@ def main():
             xval = XccyBookValuer(xbook, device=local, stream=stream.cuda_stream)
             x_prep = time.perf_counter() - t1
             ms = max_over_ranks(timed(lambda: xval.value(), reps=10, sync_all=True))
+            del xval
+            xvg = XccyBookValuer(xbook, device=local, stream=stream.cuda_stream, gamma=True)
+            ms_g = max_over_ranks(timed(lambda: xvg.value(), reps=5, sync_all=True))
             extras["xccy_config5"] = {"trades_total": nx * world, "ranks": world, "ms_per_step": ms,
-                                      "trades_per_s": nx * world / ms * 1e3, "units": int(xval.flat_for.n_units),
+                                      "trades_per_s": nx * world / ms * 1e3, "units": int(xvg.flat_for.n_units),
+                                      "ms_per_step_with_gamma": ms_g, "trades_per_s_with_gamma": nx * world / ms_g * 1e3,
+                                      "gamma_bytes_per_trade": 4 * 8192,
                                       "flatten_seconds_untimed": x_prep,
-                                      "note": "per-trade PV + three 32-wide ladder rows written (776 B/trade), VALUE + DELTA; trades "
-                                              "sharded over the ranks, no collective in the step; parity against the per-trade "
-                                              "engine path: tests/test_gpu_xccy_book.py"}
+                                      "note": "BASELINE config 5, XCCY half: per-trade PV + three 32-wide ladder rows (776 B/trade); "
+                                              "with gamma also the three per-curve 32x32 gamma matrices and the foreign x basis "
+                                              "cross-gamma matrix of every trade (32 KB/trade); trades sharded over the ranks, no "
+                                              "collective in the step; parity: tests/test_gpu_xccy_book.py, tests/test_gpu_xccy_gamma.py"}
+            del xvg
         except Exception as ex:  # noqa: BLE001
             extras["xccy_config5"] = {"error": repr(ex)}
         if world > 1:

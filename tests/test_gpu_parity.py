@@ -434,8 +434,15 @@ def test_xccy_position_and_portfolio_match_reference():
     port = Portfolio([Position(sw, m) for sw in trades]).compute([RequestTypes.VALUE, RequestTypes.DELTA])
     assert abs(port.value.amount - tot_v) <= TOL * 1e8
     assert np.max(np.abs(port.risk.USD_GBP_BASIS.risk_ladder - tot_b)) <= TOL * 1e8 * 1e-4 * 10
+    # GAMMA: three per-curve blocks and the foreign x basis cross block (validated in tests/test_gpu_xccy_gamma.py); the sum of
+    # the per-trade results is the portfolio's
+    one = [Position(sw, m).compute([RequestTypes.GAMMA]).gamma for sw in trades]
+    both = Portfolio([Position(sw, m) for sw in trades]).compute([RequestTypes.GAMMA]).gamma
+    for ct in (CurveTypes.USD_OIS_SOFR, CurveTypes.GBP_OIS_SONIA, CurveTypes.USD_GBP_BASIS):
+        tot = sum(g(ct).risk_ladder for g in one)
+        assert np.max(np.abs(both(ct).risk_ladder - tot)) <= 1e-12 * np.abs(tot).max()
     with pytest.raises(NotImplementedError):
-        Position(trades[0], m).compute([RequestTypes.GAMMA])
+        Position(trades[0], m).compute([RequestTypes.CASHFLOWS])
 
 
 def test_small_curve_seasoned_swap_and_empty_portfolio():

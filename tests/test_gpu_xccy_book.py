@@ -37,3 +37,26 @@ def test_xccy_book_matches_per_trade_path(max_offset_bd):
     tot = val.agg[0].cpu().numpy()[0] + val.agg[1].cpu().numpy()[0]
     assert abs(tot - pv.sum()) <= 1e-11 * np.abs(pv).sum()
     assert np.max(np.abs(val.agg[2].cpu().numpy()[1:33] - d_bas.sum(0))) <= 1e-11 * np.abs(d_bas).sum()
+
+
+def test_xccy_book_gammas_match_per_trade_path():
+    """Per-trade gamma rows of the batched book (three per-curve blocks + the foreign x basis cross block) against
+    compute_xccy([trade], GAMMA), whose blocks are validated by finite differences in tests/test_gpu_xccy_gamma.py."""
+    g = load_golden("ref_xccy.json")
+    m = build_xccy_model(g)
+    book = make_xccy_book(m, 300, seed=5, max_offset_bd=5, spot=g["spot_fx"])
+    val = XccyBookValuer(book, gamma=True)
+    val.value()
+    val.sync()
+    nb = len(m.curves.GBP_USD_BASIS.basis_spreads)
+    rng = np.random.Generator(np.random.PCG64(1))
+    for i in rng.choice(book.n_trades, 6, replace=False):
+        sw = book.trade(int(i))
+        ref = compute_xccy([sw], m, [RequestTypes.GAMMA]).gamma
+        pairs = ((val.gamma_dom, ref(CurveTypes.USD_OIS_SOFR).risk_ladder, 32, 32),
+                 (val.gamma_for, ref(CurveTypes.GBP_OIS_SONIA).risk_ladder, 32, 32),
+                 (val.gamma_basis, ref(CurveTypes.USD_GBP_BASIS).risk_ladder, nb, nb),
+                 (val.gamma_cross, ref.cross_gamma(CurveTypes.GBP_OIS_SONIA, CurveTypes.USD_GBP_BASIS).risk_matrix, 32, nb))
+        for got, want, r, c in pairs:
+            got = got[int(i)].cpu().numpy()[:r, :c]
+            assert np.max(np.abs(got - want)) <= 1e-10 * max(np.abs(want).max(), 1e-12), i
