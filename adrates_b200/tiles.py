@@ -31,6 +31,13 @@ NPACK = 528
 # coefficient kinds
 COEF_P, COEF_PW0, COEF_PW1, COEF_PW0SQ, COEF_PW1SQ, COEF_PW0W1 = range(6)
 
+# Plan modes.  MODE_TABLE: p (v v^T + w0 H_a + w1 H_b) is expanded into up to five table rows per term (H_a, H_b, G_aa, G_bb,
+# G_ab).  MODE_SYRK: only the curve-Hessian part sum_m p w_m H_{n_m} goes through table rows (one or two H rows per term, K
+# shrinks from ~5 to ~1 row per term once neighbouring terms share a node); the rank-one part sum_i p_i v_i v_i^T,
+# v_i = w0 g_a + w1 g_b, is a per-unit symmetric rank-k update the kernel evaluates on chip from the 67 KB g table
+# (k_units_syrk) - no table rows, no pair rows.
+MODE_TABLE, MODE_SYRK = 0, 1
+
 
 @dataclass
 class TilePlan:
@@ -50,6 +57,7 @@ class TilePlan:
     tile_mask: np.ndarray     # u32 [n_tiles] bit q set = pillar perm[q] can be non-zero in this tile's Greeks
     n_table_rows: int         # 3*G + n_pair_rows (+1 zero row appended by the library)
     leftover_units: np.ndarray  # i32 units not covered by tiles (generic kernel)
+    mode: int = 0             # MODE_TABLE: every product of log-DF gradients is a table row; MODE_SYRK: H rows only (see below)
 
     @property
     def max_k(self) -> int:
@@ -93,7 +101,7 @@ def tile_class(mask: int) -> int:
 
 
 def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = None, merge: bool = True,
-               permute: bool = True) -> TilePlan:
+               permute: bool = True, mode: int = MODE_TABLE) -> TilePlan:
     """flat: FlatPortfolio with n_pairs == 2.  G: number of curve nodes.  support: u32 [G] pillar masks of the
     nodes (node_support_masks) or None = every pillar is active everywhere (no column compaction)."""
     if flat.n_pairs != 2:
@@ -142,7 +150,11 @@ def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = No
         open_rows = {}
         for j, kk in enumerate(ks):
             knd, na, nb = int(kk >> 40), int((kk >> 20) & 0xFFFFF), int(kk & 0xFFFFF)
-            if knd == 0:
+            if mode == MODE_SYRK:
+                emit(open_rows, row_H(na, G), j, COEF_PW0)          # a grid snap has w0 = 1: p H_a (+ p g_a g_a^T on chip)
+                if knd == 2:
+                    emit(open_rows, row_H(nb, G), j, COEF_PW1)
+            elif knd == 0:
                 emit(open_rows, row_C(na, G), j, COEF_P)
             else:
                 emit(open_rows, row_H(na, G), j, COEF_PW0)
@@ -195,7 +207,7 @@ def plan_tiles(flat, G: int, min_group: int = 1, support: np.ndarray | None = No
         np.concatenate(t_units).astype(np.int32) if n_tiles else np.zeros(0, dtype=np.int32),
         i32(t_kstart), i32(t_kcount), i32(t_npos), i32(k_row), i32(k_pos), i32(k_coef), i32(k_pos2), i32(k_coef2), perm,
         pairs.reshape(-1), np.array(t_mask, dtype=np.uint32), 3 * G + len(pair_index),
-        np.array(leftover, dtype=np.int32))
+        np.array(leftover, dtype=np.int32), mode)
 
 
 def packed_index(j: int, k: int) -> int:

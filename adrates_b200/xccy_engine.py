@@ -142,9 +142,8 @@ class XccySession:
         key = (device, id(foreign_curve), id(xccy_curve))
         if key not in cls._cache:
             if len(cls._cache) >= 8:
-                old = cls._cache.pop(next(iter(cls._cache)))
-                old.ctx_for.close()
-                old.ctx_basis.close()
+                # the oldest session leaves the cache; its contexts are freed with its last reference (a caller may hold it)
+                cls._cache.pop(next(iter(cls._cache)))
             cls._cache[key] = XccySession(foreign_curve, xccy_curve, device)
         return cls._cache[key]
 
@@ -357,7 +356,7 @@ def value_frn_dual_curve(frn, model, device=0) -> AnalyticsResult:
     sess = _dual_sessions.get(key)
     if sess is None:
         if len(_dual_sessions) >= 8:
-            _dual_sessions.pop(next(iter(_dual_sessions)))[0].close()
+            _dual_sessions.pop(next(iter(_dual_sessions)))
         d_i, _, _ = CurveSession.get(idx, device).ctx.curve_read(jac=False, hess=False)
         d_d, _, _ = CurveSession.get(disc, device).ctx.curve_read(jac=False, hess=False)
         ctx = _native.Context(device)

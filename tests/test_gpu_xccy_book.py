@@ -57,6 +57,10 @@ def test_xccy_book_gammas_match_per_trade_path():
                  (val.gamma_for, ref(CurveTypes.GBP_OIS_SONIA).risk_ladder, 32, 32),
                  (val.gamma_basis, ref(CurveTypes.USD_GBP_BASIS).risk_ladder, nb, nb),
                  (val.gamma_cross, ref.cross_gamma(CurveTypes.GBP_OIS_SONIA, CurveTypes.USD_GBP_BASIS).risk_matrix, 32, nb))
+        N = book.dom_notional[i]
+        T = float((sw._maturity_dt - sw._effective_dt) / 365.0) + 1.0
         for got, want, r, c in pairs:
             got = got[int(i)].cpu().numpy()[:r, :c]
-            assert np.max(np.abs(got - want)) <= 1e-10 * max(np.abs(want).max(), 1e-12), i
+            # natural magnitude of a gamma entry: notional x 1e-8 x T^2 (a par floating leg's own-curve gamma is exactly 0 on
+            # the per-trade path and round-off of weighted unit rows on the batched one)
+            assert np.max(np.abs(got - want)) <= 1e-10 * max(np.abs(want).max(), N * 1e-8 * T * T), i

@@ -29,14 +29,15 @@ def sym_tables(d, J, C, pairs):
     return np.vstack(rows)
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("dedup", [True, False])
-def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup):
+def test_tile_gemm_matches_per_term_evaluation(ref_curves, dedup, mode):
     cv = ref_curves["gbp_readme_lzr"]
     vd, swaps = make_calibration_swaps(cv)
     curve = OISCurve(vd, swaps, InterpTypes[cv["interp"]])
     book = make_book(curve, 400, seed=9, max_offset_bd=40)
     flat = flatten_book(book, dedup=dedup)
-    check_tile_gemm(flat, cv, book.notional)
+    check_tile_gemm(flat, cv, book.notional, mode)
 
 
 @pytest.mark.parametrize("dedup", [True, False])
@@ -53,7 +54,7 @@ def test_tile_gemm_on_bond_books(ref_curves, dedup):
     check_tile_gemm(flat, cv, spec["face_value"])
 
 
-def check_tile_gemm(flat, cv, notional):
+def check_tile_gemm(flat, cv, notional, mode=0):
     """numpy emulation of the tiled Greeks kernel (coefficient tile x symmetric tables) on `flat` with the plan
     `plan_tiles` gives it, against the per-term evaluation of the same flat arrays."""
     plan = orc.plan_path_b(cv["swap_times"], cv["year_fracs"])
@@ -61,8 +62,10 @@ def check_tile_gemm(flat, cv, notional):
     support = node_support_masks(plan["swap"], plan["prev"], plan["acc"])
     for i in range(len(d)):      # the structural masks are exactly the non-zero pattern of the Jacobian rows
         assert [int(support[i]) >> r & 1 for r in range(32)] == [int(x != 0.0) for x in np.pad(J[i], (0, 32 - J.shape[1]))]
-    tp = plan_tiles(flat, len(d), support=support)
-    assert len(tp.leftover_units) == 0 and tp.tile_mask.shape == (tp.n_tiles,)
+    tp = plan_tiles(flat, len(d), support=support, mode=mode)
+    assert len(tp.leftover_units) == 0 and tp.tile_mask.shape == (tp.n_tiles,) and tp.mode == mode
+    if mode == 1:
+        assert np.all(tp.k_row < len(d)) and np.all((tp.k_coef == 1) | (tp.k_coef == 2)) and len(tp.pairs) == 0
     covered = np.sort(tp.tile_units[tp.tile_units >= 0])
     assert np.array_equal(covered, np.arange(flat.n_units))
     T = sym_tables(d, J, C, tp.pairs.reshape(-1, 2))
@@ -93,6 +96,17 @@ def check_tile_gemm(flat, cv, notional):
             A[s] += np.where(two, table2[np.where(two, coef2, 0), np.arange(kc)], 0.0)
             u_pv[u] = (flat.amt[i0:i0 + P] * np.exp(w[i0:i0 + P, 0] * L[nd[i0:i0 + P, 0]] + w[i0:i0 + P, 1] * L[nd[i0:i0 + P, 1]])).sum()
         Cm = A @ T[rows]
+        if mode == 1:        # MODE_SYRK: the rank-one part sum_i p_i v_i v_i^T per unit, v_i = w0 g_a + w1 g_b, evaluated directly
+            g = 1e-4 * J / d[:, None]
+            gp = np.pad(g, ((0, 0), (0, 32 - g.shape[1])))
+            jj, kk = np.array([(j, k) for j in range(32) for k in range(j + 1)]).T
+            for s, u in enumerate(units):
+                if u < 0:
+                    continue
+                i = np.arange(flat.unit_offsets[u], flat.unit_offsets[u + 1])
+                p = flat.amt[i] * np.exp(w[i, 0] * L[nd[i, 0]] + w[i, 1] * L[nd[i, 1]])
+                v = w[i, 0, None] * gp[nd[i, 0]] + w[i, 1, None] * gp[nd[i, 1]]
+                Cm[s, :NPACK] += ((p[:, None] * v).T @ v)[jj, kk]
         # column compaction: everything outside the tile's active pillars is structurally zero
         pos_of = np.argsort(tp.perm)              # the masks are in permuted pillar order
         act = np.array([(int(tp.tile_mask[t]) >> int(pos_of[r])) & 1 for r in range(32)], dtype=bool)
