@@ -223,8 +223,13 @@ int launch_mma_classes(cav_ctx* ctx, const SimtArgs& ga) {
 
 template <int K>
 void launch_expand_rows(cav_ctx* ctx, double* pv, double* delta) {
-    k_expand_rows<K><<<(unsigned)((ctx->n_trades + 8 * XR_ROWS - 1) / (8 * XR_ROWS)), 256, 0, ctx->stream>>>(
-        ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->u_pv, ctx->u_delta, pv, delta);
+    static const int variant = [] { const char* e = std::getenv("CAV_EXPAND_ROWS"); return e ? std::atoi(e) : 2; }();
+    if (variant == 2)       // a half-warp per row, 16-byte accesses
+        k_expand_rows2<K><<<(unsigned)((ctx->n_trades + 8 * XR2_ROWS - 1) / (8 * XR2_ROWS)), 256, 0, ctx->stream>>>(
+            ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->u_pv, ctx->u_delta, pv, delta);
+    else
+        k_expand_rows<K><<<(unsigned)((ctx->n_trades + 8 * XR_ROWS - 1) / (8 * XR_ROWS)), 256, 0, ctx->stream>>>(
+            ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->u_pv, ctx->u_delta, pv, delta);
     ctx->launches++;
 }
 

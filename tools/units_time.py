@@ -23,3 +23,5 @@ for r in range(6):
     best = [min(a, b) for a, b in zip(best, ms)]
 print(f"{layout} n={n} units={flat.n_units}: units {best[0]:.3f} ms  expand {best[1]:.3f} ms  totals {best[2]:.3f} ms  "
       f"-> {1e6 / n * best[0]:.3f} ms per 1M units-stage")
+# checksum of the results (bit-identity of kernel variants across processes)
+print("checksum", float(gm[:: max(1, n // 1000)].sum().item()), float(dl.sum().item()), float(agg[0].item()))
