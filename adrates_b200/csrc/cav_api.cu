@@ -7,6 +7,7 @@
 void cav_book_free(cav_ctx* ctx);      // cav_book.cu
 void cav_comm_free(cav_ctx* ctx);      // cav_comm.cu
 int cav_comm_reduce(cav_ctx* ctx, const double* partials, int64_t rows, double* totals);
+extern "C" int cav_book_scen_queries(cav_ctx* ctx);      // cav_book.cu: device-side dedup of the DF queries
 extern "C" void cav_book_set_plan(cav_ctx* ctx, const int32_t* node_swap, const int32_t* node_prev, const double* node_acc, int n_nodes);
 
 namespace {
@@ -235,6 +236,25 @@ void launch_expand_rows(cav_ctx* ctx, double* pv, double* delta) {
 
 }  // namespace
 
+// bootstrap + tangents: the entry-parallel kernel when its history fits shared memory, else the single-CTA one
+static cudaError_t launch_bootstrap(cav_ctx* ctx) {
+    static const int variant = [] { const char* e = std::getenv("CAV_BOOTSTRAP"); return e ? std::atoi(e) : 2; }();
+    const size_t smem = sizeof(double) * (((size_t)ctx->n_slots + 1) / 2 * 2 + 2 * (size_t)ctx->n_slots * CAV_RW + 2 * (size_t)ctx->G) +
+                        sizeof(int) * 3 * (size_t)ctx->G;
+    if (variant == 2 && ctx->node_slot && smem <= 200 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_bootstrap_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k_bootstrap_rows<<<ctx->order >= 2 ? CAV_RW : 1, 32, smem, ctx->stream>>>(ctx->G, ctx->order, ctx->n_slots, ctx->rates, ctx->node_acc,
+                                                                               ctx->node_swap, ctx->node_prev, ctx->node_slot, ctx->df,
+                                                                               ctx->P, ctx->jac, ctx->dP, ctx->hess);
+    } else {
+        k_bootstrap<<<1, 1024, 0, ctx->stream>>>(ctx->G, ctx->order, ctx->rates, ctx->node_acc, ctx->node_swap, ctx->node_prev,
+                                                 ctx->df, ctx->P, ctx->jac, ctx->dP, ctx->hess, ctx->d2P);
+    }
+    ctx->launches++;
+    return cudaGetLastError();
+}
+
 extern "C" {
 
 int cav_version(void) { return 100; }
@@ -279,7 +299,7 @@ void cav_destroy(cav_ctx* ctx) {
     cav_book_free(ctx);
     cav_comm_free(ctx);
     dev_free(ctx, &ctx->rates); dev_free(ctx, &ctx->node_time); dev_free(ctx, &ctx->node_acc);
-    dev_free(ctx, &ctx->node_swap); dev_free(ctx, &ctx->node_prev);
+    dev_free(ctx, &ctx->node_swap); dev_free(ctx, &ctx->node_prev); dev_free(ctx, &ctx->node_slot);
     dev_free(ctx, &ctx->df); dev_free(ctx, &ctx->P); dev_free(ctx, &ctx->jac); dev_free(ctx, &ctx->dP);
     dev_free(ctx, &ctx->hess); dev_free(ctx, &ctx->d2P);
     dev_free(ctx, &ctx->L); dev_free(ctx, &ctx->g); dev_free(ctx, &ctx->Hf); dev_free(ctx, &ctx->Cf);
@@ -412,17 +432,29 @@ int cav_curve_build(cav_ctx* ctx, int interp_method, const double* swap_rates, i
     CK(dev_alloc(ctx, &ctx->d2P, order >= 2 ? G * CAV_RR : 0));
     CK(dev_alloc(ctx, &ctx->Hf, order >= 2 ? G * CAV_RR : 0));
     CK(dev_alloc(ctx, &ctx->Cf, order >= 2 ? G * CAV_RR : 0));
-    k_bootstrap<<<1, 1024, 0, ctx->stream>>>(n_nodes, order, ctx->rates, ctx->node_acc, ctx->node_swap,
-                                             ctx->node_prev, ctx->df, ctx->P, ctx->jac, ctx->dP, ctx->hess,
-                                             ctx->d2P);
+    {   // history slots of the entry-parallel bootstrap: one per node that a later node's annuity refers to
+        std::vector<int> slot((size_t)n_nodes, -1);
+        int ns = 0;
+        for (int i = 0; i < n_nodes; ++i)
+            if (node_prev[i] >= 0 && slot[node_prev[i]] < 0) slot[node_prev[i]] = 0;
+        for (int i = 0; i < n_nodes; ++i)
+            if (slot[i] == 0) slot[i] = ns++;
+        CK(upload(ctx, &ctx->node_slot, slot.data(), G));
+        CK(cudaStreamSynchronize(ctx->stream));          // `slot` is a local
+        ctx->n_slots = ns;
+    }
+    const bool grid_changed = ctx->G != n_nodes || ctx->R != n_rates;
+    ctx->G = n_nodes;
+    ctx->order = order;
+    CK(launch_bootstrap(ctx));
     k_tables<<<n_nodes, 1024, 0, ctx->stream>>>(order, ctx->df, ctx->jac, ctx->hess, ctx->L, ctx->g, ctx->Hf,
                                                 ctx->Cf);
-    ctx->launches += 2;
+    ctx->launches += 1;
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));   // `padded` and host inputs may go out of scope
     // a portfolio was validated against the old grid: a grid of another size invalidates it (its node indices, tile plan
     // and DF-query cache); a same-sized grid keeps it, the caller vouches that the plan is the same
-    if (ctx->G != n_nodes || ctx->R != n_rates) {
+    if (grid_changed) {
         ctx->portfolio_valid = false; ctx->tiles_valid = false; ctx->sq_valid = false; ctx->row_tables_valid = false;
     }
     cav_book_set_plan(ctx, node_swap, node_prev, node_acc, n_nodes);
@@ -441,10 +473,9 @@ int cav_curve_rebuild_dev(cav_ctx* ctx, const double* swap_rates_dev) {
     if (ctx->order < 0 || !ctx->has_plan) return fail(ctx, CAV_E_STATE, "cav_curve_rebuild_dev: build a curve from a plan first");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->rates, swap_rates_dev, sizeof(double) * ctx->R, cudaMemcpyDeviceToDevice, ctx->stream));
-    k_bootstrap<<<1, 1024, 0, ctx->stream>>>(ctx->G, ctx->order, ctx->rates, ctx->node_acc, ctx->node_swap, ctx->node_prev,
-                                             ctx->df, ctx->P, ctx->jac, ctx->dP, ctx->hess, ctx->d2P);
+    CK(launch_bootstrap(ctx));
     k_tables<<<ctx->G, 1024, 0, ctx->stream>>>(ctx->order, ctx->df, ctx->jac, ctx->hess, ctx->L, ctx->g, ctx->Hf, ctx->Cf);
-    ctx->launches += 2;
+    ctx->launches += 1;
     ctx->tsym_valid = false;
     ctx->tables_ok = false;
     CK(cudaGetLastError());
@@ -1211,6 +1242,12 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
 // Distinct DF queries of the uploaded single-DF terms (host hash over the term arrays, once per upload).
 static int ensure_scen_queries(cav_ctx* ctx) {
     if (ctx->sq_valid) return CAV_OK;
+    static const bool on_device = [] { const char* e = std::getenv("CAV_SCEN_DEDUP"); return e ? std::atoi(e) != 0 : true; }();
+    if (on_device) {          // hash-table grouping on the device: no copy of the term arrays back to the host
+        const int rc = cav_book_scen_queries(ctx);
+        if (rc == CAV_OK) { ctx->sq_valid = true; return CAV_OK; }
+        if (rc != CAV_E_UNSUPPORTED) return rc;
+    }
     const size_t nt = (size_t)ctx->n_terms;
     std::vector<int> node(2 * nt);
     std::vector<double> w(2 * nt);

@@ -66,6 +66,7 @@ struct BookScratch {
     unsigned* unit_mask = nullptr;
     int32_t *grp_cnt = nullptr, *grp_start = nullptr, *kcount = nullptr, *kstart = nullptr, *gtiles = nullptr, *tstart = nullptr;
     int32_t* pair_index = nullptr;
+    int32_t *sq_slot = nullptr, *sq_leader = nullptr, *sq_rank = nullptr;     // scenario DF-query dedup
     int32_t *t_units = nullptr, *t_kstart = nullptr, *t_kcount = nullptr, *t_npos = nullptr;   // tiles in group order
     unsigned* t_mask = nullptr;
     // final tile plan (what k_units_mma reads)
@@ -94,7 +95,7 @@ void cav_book_free(cav_ctx* ctx) {
     dev_free(ctx, &b->tab_leader); dev_free(ctx, &b->unit_slot); dev_free(ctx, &b->is_leader); dev_free(ctx, &b->lead_rank);
     dev_free(ctx, &b->unit_gid); dev_free(ctx, &b->unit_mask); dev_free(ctx, &b->grp_cnt); dev_free(ctx, &b->grp_start);
     dev_free(ctx, &b->kcount); dev_free(ctx, &b->kstart); dev_free(ctx, &b->gtiles); dev_free(ctx, &b->tstart);
-    dev_free(ctx, &b->pair_index); dev_free(ctx, &b->t_units); dev_free(ctx, &b->t_kstart); dev_free(ctx, &b->t_kcount);
+    dev_free(ctx, &b->pair_index); dev_free(ctx, &b->sq_slot); dev_free(ctx, &b->sq_leader); dev_free(ctx, &b->sq_rank); dev_free(ctx, &b->t_units); dev_free(ctx, &b->t_kstart); dev_free(ctx, &b->t_kcount);
     dev_free(ctx, &b->t_npos); dev_free(ctx, &b->t_mask); dev_free(ctx, &b->tile_units); dev_free(ctx, &b->tile_kstart);
     dev_free(ctx, &b->tile_kcount); dev_free(ctx, &b->tile_npos); dev_free(ctx, &b->pairs); dev_free(ctx, &b->tile_mask);
     dev_free(ctx, &b->k_pack); dev_free(ctx, &b->d_stats);
@@ -689,6 +690,55 @@ __global__ void k_bk_fill_i32(int32_t* p, int64_t n, int32_t v) {
     if (i < n) p[i] = v;
 }
 
+// ---- distinct discount-factor queries of the uploaded single-DF terms (scenario DF cache, cav_scenarios) ----------------
+// A query is (node a, node b, weight a, weight b); books with shared dates ask the same query from many terms.  Terms are
+// grouped by a 64-bit hash of the query in an open-addressing table; a group's leader is its first term, every term verifies
+// its query against the leader's bit for bit (a hash collision raises a flag and the caller falls back to the host
+// path), leaders are numbered in term order - the first-seen order the host-side dedup produces, so both give the same
+// arrays.
+__global__ void __launch_bounds__(256) k_sq_insert(int64_t n, const int2* __restrict__ node, const double2* __restrict__ w,
+                                                   uint64_t* tab_key, int32_t* tab_leader, unsigned tab_mask, int32_t* term_slot) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int2 nd = node[i];
+    const double2 ww = w[i];
+    uint64_t h = mix64(((uint64_t)(uint32_t)nd.x << 32) | (uint32_t)nd.y);
+    h = mix64(h ^ (uint64_t)__double_as_longlong(ww.x)) + 0x9E3779B97F4A7C15ull;
+    h = mix64(h ^ (uint64_t)__double_as_longlong(ww.y));
+    if (h == BK_EMPTY) h = 0;
+    unsigned slot = (unsigned)h & tab_mask;
+    for (;;) {
+        const unsigned long long prev = atomicCAS((unsigned long long*)&tab_key[slot], BK_EMPTY, (unsigned long long)h);
+        if (prev == BK_EMPTY || prev == h) { atomicMin(&tab_leader[slot], (int)i); term_slot[i] = (int)slot; return; }
+        slot = (slot + 1) & tab_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_sq_verify(int64_t n, const int2* __restrict__ node, const double2* __restrict__ w,
+                                                   const int32_t* __restrict__ tab_leader, const int32_t* __restrict__ term_slot,
+                                                   int32_t* is_leader, int* flag) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int L = tab_leader[term_slot[i]];
+    is_leader[i] = (L == i);
+    if (L == i) return;
+    const int2 a = node[i], b = node[L];
+    const double2 x = w[i], y = w[L];
+    if (a.x != b.x || a.y != b.y || __double_as_longlong(x.x) != __double_as_longlong(y.x) ||
+        __double_as_longlong(x.y) != __double_as_longlong(y.y)) atomicExch(flag, 1);
+}
+
+__global__ void __launch_bounds__(256) k_sq_emit(int64_t n, const int2* __restrict__ node, const double2* __restrict__ w,
+                                                 const int32_t* __restrict__ tab_leader, const int32_t* __restrict__ term_slot,
+                                                 const int32_t* __restrict__ is_leader, const int32_t* __restrict__ rank,
+                                                 int2* q_node, double2* q_w, int* term_q) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int L = tab_leader[term_slot[i]];
+    term_q[i] = rank[L];
+    if (is_leader[i]) { q_node[rank[i]] = node[i]; q_w[rank[i]] = w[i]; }
+}
+
 inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 
 // host -> device copy of one input array: pinned sources go straight to the copy engine; pageable ones are staged through
@@ -1113,6 +1163,48 @@ int cav_book_read_tiles(cav_ctx* ctx, int32_t* tile_units, int32_t* tile_kstart,
     for (size_t k = 0; k < pk.size(); ++k) { if (k_row) k_row[k] = pk[k].x; if (k_desc) k_desc[k] = pk[k].y; }
     if (perm) for (int q = 0; q < 32; ++q) perm[q] = ctx->pp.perm[q];
     if (class_begin) for (int c = 0; c <= CAV_N_CLASSES; ++c) class_begin[c] = ctx->class_begin[c];
+    return CAV_OK;
+}
+
+// Distinct DF queries of the portfolio's terms, built on the device (no device->host copy of the term arrays): fills
+// ctx->sq_node / sq_w / sq_term / sq_n.  Returns CAV_E_UNSUPPORTED on a hash collision (the caller then uses its host path).
+int cav_book_scen_queries(cav_ctx* ctx) {
+    if (!ctx->book) ctx->book = new BookScratch();
+    BookScratch* bk = ctx->book;
+    const int64_t n = ctx->n_terms;
+    if (n <= 0 || ctx->n_pairs != 2) return CAV_E_UNSUPPORTED;
+    unsigned tab_size = 1024;
+    while ((int64_t)tab_size < 2 * n) tab_size <<= 1;
+    CK(dev_alloc(ctx, &bk->tab_key, (size_t)tab_size)); CK(dev_alloc(ctx, &bk->tab_leader, (size_t)tab_size));
+    CK(dev_alloc(ctx, &bk->sq_slot, (size_t)n)); CK(dev_alloc(ctx, &bk->sq_leader, (size_t)n)); CK(dev_alloc(ctx, &bk->sq_rank, (size_t)n + 2));
+    if (!bk->d_stats) {
+        CK(cudaEventCreateWithFlags(&bk->ev_spread, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&bk->ev_inputs, cudaEventDisableTiming));
+        CK(dev_alloc(ctx, &bk->d_stats, (size_t)1));
+        CK(cudaHostAlloc((void**)&bk->h_stats, sizeof(BookStats), cudaHostAllocDefault));
+    }
+    int* flag = &bk->d_stats->err;
+    int32_t* total = bk->sq_rank + n;                     // the scan's total lands behind the ranks
+    CK(cudaMemsetAsync(flag, 0, sizeof(int), ctx->stream));
+    const int2* node = reinterpret_cast<const int2*>(ctx->node);
+    const double2* w = reinterpret_cast<const double2*>(ctx->weight);
+    k_bk_fill_u64<<<grid_for(tab_size, 256), 256, 0, ctx->stream>>>(bk->tab_key, tab_size, BK_EMPTY);
+    k_bk_fill_i32<<<grid_for(tab_size, 256), 256, 0, ctx->stream>>>(bk->tab_leader, tab_size, 0x7FFFFFFF);
+    k_sq_insert<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, node, w, bk->tab_key, bk->tab_leader, tab_size - 1, bk->sq_slot);
+    k_sq_verify<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, node, w, bk->tab_leader, bk->sq_slot, bk->sq_leader, flag);
+    ctx->launches += 4;
+    CK((scan_exclusive<int32_t, int32_t>(ctx, bk, bk->sq_leader, bk->sq_rank, n, total)));
+    int32_t h[2] = {0, 0};
+    CK(cudaMemcpyAsync(&h[0], total, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&h[1], flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (h[1]) return CAV_E_UNSUPPORTED;
+    ctx->sq_n = h[0];
+    CK(dev_alloc(ctx, &ctx->sq_node, (size_t)h[0])); CK(dev_alloc(ctx, &ctx->sq_w, (size_t)h[0])); CK(dev_alloc(ctx, &ctx->sq_term, (size_t)n));
+    k_sq_emit<<<grid_for(n, 256), 256, 0, ctx->stream>>>(n, node, w, bk->tab_leader, bk->sq_slot, bk->sq_leader, bk->sq_rank, ctx->sq_node,
+                                                        ctx->sq_w, ctx->sq_term);
+    ctx->launches++;
+    CK(cudaGetLastError());
     return CAV_OK;
 }
 

@@ -83,7 +83,8 @@ struct cav_ctx {
     int G = 0, R = 0, interp = 0, order = -1;
     bool has_plan = false;     // bootstrap plan present (needed by cav_scenarios)
     double *rates = nullptr, *node_time = nullptr, *node_acc = nullptr;
-    int *node_swap = nullptr, *node_prev = nullptr;
+    int *node_swap = nullptr, *node_prev = nullptr, *node_slot = nullptr;
+    int n_slots = 0;           // history slots of the entry-parallel bootstrap (nodes some later node's annuity refers to)
     double *df = nullptr, *P = nullptr, *jac = nullptr, *dP = nullptr, *hess = nullptr, *d2P = nullptr;
     double *L = nullptr, *g = nullptr, *Hf = nullptr, *Cf = nullptr;
 
