@@ -48,6 +48,7 @@ _SIGS = {
     "cav_scenarios": (C.c_int, [_P, _P, C.c_int, _P]),
     "cav_curve_df": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_cashflow_pv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
+    "cav_cashflow_pv_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
     "cav_book_from_arrays": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_uint32]),
     "cav_book_info": (C.c_int, [_P, _P]),
     "cav_comm_local_handle": (C.c_int, [_P, _P]),
@@ -209,6 +210,13 @@ class Context:
         self._ck(self._dll.cav_cashflow_pv(self._h, int(interp_method), _ptr(x), _ptr(d), x.shape[0], float(t_value), n,
                                            _ptr(off), _ptr(tt), _ptr(aa), _ptr(pv), C.byref(tot)))
         return pv, float(tot.value)
+
+    def cashflow_pv_dev(self, interp_method: int, node_time, node_df, t_value: float, n_trades: int, offsets_dev, t_dev, amt_dev,
+                        pv_dev, total_dev=None):
+        """cashflow_pv on device-resident cashflow arrays (raw device addresses / tensors' data_ptr()); asynchronous."""
+        x, d = _f64(node_time), _f64(node_df)
+        self._ck(self._dll.cav_cashflow_pv_dev(self._h, int(interp_method), _ptr(x), _ptr(d), x.shape[0], float(t_value), int(n_trades),
+                                               _ptr(offsets_dev), _ptr(t_dev), _ptr(amt_dev), _ptr(pv_dev), _ptr(total_dev)))
 
     # ---- portfolio
     @staticmethod

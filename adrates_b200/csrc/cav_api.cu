@@ -6,7 +6,7 @@
 
 void cav_book_free(cav_ctx* ctx);      // cav_book.cu
 void cav_comm_free(cav_ctx* ctx);      // cav_comm.cu
-int cav_comm_reduce(cav_ctx* ctx, const double* partials, int64_t rows, double* totals);
+int cav_comm_reduce(cav_ctx* ctx, const double* partials, int64_t rows, double* totals, int n_entries);
 extern "C" int cav_book_scen_queries(cav_ctx* ctx);      // cav_book.cu: device-side dedup of the DF queries
 extern "C" void cav_book_set_plan(cav_ctx* ctx, const int32_t* node_swap, const int32_t* node_prev, const double* node_acc, int n_nodes);
 
@@ -36,8 +36,8 @@ int units_grid(const cav_ctx* ctx, int64_t n_units, bool gamma, int64_t* slots) 
 }
 
 template <typename KernelT>
-void launch_units_kernel(cav_ctx* ctx, KernelT kern, const UnitsArgs& a, int grid, int rows) {
-    const size_t smem = a.partials ? (size_t)(8 / (32 / rows)) * CAV_NOUT * sizeof(double) : 0;
+void launch_units_kernel(cav_ctx* ctx, KernelT kern, const UnitsArgs& a, int grid, int rows, bool gamma) {
+    const size_t smem = a.partials ? (size_t)(8 / (32 / rows)) * (gamma ? CAV_NOUT : 40) * sizeof(double) : 0;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, 256, smem, ctx->stream>>>(a);
     ctx->launches++;
@@ -47,13 +47,13 @@ template <int NP>
 void launch_units(cav_ctx* ctx, const UnitsArgs& a, bool delta, bool gamma, int grid) {
     if (gamma) {
         switch (units_rows()) {
-            case 4: launch_units_kernel(ctx, k_units<NP, true, true, 4>, a, grid, 4); break;
-            case 8: launch_units_kernel(ctx, k_units<NP, true, true, 8>, a, grid, 8); break;
-            default: launch_units_kernel(ctx, k_units<NP, true, true, 32>, a, grid, 32); break;
-            case 16: launch_units_kernel(ctx, k_units<NP, true, true, 16>, a, grid, 16); break;
+            case 4: launch_units_kernel(ctx, k_units<NP, true, true, 4>, a, grid, 4, true); break;
+            case 8: launch_units_kernel(ctx, k_units<NP, true, true, 8>, a, grid, 8, true); break;
+            default: launch_units_kernel(ctx, k_units<NP, true, true, 32>, a, grid, 32, true); break;
+            case 16: launch_units_kernel(ctx, k_units<NP, true, true, 16>, a, grid, 16, true); break;
         }
-    } else if (delta) launch_units_kernel(ctx, k_units<NP, true, false, 32>, a, grid, 32);
-    else launch_units_kernel(ctx, k_units<NP, false, false, 32>, a, grid, 32);
+    } else if (delta) launch_units_kernel(ctx, k_units<NP, true, false, 32>, a, grid, 32, false);
+    else launch_units_kernel(ctx, k_units<NP, false, false, 32>, a, grid, 32, false);
 }
 
 template <int K>
@@ -647,6 +647,29 @@ int cav_cashflow_pv(cav_ctx* ctx, int interp_method, const double* node_time, co
     return CAV_OK;
 }
 
+int cav_cashflow_pv_dev(cav_ctx* ctx, int interp_method, const double* node_time, const double* node_df, int n_nodes,
+                        double t_value, int64_t n_trades, const int64_t* offsets_dev, const double* t_dev, const double* amt_dev,
+                        double* pv_dev, double* total_dev) {
+    if (!ctx) return CAV_E_INVALID;
+    { int rc = check_path_a_curve(ctx, "cav_cashflow_pv_dev", interp_method, node_time, node_df, n_nodes); if (rc) return rc; }
+    if (n_trades < 0 || (n_trades && (!offsets_dev || !t_dev || !amt_dev || !pv_dev)) || !(t_value >= 0.0))
+        return fail(ctx, CAV_E_INVALID, "cav_cashflow_pv_dev: null pointer, negative size or negative valuation time");
+    CK(cudaSetDevice(ctx->device));
+    if (n_trades == 0) {
+        if (total_dev) CK(cudaMemsetAsync(total_dev, 0, sizeof(double), ctx->stream));
+        return CAV_OK;
+    }
+    // the curve nodes are small and host-resident: staged in the context (pageable source: the copy returns when staged)
+    CK(upload(ctx, &ctx->cf_x, node_time, (size_t)n_nodes));
+    CK(upload(ctx, &ctx->cf_d, node_df, (size_t)n_nodes));
+    k_cashflow_pv<<<(unsigned)((n_trades + 7) / 8), 256, 2 * n_nodes * sizeof(double), ctx->stream>>>(
+        interp_method, ctx->cf_x, ctx->cf_d, n_nodes, t_value, n_trades, offsets_dev, t_dev, amt_dev, pv_dev);
+    ctx->launches++;
+    if (total_dev) { k_sum_fixed<<<1, 1024, 0, ctx->stream>>>(pv_dev, n_trades, total_dev); ctx->launches++; }
+    CK(cudaGetLastError());
+    return CAV_OK;
+}
+
 // ---------------------------------------------------------------------------- portfolio
 int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const int64_t* unit_offsets, int n_pairs,
                          const double* amt, const double* weight, const int32_t* node, int64_t n_trades, int n_comp,
@@ -1020,7 +1043,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         // a rank whose shard is empty (or that holds no portfolio at all) still takes part in the exchange, with zeros
         CK(cudaSetDevice(ctx->device));
         double* dst = agg_dev ? agg_dev : ctx->agg;
-        { int rc = cav_comm_reduce(ctx, nullptr, 0, dst); if (rc) return rc; }
+        { int rc = cav_comm_reduce(ctx, nullptr, 0, dst, CAV_NOUT); if (rc) return rc; }
         if (agg_host) {
             CK(cudaMemcpyAsync(agg_host, dst, sizeof(double) * CAV_NOUT, cudaMemcpyDeviceToHost, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
@@ -1090,10 +1113,10 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     // the read-back is left behind it
     double* const agg_dst = agg_dev ? agg_dev : ctx->agg;
     if (need_agg && all_ranks) {       // this rank's totals, pushed to every peer and summed over ranks in the same kernel
-        int rc = cav_comm_reduce(ctx, ctx->partials, rows, agg_dst);
+        int rc = cav_comm_reduce(ctx, ctx->partials, rows, agg_dst, want_g ? CAV_NOUT : 1 + CAV_RW);
         if (rc) return rc;
     } else if (need_agg) {
-        k_reduce_partials<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(ctx->partials, rows, agg_dst);
+        k_reduce_partials<<<CAV_NOUT, 256, 0, ctx->stream>>>(ctx->partials, rows, agg_dst, want_g ? CAV_NOUT : 1 + CAV_RW);
         ctx->launches++;
         CK(cudaGetLastError());
     }

@@ -58,22 +58,26 @@ __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned l
     asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
 
-// totals[e] = sum over ranks of (sum_rows partials[row][e]); one warp per entry as in k_reduce_partials
+// totals[e] = sum over ranks of (sum_rows partials[row][e]); one CTA per entry, the same fixed-order sum as k_reduce_partials
 __global__ void __launch_bounds__(256)
-k_reduce_partials_ar(const double* __restrict__ partials, int64_t n_rows, double* totals, CommArgs c)
+k_reduce_partials_ar(const double* __restrict__ partials, int64_t n_rows, double* totals, CommArgs c, int n_entries)
 {
     __shared__ int s_last;
     __shared__ int s_timeout;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int e = blockIdx.x * 8 + (tid >> 5);
-    if (e < CAV_NOUT) {
+    __shared__ double s_w[8];
+    __shared__ double s_mine;
+    const int tid = threadIdx.x;
+    const int e = blockIdx.x;
+    {
         double s = 0.0;
-        for (int64_t w = lane; w < n_rows; w += 32) s += partials[w * CAV_NOUT + e];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane < c.world) {       // lane r pushes this rank's total into peer r (its own buffer included)
-            double* slot = reinterpret_cast<double*>(c.peer[lane]) + ((size_t)c.parity * CAV_COMM_MAX + c.rank) * CAV_COMM_STRIDE;
-            slot[e] = s;
+        if (e < n_entries)          // (entries beyond: no gamma was asked for, the units stage left them undefined)
+            for (int64_t w = tid; w < n_rows; w += 256) s += partials[w * CAV_NOUT + e];
+        const double t = block_sum_fixed(s, s_w);
+        if (tid == 0) s_mine = t;
+        __syncthreads();
+        if (tid < c.world) {        // thread r pushes this rank's total into peer r (its own buffer included)
+            double* slot = reinterpret_cast<double*>(c.peer[tid]) + ((size_t)c.parity * CAV_COMM_MAX + c.rank) * CAV_COMM_STRIDE;
+            slot[e] = s_mine;
         }
     }
     __threadfence_system();          // this CTA's pushes are visible system-wide before its ticket is
@@ -121,7 +125,7 @@ void cav_comm_free(cav_ctx* ctx) {
 }
 
 // launched by value_impl in place of k_reduce_partials when CAV_REQ_ALLREDUCE is set
-int cav_comm_reduce(cav_ctx* ctx, const double* partials, int64_t rows, double* totals) {
+int cav_comm_reduce(cav_ctx* ctx, const double* partials, int64_t rows, double* totals, int n_entries) {
     CommState* cs = ctx->comm;
     if (!cs || !cs->ready) return fail(ctx, CAV_E_STATE, "CAV_REQ_ALLREDUCE: call cav_comm_init first");
     CommArgs a;
@@ -131,7 +135,7 @@ int cav_comm_reduce(cav_ctx* ctx, const double* partials, int64_t rows, double* 
     a.parity = (int)(cs->seq & 1ull);
     for (int r = 0; r < CAV_COMM_MAX; ++r) a.peer[r] = cs->peer[r < cs->world ? r : cs->rank];
     a.counter = cs->counter; a.status = cs->status;
-    k_reduce_partials_ar<<<(CAV_NOUT + 7) / 8, 256, 0, ctx->stream>>>(partials, rows, totals, a);
+    k_reduce_partials_ar<<<CAV_NOUT, 256, 0, ctx->stream>>>(partials, rows, totals, a, n_entries);
     ctx->launches++;
     CK(cudaGetLastError());
     return CAV_OK;

@@ -10,6 +10,24 @@
 #define GT_TM 16            // units per tile of the tensor-core Greeks kernel
 struct PillarPerm { unsigned char perm[32]; unsigned char pos_of[32]; };   // position -> pillar, pillar -> position
 
+#ifdef __CUDACC__
+// sum over a 256-thread CTA in a fixed order (butterfly per warp, warp sums in warp order); valid in thread 0
+__device__ __forceinline__ double block_sum_fixed(double s, double* s_w /* [8] shared */)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = s;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+    }
+    return t;                                   // valid in thread 0
+}
+
+#endif
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

@@ -196,10 +196,14 @@ k_units(UnitsArgs A)
 {
     constexpr int WPU = CAV_RW / ROWS;            // warps per unit
     constexpr int SPC = 8 / WPU;                  // unit slots per CTA
+    // portfolio partials of a slot: PV + ladder (+ gamma).  Without gamma only the first 33 entries exist: the slot tiles
+    // shrink from 8.4 KB to 320 bytes of shared memory and the partial rows the totals kernel reads from 80 MB to 2.5 MB
+    constexpr int NTOT = GAMMA ? CAV_NOUT : (1 + CAV_RW);
+    constexpr int TSTRIDE = GAMMA ? CAV_NOUT : 40;
     __shared__ double vbuf[8][CAV_RW];
     // portfolio partials live in shared memory (one 1057-double tile per unit slot), not in
     // registers: keeping 32 more accumulators per thread starves the batch of table-row loads
-    extern __shared__ double s_tot[];             // [SPC][CAV_NOUT] when A.partials != null
+    extern __shared__ double s_tot[];             // [SPC][TSTRIDE] when A.partials != null
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int64_t gw = (int64_t)blockIdx.x * 8 + wib;
@@ -208,9 +212,9 @@ k_units(UnitsArgs A)
     const int r0 = part * ROWS;
     const int64_t n_slots = (int64_t)gridDim.x * 8 / WPU;
     const bool lead = (part == 0);
-    double* my_tot = s_tot + (size_t)(wib / WPU) * CAV_NOUT;
+    double* my_tot = s_tot + (size_t)(wib / WPU) * TSTRIDE;
     if (A.partials) {
-        for (int e = threadIdx.x; e < SPC * CAV_NOUT; e += 256) s_tot[e] = 0.0;
+        for (int e = threadIdx.x; e < SPC * TSTRIDE; e += 256) s_tot[e] = 0.0;
         __syncthreads();
     }
 
@@ -313,10 +317,13 @@ k_units(UnitsArgs A)
             }
         }
     }
-    if (A.partials) {
+    if (A.partials) {          // partial rows keep the stride of the full totals; without gamma only 33 entries are written
         __syncthreads();
         double* P = A.partials + (size_t)blockIdx.x * SPC * CAV_NOUT;
-        for (int e = threadIdx.x; e < SPC * CAV_NOUT; e += 256) P[e] = s_tot[e];
+        for (int e = threadIdx.x; e < SPC * NTOT; e += 256) {
+            const int sl = e / NTOT, k = e - sl * NTOT;
+            P[(size_t)sl * CAV_NOUT + k] = s_tot[sl * TSTRIDE + k];
+        }
     }
 }
 
@@ -687,19 +694,19 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
     }
 }
 
-// totals[e] = sum_rows partials[row][e]; one warp per entry, lane-strided partial sums combined
-// in a fixed butterfly order (bitwise reproducible for a given grid)
+// totals[e] = sum_rows partials[row][e]; one CTA per entry: threads stride the rows, a fixed butterfly per warp, the eight
+// warp sums added in warp order (bitwise reproducible for a given grid).  (A warp per entry left 33 warps on the whole GPU
+// for the PV + delta request, each waiting on ~300 strided loads: 43 us for 2.5 MB.)
 __global__ void __launch_bounds__(256)
-k_reduce_partials(const double* __restrict__ partials, int64_t n_rows, double* totals)
+k_reduce_partials(const double* __restrict__ partials, int64_t n_rows, double* totals, int n_entries)
 {
-    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (e >= CAV_NOUT) return;
+    __shared__ double s_w[8];
+    const int e = blockIdx.x;
+    if (e >= n_entries) { if (threadIdx.x == 0) totals[e] = 0.0; return; }      // entries the units stage did not produce (no gamma)
     double s = 0.0;
-    for (int64_t w = lane; w < n_rows; w += 32) s += partials[w * CAV_NOUT + e];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) totals[e] = s;
+    for (int64_t w = threadIdx.x; w < n_rows; w += 256) s += partials[w * CAV_NOUT + e];
+    const double t = block_sum_fixed(s, s_w);
+    if (threadIdx.x == 0) totals[e] = t;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1060,8 +1067,11 @@ k_cashflow_pv(int method, const double* __restrict__ x, const double* __restrict
     if (tr >= n_trades) return;
     const double inv0 = 1.0 / node_df_path_a(method, sx, sd, n, t_value);
     double acc = 0.0;
-    for (int64_t c = offsets[tr] + lane; c < offsets[tr + 1]; c += 32)
-        acc += (amt[c] * node_df_path_a(method, sx, sd, n, t[c])) * inv0;
+    for (int64_t c = offsets[tr] + lane; c < offsets[tr + 1]; c += 32) {
+        const double tc = t[c];
+        // (device-resident inputs are not scanned on the host: a negative time - the reference's LibError - gives NaN)
+        acc += tc >= 0.0 ? (amt[c] * node_df_path_a(method, sx, sd, n, tc)) * inv0 : __longlong_as_double(0x7FF8000000000000ll);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if (lane == 0) pv[tr] = acc;

@@ -602,8 +602,18 @@ def main():
             dtz = (time.perf_counter() - t1) / 5
             ref = np.array([curve._node_df(float(x)) for x in tz[:64]])
             errz = float(np.max(np.abs(pvz[:32] - (az[:64] * ref).reshape(-1, 2).sum(1)) / 1e6))
+            # the same valuation on device-resident cashflows (cav_cashflow_pv_dev): nothing crosses PCIe
+            ctxz.set_stream(stream.cuda_stream)
+            o_d, t_d, a_d = (torch.from_numpy(x).to(dev) for x in (oz, tz, az))
+            pv_d = torch.empty(nz, dtype=torch.float64, device=dev)
+            tot_d = torch.empty(1, dtype=torch.float64, device=dev)
+            ms_dev = timed(lambda: ctxz.cashflow_pv_dev(curve._interp_type.value, curve._times, curve._dfs, 0.0, nz, o_d.data_ptr(),
+                                                        t_d.data_ptr(), a_d.data_ptr(), pv_d.data_ptr(), tot_d.data_ptr()), reps=10)
+            same = bool(np.array_equal(pv_d.cpu().numpy(), pvz))
             extras["zcis_cashflow_pv_config5"] = {"trades": nz, "cashflows": 2 * nz, "ms_e2e_host_buffers": dtz * 1e3,
                                                   "trades_per_s": nz / dtz, "check_scaled_err_vs_host_df": errz,
+                                                  "ms_device_resident": ms_dev, "cashflows_per_s_device_resident": 2 * nz / ms_dev * 1e3,
+                                                  "device_resident_equals_host_call": same,
                                                   "note": "discounting of the ZCIS legs on the path-A curve; the CPI index "
                                                           "arithmetic that produces the amounts is host logic"}
             ctxz.close()

@@ -177,6 +177,12 @@ int cav_curve_df(cav_ctx* ctx, int interp_method, const double* node_time, const
 int cav_cashflow_pv(cav_ctx* ctx, int interp_method, const double* node_time, const double* node_df, int n_nodes,
                     double t_value, int64_t n_trades, const int64_t* offsets, const double* t, const double* amt,
                     double* pv, double* total);
+/* cav_cashflow_pv on DEVICE-resident cashflows: offsets_dev / t_dev / amt_dev / pv_dev / total_dev (may be NULL) are device
+ * pointers, the call is asynchronous on the context stream and moves nothing but the curve nodes (host, <= 1024).  The times
+ * are not scanned on the host: a cashflow with a negative time (the reference's LibError) makes its trade's PV NaN. */
+int cav_cashflow_pv_dev(cav_ctx* ctx, int interp_method, const double* node_time, const double* node_df, int n_nodes,
+                        double t_value, int64_t n_trades, const int64_t* offsets_dev, const double* t_dev, const double* amt_dev,
+                        double* pv_dev, double* total_dev);
 
 /* ---- valuation: replaces Position.compute / Portfolio.compute ----------------------
  * (cavour/market/position/position.py:62-80, cavour/market/portfolio/portfolio.py:39-67,

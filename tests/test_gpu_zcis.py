@@ -75,3 +75,33 @@ def test_cashflow_pv_edge_cases(g):
     pv = cashflow_pv(dc, later, [[(vd.add_days(500), 1.0)]])
     want = dc.df(vd.add_days(500), DayCountTypes.ACT_365F) / dc.df(later, DayCountTypes.ACT_365F)
     assert abs(pv[0] - want) < 1e-14
+
+
+def test_cashflow_pv_on_device_resident_cashflows_equals_the_host_buffer_call():
+    """cav_cashflow_pv_dev: same kernels on caller-owned device arrays, bit-identical PVs and total; a negative time -> NaN."""
+    import torch
+    from adrates_b200 import _native
+    from adrates_b200.market_data import readme_gbp_curve
+    curve = readme_gbp_curve()
+    rng = np.random.default_rng(2)
+    n = 5000
+    cnt = rng.integers(1, 5, n)
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(cnt, out=off[1:])
+    t = rng.uniform(0.0, 45.0, int(off[-1]))
+    amt = rng.uniform(-1e6, 1e6, int(off[-1]))
+    ctx = _native.Context(0)
+    args = (curve._interp_type.value, curve._times, curve._dfs, 0.25)
+    pv_h, tot_h = ctx.cashflow_pv(*args, off, t, amt)
+    dev = torch.device("cuda", 0)
+    o_d, t_d, a_d = (torch.from_numpy(a).to(dev) for a in (off, t, amt))
+    pv_d = torch.empty(n, dtype=torch.float64, device=dev)
+    tot_d = torch.empty(1, dtype=torch.float64, device=dev)
+    ctx.cashflow_pv_dev(*args, n, o_d.data_ptr(), t_d.data_ptr(), a_d.data_ptr(), pv_d.data_ptr(), tot_d.data_ptr())
+    ctx.sync()
+    assert np.array_equal(pv_d.cpu().numpy(), pv_h) and float(tot_d.item()) == tot_h
+    t_d[int(off[17])] = -0.5
+    ctx.cashflow_pv_dev(*args, n, o_d.data_ptr(), t_d.data_ptr(), a_d.data_ptr(), pv_d.data_ptr(), None)
+    ctx.sync()
+    got = pv_d.cpu().numpy()
+    assert np.isnan(got[17]) and np.array_equal(np.delete(got, 17), np.delete(pv_h, 17))
