@@ -555,7 +555,12 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
             for (int idx = tid; idx < GT_TM * GM_PC; idx += 256) {
                 const int u = idx >> 5, j = idx & 31;
                 double p = 0.0, w0 = 0.0, w1 = 0.0;
+#ifdef MMA_DIAG_NOSCAL      // diagnostic build: no term loads, no exp
+                if (p0 + j < P && sUnit[u] >= 0) { p = 1.0 + idx; w0 = 0.75; w1 = 0.25; }
+                if (false) {
+#else
                 if (p0 + j < P && sUnit[u] >= 0) {
+#endif
                     const int64_t i = sOff[u] + p0 + j;
                     const double2 w = __ldg(reinterpret_cast<const double2*>(a.weight) + i);
                     const int2 n = __ldg(reinterpret_cast<const int2*>(a.node) + i);
@@ -606,13 +611,21 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
             }
             __syncthreads();
             // (4) C += A . B on the tensor pipe
+#ifdef MMA_DIAG_NOMMA       // diagnostic build: no K loop
+            if (ntw > 0 && a.tile_units == nullptr) {
+#else
             if (ntw > 0) {
+#endif
                 const double* A0 = sA + ar * GM_LDA + ac;
                 const double* A1 = A0 + 8 * GM_LDA;
 #pragma unroll kMmaUnroll
                 for (int k = 0; k < kc4; k += 4) {
                     const double a0 = A0[k], a1 = A1[k];
+#ifdef MMA_DIAG_BHOT        // diagnostic build: every B operand from one L1-resident table row
+                    const double* rowp = a.T + (size_t)(sRow[k + ac] & 3) * GT_NC;
+#else
                     const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC;
+#endif
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
                         if (n < ntw) {                    // warp-uniform
@@ -663,7 +676,11 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                 const int64_t row = sOut[u];
                 const double W = sW[u];
                 const double g0 = row_s[pk4[0]], g1 = row_s[pk4[1]], g2 = row_s[pk4[2]], g3 = row_s[pk4[3]];
+#ifdef MMA_DIAG_NOSTORE     // diagnostic build: gamma rows gathered from the staging tile but not written
+                if (a.out_gamma && g0 == 1.2345e-300) {
+#else
                 if (a.out_gamma) {
+#endif
                     double* dst = a.out_gamma + (size_t)row * CAV_RR + oj * CAV_RW + ok4;
                     asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
                 }
