@@ -150,21 +150,40 @@ cudaError_t wait_trade_arrays(cav_ctx* ctx) {
 #endif
 #define MMA_CLASSES(X) X(1, 4) X(2, 4) X(3, MMA_MINB34) X(4, MMA_MINB34) X(6, 2) X(9, 2)
 
+// Two kernels run the tile GEMM: k_units_mma (every warp walks all phases of a tile; 3-4 CTAs per SM) and k_units_mma_ws
+// (warp-specialised: front warps build coefficient tiles ahead of the mma warps; 2 CTAs per SM).  Measured per size class on
+// 300k private units (profiles/r02_ws_units_mma.txt): 3.53 vs 3.25 ms per 1M units; on the 25 100 shared units of the 1M-trade
+// dedup book (classes forked onto side streams, a few hundred tiles each) 0.149 vs 0.156 ms - the specialised kernel pays
+// where a class launch fills the machine several times over.  CAV_UNITS_WS = 0 / 1 forces one of them.
+template <int NT>
+bool mma_use_ws(const cav_ctx* ctx, int n_tiles) {
+    static const int forced = [] { const char* e = std::getenv("CAV_UNITS_WS"); return e ? std::atoi(e) : -1; }();
+    if (forced >= 0) return forced != 0;
+    return NT < 6 && n_tiles > 8 * ctx->sm_count;
+}
+constexpr int ws_minb(int nt) { return nt >= 6 ? 1 : 2; }      // the two largest classes spill at 80 registers
+
 template <int NT, int MINB>
-int mma_ctas_per_sm() {
+int mma_ctas_per_sm(bool ws) {
+    static int n_ws = [] {
+        int v = 0;
+        cudaFuncSetAttribute(k_units_mma_ws<NT, ws_minb(NT)>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaSmemWs<NT>::BYTES);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_units_mma_ws<NT, ws_minb(NT)>, GW_THREADS, MmaSmemWs<NT>::BYTES) != cudaSuccess || v < 1) v = 1;
+        return v;
+    }();
     static int n = [] {
         int v = 0;
         cudaFuncSetAttribute(k_units_mma<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MmaSmem<NT>::BYTES);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, k_units_mma<NT, MINB>, 256, MmaSmem<NT>::BYTES) != cudaSuccess || v < 1) v = 1;
         return v;
     }();
-    return n;
+    return ws ? n_ws : n;
 }
 
 // grid of one class launch (persistent CTAs, at most the resident capacity of the class)
 template <int NT, int MINB>
 int mma_grid(const cav_ctx* ctx, int n_tiles) {
-    const int cap = mma_ctas_per_sm<NT, MINB>() * ctx->sm_count;
+    const int cap = mma_ctas_per_sm<NT, MINB>(mma_use_ws<NT>(ctx, n_tiles)) * ctx->sm_count;
     return n_tiles < cap ? n_tiles : cap;
 }
 
@@ -186,7 +205,21 @@ void launch_mma(cav_ctx* ctx, SimtArgs ga, int t0, int t1, cudaStream_t st, int6
     const int grid = mma_grid<NT, MINB>(ctx, t1 - t0);
     if (ga.partials) ga.partials += (size_t)(*row0) * CAV_NOUT;
     *row0 += grid;
-    k_units_mma<NT, MINB><<<grid, 256, MmaSmem<NT>::BYTES, st>>>(ga, t0, t1, 3 * ctx->G + ctx->n_pair_rows);
+    if (mma_use_ws<NT>(ctx, t1 - t0)) {
+#ifdef MMA_DIAG_CLOCKS
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_ws_clocks, z, sizeof(z));
+#endif
+        k_units_mma_ws<NT, ws_minb(NT)><<<grid, GW_THREADS, MmaSmemWs<NT>::BYTES, st>>>(ga, t0, t1, 3 * ctx->G + ctx->n_pair_rows);
+#ifdef MMA_DIAG_CLOCKS
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(z, g_ws_clocks, sizeof(z));
+        std::fprintf(stderr, "[ws clocks NT=%d grid=%d tiles=%d] per CTA (kcyc): front wait %.0f hdr %.0f loads+exp %.0f krows %.0f abuild %.0f | mma wait %.0f kloop %.0f pk4 %.0f epilogue %.0f\n",
+                     NT, grid, t1 - t0, z[0] / 1e3 / grid, z[1] / 1e3 / grid, z[2] / 1e3 / grid, z[3] / 1e3 / grid, z[4] / 1e3 / grid,
+                     z[8] / 1e3 / grid, z[9] / 1e3 / grid, z[10] / 1e3 / grid, z[11] / 1e3 / grid);
+#endif
+    } else
+        k_units_mma<NT, MINB><<<grid, 256, MmaSmem<NT>::BYTES, st>>>(ga, t0, t1, 3 * ctx->G + ctx->n_pair_rows);
     ctx->launches++;
 }
 
@@ -201,7 +234,7 @@ int launch_mma_classes(cav_ctx* ctx, const SimtArgs& ga) {
     bool small = true;
     {
         int c = 0;
-#define X(NT, MINB) small = small && (cb[c + 1] - cb[c]) <= 3 * mma_ctas_per_sm<NT, MINB>() * ctx->sm_count / 2; ++c;
+#define X(NT, MINB) small = small && (cb[c + 1] - cb[c]) <= 3 * mma_ctas_per_sm<NT, MINB>(false) * ctx->sm_count / 2; ++c;
         MMA_CLASSES(X)
 #undef X
     }

@@ -711,6 +711,506 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_units_mma_ws: the same tile GEMM with warp-specialised CTAs.  In k_units_mma every warp walks the phases of a tile one
+// after the other (term scalars, K rows, coefficient tile, K loop, epilogue) and the phases add up: diagnostic builds on
+// the private layout give skeleton 1.36 + scalars 0.35 + K loop 1.1 + row stores 0.65 = 3.5 ms per 1M units with the FP64
+// tensor pipe idle outside the K loop (profiles/r02_diag_units_mma_phases.txt).  Here warps 8-11 of the CTA ("front")
+// prepare chunk c + 1 - term scalars, K rows, coefficient tile A, unit PVs - into the other half of a double buffer
+// while warps 0-7 ("mma") run the K loop of chunk c and, after a tile's last chunk, its epilogue.  The halves change
+// hands through mbarriers (full / empty); the front warps and the mma warps use named barriers among themselves, there is no
+// CTA-wide barrier after the start.  Arithmetic and its order are those of k_units_mma: per-trade results are bit-identical.
+// ------------------------------------------------------------------------------------------
+#define GW_FRONT 128             // threads of the front warps
+#define GW_THREADS (256 + GW_FRONT)
+#ifndef GW_NBUF
+#define GW_NBUF 3                // coefficient-tile buffers in flight between the front and the mma warps
+#endif
+#ifndef GW_NSTORE
+#define GW_NSTORE 0              // 1 KB row segments per mma warp in flight to HBM as bulk stores (cp.async.bulk); 0 = plain 32-byte
+#endif                           // stores.  Measured with 3 slots: 3.65 vs 3.27 ms per 1M private units - the warps wait for the slots.
+
+template <int NT>
+struct MmaSmemWs {
+    static constexpr int NCS = 64 * NT;
+    static constexpr int LDS_ = NCS + 8;
+    static constexpr int A = 0;                                  // [GW_NBUF][16][GM_LDA] coefficient tiles
+    static constexpr int TP = A + GW_NBUF * GT_TM * GM_LDA;            // front scratch: p, w0, w1 [3][16][32]
+    static constexpr int STAGE = TP + 3 * GT_TM * GM_PC;         // mma: [8][LDS_]
+    static constexpr int TOT = STAGE + 8 * LDS_;                 // mma: [1058]
+    static constexpr int RB = TOT + 1058;                        // mma: [8 warps][GW_NSTORE][128] row segments on their way out
+    static constexpr int TW = RB + 8 * GW_NSTORE * 128;          // per tile slot: unit weights [GW_NBUF][16]
+    static constexpr int TPV = TW + GW_NBUF * GT_TM;             // per tile slot: unit PVs [GW_NBUF][16]
+    static constexpr int PVACC = TPV + GW_NBUF * GT_TM;                // front scratch [16]
+    static constexpr int OFF = PVACC + GT_TM;                    // front scratch int64 [16]
+    static constexpr int OUT = OFF + GT_TM;                      // per tile slot int64 [GW_NBUF][16]
+    static constexpr int BAR = OUT + GW_NBUF * GT_TM;            // mbarriers: full[GW_NBUF], empty[GW_NBUF]
+    static constexpr int INTS = BAR + 2 * GW_NBUF;                         // ints from here
+    // int layout: row[NBUF][GM_KC] | desc[GM_KC] | col[NBUF][NCS] | pil[32] | unit[NBUF][16] | hdr[NBUF][4] (kc4, last) | tmask[NBUF]
+    static constexpr int I_ROW = 0, I_DESC = GW_NBUF * GM_KC, I_COL = I_DESC + GM_KC, I_PIL = I_COL + GW_NBUF * NCS, I_UNIT = I_PIL + 32,
+                         I_HDR = I_UNIT + GW_NBUF * GT_TM, I_MASK = I_HDR + 4 * GW_NBUF, I_END = I_MASK + GW_NBUF + (GW_NBUF & 1);
+    static constexpr size_t BYTES = (size_t)INTS * 8 + (size_t)I_END * 4;
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" :: "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile("{ .reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=: }" :: "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bar_named(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ int bar_named_count(int id, int n, bool pred) {
+    int c;
+    asm volatile("{ .reg .pred p; setp.ne.s32 p, %1, 0; bar.red.popc.u32 %0, %2, %3, p; }" : "=r"(c) : "r"((int)pred), "r"(id), "r"(n) : "memory");
+    return c;
+}
+
+#ifdef MMA_DIAG_CLOCKS           // diagnostic build: cycles per section, summed per CTA into a.partials-free scratch (g_ws_clocks)
+__device__ unsigned long long g_ws_clocks[16];
+#define WS_T0() long long t_prev = clock64()
+#define WS_T(slot) do { const long long t_now = clock64(); t_acc[slot] += t_now - t_prev; t_prev = t_now; } while (0)
+#define WS_TDECL() long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define WS_TFLUSH(base, lead) do { if (lead) for (int q = 0; q < 8; ++q) atomicAdd(&g_ws_clocks[(base) + q], (unsigned long long)t_acc[q]); } while (0)
+#else
+#define WS_T0()
+#define WS_T(slot)
+#define WS_TDECL()
+#define WS_TFLUSH(base, lead)
+#endif
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(GW_THREADS, MINB)
+k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
+{
+    using SM = MmaSmemWs<NT>;
+    extern __shared__ double smem[];
+    double* sAall = smem + SM::A;
+    double* sTp = smem + SM::TP;
+    double* sTw0 = sTp + GT_TM * GM_PC;
+    double* sTw1 = sTw0 + GT_TM * GM_PC;
+    double* sStage = smem + SM::STAGE;
+    double* sTot = smem + SM::TOT;
+    double* sRowBuf = smem + SM::RB;
+    double* sWall = smem + SM::TW;
+    double* sPvAll = smem + SM::TPV;
+    double* sPvAcc = smem + SM::PVACC;
+    int64_t* sOff = reinterpret_cast<int64_t*>(smem + SM::OFF);
+    int64_t* sOutAll = reinterpret_cast<int64_t*>(smem + SM::OUT);
+    uint64_t* sBar = reinterpret_cast<uint64_t*>(smem + SM::BAR);          // full[GW_NBUF], empty[GW_NBUF]
+    int* sInt = reinterpret_cast<int*>(smem + SM::INTS);
+    int* sRowAll = sInt + SM::I_ROW;
+    int* sDesc = sInt + SM::I_DESC;
+    int* sColAll = sInt + SM::I_COL;
+    int* sPil = sInt + SM::I_PIL;
+    int* sUnitAll = sInt + SM::I_UNIT;
+    int* sHdr = sInt + SM::I_HDR;
+    unsigned* sMask = reinterpret_cast<unsigned*>(sInt + SM::I_MASK);
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (tid == 0) {
+        for (int q = 0; q < GW_NBUF; ++q) { mbar_init(&sBar[q], GW_FRONT / 32); mbar_init(&sBar[GW_NBUF + q], 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (tid >= 256) {
+        // ============================== front warps: up to GW_NBUF chunks ahead of the mma warps ==============================
+        // The front is a chain of dependent global loads (tile header -> unit ids -> term offsets -> terms -> log-DFs); what
+        // can be fetched ahead is: the next tile's header and unit data travel in registers while the current tile is built,
+        // and a chunk's term loads are issued together before the first exp.
+        const int ft = tid - 256, fw = ft >> 5;
+        WS_TDECL();
+        int g = 0;                                               // chunk counter of this CTA (buffer g % NBUF, use g / NBUF)
+        int tslot = 0, bslot = 0, buse = 0;                      // tile-data slot; chunk buffer and how often it has been used
+        int tile = tile_begin + blockIdx.x;
+        int nK = 0, nks = 0, nP = 0; unsigned nmask = 0u;        // header of the next tile
+        unsigned last_mask = 0u;                                 // mask of the previous tile (0 = none: an empty mask has no columns)
+        int nx_uid = -1; int64_t nx_off = 0, nx_out = 0; double nx_w = 1.0;
+        if (tile < tile_end) {
+            nK = a.tile_kcount[tile]; nks = a.tile_kstart[tile]; nP = a.tile_npos[tile]; nmask = a.tile_mask[tile];
+            if (ft < GT_TM) {
+                nx_uid = a.tile_units[tile * GT_TM + ft];
+                nx_off = nx_uid >= 0 ? a.unit_offsets[nx_uid] : 0;
+                nx_out = nx_uid >= 0 ? (a.out_index ? a.out_index[nx_uid] : nx_uid) : 0;
+                nx_w = (nx_uid >= 0 && a.unit_weight) ? a.unit_weight[nx_uid] : 1.0;
+            }
+        }
+        for (; tile < tile_end; tile += gridDim.x) {
+            const int K = nK, ks = nks, P = nP;
+            const unsigned mask = nmask;
+            const int na = __popc(mask), nc = na * (na + 1) / 2, ncols = nc + na, nnt = (ncols + 7) >> 3;
+            const int tp = tslot;
+            tslot = tslot + 1 == GW_NBUF ? 0 : tslot + 1;
+            int* sUnit = sUnitAll + tp * GT_TM;
+            int* sCol = sColAll + tp * SM::NCS;
+            int kdone = 0;
+            const int nchunks = P > 0 ? (P + GM_PC - 1) / GM_PC : 1;
+            const int tnext = tile + gridDim.x;
+            int nn_uid = -1;
+            const unsigned prev_mask = last_mask;
+            last_mask = mask;
+            for (int ch = 0; ch < nchunks; ++ch, ++g) {
+                const int b = bslot, p0 = ch * GM_PC;
+                double* sA = sAall + b * GT_TM * GM_LDA;
+                int* sRow = sRowAll + b * GM_KC;
+                WS_T0();
+                mbar_wait(&sBar[GW_NBUF + b], (buse & 1) ^ 1);
+                WS_T(0);   // the mma warps are done with this buffer (and, NBUF chunks back, with the tile slot)
+                bar_named(2, GW_FRONT);                          // the scratch arrays of the previous chunk are free
+                if (ch == 0) {
+                    if (ft < GT_TM) {
+                        sUnit[ft] = nx_uid; sOff[ft] = nx_off; sOutAll[tp * GT_TM + ft] = nx_out; sWall[tp * GT_TM + ft] = nx_w;
+                        sPvAcc[ft] = 0.0;
+                        if (tnext < tile_end) nn_uid = a.tile_units[tnext * GT_TM + ft];       // consumed after this chunk's work
+                    }
+                    if (ft >= 32 && ft < 64 && ((mask >> (ft - 32)) & 1u)) sPil[__popc(mask & ((1u << (ft - 32)) - 1u))] = ft - 32;
+                    if (ft == 64) sMask[tp] = mask;
+                    if (tnext < tile_end) { nK = a.tile_kcount[tnext]; nks = a.tile_kstart[tnext]; nP = a.tile_npos[tnext]; nmask = a.tile_mask[tnext]; }
+                    bar_named(2, GW_FRONT);
+                    if (mask == prev_mask) {                     // tiles of a signature group follow each other: same column map
+                        const int* pc = sColAll + (tp == 0 ? GW_NBUF - 1 : tp - 1) * SM::NCS;
+                        for (int cc = ft; cc < nnt * 8; cc += GW_FRONT) sCol[cc] = pc[cc];
+                    } else
+                    for (int cc = ft; cc < nnt * 8; cc += GW_FRONT) {
+                        int col = GT_NPACK + CAV_RW;             // a zero column of the tables
+                        if (cc < nc) {
+                            int j = (int)((sqrtf(8.0f * cc + 1.0f) - 1.0f) * 0.5f);
+                            while (j * (j + 1) / 2 > cc) --j;
+                            while ((j + 1) * (j + 2) / 2 <= cc) ++j;
+                            const int pj = sPil[j], pk2 = sPil[cc - j * (j + 1) / 2];
+                            col = pj * (pj + 1) / 2 + pk2;
+                        } else if (cc < ncols) col = GT_NPACK + sPil[cc - nc];
+                        sCol[cc] = col;
+                    }
+                }
+                WS_T(1);
+                // (1) term scalars of this chunk: p = amt * DF, w0, w1 for 16 units x 32 positions; (2) K rows of this chunk =
+                // the prefix of the remaining rows whose position lies in the chunk.  All first-level loads go out together.
+                constexpr int SQ = GT_TM * GM_PC / GW_FRONT;     // scalar slots per front thread
+                double2 wv[SQ]; int2 nv[SQ]; double av[SQ]; bool okq[SQ];
+#pragma unroll
+                for (int q = 0; q < SQ; ++q) {
+                    const int idx = ft + q * GW_FRONT, u = idx >> 5, j = idx & 31;
+                    okq[q] = p0 + j < P && sUnit[u] >= 0;
+                    wv[q] = make_double2(0.0, 0.0); nv[q] = make_int2(0, 0); av[q] = 0.0;
+#ifndef MMA_DIAG_NOSCAL
+                    if (okq[q]) {
+                        const int64_t i = sOff[u] + p0 + j;
+                        wv[q] = __ldg(reinterpret_cast<const double2*>(a.weight) + i);
+                        nv[q] = __ldg(reinterpret_cast<const int2*>(a.node) + i);
+                        av[q] = __ldg(a.amt + i);
+                    }
+#endif
+                }
+                int2 pk0 = make_int2(zero_row, 0), pk1 = make_int2(zero_row, 0);
+                bool in0 = false, in1 = false;
+                if (kdone + ft < K) { pk0 = __ldg(a.k_pack + ks + kdone + ft); in0 = (pk0.y & 0xFF) < p0 + GM_PC; }
+                if (ft + GW_FRONT < GM_KC && kdone + ft + GW_FRONT < K) {
+                    pk1 = __ldg(a.k_pack + ks + kdone + ft + GW_FRONT);
+                    in1 = (pk1.y & 0xFF) < p0 + GM_PC;
+                }
+                double la[SQ], lb[SQ];
+#pragma unroll
+                for (int q = 0; q < SQ; ++q) { la[q] = __ldg(a.L + nv[q].x); lb[q] = __ldg(a.L + nv[q].y); }
+#pragma unroll
+                for (int q = 0; q < SQ; ++q) {
+                    const int idx = ft + q * GW_FRONT;
+                    double p = 0.0;
+#ifdef MMA_DIAG_NOSCAL
+                    if (okq[q]) { p = 1.0 + idx; wv[q] = make_double2(0.75, 0.25); }
+#else
+                    if (okq[q]) p = av[q] * exp(wv[q].x * la[q] + wv[q].y * lb[q]);
+#endif
+                    sTp[idx] = p; sTw0[idx] = okq[q] ? wv[q].x : 0.0; sTw1[idx] = okq[q] ? wv[q].y : 0.0;
+                }
+                if (ch == 0 && ft < GT_TM) {                     // second level of the next tile's unit data (its ids have arrived by now)
+                    nx_uid = nn_uid;
+                    nx_off = nx_uid >= 0 ? a.unit_offsets[nx_uid] : 0;
+                    nx_out = nx_uid >= 0 ? (a.out_index ? a.out_index[nx_uid] : nx_uid) : 0;
+                    nx_w = (nx_uid >= 0 && a.unit_weight) ? a.unit_weight[nx_uid] : 1.0;
+                }
+                WS_T(2);
+                const int kc = bar_named_count(2, GW_FRONT, in0) + bar_named_count(2, GW_FRONT, in1);   // also publishes the scalars
+                const int kc4 = (kc + 3) & ~3;
+                if (ft < kc4) { sRow[ft] = in0 ? pk0.x : zero_row; sDesc[ft] = in0 ? pk0.y : -1; }
+                if (ft + GW_FRONT < kc4) { sRow[ft + GW_FRONT] = in1 ? pk1.x : zero_row; sDesc[ft + GW_FRONT] = in1 ? pk1.y : -1; }
+                bar_named(2, GW_FRONT);
+                WS_T(3);
+                // (3) unit PVs (fixed butterfly order) and the coefficient tile A: front warp w owns units 4w .. 4w+3.
+                // Every FP64 instruction of a front warp queues behind the DMMAs of the mma warps on the same pipe (hundreds of
+                // cycles each under load, measured), so dependent FP64 chains are what the front must avoid: a K row's
+                // descriptor is decoded once and its coefficient evaluated for the warp's four units side by side.
+                {
+                    double pv4[4];
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) pv4[uu] = sTp[(4 * fw + uu) * GM_PC + lane];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu) pv4[uu] += __shfl_xor_sync(0xffffffffu, pv4[uu], o);
+                    }
+                    if (lane < 4) {
+                        const int u = 4 * fw + lane;
+                        const double pvl = lane == 0 ? pv4[0] : lane == 1 ? pv4[1] : lane == 2 ? pv4[2] : pv4[3];
+                        const double acc = sPvAcc[u] + pvl;
+                        sPvAcc[u] = acc;
+                        if (ch == nchunks - 1) sPvAll[tp * GT_TM + u] = acc;
+                    }
+                }
+                for (int k = lane; k < kc4; k += 32) {
+                    const int d = sDesc[k];
+                    const int cf = (d >> 8) & 0xF, cf2 = (d >> 24) & 0xF;
+                    const int s1 = (cf == 1 || cf == 3 || cf == 5) ? 0 : ((cf == 2 || cf == 4) ? 1 : 2);       // factor 1: w0 / w1 / 1
+                    const int s2 = cf == 3 ? 0 : ((cf == 4 || cf == 5) ? 1 : 2);
+                    const int r1 = (cf2 == 1 || cf2 == 3 || cf2 == 5) ? 0 : ((cf2 == 2 || cf2 == 4) ? 1 : 2);
+                    const int r2 = cf2 == 3 ? 0 : ((cf2 == 4 || cf2 == 5) ? 1 : 2);
+                    const bool two = d >= 0 && cf2 != 7;
+                    double v[4];
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const int t = (4 * fw + uu) * GM_PC + (d & 31);
+                        const double x0 = sTw0[t], x1 = sTw1[t];
+                        const double f1 = s1 == 0 ? x0 : (s1 == 1 ? x1 : 1.0);
+                        const double f2 = s2 == 0 ? x0 : (s2 == 1 ? x1 : 1.0);
+                        v[uu] = d >= 0 ? sTp[t] * f1 * f2 : 0.0;
+                    }
+                    if (two) {                                   // second term feeding the same table row (same chunk)
+#pragma unroll
+                        for (int uu = 0; uu < 4; ++uu) {
+                            const int t2 = (4 * fw + uu) * GM_PC + ((d >> 16) & 31);
+                            const double y0 = sTw0[t2], y1 = sTw1[t2];
+                            const double h1 = r1 == 0 ? y0 : (r1 == 1 ? y1 : 1.0);
+                            const double h2 = r2 == 0 ? y0 : (r2 == 1 ? y1 : 1.0);
+                            v[uu] = fma(sTp[t2] * h1, h2, v[uu]);
+                        }
+                    }
+#pragma unroll
+                    for (int uu = 0; uu < 4; ++uu) sA[(4 * fw + uu) * GM_LDA + k] = v[uu];
+                }
+                if (ft == 0) { sHdr[b * 4] = kc4; sHdr[b * 4 + 1] = (ch == nchunks - 1); }
+                kdone += kc;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sBar[b]);            // this warp's share of the buffer is published
+                WS_T(4);
+#ifndef WS_NO_PREFETCH
+                if (ch == 0 && fw == 0 && tnext < tile_end) {
+                    // the next tile's terms are streamed from DRAM once (irregular books): pull their lines into L2 a tile ahead,
+                    // two lanes per unit
+                    const int pu = lane >> 1;
+                    const int64_t o = __shfl_sync(0xffffffffu, nx_off, pu);
+                    const int puid = __shfl_sync(0xffffffffu, nx_uid, pu);
+                    if (puid >= 0) {
+                        const char* w0 = reinterpret_cast<const char*>(a.weight) + o * 16;
+                        const char* a0 = reinterpret_cast<const char*>(a.amt) + o * 8;
+                        const char* n0 = reinterpret_cast<const char*>(a.node) + o * 8;
+                        const int64_t skip = (lane & 1) * 128;
+                        for (const char* q = w0 - (reinterpret_cast<uintptr_t>(w0) & 127) + skip; q < w0 + (int64_t)nP * 16; q += 256)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+                        for (const char* q = a0 - (reinterpret_cast<uintptr_t>(a0) & 127) + skip; q < a0 + (int64_t)nP * 8; q += 256)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+                        for (const char* q = n0 - (reinterpret_cast<uintptr_t>(n0) & 127) + skip; q < n0 + (int64_t)nP * 8; q += 256)
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+                    }
+                }
+#endif
+                if (++bslot == GW_NBUF) { bslot = 0; ++buse; }
+            }
+        }
+        WS_TFLUSH(0, ft == 0);
+        return;
+    }
+
+    // ================================== mma warps: K loops and epilogues ==================================
+    const int ng = tid >> 5;
+    const int ar = lane >> 2, ac = lane & 3;
+    const int oj = tid >> 3, ok4 = (tid & 7) * 4;        // epilogue: this thread owns gamma entries (oj, ok4..ok4+3)
+    if (tid < 8) sStage[tid * SM::LDS_ + SM::NCS] = 0.0;
+    double* my_tg = sTot + 33 + oj * CAV_RW + ok4;
+    my_tg[0] = my_tg[1] = my_tg[2] = my_tg[3] = 0.0;
+    if (tid <= CAV_RW) sTot[tid] = 0.0;
+
+    int tslot = 0, bslot = 0, buse = 0;
+    int n_out = 0;                                               // row segments this warp has sent (bulk-store slot = n_out % GW_NSTORE)
+    WS_TDECL();
+    for (int tile = tile_begin + blockIdx.x; tile < tile_end; tile += gridDim.x) {
+        WS_T0();
+        const int tp = tslot;
+        tslot = tslot + 1 == GW_NBUF ? 0 : tslot + 1;
+        const int* sUnit = sUnitAll + tp * GT_TM;
+        const int* sCol = sColAll + tp * SM::NCS;
+        const int64_t* sOut = sOutAll + tp * GT_TM;
+        const double* sW = sWall + tp * GT_TM;
+        const double* sPv = sPvAll + tp * GT_TM;
+        mbar_wait(&sBar[bslot], buse & 1);                       // first chunk of the tile (publishes the tile data as well)
+        WS_T(0);
+        const unsigned mask = sMask[tp];
+        const int na = __popc(mask), nc = na * (na + 1) / 2, ncols = nc + na, nnt = (ncols + 7) >> 3;
+        const int ntw = nnt > ng ? (nnt - ng + 7) >> 3 : 0;      // n-tiles of this warp: ng, ng+8, ...
+        int cn[NT];
+        double c[2][NT][2];
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            cn[n] = (n < ntw) ? sCol[(ng + 8 * n) * 8 + ar] : (GT_NPACK + CAV_RW);
+            c[0][n][0] = c[0][n][1] = c[1][n][0] = c[1][n][1] = 0.0;
+        }
+        bool last = false;
+        while (!last) {
+            const int b = bslot;
+            WS_T(1);
+            mbar_wait(&sBar[b], buse & 1);
+            WS_T(0);
+            const int kc4 = sHdr[b * 4];
+            last = sHdr[b * 4 + 1] != 0;
+            const double* sA = sAall + b * GT_TM * GM_LDA;
+            const int* sRow = sRowAll + b * GM_KC;
+#ifdef MMA_DIAG_NOMMA
+            if (ntw > 0 && a.tile_units == nullptr) {
+#else
+            if (ntw > 0) {
+#endif
+                const double* A0 = sA + ar * GM_LDA + ac;
+                const double* A1 = A0 + 8 * GM_LDA;
+#pragma unroll kMmaUnroll
+                for (int k = 0; k < kc4; k += 4) {
+                    const double a0 = A0[k], a1 = A1[k];
+                    const double* rowp = a.T + (size_t)sRow[k + ac] * GT_NC;
+#pragma unroll
+                    for (int n = 0; n < NT; ++n) {
+                        if (n < ntw) {                    // warp-uniform
+                            const double bv = __ldg(rowp + cn[n]);
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(bv));
+                            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                         : "+d"(c[1][n][0]), "+d"(c[1][n][1]) : "d"(a1), "d"(bv));
+                        }
+                    }
+                }
+            }
+            if (!last) {                                         // hand the half back; the last chunk's goes back after the epilogue
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sBar[GW_NBUF + b]);
+                if (++bslot == GW_NBUF) { bslot = 0; ++buse; }
+            }
+        }
+        WS_T(1);
+        // ---- epilogue: stage 8 units at a time, scatter to full symmetric rows ----
+        int pk4[4], pd = SM::NCS;
+        {   // real pillar r lives at position pos_of[r] of the permuted order the mask and the tables use
+            const int qj = a.pp.pos_of[oj];
+            const int ij = ((mask >> qj) & 1u) ? __popc(mask & ((1u << qj) - 1u)) : -1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int qk = a.pp.pos_of[ok4 + q];
+                const int ik = ((mask >> qk) & 1u) ? __popc(mask & ((1u << qk) - 1u)) : -1;
+                pk4[q] = (ij < 0 || ik < 0) ? SM::NCS : (ij >= ik ? ij * (ij + 1) / 2 + ik : ik * (ik + 1) / 2 + ij);
+            }
+            if (tid < CAV_RW) {
+                const int qd = a.pp.pos_of[tid];
+                if ((mask >> qd) & 1u) pd = nc + __popc(mask & ((1u << qd) - 1u));
+            }
+        }
+        // portfolio partials of this tile: two interleaved accumulator sets (units alternate) - every DFMA here waits in the
+        // FP64 pipe behind the other CTA's DMMAs, so the length of the dependent chain is what costs
+        double tg[2][4] = {{0.0, 0.0, 0.0, 0.0}, {0.0, 0.0, 0.0, 0.0}}, tdl[2] = {0.0, 0.0}, tpv[2] = {0.0, 0.0};
+        WS_T(2);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            bar_named(1, 256);                           // stage rows free
+            double* st = sStage + (size_t)ar * SM::LDS_ + 2 * ac;
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+                if (n < ntw)
+                    *reinterpret_cast<double2*>(st + (ng + 8 * n) * 8) = make_double2(c[mt][n][0], c[mt][n][1]);
+            bar_named(1, 256);
+#pragma unroll
+            for (int s8 = 0; s8 < 8; ++s8) {
+                const int u = mt * 8 + s8;
+                const int uid = sUnit[u];
+                if (uid >= 0) {
+                    const double* row_s = sStage + (size_t)s8 * SM::LDS_;
+                    const int64_t row = sOut[u];
+                    const double W = sW[u];
+                    const double g0 = row_s[pk4[0]], g1 = row_s[pk4[1]], g2 = row_s[pk4[2]], g3 = row_s[pk4[3]];
+#ifdef MMA_DIAG_NOSTORE
+                    if (a.out_gamma && g0 == 1.2345e-300) {
+#else
+                    if (a.out_gamma) {
+#endif
+#if GW_NSTORE > 0
+                        // The warp's 4 matrix rows of this unit are 1 KB of contiguous output: staged in a warp-private
+                        // buffer and sent with one bulk store (cp.async.bulk), which the copy engine drains while the warp
+                        // goes on - plain stores stall the mma warps whenever the store path backs up (HBM write bursts of
+                        // 128 KB per tile), measured as ~9k cycles of epilogue per tile.
+                        double* rb = sRowBuf + (size_t)(ng * GW_NSTORE + n_out % GW_NSTORE) * 128;
+                        if (n_out >= GW_NSTORE) {                // the slot's previous segment has been read out
+                            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(GW_NSTORE - 1) : "memory");
+                            __syncwarp();
+                        }
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(smem_addr(rb + lane * 4)), "d"(g0), "d"(g1) : "memory");
+                        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(smem_addr(rb + lane * 4 + 2)), "d"(g2), "d"(g3) : "memory");
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        __syncwarp();
+                        if (lane == 0) {
+                            double* dst = a.out_gamma + (size_t)row * CAV_RR + ng * 128;
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 1024;"
+                                         :: "l"(dst), "r"(smem_addr(rb)) : "memory");
+                            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        }
+                        ++n_out;
+#else
+                        double* dst = a.out_gamma + (size_t)row * CAV_RR + oj * CAV_RW + ok4;
+                        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(dst), "d"(g0), "d"(g1), "d"(g2), "d"(g3) : "memory");
+#endif
+                    }
+                    if (a.partials) {
+                        tg[s8 & 1][0] = fma(W, g0, tg[s8 & 1][0]); tg[s8 & 1][1] = fma(W, g1, tg[s8 & 1][1]);
+                        tg[s8 & 1][2] = fma(W, g2, tg[s8 & 1][2]); tg[s8 & 1][3] = fma(W, g3, tg[s8 & 1][3]);
+                    }
+                    if (tid < CAV_RW) {
+                        const double dl = row_s[pd];
+                        if (a.out_delta) a.out_delta[(size_t)row * CAV_RW + tid] = dl;
+                        tdl[s8 & 1] = fma(W, dl, tdl[s8 & 1]);
+                    }
+                    if (tid == 32) {
+                        if (a.out_pv) a.out_pv[row] = sPv[u];
+                        tpv[s8 & 1] = fma(W, sPv[u], tpv[s8 & 1]);
+                    }
+                }
+            }
+        }
+        if (a.partials) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) my_tg[q] += tg[0][q] + tg[1][q];
+            if (tid < CAV_RW) sTot[1 + tid] += tdl[0] + tdl[1];
+            if (tid == 32) sTot[0] += tpv[0] + tpv[1];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sBar[GW_NBUF + bslot]);      // the tile's last buffer, and with it the tile slot, go back
+        WS_T(3);
+        if (++bslot == GW_NBUF) { bslot = 0; ++buse; }
+    }
+#if GW_NSTORE > 0
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // shared memory stays put until the last segment is out
+#endif
+    WS_TFLUSH(8, tid == 0);
+    if (a.partials) {     // this CTA's partial row (every launch owns its own block of rows and overwrites it)
+        double* Pr = a.partials + (size_t)blockIdx.x * CAV_NOUT;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) Pr[33 + oj * CAV_RW + ok4 + q] = my_tg[q];
+        if (tid < CAV_RW) Pr[1 + tid] = sTot[1 + tid];
+        if (tid == 32) Pr[0] = sTot[0];
+    }
+}
+
 // totals[e] = sum_rows partials[row][e]; one CTA per entry: threads stride the rows, a fixed butterfly per warp, the eight
 // warp sums added in warp order (bitwise reproducible for a given grid).  (A warp per entry left 33 warps on the whole GPU
 // for the PV + delta request, each waiting on ~300 strided loads: 43 us for 2.5 MB.)
