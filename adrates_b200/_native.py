@@ -38,6 +38,7 @@ _SIGS = {
     "cav_curve_set_tables": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int]),
     "cav_curve_rebuild_dev": (C.c_int, [_P, _P]),
     "cav_df_ad": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_int64, _P]),
+    "cav_xccy_curve_scan": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_double, _P, C.c_int, C.c_int, _P, _P, _P]),
     "cav_portfolio_upload": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int64, C.c_int, _P,
                                        C.c_int64, _P, _P, _P, _P]),
     "cav_portfolio_set_tiles": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, C.c_int64, _P, _P, _P, _P, _P, C.c_int, _P, _P,
@@ -192,6 +193,24 @@ class Context:
         out = np.empty_like(tt)
         self._ck(self._dll.cav_df_ad(self._h, _ptr(x), _ptr(d), x.shape[0], _ptr(tt), tt.shape[0], _ptr(out)))
         return out
+
+    def xccy_curve_scan(self, pt_time, pt_swap, pt_flags, pt_sens, pt_base, pt_df_ois, pt_pv_dom, spot_fx: float, spreads, order: int = 1):
+        """XccyCurve bootstrap on the device for one or more spread sets: (dfs [S, n], jac [S, n, nb] | None, hess [S, n, nb, nb] | None)."""
+        tt, ss, bb, oo, pp = _f64(pt_time), _f64(pt_sens), _f64(pt_base), _f64(pt_df_ois), _f64(pt_pv_dom)
+        sw = np.ascontiguousarray(pt_swap, dtype=np.int32)
+        fl = np.ascontiguousarray(pt_flags, dtype=np.int32)
+        sp = np.atleast_2d(_f64(spreads))
+        n, (S, nb) = tt.shape[0], sp.shape
+        for arr in (ss, bb, oo, pp, sw, fl):
+            if arr.shape[0] != n:
+                raise LibError("xccy_curve_scan: per-point arrays differ in length")
+        df = np.empty((S, n))
+        jac = np.empty((S, n, nb)) if order >= 1 else None
+        hess = np.empty((S, n, nb, nb)) if order >= 2 else None
+        self._ck(self._dll.cav_xccy_curve_scan(self._h, n, nb, _ptr(tt), _ptr(sw), _ptr(fl), _ptr(ss), _ptr(bb), _ptr(oo), _ptr(pp),
+                                               float(spot_fx), _ptr(sp), S, int(order), _ptr(df),
+                                               _ptr(jac) if jac is not None else None, _ptr(hess) if hess is not None else None))
+        return df, jac, hess
 
     def curve_df(self, interp_method: int, node_time, node_df, t):
         """DiscountCurve.df / Interpolator._uinterpolate on the path-A nodes."""

@@ -341,7 +341,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->sq_node); dev_free(ctx, &ctx->sq_w); dev_free(ctx, &ctx->sq_term); dev_free(ctx, &ctx->sc_dfq);
     dev_free(ctx, &ctx->cf_x); dev_free(ctx, &ctx->cf_d); dev_free(ctx, &ctx->cf_t); dev_free(ctx, &ctx->cf_amt);
     dev_free(ctx, &ctx->cf_pv); dev_free(ctx, &ctx->cf_off);
-    dev_free(ctx, &ctx->tile_arena); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag);
+    dev_free(ctx, &ctx->tile_arena); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag); dev_free(ctx, &ctx->xc_arena);
     dev_free(ctx, &ctx->Qmat);
     dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
@@ -704,6 +704,61 @@ int cav_cashflow_pv_dev(cav_ctx* ctx, int interp_method, const double* node_time
 }
 
 // ---------------------------------------------------------------------------- portfolio
+int cav_xccy_curve_scan(cav_ctx* ctx, int n_points, int n_spreads, const double* pt_time, const int32_t* pt_swap,
+                        const int32_t* pt_flags, const double* pt_spread_sens, const double* pt_base, const double* pt_df_ois,
+                        const double* pt_pv_dom, double spot_fx, const double* spreads, int n_scen, int order,
+                        double* df_out, double* jac_out, double* hess_out) {
+    if (!ctx) return CAV_E_INVALID;
+    if (n_points < 0 || n_spreads < 1 || n_spreads > CAV_RW) return fail(ctx, CAV_E_INVALID, "cav_xccy_curve_scan: 1..32 pillar spreads");
+    if (n_scen < 1 || order < 0 || order > 2) return fail(ctx, CAV_E_INVALID, "cav_xccy_curve_scan: n_scen >= 1, order 0..2");
+    if (!pt_time || !pt_swap || !pt_flags || !pt_spread_sens || !pt_base || !pt_df_ois || !pt_pv_dom || !spreads || !df_out)
+        return fail(ctx, CAV_E_INVALID, "cav_xccy_curve_scan: null argument");
+    if ((order >= 1 && !jac_out) || (order >= 2 && !hess_out)) return fail(ctx, CAV_E_INVALID, "cav_xccy_curve_scan: missing output for the requested order");
+    if (n_points == 0) return CAV_OK;
+    for (int i = 0; i < n_points; ++i) {
+        if (pt_swap[i] < 0 || pt_swap[i] >= n_spreads) return fail(ctx, CAV_E_INVALID, "cav_xccy_curve_scan: swap index out of range");
+        if (i > 0 && pt_time[i] < pt_time[i - 1]) return fail(ctx, CAV_E_INVALID, "cav_xccy_curve_scan: payment points must be sorted by time");
+        if (!(pt_df_ois[i] > 0.0)) return fail(ctx, CAV_E_INVALID, "cav_xccy_curve_scan: foreign discount factors must be positive");
+    }
+    CK(cudaSetDevice(ctx->device));
+    const size_t np = (size_t)n_points, nb = (size_t)n_spreads, ns = (size_t)n_scen;
+    // one arena: doubles first (time, sens, base, dfois, pvdom, spreads | df, jac, hess), then the two int arrays
+    const size_t n_in = 5 * np + ns * nb;
+    const size_t n_out = ns * np + (order >= 1 ? ns * np * nb : 0) + (order >= 2 ? ns * np * nb * nb : 0);
+    CK(dev_alloc(ctx, &ctx->xc_arena, n_in + n_out + np + 2));
+    double* d = ctx->xc_arena;
+    double *d_time = d, *d_sens = d + np, *d_base = d + 2 * np, *d_o = d + 3 * np, *d_pv = d + 4 * np, *d_s = d + 5 * np;
+    double* d_df = d + n_in;
+    double* d_jac = order >= 1 ? d_df + ns * np : nullptr;
+    double* d_hess = order >= 2 ? d_jac + ns * np * nb : nullptr;
+    int* d_swap = reinterpret_cast<int*>(d + n_in + n_out);
+    int* d_flags = d_swap + np;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(d_time, pt_time, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_sens, pt_spread_sens, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_base, pt_base, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_o, pt_df_ois, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_pv, pt_pv_dom, sizeof(double) * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_s, spreads, sizeof(double) * ns * nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_swap, pt_swap, sizeof(int) * np, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_flags, pt_flags, sizeof(int) * np, cudaMemcpyHostToDevice, st));
+    const size_t smem = sizeof(double) * (32 + 2 * 32 * 32);
+    const dim3 grid(order >= 2 ? n_spreads : 1, n_scen);
+    if (order >= 2)
+        k_xccy_scan<2><<<grid, 32, smem, st>>>(n_points, n_spreads, d_time, d_swap, d_flags, d_sens, d_base, d_o, d_pv, spot_fx, d_s, d_df, d_jac, d_hess);
+    else if (order == 1)
+        k_xccy_scan<1><<<grid, 32, smem, st>>>(n_points, n_spreads, d_time, d_swap, d_flags, d_sens, d_base, d_o, d_pv, spot_fx, d_s, d_df, d_jac, nullptr);
+    else
+        k_xccy_scan<0><<<grid, 32, smem, st>>>(n_points, n_spreads, d_time, d_swap, d_flags, d_sens, d_base, d_o, d_pv, spot_fx, d_s, d_df, nullptr, nullptr);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(df_out, d_df, sizeof(double) * ns * np, cudaMemcpyDeviceToHost, st));
+    if (order >= 1) CK(cudaMemcpyAsync(jac_out, d_jac, sizeof(double) * ns * np * nb, cudaMemcpyDeviceToHost, st));
+    if (order >= 2) CK(cudaMemcpyAsync(hess_out, d_hess, sizeof(double) * ns * np * nb * nb, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return CAV_OK;
+}
+
 int cav_portfolio_upload(cav_ctx* ctx, int64_t n_units, int64_t n_terms, const int64_t* unit_offsets, int n_pairs,
                          const double* amt, const double* weight, const int32_t* node, int64_t n_trades, int n_comp,
                          const double* comp_weight, int64_t n_groups, const int64_t* group_offsets,

@@ -126,6 +126,7 @@ struct cav_ctx {
     int class_begin[CAV_N_CLASSES + 1] = {0};   // tiles are ordered by size class (compact columns / 32)
     unsigned *tile_mask = nullptr, *row_masks = nullptr;
     int* check_flag = nullptr;
+    double* xc_arena = nullptr;       // inputs and outputs of cav_xccy_curve_scan
     int *tile_units = nullptr, *tile_kstart = nullptr, *tile_kcount = nullptr, *tile_npos = nullptr, *pairs = nullptr;
     int2* k_pack = nullptr;
     char* tile_arena = nullptr;        // the tile plan's device arrays are slices of one arena: one host->device copy per plan

@@ -1211,6 +1211,91 @@ k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// XccyCurve bootstrap (cavour/trades/rates/xccy_curve.py:954-1206) with exact forward-mode tangents w.r.t. the pillar basis
+// spreads: values, d(DF)/d(spread) (the reference's _jac_basis, jacrev through the scan, xccy_curve.py:594) and
+// d2(DF)/d(spread)^2 (_hess_basis, xccy_curve.py:603-606), batched over shocked spread sets.
+// The scan is serial in the payment points (each depends on the previous XCCY node and, at a maturity, on the swap's earlier
+// cashflows), so the parallel axes are the derivative entries and the scenarios: one single-warp CTA per (Hessian row a,
+// scenario), lane b = column.  A warp carries everything its row needs - the values, the gradient entry of lane b and of
+// row a (a shuffle), the Hessian entry (a, b) - through the scan on its own: no barrier, the per-swap sums of known
+// cashflow PVs (value, gradient, Hessian row) live in shared memory.  ORDER 0 / 1 run one warp per scenario.
+//   d_int = DF_prev * grow,  grow = DF_ois(t)/DF_ois(t_prev) * exp(-s_k (t - t_prev))          (s_k: spread of the point's swap)
+//   d grow = -(dt) grow e_k,  d2 grow = dt^2 grow e_k e_k^T;  cash = base + s_k * sens,  pv = cash * d_int
+//   at a maturity DF = num / den, num = spot * known - pv_dom, den = -spot * cash:
+//   dDF = (dnum - DF dden)/den,  d2DF = (d2num - dDF (x) dden - dden (x) dDF)/den.
+// ------------------------------------------------------------------------------------------
+#define XC_EXCH 1
+#define XC_ATVAL 4
+#define XC_MAT 8
+
+template <int ORDER>
+__global__ void __launch_bounds__(32)
+k_xccy_scan(int n_pts, int nb, const double* __restrict__ pt_time, const int* __restrict__ pt_swap, const int* __restrict__ pt_flags,
+            const double* __restrict__ pt_sens, const double* __restrict__ pt_base, const double* __restrict__ pt_dfois,
+            const double* __restrict__ pt_pvdom, double spot, const double* __restrict__ spreads,
+            double* __restrict__ df_out, double* __restrict__ jac_out, double* __restrict__ hess_out)
+{
+    extern __shared__ double xs[];
+    double* kV = xs;                       // [nb]      known cashflow PVs per swap
+    double* kG = kV + 32;                  // [nb][32]  their gradients (lane b)
+    double* kH = kG + 32 * 32;             // [nb][32]  row a of their Hessians
+    const int a = blockIdx.x, sc = blockIdx.y, b = threadIdx.x;
+    const double* s = spreads + (size_t)sc * nb;
+    for (int k = 0; k < nb; ++k) { if (b == 0) kV[k] = 0.0; kG[k * 32 + b] = 0.0; if (ORDER > 1) kH[k * 32 + b] = 0.0; }
+    __syncwarp();
+    double dfp = 1.0, gp = 0.0, hp = 0.0, t_prev = 0.0, o_prev = 1.0;
+    bool have_prev = false;
+    for (int i = 0; i < n_pts; ++i) {
+        const int k = pt_swap[i], fl = pt_flags[i];
+        const double t = pt_time[i], sens = pt_sens[i], o = pt_dfois[i], sk = s[k];
+        const double cash = pt_base[i] + sk * sens;
+        const double eb = (b == k) ? 1.0 : 0.0, ea = (a == k) ? 1.0 : 0.0;
+        const double dcb = sens * eb, dca = sens * ea;
+        const double dt = have_prev ? t - t_prev : t;
+        const double grow = (have_prev ? o / o_prev : o) * exp(-sk * dt);
+        const double d_int = dfp * grow;                                   // dfp = 1 before the first node
+        const double gpa = ORDER > 1 ? __shfl_sync(0xffffffffu, gp, a) : 0.0;
+        const double g_int = gp * grow - dt * d_int * eb;
+        const double g_inta = gpa * grow - dt * d_int * ea;
+        double h_int = 0.0;
+        if (ORDER > 1) h_int = hp * grow - dt * grow * (gpa * eb + ea * gp) + dt * dt * d_int * ea * eb;
+        double pvV = 0.0, pvG = 0.0, pvH = 0.0;
+        if (fl & XC_ATVAL) { pvV = cash; pvG = dcb; }
+        else if (!(fl & XC_MAT)) {
+            pvV = cash * d_int;
+            pvG = dcb * d_int + cash * g_int;
+            if (ORDER > 1) pvH = dca * g_int + g_inta * dcb + cash * h_int;
+        }
+        double df = d_int, g = g_int, h = h_int;
+        if (fl & XC_MAT) {
+            const double known = kV[k] + pvV, knownG = kG[k * 32 + b] + pvG;
+            const double num = -(pt_pvdom[i] + spot * (-known)), den = spot * (-cash);
+            if (fabs(den) > 1e-12) {
+                const double dnum = spot * knownG, dden = -spot * dcb;
+                df = num / den;
+                g = (dnum - df * dden) / den;
+                if (ORDER > 1) {
+                    const double ga = __shfl_sync(0xffffffffu, g, a), ddena = -spot * dca;
+                    h = (spot * (kH[k * 32 + b] + pvH) - ga * dden - ddena * g) / den;
+                }
+            }
+        } else {
+            __syncwarp();
+            if (b == 0) kV[k] += pvV;
+            kG[k * 32 + b] += pvG;
+            if (ORDER > 1) kH[k * 32 + b] += pvH;
+            __syncwarp();
+        }
+        if (a == 0) {
+            if (b == 0) df_out[(size_t)sc * n_pts + i] = df;
+            if (ORDER > 0 && jac_out && b < nb) jac_out[((size_t)sc * n_pts + i) * nb + b] = g;
+        }
+        if (ORDER > 1 && hess_out && b < nb) hess_out[(((size_t)sc * n_pts + i) * nb + a) * nb + b] = h;
+        if (!(fl & XC_ATVAL)) { dfp = df; gp = g; hp = h; t_prev = t; o_prev = o; have_prev = true; }
+    }
+}
+
 // totals[e] = sum_rows partials[row][e]; one CTA per entry: threads stride the rows, a fixed butterfly per warp, the eight
 // warp sums added in warp order (bitwise reproducible for a given grid).  (A warp per entry left 33 warps on the whole GPU
 // for the PV + delta request, each waiting on ~300 strided loads: 43 us for 2.5 MB.)

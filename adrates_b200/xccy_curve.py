@@ -2,9 +2,10 @@
 
 Mirror of cavour/trades/rates/xccy_curve.py for the part the valuation path consumes:
 `_times`, `_dfs`, `swap_times`, `basis_spreads`, `_spot_fx`, `_interp_type`, `_dc_type`, `df()` and
-`_jac_basis` = d(xccy DFs)/d(pillar basis spreads) (xccy_curve.py:594).  The curve is an input
-producer (built once per curve on the host, like OISCurve path A); its tables are uploaded to the
-device with cav_curve_set_tables.
+`_jac_basis` = d(xccy DFs)/d(pillar basis spreads) (xccy_curve.py:594).  The payment-point plan is host
+work (dates, legs); the recursion itself with its first- and second-order tangents w.r.t. the pillar spreads also runs on
+the device, batched over shocked spread sets (`device_tables` -> cav_xccy_curve_scan / k_xccy_scan); the tables reach the
+valuation kernels through cav_curve_set_tables.
 
 Bootstrap (xccy_curve.py:707-935 plan, :954-1206 recursion), per foreign-leg payment point in
 (time, swap) order:
@@ -150,6 +151,53 @@ class XccyCurve(DiscountCurve):
             self._check_refits(1e-8)
 
     # ---------------------------------------------------------------------------------
+    def scan_plan(self):
+        """Per-point arrays of the bootstrap recursion for the device scan (cav_xccy_curve_scan): everything that does not
+        depend on the pillar spreads - times, swap index, flags (1 exchange | 4 on the valuation date | 8 maturity), spread
+        sensitivities, the cashflow at zero spread (forward rate from the foreign curve, xccy_curve.py:636-639), foreign DFs at
+        the payment dates and the domestic-leg PVs."""
+        pts = self._pts
+        fx, fd = np.asarray(self._foreign_curve._times, dtype=np.float64), np.asarray(self._foreign_curve._dfs, dtype=np.float64)
+        log_fd = np.log(fd)
+        n = len(pts)
+        base = np.zeros(n)
+        flags = np.zeros(n, dtype=np.int32)
+        for i, p in enumerate(pts):
+            if p["exch"]:
+                base[i] = p["notional"] if p["last"] else -p["notional"]
+            else:
+                df_s = np.exp(np.interp(p["t_start"], fx, log_fd))
+                df_e = np.exp(np.interp(p["t_end"], fx, log_fd))
+                fwd = (df_s / df_e - 1.0) / max(p["alpha"], 1e-10) if p["alpha"] > 1e-10 else 0.0
+                base[i] = fwd * p["alpha"] * p["notional"] + (p["notional"] if p["last"] else 0.0)
+            flags[i] = (1 if p["exch"] else 0) | (4 if p["at_val"] else 0) | (8 if p["is_mat"] else 0)
+        return dict(time=np.array([p["time"] for p in pts]), swap=np.array([p["swap"] for p in pts], dtype=np.int32), flags=flags,
+                    sens=np.array([p["spread_sens"] for p in pts]), base=base, df_ois=np.array([p["df_ois"] for p in pts]),
+                    pv_dom=np.array([p["pv_dom"] for p in pts]))
+
+    def device_tables(self, ctx=None, spreads=None, order: int = 2):
+        """The curve's node tables from the device bootstrap (k_xccy_scan): (dfs [S, nodes], jac_basis [S, nodes, nb] | None,
+        hess_basis [S, nodes, nb, nb] | None) for S spread sets (default: the curve's own spreads, S = 1), rows in the order of
+        `_times` (row 0 = the (0, 1.0) node).  Shocked basis curves re-bootstrap in one launch: spreads[S][nb]."""
+        from . import _native
+        own = ctx is None
+        if own:
+            ctx = _native.Context(0)
+        try:
+            sp = np.atleast_2d(np.asarray(self.basis_spreads if spreads is None else spreads, dtype=np.float64))
+            pl = self.scan_plan()
+            df, jac, hess = ctx.xccy_curve_scan(pl["time"], pl["swap"], pl["flags"], pl["sens"], pl["base"], pl["df_ois"], pl["pv_dom"],
+                                                self._spot_fx, sp, order=order)
+        finally:
+            if own:
+                ctx.close()
+        idx = np.asarray(self._node_idx, dtype=np.int64)
+        S, nb = sp.shape
+        dfs = np.concatenate([np.ones((S, 1)), df[:, idx]], axis=1)
+        jn = None if jac is None else np.concatenate([np.zeros((S, 1, nb)), jac[:, idx]], axis=1)
+        hn = None if hess is None else np.concatenate([np.zeros((S, 1, nb, nb)), hess[:, idx]], axis=1)
+        return dfs, jn, hn
+
     def _scan(self, basis, df_ois):
         """The bootstrap recursion of `_bootstrap` on generic numbers (floats or dual2.D2): basis[k] = spread of pillar k,
         df_ois[i] = foreign OIS discount factor at payment point i.  Returns the XCCY discount factor of every point."""

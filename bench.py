@@ -498,6 +498,33 @@ def main():
             barrier()
 
     if not args.no_extra and world == 1:
+        # XccyCurve bootstrap on the device: the GBP/USD basis curve with its first- and second-order spread tangents, and
+        # a batch of shocked basis curves re-bootstrapped in one launch (DFs only)
+        try:
+            from adrates_b200.market_data import readme_model as _rm
+            xc = _rm(with_basis=True).curves.GBP_USD_BASIS
+            ctxx = _native.Context(local)
+            nb_x = len(xc.basis_spreads)
+            t1 = time.perf_counter(); xc.device_tables(ctx=ctxx, order=2); xc.device_tables(ctx=ctxx, order=2)
+            t2 = time.perf_counter()
+            for _ in range(5):
+                xc.device_tables(ctx=ctxx, order=2)
+            ms2 = (time.perf_counter() - t2) / 5 * 1e3
+            S_x = 4096
+            shocks = np.array(xc.basis_spreads)[None, :] + np.random.Generator(np.random.PCG64(3)).normal(0, 5e-4, (S_x, nb_x))
+            xc.device_tables(ctx=ctxx, spreads=shocks, order=0)
+            t3 = time.perf_counter()
+            for _ in range(3):
+                xc.device_tables(ctx=ctxx, spreads=shocks, order=0)
+            ms0 = (time.perf_counter() - t3) / 3 * 1e3
+            extras["xccy_curve_device"] = {
+                "payment_points": len(xc._pts), "pillars": nb_x, "ms_values_jacobian_hessian": ms2,
+                "shocked_curves": S_x, "ms_shocked_curves_dfs": ms0, "curves_per_s": S_x / ms0 * 1e3,
+                "note": "cav_xccy_curve_scan (k_xccy_scan): wall time of the host-pointer call incl. plan arrays, copies and the "
+                        "read-back; parity: tests/test_gpu_xccy_curve_device.py"}
+            ctxx.close()
+        except Exception as ex:  # noqa: BLE001
+            extras["xccy_curve_device"] = {"error": repr(ex)}
         # ---- single-GPU side measurements (device-resident inputs) ----
         M_PD = _native.REQ_VALUE | _native.REQ_DELTA
         ms = timed(lambda: ctx.portfolio_value(M_PD, pv.data_ptr(), dl.data_ptr(), None, agg.data_ptr()))

@@ -116,6 +116,20 @@ int cav_curve_set_tables(cav_ctx* ctx, const double* dfs, const double* jac, con
 int cav_df_ad(cav_ctx* ctx, const double* node_time, const double* node_df, int n_nodes,
               const double* t, int64_t n, double* out);
 
+/* ---- XccyCurve bootstrap on the device: replaces XccyCurve._build_curve_ad and the jacrev / hessian through it
+ * (cavour/trades/rates/xccy_curve.py:954-1206 recursion, :594 _jac_basis, :603-606 _hess_basis).
+ * The payment points of the calibration swaps' foreign legs come from the host plan (xccy_curve.py:707-935), sorted by
+ * (time, swap): pt_swap = pillar index, pt_flags = 1 notional exchange | 4 paid on the valuation date | 8 maturity of its
+ * swap, pt_spread_sens = accrual x notional (0 for exchanges), pt_base = the cashflow at zero spread, pt_df_ois = foreign
+ * OIS discount factor at the payment date, pt_pv_dom = PV of the swap's domestic leg (read at maturity points).
+ * spreads[n_scen][n_spreads] are the pillar basis spreads of n_scen curves (base + shocked).  Outputs (host):
+ * df_out[n_scen][n_points]; order >= 1: jac_out[n_scen][n_points][n_spreads] = d DF / d spread; order 2:
+ * hess_out[n_scen][n_points][n_spreads][n_spreads].  n_spreads <= 32. */
+int cav_xccy_curve_scan(cav_ctx* ctx, int n_points, int n_spreads, const double* pt_time, const int32_t* pt_swap,
+                        const int32_t* pt_flags, const double* pt_spread_sens, const double* pt_base, const double* pt_df_ois,
+                        const double* pt_pv_dom, double spot_fx, const double* spreads, int n_scen, int order,
+                        double* df_out, double* jac_out, double* hess_out);
+
 /* ---- portfolio: the flattened cashflow schedule ------------------------------------
  * Replaces the per-trade host prep of Engine._fixed_leg_analytics / _float_leg_analytics
  * (engine.py:2519-2539, 2858-2897).  A *unit* is a set of terms
