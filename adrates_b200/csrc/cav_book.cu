@@ -59,6 +59,9 @@ struct BookScratch {
     int32_t *cls_spread = nullptr, *cnt3 = nullptr, *has3 = nullptr, *uid3 = nullptr, *ng = nullptr, *gstart = nullptr;
     int32_t* unit_cnt = nullptr;
     int2* sched3 = nullptr;                  // (dates before the duplicate filter - 1, dropped head dates) per (part, class)
+    int32_t* date_tab = nullptr;             // [n_sched * S][BK_TAB] raw schedule dates (k_bk_sched_table)
+    int4* date_hdr = nullptr;                // [n_sched * S] (cnt or -1, dup, err, 0)
+    double2* term_rec = nullptr;             // [3 S][BK_TAB_TERMS] (time, amount) of the terms the count pass walked
     // tile plan
     unsigned* support = nullptr;             // [G] pillar-support masks of the curve nodes
     uint64_t* tab_key = nullptr;
@@ -91,7 +94,7 @@ void cav_book_free(cav_ctx* ctx) {
     { char* p = (char*)b->scan_sums; dev_free(ctx, &p); b->scan_sums = nullptr; }
     dev_free(ctx, &b->flag); dev_free(ctx, &b->cls); dev_free(ctx, &b->cls_start); dev_free(ctx, &b->cls_key);
     dev_free(ctx, &b->cls_spread); dev_free(ctx, &b->cnt3); dev_free(ctx, &b->has3); dev_free(ctx, &b->uid3); dev_free(ctx, &b->ng);
-    dev_free(ctx, &b->gstart); dev_free(ctx, &b->unit_cnt); dev_free(ctx, &b->sched3); dev_free(ctx, &b->support); dev_free(ctx, &b->tab_key);
+    dev_free(ctx, &b->gstart); dev_free(ctx, &b->unit_cnt); dev_free(ctx, &b->sched3); dev_free(ctx, &b->date_tab); dev_free(ctx, &b->date_hdr); dev_free(ctx, &b->term_rec); dev_free(ctx, &b->support); dev_free(ctx, &b->tab_key);
     dev_free(ctx, &b->tab_leader); dev_free(ctx, &b->unit_slot); dev_free(ctx, &b->is_leader); dev_free(ctx, &b->lead_rank);
     dev_free(ctx, &b->unit_gid); dev_free(ctx, &b->unit_mask); dev_free(ctx, &b->grp_cnt); dev_free(ctx, &b->grp_start);
     dev_free(ctx, &b->kcount); dev_free(ctx, &b->kstart); dev_free(ctx, &b->gtiles); dev_free(ctx, &b->tstart);
@@ -329,9 +332,14 @@ __global__ void __launch_bounds__(256) k_bk_spread_flags(int64_t n, const uint32
 // ------------------------------------------------------------------------------------------------------------------
 // classes
 // ------------------------------------------------------------------------------------------------------------------
+#define BK_TAB_TERMS 64
 struct CountSink {
     int c[3];
-    __device__ __forceinline__ void term(int part, double, double) { c[part]++; }
+    double2* rec;      // optional: the first BK_TAB (time, amount) pairs of the walked part, for the parallel fill (k_bk_terms_plan)
+    __device__ __forceinline__ void term(int part, double t, double a) {
+        if (rec && c[part] < BK_TAB_TERMS) rec[c[part]] = make_double2(t, a);
+        c[part]++;
+    }
 };
 
 struct FillSink {
@@ -358,11 +366,72 @@ __device__ __forceinline__ void class_dates(uint64_t key, int64_t& eff, int64_t&
     term = eff + (int64_t)(key & (((uint64_t)1 << BK_KEY_SPAN_BITS) - 1));
 }
 
+// Date tables.  The walkers below run one thread per (class, part) and are serial in the schedule; what made them slow was
+// recomputing every date (month arithmetic, business-day roll) each time a walker asks for it - three to six times per
+// period over the count and the fill pass, 0.40 ms per 1M trades for 25k threads.  Every raw date is a pure function of its
+// position (sched_raw_date), so the dates are computed once, a thread per (schedule, position), into a table the walkers
+// read; the duplicate / monotonicity pass of make_sched becomes a neighbour comparison.  A CTA owns four schedules of up to
+// BK_TAB dates; longer schedules (hdr.x = -1) keep the serial path.  Schedule 0 = fixed leg, 1 = floating leg (shared when
+// both legs have the same frequency).
+#define BK_TAB 64
+__global__ void __launch_bounds__(256) k_bk_sched_table(Conv cv, int64_t S, int n_sched, const uint64_t* __restrict__ cls_key,
+                                                        int32_t* tab, int4* hdr) {
+    __shared__ int s_cnt[4], s_err[4], s_dup[4];
+    __shared__ int64_t s_date[4][BK_TAB];
+    const int q = threadIdx.x >> 6, pos = threadIdx.x & 63;
+    const int64_t pair = (int64_t)blockIdx.x * 4 + q;
+    const bool live = pair < S * n_sched;
+    const int which = live ? (int)(pair / S) : 0;
+    const int64_t c = live ? pair - (int64_t)which * S : 0;
+    int64_t eff = 0, term = 1;
+    if (live) class_dates(cls_key[c], eff, term);
+    Sched sc = sched_from(eff, term, which == 0 ? cv.fixed_step : cv.float_step, cv.cal, cv.bd, cv.dg, cv.eom, 0, 0);
+    if (pos == 0) {
+        sched_header(sc, BK_MAX_DATES);
+        s_cnt[q] = sc.cnt; s_err[q] = sc.err; s_dup[q] = 0;
+    }
+    __syncthreads();
+    sc.cnt = s_cnt[q];
+    const bool fits = live && s_err[q] == 0 && sc.cnt < BK_TAB;
+    int64_t d = 0;
+    if (fits && pos <= sc.cnt) { d = sched_raw_date(sc, pos); s_date[q][pos] = d; }
+    __syncthreads();
+    if (fits && pos >= 1 && pos <= sc.cnt) {
+        const int64_t prev = s_date[q][pos - 1];
+        if (d < prev) atomicOr(&s_err[q], E_NOT_MONOTONIC);
+        if (d == prev) atomicAdd(&s_dup[q], 1);
+    }
+    __syncthreads();
+    if (!live) return;
+    if (fits && pos <= sc.cnt) tab[pair * BK_TAB + pos] = (int32_t)d;
+    if (pos == 0) hdr[pair] = make_int4(fits ? sc.cnt : -1, s_dup[q], s_err[q], 0);
+}
+
+// a (class, part)'s schedule from the date table, or rebuilt serially where the table does not hold it
+__device__ __forceinline__ Sched class_sched(const Conv& cv, int64_t S, int n_sched, int64_t c, int part, int64_t eff, int64_t term,
+                                             const int32_t* __restrict__ tab, const int4* __restrict__ hdr) {
+    const int which = (part == 0 || n_sched == 1) ? 0 : 1;
+    const int step = part == 0 ? cv.fixed_step : cv.float_step;
+    if (hdr) {
+        const int64_t pair = (int64_t)which * S + c;
+        const int4 h = hdr[pair];
+        if (h.x >= 0 || h.z != 0) {
+            Sched sc = sched_from(eff, term, step, cv.cal, cv.bd, cv.dg, cv.eom, h.x < 0 ? 0 : h.x, h.y);
+            sc.err = h.z;
+            if (h.x >= 0) sc.tab = tab + pair * BK_TAB;
+            return sc;
+        }
+    }
+    return make_sched(eff, term, step, cv.cal, cv.bd, cv.dg, cv.eom, BK_MAX_DATES);
+}
+
 // one thread per (class, part): part 0 walks the fixed-leg schedule, parts 1 and 2 the floating-leg schedule.  The schedule
 // shape (dates before the duplicate filter, dropped head dates) is verified here and stored for the fill pass.
 __global__ void __launch_bounds__(128) k_bk_class_count(Conv cv, int64_t S, const uint64_t* __restrict__ cls_key,
                                                         const int64_t* __restrict__ cls_start, const int32_t* __restrict__ cls_spread,
-                                                        int32_t* cnt3, int32_t* has3, int32_t* ng, int2* sched3, BookStats* st) {
+                                                        int32_t* cnt3, int32_t* has3, int32_t* ng, int2* sched3, BookStats* st,
+                                                        int n_sched, const int32_t* __restrict__ tab, const int4* __restrict__ hdr,
+                                                        double2* term_rec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * S) return;
     const int part = (int)(i / S);
@@ -372,11 +441,12 @@ __global__ void __launch_bounds__(128) k_bk_class_count(Conv cv, int64_t S, cons
     if (part < 2 || (cls_spread && cls_spread[c] != 0)) {
         int64_t eff, term;
         class_dates(cls_key[c], eff, term);
-        const Sched sc = make_sched(eff, term, part == 0 ? cv.fixed_step : cv.float_step, cv.cal, cv.bd, cv.dg, cv.eom, BK_MAX_DATES);
+        const Sched sc = class_sched(cv, S, n_sched, c, part, eff, term, tab, hdr);
         err = sc.err;
         shape = make_int2(sc.cnt, sc.dup);
         CountSink sink;
         sink.c[0] = sink.c[1] = sink.c[2] = 0;
+        sink.rec = term_rec ? term_rec + i * BK_TAB_TERMS : nullptr;
         if (!err) err |= part == 0 ? walk_annuity(cv, sc, sink) : (part == 1 ? walk_float(cv, sc, sink) : walk_spread(cv, sc, sink));
         n = sink.c[part];
     }
@@ -398,15 +468,22 @@ __global__ void __launch_bounds__(256) k_bk_unit_counts(int64_t S3, const int32_
 __global__ void __launch_bounds__(128) k_bk_class_fill(Conv cv, int64_t S, const uint64_t* __restrict__ cls_key,
                                                        const int32_t* __restrict__ has3, const int32_t* __restrict__ uid3,
                                                        const int2* __restrict__ sched3, const int64_t* __restrict__ unit_offsets,
-                                                       const double* __restrict__ x, int G, int lzr, double* amt, double* weight, int* node) {
+                                                       const double* __restrict__ x, int G, int lzr, double* amt, double* weight, int* node,
+                                                       int n_sched, const int32_t* __restrict__ tab, const int4* __restrict__ hdr,
+                                                       const int32_t* __restrict__ cnt3, int skip_recorded) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * S || !has3[i]) return;
+    if (skip_recorded && cnt3[i] <= BK_TAB_TERMS) return;      // its terms were recorded by the count pass: k_bk_terms_plan fills them
     const int part = (int)(i / S);
     const int64_t c = i - (int64_t)part * S;
     int64_t eff, term;
     class_dates(cls_key[c], eff, term);
     const int2 shape = sched3[i];
-    const Sched sc = sched_from(eff, term, part == 0 ? cv.fixed_step : cv.float_step, cv.cal, cv.bd, cv.dg, cv.eom, shape.x, shape.y);
+    Sched sc = sched_from(eff, term, part == 0 ? cv.fixed_step : cv.float_step, cv.cal, cv.bd, cv.dg, cv.eom, shape.x, shape.y);
+    {
+        const int64_t pair = (int64_t)((part == 0 || n_sched == 1) ? 0 : 1) * S + c;
+        if (hdr && hdr[pair].x >= 0) sc.tab = tab + pair * BK_TAB;
+    }
     FillSink sink;
     sink.x = x; sink.G = G; sink.lzr = lzr != 0; sink.amt = amt; sink.weight = weight; sink.node = node;
     sink.n[0] = sink.n[1] = sink.n[2] = 0;
@@ -414,6 +491,32 @@ __global__ void __launch_bounds__(128) k_bk_class_fill(Conv cv, int64_t S, const
     if (part == 0) walk_annuity(cv, sc, sink);
     else if (part == 1) walk_float(cv, sc, sink);
     else walk_spread(cv, sc, sink);
+}
+
+// Parallel fill: the count pass has recorded (time, amount) of every term of a (class, part) with at most BK_TAB_TERMS terms;
+// here a thread per recorded term plans its bracket (three binary searches and the weight arithmetic of plan_query, the
+// expensive part of the serial fill walk) and writes the flat arrays.
+__global__ void __launch_bounds__(256) k_bk_terms_plan(int64_t S3, const int32_t* __restrict__ cnt3, const int32_t* __restrict__ has3,
+                                                       const int32_t* __restrict__ uid3, const int64_t* __restrict__ unit_offsets,
+                                                       const double2* __restrict__ term_rec, const double* __restrict__ x, int G, int lzr,
+                                                       double* amt, double* weight, int* node) {
+    extern __shared__ double sx[];
+    for (int k = threadIdx.x; k < G; k += 256) sx[k] = x[k];
+    __syncthreads();
+    const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const int64_t i = e / BK_TAB_TERMS;
+    const int k = (int)(e - i * BK_TAB_TERMS);
+    if (i >= S3 || !has3[i]) return;
+    const int n = cnt3[i];
+    if (n > BK_TAB_TERMS || k >= n) return;
+    const double2 ta = term_rec[e];
+    int na, nb;
+    double wa, wb;
+    plan_query(ta.x, sx, G, lzr != 0, na, nb, wa, wb);
+    const int64_t o = unit_offsets[uid3[i]] + k;
+    amt[o] = ta.y;
+    weight[2 * o] = wa; weight[2 * o + 1] = wb;
+    node[2 * o] = na; node[2 * o + 1] = nb;
 }
 
 __global__ void __launch_bounds__(128) k_bk_groups_fill(int64_t S, int K, int64_t n_trades, int64_t n_groups,
@@ -944,8 +1047,19 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
         ctx->launches++;
     }
     CK(dev_alloc(ctx, &bk->sched3, (size_t)3 * S));
+    const int n_sched = cv.fixed_step == cv.float_step ? 1 : 2;
+    static const bool use_tab = [] { const char* e = std::getenv("CAV_BOOK_DATE_TABLE"); return e ? std::atoi(e) != 0 : true; }();
+    if (use_tab) {
+        CK(dev_alloc(ctx, &bk->date_tab, (size_t)S * n_sched * BK_TAB));
+        CK(dev_alloc(ctx, &bk->date_hdr, (size_t)S * n_sched));
+        k_bk_sched_table<<<grid_for(S * n_sched * 64, 256), 256, 0, ctx->stream>>>(cv, S, n_sched, bk->cls_key, bk->date_tab, bk->date_hdr);
+        ctx->launches++;
+    }
+    if (use_tab) CK(dev_alloc(ctx, &bk->term_rec, (size_t)3 * S * BK_TAB_TERMS));
     k_bk_class_count<<<grid_for(3 * S, 128), 128, 0, ctx->stream>>>(cv, S, bk->cls_key, bk->cls_start, spread ? bk->cls_spread : nullptr,
-                                                                   bk->cnt3, bk->has3, bk->ng, bk->sched3, bk->d_stats);
+                                                                   bk->cnt3, bk->has3, bk->ng, bk->sched3, bk->d_stats,
+                                                                   n_sched, use_tab ? bk->date_tab : nullptr, use_tab ? bk->date_hdr : nullptr,
+                                                                   use_tab ? bk->term_rec : nullptr);
     ctx->launches++;
     CK(cudaGetLastError());
     BookStats* ds = bk->d_stats;
@@ -981,7 +1095,15 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     CK(dev_alloc(ctx, &ctx->unit_weight, (size_t)U));
     k_bk_class_fill<<<grid_for(3 * S, 128), 128, 0, ctx->stream>>>(cv, S, bk->cls_key, bk->has3, bk->uid3, bk->sched3, ctx->unit_offsets,
                                                                   ctx->node_time, G, ctx->interp == CAV_INTERP_LINEAR_ZERO_RATES,
-                                                                  ctx->amt, ctx->weight, ctx->node);
+                                                                  ctx->amt, ctx->weight, ctx->node,
+                                                                  n_sched, use_tab ? bk->date_tab : nullptr, use_tab ? bk->date_hdr : nullptr,
+                                                                  bk->cnt3, use_tab ? 1 : 0);
+    if (use_tab) {
+        k_bk_terms_plan<<<grid_for(3 * S * BK_TAB_TERMS, 256), 256, sizeof(double) * G, ctx->stream>>>(
+            3 * S, bk->cnt3, bk->has3, bk->uid3, ctx->unit_offsets, bk->term_rec, ctx->node_time, G,
+            ctx->interp == CAV_INTERP_LINEAR_ZERO_RATES, ctx->amt, ctx->weight, ctx->node);
+        ctx->launches++;
+    }
     k_bk_groups_fill<<<grid_for(S, 128), 128, 0, ctx->stream>>>(S, K, N, NG, bk->cls_start, bk->ng, bk->gstart, bk->has3, bk->uid3,
                                                                ctx->group_offsets, ctx->group_units);
     CK(cudaStreamWaitEvent(ctx->stream, bk->ev_inputs, 0));

@@ -178,10 +178,12 @@ struct Sched {
     int cnt;          // dates before the duplicate filter = cnt + 1
     int dup;          // head dates dropped by the duplicate filter
     int err;          // E_* bits
+    const int32_t* tab;   // optional: the cnt + 1 raw dates, precomputed (device flattener: k_bk_sched_table); null = recompute
     CAVB_HD int n_dates() const { return cnt + 1 - dup; }
 };
 
 CAVB_HD int64_t sched_raw_date(const Sched& s, int pos) {     // position before the duplicate filter
+    if (s.tab) return (int64_t)s.tab[pos];
     int64_t dt;
     if (s.dg == DG_BACKWARD) {
         const int k = s.cnt - pos;
@@ -202,15 +204,15 @@ CAVB_HD int64_t sched_date(const Sched& s, int pos) { return sched_raw_date(s, p
 CAVB_HD Sched sched_from(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int cnt, int dup) {
     Sched s;
     s.eff = eff; s.term = term; s.step = step; s.cal = cal; s.bd = bd; s.dg = dg; s.eom = eom;
-    s.cnt = cnt; s.dup = dup; s.err = 0;
+    s.cnt = cnt; s.dup = dup; s.err = 0; s.tab = nullptr;
     return s;
 }
 
-CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int max_dates) {
-    Sched s;
-    s.eff = eff; s.term = term; s.step = step; s.cal = cal; s.bd = bd; s.dg = dg; s.eom = eom;
-    s.cnt = 0; s.dup = 0; s.err = 0;
-    if (eff >= term) { s.err = E_EFF_GE_TERM; return s; }
+// number of dates before the duplicate filter (cnt + 1) of a schedule; sets s.cnt or s.err
+CAVB_HD void sched_header(Sched& s, int max_dates) {
+    const int64_t eff = s.eff, term = s.term;
+    const int step = s.step, dg = s.dg, eom = s.eom;
+    if (eff >= term) { s.err = E_EFF_GE_TERM; return; }
     int de, me, dt, mt;
     int64_t ye, yt;
     ymd(eff, de, me, ye);
@@ -225,8 +227,16 @@ CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, int cal, int bd, i
         const int64_t same_month = add_months(eff, (int64_t)step * q, false);
         cnt += (r == 0) && (same_month < term);
     }
-    if (cnt + 1 > max_dates) { s.err = E_TOO_MANY_DATES; return s; }
+    if (cnt + 1 > max_dates) { s.err = E_TOO_MANY_DATES; return; }
     s.cnt = cnt;
+}
+
+CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int max_dates) {
+    Sched s;
+    s.eff = eff; s.term = term; s.step = step; s.cal = cal; s.bd = bd; s.dg = dg; s.eom = eom;
+    s.cnt = 0; s.dup = 0; s.err = 0; s.tab = nullptr;
+    sched_header(s, max_dates);
+    if (s.err) return s;
     int64_t prev = sched_raw_date(s, 0);
     for (int pos = 1; pos <= s.cnt; ++pos) {
         const int64_t cur = sched_raw_date(s, pos);

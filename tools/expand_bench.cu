@@ -355,6 +355,45 @@ __global__ void __launch_bounds__(256) k_q(const double* __restrict__ units, con
     }
 }
 
+// ---- K: compact unit rows.  The units stage leaves every unit's gamma as the packed triangle of its active pillars (CW doubles
+// instead of 1024), written right before the expansion, so the whole set (~2 x G x CW x 8 bytes) is L2-resident when the
+// expansion gathers it; rows are stored with an evict_first policy.  MODE 0: plain loads / stores   1: evict_first stores
+template <int MODE, int CW>
+__global__ void __launch_bounds__(256) k_cprod(double* cunits) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    cunits[i] = 1e-3 * (double)(i & 1023);
+}
+template <int MODE, int CW>
+__global__ void __launch_bounds__(256) k_k(const double* __restrict__ cunits, const double* __restrict__ w,
+                                           const long long* __restrict__ rows, int gsz, double* out) {
+    __shared__ double sw[256][2];
+    __shared__ long long sr[256];
+    int g = blockIdx.x, tid = threadIdx.x;
+    long long t0 = (long long)g * gsz;
+    if (tid < gsz) { sw[tid][0] = w[(t0 + tid) * 2]; sw[tid][1] = w[(t0 + tid) * 2 + 1]; sr[tid] = rows[t0 + tid]; }
+    unsigned long long pol = 0;
+    if (MODE == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    // symmetric gather: entry (j, k) of the 32x32 matrix from packed position of (max, min) folded into the CW-wide row
+    const int j = tid >> 3, k0 = (tid & 7) * 4;
+    const double* U0 = cunits + (size_t)(2 * g) * CW;
+    const double* U1 = U0 + CW;
+    double u0[4], u1[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int k = k0 + q, hi = j > k ? j : k, lo = j > k ? k : j;
+        const int pidx = (hi * (hi + 1) / 2 + lo) % CW;
+        u0[q] = U0[pidx]; u1[q] = U1[pidx];
+    }
+    __syncthreads();
+    for (int i = 0; i < gsz; ++i) {
+        double a = sw[i][0], b = sw[i][1];
+        double* dst = out + (size_t)sr[i] * RR + tid * 4;
+        const double x0 = a * u0[0] + b * u1[0], x1 = a * u0[1] + b * u1[1], x2 = a * u0[2] + b * u1[2], x3 = a * u0[3] + b * u1[3];
+        if (MODE == 1) asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1,%2,%3,%4}, %5;" :: "l"(dst), "d"(x0), "d"(x1), "d"(x2), "d"(x3), "l"(pol) : "memory");
+        else asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(dst), "d"(x0), "d"(x1), "d"(x2), "d"(x3) : "memory");
+    }
+}
+
 int main() {
     const long long N = 1000000; const int gsz = 64; const int G = (int)(N / gsz);
     double *units, *w, *out; long long* rows;
@@ -406,6 +445,25 @@ int main() {
     run("G no loads, FMA", [&] { k_g<1><<<G, 256>>>(units, w, rows, gsz, out); });
     run("G DRAM units, no FMA", [&] { k_g<2><<<G, 256>>>(units, w, rows, gsz, out); });
     run("G L2 units+FMA+evict hints", [&] { k_g<3><<<G, 256>>>(units, w, rows, gsz, out); });
+    {   // compact unit rows (CW doubles per unit) written right before the expansion: producer untimed, expansion timed
+        auto runk = [&](const char* name, auto prod, auto cons) {
+            for (int order = 0; order < 2; ++order) {
+                cudaMemcpy(rows, order ? rnd.data() : seq.data(), sizeof(long long) * N, cudaMemcpyHostToDevice);
+                float best = 1e9;
+                for (int rep = 0; rep < 4; ++rep) {
+                    prod();
+                    cudaEventRecord(e0); cons(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+                    float ms; cudaEventElapsedTime(&ms, e0, e1); if (rep) best = std::min(best, ms);
+                }
+                printf("%-28s rows=%s  %.3f ms  %.0f GB/s (%s)\n", name, order ? "random" : "seq   ", best,
+                       N * RR * 8.0 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+            }
+        };
+        runk("K compact 160 plain", [&] { k_cprod<0, 160><<<2 * G * 160 / 256, 256>>>(units); }, [&] { k_k<0, 160><<<G, 256>>>(units, w, rows, gsz, out); });
+        runk("K compact 160 evict_first", [&] { k_cprod<0, 160><<<2 * G * 160 / 256, 256>>>(units); }, [&] { k_k<1, 160><<<G, 256>>>(units, w, rows, gsz, out); });
+        runk("K compact 256 evict_first", [&] { k_cprod<0, 256><<<2 * G * 256 / 256, 256>>>(units); }, [&] { k_k<1, 256><<<G, 256>>>(units, w, rows, gsz, out); });
+        runk("K compact 528 evict_first", [&] { k_cprod<0, 528><<<2 * G * 528 / 256, 256>>>(units); }, [&] { k_k<1, 528><<<G, 256>>>(units, w, rows, gsz, out); });
+    }
 
 
     cudaMemcpy(rows, rnd.data(), sizeof(long long) * N, cudaMemcpyHostToDevice);
