@@ -36,3 +36,14 @@ def test_warp_specialised_tile_kernel_matches_single_role_kernel_and_oracle():
     assert np.max(np.abs(agg_a[1:33] - agg_b[1:33])) <= 1e-12 * mass[1]
     assert np.max(np.abs(agg_a[33:] - agg_b[33:])) <= 1e-12 * mass[2]
     assert b["oracle_err"] < 1e-10
+
+
+def test_parity_suites_pass_with_the_warp_specialised_kernel_forced():
+    """Small and ragged books (padding units, single-tile classes, bonds, device-built plans) through k_units_mma_ws: the parity
+    suites that pin the tiled Greeks to the reference engine's goldens, re-run in a process where CAV_UNITS_WS=1."""
+    env = dict(os.environ, CAV_UNITS_WS="1")
+    cmd = [sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-p", "no:cacheprovider",
+           os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_bond_book.py"),
+           os.path.join(ROOT, "tests", "test_gpu_book_device.py")]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=560, cwd=ROOT)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-1000:]
