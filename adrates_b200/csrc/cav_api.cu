@@ -59,6 +59,12 @@ void launch_units(cav_ctx* ctx, const UnitsArgs& a, bool delta, bool gamma, int 
 template <int K>
 void launch_expand(cav_ctx* ctx, cudaStream_t st, double* pv, double* delta, double* gamma, int64_t g0, int64_t g1) {
     if (g1 <= g0) return;
+    if (gamma && ctx->expand_compact && !pv && !delta) {
+        k_expand_c<K><<<(unsigned)(g1 - g0), 256, 0, st>>>(ctx->group_offsets + g0, ctx->group_units + g0 * K, ctx->comp_weight,
+                                                         ctx->out_index, ctx->u_cgamma, ctx->u_cmask, ctx->pp, gamma);
+        ctx->launches++;
+        return;
+    }
     k_expand<K><<<(unsigned)(g1 - g0), 256, 0, st>>>(
         ctx->group_offsets + g0, ctx->group_units + g0 * K, ctx->comp_weight, ctx->out_index, ctx->u_pv, ctx->u_delta,
         ctx->u_gamma, pv, delta, gamma);
@@ -345,6 +351,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->Qmat);
     dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
+    dev_free(ctx, &ctx->u_cgamma); dev_free(ctx, &ctx->u_cmask);
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -1169,6 +1176,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
     a.n_units = ctx->n_units; a.unit_offsets = ctx->unit_offsets; a.amt = ctx->amt; a.weight = ctx->weight;
     a.node = ctx->node; a.L = ctx->L; a.g = ctx->g; a.Hf = ctx->Hf; a.Cf = ctx->Cf;
     a.partials = need_agg ? ctx->partials : nullptr;
+    ctx->expand_compact = false;
     if (ctx->direct) {
         a.unit_weight = nullptr; a.out_index = ctx->out_index;
         a.out_pv = pv; a.out_delta = delta; a.out_gamma = gamma;
@@ -1177,12 +1185,19 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         if (per_trade) {
             CK(dev_alloc(ctx, &ctx->u_pv, (size_t)ctx->n_units));
             if (delta) CK(dev_alloc(ctx, &ctx->u_delta, (size_t)ctx->n_units * CAV_RW));
-            if (gamma) CK(dev_alloc(ctx, &ctx->u_gamma, (size_t)ctx->n_units * CAV_RR));
+            // unit gammas of a tiled book stay compact (packed triangle over the tile's active pillars): the expansion then
+            // reads them from L2 instead of threading DRAM reads through its write stream (CAV_EXPAND_COMPACT=0: full rows)
+            const char* ce = std::getenv("CAV_EXPAND_COMPACT");
+            ctx->expand_compact = gamma && use_gemm && ctx->n_groups > 0 && !(ce && std::atoi(ce) == 0);
+            if (gamma && ctx->expand_compact) {
+                CK(dev_alloc(ctx, &ctx->u_cgamma, (size_t)ctx->n_units * GT_NPACK));
+                CK(dev_alloc(ctx, &ctx->u_cmask, (size_t)ctx->n_units));
+            } else if (gamma) CK(dev_alloc(ctx, &ctx->u_gamma, (size_t)ctx->n_units * CAV_RR));
         }
         a.unit_weight = ctx->unit_weight; a.out_index = nullptr;
         a.out_pv = per_trade ? ctx->u_pv : nullptr;
         a.out_delta = delta ? ctx->u_delta : nullptr;
-        a.out_gamma = gamma ? ctx->u_gamma : nullptr;
+        a.out_gamma = (gamma && !ctx->expand_compact) ? ctx->u_gamma : nullptr;
     }
     if (ctx->profile) CK(cudaEventRecord(ctx->evk[0], ctx->stream));
     if (use_gemm) {
@@ -1192,6 +1207,7 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         ga.unit_offsets = a.unit_offsets; ga.amt = a.amt; ga.weight = a.weight; ga.node = a.node; ga.L = a.L;
         ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
         ga.out_gamma = a.out_gamma; ga.partials = a.partials;
+        if (!ctx->direct && ctx->expand_compact && gamma) { ga.out_cgamma = ctx->u_cgamma; ga.out_cmask = ctx->u_cmask; }
         { int rc = launch_mma_classes(ctx, ga); if (rc) return rc; }
     } else if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
     else launch_units<6>(ctx, a, want_d, want_g, grid);

@@ -164,6 +164,9 @@ struct cav_ctx {
 
     // scratch
     double *u_pv = nullptr, *u_delta = nullptr, *u_gamma = nullptr;
+    double* u_cgamma = nullptr;          // compact unit gammas [n_units][528] (tile kernels -> k_expand_c)
+    unsigned* u_cmask = nullptr;         // [n_units] active-pillar mask of each compact row
+    bool expand_compact = false;         // this valuation's expansion reads the compact rows
     double* partials = nullptr;
     double* agg = nullptr;
 };

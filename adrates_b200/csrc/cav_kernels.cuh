@@ -456,6 +456,8 @@ struct SimtArgs {
     double* out_delta;
     double* out_gamma;
     double* partials;          // [CTAs of this launch][1057] totals per persistent CTA, or null
+    double* out_cgamma = nullptr;   // compact unit gammas [unit][GT_NPACK]: packed triangle over the tile's active pillars (k_expand_c)
+    unsigned* out_cmask = nullptr;  // [unit] the active-pillar mask its compact row is laid out by
 };
 
 #define GM_PC 32                 // term positions per chunk
@@ -676,6 +678,11 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                 const int64_t row = sOut[u];
                 const double W = sW[u];
                 const double g0 = row_s[pk4[0]], g1 = row_s[pk4[1]], g2 = row_s[pk4[2]], g3 = row_s[pk4[3]];
+                if (a.out_cgamma) {                       // compact unit row: the staged packed triangle as it is (coalesced)
+                    double* cdst = a.out_cgamma + (size_t)uid * GT_NPACK;
+                    for (int cc = tid; cc < nc; cc += 256) cdst[cc] = row_s[cc];
+                    if (tid == 0) a.out_cmask[uid] = mask;
+                }
 #ifdef MMA_DIAG_NOSTORE     // diagnostic build: gamma rows gathered from the staging tile but not written
                 if (a.out_gamma && g0 == 1.2345e-300) {
 #else
@@ -1140,6 +1147,11 @@ k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                     const int64_t row = sOut[u];
                     const double W = sW[u];
                     const double g0 = row_s[pk4[0]], g1 = row_s[pk4[1]], g2 = row_s[pk4[2]], g3 = row_s[pk4[3]];
+                    if (a.out_cgamma) {                   // compact unit row: the staged packed triangle as it is (coalesced)
+                        double* cdst = a.out_cgamma + (size_t)uid * GT_NPACK;
+                        for (int cc = tid; cc < nc; cc += 256) cdst[cc] = row_s[cc];
+                        if (tid == 0) a.out_cmask[uid] = mask;
+                    }
 #ifdef MMA_DIAG_NOSTORE
                     if (a.out_gamma && g0 == 1.2345e-300) {
 #else
@@ -1383,6 +1395,63 @@ k_expand(const int64_t* __restrict__ group_offsets, const int* __restrict__ grou
             for (int k = 0; k < K; ++k) spv += w[k] * pvv[k];
             pv[row] = spv;
         }
+    }
+}
+
+// Gamma expansion from COMPACT unit rows.  The tile kernels leave a unit's gamma as the packed triangle over the active
+// pillars of its tile (u_cgamma[unit][<= 528], u_cmask[unit]; ~30 MB instead of 205 MB for the 25 100 units of the 1M-trade
+// book), written right before this kernel runs, so the expansion's unit reads are L2 hits instead of DRAM reads threaded
+// through the 8 GB write stream (store microbenchmark tools/expand_bench.cu, variants F / K: 6.50 -> 6.90 TB/s).  Thread t
+// owns matrix entries (t >> 3, 4 (t & 7) ..+3) as in k_expand; their positions in the packed triangle follow from the mask and
+// the pillar permutation exactly as in the tile kernel's epilogue, so every row is bit-identical to the full-row path.
+template <int K>
+__global__ void __launch_bounds__(256)
+k_expand_c(const int64_t* __restrict__ group_offsets, const int* __restrict__ group_units,
+           const double* __restrict__ comp_weight, const int64_t* __restrict__ out_index,
+           const double* __restrict__ u_cgamma, const unsigned* __restrict__ u_cmask, PillarPerm pp, double* gamma)
+{
+    __shared__ double s_w[256][K];
+    __shared__ int64_t s_row[256];
+    const int gidx = blockIdx.x, tid = threadIdx.x;
+    const int64_t t0 = group_offsets[gidx];
+    const int cnt = (int)(group_offsets[gidx + 1] - t0);        // <= 256 (checked at upload)
+    if (tid < cnt) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) s_w[tid][k] = comp_weight[(t0 + tid) * K + k];
+        s_row[tid] = out_index ? out_index[t0 + tid] : t0 + tid;
+    }
+    const int oj = tid >> 3, ok4 = (tid & 7) * 4;
+    const int qj = pp.pos_of[oj];
+    int qk[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) qk[q] = pp.pos_of[ok4 + q];
+    double gv[K][4];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int uid = group_units[gidx * K + k];
+        const unsigned mask = __ldg(u_cmask + uid);
+        const double* src = u_cgamma + (size_t)uid * GT_NPACK;
+        const int ij = ((mask >> qj) & 1u) ? __popc(mask & ((1u << qj) - 1u)) : -1;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int ik = ((mask >> qk[q]) & 1u) ? __popc(mask & ((1u << qk[q]) - 1u)) : -1;
+            const int idx = ij >= ik ? ij * (ij + 1) / 2 + ik : ik * (ik + 1) / 2 + ij;
+            gv[k][q] = (ij < 0 || ik < 0) ? 0.0 : __ldg(src + idx);
+        }
+    }
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    __syncthreads();
+    for (int i = 0; i < cnt; ++i) {
+        double w[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] = s_w[i][k];
+        double x0 = 0.0, x1 = 0.0, x2 = 0.0, x3 = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) { x0 += w[k] * gv[k][0]; x1 += w[k] * gv[k][1]; x2 += w[k] * gv[k][2]; x3 += w[k] * gv[k][3]; }
+        double* dst = gamma + (size_t)s_row[i] * CAV_RR + tid * 4;
+        asm volatile("st.global.L2::cache_hint.v4.f64 [%0], {%1, %2, %3, %4}, %5;"
+                     :: "l"(dst), "d"(x0), "d"(x1), "d"(x2), "d"(x3), "l"(pol) : "memory");
     }
 }
 
