@@ -60,7 +60,12 @@ template <int K>
 void launch_expand(cav_ctx* ctx, cudaStream_t st, double* pv, double* delta, double* gamma, int64_t g0, int64_t g1) {
     if (g1 <= g0) return;
     if (gamma && ctx->expand_compact && !pv && !delta) {
-        k_expand_c<K><<<(unsigned)(g1 - g0), 256, 0, st>>>(ctx->group_offsets + g0, ctx->group_units + g0 * K, ctx->comp_weight,
+        // CAV_EXPAND_PAD_KB: unused dynamic shared memory per CTA, which caps the CTAs per SM.  Three resident CTAs (72 KB each)
+        // write the rows faster than the five the registers allow (1.287 vs 1.307 ms per 1M trades; 2: 1.289, 1: 1.394): fewer
+        // row streams interleave at the memory controllers
+        static const int pad_kb = [] { const char* e = std::getenv("CAV_EXPAND_PAD_KB"); return e ? std::atoi(e) : 72; }();
+        if (pad_kb > 40) cudaFuncSetAttribute(k_expand_c<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, pad_kb * 1024);
+        k_expand_c<K><<<(unsigned)(g1 - g0), 256, (size_t)pad_kb * 1024, st>>>(ctx->group_offsets + g0, ctx->group_units + g0 * K, ctx->comp_weight,
                                                          ctx->out_index, ctx->u_cgamma, ctx->u_cmask, ctx->pp, gamma);
         ctx->launches++;
         return;
