@@ -782,12 +782,33 @@ class OISBook:
                        self.fixed_dc_type, self.float_freq_type, self.float_dc_type, self.payment_lag, self.cal_type,
                        self.bd_type, self.dg_type)
 
-    def compute_distributed(self, request_list, device: int | None = None, dedup: bool = True, per_trade: bool = True):
+    def shard_by_schedule(self, rank: int, world: int):
+        """Strong-scaling shard: trades are dealt to the ranks by SCHEDULE (effective, termination), so that every schedule's
+        shared units are valued on one rank only (a contiguous slice of a shuffled book touches almost every schedule on
+        every rank and repeats the units stage `world` times).  Schedules go to ranks as contiguous key ranges with balanced
+        coupon counts.  Returns (book of this rank's trades in their original order, their indices in the whole book)."""
+        from .parallel import shard_bounds
+        key = self.effective.astype(np.int64) * (1 << 21) + (self.termination - self.effective).astype(np.int64)
+        uniq, inv = np.unique(key, return_inverse=True)
+        per_year = annual_frequency(self.fixed_freq_type) + annual_frequency(self.float_freq_type)
+        cost = np.maximum((self.termination - self.effective) / 365.25 * per_year, 1.0)
+        cls_cost = np.bincount(inv, weights=cost, minlength=uniq.shape[0])
+        lo, hi = shard_bounds(cls_cost, world)[rank]
+        idx = np.nonzero((inv >= lo) & (inv < hi))[0]
+        book = OISBook(self.curve, self.effective[idx], self.termination[idx], self.fixed_sign[idx], self.coupon[idx],
+                       self.notional[idx], None if self._spread is None else self._spread[idx], self.fixed_freq_type,
+                       self.fixed_dc_type, self.float_freq_type, self.float_dc_type, self.payment_lag, self.cal_type,
+                       self.bd_type, self.dg_type)
+        return book, idx
+
+    def compute_distributed(self, request_list, device: int | None = None, dedup: bool = True, per_trade: bool = True,
+                            shard: str = "range"):
         """Every rank of the initialised torch.distributed group calls this with the SAME book: each values its own
         shard on its GPU (no data-path collective) and the 1057 totals are summed over the ranks.  With an NCCL group (one
         process per GPU) the sum happens inside the totals kernel over NVLink peer memory (REQ_ALLREDUCE, csrc/cav_comm.cu):
         no collective call, one device->host read.  Other groups (gloo) all-reduce the host totals.
-        Returns (AnalyticsResult of the WHOLE book, rows of this rank's shard, (lo, hi))."""
+        Returns (AnalyticsResult of the WHOLE book, rows of this rank's shard, (lo, hi)); with shard="schedule" the trades are
+        dealt by schedule (shard_by_schedule) and the third item is the index array of this rank's trades."""
         import os
         import torch
         import torch.distributed as dist
@@ -799,7 +820,9 @@ class OISBook:
         if device is None:
             device = int(os.environ.get("LOCAL_RANK", rank))
         mask = request_mask(request_list)
-        mine = self.shard(rank, world)
+        if shard not in ("range", "schedule"):
+            raise LibError("shard must be 'range' or 'schedule'")
+        mine, idx = self.shard_by_schedule(rank, world) if shard == "schedule" else (self.shard(rank, world), None)
         backend = dist.get_backend() if dist.is_initialized() else None
         if backend == "nccl" and world > 1:
             init_device_allreduce(CurveSession.get(self.curve, device).ctx, rank, world)
@@ -808,6 +831,9 @@ class OISBook:
         else:
             agg, rows = mine._value(mask, device, dedup, per_trade)
             tot = all_reduce_totals(torch.from_numpy(agg)).numpy()
+        res = _result_from_totals(tot, mask, self.curve, self.curve._used_swaps[0])
+        if idx is not None:
+            return res, rows, idx
         per_year = annual_frequency(self.fixed_freq_type) + annual_frequency(self.float_freq_type)
         cost = np.maximum((self.termination - self.effective) / 365.25 * per_year, 1.0)
-        return (_result_from_totals(tot, mask, self.curve, self.curve._used_swaps[0]), rows, shard_bounds(cost, world)[rank])
+        return (res, rows, shard_bounds(cost, world)[rank])

@@ -1093,7 +1093,11 @@ k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
 #pragma unroll
                     for (int n = 0; n < NT; ++n) {
                         if (n < ntw) {                    // warp-uniform
+#ifdef MMA_DIAG_BSMEM       // diagnostic build: B operands from shared memory, conflict-free pattern (wrong values; timing only)
+                            const double bv = sAall[(k * 4 + ac * 4 + ar + n * 16) & 1023];
+#else
                             const double bv = __ldg(rowp + cn[n]);
+#endif
                             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                                          : "+d"(c[0][n][0]), "+d"(c[0][n][1]) : "d"(a0), "d"(bv));
                             asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"

@@ -420,7 +420,7 @@ def main():
         # by coupon count, totals summed in the totals kernel), per-trade rows of the shard written
         try:
             sbook = make_array_book(curve, n, seed=20240430)        # the same book on every rank
-            shard = sbook.shard(rank, world)
+            shard, _ = sbook.shard_by_schedule(rank, world)       # whole schedules per rank: the units stage is not repeated
             sctx = CurveSession.get(curve, local).ctx
             shard.upload(sctx)
             if world > 1:
@@ -434,7 +434,7 @@ def main():
             ms = max_over_ranks(ms)
             extras["strong_scaling_1m_book"] = {
                 "ranks": world, "trades_total": n, "trades_this_rank": ns, "ms_per_step": ms, "trades_per_s": n / ms * 1e3,
-                "note": "one 1M-trade book sharded over the ranks (OISBook.shard, balanced by coupon count), per-trade rows of "
+                "note": "one 1M-trade book sharded over the ranks by schedule (OISBook.shard_by_schedule: whole schedules per rank, balanced by coupon count), per-trade rows of "
                         "the shard written, totals of the WHOLE book on every rank via the in-kernel NVLink all-reduce; "
                         "back-to-back steps without an L2 flush, max over ranks"}
         except Exception as ex:  # noqa: BLE001
@@ -494,6 +494,39 @@ def main():
             del xvg
         except Exception as ex:  # noqa: BLE001
             extras["xccy_config5"] = {"error": repr(ex)}
+        if world > 1:
+            barrier()
+
+        # (4) BASELINE config 5, ZCIS half: 500k zero-coupon inflation swaps (two cashflows each on the path-A nodes) sharded over
+        # the ranks, device-resident cashflows, per-trade PVs + the shard total; the book total is one all-reduced double
+        try:
+            nzr = 500_000 // world
+            rzr = np.random.Generator(np.random.PCG64(101 + rank))
+            tzr = np.repeat(rzr.integers(1, 31, nzr).astype(np.float64) + rzr.uniform(0.0, 0.02, nzr), 2)
+            azr = rzr.uniform(-1e6, 1e6, 2 * nzr)
+            ozr = np.arange(0, 2 * nzr + 1, 2, dtype=np.int64)
+            ctxzr = _native.Context(local)
+            ctxzr.set_stream(stream.cuda_stream)
+            o_r, t_r, a_r = (torch.from_numpy(x).to(dev) for x in (ozr, tzr, azr))
+            pv_r = torch.empty(nzr, dtype=torch.float64, device=dev)
+            tot_r = torch.zeros(1, dtype=torch.float64, device=dev)
+            ms_z = max_over_ranks(timed(lambda: ctxzr.cashflow_pv_dev(curve._interp_type.value, curve._times, curve._dfs, 0.0, nzr,
+                                                                      o_r.data_ptr(), t_r.data_ptr(), a_r.data_ptr(), pv_r.data_ptr(),
+                                                                      tot_r.data_ptr()), reps=10, sync_all=True))
+            book_total = tot_r.clone()
+            if world > 1:
+                dist.all_reduce(book_total)
+            ref_r = np.array([curve._node_df(float(x)) for x in tzr[:64]])
+            err_r = float(np.max(np.abs(pv_r[:32].cpu().numpy() - (azr[:64] * ref_r).reshape(-1, 2).sum(1)) / 1e6))
+            extras["zcis_config5"] = {"trades_total": nzr * world, "cashflows_total": 2 * nzr * world, "ranks": world, "ms_per_step": ms_z,
+                                      "cashflows_per_s": 2 * nzr * world / ms_z * 1e3, "book_total_pv": float(book_total.item()),
+                                      "check_scaled_err_vs_host_df": err_r,
+                                      "note": "BASELINE config 5, ZCIS half: leg discounting on the path-A curve (cav_cashflow_pv_dev), "
+                                              "cashflows resident in HBM, trades sharded over the ranks, no collective in the step (the "
+                                              "book total is one all-reduced double afterwards); max over ranks"}
+            ctxzr.close()
+        except Exception as ex:  # noqa: BLE001
+            extras["zcis_config5"] = {"error": repr(ex)}
         if world > 1:
             barrier()
 

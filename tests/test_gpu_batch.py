@@ -153,6 +153,10 @@ def _dist_worker(rank, world, port, out):
     curve = bm(cv).curves.GBP_OIS_SONIA
     book = make_array_book(curve, 5000, seed=21)
     res, rows, (lo, hi) = book.compute_distributed(ALL, device=0)       # both ranks share the one test GPU
+    # the same book dealt by schedule: same totals, the shard's rows are the rows of its index set
+    res_s, rows_s, idx = book.compute_distributed(ALL, device=0, shard="schedule")
+    tot_s = np.concatenate([[res_s.value.amount], res_s.risk.risk_ladder, res_s.gamma.risk_ladder.reshape(-1)])
+    np.save(f"{out}_sched_{rank}.npy", np.concatenate([tot_s, [float(len(idx)), float(rows_s["pv"].sum())]]))
     np.save(f"{out}_{rank}.npy", np.concatenate([[res.value.amount], res.risk.risk_ladder, res.gamma.risk_ladder.reshape(-1),
                                                  [lo, hi, float(rows["pv"].sum())]]))
     dist.destroy_process_group()
@@ -174,3 +178,8 @@ def test_compute_distributed_two_ranks_equal_single_process(ref_curves, tmp_path
     assert np.max(np.abs(a[:-3] - ref) / np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))) < 1e-10
     assert (a[-3], b[-2]) == (0, 5000) and a[-2] == b[-3]                 # shards are contiguous and cover the book
     assert abs(a[-1] + b[-1] - float(rows["pv"].sum())) <= 1e-10 * float(rows["pv"].abs().sum())
+    sa, sb = np.load(out + "_sched_0.npy"), np.load(out + "_sched_1.npy")
+    assert np.array_equal(sa[:-2], sb[:-2])
+    assert np.max(np.abs(sa[:-2] - ref) / np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)))) < 1e-10
+    assert sa[-2] + sb[-2] == 5000 and min(sa[-2], sb[-2]) > 1500
+    assert abs(sa[-1] + sb[-1] - float(rows["pv"].sum())) <= 1e-10 * float(rows["pv"].abs().sum())

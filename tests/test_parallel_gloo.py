@@ -95,3 +95,28 @@ def test_array_book_shards_cover_the_book_and_add_up():
         assert max(costs) - min(costs) <= 2 * 51 * 366
         tot = sum(totals(s) for s in shards)
         assert np.max(np.abs(tot - ref)) <= 1e-12 * np.max(np.abs(ref))
+
+
+def test_schedule_shards_partition_the_book_and_keep_schedules_whole():
+    """OISBook.shard_by_schedule: the index sets of the ranks partition the book, no (effective, termination) schedule is
+    split over two ranks, coupon counts are balanced, and the trades of a shard keep their original order."""
+    from adrates_b200.batch import OISBook, add_weekdays
+    from adrates_b200.market_data import readme_model
+    curve = readme_model().curves.GBP_OIS_SONIA
+    rng = np.random.Generator(np.random.PCG64(3))
+    n = 4000
+    eff = add_weekdays(np.full(n, curve._value_dt._n), rng.integers(0, 40, n))
+    book = OISBook.from_arrays(curve, eff, tenor_years=rng.integers(1, 31, n).astype(np.int32), fixed_sign=np.where(rng.random(n) < 0.5, 1.0, -1.0),
+                               fixed_coupon=rng.uniform(0.01, 0.05, n), notional=rng.uniform(1e5, 1e7, n))
+    for world in (1, 2, 4, 8):
+        parts = [book.shard_by_schedule(r, world) for r in range(world)]
+        idx = np.concatenate([p[1] for p in parts])
+        assert np.array_equal(np.sort(idx), np.arange(n))
+        owner = {}
+        for r, (b, ix) in enumerate(parts):
+            assert np.all(np.diff(ix) > 0) and np.array_equal(b.notional, book.notional[ix])
+            for k in set(zip(b.effective.tolist(), b.termination.tolist())):
+                assert owner.setdefault(k, r) == r
+        if world > 1:
+            costs = [float(np.sum(b.termination - b.effective)) for b, _ in parts]
+            assert max(costs) <= 1.25 * (sum(costs) / world)
