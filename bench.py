@@ -688,35 +688,36 @@ def main():
     k = np.array(kern_ms)                      # [steps, 3] units / expand / totals
     dom = int(np.argmax(k.mean(0)))
     dom_name = ["k_units_mma (fused interpolation + PV + delta + gamma per schedule unit, FP64 DMMA tiles)",
-                "k_expand (per-trade PV/delta/gamma rows from unit results, streaming stores)",
+                "k_expand_c + k_expand_rows2 (per-trade gamma / PV / delta rows from the compact unit results, streaming 32-byte stores)",
                 "k_reduce_partials"][dom]
     dom_ms = float(k[:, dom].mean())
     U, T, K = info["n_units"], info["n_terms"], info["n_comp"]
-    if dom == 1:      # what the expansion stage must move: rows out; unit rows, per-trade weights and row ids in
-        phys = n * 8456 + U * 8456 + n * (K * 8 + 8)
+    if dom == 1:      # what the expansion stage must move: rows out; per-trade weights / row ids (group order) and unit ids /
+        # weights (row order) in; unit PV / delta rows in (the compact unit gammas are read from L2, not from DRAM)
+        phys = n * 8456 + n * (K * 8 + 8) + n * K * 12 + U * 264
     else:             # the units stage: terms in, unit rows (or, private layout, the trade rows) out
         phys = T * 28 + (n if args.layout == "private" else U) * 8456
     achieved_alg = n * BYTES_PER_TRADE / (dom_ms * 1e-3) / 1e9
     achieved_phys = phys / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved_phys, "peak": peak, "unit": "GB/s",
                 "frac": achieved_phys / peak, "traffic": None, "peak_source": peak_src,
-                "bytes_basis": "physical: bytes the dominant stage must move per launch (rows written + unit rows, weights and row "
-                               "ids read; model from the array sizes, see `traffic` for the ncu capture)",
+                "bytes_basis": "physical: bytes the dominant stage must move through HBM per launch (rows written; per-trade weights, row ids "
+                               "and unit PV / delta rows read; model from the array sizes, see `traffic` for the ncu capture)",
                 "physical_bytes_per_launch": phys,
                 "achieved_algorithmic": achieved_alg, "frac_algorithmic": achieved_alg / peak,
                 "algorithmic_bytes_per_launch": n * BYTES_PER_TRADE,
                 "kernel_ms": dom_ms, "kernel_share_of_step": dom_ms / ms_per_step,
-                "step_frac_physical": ((n * 8456 + U * 8456 * 2 + T * 28 + n * (K * 8 + 8)) / (ms_per_step * 1e-3) / 1e9) / peak,
+                "step_frac_physical": ((n * 8456 + n * (K * 8 + 8) + n * K * 12 + U * 264 * 2 + T * 28) / (ms_per_step * 1e-3) / 1e9) / peak,
                 "step_frac_algorithmic": (n * BYTES_PER_TRADE / (ms_per_step * 1e-3) / 1e9) / peak,
                 "all_kernels_ms": {"k_units": float(k[:, 0].mean()), "k_expand": float(k[:, 1].mean()),
                                    "k_reduce_partials": float(k[:, 2].mean())}}
-    prof = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    prof = os.path.join(ROOT, "profiles", "r02h_traffic.json")
     if os.path.exists(prof):
         try:
             with open(prof) as f:
                 tr = json.load(f)
             roofline["traffic"] = tr.get(args.layout)
-            roofline["traffic_source"] = {"file": "profiles/r02_traffic.json", "captured_at_commit": tr.get("commit"),
+            roofline["traffic_source"] = {"file": "profiles/r02h_traffic.json", "captured_at_commit": tr.get("commit"),
                                           "note": tr.get("note"), "bench_commit": git_commit()}
         except Exception:  # noqa: BLE001
             pass

@@ -1,5 +1,5 @@
-"""k_expand (8 KB unit rows) against k_expand_c (compact unit rows, L2-resident): the 1M-trade step with L2 flushed before
-each step, per-kernel times from the library's events.  CAV_EXPAND_COMPACT is read on every valuation."""
+"""Expansion stage of the 1M-trade step with L2 flushed before each step, per-kernel times from the library's events:
+request masks (7 = PV + delta + gamma, 4 = gamma only) x CAV_EXPAND_COMPACT (read on every valuation)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -15,15 +15,16 @@ pv = torch.empty(n, dtype=torch.float64, device="cuda"); dl = torch.empty(n, 32,
 gm = torch.empty(n, 32, 32, dtype=torch.float64, device="cuda"); agg = torch.zeros(1057, dtype=torch.float64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 ctx.profile(True)
-def run(mode, reps=30):
+def run(mode, mask, reps=30):
     os.environ["CAV_EXPAND_COMPACT"] = str(mode)
-    tot = 0.0; ks = np.zeros(3)
+    ks = np.zeros(3)
     for i in range(reps + 3):
         flush.zero_(); torch.cuda.synchronize()
-        ctx.portfolio_value(7, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr()); ctx.sync()
+        ctx.portfolio_value(mask, pv.data_ptr(), dl.data_ptr(), gm.data_ptr(), agg.data_ptr()); ctx.sync()
         if i >= 3:
-            k = np.array(ctx.last_kernel_ms()[:3]); ks += k; tot += k.sum()
-    return tot / reps, ks / reps
-for mode in (0, 1, 0, 1):
-    t, ks = run(mode)
-    print(f"compact={mode}: step {t:.4f} ms   kernels {np.round(ks, 4)}  pv0 {float(agg[0]):.6e}")
+            ks += np.array(ctx.last_kernel_ms()[:3])
+    return ks / reps
+for mask in (7, 4, 7, 4):
+    for mode in (0, 1):
+        ks = run(mode, mask)
+        print(f"mask={mask} compact={mode}: step {ks.sum():.4f} ms   units / expand / totals {np.round(ks, 4)}")

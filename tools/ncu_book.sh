@@ -1,7 +1,7 @@
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02e_launches_book.csv python tools/book_once.py > /dev/null 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r02h_launches_book.csv python tools/book_once.py > /dev/null 2>&1
 python - <<'P'
 import csv
-rows=[r for r in csv.reader(open('gpurun_out/r02e_launches_book.csv')) if len(r)>5 and r[0].isdigit()]
+rows=[r for r in csv.reader(open('gpurun_out/r02h_launches_book.csv')) if len(r)>5 and r[0].isdigit()]
 names=[r[4].split('(')[0].replace('<unnamed>::','').replace('void ','') for r in rows]
 idx=[i for i,n in enumerate(names) if n.startswith('k_bk_keys')]
 start=idx[-1]
