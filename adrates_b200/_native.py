@@ -60,6 +60,7 @@ _SIGS = {
 }
 E_INVALID, E_CUDA, E_STATE, E_UNSUPPORTED = -1, -2, -3, -4
 TENOR_YEARS, TENOR_MONTHS = 0, 1
+BOOK_TILES, BOOK_DATES_I32, BOOK_SIGN_I8 = 1, 2, 4      # flags of cav_book_from_arrays
 
 
 class BookConv(C.Structure):
@@ -311,15 +312,22 @@ class Context:
         """cav_book_from_arrays: per-trade arrays -> flat book + tile plan in HBM (no flat arrays cross PCIe)."""
         def arr(a, dtype):
             return None if a is None else np.ascontiguousarray(a, dtype=dtype)
-        eff = arr(effective, np.int64)
+        # narrow inputs travel as they are: int32 day serials (both date arrays) and int8 sides (flags of the C call)
+        is_dt = lambda a, dt: isinstance(a, np.ndarray) and a.dtype == dt      # noqa: E731
+        d32 = is_dt(effective, np.int32) and (termination is None or is_dt(termination, np.int32))
+        s8 = is_dt(fixed_sign, np.int8)
+        date_t = np.int32 if d32 else np.int64
+        eff = arr(effective, date_t)
         n = eff.shape[0]
-        term, ten = arr(termination, np.int64), arr(tenor, np.int32)
-        sg, cp, no, sp = (arr(a, np.float64) for a in (fixed_sign, coupon, notional, spread))
+        term, ten = arr(termination, date_t), arr(tenor, np.int32)
+        sg = arr(fixed_sign, np.int8 if s8 else np.float64)
+        cp, no, sp = (arr(a, np.float64) for a in (coupon, notional, spread))
         for name, a in (("termination", term), ("tenor", ten), ("fixed_sign", sg), ("coupon", cp), ("notional", no), ("spread", sp)):
             if a is not None and a.shape != (n,):
                 raise LibError(f"book_from_arrays: {name} must have one entry per trade")
         self._ck(self._dll.cav_book_from_arrays(self._h, C.addressof(conv), n, _ptr(eff), _ptr(term), _ptr(ten), int(tenor_unit),
-                                                _ptr(sg), _ptr(cp), _ptr(no), _ptr(sp), 1 if tiles else 0))
+                                                _ptr(sg), _ptr(cp), _ptr(no), _ptr(sp),
+                                                (BOOK_TILES if tiles else 0) | (BOOK_DATES_I32 if d32 else 0) | (BOOK_SIGN_I8 if s8 else 0)))
         self._n_trades = n
 
     def book_info(self) -> dict:

@@ -354,11 +354,20 @@ class OISBook:
                  bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING, dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  tenor=None, tenor_unit: str = "Y"):
         self.curve = curve
-        self.effective = effective            # int64 serials
+        # Narrow per-trade arrays (int32 serials, int8 sides) are kept as the caller passed them: the device flattener reads
+        # them as they are (less to move over the host link); int64 / float64 views for host code are made on first use.
+        self._eff_wire = self._sign_wire = self._term_wire = None
+        if isinstance(effective, np.ndarray) and effective.dtype == np.int32:
+            self._eff_wire, effective = effective, None
+        if isinstance(termination, np.ndarray) and termination.dtype == np.int32:
+            self._term_wire, termination = termination, None
+        if isinstance(fixed_sign, np.ndarray) and fixed_sign.dtype == np.int8:
+            self._sign_wire, fixed_sign = fixed_sign, None
+        self._effective = effective           # int64 serials
         self._termination = termination       # int64 serials (unadjusted) or None while only the tenor is known
         self._tenor = tenor                   # int32 counts in `tenor_unit` ('Y' / 'M') or None
         self._tenor_unit = tenor_unit
-        self.fixed_sign = fixed_sign          # f64: +1 receive fixed, -1 pay fixed
+        self._fixed_sign = fixed_sign         # f64: +1 receive fixed, -1 pay fixed
         self.coupon = coupon
         self.notional = notional
         self._spread = spread                 # f64 per trade, or None = no spreads
@@ -373,9 +382,30 @@ class OISBook:
         self._validated = False
 
     @property
+    def effective(self) -> np.ndarray:
+        if self._effective is None:
+            self._effective = self._eff_wire.astype(I64)
+        return self._effective
+
+    @effective.setter
+    def effective(self, a):
+        self._effective, self._eff_wire = a, None
+
+    @property
+    def fixed_sign(self) -> np.ndarray:
+        if self._fixed_sign is None:
+            self._fixed_sign = self._sign_wire.astype(np.float64)
+        return self._fixed_sign
+
+    @fixed_sign.setter
+    def fixed_sign(self, a):
+        self._fixed_sign, self._sign_wire = a, None
+
+    @property
     def termination(self) -> np.ndarray:
         if self._termination is None:
-            self._termination = add_tenor(self.effective, self._tenor, self._tenor_unit)
+            self._termination = self._term_wire.astype(I64) if self._term_wire is not None else \
+                add_tenor(self.effective, self._tenor, self._tenor_unit)
         return self._termination
 
     @property
@@ -386,7 +416,7 @@ class OISBook:
 
     @property
     def n_trades(self) -> int:
-        return int(self.effective.shape[0])
+        return int((self._eff_wire if self._effective is None else self._effective).shape[0])
 
     @classmethod
     def from_arrays(cls, curve: OISCurve, effective, termination=None, tenor_years=None, tenor_months=None,
@@ -396,12 +426,14 @@ class OISBook:
         `tenor_months` (integers, applied like Date.add_tenor('nY' / 'nM')).  Side: `fixed_leg_type` (SwapTypes per
         trade) or `fixed_sign` (+1 receive / -1 pay).  Arrays of the right dtype are kept as they are (no copies)."""
         from .global_types import SwapTypes
-        eff = serials(effective)
+        narrow_dates = isinstance(effective, np.ndarray) and effective.dtype == np.int32 and effective.flags.c_contiguous and \
+            (termination is None or (isinstance(termination, np.ndarray) and termination.dtype == np.int32))
+        eff = effective if narrow_dates else serials(effective)
         n = eff.shape[0]
         term = tenor = None
         unit = "Y"
         if termination is not None:
-            term = serials(termination)
+            term = np.ascontiguousarray(termination) if narrow_dates else serials(termination)
             if term.shape[0] != n:
                 raise LibError("effective and termination arrays differ in length")
         elif tenor_years is not None or tenor_months is not None:
@@ -422,7 +454,10 @@ class OISBook:
         if fixed_coupon is None:
             raise LibError("fixed_coupon is required")
         no_spread = np.ndim(float_spread) == 0 and float(float_spread) == 0.0
-        book = cls(curve, eff, term, vec(fixed_sign), vec(fixed_coupon), vec(notional), None if no_spread else vec(float_spread),
+        narrow_sign = isinstance(fixed_sign, np.ndarray) and fixed_sign.dtype == np.int8 and fixed_sign.shape == (n,) and \
+            fixed_sign.flags.c_contiguous
+        book = cls(curve, eff, term, fixed_sign if narrow_sign else vec(fixed_sign), vec(fixed_coupon), vec(notional),
+                   None if no_spread else vec(float_spread),
                    tenor=tenor, tenor_unit=unit, **conventions)
         if n <= EAGER_CHECK_MAX:
             book._validate()
@@ -682,8 +717,13 @@ class OISBook:
         if conv is not None:
             try:
                 unit = _native.TENOR_YEARS if self._tenor_unit == "Y" else _native.TENOR_MONTHS
-                ctx.book_from_arrays(conv, self.effective, self._termination, None if self._termination is not None else self._tenor,
-                                     unit, self.fixed_sign, self.coupon, self.notional, self._spread, tiles=tiles)
+                has_term = self._termination is not None or self._term_wire is not None
+                narrow = self._eff_wire is not None and (not has_term or self._term_wire is not None)
+                eff = self._eff_wire if narrow else self.effective
+                term = None if not has_term else (self._term_wire if narrow else self.termination)
+                ctx.book_from_arrays(conv, eff, term, None if has_term else self._tenor, unit,
+                                     self._sign_wire if self._sign_wire is not None else self.fixed_sign, self.coupon, self.notional,
+                                     self._spread, tiles=tiles)
                 self._validated = True
                 return "device"
             except LibError as ex:

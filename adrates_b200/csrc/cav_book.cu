@@ -50,6 +50,8 @@ struct BookScratch {
     // sort
     uint64_t* key[2] = {nullptr, nullptr};
     uint32_t* idx[2] = {nullptr, nullptr};
+    uint64_t* ukey[2] = {nullptr, nullptr};  // sort buffers of the tile planner (units, tiles): the trade sort's result stays intact
+    uint32_t* uidx[2] = {nullptr, nullptr};  // until the per-trade fill, which runs last (behind the last input copy)
     uint32_t* hist = nullptr;
     void* scan_sums = nullptr;               // block totals of the generic scan (8 bytes per block)
     int32_t *flag = nullptr, *cls = nullptr;
@@ -90,6 +92,7 @@ void cav_book_free(cav_ctx* ctx) {
     dev_free(ctx, &b->eff); dev_free(ctx, &b->term_in); dev_free(ctx, &b->tenor); dev_free(ctx, &b->sign); dev_free(ctx, &b->cpn);
     dev_free(ctx, &b->notl); dev_free(ctx, &b->spread); dev_free(ctx, &b->term);
     dev_free(ctx, &b->key[0]); dev_free(ctx, &b->key[1]); dev_free(ctx, &b->idx[0]); dev_free(ctx, &b->idx[1]);
+    dev_free(ctx, &b->ukey[0]); dev_free(ctx, &b->ukey[1]); dev_free(ctx, &b->uidx[0]); dev_free(ctx, &b->uidx[1]);
     dev_free(ctx, &b->hist);
     { char* p = (char*)b->scan_sums; dev_free(ctx, &p); b->scan_sums = nullptr; }
     dev_free(ctx, &b->flag); dev_free(ctx, &b->cls); dev_free(ctx, &b->cls_start); dev_free(ctx, &b->cls_key);
@@ -277,13 +280,14 @@ int radix_sort(cav_ctx* ctx, BookScratch* bk, int64_t n, uint64_t kmin, int bits
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bk_keys(Conv cv, int64_t n, const int64_t* __restrict__ eff, const int64_t* __restrict__ term_in,
                                                  const int32_t* __restrict__ tenor, int tenor_years, int64_t* term_out,
-                                                 uint64_t* key, BookStats* st) {
+                                                 uint64_t* key, BookStats* st, int dates_i32) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long k = 0, kmn = ~0ull, kmx = 0;
     int err = 0;
     if (i < n) {
-        const int64_t e = eff[i];
-        const int64_t t = term_in ? term_in[i] : add_tenor(e, tenor[i], tenor_years != 0);
+        const int64_t e = dates_i32 ? (int64_t)reinterpret_cast<const int32_t*>(eff)[i] : eff[i];
+        const int64_t t = term_in ? (dates_i32 ? (int64_t)reinterpret_cast<const int32_t*>(term_in)[i] : term_in[i])
+                                  : add_tenor(e, tenor[i], tenor_years != 0);
         term_out[i] = t;
         const int64_t span = t - e;
         if (e > adjust(t, cv.bd, cv.cal)) err |= E_START_AFTER_MAT;
@@ -539,12 +543,12 @@ __global__ void __launch_bounds__(256) k_bk_trades_fill(int64_t n, int64_t S, in
                                                         const int32_t* __restrict__ cls, const int32_t* __restrict__ has3,
                                                         const double* __restrict__ sign, const double* __restrict__ cpn,
                                                         const double* __restrict__ notl, const double* __restrict__ spread,
-                                                        double* comp_weight, int64_t* out_index) {
+                                                        double* comp_weight, int64_t* out_index, int sign_i8) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t t = idx[i];
     const int c = cls[i];
-    const double s = sign[t], N = notl[t];
+    const double s = sign_i8 ? (double)reinterpret_cast<const signed char*>(sign)[t] : sign[t], N = notl[t];
     const double wA = __dmul_rn(__dmul_rn(s, N), cpn[t]);
     const double wF = __dmul_rn(-s, N);
     comp_weight[i * K] = has3[c] ? wA : 0.0;
@@ -970,6 +974,10 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     CK(cudaMemcpyAsync(bk->d_stats, bk->h_stats, sizeof(BookStats), cudaMemcpyHostToDevice, ctx->stream));
 
     // ---- inputs ----
+    // narrow per-trade inputs (flags): int32 day serials and int8 sides travel as they are and are widened by the kernels that
+    // read them - 25 MB instead of 36 MB per 1M trades over the host link
+    const bool dates_i32 = (flags & CAV_BOOK_DATES_I32) != 0, sign_i8 = (flags & CAV_BOOK_SIGN_I8) != 0;
+    const size_t date_bytes = dates_i32 ? sizeof(int32_t) : sizeof(int64_t);
     {
         const size_t need = (size_t)N * (8 + 8 + 8 + 8 + 8 + 8) + 8 * 256;
         if (need > bk->stage_cap) {
@@ -982,8 +990,8 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
         // and notionals (two thirds of the bytes) follow on the copy stream and are awaited by k_bk_trades_fill only.
         size_t off = 0;
         CK(dev_alloc(ctx, &bk->eff, (size_t)N));
-        CK(h2d_input(ctx, bk, bk->eff, effective, sizeof(int64_t) * N, &off, ctx->stream));
-        if (termination) { CK(dev_alloc(ctx, &bk->term_in, (size_t)N)); CK(h2d_input(ctx, bk, bk->term_in, termination, sizeof(int64_t) * N, &off, ctx->stream)); }
+        CK(h2d_input(ctx, bk, bk->eff, effective, date_bytes * N, &off, ctx->stream));
+        if (termination) { CK(dev_alloc(ctx, &bk->term_in, (size_t)N)); CK(h2d_input(ctx, bk, bk->term_in, termination, date_bytes * N, &off, ctx->stream)); }
         else { CK(dev_alloc(ctx, &bk->tenor, (size_t)N)); CK(h2d_input(ctx, bk, bk->tenor, tenor, sizeof(int32_t) * N, &off, ctx->stream)); }
         CK(dev_alloc(ctx, &bk->sign, (size_t)N)); CK(dev_alloc(ctx, &bk->cpn, (size_t)N)); CK(dev_alloc(ctx, &bk->notl, (size_t)N));
         if (spread) CK(dev_alloc(ctx, &bk->spread, (size_t)N));
@@ -992,7 +1000,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
         CK(cudaStreamWaitEvent(ctx->copy, ctx->ev_up, 0));
         if (spread) CK(h2d_input(ctx, bk, bk->spread, spread, sizeof(double) * N, &off, ctx->copy));     // class flags need it first
         CK(cudaEventRecord(bk->ev_spread, ctx->copy));
-        CK(h2d_input(ctx, bk, bk->sign, fixed_sign, sizeof(double) * N, &off, ctx->copy));
+        CK(h2d_input(ctx, bk, bk->sign, fixed_sign, (sign_i8 ? sizeof(signed char) : sizeof(double)) * N, &off, ctx->copy));
         CK(h2d_input(ctx, bk, bk->cpn, coupon, sizeof(double) * N, &off, ctx->copy));
         CK(h2d_input(ctx, bk, bk->notl, notional, sizeof(double) * N, &off, ctx->copy));
         CK(cudaEventRecord(bk->ev_inputs, ctx->copy));
@@ -1006,7 +1014,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     // ---- trades: keys, sort, classes ----
     k_bk_keys<<<grid_for(N, 256), 256, 0, ctx->stream>>>(cv, N, bk->eff, termination ? bk->term_in : nullptr,
                                                         termination ? nullptr : bk->tenor, tenor_unit == CAV_TENOR_YEARS, bk->term,
-                                                        bk->key[0], bk->d_stats);
+                                                        bk->key[0], bk->d_stats, dates_i32 ? 1 : 0);
     ctx->launches++;
     CK(cudaGetLastError());
     { int rc = sync_stats(ctx, bk); if (rc) return rc; }
@@ -1106,13 +1114,24 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     }
     k_bk_groups_fill<<<grid_for(S, 128), 128, 0, ctx->stream>>>(S, K, N, NG, bk->cls_start, bk->ng, bk->gstart, bk->has3, bk->uid3,
                                                                ctx->group_offsets, ctx->group_units);
-    CK(cudaStreamWaitEvent(ctx->stream, bk->ev_inputs, 0));
-    k_bk_trades_fill<<<grid_for(N, 256), 256, 0, ctx->stream>>>(N, S, K, sidx, bk->cls, bk->has3, bk->sign, bk->cpn, bk->notl,
-                                                               spread ? bk->spread : nullptr, ctx->comp_weight, ctx->out_index);
-    k_bk_unit_weight<<<grid_for(S * K * 32, 256), 256, 0, ctx->stream>>>(S, K, bk->cls_start, bk->has3, bk->uid3, ctx->comp_weight,
-                                                                        ctx->unit_weight);
-    ctx->launches += 4;
+    ctx->launches += 2;
     CK(cudaGetLastError());
+    // The per-trade fill (weights, output rows, unit weights) is the only consumer of the sides / coupons / notionals, two thirds
+    // of the input bytes, which travel on the copy stream: it runs LAST, behind the tile planner, so that a slow host link (eight
+    // ranks sharing the host's PCIe switches) is hidden behind ~0.5 ms more of planning.  The call returns after the copies have
+    // landed (the caller's arrays may be reused).
+    auto finish_trades = [&]() -> int {
+        CK(cudaStreamWaitEvent(ctx->stream, bk->ev_inputs, 0));
+        k_bk_trades_fill<<<grid_for(N, 256), 256, 0, ctx->stream>>>(N, S, K, sidx, bk->cls, bk->has3, bk->sign, bk->cpn, bk->notl,
+                                                                   spread ? bk->spread : nullptr, ctx->comp_weight, ctx->out_index,
+                                                                   sign_i8 ? 1 : 0);
+        k_bk_unit_weight<<<grid_for(S * K * 32, 256), 256, 0, ctx->stream>>>(S, K, bk->cls_start, bk->has3, bk->uid3, ctx->comp_weight,
+                                                                            ctx->unit_weight);
+        ctx->launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaEventSynchronize(bk->ev_inputs));
+        return CAV_OK;
+    };
 
     ctx->n_units = U; ctx->n_terms = T; ctx->n_trades = N; ctx->n_groups = NG;
     ctx->n_pairs = 2; ctx->n_comp = K; ctx->direct = false;
@@ -1124,10 +1143,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
 
     // ---- tile plan ----
     const bool want_tiles = (flags & CAV_BOOK_TILES) != 0 && bk->h_stats->max_terms <= 255;
-    if (!want_tiles) {
-        CK(cudaEventSynchronize(bk->ev_inputs));      // the caller's arrays may be reused when this call returns
-        return CAV_OK;
-    }
+    if (!want_tiles) return finish_trades();
     if (bk->support_G != G || bk->h_support.size() != (size_t)G)
         return fail(ctx, CAV_E_STATE, "cav_book_from_arrays: node support masks missing (rebuild the curve)");
     CK(upload(ctx, &bk->support, bk->h_support.data(), (size_t)G));
@@ -1140,10 +1156,16 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     CK(dev_alloc(ctx, &bk->kcount, (size_t)U + 1)); CK(dev_alloc(ctx, &bk->kstart, (size_t)U + 1));
     CK(dev_alloc(ctx, &bk->gtiles, (size_t)U + 1)); CK(dev_alloc(ctx, &bk->tstart, (size_t)U + 1));
     CK(dev_alloc(ctx, &bk->pair_index, (size_t)G)); CK(dev_alloc(ctx, &bk->pairs, (size_t)2 * G));
-    if ((int64_t)U > N) {    // the sort buffers were sized for the trades
-        CK(dev_alloc(ctx, &bk->key[0], (size_t)U)); CK(dev_alloc(ctx, &bk->key[1], (size_t)U));
-        CK(dev_alloc(ctx, &bk->idx[0], (size_t)U)); CK(dev_alloc(ctx, &bk->idx[1], (size_t)U));
-    }
+    CK(dev_alloc(ctx, &bk->ukey[0], (size_t)U)); CK(dev_alloc(ctx, &bk->ukey[1], (size_t)U));
+    CK(dev_alloc(ctx, &bk->uidx[0], (size_t)U)); CK(dev_alloc(ctx, &bk->uidx[1], (size_t)U));
+    // the planner's sorts (units by group, tiles by size class) run in their own buffers: `sidx` is still needed
+    struct SortBufs {
+        BookScratch* b; uint64_t* k[2]; uint32_t* i[2];
+        explicit SortBufs(BookScratch* bk_) : b(bk_) {
+            for (int q = 0; q < 2; ++q) { k[q] = b->key[q]; i[q] = b->idx[q]; b->key[q] = b->ukey[q]; b->idx[q] = b->uidx[q]; }
+        }
+        ~SortBufs() { for (int q = 0; q < 2; ++q) { b->key[q] = k[q]; b->idx[q] = i[q]; } }
+    } sort_bufs(bk);
     k_bk_fill_u64<<<grid_for(tab_size, 256), 256, 0, ctx->stream>>>(bk->tab_key, tab_size, BK_EMPTY);
     k_bk_fill_i32<<<grid_for(tab_size, 256), 256, 0, ctx->stream>>>(bk->tab_leader, tab_size, 0x7FFFFFFF);
     k_bk_sig<<<grid_for(U, 128), 128, 0, ctx->stream>>>(U, ctx->unit_offsets, ctx->weight, ctx->node, bk->support, bk->tab_key,
@@ -1176,7 +1198,7 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     { int rc = sync_stats(ctx, bk); if (rc) return rc; }
     trace.mark("fill + tile groups (sync 4)");
     const BookStats& hs = *bk->h_stats;
-    if (hs.err & E_SIG_COLLISION) return CAV_OK;      // (never seen) keep the book, leave the Greeks to the generic kernel
+    if (hs.err & E_SIG_COLLISION) return finish_trades();      // (never seen) keep the book, leave the Greeks to the generic kernel
     const int64_t n_sig = hs.n_sig, n_tiles = hs.n_tiles, n_krows = hs.n_krows;
     CK(dev_alloc(ctx, &bk->k_pack, (size_t)n_krows));
     CK(dev_alloc(ctx, &bk->t_units, (size_t)n_tiles * GT_TM)); CK(dev_alloc(ctx, &bk->t_kstart, (size_t)n_tiles));
@@ -1217,7 +1239,8 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     ctx->tiles_valid = n_tiles > 0;
     ctx->tsym_valid = false;
     if (!same_tables) ctx->tables_ok = false;
-    if (trace.on) { cudaStreamSynchronize(ctx->stream); trace.mark("tiles filled (traced sync)"); }
+    { int rc = finish_trades(); if (rc) return rc; }
+    if (trace.on) { cudaStreamSynchronize(ctx->stream); trace.mark("tiles + trades filled (traced sync)"); }
     return CAV_OK;
 }
 

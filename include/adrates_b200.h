@@ -246,6 +246,8 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
 #define CAV_TENOR_YEARS  0
 #define CAV_TENOR_MONTHS 1
 #define CAV_BOOK_TILES   1u
+#define CAV_BOOK_DATES_I32 2u   /* `effective` / `termination` address int32 day serials (4 bytes per trade over the host link) */
+#define CAV_BOOK_SIGN_I8   4u   /* `fixed_sign` addresses int8 values +1 (receive fixed) / -1 (pay fixed) */
 typedef struct cav_book_conv {
     int64_t value_dt;            /* curve value date (serial) */
     int32_t fixed_freq_months;   /* 12 / annual_frequency(fixed_freq_type) */

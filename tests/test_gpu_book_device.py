@@ -198,3 +198,30 @@ def test_device_flatten_at_baseline_size(ref_curves):
     import torch
     assert torch.equal(rows["gamma"][::997], rows_h["gamma"][::997]) and torch.equal(rows["pv"], rows_h["pv"])
     assert abs(res.value.amount - res_h.value.amount) <= 1e-12 * max(abs(res_h.value.amount), 1.0)
+
+
+def test_narrow_inputs_build_the_same_book_on_the_device():
+    """int32 day serials + int8 sides (CAV_BOOK_DATES_I32 | CAV_BOOK_SIGN_I8) against int64 / float64 inputs: the device
+    flattener must build bit-identical flat arrays; also with explicit int32 termination dates."""
+    import numpy as np
+    from adrates_b200 import _native
+    from adrates_b200.batch import OISBook
+    from adrates_b200.market_data import readme_model
+    from adrates_b200.synthetic import make_array_book
+    curve = readme_model().curves.GBP_OIS_SONIA
+    wide = make_array_book(curve, 20_000, seed=3)
+    conv = dict(fixed_freq_type=wide.fixed_freq_type, fixed_dc_type=wide.fixed_dc_type, float_freq_type=wide.float_freq_type,
+                float_dc_type=wide.float_dc_type, bd_type=wide.bd_type)
+    narrow = OISBook.from_arrays(curve, wide.effective.astype(np.int32), tenor_years=wide._tenor, fixed_sign=wide.fixed_sign.astype(np.int8),
+                                 fixed_coupon=wide.coupon, notional=wide.notional, **conv)
+    narrow_t = OISBook.from_arrays(curve, wide.effective.astype(np.int32), termination=wide.termination.astype(np.int32),
+                                   fixed_sign=wide.fixed_sign.astype(np.int8), fixed_coupon=wide.coupon, notional=wide.notional, **conv)
+    ctx = _native.Context(0)
+    ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=2)
+    flats = []
+    for b in (wide, narrow, narrow_t):
+        assert b.upload(ctx) == "device"
+        flats.append(ctx.book_read())
+    for k in ("unit_offsets", "amt", "weight", "node", "comp_weight", "group_offsets", "group_units", "out_index", "unit_weight"):
+        for f in flats[1:]:
+            assert np.array_equal(getattr(flats[0], k), getattr(f, k)), k
