@@ -6,7 +6,7 @@ Device side: hand-written sm_100a CUDA kernels behind the C ABI in include/adrat
 (adrates_b200/csrc), loaded with ctypes.  There is no CPU fallback for valuation.
 """
 from .error import LibError
-from .dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
+from .dates import (Date, Calendar, CalendarTypes, create_calendar_intersection, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
                     DayCountTypes, FrequencyTypes, Schedule, to_tenor, times_from_dates)
 from .global_types import (SwapTypes, InstrumentTypes, RequestTypes, InterpTypes, CurveTypes,
                            CurrencyTypes, CollateralType)
@@ -17,15 +17,16 @@ from .curves import OISCurve, DiscountCurve
 from .models import Model
 from .position import Position, Portfolio, Engine
 from .results import Valuation, Delta, Gamma, CrossGamma, Risk, AnalyticsResult
+from .cashflows import CashflowItem, Cashflows
 from .credit import Bond, FRN
 from .inflation import (InflationIndex, InflationCurve, InflationIndexTypes, InflationInterpTypes, SwapInflationLeg,
                         ZeroCouponInflationSwap, SwapYoYInflationLeg, YoYInflationSwap)
 
 __all__ = [
     "OIS", "SwapFixedLeg", "SwapFloatLeg", "XccyBasisSwap", "XccyCurve", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
-    "Valuation", "Delta", "Gamma", "CrossGamma", "Risk", "AnalyticsResult", "InflationIndex", "InflationCurve", "InflationIndexTypes",
+    "Valuation", "Delta", "Gamma", "CrossGamma", "Risk", "AnalyticsResult", "CashflowItem", "Cashflows", "InflationIndex", "InflationCurve", "InflationIndexTypes",
     "InflationInterpTypes", "SwapInflationLeg", "ZeroCouponInflationSwap", "SwapYoYInflationLeg", "YoYInflationSwap", "Bond", "FRN",
-    "LibError", "Date", "Calendar", "CalendarTypes", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
+    "LibError", "Date", "Calendar", "CalendarTypes", "create_calendar_intersection", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
     "DayCountTypes", "FrequencyTypes", "Schedule", "to_tenor", "times_from_dates", "SwapTypes",
     "InstrumentTypes", "RequestTypes", "InterpTypes", "CurveTypes", "CurrencyTypes", "CollateralType",
 ]

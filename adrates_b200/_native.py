@@ -50,6 +50,7 @@ _SIGS = {
     "cav_curve_df": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_cashflow_pv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
     "cav_cashflow_pv_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
+    "cav_book_set_holidays": (C.c_int, [_P, _P, C.c_int64, C.c_int64]),
     "cav_book_from_arrays": (C.c_int, [_P, _P, C.c_int64, _P, _P, _P, C.c_int, _P, _P, _P, _P, C.c_uint32]),
     "cav_book_info": (C.c_int, [_P, _P]),
     "cav_comm_local_handle": (C.c_int, [_P, _P]),
@@ -307,6 +308,19 @@ class Context:
         return int(r.value), int(w.value), bool(lost.value)
 
     # ---- device-side flattening of array books
+    def book_set_holidays(self, table=None):
+        """cav_book_set_holidays: the non-business-day bitmap (adrates_b200.holidays table) the device flattener walks in
+        Calendar.adjust for cal_type >= 3; None clears it.  The same table is uploaded once per context."""
+        if table is getattr(self, "_hol_table", None):
+            return
+        if table is None:
+            self._ck(self._dll.cav_book_set_holidays(self._h, None, 0, 0))
+        else:
+            from . import holidays
+            words = table.words()
+            self._ck(self._dll.cav_book_set_holidays(self._h, _ptr(words), holidays.BASE, holidays.N_DAYS))
+        self._hol_table = table
+
     def book_from_arrays(self, conv: "BookConv", effective, termination=None, tenor=None, tenor_unit: int = TENOR_YEARS,
                          fixed_sign=None, coupon=None, notional=None, spread=None, tiles: bool = True):
         """cav_book_from_arrays: per-trade arrays -> flat book + tile plan in HBM (no flat arrays cross PCIe)."""

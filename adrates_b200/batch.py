@@ -28,7 +28,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from .curves import OISCurve, plan_queries
-from .dates import (BusDayAdjustTypes, CalendarTypes, Date, DateGenRuleTypes, DayCountTypes, FrequencyTypes,
+from .dates import (BusDayAdjustTypes, Calendar, CalendarTypes, Date, DateGenRuleTypes, DayCountTypes, FrequencyTypes,
                     annual_frequency)
 from .error import LibError
 from .flatten import FlatPortfolio, group_trades
@@ -120,22 +120,49 @@ def add_weekdays(n, k):
     return np.where(k > 0, fwd, np.where(k < 0, bwd, n))
 
 
-def adjust(n, bd_type: BusDayAdjustTypes, cal_type: CalendarTypes = CalendarTypes.WEEKEND):
-    """Calendar.adjust on arrays (calendar.py:139-217) for the WEEKEND / NONE calendars."""
+def _cal_table(cal):
+    """(CalendarTypes value, holidays table or None) of a CalendarTypes member or a dates.Calendar (INTERSECTION)."""
+    if isinstance(cal, Calendar):
+        return cal._cal_type, cal._table()
+    if cal in (CalendarTypes.WEEKEND, CalendarTypes.NONE):
+        return cal, None
+    if cal == CalendarTypes.INTERSECTION:
+        raise LibError("Pass the Calendar object made by create_calendar_intersection, not CalendarTypes.INTERSECTION")
+    from . import holidays
+    return cal, holidays.table(cal)
+
+
+def adjust(n, bd_type: BusDayAdjustTypes, cal_type=CalendarTypes.WEEKEND):
+    """Calendar.adjust on arrays (calendar.py:139-217): weekday arithmetic for the WEEKEND / NONE calendars, look-ups in
+    the next / previous-business-day tables of adrates_b200.holidays for the holiday calendars (`cal_type` is a
+    CalendarTypes member, or the Calendar object of an INTERSECTION)."""
     if type(bd_type) != BusDayAdjustTypes:
         raise LibError("Invalid type passed. Need Finbd_type")
-    if cal_type not in (CalendarTypes.WEEKEND, CalendarTypes.NONE):
-        raise LibError(f"Calendar {cal_type.name} is outside the accelerated path; use WEEKEND or NONE")
+    cal_type, tab = _cal_table(cal_type)
     n = np.asarray(n, dtype=I64)
     if cal_type == CalendarTypes.NONE or bd_type == BusDayAdjustTypes.NONE:
         return n
+    following = bd_type in (BusDayAdjustTypes.FOLLOWING, BusDayAdjustTypes.MODIFIED_FOLLOWING)
+    modified = bd_type in (BusDayAdjustTypes.MODIFIED_FOLLOWING, BusDayAdjustTypes.MODIFIED_PRECEDING)
+    if tab is not None:
+        from . import holidays
+        holidays.check_range(n)
+        i = n - holidays.BASE
+        fwd, bwd = tab.next_bd[i], tab.prev_bd[i]
+        if np.any(fwd >= holidays.N_DAYS) or np.any(bwd < 0):
+            holidays.check_range(np.asarray([holidays.BASE - 1]))
+        first, other = (fwd, bwd) if following else (bwd, fwd)
+        out = first + holidays.BASE
+        if modified:
+            crossed = ymd(out)[1] != ymd(n)[1]
+            out = np.where(crossed, other + holidays.BASE, out)
+        return out
     w = weekday(n)
     fwd = np.where(w == 5, 2, np.where(w == 6, 1, 0))
     bwd = -np.where(w == 5, 1, np.where(w == 6, 2, 0))
-    first, other = (fwd, bwd) if bd_type in (BusDayAdjustTypes.FOLLOWING, BusDayAdjustTypes.MODIFIED_FOLLOWING) \
-        else (bwd, fwd)
+    first, other = (fwd, bwd) if following else (bwd, fwd)
     out = n + first
-    if bd_type in (BusDayAdjustTypes.MODIFIED_FOLLOWING, BusDayAdjustTypes.MODIFIED_PRECEDING):
+    if modified:
         crossed = ymd(out)[1] != ymd(n)[1]
         out = np.where(crossed, n + other, out)
     return out
@@ -693,7 +720,7 @@ class OISBook:
     def device_conv(self):
         """cav_book_conv of this book, or None when only the host flattener handles its conventions."""
         from . import _native
-        if self.payment_lag != 0 or self.cal_type not in (CalendarTypes.WEEKEND, CalendarTypes.NONE):
+        if self.payment_lag != 0:
             return None
         supported = set(_FIXED_DEN) | set(_THIRTY) | {DayCountTypes.ACT_ACT_ISDA, DayCountTypes.ZERO}
         if self.fixed_dc_type not in supported or self.float_dc_type not in supported:
@@ -705,7 +732,7 @@ class OISBook:
         if any(st < 1 or st > 12 for st in steps):
             return None
         return _native.BookConv(self.curve._value_dt._n, steps[0], steps[1], self.fixed_dc_type.value, self.float_dc_type.value,
-                                self.cal_type.value, self.bd_type.value, self.dg_type.value, 0, 0)
+                                _cal_table(self.cal_type)[0].value, self.bd_type.value, self.dg_type.value, 0, 0)
 
     def upload(self, ctx, tiles: bool = True, dedup: bool = True, device_flatten: bool = True) -> str:
         """Make this book the portfolio of `ctx` (a _native.Context whose curve is this book's).  Shared-unit books with
@@ -721,6 +748,9 @@ class OISBook:
                 narrow = self._eff_wire is not None and (not has_term or self._term_wire is not None)
                 eff = self._eff_wire if narrow else self.effective
                 term = None if not has_term else (self._term_wire if narrow else self.termination)
+                hol = _cal_table(self.cal_type)[1]
+                if hol is not None:                       # holiday calendar: the device walks its non-business-day bitmap
+                    ctx.book_set_holidays(hol)
                 ctx.book_from_arrays(conv, eff, term, None if has_term else self._tenor, unit,
                                      self._sign_wire if self._sign_wire is not None else self.fixed_sign, self.coupon, self.notional,
                                      self._spread, tiles=tiles)

@@ -1,0 +1,151 @@
+"""CASHFLOWS request of a single-curve OIS (reference engine.py:190-213, `_extract_leg_cashflows` :34-86) and its result
+containers `CashflowItem` / `Cashflows` (results.py:945-1120).
+
+The reference answers the request by valuing both legs on the NON-AD path - `SwapFixedLeg.value` / `SwapFloatLeg.value`
+(swap_fixed_leg.py:200-245, swap_float_leg.py:190-352): one `DiscountCurve.df(date, day_count)` look-up on the path-A
+nodes per payment / accrual date - and reading the per-payment lists the legs keep afterwards.  Here every date of both
+legs becomes one batch of year fractions whose path-A discount factors come from ONE device call (`cav_curve_df`,
+`k_curve_df`: Interpolator._uinterpolate per query); the rows are then assembled on the host.  Nothing is written into the
+leg objects.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any, Dict, List
+
+import numpy as np
+
+from .dates import Date, DayCount, times_from_dates
+from .error import LibError
+from .global_types import SwapTypes
+from .results import Valuation
+
+
+@dataclass(frozen=True)
+class CashflowItem:
+    payment_date: Date
+    notional: float
+    payment_fraction: float        # amount / notional as the leg holds it (unsigned)
+    accrual_period: float
+    amount: float                  # signed: pay legs negative
+    discount_factor: float
+    discounted_amount: float
+    leg_type: str                  # "Fixed_Pay" | "Fixed_Rec" | "Float_Pay" | "Float_Rec"
+
+    def to_dict(self) -> Dict[str, Any]:
+        return {"payment_date": str(self.payment_date), "notional": float(self.notional),
+                "payment_fraction": float(self.payment_fraction), "accrual_period": float(self.accrual_period),
+                "amount": float(self.amount), "discount_factor": float(self.discount_factor),
+                "discounted_amount": float(self.discounted_amount), "leg_type": self.leg_type}
+
+
+class Cashflows:
+    def __init__(self, cashflows: List[CashflowItem], currency):
+        self.cashflows = cashflows
+        self.currency = currency
+
+    def validate(self) -> bool:
+        if not isinstance(self.cashflows, list):
+            raise ValueError("cashflows must be a list")
+        if not all(isinstance(cf, CashflowItem) for cf in self.cashflows):
+            raise ValueError("All items must be CashflowItem instances")
+        return True
+
+    def to_dict(self) -> Dict[str, Any]:
+        return {"currency": self.currency.name, "cashflows": [cf.to_dict() for cf in self.cashflows],
+                "total_amount": float(self.total_amount), "total_pv": float(self.total_pv), "count": len(self.cashflows)}
+
+    @property
+    def df(self):
+        import pandas as pd
+        if not self.cashflows:
+            return pd.DataFrame()
+        frame = pd.DataFrame([cf.to_dict() for cf in self.cashflows])
+        frame.set_index("payment_date", inplace=True)
+        return frame
+
+    @property
+    def total_amount(self) -> float:
+        return sum(cf.amount for cf in self.cashflows)
+
+    @property
+    def total_pv(self) -> float:
+        return sum(cf.discounted_amount for cf in self.cashflows)
+
+    def _only(self, word: str) -> "Cashflows":
+        return Cashflows([cf for cf in self.cashflows if word in cf.leg_type], self.currency)
+
+    def fixed(self): return self._only("Fixed")
+    def floating(self): return self._only("Float")
+    def pay(self): return self._only("Pay")
+    def receive(self): return self._only("Rec")
+    def notional_exchange(self): return self._only("Notional")
+
+    def sum(self) -> Valuation:
+        return Valuation(amount=self.total_pv, currency=self.currency)
+
+    def __len__(self) -> int:
+        return len(self.cashflows)
+
+    def __repr__(self) -> str:
+        return f"Cashflows(count={len(self.cashflows)}, total_pv={self.total_pv:,.2f} {self.currency.name})"
+
+
+def _times(dts, value_dt: Date, dc_type) -> np.ndarray:
+    return np.atleast_1d(np.asarray(times_from_dates(list(dts), value_dt, dc_type), dtype=np.float64))
+
+
+def ois_cashflows(derivative, curve, device: int = 0) -> Cashflows:
+    """Cashflow table of a single-curve OIS on `curve` (discounting and projection), rows in the reference's order: fixed
+    leg then floating leg, payments in schedule order; payments on or before the value date carry zeros."""
+    from .position import CurveSession
+    fixed, flt = derivative._fixed_leg, derivative._float_leg
+    if flt._notional_exchange or flt._notional_array:
+        raise LibError("CASHFLOWS: notional exchanges / amortising notionals are outside the accelerated path")
+    vd = curve._value_dt
+    live_x = np.array([d > vd for d in fixed._payment_dts])
+    live_f = np.array([d > vd for d in flt._payment_dts])
+    # one batch of path-A queries: [value date (fixed dc), fixed pays, value date (float dc), float pays, starts, ends]
+    t = np.concatenate([_times([vd], vd, fixed._dc_type), _times(fixed._payment_dts, vd, fixed._dc_type),
+                        _times([vd], vd, flt._dc_type), _times(flt._payment_dts, vd, flt._dc_type),
+                        _times(flt._start_accrued_dts, vd, flt._dc_type), _times(flt._end_accrued_dts, vd, flt._dc_type)])
+    nx, nf = len(fixed._payment_dts), len(flt._payment_dts)
+    live = np.concatenate([[True], live_x, [True], live_f, live_f, live_f])
+    if np.any(t[live] < 0.0):
+        raise LibError("Interpolate times must all be >= 0")
+    q = np.where(live, t, 0.0)                      # dead rows are not looked up by the reference; keep the batch dense
+    sess = CurveSession.get(curve, device)
+    df = sess.ctx.curve_df(curve._interp_type.value, curve._times, curve._dfs, q)
+    df0_x, df_x = df[0], df[1:1 + nx]
+    df0_f, df_p, df_s, df_e = df[1 + nx], df[2 + nx:2 + nx + nf], df[2 + nx + nf:2 + nx + 2 * nf], df[2 + nx + 2 * nf:]
+
+    items: List[CashflowItem] = []
+    sign_x = -1.0 if fixed._leg_type == SwapTypes.PAY else 1.0
+    name_x = "Fixed_Pay" if fixed._leg_type == SwapTypes.PAY else "Fixed_Rec"
+    name_f = "Float_Rec" if fixed._leg_type == SwapTypes.PAY else "Float_Pay"   # the reference names it off the FIXED leg
+    sign_f = -1.0 if "Pay" in name_f else 1.0
+    notl = float(fixed._notional)
+    for i in range(nx):
+        amt = float(fixed._payments[i])
+        dfp = float(df_x[i] / df0_x) if live_x[i] else 0.0
+        pv = amt * dfp if live_x[i] else 0.0
+        if i == nx - 1 and live_x[i]:
+            pv += fixed._principal * dfp * fixed._notional
+        items.append(CashflowItem(fixed._payment_dts[i], notl, amt / notl if notl != 0 else 0.0, float(fixed._year_fracs[i]),
+                                  sign_x * amt, dfp, sign_x * pv, name_x))
+    idx_dc = DayCount(curve._dc_type)
+    notl = float(flt._notional)
+    for i in range(nf):
+        if live_f[i]:
+            alpha_idx = idx_dc.year_frac(flt._start_accrued_dts[i], flt._end_accrued_dts[i])[0]
+            fwd = (df_s[i] / df_e[i] - 1.0) / alpha_idx
+            amt = float((fwd + flt._spread) * flt._year_fracs[i] * flt._notional)
+            dfp = float(df_p[i] / df0_f)
+            pv = amt * dfp
+            if i == nf - 1:
+                pv += flt._principal * dfp * flt._notional
+        else:
+            amt = dfp = pv = 0.0
+        items.append(CashflowItem(flt._payment_dts[i], notl, amt / notl if notl != 0 else 0.0, float(flt._year_fracs[i]),
+                                  sign_f * amt, dfp, sign_f * pv, name_f))
+    return Cashflows(items, derivative._currency)

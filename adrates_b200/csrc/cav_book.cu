@@ -84,6 +84,9 @@ struct BookScratch {
     cudaEvent_t ev_spread = nullptr, ev_inputs = nullptr;     // per-trade inputs that travel on the copy stream have landed
     std::vector<unsigned> h_support;         // host copy, rebuilt per curve
     int support_G = -1;
+    // holiday calendar of the next books (cav_book_set_holidays): non-business-day bitmap over [hol_base, hol_base + hol_days)
+    uint32_t* d_hol = nullptr;
+    int hol_base = 0, hol_days = 0;
 };
 
 void cav_book_free(cav_ctx* ctx) {
@@ -104,7 +107,7 @@ void cav_book_free(cav_ctx* ctx) {
     dev_free(ctx, &b->pair_index); dev_free(ctx, &b->sq_slot); dev_free(ctx, &b->sq_leader); dev_free(ctx, &b->sq_rank); dev_free(ctx, &b->t_units); dev_free(ctx, &b->t_kstart); dev_free(ctx, &b->t_kcount);
     dev_free(ctx, &b->t_npos); dev_free(ctx, &b->t_mask); dev_free(ctx, &b->tile_units); dev_free(ctx, &b->tile_kstart);
     dev_free(ctx, &b->tile_kcount); dev_free(ctx, &b->tile_npos); dev_free(ctx, &b->pairs); dev_free(ctx, &b->tile_mask);
-    dev_free(ctx, &b->k_pack); dev_free(ctx, &b->d_stats);
+    dev_free(ctx, &b->k_pack); dev_free(ctx, &b->d_stats); dev_free(ctx, &b->d_hol);
     if (b->ev_spread) cudaEventDestroy(b->ev_spread);
     if (b->ev_inputs) cudaEventDestroy(b->ev_inputs);
     if (b->h_stats) cudaFreeHost(b->h_stats);
@@ -294,6 +297,9 @@ __global__ void __launch_bounds__(256) k_bk_keys(Conv cv, int64_t n, const int64
         if (span < 0 || span >= ((int64_t)1 << BK_KEY_SPAN_BITS)) err |= E_START_AFTER_MAT;
         else if (e >= t) err |= E_EFF_GE_TERM;
         if (e < 0 || e >= ((int64_t)1 << 30)) err |= E_KEY_RANGE;
+        // every schedule date lies between the effective date and the adjusted termination date: a margin of two months on
+        // either side keeps all bitmap walks of a holiday calendar inside its table
+        if (cv.cal.bits && !cv.cal.covers(e - 62, t + 62)) err |= E_CAL_RANGE;
         if (!err) { k = ((unsigned long long)e << BK_KEY_SPAN_BITS) | (unsigned long long)span; kmn = k; kmx = k; }
         key[i] = k;
     }
@@ -915,6 +921,7 @@ int book_error(cav_ctx* ctx, int err) {
     if (err & E_NOT_MONOTONIC) return fail(ctx, CAV_E_INVALID, "Dates are not monotonic");
     if (err & E_SHORT_SCHEDULE) return fail(ctx, CAV_E_INVALID, "Schedule has none or only one date");
     if (err & E_KEY_RANGE) return fail(ctx, CAV_E_INVALID, "cav_book_from_arrays: date serial out of range");
+    if (err & E_CAL_RANGE) return fail(ctx, CAV_E_INVALID, "cav_book_from_arrays: a trade's dates lie outside the holiday bitmap (cav_book_set_holidays)");
     if (err & E_TOO_MANY_DATES) return fail(ctx, CAV_E_UNSUPPORTED, "cav_book_from_arrays: more than 4096 dates in a schedule");
     if (err & E_TIME_ORDER) return fail(ctx, CAV_E_UNSUPPORTED, "cav_book_from_arrays: cashflow times of a schedule are not ordered");
     return fail(ctx, CAV_E_INVALID, "cav_book_from_arrays: internal error");
@@ -923,6 +930,29 @@ int book_error(cav_ctx* ctx, int err) {
 }  // namespace
 
 extern "C" {
+
+int cav_book_set_holidays(cav_ctx* ctx, const uint32_t* non_business_bits, int64_t base_serial, int64_t n_days) {
+    if (!ctx) return CAV_E_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->book) ctx->book = new BookScratch();
+    BookScratch* bk = ctx->book;
+    CK(cudaStreamSynchronize(ctx->stream));               // a flattener still reading the previous bitmap
+    if (!non_business_bits) {                             // back to WEEKEND / NONE only
+        dev_free(ctx, &bk->d_hol);
+        bk->hol_base = bk->hol_days = 0;
+        return CAV_OK;
+    }
+    if (n_days <= 0 || n_days > ((int64_t)1 << 24) || base_serial < 0 || base_serial + n_days >= ((int64_t)1 << 30))
+        return fail(ctx, CAV_E_INVALID, "cav_book_set_holidays: bad range");
+    const size_t words = (size_t)((n_days + 31) / 32);
+    dev_free(ctx, &bk->d_hol);
+    CK(dev_alloc(ctx, &bk->d_hol, words));
+    CK(cudaMemcpyAsync(bk->d_hol, non_business_bits, words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));               // the caller's buffer may be reused
+    bk->hol_base = (int)base_serial;
+    bk->hol_days = (int)n_days;
+    return CAV_OK;
+}
 
 int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trades, const int64_t* effective,
                          const int64_t* termination, const int32_t* tenor, int tenor_unit, const double* fixed_sign,
@@ -937,8 +967,10 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     if (conv->payment_lag != 0) return fail(ctx, CAV_E_UNSUPPORTED, "cav_book_from_arrays: payment lag (product terms) is flattened on the host");
     if (!dc_supported(conv->fixed_dc) || !dc_supported(conv->float_dc))
         return fail(ctx, CAV_E_UNSUPPORTED, "cav_book_from_arrays: day count needs a third date; use the object-based legs");
-    if (conv->cal_type != CAL_NONE && conv->cal_type != CAL_WEEKEND)
-        return fail(ctx, CAV_E_UNSUPPORTED, "cav_book_from_arrays: calendar is outside the accelerated path; use WEEKEND or NONE");
+    if (conv->cal_type < CAL_NONE || conv->cal_type > CAL_LAST) return fail(ctx, CAV_E_INVALID, "cav_book_from_arrays: bad calendar type");
+    const bool holiday_cal = conv->cal_type != CAL_NONE && conv->cal_type != CAL_WEEKEND;
+    if (holiday_cal && !(ctx->book && ctx->book->d_hol))
+        return fail(ctx, CAV_E_UNSUPPORTED, "cav_book_from_arrays: a holiday calendar needs its non-business-day bitmap (cav_book_set_holidays)");
     if (conv->bd_type < BD_NONE || conv->bd_type > BD_MOD_PRECEDING || (conv->dg_type != DG_FORWARD && conv->dg_type != DG_BACKWARD) ||
         conv->fixed_freq_months < 1 || conv->float_freq_months < 1 || conv->fixed_freq_months > 12 || conv->float_freq_months > 12)
         return fail(ctx, CAV_E_INVALID, "cav_book_from_arrays: bad convention");
@@ -958,7 +990,8 @@ int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trad
     const int G = ctx->G;
     Conv cv;
     cv.value_dt = conv->value_dt; cv.fixed_step = conv->fixed_freq_months; cv.float_step = conv->float_freq_months;
-    cv.fixed_dc = conv->fixed_dc; cv.float_dc = conv->float_dc; cv.cal = conv->cal_type; cv.bd = conv->bd_type;
+    cv.fixed_dc = conv->fixed_dc; cv.float_dc = conv->float_dc; cv.bd = conv->bd_type;
+    cv.cal = holiday_cal ? CalRef(conv->cal_type, bk->d_hol, bk->hol_base, bk->hol_days) : CalRef(conv->cal_type);
     cv.dg = conv->dg_type; cv.eom = conv->end_of_month;
     // the two legs share one schedule when their frequencies agree; the day count only enters the fractions
     if (!bk->d_stats) {

@@ -8,7 +8,8 @@
 //
 // What each block replaces in the reference (per trade, as Python objects):
 //   cavour/utils/date.py:529-653, 796-879     Date.add_months / add_tenor
-//   cavour/utils/calendar.py:139-217          Calendar.adjust (WEEKEND / NONE calendars)
+//   cavour/utils/calendar.py:139-217          Calendar.adjust (WEEKEND / NONE in closed form; holiday calendars by a walk over the
+//                                             non-business-day bitmap of adrates_b200/holidays.py, calendar.py:257-1099)
 //   cavour/utils/schedule.py:163-270          Schedule.generate (backward / forward roll, termination adjust, duplicate filter)
 //   cavour/utils/day_count.py:122-330         DayCount.year_frac (two-date conventions)
 //   cavour/utils/helpers.py:154-197           times_from_dates
@@ -34,18 +35,36 @@ namespace cavb {
 enum { DC_ZERO = 0, DC_30_360_BOND = 1, DC_30E_360 = 2, DC_30E_360_ISDA = 3, DC_30E_PLUS_360 = 4, DC_ACT_ACT_ISDA = 5,
        DC_ACT_ACT_ICMA = 6, DC_ACT_365F = 7, DC_ACT_360 = 8, DC_ACT_365L = 9, DC_SIMPLE = 10 };
 enum { BD_NONE = 1, BD_FOLLOWING = 2, BD_MOD_FOLLOWING = 3, BD_PRECEDING = 4, BD_MOD_PRECEDING = 5 };
-enum { CAL_NONE = 1, CAL_WEEKEND = 2 };
+enum { CAL_NONE = 1, CAL_WEEKEND = 2, CAL_LAST = 16 };   // 3..16: holiday calendars, need a bitmap (CalRef::bits)
 enum { DG_FORWARD = 1, DG_BACKWARD = 2 };
 
 // error bits (OR-ed into a device flag word; the host turns them into the reference's LibError messages)
 enum { E_START_AFTER_MAT = 1, E_EFF_GE_TERM = 2, E_NOT_MONOTONIC = 4, E_SHORT_SCHEDULE = 8, E_TIME_ORDER = 16,
-       E_TOO_MANY_DATES = 32, E_SIG_COLLISION = 64, E_KEY_RANGE = 128 };
+       E_TOO_MANY_DATES = 32, E_SIG_COLLISION = 64, E_KEY_RANGE = 128, E_CAL_RANGE = 256 };
+
+// A calendar as the date rules see it: its CalendarTypes value and, for the holiday calendars, the bitmap of non-business
+// days (weekend or holiday; bit (i & 31) of word (i >> 5) = day serial base + i, i < ndays).  An int converts implicitly
+// (WEEKEND / NONE need no table), so call sites that pass a CalendarTypes value read as before.
+struct CalRef {
+    int type;
+    int base, ndays;
+    const uint32_t* bits;
+    CAVB_HD CalRef(int t = CAL_WEEKEND) : type(t), base(0), ndays(0), bits(nullptr) {}
+    CAVB_HD CalRef(int t, const uint32_t* b, int base_, int nd) : type(t), base(base_), ndays(nd), bits(b) {}
+    CAVB_HD bool closed(int n) const {              // not a business day; outside the table only weekends are known
+        const int i = n - base;
+        if (i < 0 || i >= ndays) { int w = (n + 2) % 7; if (w < 0) w += 7; return w >= 5; }
+        return (bits[i >> 5] >> (i & 31)) & 1u;
+    }
+    CAVB_HD bool covers(int64_t lo, int64_t hi) const { return lo >= base && hi < (int64_t)base + ndays; }
+};
 
 struct Conv {                 // book-wide conventions (per currency in practice)
     int64_t value_dt;         // day serial of the curve's value date
     int fixed_step, float_step;   // months per coupon period (12 / annual_frequency)
     int fixed_dc, float_dc;       // DayCountTypes values
-    int cal, bd, dg;              // CalendarTypes / BusDayAdjustTypes / DateGenRuleTypes values
+    CalRef cal;                   // CalendarTypes value (+ the non-business-day bitmap of a holiday calendar)
+    int bd, dg;                   // BusDayAdjustTypes / DateGenRuleTypes values
     int eom;                      // end-of-month roll
 };
 
@@ -115,16 +134,30 @@ CAVB_HD int64_t add_tenor(int64_t n, int64_t count, bool years) {
     return add_months(n, 12 * count, false, day);
 }
 
-// Calendar.adjust for the WEEKEND / NONE calendars
-CAVB_HD int64_t adjust(int64_t n, int bd, int cal) {
-    if (cal == CAL_NONE || bd == BD_NONE) return n;
+// Calendar.adjust: weekday arithmetic for the WEEKEND / NONE calendars, a walk over the bitmap for the holiday calendars
+CAVB_HD int64_t adjust(int64_t n, int bd, const CalRef& cal) {
+    if (cal.type == CAL_NONE || bd == BD_NONE) return n;
+    const bool following = (bd == BD_FOLLOWING || bd == BD_MOD_FOLLOWING);
+    const bool modified = (bd == BD_MOD_FOLLOWING || bd == BD_MOD_PRECEDING);
+    if (cal.bits) {
+        const int step = following ? 1 : -1;
+        int out = (int)n;
+        while (cal.closed(out)) out += step;
+        if (modified && out != (int)n) {
+            int d0, m0, d1, m1;
+            int64_t y0, y1;
+            ymd(n, d0, m0, y0);
+            ymd(out, d1, m1, y1);
+            if (m1 != m0) { out = (int)n; while (cal.closed(out)) out -= step; }
+        }
+        return out;
+    }
     const int w = weekday(n);
     const int fwd = w == 5 ? 2 : (w == 6 ? 1 : 0);
     const int bwd = -(w == 5 ? 1 : (w == 6 ? 2 : 0));
-    const bool following = (bd == BD_FOLLOWING || bd == BD_MOD_FOLLOWING);
     const int first = following ? fwd : bwd, other = following ? bwd : fwd;
     int64_t out = n + first;
-    if (bd == BD_MOD_FOLLOWING || bd == BD_MOD_PRECEDING) {
+    if (modified) {
         int d0, m0, d1, m1;
         int64_t y0, y1;
         ymd(n, d0, m0, y0);
@@ -174,7 +207,9 @@ CAVB_HD double year_frac(int64_t n1, int64_t n2, int dc) {
 // ------------------------------------------------------------------------------------------------------------------
 struct Sched {
     int64_t eff, term;
-    int step, cal, bd, dg, eom;
+    int step;
+    CalRef cal;
+    int bd, dg, eom;
     int cnt;          // dates before the duplicate filter = cnt + 1
     int dup;          // head dates dropped by the duplicate filter
     int err;          // E_* bits
@@ -201,7 +236,7 @@ CAVB_HD int64_t sched_raw_date(const Sched& s, int pos) {     // position before
 CAVB_HD int64_t sched_date(const Sched& s, int pos) { return sched_raw_date(s, pos + s.dup); }
 
 // a schedule whose (cnt, dup) an earlier make_sched has already derived and verified
-CAVB_HD Sched sched_from(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int cnt, int dup) {
+CAVB_HD Sched sched_from(int64_t eff, int64_t term, int step, const CalRef& cal, int bd, int dg, int eom, int cnt, int dup) {
     Sched s;
     s.eff = eff; s.term = term; s.step = step; s.cal = cal; s.bd = bd; s.dg = dg; s.eom = eom;
     s.cnt = cnt; s.dup = dup; s.err = 0; s.tab = nullptr;
@@ -231,7 +266,7 @@ CAVB_HD void sched_header(Sched& s, int max_dates) {
     s.cnt = cnt;
 }
 
-CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int max_dates) {
+CAVB_HD Sched make_sched(int64_t eff, int64_t term, int step, const CalRef& cal, int bd, int dg, int eom, int max_dates) {
     Sched s;
     s.eff = eff; s.term = term; s.step = step; s.cal = cal; s.bd = bd; s.dg = dg; s.eom = eom;
     s.cnt = 0; s.dup = 0; s.err = 0; s.tab = nullptr;

@@ -10,9 +10,8 @@ error behaviour) so that trades written against the reference build unchanged:
     cavour/utils/frequency.py   FrequencyTypes, annual_frequency
 
 The implementation is independent: dates are proleptic-Gregorian day ordinals (integer
-arithmetic, no lookup tables), which is all the flattener needs.  Holiday calendars other
-than WEEKEND / NONE are outside the hot path (Model.build_curve never passes one,
-models.py:190-206) and raise LibError.
+arithmetic).  WEEKEND / NONE calendars are closed-form; the national / TARGET holiday calendars
+are day-serial tables built from rule lists (adrates_b200/holidays.py).
 """
 from __future__ import annotations
 
@@ -239,8 +238,10 @@ class DateGenRuleTypes(Enum):
 
 
 class Calendar:
-    """Business-day calendar.  WEEKEND and NONE are implemented (the hot path's default,
-    ois.py:114); national holiday tables are out of scope and raise LibError."""
+    """Business-day calendar (reference calendar.py:117-335).  WEEKEND and NONE are closed-form weekday arithmetic (the hot
+    path's default, ois.py:114); the thirteen national / TARGET calendars and INTERSECTION are look-ups in the day-serial
+    tables of `adrates_b200.holidays` (rule tables evaluated once over 1901-2199, pinned bit for bit against the
+    reference's is_holiday)."""
 
     def __init__(self, cal_type: CalendarTypes, constituent_calendars=None):
         if cal_type not in CalendarTypes:
@@ -248,19 +249,45 @@ class Calendar:
         self._cal_type = cal_type
         self._constituent_calendars = constituent_calendars or []
 
-    def is_holiday(self, dt: Date) -> bool:
+    def _table(self):
+        """holidays._Table of this calendar, or None for NONE / WEEKEND (no table needed)"""
+        if self._cal_type in (CalendarTypes.NONE, CalendarTypes.WEEKEND):
+            return None
+        from . import holidays
         if self._cal_type == CalendarTypes.INTERSECTION:
-            return any(c.is_holiday(dt) for c in self._constituent_calendars)
+            flat = []
+            for c in self._constituent_calendars:
+                flat.extend(c._leaf_types())
+            return holidays.table(CalendarTypes.INTERSECTION, tuple(flat))
+        return holidays.table(self._cal_type)
+
+    def _leaf_types(self):
+        if self._cal_type == CalendarTypes.INTERSECTION:
+            out = []
+            for c in self._constituent_calendars:
+                out.extend(c._leaf_types())
+            return out
+        return [] if self._cal_type == CalendarTypes.NONE else [self._cal_type]
+
+    @staticmethod
+    def _slot(dt: Date) -> int:
+        from . import holidays
+        i = dt._n - holidays.BASE
+        if i < 0 or i >= holidays.N_DAYS:
+            raise LibError(f"Holiday calendars cover {holidays.YEAR_LO}-{holidays.YEAR_HI} (the span of the reference's Easter table)")
+        return i
+
+    def is_holiday(self, dt: Date) -> bool:
         if self._cal_type == CalendarTypes.NONE:
             return False
         if self._cal_type == CalendarTypes.WEEKEND:
             return dt.is_weekend()
-        raise LibError(f"Calendar {self._cal_type.name} is outside the accelerated path; use WEEKEND or NONE")
+        return bool(self._table().holiday[self._slot(dt)])
 
     def is_business_day(self, dt: Date) -> bool:
-        if self._cal_type == CalendarTypes.INTERSECTION:
-            return all(c.is_business_day(dt) for c in self._constituent_calendars)
-        if dt.is_weekend():
+        if self._cal_type == CalendarTypes.INTERSECTION and not self._constituent_calendars:
+            return True                      # all() over no calendars
+        if dt.is_weekend():                  # every calendar, NONE included, answers False at weekends (calendar.py:268-270)
             return False
         return not self.is_holiday(dt)
 
@@ -270,6 +297,9 @@ class Calendar:
             raise LibError("Invalid type passed. Need Finbd_type")
         if self._cal_type == CalendarTypes.NONE or bd_type == BusDayAdjustTypes.NONE:
             return dt
+        if bd_type not in (BusDayAdjustTypes.FOLLOWING, BusDayAdjustTypes.MODIFIED_FOLLOWING,
+                           BusDayAdjustTypes.PRECEDING, BusDayAdjustTypes.MODIFIED_PRECEDING):
+            raise LibError("Unknown adjustment convention" + str(bd_type))
         fwd = bd_type in (BusDayAdjustTypes.FOLLOWING, BusDayAdjustTypes.MODIFIED_FOLLOWING)
         step = 1 if fwd else -1
         out = dt
@@ -292,6 +322,38 @@ class Calendar:
             if self.is_business_day(dt):
                 left -= 1
         return dt
+
+    def get_holiday_list(self, year: int):
+        """Business-day holidays of a year as strings (reference calendar.py:1107-1121)."""
+        out, dt, end = [], Date(1, 1, year), Date(1, 1, year + 1)
+        while dt < end:
+            if not self.is_business_day(dt) and not dt.is_weekend():
+                out.append(f"{dt._d:02d}-{_MONTH_NAMES[dt._m - 1]}-{dt._y}")      # the reference's default date format
+            dt = dt.add_days(1)
+        return out
+
+    def easter_monday(self, year: int) -> Date:
+        """Reference calendar.py:1124-1137 (its Easter table; here the Gregorian computus, equal on 1901-2199)."""
+        if year > 2100:
+            raise LibError("Unable to determine Easter monday in year " + str(year))
+        from . import holidays
+        return Date._of(int(holidays.easter_monday_serial(year)))
+
+    def __str__(self):
+        return self._cal_type.name
+
+    def __repr__(self):
+        return self._cal_type.name
+
+
+def create_calendar_intersection(*calendars) -> Calendar:
+    """A date is a business day only if it is one in ALL calendars (reference calendar.py:1153-1176)."""
+    if len(calendars) < 2:
+        raise LibError("Need at least 2 calendars to create intersection")
+    for cal in calendars:
+        if not isinstance(cal, Calendar):
+            raise LibError("All arguments must be Calendar objects")
+    return Calendar(CalendarTypes.INTERSECTION, list(calendars))
 
 
 # --------------------------------------------------------------------------------------

@@ -29,7 +29,7 @@ from .results import AnalyticsResult, Delta, Gamma, Valuation
 TILE_MIN_UNITS = 64     # below this the warp-per-unit kernel is as fast and the tile plan is pure overhead
 
 
-def request_mask(request_list) -> int:
+def request_mask(request_list, allow_cashflows: bool = False) -> int:
     reqs = set(request_list)
     unknown = [r for r in reqs if not isinstance(r, RequestTypes)]
     if unknown:
@@ -41,8 +41,8 @@ def request_mask(request_list) -> int:
         mask |= _native.REQ_DELTA
     if RequestTypes.GAMMA in reqs:
         mask |= _native.REQ_GAMMA
-    if RequestTypes.CASHFLOWS in reqs:
-        raise NotImplementedError("CASHFLOWS reports use the non-AD path-A legs and are outside the CUDA path")
+    if RequestTypes.CASHFLOWS in reqs and not allow_cashflows:
+        raise NotImplementedError("CASHFLOWS reports are offered for single-curve OIS positions (Position.compute)")
     return mask
 
 
@@ -112,7 +112,16 @@ class Engine:
             if collateral_ccy != derivative._currency:
                 from .xccy_engine import compute_ois_xccy_collateral
                 return compute_ois_xccy_collateral(derivative, self.model, request_list, collateral_ccy, self.device)
-        return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
+        curve = self._curve_for(derivative)
+        if RequestTypes.CASHFLOWS not in set(request_list):
+            return value_positions([derivative], curve, request_list, self.device)
+        # CASHFLOWS (engine.py:190-213): the non-AD leg valuation on the path-A nodes, one batched DF call on the device
+        from .cashflows import ois_cashflows
+        rest = [r for r in request_list if r != RequestTypes.CASHFLOWS]
+        request_mask(rest)                                    # unknown request types are rejected as without CASHFLOWS
+        res = value_positions([derivative], curve, rest, self.device) if rest else AnalyticsResult()
+        return AnalyticsResult(value=res.value, risk=res.risk, gamma=res.gamma,
+                               cashflows=ois_cashflows(derivative, curve, self.device))
 
 
 ARRAY_ROUTE_MIN = 512   # object books at least this large are flattened as arrays (batch.OISBook)

@@ -242,7 +242,8 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
  * flags: CAV_BOOK_TILES also plans the tiles of the tensor-core Greeks kernel.
  * Errors: CAV_E_INVALID with the reference's LibError text ("Start date after maturity date", "Effective date must be
  * before termination date.", "Dates are not monotonic", "Schedule has none or only one date"); CAV_E_UNSUPPORTED for what
- * only the host flattener handles (payment lag, three-date day counts, holiday calendars, a fully matured book). */
+ * only the host flattener handles (payment lag, three-date day counts, a holiday calendar whose bitmap has not been set,
+ * a fully matured book). */
 #define CAV_TENOR_YEARS  0
 #define CAV_TENOR_MONTHS 1
 #define CAV_BOOK_TILES   1u
@@ -253,12 +254,19 @@ typedef struct cav_book_conv {
     int32_t fixed_freq_months;   /* 12 / annual_frequency(fixed_freq_type) */
     int32_t float_freq_months;
     int32_t fixed_dc, float_dc;  /* DayCountTypes values (cavour/utils/day_count.py:91-120) */
-    int32_t cal_type;            /* CalendarTypes: 1 NONE, 2 WEEKEND */
+    int32_t cal_type;            /* CalendarTypes: 1 NONE, 2 WEEKEND; 3..16 holiday calendars (cav_book_set_holidays first) */
     int32_t bd_type;             /* BusDayAdjustTypes 1..5 */
     int32_t dg_type;             /* DateGenRuleTypes: 1 FORWARD, 2 BACKWARD */
     int32_t end_of_month;
     int32_t payment_lag;         /* must be 0 on this path */
 } cav_book_conv;
+/* Holiday calendar of the books flattened from now on.  Replaces the per-date if-chains of Calendar.is_holiday /
+ * is_business_day (cavour/utils/calendar.py:257-1099) by a bitmap the schedule kernels walk in Calendar.adjust
+ * (calendar.py:139-217): bit (i & 31) of word (i >> 5) is set when day serial base_serial + i is NOT a business day
+ * (weekend or holiday), i < n_days (adrates_b200.holidays.table(cal).words(), 1901-2199).  Host pointer, copied before the
+ * call returns; NULL clears it.  A book whose trades reach within two months of either end of the range is rejected
+ * (CAV_E_INVALID). */
+int cav_book_set_holidays(cav_ctx* ctx, const uint32_t* non_business_bits, int64_t base_serial, int64_t n_days);
 int cav_book_from_arrays(cav_ctx* ctx, const cav_book_conv* conv, int64_t n_trades, const int64_t* effective,
                          const int64_t* termination, const int32_t* tenor, int tenor_unit, const double* fixed_sign,
                          const double* coupon, const double* notional, const double* spread, uint32_t flags);

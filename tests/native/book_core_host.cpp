@@ -13,7 +13,19 @@
 
 using namespace cavb;
 
+// holiday calendar of the following calls (cal >= 3): the non-business-day bitmap of adrates_b200.holidays, as the device gets it
+static std::vector<uint32_t> g_hol;
+static int g_hol_base = 0, g_hol_days = 0;
+static CalRef cal_of(int cal) {
+    return (cal > CAL_WEEKEND && !g_hol.empty()) ? CalRef(cal, g_hol.data(), g_hol_base, g_hol_days) : CalRef(cal);
+}
+
 extern "C" {
+
+void bkh_set_holidays(const uint32_t* bits, int64_t base, int64_t ndays) {
+    g_hol.assign(bits, bits + (bits ? (ndays + 31) / 32 : 0));
+    g_hol_base = (int)base; g_hol_days = (int)ndays;
+}
 
 void bkh_ymd(const int64_t* n, int64_t cnt, int64_t* d, int64_t* m, int64_t* y) {
     for (int64_t i = 0; i < cnt; ++i) { int dd, mm; int64_t yy; ymd(n[i], dd, mm, yy); d[i] = dd; m[i] = mm; y[i] = yy; }
@@ -25,7 +37,7 @@ void bkh_add_tenor(const int64_t* n, const int64_t* c, int64_t cnt, int years, i
     for (int64_t i = 0; i < cnt; ++i) out[i] = add_tenor(n[i], c[i], years != 0);
 }
 void bkh_adjust(const int64_t* n, int64_t cnt, int bd, int cal, int64_t* out) {
-    for (int64_t i = 0; i < cnt; ++i) out[i] = adjust(n[i], bd, cal);
+    for (int64_t i = 0; i < cnt; ++i) out[i] = adjust(n[i], bd, cal_of(cal));
 }
 void bkh_year_frac(const int64_t* n1, const int64_t* n2, int64_t cnt, int dc, double* out) {
     for (int64_t i = 0; i < cnt; ++i) out[i] = year_frac(n1[i], n2[i], dc);
@@ -33,7 +45,7 @@ void bkh_year_frac(const int64_t* n1, const int64_t* n2, int64_t cnt, int dc, do
 
 // schedule of one (eff, term): returns the number of dates (<= cap) or -(error bits)
 int bkh_schedule(int64_t eff, int64_t term, int step, int cal, int bd, int dg, int eom, int64_t* dates, int cap) {
-    const Sched s = make_sched(eff, term, step, cal, bd, dg, eom, 4096);
+    const Sched s = make_sched(eff, term, step, cal_of(cal), bd, dg, eom, 4096);
     if (s.err) return -s.err;
     const int n = s.n_dates();
     for (int i = 0; i < n && i < cap; ++i) dates[i] = sched_date(s, i);
@@ -58,7 +70,7 @@ struct FillSink {
 static Conv make_conv(const int64_t* cv) {
     Conv c;
     c.value_dt = cv[0]; c.fixed_step = (int)cv[1]; c.float_step = (int)cv[2]; c.fixed_dc = (int)cv[3]; c.float_dc = (int)cv[4];
-    c.cal = (int)cv[5]; c.bd = (int)cv[6]; c.dg = (int)cv[7]; c.eom = (int)cv[8];
+    c.cal = cal_of((int)cv[5]); c.bd = (int)cv[6]; c.dg = (int)cv[7]; c.eom = (int)cv[8];
     return c;
 }
 

@@ -58,6 +58,15 @@ def add_tenor(n, c, years=True):
     return out
 
 
+def set_holidays(words, base, ndays):
+    """non-business-day bitmap used by the following calls with cal >= 3 (None clears)"""
+    if words is None:
+        lib().bkh_set_holidays(None, C.c_int64(0), C.c_int64(0))
+    else:
+        w = np.ascontiguousarray(words, dtype=np.uint32)
+        lib().bkh_set_holidays(_p(w), C.c_int64(int(base)), C.c_int64(int(ndays)))
+
+
 def adjust(n, bd, cal=2):
     n = i64(n)
     out = np.empty_like(n)

@@ -225,3 +225,50 @@ def test_narrow_inputs_build_the_same_book_on_the_device():
     for k in ("unit_offsets", "amt", "weight", "node", "comp_weight", "group_offsets", "group_units", "out_index", "unit_weight"):
         for f in flats[1:]:
             assert np.array_equal(getattr(flats[0], k), getattr(f, k)), k
+
+
+@pytest.mark.parametrize("cal", ["UNITED_KINGDOM", "UNITED_STATES", "TARGET"])
+def test_device_flatten_on_a_holiday_calendar(ref_curves, cal):
+    """Books rolled on a holiday calendar are flattened on the device too (cav_book_set_holidays: the schedule kernels walk the
+    non-business-day bitmap): flat arrays and tile plan equal the host flattener's bit for bit, which the reference's own
+    holiday calendars and schedules pin (tests/test_calendars_cpu.py); the per-trade results follow."""
+    curve = _curve(ref_curves["gbp_readme_lzr"])
+    rng = np.random.default_rng(43)
+    conv = dict(CONVS["semi_vs_quarterly"], bd_type=BusDayAdjustTypes.MODIFIED_FOLLOWING)
+    arrays = _random_book(curve, 3000, rng, True)
+    book = B.OISBook.from_arrays(curve, **arrays, cal_type=CalendarTypes[cal], **conv)
+    sess = CurveSession.get(curve, 0)
+    assert book.upload(sess.ctx, tiles=True) == "device"
+    ref = book.flatten(dedup=True, tiles=True)
+    _assert_flat_equal(sess.ctx.book_read(), ref)
+    _assert_tiles_equal(sess.ctx.book_read_tiles(), ref.tile_plan, curve.path_b_plan().n_nodes)
+    weekend = B.OISBook.from_arrays(curve, **arrays, **conv).flatten(dedup=True, tiles=False)
+    assert not np.array_equal(weekend.amt, ref.amt)                    # the holidays moved coupon dates
+    tot_d, rows_d = book.compute(ALL)
+    tot_h, rows_h = book.compute(ALL, device_flatten=False)
+    for k in ("pv", "delta", "gamma"):
+        assert np.array_equal(rows_d[k].cpu().numpy(), rows_h[k].cpu().numpy()), k
+    # the WEEKEND book afterwards is flattened without the bitmap again
+    plain = B.OISBook.from_arrays(curve, **arrays, **conv)
+    assert plain.upload(sess.ctx, tiles=False) == "device"
+    _assert_flat_equal(sess.ctx.book_read(), weekend)
+
+
+def test_holiday_calendar_needs_its_bitmap_and_its_range(ref_curves):
+    curve = _curve(ref_curves["gbp_readme_lzr"])
+    sess = CurveSession.get(curve, 0)
+    vd = curve._value_dt._n
+    conv = _native.BookConv(vd, 12, 12, 7, 7, CalendarTypes.TARGET.value, 3, 2, 0, 0)
+    sess.ctx.book_set_holidays(None)
+    args = dict(effective=np.array([vd], dtype=np.int64), tenor=np.array([5], dtype=np.int32), fixed_sign=np.ones(1),
+                coupon=np.full(1, 0.03), notional=np.full(1, 1e6))
+    with pytest.raises(LibError) as ex:
+        sess.ctx.book_from_arrays(conv, **args)
+    assert ex.value.code == _native.E_UNSUPPORTED
+    from adrates_b200 import holidays as H
+    sess.ctx.book_set_holidays(H.table(CalendarTypes.TARGET))
+    sess.ctx.book_from_arrays(conv, **args)
+    far = dict(args, effective=np.array([Date(1, 6, 2199)._n], dtype=np.int64))
+    with pytest.raises(LibError) as ex:
+        sess.ctx.book_from_arrays(conv, **far)
+    assert "holiday bitmap" in str(ex.value)
