@@ -1,0 +1,68 @@
+"""CASHFLOWS request, host logic (adrates_b200/cashflows.py) against rows produced by the unmodified reference engine
+(tests/golden/ref_cashflows.json: engine.py:190-213 + _extract_leg_cashflows).  The discount factors come from the device in
+the product (cav_curve_df); here a TEST DOUBLE stands in for the context so that the row assembly - ordering, signs, leg
+names, dead rows, forward rates, the seasoned-swap error - is covered without a GPU.  tests/test_gpu_cashflows.py runs the
+same goldens through the real path."""
+import numpy as np
+import pytest
+
+from adrates_b200 import cashflows as CF
+from adrates_b200 import position
+from adrates_b200.error import LibError
+from tests.util_cashflows import assert_rows_match, golden, make_cal_trade
+from tests.util_trades import build_model
+
+
+class _HostDfContext:
+    """test double of _native.Context.curve_df: the host's scalar path-A interpolation (DiscountCurve._node_df)"""
+    def __init__(self, curve):
+        self.curve = curve
+
+    def curve_df(self, interp_method, node_time, node_df, t):
+        assert interp_method == self.curve._interp_type.value
+        return np.array([self.curve._node_df(float(u)) for u in np.asarray(t)])
+
+
+class _Session:
+    def __init__(self, curve):
+        self.ctx = _HostDfContext(curve)
+
+
+@pytest.fixture()
+def host_df(monkeypatch):
+    monkeypatch.setattr(position.CurveSession, "get", classmethod(lambda cls, curve, device=0: _Session(curve)))
+
+
+def test_cashflow_rows_match_the_reference_engine(ref_curves, host_df):
+    models = {}
+    seen_error = 0
+    for spec in golden():
+        cv = ref_curves[spec["curve"]]
+        model = models.setdefault(spec["curve"], build_model(cv))
+        curve = model.curves[cv["name"]]
+        swap = make_cal_trade(spec, cv)
+        if "error" in spec:                                  # seasoned swap: the reference raises from the float leg
+            with pytest.raises(LibError) as ex:
+                CF.ois_cashflows(swap, curve)
+            assert str(ex.value) in spec["error"]
+            seen_error += 1
+            continue
+        assert [[d.d(), d.m(), d.y()] for d in swap._fixed_leg._payment_dts] == spec["fixed_payment_dts"]
+        assert [[d.d(), d.m(), d.y()] for d in swap._float_leg._payment_dts] == spec["float_payment_dts"]
+        cf = CF.ois_cashflows(swap, curve)
+        assert_rows_match(cf, spec)
+        assert cf.validate()
+        assert repr(cf) == spec["repr"]
+        first = cf.cashflows[0].to_dict()
+        assert set(first) == set(spec["first_row_dict"]) and first["leg_type"] == spec["first_row_dict"]["leg_type"]
+        d = cf.to_dict()
+        assert d["count"] == len(cf) and d["currency"] == "GBP"
+        assert cf.df.shape == (len(cf), 7)
+    assert seen_error == 1
+
+
+def test_cashflows_request_is_rejected_where_it_is_not_offered(ref_curves):
+    from adrates_b200 import RequestTypes
+    with pytest.raises(NotImplementedError):
+        position.request_mask([RequestTypes.VALUE, RequestTypes.CASHFLOWS])
+    assert position.request_mask([RequestTypes.VALUE, RequestTypes.CASHFLOWS], allow_cashflows=True) == position.request_mask([RequestTypes.VALUE])

@@ -1,0 +1,36 @@
+"""Position.compute([VALUE, DELTA, GAMMA, CASHFLOWS]) on the device against the unmodified reference engine
+(tests/golden/ref_cashflows.json): the cashflow table (path-A discount factors from cav_curve_df) and, for the trades rolled
+on HOLIDAY calendars (UNITED_KINGDOM / TARGET / UNITED_STATES), VALUE / delta / gamma of the engine path to 1e-10."""
+import numpy as np
+import pytest
+
+from adrates_b200 import RequestTypes
+from adrates_b200.error import LibError
+from tests.util_cashflows import ALL4, assert_rows_match, golden, make_cal_trade
+from tests.util_trades import build_model, rel_err, trade_scales
+
+pytestmark = pytest.mark.gpu
+
+
+def test_cashflows_and_holiday_calendar_trades_match_the_reference(ref_curves):
+    models = {}
+    n_cal = 0
+    for spec in golden():
+        cv = ref_curves[spec["curve"]]
+        model = models.setdefault(spec["curve"], build_model(cv))
+        pos = make_cal_trade(spec, cv).position(model)
+        if "error" in spec:
+            with pytest.raises(LibError) as ex:
+                pos.compute(ALL4)
+            assert str(ex.value) in spec["error"]
+            continue
+        res = pos.compute(ALL4)
+        s_pv, s_d, s_g = trade_scales(spec)
+        e = (rel_err(res.value.amount, spec["value"], s_pv), rel_err(np.asarray(res.risk.risk_ladder), np.asarray(spec["delta"]), s_d),
+             rel_err(np.asarray(res.gamma.risk_ladder), np.asarray(spec["gamma"]), s_g))
+        assert max(e) < 1e-10, (spec["id"], e)
+        assert_rows_match(res.cashflows, spec)
+        n_cal += spec["cal"] != "WEEKEND"
+        only = pos.compute([RequestTypes.CASHFLOWS])
+        assert only.value is None and only.risk is None and len(only.cashflows) == len(spec["rows"])
+    assert n_cal == 4

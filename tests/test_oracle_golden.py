@@ -95,3 +95,23 @@ def test_trades_match_reference_engine(ref_curves, ref_trades):
         assert max(e) < TOL, (spec["id"], e)
         assert np.allclose(gamma, gamma.T, rtol=1e-10, atol=1e-14)
     assert len(worst) >= 27
+
+
+def test_holiday_calendar_trades_match_reference_engine(ref_curves):
+    """OIS rolled on UNITED_KINGDOM / TARGET / UNITED_STATES calendars (and the WEEKEND trades of the CASHFLOWS goldens), valued
+    by the unmodified reference engine: the oracle on the host legs' dates pins holiday schedules through VALUE, delta, gamma."""
+    from tests.util_cashflows import golden, make_cal_trade
+    n = 0
+    for spec in golden():
+        if "error" in spec:
+            continue
+        cv = ref_curves[spec["curve"]]
+        swap = make_cal_trade(spec, cv)
+        assert [[d.d(), d.m(), d.y()] for d in swap._fixed_leg._payment_dts] == spec["fixed_payment_dts"]
+        fixed, floating = leg_arrays(swap, Date(*cv["value_dt"]))
+        v, delta, gamma = orc.ois_analytics(tables_for(spec["curve"], cv), METHOD[cv["interp"]], fixed, floating)
+        s_pv, s_d, s_g = trade_scales(spec)
+        e = (rel_err(v, spec["value"], s_pv), rel_err(delta, spec["delta"], s_d), rel_err(gamma, spec["gamma"], s_g))
+        assert max(e) < TOL, (spec["id"], e)
+        n += spec["cal"] != "WEEKEND"
+    assert n == 4
