@@ -191,6 +191,15 @@ int mma_ctas_per_sm(bool ws) {
     return ws ? n_ws : n;
 }
 
+// Term scalars in a streaming pre-pass (k_term_scalars): an experiment switch, OFF by default.  The idea was that books of
+// private units are bound by the front warps' exp / gather work in the smaller size classes; measured on 300k private units
+// (profiles/r02m_experiments.txt) the tile kernels gain 0.02 ms of 0.99 and the pre-pass costs 0.05: 3.38 vs 3.30 ms per 1M
+// units, rows bit-identical.  The front is not what the mma warps wait for.  CAV_TERM_PREPASS = 1 turns it on.
+bool mma_term_prepass(const cav_ctx*) {
+    static const int forced = [] { const char* e = std::getenv("CAV_TERM_PREPASS"); return e ? std::atoi(e) : 0; }();
+    return forced != 0;
+}
+
 // grid of one class launch (persistent CTAs, at most the resident capacity of the class)
 template <int NT, int MINB>
 int mma_grid(const cav_ctx* ctx, int n_tiles) {
@@ -356,7 +365,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->Qmat);
     dev_free(ctx, &ctx->Tsym); dev_free(ctx, &ctx->row_units); dev_free(ctx, &ctx->row_weight); dev_free(ctx, &ctx->sc_rates); dev_free(ctx, &ctx->sc_P); dev_free(ctx, &ctx->sc_L); dev_free(ctx, &ctx->sc_upv); dev_free(ctx, &ctx->out_index); dev_free(ctx, &ctx->unit_weight);
     dev_free(ctx, &ctx->u_pv); dev_free(ctx, &ctx->u_delta); dev_free(ctx, &ctx->u_gamma);
-    dev_free(ctx, &ctx->u_cgamma); dev_free(ctx, &ctx->u_cmask);
+    dev_free(ctx, &ctx->u_cgamma); dev_free(ctx, &ctx->u_cmask); dev_free(ctx, &ctx->term_p);
     dev_free(ctx, &ctx->partials); dev_free(ctx, &ctx->agg);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
@@ -1213,6 +1222,15 @@ static int value_impl(cav_ctx* ctx, uint32_t mask, double* pv, double* delta, do
         ga.unit_weight = a.unit_weight; ga.out_index = a.out_index; ga.out_pv = a.out_pv; ga.out_delta = a.out_delta;
         ga.out_gamma = a.out_gamma; ga.partials = a.partials;
         if (!ctx->direct && ctx->expand_compact && gamma) { ga.out_cgamma = ctx->u_cgamma; ga.out_cmask = ctx->u_cmask; }
+        if (ctx->n_terms > 0 && mma_term_prepass(ctx)) {
+            CK(dev_alloc(ctx, &ctx->term_p, (size_t)ctx->n_terms));
+            const int64_t blocks = (ctx->n_terms + 255) / 256;
+            const int cap_blocks = 16 * ctx->sm_count;
+            k_term_scalars<<<(int)(blocks < cap_blocks ? blocks : cap_blocks), 256, 0, ctx->stream>>>(
+                ctx->n_terms, ga.amt, ga.weight, ga.node, ga.L, ctx->term_p);
+            ctx->launches++;
+            ga.term_p = ctx->term_p;
+        }
         { int rc = launch_mma_classes(ctx, ga); if (rc) return rc; }
     } else if (ctx->n_pairs == 2) launch_units<2>(ctx, a, want_d, want_g, grid);
     else launch_units<6>(ctx, a, want_d, want_g, grid);

@@ -164,6 +164,7 @@ struct cav_ctx {
 
     // scratch
     double *u_pv = nullptr, *u_delta = nullptr, *u_gamma = nullptr;
+    double* term_p = nullptr;            // [n_terms] term scalars of the current valuation (k_term_scalars), tiled books of private units
     double* u_cgamma = nullptr;          // compact unit gammas [n_units][528] (tile kernels -> k_expand_c)
     unsigned* u_cmask = nullptr;         // [n_units] active-pillar mask of each compact row
     bool expand_compact = false;         // this valuation's expansion reads the compact rows

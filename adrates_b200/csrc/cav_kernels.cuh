@@ -456,9 +456,26 @@ struct SimtArgs {
     double* out_delta;
     double* out_gamma;
     double* partials;          // [CTAs of this launch][1057] totals per persistent CTA, or null
+    const double* term_p = nullptr; // [n_terms] p = amt * DF computed by k_term_scalars ahead of the tile kernels, or null (computed in place)
     double* out_cgamma = nullptr;   // compact unit gammas [unit][GT_NPACK]: packed triangle over the tile's active pillars (k_expand_c)
     unsigned* out_cmask = nullptr;  // [unit] the active-pillar mask its compact row is laid out by
 };
+
+// Term scalars p = amt * DF(t) of every term in one streaming pass (experiment, CAV_TERM_PREPASS=1; off by default): the exp
+// chain, the two dependent log-DF gathers and the node loads leave the tile kernels and run here at the HBM rate (40 bytes per
+// term).  Same expression as in the tile kernels: bit-identical p (tests/test_gpu_units_ws.py).  Measured slower overall on
+// private units (3.38 vs 3.30 ms per 1M): the front warps are not what the mma warps wait for.
+__global__ void __launch_bounds__(256)
+k_term_scalars(int64_t n_terms, const double* __restrict__ amt, const double* __restrict__ weight, const int* __restrict__ node,
+               const double* __restrict__ L, double* __restrict__ p_out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_terms; i += (int64_t)gridDim.x * 256) {
+        const double2 w = __ldg(reinterpret_cast<const double2*>(weight) + i);
+        const int2 n = __ldg(reinterpret_cast<const int2*>(node) + i);
+        const double la = __ldg(L + n.x), lb = __ldg(L + n.y);
+        p_out[i] = __ldg(amt + i) * exp(w.x * la + w.y * lb);
+    }
+}
 
 #define GM_PC 32                 // term positions per chunk
 #define GM_KC 160                // K rows per chunk (at most 5 per position)
@@ -565,9 +582,12 @@ k_units_mma(SimtArgs a, int tile_begin, int tile_end, int zero_row)
 #endif
                     const int64_t i = sOff[u] + p0 + j;
                     const double2 w = __ldg(reinterpret_cast<const double2*>(a.weight) + i);
-                    const int2 n = __ldg(reinterpret_cast<const int2*>(a.node) + i);
                     w0 = w.x; w1 = w.y;
-                    p = __ldg(a.amt + i) * exp(w.x * __ldg(a.L + n.x) + w.y * __ldg(a.L + n.y));
+                    if (a.term_p) p = __ldg(a.term_p + i);
+                    else {
+                        const int2 n = __ldg(reinterpret_cast<const int2*>(a.node) + i);
+                        p = __ldg(a.amt + i) * exp(w.x * __ldg(a.L + n.x) + w.y * __ldg(a.L + n.y));
+                    }
                 }
                 sTp[idx] = p; sTw0[idx] = w0; sTw1[idx] = w1;
             }
@@ -913,8 +933,8 @@ k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                     if (okq[q]) {
                         const int64_t i = sOff[u] + p0 + j;
                         wv[q] = __ldg(reinterpret_cast<const double2*>(a.weight) + i);
-                        nv[q] = __ldg(reinterpret_cast<const int2*>(a.node) + i);
-                        av[q] = __ldg(a.amt + i);
+                        if (a.term_p) av[q] = __ldg(a.term_p + i);               // p itself (k_term_scalars)
+                        else { nv[q] = __ldg(reinterpret_cast<const int2*>(a.node) + i); av[q] = __ldg(a.amt + i); }
                     }
 #endif
                 }
@@ -927,7 +947,10 @@ k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                 }
                 double la[SQ], lb[SQ];
 #pragma unroll
-                for (int q = 0; q < SQ; ++q) { la[q] = __ldg(a.L + nv[q].x); lb[q] = __ldg(a.L + nv[q].y); }
+                for (int q = 0; q < SQ; ++q) {
+                    la[q] = lb[q] = 0.0;
+                    if (!a.term_p) { la[q] = __ldg(a.L + nv[q].x); lb[q] = __ldg(a.L + nv[q].y); }
+                }
 #pragma unroll
                 for (int q = 0; q < SQ; ++q) {
                     const int idx = ft + q * GW_FRONT;
@@ -935,7 +958,7 @@ k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
 #ifdef MMA_DIAG_NOSCAL
                     if (okq[q]) { p = 1.0 + idx; wv[q] = make_double2(0.75, 0.25); }
 #else
-                    if (okq[q]) p = av[q] * exp(wv[q].x * la[q] + wv[q].y * lb[q]);
+                    if (okq[q]) p = a.term_p ? av[q] : av[q] * exp(wv[q].x * la[q] + wv[q].y * lb[q]);
 #endif
                     sTp[idx] = p; sTw0[idx] = okq[q] ? wv[q].x : 0.0; sTw1[idx] = okq[q] ? wv[q].y : 0.0;
                 }
@@ -1017,13 +1040,14 @@ k_units_mma_ws(SimtArgs a, int tile_begin, int tile_end, int zero_row)
                     const int puid = __shfl_sync(0xffffffffu, nx_uid, pu);
                     if (puid >= 0) {
                         const char* w0 = reinterpret_cast<const char*>(a.weight) + o * 16;
-                        const char* a0 = reinterpret_cast<const char*>(a.amt) + o * 8;
+                        const char* a0 = reinterpret_cast<const char*>(a.term_p ? a.term_p : a.amt) + o * 8;
                         const char* n0 = reinterpret_cast<const char*>(a.node) + o * 8;
                         const int64_t skip = (lane & 1) * 128;
                         for (const char* q = w0 - (reinterpret_cast<uintptr_t>(w0) & 127) + skip; q < w0 + (int64_t)nP * 16; q += 256)
                             asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
                         for (const char* q = a0 - (reinterpret_cast<uintptr_t>(a0) & 127) + skip; q < a0 + (int64_t)nP * 8; q += 256)
                             asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
+                        if (!a.term_p)
                         for (const char* q = n0 - (reinterpret_cast<uintptr_t>(n0) & 127) + skip; q < n0 + (int64_t)nP * 8; q += 256)
                             asm volatile("prefetch.global.L2 [%0];" :: "l"(q));
                     }
