@@ -47,6 +47,7 @@ _SIGS = {
     "cav_portfolio_value_host": (C.c_int, [_P, C.c_uint32, _P, _P, _P, _P]),
     "cav_portfolio_delta_gemm": (C.c_int, [_P, _P, _P, C.POINTER(C.c_float), C.POINTER(C.c_double)]),
     "cav_scenarios": (C.c_int, [_P, _P, C.c_int, _P]),
+    "cav_scenarios_info": (C.c_int, [_P, _P]),
     "cav_curve_df": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, _P, C.c_int64, _P]),
     "cav_cashflow_pv": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
     "cav_cashflow_pv_dev": (C.c_int, [_P, C.c_int, _P, _P, C.c_int, C.c_double, C.c_int64, _P, _P, _P, _P, _P]),
@@ -395,6 +396,11 @@ class Context:
     def scenarios(self, shocked_rates, pnl_dev):
         r = _f64(shocked_rates)
         self._ck(self._dll.cav_scenarios(self._h, _ptr(r), r.shape[0], _ptr(pnl_dev)))
+
+    def scenarios_info(self) -> dict:
+        out = np.zeros(4, dtype=np.int64)
+        self._ck(self._dll.cav_scenarios_info(self._h, _ptr(out)))
+        return dict(zip(("queries", "chains", "chain_terms", "chain_kernel"), (int(x) for x in out)))
 
 
 _default = {}

@@ -359,6 +359,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
     dev_free(ctx, &ctx->sq_node); dev_free(ctx, &ctx->sq_w); dev_free(ctx, &ctx->sq_term); dev_free(ctx, &ctx->sc_dfq);
+    dev_free(ctx, &ctx->sch_ext); dev_free(ctx, &ctx->sch_head); dev_free(ctx, &ctx->sch_count);
     dev_free(ctx, &ctx->cf_x); dev_free(ctx, &ctx->cf_d); dev_free(ctx, &ctx->cf_t); dev_free(ctx, &ctx->cf_amt);
     dev_free(ctx, &ctx->cf_pv); dev_free(ctx, &ctx->cf_off);
     dev_free(ctx, &ctx->tile_arena); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag); dev_free(ctx, &ctx->xc_arena);
@@ -1392,6 +1393,7 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
 // Distinct DF queries of the uploaded single-DF terms (host hash over the term arrays, once per upload).
 static int ensure_scen_queries(cav_ctx* ctx) {
     if (ctx->sq_valid) return CAV_OK;
+    ctx->sch_valid = false;      // chains are found over the query ids
     static const bool on_device = [] { const char* e = std::getenv("CAV_SCEN_DEDUP"); return e ? std::atoi(e) != 0 : true; }();
     if (on_device) {          // hash-table grouping on the device: no copy of the term arrays back to the host
         const int rc = cav_book_scen_queries(ctx);
@@ -1436,6 +1438,46 @@ static int ensure_scen_queries(cav_ctx* ctx) {
     return CAV_OK;
 }
 
+// Prefix chains of the uploaded units over their DF queries (once per upload, after the query dedup): flags on the device,
+// run boundaries on the host (one int per unit comes back).
+static int ensure_scen_chains(cav_ctx* ctx) {
+    if (ctx->sch_valid) return CAV_OK;
+    const int64_t U = ctx->n_units;
+    ctx->sch_n = 0; ctx->sch_terms = 0;
+    if (U <= 0 || U >= ((int64_t)1 << 31)) { ctx->sch_valid = true; return CAV_OK; }
+    CK(dev_alloc(ctx, &ctx->sch_ext, (size_t)U));
+    k_scen_chain_flags<<<(unsigned)((U + 255) / 256), 256, 0, ctx->stream>>>(U, ctx->unit_offsets, ctx->amt, ctx->sq_term, ctx->sch_ext);
+    CK(cudaGetLastError());
+    std::vector<int> ext((size_t)U);
+    std::vector<int64_t> off((size_t)U + 1);
+    CK(cudaMemcpyAsync(ext.data(), ctx->sch_ext, sizeof(int) * U, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(off.data(), ctx->unit_offsets, sizeof(int64_t) * (U + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<int> head, count;
+    int64_t walk = 0;
+    for (int64_t u = 0; u < U; ++u) {
+        if (!ext[u]) { head.push_back((int)u); count.push_back(1); }
+        else count.back()++;
+        if (u + 1 == U || !ext[u + 1]) walk += off[u + 1] - off[u];       // last member of its chain
+    }
+    ctx->sch_n = (int64_t)head.size();
+    ctx->sch_terms = walk;
+    CK(upload(ctx, &ctx->sch_head, head.data(), head.size()));
+    CK(upload(ctx, &ctx->sch_count, count.data(), count.size()));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->sch_valid = true;
+    return CAV_OK;
+}
+
+int cav_scenarios_info(cav_ctx* ctx, int64_t* out) {
+    if (!ctx || !out) return CAV_E_INVALID;
+    out[0] = ctx->sq_valid ? ctx->sq_n : 0;
+    out[1] = ctx->sch_valid ? ctx->sch_n : 0;
+    out[2] = ctx->sch_valid ? ctx->sch_terms : 0;
+    out[3] = ctx->sch_used;
+    return CAV_OK;
+}
+
 int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev) {
     if (!ctx) return CAV_E_INVALID;
     if (!shocked_rates || n_scen < 1 || !pnl_dev) return fail(ctx, CAV_E_INVALID, "cav_scenarios: bad arguments");
@@ -1465,8 +1507,19 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
         CK(dev_alloc(ctx, &ctx->sc_dfq, (size_t)ctx->sq_n * S));
         dim3 gq((unsigned)ctx->sq_n, (unsigned)((n_scen + 127) / 128));
         k_scen_df<<<gq, 128, 0, ctx->stream>>>(n_scen, ctx->sq_node, ctx->sq_w, ctx->sc_L, ctx->sc_dfq);
-        const int units_variant = [] { const char* e = std::getenv("CAV_SCEN_UNITS"); return e ? std::atoi(e) : 2; }();
-        if (units_variant == 2 && n_scen % 2 == 0) {    // two scenarios per thread, 16-byte gathers
+        const int units_variant = [] { const char* e = std::getenv("CAV_SCEN_UNITS"); return e ? std::atoi(e) : 3; }();
+        ctx->sch_used = 0;
+        bool chains = false;
+        if (units_variant == 3 && n_scen % 2 == 0) {    // prefix chains, when they save at least a third of the gathers
+            { int rc = ensure_scen_chains(ctx); if (rc) return rc; }
+            chains = ctx->sch_n > 0 && ctx->sch_terms * 3 <= ctx->n_terms * 2;
+        }
+        if (chains) {
+            dim3 gc((unsigned)ctx->sch_n, (unsigned)((n_scen / 2 + 127) / 128));
+            k_scen_units_chain<<<gc, 128, 0, ctx->stream>>>(n_scen, ctx->sch_head, ctx->sch_count, ctx->unit_offsets, ctx->amt, ctx->sq_term,
+                                                            ctx->sc_dfq, ctx->sc_upv);
+            ctx->sch_used = 1;
+        } else if (units_variant >= 2 && n_scen % 2 == 0) {    // two scenarios per thread, 16-byte gathers
             dim3 gu2((unsigned)ctx->n_units, (unsigned)((n_scen / 2 + 127) / 128));
             k_scen_units_q2<<<gu2, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->sq_term, ctx->sc_dfq, ctx->sc_upv);
         } else
@@ -1476,8 +1529,25 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
         k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
     else
         k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
-    const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 2; }();
-    if (expand_variant == 2 && n_scen % 2 == 0) {       // 16-byte reads of the unit values need an even row length
+    const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 3; }();
+    if (expand_variant == 3 && n_scen % 2 == 0 && ctx->n_trades % 2 == 0 && (reinterpret_cast<uintptr_t>(pnl_dev) & 15) == 0) {
+        // bulk-store kernel: rows of the P&L matrix must start and end on 16-byte boundaries
+        dim3 ge((unsigned)((ctx->n_trades + SX3_R - 1) / SX3_R), (unsigned)((n_scen + SX3_S - 1) / SX3_S));
+        const size_t sm3 = (size_t)SX3_DOUBLES * sizeof(double);
+        // (per call: the attribute belongs to the function on the current device, and a call costs microseconds)
+        switch (ctx->n_comp) {
+            case 1: CK(cudaFuncSetAttribute(k_scen_expand3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
+            case 2: CK(cudaFuncSetAttribute(k_scen_expand3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
+            case 3: CK(cudaFuncSetAttribute(k_scen_expand3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
+            default: CK(cudaFuncSetAttribute(k_scen_expand3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
+        }
+        switch (ctx->n_comp) {
+            case 1: k_scen_expand3<1><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            case 2: k_scen_expand3<2><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            case 3: k_scen_expand3<3><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+            default: k_scen_expand3<4><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
+        }
+    } else if (expand_variant >= 2 && n_scen % 2 == 0) {       // 16-byte reads of the unit values need an even row length
         dim3 ge((unsigned)((ctx->n_trades + SX2_R - 1) / SX2_R), (unsigned)((n_scen + SX2_S - 1) / SX2_S));
         switch (ctx->n_comp) {
             case 1: k_scen_expand2<1><<<ge, 256, 0, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;

@@ -146,6 +146,11 @@ struct cav_ctx {
     double* sc_dfq = nullptr;
     int64_t sq_n = 0;
     bool sq_valid = false;
+    // prefix chains of units over the queries (k_scen_units_chain): runs of units whose term lists extend their predecessor's
+    int *sch_ext = nullptr, *sch_head = nullptr, *sch_count = nullptr;
+    int64_t sch_n = 0, sch_terms = 0;    // chains; terms the chain kernel walks (sum of the last members' lists)
+    bool sch_valid = false;
+    int sch_used = 0;                    // the last cav_scenarios call took the chain kernel
     double *cf_x = nullptr, *cf_d = nullptr, *cf_t = nullptr, *cf_amt = nullptr, *cf_pv = nullptr;   // cashflow PV scratch (grow-only)
     int64_t* cf_off = nullptr;
     int64_t* out_index = nullptr;

@@ -2022,3 +2022,156 @@ k_scen_expand2(int n_scen, int64_t n_trades, const int* __restrict__ row_units /
         if (sc < n_scen && row_in) __stcs(pnl + (size_t)sc * n_trades + rbase + tx, tile[tx * (SX2_S + 1) + c]);
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// Prefix chains of units.  Schedule units of one start date and growing maturity are prefixes of each other: the annuity
+// of the 7Y swap is the annuity of the 6Y swap plus one term, same dates, same accruals.  The flattener numbers such units
+// consecutively (classes are sorted by (effective, span)), so a chain is a run of units u0, u0+1, ... in which every term
+// list starts with the whole list of its predecessor (k_scen_chain_flags: same DF query and bit-equal amount, position by
+// position).  k_scen_units_chain then walks ONLY the last member's list and drops every member's value at its prefix
+// point: the sum is the same left-to-right chain of FMAs k_scen_units_q2 runs per unit, so the unit values are bit-identical,
+// at the gather work of one unit per chain instead of all of them (BASELINE config 4: 12.6k distinct queries against 339k
+// terms - 27x fewer gathers from the L2-resident DF slab).  Units outside any run are chains of one.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_scen_chain_flags(int64_t n_units, const int64_t* __restrict__ unit_offsets, const double* __restrict__ amt,
+                   const int* __restrict__ term_q, int* __restrict__ ext)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    int e = 0;
+    if (u > 0) {
+        const int64_t p0 = unit_offsets[u - 1], t0 = unit_offsets[u], t1 = unit_offsets[u + 1];
+        const int64_t lp = t0 - p0, lu = t1 - t0;
+        if (lp > 0 && lu >= lp) {
+            e = 1;
+            for (int64_t i = 0; i < lp; ++i)
+                if (term_q[p0 + i] != term_q[t0 + i] || __double_as_longlong(amt[p0 + i]) != __double_as_longlong(amt[t0 + i])) { e = 0; break; }
+        }
+    }
+    ext[u] = e;
+}
+
+__global__ void __launch_bounds__(128)
+k_scen_units_chain(int n_scen, const int* __restrict__ chain_head, const int* __restrict__ chain_count,
+                   const int64_t* __restrict__ unit_offsets, const double* __restrict__ amt, const int* __restrict__ term_q,
+                   const double* __restrict__ dfq, double* unit_pv /*[U][S]*/)
+{
+    const int s = 2 * (blockIdx.y * blockDim.x + threadIdx.x);
+    if (s >= n_scen) return;
+    const int u0 = chain_head[blockIdx.x], cnt = chain_count[blockIdx.x];
+    const int64_t t0 = unit_offsets[u0 + cnt - 1];
+    const int L = (int)(unit_offsets[u0 + cnt] - t0);                 // the last member's list contains every member's
+    const double* base = dfq + s;
+    double2 pv = make_double2(0.0, 0.0);
+    int m = 0;                                                        // next member to complete, at prefix length next_len
+    int next_len = (int)(unit_offsets[u0 + 1] - unit_offsets[u0]);
+    while (m < cnt && next_len == 0) {                                // (no flattened book has empty units)
+        *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
+        ++m;
+        next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
+    }
+    double2 d[4];
+    double a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {                                     // four gathers in flight, refilled as they are consumed
+        a[j] = 0.0; d[j] = make_double2(0.0, 0.0);
+        if (j < L) { a[j] = amt[t0 + j]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + j] * n_scen); }
+    }
+    for (int i = 0; i < L; i += 4) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ii = i + j;
+            if (ii < L) {
+                pv.x += a[j] * d[j].x; pv.y += a[j] * d[j].y;          // summed in term order, as k_scen_units_q2 does
+                if (ii + 4 < L) { a[j] = amt[t0 + ii + 4]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + ii + 4] * n_scen); }
+                while (ii + 1 == next_len) {
+                    *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
+                    ++m;
+                    next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
+                }
+            }
+        }
+    }
+}
+
+// Variant with bulk stores (even scenario and trade counts): a 128 x 64 (trades x scenarios) tile assembled in shared memory
+// in OUTPUT orientation (one row per scenario, trades contiguous) and written by the copy engine, one
+// cp.async.bulk.global.shared::cta of up to 1 KB per scenario row.  k_scen_expand2 spends ~29 instructions per output, more than
+// half of them on the store side (LDS + 64-bit address + predicate + STG per 8-byte output, 256-byte row segments): it is
+// issue-bound at 3 TB/s of P&L.  Here the store side costs 64 instructions per 8 192 outputs, the rows go out as 1 KB bursts
+// and the gather side is trimmed as well (weights and unit ids of two trades in three 16-byte loads, one 32 x 32 -> 64-bit
+// multiply-add per unit-row address): ~13 instructions per output in SASS.  A thread gathers a 2 x 2 block (trades r, r+1 x scenarios s, s+1): 16-byte reads of the unit values as before, and
+// two 16-byte shared-memory stores; scenario row s starts at s*128 + 2*(s>>1) doubles, which keeps the rows 16-byte aligned
+// and the quarter-warps of those stores on distinct banks.  Same sums in the same order: bit-identical to the other kernels.
+#define SX3_R 128
+#define SX3_S 64
+#define SX3_DOUBLES (SX3_S * SX3_R + SX3_S)
+template <int K>
+__global__ void __launch_bounds__(256, 3)
+k_scen_expand3(int n_scen, int64_t n_trades, const int* __restrict__ row_units /*[N][K]*/,
+               const double* __restrict__ row_weight, const double* __restrict__ unit_pv, double* pnl)
+{
+    extern __shared__ __align__(16) double tile3[];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 scenario pairs x 8 warps
+    const int64_t rbase = (int64_t)blockIdx.x * SX3_R;
+    const int sbase = blockIdx.y * SX3_S;
+    const int s0 = sbase + 2 * tx;
+    const bool in0 = s0 < n_scen;                             // n_scen is even: a pair is inside or outside as a whole
+    const int64_t left = n_trades - rbase;
+    const int nloc = left < SX3_R ? (int)left : SX3_R;        // trades of this tile: even, because n_trades is
+    double* trow = tile3 + (2 * tx) * SX3_R + 2 * tx;          // row 2tx; row 2tx + 1 starts SX3_R doubles further
+    // unit row u holds its n_scen values contiguously: one 32 x 32 -> 64-bit multiply-add per address
+    const char* ubase = reinterpret_cast<const char*>(unit_pv + (in0 ? s0 : 0));
+    const unsigned row_bytes = (unsigned)n_scen * 8u;
+    const double* wp = row_weight + rbase * K;
+    const int* up = row_units + rbase * K;
+#pragma unroll 2
+    for (int it = 0; it < SX3_R / 16; ++it) {
+        const int r = 2 * (ty + 8 * it);                      // trades r, r + 1 (both inside or both outside: nloc is even)
+        double2 va = make_double2(0.0, 0.0), vb = va;
+        if (in0 && r < nloc) {
+            double w[2 * K];
+            int u[2 * K];
+            if constexpr (K == 2) {                           // weights and unit ids of both trades in three 16-byte loads
+                const double2 wa = __ldg(reinterpret_cast<const double2*>(wp + 2 * r));
+                const double2 wb = __ldg(reinterpret_cast<const double2*>(wp + 2 * r + 2));
+                const int4 uu = __ldg(reinterpret_cast<const int4*>(up + 2 * r));
+                w[0] = wa.x; w[1] = wa.y; w[2] = wb.x; w[3] = wb.y;
+                u[0] = uu.x; u[1] = uu.y; u[2] = uu.z; u[3] = uu.w;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2 * K; ++k) { w[k] = __ldg(wp + r * K + k); u[k] = __ldg(up + r * K + k); }
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (w[k] != 0.0) {
+                    const double2 a = __ldg(reinterpret_cast<const double2*>(ubase + (unsigned long long)(unsigned)u[k] * row_bytes));
+                    va.x = fma(w[k], a.x, va.x); va.y = fma(w[k], a.y, va.y);
+                }
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                if (w[K + k] != 0.0) {
+                    const double2 a = __ldg(reinterpret_cast<const double2*>(ubase + (unsigned long long)(unsigned)u[K + k] * row_bytes));
+                    vb.x = fma(w[K + k], a.x, vb.x); vb.y = fma(w[K + k], a.y, vb.y);
+                }
+        }
+        *reinterpret_cast<double2*>(trow + r) = make_double2(va.x, vb.x);
+        *reinterpret_cast<double2*>(trow + SX3_R + r) = make_double2(va.y, vb.y);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the tile, written through the generic proxy, is read by the copy engine
+    __syncthreads();
+    if (threadIdx.x < SX3_S) {
+        const int c = threadIdx.x, sc = sbase + c;
+        if (sc < n_scen) {
+            unsigned long long pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            const double* src = tile3 + c * SX3_R + 2 * (c >> 1);
+            double* dst = pnl + (size_t)sc * n_trades + rbase;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                         :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(src)), "r"((unsigned)nloc * 8u), "l"(pol) : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the copy engine's reads
+    }
+}

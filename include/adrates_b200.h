@@ -225,6 +225,10 @@ int cav_portfolio_delta_gemm(cav_ctx* ctx, double* pv_dev, double* delta_dev, fl
  * full par-rate vector; every curve is re-bootstrapped (DFs only) and every trade
  * revalued.  pnl_dev[s][trade] = PV under scenario s (device, [n_scen][n_trades]). */
 int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double* pnl_dev);
+/* what the scenario path found in the uploaded book (after a cav_scenarios call): out[4] = distinct DF queries, prefix chains
+ * of units (runs of units whose term lists extend their predecessor's: same dates, growing maturity), terms the chain kernel
+ * walks (against n_terms for the per-unit kernels), 1 if the last call took the chain kernel.  Measurement / tests only. */
+int cav_scenarios_info(cav_ctx* ctx, int64_t* out);
 
 /* ---- device-side book flattener: replaces the per-trade object layer in front of the valuation ------------------
  * The reference turns every OIS into a Schedule, two legs and ~50 Date objects before it values a cashflow

@@ -71,23 +71,59 @@ def test_array_book_scenario_values_match_books_on_rebuilt_curves(ref_curves, co
 
 
 @pytest.mark.parametrize("n_scen", [2, 38, 130, 256])
-def test_scenario_expansion_kernels_agree_bitwise(ref_curves, monkeypatch, n_scen):
-    """Even scenario counts take the 32x128 expansion kernel with 16-byte reads, odd ones (and CAV_SCEN_EXPAND=1) the
-    64x64 kernel: same sums in the same order, so the matrices are identical, ragged tile edges included."""
-    from adrates_b200.synthetic import make_book, shocked_rate_scenarios
+@pytest.mark.parametrize("n", [1237, 1238])
+def test_scenario_expansion_kernels_agree_bitwise(ref_curves, monkeypatch, n_scen, n):
+    """Even scenario counts take the bulk-store expansion kernel (128 x 64 tiles written by cp.async.bulk; even trade counts
+    only) or the 32x128 kernel with 16-byte reads, odd ones (and CAV_SCEN_EXPAND=1) the 64x64 kernel: same sums in the same
+    order, so the matrices are identical, ragged tile edges included (1237 / 1238 trades: neither a multiple of 32 nor of 128)."""
+    from adrates_b200.synthetic import shocked_rate_scenarios
     cv = ref_curves["gbp_readme_lzr"]
     model = build_model(cv)
     curve = model.curves[cv["name"]]
     rng = np.random.default_rng(8)
-    n = 1237                                                    # not a multiple of 32: ragged last row tile
     spec = _random_book(curve, n, rng)
     book = B.OISBook.from_arrays(curve, **spec, **CONVS["annual_act365"])
     rates = shocked_rate_scenarios(curve, n_scen)
     out = {}
-    for variant in ("1", "2"):
+    for variant in ("1", "2", "3"):
         monkeypatch.setenv("CAV_SCEN_EXPAND", variant)
-        monkeypatch.setenv("CAV_SCEN_UNITS", variant)             # ... and the unit sums with two scenarios per thread
+        monkeypatch.setenv("CAV_SCEN_UNITS", variant)             # ... and the unit sums (2: two scenarios per thread, 3: chains)
         out[variant] = book.scenario_values(rates).cpu().numpy()
     assert np.array_equal(out["1"], out["2"])
+    assert np.array_equal(out["1"], out["3"])
     odd = book.scenario_values(rates[: n_scen - 1]).cpu().numpy()     # odd count: always the 64x64 kernel
     assert np.array_equal(odd, out["2"][: n_scen - 1])
+
+
+@pytest.mark.parametrize("device_flatten", [True, False])
+def test_prefix_chain_unit_sums_agree_bitwise(ref_curves, monkeypatch, device_flatten):
+    """A book shaped like BASELINE config 2 / 4 (a few start dates x tenors 1..50Y): the annuity units of one start date are
+    prefixes of each other, k_scen_units_chain walks one list per chain and must give the per-unit kernels' values bit for
+    bit - for the device-built and the host-built book alike - while doing a fraction of their gathers."""
+    from adrates_b200.position import CurveSession
+    from adrates_b200.synthetic import make_array_book, shocked_rate_scenarios
+    cv = ref_curves["gbp_readme_lzr"]
+    model = build_model(cv)
+    curve = model.curves[cv["name"]]
+    book = make_array_book(curve, 6000, seed=5)
+    rates = shocked_rate_scenarios(curve, 66)
+    out = {}
+    for variant in ("2", "3"):
+        monkeypatch.setenv("CAV_SCEN_EXPAND", variant)
+        monkeypatch.setenv("CAV_SCEN_UNITS", variant)
+        sess = CurveSession.get(curve, 0)
+        book.upload(sess.ctx, tiles=False, device_flatten=device_flatten)
+        pnl = torch.empty(66, book.n_trades, dtype=torch.float64, device="cuda")
+        sess.ctx.scenarios(rates, pnl.data_ptr())
+        sess.ctx.sync()
+        out[variant] = pnl.cpu().numpy()
+        info = sess.ctx.scenarios_info()
+        assert info["chain_kernel"] == (variant == "3")
+        if variant == "3":
+            n_terms = sess.ctx.book_info()["n_terms"] if device_flatten else None
+            assert info["chains"] > 0 and info["queries"] > 0
+            if n_terms:
+                assert info["chain_terms"] * 3 <= n_terms       # at least three times fewer gathers on this book
+    assert np.array_equal(out["2"], out["3"])
+    api = book.scenario_values(rates).cpu().numpy()                 # the public call, default kernels, output in trade order
+    assert api.shape == out["3"].shape

@@ -21,7 +21,7 @@ shocked = shocked_rate_scenarios(curve, a.scen)
 pnl = torch.empty(a.scen, a.trades, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
 ref = None
-for variant in ("11", "21", "22", "11", "22"):
+for variant in ("22", "32", "23", "33", "22", "33"):
   os.environ["CAV_SCEN_EXPAND"], os.environ["CAV_SCEN_UNITS"] = variant[0], variant[1]
   for r in range(a.reps):
     t0 = time.perf_counter()
@@ -32,4 +32,5 @@ for variant in ("11", "21", "22", "11", "22"):
         chk = pnl.sum().item()
         ref = chk if ref is None else ref
         assert chk == ref
+    if r == a.reps - 1: print("  info", ctx.scenarios_info())
     print(f"expand/units variant {variant} rep {r}: {dt*1e3:.2f} ms  {a.scen*a.trades/dt/1e9:.2f} G revaluations/s  units={flat.n_units} terms={flat.n_terms}")
