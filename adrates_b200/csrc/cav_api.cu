@@ -1515,8 +1515,8 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
             chains = ctx->sch_n > 0 && ctx->sch_terms * 3 <= ctx->n_terms * 2;
         }
         if (chains) {
-            dim3 gc((unsigned)ctx->sch_n, (unsigned)((n_scen / 2 + 127) / 128));
-            k_scen_units_chain<<<gc, 128, 0, ctx->stream>>>(n_scen, ctx->sch_head, ctx->sch_count, ctx->unit_offsets, ctx->amt, ctx->sq_term,
+            dim3 gc((unsigned)((ctx->sch_n + SCH_PER_CTA - 1) / SCH_PER_CTA), (unsigned)((n_scen / 2 + 127) / 128));
+            k_scen_units_chain<<<gc, 128, 0, ctx->stream>>>(n_scen, (int)ctx->sch_n, ctx->sch_head, ctx->sch_count, ctx->unit_offsets, ctx->amt, ctx->sq_term,
                                                             ctx->sc_dfq, ctx->sc_upv);
             ctx->sch_used = 1;
         } else if (units_variant >= 2 && n_scen % 2 == 0) {    // two scenarios per thread, 16-byte gathers
@@ -1529,7 +1529,7 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
         k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
     else
         k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
-    const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 3; }();
+    const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 2; }();
     if (expand_variant == 3 && n_scen % 2 == 0 && ctx->n_trades % 2 == 0 && (reinterpret_cast<uintptr_t>(pnl_dev) & 15) == 0) {
         // bulk-store kernel: rows of the P&L matrix must start and end on 16-byte boundaries
         dim3 ge((unsigned)((ctx->n_trades + SX3_R - 1) / SX3_R), (unsigned)((n_scen + SX3_S - 1) / SX3_S));

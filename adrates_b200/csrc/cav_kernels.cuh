@@ -2052,43 +2052,47 @@ k_scen_chain_flags(int64_t n_units, const int64_t* __restrict__ unit_offsets, co
     ext[u] = e;
 }
 
+#define SCH_PER_CTA 8            // chains per CTA: half of a book's chains are two-term floating units, a CTA for each is all launch overhead
 __global__ void __launch_bounds__(128)
-k_scen_units_chain(int n_scen, const int* __restrict__ chain_head, const int* __restrict__ chain_count,
+k_scen_units_chain(int n_scen, int n_chains, const int* __restrict__ chain_head, const int* __restrict__ chain_count,
                    const int64_t* __restrict__ unit_offsets, const double* __restrict__ amt, const int* __restrict__ term_q,
                    const double* __restrict__ dfq, double* unit_pv /*[U][S]*/)
 {
     const int s = 2 * (blockIdx.y * blockDim.x + threadIdx.x);
     if (s >= n_scen) return;
-    const int u0 = chain_head[blockIdx.x], cnt = chain_count[blockIdx.x];
-    const int64_t t0 = unit_offsets[u0 + cnt - 1];
-    const int L = (int)(unit_offsets[u0 + cnt] - t0);                 // the last member's list contains every member's
     const double* base = dfq + s;
-    double2 pv = make_double2(0.0, 0.0);
-    int m = 0;                                                        // next member to complete, at prefix length next_len
-    int next_len = (int)(unit_offsets[u0 + 1] - unit_offsets[u0]);
-    while (m < cnt && next_len == 0) {                                // (no flattened book has empty units)
-        *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
-        ++m;
-        next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
-    }
-    double2 d[4];
-    double a[4];
+    const int c_end = min(n_chains, (int)(blockIdx.x + 1) * SCH_PER_CTA);
+    for (int c = blockIdx.x * SCH_PER_CTA; c < c_end; ++c) {
+        const int u0 = chain_head[c], cnt = chain_count[c];
+        const int64_t t0 = unit_offsets[u0 + cnt - 1];
+        const int L = (int)(unit_offsets[u0 + cnt] - t0);             // the last member's list contains every member's
+        double2 pv = make_double2(0.0, 0.0);
+        int m = 0;                                                    // next member to complete, at prefix length next_len
+        int next_len = (int)(unit_offsets[u0 + 1] - unit_offsets[u0]);
+        while (m < cnt && next_len == 0) {                            // (no flattened book has empty units)
+            *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
+            ++m;
+            next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
+        }
+        double2 d[4];
+        double a[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {                                     // four gathers in flight, refilled as they are consumed
-        a[j] = 0.0; d[j] = make_double2(0.0, 0.0);
-        if (j < L) { a[j] = amt[t0 + j]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + j] * n_scen); }
-    }
-    for (int i = 0; i < L; i += 4) {
+        for (int j = 0; j < 4; ++j) {                                 // four gathers in flight, refilled as they are consumed
+            a[j] = 0.0; d[j] = make_double2(0.0, 0.0);
+            if (j < L) { a[j] = amt[t0 + j]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + j] * n_scen); }
+        }
+        for (int i = 0; i < L; i += 4) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ii = i + j;
-            if (ii < L) {
-                pv.x += a[j] * d[j].x; pv.y += a[j] * d[j].y;          // summed in term order, as k_scen_units_q2 does
-                if (ii + 4 < L) { a[j] = amt[t0 + ii + 4]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + ii + 4] * n_scen); }
-                while (ii + 1 == next_len) {
-                    *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
-                    ++m;
-                    next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
+            for (int j = 0; j < 4; ++j) {
+                const int ii = i + j;
+                if (ii < L) {
+                    pv.x += a[j] * d[j].x; pv.y += a[j] * d[j].y;      // summed in term order, as k_scen_units_q2 does
+                    if (ii + 4 < L) { a[j] = amt[t0 + ii + 4]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + ii + 4] * n_scen); }
+                    while (ii + 1 == next_len) {
+                        *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
+                        ++m;
+                        next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
+                    }
                 }
             }
         }

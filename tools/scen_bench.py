@@ -3,7 +3,7 @@ import argparse, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from adrates_b200 import _native
-from adrates_b200.synthetic import make_book, flatten_book, shocked_rate_scenarios
+from adrates_b200.synthetic import make_array_book, shocked_rate_scenarios
 from bench import load_curve
 
 ap = argparse.ArgumentParser()
@@ -12,16 +12,17 @@ ap.add_argument("--trades", type=int, default=100000)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 cv, curve = load_curve()
-book = make_book(curve, a.trades, seed=7)
-flat = flatten_book(book, dedup=True)
+book = make_array_book(curve, a.trades, seed=20240430)        # the book of bench.py's config-4 extra, flattened on the device
 ctx = _native.Context(0)
 ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
-ctx.portfolio_upload(flat)
+book.upload(ctx, tiles=False)
+info = ctx.book_info()
+class flat: n_units, n_terms = info["n_units"], info["n_terms"]
 shocked = shocked_rate_scenarios(curve, a.scen)
 pnl = torch.empty(a.scen, a.trades, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
 ref = None
-for variant in ("22", "32", "23", "33", "22", "33"):
+for variant in ("22", "23", "33", "22", "23"):
   os.environ["CAV_SCEN_EXPAND"], os.environ["CAV_SCEN_UNITS"] = variant[0], variant[1]
   for r in range(a.reps):
     t0 = time.perf_counter()
