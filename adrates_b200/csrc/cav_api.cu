@@ -1445,20 +1445,33 @@ static int ensure_scen_chains(cav_ctx* ctx) {
     const int64_t U = ctx->n_units;
     ctx->sch_n = 0; ctx->sch_terms = 0;
     if (U <= 0 || U >= ((int64_t)1 << 31)) { ctx->sch_valid = true; return CAV_OK; }
-    CK(dev_alloc(ctx, &ctx->sch_ext, (size_t)U));
+    CK(dev_alloc(ctx, &ctx->sch_ext, (size_t)2 * U));
     k_scen_chain_flags<<<(unsigned)((U + 255) / 256), 256, 0, ctx->stream>>>(U, ctx->unit_offsets, ctx->amt, ctx->sq_term, ctx->sch_ext);
+    k_scen_unit_lastq<<<(unsigned)((U + 255) / 256), 256, 0, ctx->stream>>>(U, ctx->unit_offsets, ctx->sq_term, ctx->sch_ext + U);
     CK(cudaGetLastError());
-    std::vector<int> ext((size_t)U);
+    std::vector<int> ext((size_t)2 * U);
     std::vector<int64_t> off((size_t)U + 1);
-    CK(cudaMemcpyAsync(ext.data(), ctx->sch_ext, sizeof(int) * U, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ext.data(), ctx->sch_ext, sizeof(int) * 2 * U, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(off.data(), ctx->unit_offsets, sizeof(int64_t) * (U + 1), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    const int* lastq = ext.data() + U;
     std::vector<int> head, count;
     int64_t walk = 0;
     for (int64_t u = 0; u < U; ++u) {
         if (!ext[u]) { head.push_back((int)u); count.push_back(1); }
         else count.back()++;
         if (u + 1 == U || !ext[u + 1]) walk += off[u + 1] - off[u];       // last member of its chain
+    }
+    {   // Chains are processed in the order of their last DF query: the floating unit of a schedule (DF(start) - DF(end)) then
+        // runs next to the annuity chain whose walk has just pulled the same query rows into L2, instead of a whole unit
+        // block later (ncu: the DF cache was read twice from DRAM).  Stable, so equal keys keep the unit order.
+        std::vector<int> order(head.size());
+        for (size_t c = 0; c < order.size(); ++c) order[c] = (int)c;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return lastq[head[a] + count[a] - 1] < lastq[head[b] + count[b] - 1]; });
+        std::vector<int> h2(head.size()), c2(head.size());
+        for (size_t c = 0; c < order.size(); ++c) { h2[c] = head[order[c]]; c2[c] = count[order[c]]; }
+        head.swap(h2); count.swap(c2);
     }
     ctx->sch_n = (int64_t)head.size();
     ctx->sch_terms = walk;

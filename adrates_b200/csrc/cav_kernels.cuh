@@ -2052,6 +2052,16 @@ k_scen_chain_flags(int64_t n_units, const int64_t* __restrict__ unit_offsets, co
     ext[u] = e;
 }
 
+// DF query of a unit's last term (the key the chains are ordered by, see ensure_scen_chains)
+__global__ void __launch_bounds__(256)
+k_scen_unit_lastq(int64_t n_units, const int64_t* __restrict__ unit_offsets, const int* __restrict__ term_q, int* __restrict__ lastq)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const int64_t t0 = unit_offsets[u], t1 = unit_offsets[u + 1];
+    lastq[u] = t1 > t0 ? term_q[t1 - 1] : -1;
+}
+
 #define SCH_PER_CTA 8            // chains per CTA: half of a book's chains are two-term floating units, a CTA for each is all launch overhead
 __global__ void __launch_bounds__(128)
 k_scen_units_chain(int n_scen, int n_chains, const int* __restrict__ chain_head, const int* __restrict__ chain_count,

@@ -471,9 +471,11 @@ def main():
             extras["scenarios_config4"] = {
                 "scenarios_total": S, "scenarios_this_rank": hi - lo, "trades": nt, "ranks": world, "ms": ms,
                 "revaluations_per_s": S * nt / ms * 1e3, "pnl_bytes_total": S * nt * 8,
+                "kernels": ctx2.scenarios_info(),
                 "note": "BASELINE config 4: every shocked curve re-bootstrapped on the device (DFs only) + full revaluation (one "
-                        "exp per distinct DF query and scenario); scenarios sharded over the ranks, no collective; includes the "
-                        "H2D of the shocked rates; max over ranks"}
+                        "exp per distinct DF query and scenario; unit values by prefix chains: units whose term lists extend "
+                        "their predecessor's are summed in one walk); scenarios sharded over the ranks, no collective; includes "
+                        "the H2D of the shocked rates; max over ranks"}
             del pnl
             ctx2.close()
         except Exception as ex:  # noqa: BLE001
