@@ -1542,24 +1542,21 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
         k_scen_units<2><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
     else
         k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
-    const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 2; }();
-    if (expand_variant == 3 && n_scen % 2 == 0 && ctx->n_trades % 2 == 0 && (reinterpret_cast<uintptr_t>(pnl_dev) & 15) == 0) {
-        // bulk-store kernel: rows of the P&L matrix must start and end on 16-byte boundaries
-        dim3 ge((unsigned)((ctx->n_trades + SX3_R - 1) / SX3_R), (unsigned)((n_scen + SX3_S - 1) / SX3_S));
-        const size_t sm3 = (size_t)SX3_DOUBLES * sizeof(double);
-        // (per call: the attribute belongs to the function on the current device, and a call costs microseconds)
+    const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 3; }();
+    if (expand_variant >= 3 && n_scen % 2 == 0 && ctx->n_trades % 2 == 0 && (reinterpret_cast<uintptr_t>(pnl_dev) & 15) == 0) {
+        // bulk-store kernel (128 x 32 tiles, four CTAs per SM, the rest of the SM's memory left to L1): rows of the P&L matrix
+        // must start and end on 16-byte boundaries
+        dim3 ge((unsigned)((ctx->n_trades + SX4_R - 1) / SX4_R), (unsigned)((n_scen + SX4_S - 1) / SX4_S));
+        const size_t sm4 = (size_t)SX4_DOUBLES * sizeof(double);
+#define X4(KK) { CK(cudaFuncSetAttribute(k_scen_expand4<KK>, cudaFuncAttributePreferredSharedMemoryCarveout, 60));                              \
+                 k_scen_expand4<KK><<<ge, 256, sm4, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); }
         switch (ctx->n_comp) {
-            case 1: CK(cudaFuncSetAttribute(k_scen_expand3<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
-            case 2: CK(cudaFuncSetAttribute(k_scen_expand3<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
-            case 3: CK(cudaFuncSetAttribute(k_scen_expand3<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
-            default: CK(cudaFuncSetAttribute(k_scen_expand3<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3)); break;
+            case 1: X4(1) break;
+            case 2: X4(2) break;
+            case 3: X4(3) break;
+            default: X4(4) break;
         }
-        switch (ctx->n_comp) {
-            case 1: k_scen_expand3<1><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
-            case 2: k_scen_expand3<2><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
-            case 3: k_scen_expand3<3><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
-            default: k_scen_expand3<4><<<ge, 256, sm3, ctx->stream>>>(n_scen, ctx->n_trades, ctx->row_units, ctx->row_weight, ctx->sc_upv, pnl_dev); break;
-        }
+#undef X4
     } else if (expand_variant >= 2 && n_scen % 2 == 0) {       // 16-byte reads of the unit values need an even row length
         dim3 ge((unsigned)((ctx->n_trades + SX2_R - 1) / SX2_R), (unsigned)((n_scen + SX2_S - 1) / SX2_S));
         switch (ctx->n_comp) {

@@ -2109,51 +2109,71 @@ k_scen_units_chain(int n_scen, int n_chains, const int* __restrict__ chain_head,
     }
 }
 
-// Variant with bulk stores (even scenario and trade counts): a 128 x 64 (trades x scenarios) tile assembled in shared memory
-// in OUTPUT orientation (one row per scenario, trades contiguous) and written by the copy engine, one
-// cp.async.bulk.global.shared::cta of up to 1 KB per scenario row.  k_scen_expand2 spends ~29 instructions per output, more than
-// half of them on the store side (LDS + 64-bit address + predicate + STG per 8-byte output, 256-byte row segments): it is
-// issue-bound at 3 TB/s of P&L.  Here the store side costs 64 instructions per 8 192 outputs, the rows go out as 1 KB bursts
-// and the gather side is trimmed as well (weights and unit ids of two trades in three 16-byte loads, one 32 x 32 -> 64-bit
-// multiply-add per unit-row address): ~13 instructions per output in SASS.  A thread gathers a 2 x 2 block (trades r, r+1 x scenarios s, s+1): 16-byte reads of the unit values as before, and
-// two 16-byte shared-memory stores; scenario row s starts at s*128 + 2*(s>>1) doubles, which keeps the rows 16-byte aligned
-// and the quarter-warps of those stores on distinct banks.  Same sums in the same order: bit-identical to the other kernels.
-#define SX3_R 128
-#define SX3_S 64
-#define SX3_DOUBLES (SX3_S * SX3_R + SX3_S)
+// Variant with bulk stores (even scenario and trade counts; the default): a 128 x 32 (trades x scenarios) tile assembled in
+// shared memory in OUTPUT orientation (one row per scenario, trades contiguous) and written by the copy engine, one
+// cp.async.bulk.global.shared::cta of up to 1 KB per scenario row.  A half-warp owns a trade pair: a thread gathers a 2 x 2 block
+// (trades r, r+1 x scenarios s, s+1) with 16-byte reads of the unit values and leaves it with two 16-byte shared-memory
+// stores; scenario row s starts at s*128 + 2*(s>>1) doubles, which keeps the rows 16-byte aligned and the quarter-warps of those
+// stores on distinct banks.  Weights and unit ids are per trade, i.e. warp-uniform: lane j fetches those of the warp's j-th trade
+// pair once per tile and the trips broadcast them with shuffles (one dependent load level instead of two per trip); a unit-row
+// address is one 32 x 32 -> 64-bit multiply-add.  ~14 instructions per output in SASS against ~29 of k_scen_expand2.
+// What the measurements say about this kernel family (profiles/r02m_experiments.txt): the P&L matrix can be written in exactly
+// these tiles at the memset rate (7.5 TB/s, tools/pnl_store_bench.cu), so the store side is free; the gather side is bound by
+// exposed load latency and by the SM's L2 -> L1 fill (two gathered bytes per byte written, trades arrive in trade order).  Hence
+// the small tile: 33 KB of shared memory, four CTAs per SM, ~120 KB left to L1, where the unit rows of the schedules many trades
+// share (spot starts: half of a typical book) survive across the CTAs of an SM.  5 or 6 CTAs per SM (less L1) are slower, a
+// 128 x 64 tile (three CTAs, 58 KB of L1) is as slow as k_scen_expand2, a persistent double-buffered form (gather of tile i + 1
+// beside the copy engine draining tile i) is slower still: resident warps and L1 beat overlap inside a CTA.
+// Same sums in the same order as the other expansion kernels: bit-identical.
+#define SX4_R 128
+#define SX4_S 32
+#define SX4_DOUBLES (SX4_S * SX4_R + SX4_S)
 template <int K>
-__global__ void __launch_bounds__(256, 3)
-k_scen_expand3(int n_scen, int64_t n_trades, const int* __restrict__ row_units /*[N][K]*/,
+__global__ void __launch_bounds__(256, 4)
+k_scen_expand4(int n_scen, int64_t n_trades, const int* __restrict__ row_units /*[N][K]*/,
                const double* __restrict__ row_weight, const double* __restrict__ unit_pv, double* pnl)
 {
-    extern __shared__ __align__(16) double tile3[];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 scenario pairs x 8 warps
-    const int64_t rbase = (int64_t)blockIdx.x * SX3_R;
-    const int sbase = blockIdx.y * SX3_S;
-    const int s0 = sbase + 2 * tx;
-    const bool in0 = s0 < n_scen;                             // n_scen is even: a pair is inside or outside as a whole
+    extern __shared__ __align__(16) double tile4[];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int sp = tx & 15, half = tx >> 4;                   // scenario pair, trade pair of the warp's two
+    const int64_t rbase = (int64_t)blockIdx.x * SX4_R;
+    const int sbase = blockIdx.y * SX4_S;
+    const int s0 = sbase + 2 * sp;
+    const bool in0 = s0 < n_scen;                             // n_scen is even
     const int64_t left = n_trades - rbase;
-    const int nloc = left < SX3_R ? (int)left : SX3_R;        // trades of this tile: even, because n_trades is
-    double* trow = tile3 + (2 * tx) * SX3_R + 2 * tx;          // row 2tx; row 2tx + 1 starts SX3_R doubles further
-    // unit row u holds its n_scen values contiguously: one 32 x 32 -> 64-bit multiply-add per address
+    const int nloc = left < SX4_R ? (int)left : SX4_R;        // even, because n_trades is
+    double* trow = tile4 + (2 * sp) * SX4_R + 2 * sp;          // row 2sp starts at 2sp*128 + 2sp doubles; row 2sp + 1 SX4_R further
     const char* ubase = reinterpret_cast<const char*>(unit_pv + (in0 ? s0 : 0));
     const unsigned row_bytes = (unsigned)n_scen * 8u;
     const double* wp = row_weight + rbase * K;
     const int* up = row_units + rbase * K;
-#pragma unroll 2
-    for (int it = 0; it < SX3_R / 16; ++it) {
-        const int r = 2 * (ty + 8 * it);                      // trades r, r + 1 (both inside or both outside: nloc is even)
+    // trade pair of (trip it, half h) = 2 * (2 * (ty + 8 * it) + h); lane j < 8 prefetches the header of (it = j >> 1, h = j & 1)
+    double2 hw0 = make_double2(0.0, 0.0), hw1 = hw0;
+    int4 hu = make_int4(0, 0, 0, 0);
+    if constexpr (K == 2) {
+        const int j = tx & 7;
+        const int rj = 2 * (2 * (ty + 8 * (j >> 1)) + (j & 1));
+        if (rj < nloc) {
+            hw0 = __ldg(reinterpret_cast<const double2*>(wp + 2 * rj));
+            hw1 = __ldg(reinterpret_cast<const double2*>(wp + 2 * rj + 2));
+            hu = __ldg(reinterpret_cast<const int4*>(up + 2 * rj));
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < SX4_R / 32; ++it) {
+        const int r = 2 * (2 * (ty + 8 * it) + half);
         double2 va = make_double2(0.0, 0.0), vb = va;
+        double w[2 * K];
+        int u[2 * K];
+        if constexpr (K == 2) {
+            const int src = 2 * it + half;
+            w[0] = __shfl_sync(0xffffffffu, hw0.x, src); w[1] = __shfl_sync(0xffffffffu, hw0.y, src);
+            w[2] = __shfl_sync(0xffffffffu, hw1.x, src); w[3] = __shfl_sync(0xffffffffu, hw1.y, src);
+            u[0] = __shfl_sync(0xffffffffu, hu.x, src); u[1] = __shfl_sync(0xffffffffu, hu.y, src);
+            u[2] = __shfl_sync(0xffffffffu, hu.z, src); u[3] = __shfl_sync(0xffffffffu, hu.w, src);
+        }
         if (in0 && r < nloc) {
-            double w[2 * K];
-            int u[2 * K];
-            if constexpr (K == 2) {                           // weights and unit ids of both trades in three 16-byte loads
-                const double2 wa = __ldg(reinterpret_cast<const double2*>(wp + 2 * r));
-                const double2 wb = __ldg(reinterpret_cast<const double2*>(wp + 2 * r + 2));
-                const int4 uu = __ldg(reinterpret_cast<const int4*>(up + 2 * r));
-                w[0] = wa.x; w[1] = wa.y; w[2] = wb.x; w[3] = wb.y;
-                u[0] = uu.x; u[1] = uu.y; u[2] = uu.z; u[3] = uu.w;
-            } else {
+            if constexpr (K != 2) {
 #pragma unroll
                 for (int k = 0; k < 2 * K; ++k) { w[k] = __ldg(wp + r * K + k); u[k] = __ldg(up + r * K + k); }
             }
@@ -2171,21 +2191,22 @@ k_scen_expand3(int n_scen, int64_t n_trades, const int* __restrict__ row_units /
                 }
         }
         *reinterpret_cast<double2*>(trow + r) = make_double2(va.x, vb.x);
-        *reinterpret_cast<double2*>(trow + SX3_R + r) = make_double2(va.y, vb.y);
+        *reinterpret_cast<double2*>(trow + SX4_R + r) = make_double2(va.y, vb.y);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the tile, written through the generic proxy, is read by the copy engine
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (threadIdx.x < SX3_S) {
+    if (threadIdx.x < SX4_S) {
         const int c = threadIdx.x, sc = sbase + c;
         if (sc < n_scen) {
             unsigned long long pol;
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-            const double* src = tile3 + c * SX3_R + 2 * (c >> 1);
+            const double* src = tile4 + c * SX4_R + 2 * (c >> 1);
             double* dst = pnl + (size_t)sc * n_trades + rbase;
             asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
                          :: "l"(dst), "r"((unsigned)__cvta_generic_to_shared(src)), "r"((unsigned)nloc * 8u), "l"(pol) : "memory");
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the tile must outlive the copy engine's reads
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
+

@@ -73,7 +73,7 @@ def test_array_book_scenario_values_match_books_on_rebuilt_curves(ref_curves, co
 @pytest.mark.parametrize("n_scen", [2, 38, 130, 256])
 @pytest.mark.parametrize("n", [1237, 1238])
 def test_scenario_expansion_kernels_agree_bitwise(ref_curves, monkeypatch, n_scen, n):
-    """Even scenario counts take the bulk-store expansion kernel (128 x 64 tiles written by cp.async.bulk; even trade counts
+    """Even scenario counts take the bulk-store expansion kernel (128 x 32 tiles written by cp.async.bulk; even trade counts
     only) or the 32x128 kernel with 16-byte reads, odd ones (and CAV_SCEN_EXPAND=1) the 64x64 kernel: same sums in the same
     order, so the matrices are identical, ragged tile edges included (1237 / 1238 trades: neither a multiple of 32 nor of 128)."""
     from adrates_b200.synthetic import shocked_rate_scenarios

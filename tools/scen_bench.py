@@ -10,9 +10,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--scen", type=int, default=2000)
 ap.add_argument("--trades", type=int, default=100000)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--max-offset-bd", type=int, default=250, help="forward starts up to this many business days (1: ~200 units, all hot)")
+ap.add_argument("--variants", default="22,23,33,22,33")
 a = ap.parse_args()
 cv, curve = load_curve()
-book = make_array_book(curve, a.trades, seed=20240430)        # the book of bench.py's config-4 extra, flattened on the device
+book = make_array_book(curve, a.trades, seed=20240430, max_offset_bd=a.max_offset_bd)        # the book of bench.py's config-4 extra, flattened on the device
 ctx = _native.Context(0)
 ctx.curve_build(curve._interp_type.value, curve.swap_rates, curve.path_b_plan(), order=0)
 book.upload(ctx, tiles=False)
@@ -22,7 +24,7 @@ shocked = shocked_rate_scenarios(curve, a.scen)
 pnl = torch.empty(a.scen, a.trades, dtype=torch.float64, device="cuda")
 torch.cuda.synchronize()
 ref = None
-for variant in ("22", "23", "33", "22", "23"):
+for variant in a.variants.split(","):
   os.environ["CAV_SCEN_EXPAND"], os.environ["CAV_SCEN_UNITS"] = variant[0], variant[1]
   for r in range(a.reps):
     t0 = time.perf_counter()
