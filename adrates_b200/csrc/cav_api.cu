@@ -359,7 +359,7 @@ void cav_destroy(cav_ctx* ctx) {
     dev_free(ctx, &ctx->unit_offsets); dev_free(ctx, &ctx->amt); dev_free(ctx, &ctx->weight); dev_free(ctx, &ctx->node);
     dev_free(ctx, &ctx->comp_weight); dev_free(ctx, &ctx->group_offsets); dev_free(ctx, &ctx->group_units);
     dev_free(ctx, &ctx->sq_node); dev_free(ctx, &ctx->sq_w); dev_free(ctx, &ctx->sq_term); dev_free(ctx, &ctx->sc_dfq);
-    dev_free(ctx, &ctx->sch_ext); dev_free(ctx, &ctx->sch_head); dev_free(ctx, &ctx->sch_count);
+    dev_free(ctx, &ctx->sch_ext); dev_free(ctx, &ctx->sch_desc); dev_free(ctx, &ctx->sch_t0);
     dev_free(ctx, &ctx->cf_x); dev_free(ctx, &ctx->cf_d); dev_free(ctx, &ctx->cf_t); dev_free(ctx, &ctx->cf_amt);
     dev_free(ctx, &ctx->cf_pv); dev_free(ctx, &ctx->cf_off);
     dev_free(ctx, &ctx->tile_arena); dev_free(ctx, &ctx->row_masks); dev_free(ctx, &ctx->check_flag); dev_free(ctx, &ctx->xc_arena);
@@ -1475,8 +1475,15 @@ static int ensure_scen_chains(cav_ctx* ctx) {
     }
     ctx->sch_n = (int64_t)head.size();
     ctx->sch_terms = walk;
-    CK(upload(ctx, &ctx->sch_head, head.data(), head.size()));
-    CK(upload(ctx, &ctx->sch_count, count.data(), count.size()));
+    std::vector<int4> desc(head.size());
+    std::vector<int64_t> t0s(head.size());
+    for (size_t c = 0; c < head.size(); ++c) {
+        const int64_t last = (int64_t)head[c] + count[c] - 1;
+        desc[c] = make_int4(head[c], count[c], (int)(off[last + 1] - off[last]), 0);
+        t0s[c] = off[last];
+    }
+    CK(upload(ctx, &ctx->sch_desc, desc.data(), desc.size()));
+    CK(upload(ctx, &ctx->sch_t0, t0s.data(), t0s.size()));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->sch_valid = true;
     return CAV_OK;
@@ -1529,7 +1536,7 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
         }
         if (chains) {
             dim3 gc((unsigned)((ctx->sch_n + SCH_PER_CTA - 1) / SCH_PER_CTA), (unsigned)((n_scen / 2 + 127) / 128));
-            k_scen_units_chain<<<gc, 128, 0, ctx->stream>>>(n_scen, (int)ctx->sch_n, ctx->sch_head, ctx->sch_count, ctx->unit_offsets, ctx->amt, ctx->sq_term,
+            k_scen_units_chain<<<gc, 128, 0, ctx->stream>>>(n_scen, (int)ctx->sch_n, ctx->sch_desc, ctx->sch_t0, ctx->unit_offsets, ctx->amt, ctx->sq_term,
                                                             ctx->sc_dfq, ctx->sc_upv);
             ctx->sch_used = 1;
         } else if (units_variant >= 2 && n_scen % 2 == 0) {    // two scenarios per thread, 16-byte gathers

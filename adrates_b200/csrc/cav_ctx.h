@@ -147,7 +147,9 @@ struct cav_ctx {
     int64_t sq_n = 0;
     bool sq_valid = false;
     // prefix chains of units over the queries (k_scen_units_chain): runs of units whose term lists extend their predecessor's
-    int *sch_ext = nullptr, *sch_head = nullptr, *sch_count = nullptr;
+    int* sch_ext = nullptr;
+    int4* sch_desc = nullptr;            // per chain: first unit, members, terms of the last member, 0
+    int64_t* sch_t0 = nullptr;           // per chain: term offset of the last member
     int64_t sch_n = 0, sch_terms = 0;    // chains; terms the chain kernel walks (sum of the last members' lists)
     bool sch_valid = false;
     int sch_used = 0;                    // the last cav_scenarios call took the chain kernel

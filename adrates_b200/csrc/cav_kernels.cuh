@@ -2063,33 +2063,39 @@ k_scen_unit_lastq(int64_t n_units, const int64_t* __restrict__ unit_offsets, con
 }
 
 #define SCH_PER_CTA 8            // chains per CTA: half of a book's chains are two-term floating units, a CTA for each is all launch overhead
+// chain_desc[c] = (first unit, members, terms of the last member, 0), chain_t0[c] = term offset of the last member: one load
+// level instead of three (head -> unit offsets -> terms) in front of every chain's gathers, and the next chain's descriptor
+// is fetched while this one is summed - the two-term floating units are pure latency otherwise.
 __global__ void __launch_bounds__(128)
-k_scen_units_chain(int n_scen, int n_chains, const int* __restrict__ chain_head, const int* __restrict__ chain_count,
+k_scen_units_chain(int n_scen, int n_chains, const int4* __restrict__ chain_desc, const int64_t* __restrict__ chain_t0,
                    const int64_t* __restrict__ unit_offsets, const double* __restrict__ amt, const int* __restrict__ term_q,
                    const double* __restrict__ dfq, double* unit_pv /*[U][S]*/)
 {
     const int s = 2 * (blockIdx.y * blockDim.x + threadIdx.x);
     if (s >= n_scen) return;
     const double* base = dfq + s;
-    const int c_end = min(n_chains, (int)(blockIdx.x + 1) * SCH_PER_CTA);
-    for (int c = blockIdx.x * SCH_PER_CTA; c < c_end; ++c) {
-        const int u0 = chain_head[c], cnt = chain_count[c];
-        const int64_t t0 = unit_offsets[u0 + cnt - 1];
-        const int L = (int)(unit_offsets[u0 + cnt] - t0);             // the last member's list contains every member's
-        double2 pv = make_double2(0.0, 0.0);
-        int m = 0;                                                    // next member to complete, at prefix length next_len
-        int next_len = (int)(unit_offsets[u0 + 1] - unit_offsets[u0]);
-        while (m < cnt && next_len == 0) {                            // (no flattened book has empty units)
-            *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
-            ++m;
-            next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
-        }
+    const int c0 = blockIdx.x * SCH_PER_CTA;
+    const int c_end = min(n_chains, c0 + SCH_PER_CTA);
+    int4 nd = __ldg(chain_desc + c0);
+    int64_t nt0 = __ldg(chain_t0 + c0);
+    for (int c = c0; c < c_end; ++c) {
+        const int u0 = nd.x, cnt = nd.y, L = nd.z;                    // the last member's list contains every member's
+        const int64_t t0 = nt0;
+        if (c + 1 < c_end) { nd = __ldg(chain_desc + c + 1); nt0 = __ldg(chain_t0 + c + 1); }
         double2 d[4];
         double a[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                                 // four gathers in flight, refilled as they are consumed
             a[j] = 0.0; d[j] = make_double2(0.0, 0.0);
-            if (j < L) { a[j] = amt[t0 + j]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + j] * n_scen); }
+            if (j < L) { a[j] = __ldg(amt + t0 + j); d[j] = *reinterpret_cast<const double2*>(base + (size_t)__ldg(term_q + t0 + j) * n_scen); }
+        }
+        double2 pv = make_double2(0.0, 0.0);
+        int m = 0;                                                    // next member to complete, at prefix length next_len
+        int next_len = cnt == 1 ? L : (int)(unit_offsets[u0 + 1] - unit_offsets[u0]);
+        while (m < cnt && next_len == 0) {                            // (no flattened book has empty units)
+            *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
+            ++m;
+            next_len = m < cnt ? (int)(unit_offsets[u0 + m + 1] - unit_offsets[u0 + m]) : -1;
         }
         for (int i = 0; i < L; i += 4) {
 #pragma unroll
@@ -2097,7 +2103,7 @@ k_scen_units_chain(int n_scen, int n_chains, const int* __restrict__ chain_head,
                 const int ii = i + j;
                 if (ii < L) {
                     pv.x += a[j] * d[j].x; pv.y += a[j] * d[j].y;      // summed in term order, as k_scen_units_q2 does
-                    if (ii + 4 < L) { a[j] = amt[t0 + ii + 4]; d[j] = *reinterpret_cast<const double2*>(base + (size_t)term_q[t0 + ii + 4] * n_scen); }
+                    if (ii + 4 < L) { a[j] = __ldg(amt + t0 + ii + 4); d[j] = *reinterpret_cast<const double2*>(base + (size_t)__ldg(term_q + t0 + ii + 4) * n_scen); }
                     while (ii + 1 == next_len) {
                         *reinterpret_cast<double2*>(unit_pv + (size_t)(u0 + m) * n_scen + s) = pv;
                         ++m;
