@@ -147,3 +147,42 @@ def test_class_units_on_a_holiday_calendar_equal_batch_flatten(ref_curves, cal):
     assert np.array_equal(off, flat.unit_offsets) and np.array_equal(amt, flat.amt)
     assert np.array_equal(weight, flat.weight) and np.array_equal(node, flat.node)
     assert book.device_conv().cal_type == CalendarTypes[cal].value
+
+
+def test_reference_intersection_known_answers():
+    """The known answers of the reference's own tests/test_calendar_intersection.py (:60-262), as one table: joint US / UK (and
+    US / UK / TARGET) business days, holiday flags of the single calendars, the four roll conventions around 4 July and the
+    August bank holiday 2024, business-day stepping over a US holiday, constructor errors, the WEEKEND baseline."""
+    us, uk, tgt = (Calendar(CalendarTypes[n]) for n in ("UNITED_STATES", "UNITED_KINGDOM", "TARGET"))
+    joint = create_calendar_intersection(us, uk)
+    assert joint._cal_type == CalendarTypes.INTERSECTION and joint._constituent_calendars == [us, uk]
+    assert len(Calendar(CalendarTypes.INTERSECTION, [us, uk])._constituent_calendars) == 2
+    with pytest.raises(LibError, match="at least 2 calendars"):
+        create_calendar_intersection(us)
+    with pytest.raises(LibError, match="must be Calendar objects"):
+        create_calendar_intersection(us, "not a calendar")
+    # (date, US holiday, UK holiday, joint business day)
+    for dmy, h_us, h_uk, bd in [((5, 6, 2024), False, False, True), ((4, 7, 2024), True, False, False),
+                                ((26, 8, 2024), False, True, False), ((25, 12, 2024), True, True, False),
+                                ((1, 1, 2024), True, True, False), ((2, 1, 2024), False, False, True)]:
+        d = Date(*dmy)
+        assert (us.is_holiday(d), uk.is_holiday(d)) == (h_us, h_uk), dmy
+        assert joint.is_holiday(d) == (h_us or h_uk) and joint.is_business_day(d) == bd, dmy
+    assert not joint.is_business_day(Date(1, 6, 2024)) and not joint.is_business_day(Date(2, 6, 2024))     # weekend
+    july4, aug26 = Date(4, 7, 2024), Date(26, 8, 2024)
+    assert joint.adjust(july4, BusDayAdjustTypes.FOLLOWING) == Date(5, 7, 2024)
+    assert joint.adjust(july4, BusDayAdjustTypes.PRECEDING) == Date(3, 7, 2024)
+    assert joint.adjust(aug26, BusDayAdjustTypes.MODIFIED_FOLLOWING) == Date(27, 8, 2024)
+    assert joint.adjust(july4, BusDayAdjustTypes.NONE) == july4
+    triple = create_calendar_intersection(us, uk, tgt)
+    assert len(triple._constituent_calendars) == 3
+    assert triple.is_holiday(Date(1, 5, 2024)) and not triple.is_business_day(Date(1, 5, 2024))           # TARGET Labour Day
+    assert joint.add_business_days(Date(3, 7, 2024), 3) == Date(9, 7, 2024)
+    assert joint.add_business_days(Date(5, 7, 2024), -1) == Date(3, 7, 2024)
+    assert str(joint) == "INTERSECTION"
+    wk = Calendar(CalendarTypes.WEEKEND)
+    assert not wk.is_business_day(Date(1, 6, 2024)) and not wk.is_business_day(Date(2, 6, 2024)) and wk.is_business_day(Date(3, 6, 2024))
+    assert not wk.is_holiday(Date(25, 12, 2024))
+    # the array layer takes the intersection as a Calendar object
+    n = np.array([july4._n, aug26._n, Date(5, 6, 2024)._n])
+    assert np.array_equal(B.adjust(n, BusDayAdjustTypes.FOLLOWING, joint), [Date(5, 7, 2024)._n, Date(27, 8, 2024)._n, n[2]])
