@@ -1,5 +1,6 @@
-"""CASHFLOWS request of a single-curve OIS (reference engine.py:190-213, `_extract_leg_cashflows` :34-86) and its result
-containers `CashflowItem` / `Cashflows` (results.py:945-1120).
+"""CASHFLOWS request of a single-curve OIS (reference engine.py:190-213, `_extract_leg_cashflows` :34-86), of bonds
+(engine.py:648-696) and of floating-rate notes (engine.py:930-983), and its result containers `CashflowItem` / `Cashflows`
+(results.py:945-1120).
 
 The reference answers the request by valuing both legs on the NON-AD path - `SwapFixedLeg.value` / `SwapFloatLeg.value`
 (swap_fixed_leg.py:200-245, swap_float_leg.py:190-352): one `DiscountCurve.df(date, day_count)` look-up on the path-A
@@ -149,3 +150,82 @@ def ois_cashflows(derivative, curve, device: int = 0) -> Cashflows:
         items.append(CashflowItem(flt._payment_dts[i], notl, amt / notl if notl != 0 else 0.0, float(flt._year_fracs[i]),
                                   sign_f * amt, dfp, sign_f * pv, name_f))
     return Cashflows(items, derivative._currency)
+
+
+def _curve_dfs(curve, times, device: int) -> np.ndarray:
+    """Path-A discount factors of `curve` at year fractions `times`, one device call (cav_curve_df)."""
+    from .position import CurveSession
+    t = np.asarray(times, dtype=np.float64)
+    if np.any(t < 0.0):
+        raise LibError("Interpolate times must all be >= 0")
+    return CurveSession.get(curve, device).ctx.curve_df(curve._interp_type.value, curve._times, curve._dfs, t)
+
+
+def bond_cashflows(bond, curve, device: int = 0) -> Cashflows:
+    """CASHFLOWS of a bond (reference engine.py:648-696 over Bond.value, bond.py:264-365): a "Coupon" row per non-zero coupon and
+    a "Principal" row per non-zero principal repayment, discount factors `curve.df(payment date)` in the curve API's default day
+    count (ACT/ACT ISDA), relative to the value date; payments on or before it carry zero DF / PV."""
+    from .dates import DayCountTypes
+    vd = curve._value_dt
+    dts = bond._payment_dts
+    live = np.array([d > vd for d in dts])
+    t = np.concatenate([_times([vd], vd, DayCountTypes.ACT_ACT_ISDA), _times(dts, vd, DayCountTypes.ACT_ACT_ISDA)])
+    df = _curve_dfs(curve, np.where(np.concatenate([[True], live]), t, 0.0), device)
+    df0, dfp = df[0], df[1:]
+    items: List[CashflowItem] = []
+    for i, dt in enumerate(dts):
+        rel = float(dfp[i] / df0) if live[i] else 0.0
+        cpn = float(bond._coupon_payments[i])
+        prin = float(bond._principal_payments[i])
+        if abs(cpn) > 1e-10:
+            notl = bond._principal_schedule[i]
+            items.append(CashflowItem(dt, notl, cpn / notl if notl != 0 else 0.0, float(bond._year_fracs[i]), cpn, rel,
+                                      cpn * rel if live[i] else 0.0, "Coupon"))
+        if abs(prin) > 1e-10:
+            pv = prin * rel if (live[i] and prin > 0) else 0.0
+            items.append(CashflowItem(dt, prin, 1.0, 0.0, prin, rel, pv, "Principal"))
+    return Cashflows(items, bond._currency)
+
+
+def frn_cashflows(frn, discount_curve, index_curve, device: int = 0) -> Cashflows:
+    """CASHFLOWS of a floating-rate note (reference engine.py:930-983 over FRN.value, frn.py:218-330): a "Floating_Coupon" row per
+    live coupon - forward rate off the index curve (or the first fixing), plus margin, capped / floored - and a "Principal" row
+    at the last payment date; all year fractions in the note's day count, forward accruals in the index curve's."""
+    vd = discount_curve._value_dt
+    dts = frn._payment_dts
+    n = len(dts)
+    live = np.array([d > vd for d in dts])
+    # which live periods need index-curve look-ups (all but a first live period that carries a fixing)
+    first_live = int(np.argmax(live)) if live.any() else -1
+    fixed_first = frn._first_fixing_rate is not None and first_live >= 0
+    need = live.copy()
+    if fixed_first:
+        need[first_live] = False
+    ts = _times(frn._start_accrued_dts, vd, frn._dc_type)
+    te = _times(frn._end_accrued_dts, vd, frn._dc_type)
+    idx = _curve_dfs(index_curve, np.concatenate([np.where(need, ts, 0.0), np.where(need, te, 0.0)]), device)
+    tp = np.concatenate([_times([vd], vd, frn._dc_type), _times(dts, vd, frn._dc_type)])
+    dis = _curve_dfs(discount_curve, np.where(np.concatenate([[True], live]), tp, 0.0), device)
+    df0, dfp = dis[0], dis[1:]
+    idx_dc = DayCount(index_curve._dc_type)
+    items: List[CashflowItem] = []
+    face = float(frn._face_value)
+    for i, dt in enumerate(dts):
+        rate = amount = rel = 0.0
+        if live[i]:
+            if fixed_first and i == first_live:
+                fwd = frn._first_fixing_rate
+            else:
+                fwd = (idx[i] / idx[n + i] - 1.0) / idx_dc.year_frac(frn._start_accrued_dts[i], frn._end_accrued_dts[i])[0]
+            rate = fwd + frn._quoted_margin
+            if frn._cap_rate is not None:
+                rate = min(rate, frn._cap_rate)
+            if frn._floor_rate is not None:
+                rate = max(rate, frn._floor_rate)
+            amount = float(rate * frn._year_fracs[i] * frn._face_value)
+            rel = float(dfp[i] / df0)
+        if abs(amount) > 1e-10:
+            items.append(CashflowItem(dt, face, float(rate), float(frn._year_fracs[i]), amount, rel, amount * rel, "Floating_Coupon"))
+        if i == n - 1:
+            items.append(CashflowItem(dt, face, 1.0, 0.0, face, rel, face * rel, "Principal"))
+    return Cashflows(items, frn._currency)

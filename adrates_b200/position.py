@@ -90,20 +90,43 @@ class Engine:
         if dtype == InstrumentTypes.YOY_INFLATION_SWAP:      # Engine._compute_yoy_iis (engine.py:120-122, 986-1408)
             from .yoy_engine import compute_yoy
             return compute_yoy([derivative], self.model, request_list, self.device)
+        want_cf = RequestTypes.CASHFLOWS in set(request_list) and dtype in (InstrumentTypes.BOND, InstrumentTypes.FRN)
+        rest = [r for r in request_list if r != RequestTypes.CASHFLOWS] if want_cf else request_list
+        if want_cf:
+            request_mask(rest)                  # unknown request types are rejected as without CASHFLOWS
+
+        def with_cashflows(res, cf):
+            return AnalyticsResult(value=res.value, risk=res.risk, gamma=res.gamma, cashflows=cf)
+
         if dtype == InstrumentTypes.BOND:      # Engine._compute_bond (engine.py:505-640): OIS curve of the currency
-            return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
+            curve = self._curve_for(derivative)
+            res = value_positions([derivative], curve, rest, self.device) if (rest or not want_cf) else AnalyticsResult()
+            if not want_cf:
+                return res
+            from .cashflows import bond_cashflows
+            return with_cashflows(res, bond_cashflows(derivative, curve, self.device))
         if dtype == InstrumentTypes.FRN:       # Engine._compute_frn (engine.py:700-925)
             from .credit import BOND_CURVE
             if derivative._currency not in BOND_CURVE:
                 raise LibError(f"No default OIS curve for currency {derivative._currency}")
+            index_curve = self._curve_for(derivative)
+            try:
+                discount_curve = getattr(self.model.curves, BOND_CURVE[derivative._currency].name)
+            except AttributeError:
+                raise LibError(f"No curve {BOND_CURVE[derivative._currency].name} in the model")
             if BOND_CURVE[derivative._currency] != derivative._floating_index:
                 # the reference values dual-curve FRNs but has no Greeks for them (engine.py:921-924)
-                if set(request_list) - {RequestTypes.VALUE}:
+                if set(rest) - {RequestTypes.VALUE}:
                     raise LibError("Dual-curve FRN delta/gamma not yet implemented. "
                                    "Use same curve for discounting and projection.")
                 from .xccy_engine import value_frn_dual_curve
-                return value_frn_dual_curve(derivative, self.model, self.device)
-            return value_positions([derivative], self._curve_for(derivative), request_list, self.device)
+                res = value_frn_dual_curve(derivative, self.model, self.device) if (rest or not want_cf) else AnalyticsResult()
+            else:
+                res = value_positions([derivative], index_curve, rest, self.device) if (rest or not want_cf) else AnalyticsResult()
+            if not want_cf:
+                return res
+            from .cashflows import frn_cashflows
+            return with_cashflows(res, frn_cashflows(derivative, discount_curve, index_curve, self.device))
         if dtype != InstrumentTypes.OIS_SWAP:
             raise LibError(f"{dtype} not yet implemented")
         if collateral_type is not None:

@@ -66,3 +66,31 @@ def test_cashflows_request_is_rejected_where_it_is_not_offered(ref_curves):
     with pytest.raises(NotImplementedError):
         position.request_mask([RequestTypes.VALUE, RequestTypes.CASHFLOWS])
     assert position.request_mask([RequestTypes.VALUE, RequestTypes.CASHFLOWS], allow_cashflows=True) == position.request_mask([RequestTypes.VALUE])
+
+
+def test_bond_and_frn_cashflow_rows_match_the_reference_engine(host_df):
+    """Bonds (bullet, amortising, zero-coupon, seasoned, payment lag) and floating-rate notes (margins, first fixings, seasoned,
+    dual-curve) of the bond / FRN goldens: the CASHFLOWS rows of Engine._compute_bond / _compute_frn, row assembly on the host
+    with the DF test double (the GPU test runs the same goldens through cav_curve_df)."""
+    from tests.util_bonds import build_bond_model, make_bond, make_frn
+    from tests.util_cashflows import assert_credit_rows_match, credit_golden
+    from adrates_b200.credit import BOND_CURVE
+    g = credit_golden()
+    model = build_bond_model(g)
+    for rec in g["bonds"]:
+        b = make_bond(rec)
+        cf = CF.bond_cashflows(b, model.curves[b._floating_index.name])
+        assert_credit_rows_match(cf, rec, rec["face"])
+    n_err = 0
+    for rec in g["frns"]:
+        f = make_frn({**rec})
+        disc = model.curves[BOND_CURVE[f._currency].name]
+        idx = model.curves[f._floating_index.name]
+        if "error" in rec:
+            with pytest.raises(LibError) as ex:
+                CF.frn_cashflows(f, disc, idx)
+            assert str(ex.value) in rec["error"]
+            n_err += 1
+            continue
+        assert_credit_rows_match(CF.frn_cashflows(f, disc, idx), rec, rec["face"])
+    assert n_err == 1 and len(g["bonds"]) == 9 and len(g["frns"]) == 10

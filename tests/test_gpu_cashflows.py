@@ -34,3 +34,34 @@ def test_cashflows_and_holiday_calendar_trades_match_the_reference(ref_curves):
         only = pos.compute([RequestTypes.CASHFLOWS])
         assert only.value is None and only.risk is None and len(only.cashflows) == len(spec["rows"])
     assert n_cal == 4
+
+
+def test_bond_and_frn_cashflows_match_the_reference():
+    """Position(bond / FRN).compute([..., CASHFLOWS]) on the device against Engine._compute_bond / _compute_frn of the unmodified
+    reference (tests/golden/ref_cashflows_credit.json), next to VALUE where the reference offers it (dual-curve notes: VALUE only)."""
+    from adrates_b200.credit import BOND_CURVE
+    from tests.conftest import load_golden
+    from tests.util_bonds import build_bond_model, make_bond, make_frn
+    from tests.util_cashflows import assert_credit_rows_match, credit_golden
+    g = credit_golden()
+    model = build_bond_model(g)
+    values = {b["id"]: b["value"] for b in load_golden("ref_bonds.json")["bonds"]}
+    for rec in g["bonds"]:
+        res = make_bond(rec).position(model).compute([RequestTypes.VALUE, RequestTypes.CASHFLOWS])
+        assert_credit_rows_match(res.cashflows, rec, rec["face"])
+        assert abs(res.value.amount - values[rec["id"]]) <= 1e-10 * rec["face"]
+    for rec in g["frns"]:
+        f = make_frn({**rec})
+        dual = BOND_CURVE[f._currency] != f._floating_index
+        if "error" in rec:
+            with pytest.raises(LibError):
+                f.position(model).compute([RequestTypes.CASHFLOWS])
+            continue
+        res = f.position(model).compute([RequestTypes.VALUE, RequestTypes.CASHFLOWS])
+        assert_credit_rows_match(res.cashflows, rec, rec["face"])
+        assert res.value is not None
+        only = f.position(model).compute([RequestTypes.CASHFLOWS])
+        assert only.value is None and len(only.cashflows) == len(rec["rows"])
+        if dual:
+            with pytest.raises(LibError):
+                f.position(model).compute([RequestTypes.DELTA, RequestTypes.CASHFLOWS])

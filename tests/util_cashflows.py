@@ -43,3 +43,23 @@ def assert_rows_match(cf, spec, tol=1e-12):
     assert len(cf.fixed()) + len(cf.floating()) == len(cf) and len(cf.pay()) + len(cf.receive()) == len(cf)
     assert len(cf.notional_exchange()) == 0
     assert np.isclose(cf.fixed().total_pv + cf.floating().total_pv, cf.total_pv)
+
+
+def credit_golden():
+    return load_golden("ref_cashflows_credit.json")
+
+
+def assert_credit_rows_match(cf, rec, scale, tol=1e-12):
+    rows = rec["rows"]
+    assert [c.leg_type for c in cf.cashflows] == [r["leg_type"] for r in rows]
+    for got, ref in zip(cf.cashflows, rows):
+        assert [got.payment_date.d(), got.payment_date.m(), got.payment_date.y()] == ref["payment_date"]
+        assert abs(got.notional - ref["notional"]) <= tol * scale
+        assert got.accrual_period == ref["accrual_period"]
+        assert abs(got.payment_fraction - ref["payment_fraction"]) <= tol
+        assert abs(got.amount - ref["amount"]) <= tol * scale
+        assert abs(got.discount_factor - ref["discount_factor"]) <= tol
+        assert abs(got.discounted_amount - ref["discounted_amount"]) <= tol * scale
+    assert abs(cf.total_amount - rec["total_amount"]) <= 10 * tol * scale
+    assert abs(cf.total_pv - rec["total_pv"]) <= 10 * tol * scale
+    assert repr(cf) == rec["repr"]
