@@ -1550,7 +1550,8 @@ int cav_scenarios(cav_ctx* ctx, const double* shocked_rates, int n_scen, double*
     else
         k_scen_units<6><<<gu, 128, 0, ctx->stream>>>(n_scen, ctx->unit_offsets, ctx->amt, ctx->weight, ctx->node, ctx->sc_L, ctx->sc_upv);
     const int expand_variant = [] { const char* e = std::getenv("CAV_SCEN_EXPAND"); return e ? std::atoi(e) : 3; }();
-    if (expand_variant >= 3 && n_scen % 2 == 0 && ctx->n_trades % 2 == 0 && (reinterpret_cast<uintptr_t>(pnl_dev) & 15) == 0) {
+    if (expand_variant >= 3 && n_scen % 2 == 0 && ctx->n_trades % 2 == 0 && (reinterpret_cast<uintptr_t>(pnl_dev) & 15) == 0 &&
+        (n_scen + SX4_S - 1) / SX4_S <= 65535) {
         // bulk-store kernel (128 x 32 tiles, four CTAs per SM, the rest of the SM's memory left to L1): rows of the P&L matrix
         // must start and end on 16-byte boundaries
         dim3 ge((unsigned)((ctx->n_trades + SX4_R - 1) / SX4_R), (unsigned)((n_scen + SX4_S - 1) / SX4_S));
