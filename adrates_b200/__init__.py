@@ -6,8 +6,9 @@ Device side: hand-written sm_100a CUDA kernels behind the C ABI in include/adrat
 (adrates_b200/csrc), loaded with ctypes.  There is no CPU fallback for valuation.
 """
 from .error import LibError
-from .dates import (Date, Calendar, CalendarTypes, create_calendar_intersection, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
-                    DayCountTypes, FrequencyTypes, Schedule, to_tenor, times_from_dates)
+from .dates import (Date, DateFormatTypes, set_date_format, Calendar, CalendarTypes, create_calendar_intersection,
+                    BusDayAdjustTypes, DateGenRuleTypes, DayCount, DayCountTypes, FrequencyTypes, Schedule, to_tenor,
+                    times_from_dates)
 from .global_types import (SwapTypes, InstrumentTypes, RequestTypes, InterpTypes, CurveTypes,
                            CurrencyTypes, CollateralType)
 
@@ -26,7 +27,7 @@ __all__ = [
     "OIS", "SwapFixedLeg", "SwapFloatLeg", "XccyBasisSwap", "XccyCurve", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
     "Valuation", "Delta", "Gamma", "CrossGamma", "Risk", "AnalyticsResult", "CashflowItem", "Cashflows", "InflationIndex", "InflationCurve", "InflationIndexTypes",
     "InflationInterpTypes", "SwapInflationLeg", "ZeroCouponInflationSwap", "SwapYoYInflationLeg", "YoYInflationSwap", "Bond", "FRN",
-    "LibError", "Date", "Calendar", "CalendarTypes", "create_calendar_intersection", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
+    "LibError", "Date", "DateFormatTypes", "set_date_format", "Calendar", "CalendarTypes", "create_calendar_intersection", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",
     "DayCountTypes", "FrequencyTypes", "Schedule", "to_tenor", "times_from_dates", "SwapTypes",
     "InstrumentTypes", "RequestTypes", "InterpTypes", "CurveTypes", "CurrencyTypes", "CollateralType",
 ]

@@ -1,6 +1,6 @@
 """CASHFLOWS request of a single-curve OIS (reference engine.py:190-213, `_extract_leg_cashflows` :34-86), of bonds
-(engine.py:648-696) and of floating-rate notes (engine.py:930-983), and its result containers `CashflowItem` / `Cashflows`
-(results.py:945-1120).
+(engine.py:648-696), of floating-rate notes (engine.py:930-983) and of year-on-year inflation swaps (engine.py:1355-1406), and
+its result containers `CashflowItem` / `Cashflows` (results.py:945-1120).
 
 The reference answers the request by valuing both legs on the NON-AD path - `SwapFixedLeg.value` / `SwapFloatLeg.value`
 (swap_fixed_leg.py:200-245, swap_float_leg.py:190-352): one `DiscountCurve.df(date, day_count)` look-up on the path-A
@@ -229,3 +229,42 @@ def frn_cashflows(frn, discount_curve, index_curve, device: int = 0) -> Cashflow
         if i == n - 1:
             items.append(CashflowItem(dt, face, 1.0, 0.0, face, rel, face * rel, "Principal"))
     return Cashflows(items, frn._currency)
+
+
+def yoy_cashflows(swap, discount_curve, inflation_curve, device: int = 0) -> Cashflows:
+    """CASHFLOWS of a year-on-year inflation swap as the reference answers it (engine.py:1355-1406): the non-AD
+    `YoYInflationSwap.value` first (yoy_inflation_swap.py:224-260: fixed leg on the path-A nodes, then the inflation leg, whose
+    CPI look-ups raise for reference dates before the value date without a fixing - every sub-annual or seasoned swap,
+    swap_yoy_inflation_leg.py:267-366), then the rows of the FIXED leg only: the reference reads the inflation leg's rows off
+    `_payment_pvs`, an attribute that leg never has (it keeps `_pvs`), so its loop at engine.py:1371-1402 never runs.  The
+    rows pinned by the unmodified reference are tests/golden/ref_cashflows_yoy.json."""
+    fixed, leg = swap._fixed_leg, swap._inflation_leg
+    vd = discount_curve._value_dt
+    dts = fixed._payment_dts
+    live = np.array([d > vd for d in dts])
+    t = np.concatenate([_times([vd], vd, fixed._dc_type), _times(dts, vd, fixed._dc_type)])
+    df = _curve_dfs(discount_curve, np.where(np.concatenate([[True], live]), t, 0.0), device)
+    # the inflation leg's valuation: nothing of it reaches the rows, its errors do
+    index = leg._inflation_index
+    if inflation_curve is not None:
+        index.set_inflation_curve(inflation_curve)
+    for i, dt in enumerate(leg._payment_dts):
+        if dt <= vd:
+            continue
+        start_cpi = index.get_index(leg._yoy_start_dts[i], apply_lag=True)
+        index.get_index(leg._yoy_end_dts[i], apply_lag=True)
+        if start_cpi <= 0.0:
+            raise LibError(f"Start CPI must be positive, got {start_cpi}")
+    sign = -1.0 if fixed._leg_type == SwapTypes.PAY else 1.0
+    name = "Fixed_Pay" if fixed._leg_type == SwapTypes.PAY else "Fixed_Rec"
+    notl = float(fixed._notional)
+    items: List[CashflowItem] = []
+    for i, dt in enumerate(dts):
+        amt = float(fixed._payments[i])
+        rel = float(df[1 + i] / df[0]) if live[i] else 0.0
+        pv = amt * rel if live[i] else 0.0
+        if i == len(dts) - 1 and live[i]:
+            pv += fixed._principal * rel * fixed._notional
+        items.append(CashflowItem(dt, notl, amt / notl if notl != 0 else 0.0, float(fixed._year_fracs[i]), sign * amt, rel,
+                                  sign * pv, name))
+    return Cashflows(items, index._currency)

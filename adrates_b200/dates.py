@@ -25,6 +25,28 @@ _MONTH_NAMES = ("JAN", "FEB", "MAR", "APR", "MAY", "JUN", "JUL", "AUG", "SEP", "
 _DAY_NAMES = ("MON", "TUE", "WED", "THU", "FRI", "SAT", "SUN")
 
 
+class DateFormatTypes(Enum):
+    """How `repr(Date)` / `str(Date)` print (reference date.py:46-66); the reference's default is UK_LONG."""
+    BLOOMBERG = 1
+    US_SHORT = 2
+    US_MEDIUM = 3
+    US_LONG = 4
+    US_LONGEST = 5
+    UK_SHORT = 6
+    UK_MEDIUM = 7
+    UK_LONG = 8
+    UK_LONGEST = 9
+    DATETIME = 10
+
+
+_date_format = DateFormatTypes.UK_LONG
+
+
+def set_date_format(format_type) -> None:
+    global _date_format
+    _date_format = format_type
+
+
 def is_leap_year(y: int) -> bool:
     return (y % 4 == 0 and y % 100 != 0) or (y % 400 == 0)
 
@@ -172,7 +194,31 @@ class Date:
         return dt
 
     def __repr__(self):
-        return f"{_DAY_NAMES[self.weekday()]} {self._d:02d} {_MONTH_NAMES[self._m - 1]} {self._y}"
+        """The date in the format chosen by set_date_format (reference date.py:908-1008); dates carry no time of day here, so
+        DATETIME prints midnight."""
+        day, mon, name, year = f"{self._d:02d}", f"{self._m:02d}", _MONTH_NAMES[self._m - 1], str(self._y)
+        f = _date_format
+        if f == DateFormatTypes.UK_LONGEST:
+            return f"{_DAY_NAMES[self.weekday()]} {day} {name} {year}"
+        if f == DateFormatTypes.UK_LONG:
+            return f"{day}-{name}-{year}"
+        if f == DateFormatTypes.UK_MEDIUM:
+            return f"{day}/{mon}/{year}"
+        if f == DateFormatTypes.UK_SHORT:
+            return f"{day}/{mon}/{year[2:]}"
+        if f == DateFormatTypes.US_LONGEST:
+            return f"{_DAY_NAMES[self.weekday()]} {name} {day} {year}"
+        if f == DateFormatTypes.US_LONG:
+            return f"{name}-{day}-{year}"
+        if f == DateFormatTypes.US_MEDIUM:
+            return f"{mon}-{day}-{year}"
+        if f == DateFormatTypes.US_SHORT:
+            return f"{mon}-{day}-{year[2:]}"
+        if f == DateFormatTypes.BLOOMBERG:
+            return f"{mon}/{day}/{year[2:]}"
+        if f == DateFormatTypes.DATETIME:
+            return f"{day}/{mon}/{year} 00:00:00"
+        raise LibError("Unknown date format")
 
     def str(self):
         return f"{self._d:02d}{_MONTH_NAMES[self._m - 1]}{self._y}"

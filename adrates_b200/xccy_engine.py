@@ -317,7 +317,11 @@ def compute_ois_xccy_collateral(derivative, model, request_list, collateral_ccy,
             Delta(np.array(agg_o[1:1 + xs.n_for]), to_tenor(ois.swap_times), collateral_ccy, derivative._floating_index),
             Delta(np.array(agg_b[1:1 + xs.n_basis]), to_tenor(xc.swap_times), collateral_ccy, CurveTypes.USD_GBP_BASIS),
         ])
-    return AnalyticsResult(value=value, risk=delta, gamma=None)
+    cashflows = None
+    if RequestTypes.CASHFLOWS in reqs:          # the reference's placeholder: an empty table (engine.py:497-501)
+        from .cashflows import Cashflows
+        cashflows = Cashflows([], derivative._currency)
+    return AnalyticsResult(value=value, risk=delta, gamma=None, cashflows=cashflows)
 
 
 # ======================================================================================

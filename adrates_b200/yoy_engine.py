@@ -110,8 +110,9 @@ def compute_yoy(derivatives, model, request_list, device=0) -> AnalyticsResult:
     """One or many YoY inflation swaps of one (currency, index): summed AnalyticsResult (Portfolio semantics)."""
     from .position import CurveSession
     reqs = set(request_list)
-    if RequestTypes.CASHFLOWS in reqs:
-        raise NotImplementedError("CASHFLOWS reports use the non-AD path-A legs and are outside the CUDA path")
+    want_cf = RequestTypes.CASHFLOWS in reqs
+    if want_cf and len(derivatives) != 1:
+        raise NotImplementedError("CASHFLOWS reports are per position (Position.compute), not per portfolio")
     d0 = derivatives[0]
     currency = d0._inflation_index._currency
     index_name = d0._inflation_index._index_type.name
@@ -133,8 +134,12 @@ def compute_yoy(derivatives, model, request_list, device=0) -> AnalyticsResult:
     vd = model.value_dt
     want_v, want_d, want_g = (r in reqs for r in (RequestTypes.VALUE, RequestTypes.DELTA, RequestTypes.GAMMA))
     mask = (_native.REQ_VALUE if want_v else 0) | (_native.REQ_DELTA if want_d else 0) | (_native.REQ_GAMMA if want_g else 0)
+    cashflows = None
+    if want_cf:          # engine.py:1355-1406: the non-AD valuation (its errors included) and the fixed leg's rows
+        from .cashflows import yoy_cashflows
+        cashflows = yoy_cashflows(d0, disc, infl, device)
     if mask == 0:
-        return AnalyticsResult()
+        return AnalyticsResult(cashflows=cashflows)
     dsess = CurveSession.get(disc, device)
     isess = InflationSession.get(infl, device)
     # ---- discount side: fixed cashflows on the OIS engine grid (inflation factors frozen)
@@ -160,7 +165,7 @@ def compute_yoy(derivatives, model, request_list, device=0) -> AnalyticsResult:
         if want_g:
             gamma = Risk([Gamma(np.array(agg_d[33:].reshape(32, 32)[:Rd, :Rd]), t_d, currency, disc_type),
                           Gamma(np.array(agg_i[33:].reshape(32, 32)[:Ri, :Ri]), t_i, currency, infl_type)])
-    return AnalyticsResult(value=value, risk=delta, gamma=gamma)
+    return AnalyticsResult(value=value, risk=delta, gamma=gamma, cashflows=cashflows)
 
 
 def _has(model, name) -> bool:

@@ -94,3 +94,44 @@ def test_bond_and_frn_cashflow_rows_match_the_reference_engine(host_df):
             continue
         assert_credit_rows_match(CF.frn_cashflows(f, disc, idx), rec, rec["face"])
     assert n_err == 1 and len(g["bonds"]) == 9 and len(g["frns"]) == 10
+
+
+def test_yoy_cashflow_rows_match_the_reference_engine(host_df):
+    """Year-on-year inflation swaps (engine.py:1355-1406): the reference values the swap on the non-AD path - sub-annual and
+    seasoned swaps raise from the CPI look-up before the value date - and then reports the FIXED leg's rows only (its inflation
+    leg loop is guarded by an attribute that leg never has).  14 cases run by the unmodified reference
+    (tests/golden/gen/make_golden_cashflows_yoy.py), both index conventions."""
+    from adrates_b200 import RequestTypes
+    from adrates_b200.yoy_engine import compute_yoy
+    from tests.conftest import load_golden
+    from tests.util_cashflows import assert_rows_match
+    from tests.util_yoy import make_model, make_swap
+    g = load_golden("ref_yoy.json")
+    cf_g = {c["id"]: c for c in load_golden("ref_cashflows_yoy.json")["cases"]}
+    n_err = n_ok = 0
+    for name in g["inflation_curves"]:
+        model, idx, ic = make_model(g, name)
+        disc = model.curves.GBP_OIS_SONIA
+        for c in (c for c in g["cases"] if c["index"] == name):
+            ref = cf_g[c["id"]]["cf_only"]
+            assert ("error" in ref) == ("error" in cf_g[c["id"]]["value_cf"])
+            swap = make_swap(c, idx)
+            if "error" in ref:
+                with pytest.raises(LibError) as ex:
+                    CF.yoy_cashflows(swap, disc, ic)
+                assert "LibError: " + str(ex.value) == ref["error"]
+                with pytest.raises(LibError):
+                    compute_yoy([swap], model, [RequestTypes.CASHFLOWS])
+                n_err += 1
+                continue
+            cf = CF.yoy_cashflows(swap, disc, ic)
+            assert {r["leg_type"] for r in ref["rows"]} == {"Fixed_Pay" if c["fixed_leg"] == "PAY" else "Fixed_Rec"}
+            assert_rows_match(cf, dict(ref, notional=c["notional"]))
+            assert repr(cf) == ref["repr"] and cf.validate()
+            res = compute_yoy([swap], model, [RequestTypes.CASHFLOWS])       # nothing but the table: no device work besides DFs
+            assert res.value is None and res.risk is None and res.gamma is None
+            assert_rows_match(res.cashflows, dict(ref, notional=c["notional"]))
+            n_ok += 1
+    assert n_err == 8 and n_ok == 6
+    with pytest.raises(NotImplementedError):
+        compute_yoy([swap, swap], model, [RequestTypes.CASHFLOWS])

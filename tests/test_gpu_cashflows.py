@@ -65,3 +65,41 @@ def test_bond_and_frn_cashflows_match_the_reference():
         if dual:
             with pytest.raises(LibError):
                 f.position(model).compute([RequestTypes.DELTA, RequestTypes.CASHFLOWS])
+
+
+def test_yoy_and_collateral_cashflows_match_the_reference():
+    """Position(yoy).compute([VALUE, CASHFLOWS]) on the device against Engine._compute_yoy_iis of the unmodified reference
+    (tests/golden/ref_cashflows_yoy.json: the fixed leg's rows, or the CPI look-up error of sub-annual / seasoned swaps), and the
+    empty table the reference returns for an OIS with cross-currency collateral (engine.py:497-501)."""
+    from adrates_b200.position import Position
+    from tests.conftest import load_golden
+    from tests.util_yoy import make_model, make_swap
+    g = load_golden("ref_yoy.json")
+    cf_g = {c["id"]: c for c in load_golden("ref_cashflows_yoy.json")["cases"]}
+    n_ok = 0
+    for name in g["inflation_curves"]:
+        model, idx, ic = make_model(g, name)
+        for c in (c for c in g["cases"] if c["index"] == name):
+            ref = cf_g[c["id"]]["value_cf"]
+            pos = Position(make_swap(c, idx), model)
+            if "error" in ref:
+                with pytest.raises(LibError) as ex:
+                    pos.compute([RequestTypes.VALUE, RequestTypes.CASHFLOWS])
+                assert "LibError: " + str(ex.value) == ref["error"]
+                continue
+            res = pos.compute([RequestTypes.VALUE, RequestTypes.CASHFLOWS])
+            assert abs(res.value.amount - ref["value"]) <= 1e-10 * c["notional"]
+            assert res.risk is None and res.gamma is None
+            assert_rows_match(res.cashflows, dict(ref, notional=c["notional"]))
+            n_ok += 1
+    assert n_ok == 6
+    from adrates_b200 import CollateralType
+    from tests.util_trades import make_trade
+    from tests.util_xccy import build_xccy_model
+    cmodel = build_xccy_model(load_golden("ref_xccy.json"), xccy_name="GBP_USD_XCCY")
+    t = load_golden("ref_collateral.json")["trades"][0]
+    sw = make_trade(dict(t, payment_lag=0), {"name": "GBP_OIS_SONIA", "dc": "ACT_365F"})
+    res = sw.position(cmodel).compute([RequestTypes.VALUE, RequestTypes.CASHFLOWS], collateral_type=CollateralType.USD)
+    assert len(res.cashflows) == 0 and res.cashflows.currency.name == "GBP" and res.cashflows.total_pv == 0
+    assert abs(res.value.amount - t["value"]) <= 1e-10 * max(abs(t["value"]), t["notional"])
+    assert sw.position(cmodel).compute([RequestTypes.VALUE], collateral_type=CollateralType.USD).cashflows is None
