@@ -8,13 +8,14 @@ An FRN (cavour/trades/credit/frn.py:80-220, Engine._compute_frn engine.py:700-92
 on the same curve: coupons (forward + quoted margin) x accrual x face, an optional known first fixing, the face value
 at maturity; caps and floors are ignored by the engine (and here).  Like the reference, DELTA / GAMMA exist only when
 the index curve is the discount curve of the currency.
-Yield, spread, discount-margin and duration analytics of the reference's classes (bond.py:264-875, frn.py:222-640)
-are path-A host code outside this path and are not mirrored.
+The stand-alone price / yield / spread / duration methods of the reference's classes (bond.py:264-875, frn.py:222-573) are
+non-AD host code; they are mirrored in credit_analytics.py and mixed in here.
 """
 from __future__ import annotations
 
 from .dates import (BusDayAdjustTypes, Calendar, CalendarTypes, Date, DateGenRuleTypes, DayCount, DayCountTypes,
                     FrequencyTypes, Schedule)
+from .credit_analytics import BondAnalytics, FRNAnalytics
 from .error import LibError
 from .global_types import CurrencyTypes, CurveTypes, InstrumentTypes
 
@@ -23,7 +24,7 @@ BOND_CURVE = {CurrencyTypes.GBP: CurveTypes.GBP_OIS_SONIA, CurrencyTypes.USD: Cu
               CurrencyTypes.EUR: CurveTypes.EUR_OIS_ESTR}
 
 
-class Bond:
+class Bond(BondAnalytics):
     def __init__(self, issue_dt: Date, maturity_dt_or_tenor, coupon: float, freq_type: FrequencyTypes,
                  dc_type: DayCountTypes, currency: CurrencyTypes, face_value: float = 100.0, payment_lag: int = 0,
                  amortization_schedule=None, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
@@ -99,7 +100,7 @@ class Bond:
         return Position(self, model)
 
 
-class FRN:
+class FRN(FRNAnalytics):
     def __init__(self, issue_dt: Date, maturity_dt_or_tenor, quoted_margin: float, freq_type: FrequencyTypes,
                  dc_type: DayCountTypes, currency: CurrencyTypes, floating_index: CurveTypes, face_value: float = 100.0,
                  payment_lag: int = 0, cap_rate=None, floor_rate=None, first_fixing_rate=None,

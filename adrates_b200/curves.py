@@ -20,12 +20,11 @@ generic (ln DF = wa*L[a] + wb*L[b]).
 """
 from __future__ import annotations
 
-import math
 from dataclasses import dataclass
 
 import numpy as np
 
-from .dates import Date, DayCount, DayCountTypes, times_from_dates
+from .dates import Date, DayCount, DayCountTypes, FrequencyTypes, times_from_dates
 from .error import LibError
 from .global_types import InterpTypes
 
@@ -142,6 +141,9 @@ def plan_queries(t, node_time: np.ndarray, interp_type: InterpTypes):
 # ======================================================================================
 # curve objects (path A + API surface)
 # ======================================================================================
+_NODE_SCHEMES = (InterpTypes.LINEAR_ZERO_RATES, InterpTypes.FLAT_FWD_RATES, InterpTypes.LINEAR_FWD_RATES)
+
+
 class DiscountCurve:
     """Base curve: `df(date, day_count)` and `df_ad(t)` on the path-A nodes
     (cavour/market/curves/discount_curve.py:300-436)."""
@@ -174,6 +176,9 @@ class DiscountCurve:
         self._value_dt = value_dt
         self._dfs = np.array(dfs)
         self._interp_type = interp_type
+        self._df_dts = df_dts
+        self._freq_type = FrequencyTypes.CONTINUOUS
+        self._dc_type = DayCountTypes.ACT_ACT_ISDA
 
     def df(self, dt, day_count=DayCountTypes.ACT_ACT_ISDA):
         times = times_from_dates(dt, self._value_dt, day_count)
@@ -183,39 +188,22 @@ class DiscountCurve:
             return np.array([self._node_df(float(u)) for u in times])
         if times < 0.0:
             raise LibError("Interpolate times must all be >= 0")
+        if self._interp_type not in _NODE_SCHEMES and abs(times) >= 1e-12:
+            return np.array([self._node_df(float(times))])     # the spline schemes answer a single date with a 1-vector
         return self._node_df(float(times))
 
     def _node_df(self, t: float) -> float:
-        """Scalar path-A interpolation (cavour/market/curves/interpolator.py:69-170):
-        exact hit on node 0, first segment flat in zero rate for LINEAR_ZERO_RATES,
-        true flat-forward extrapolation for FLAT_FWD_RATES."""
-        x, d = self._times, self._dfs
-        n = x.shape[0]
-        if t == x[0]:
-            return float(d[0])
-        ge = x >= t                                   # first node with x[i] >= t, scanning from the front like the
-        i = int(np.argmax(ge)) if ge.any() else n - 1 # reference (its OIS curves have duplicate times off by an ulp)
-        if t > x[i]:
-            i = n
-        if self._interp_type == InterpTypes.LINEAR_ZERO_RATES:
-            if i == 1:
-                z1 = z2 = -math.log(d[1]) / x[1]
-                lo, hi = 0, 1
-            elif i < n:
-                z1 = -math.log(d[i - 1]) / x[i - 1]
-                z2 = -math.log(d[i]) / x[i]
-                lo, hi = i - 1, i
-            else:
-                z1 = z2 = -math.log(d[n - 1]) / x[n - 1]
-                lo, hi = n - 2, n - 1
-            z = ((x[hi] - t) * z1 + (t - x[lo]) * z2) / (x[hi] - x[lo])
-            return math.exp(-z * t)
-        if self._interp_type == InterpTypes.FLAT_FWD_RATES:
-            lo, hi = (i - 1, i) if i < n else (n - 2, n - 1)
-            y1, y2 = -math.log(d[lo]), -math.log(d[hi])
-            y = ((x[hi] - t) * y1 + (t - x[lo]) * y2) / (x[hi] - x[lo])
-            return math.exp(-y)
-        raise LibError("Invalid interpolation scheme.")
+        """Scalar look-up on the path-A nodes in the curve's own scheme (discount_curve.py:417-436 over
+        interpolator.py:69-170 / the fitted splines): exact hit on node 0, first segment flat in zero rate for
+        LINEAR_ZERO_RATES, true flat-forward extrapolation for FLAT_FWD_RATES."""
+        from .interpolator import Interpolator, node_df
+        if self._interp_type in _NODE_SCHEMES:
+            return float(node_df(t, self._times, self._dfs, self._interp_type.value))
+        fitted = getattr(self, "_interpolator", None)
+        if fitted is None or fitted._times is not self._times:          # spline schemes: fitted once per node set
+            fitted = self._interpolator = Interpolator(self._interp_type)
+            fitted.fit(self._times, self._dfs)
+        return float(np.asarray(fitted.interpolate(float(t))).reshape(-1)[0])
 
     def df_ad(self, t, day_count=DayCountTypes.ACT_ACT_ISDA):
         """DF at time(s) t in years: linear interpolation of piecewise forward rates on the

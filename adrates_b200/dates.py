@@ -84,22 +84,64 @@ class Date:
     """Calendar date; `dt2 - dt1` is the day difference (reference date.py:421-425)."""
 
     MON, TUE, WED, THU, FRI, SAT, SUN = range(7)
-    __slots__ = ("_d", "_m", "_y", "_n")
+    __slots__ = ("_d", "_m", "_y", "_n", "_hh", "_mm", "_ss", "_t")
 
-    def __init__(self, d: int, m: int, y: int):
+    def __init__(self, d: int, m: int, y: int, hh: int = 0, mm: int = 0, ss: int = 0):
+        """Day, month, four-digit year from 1900 on, optionally a time of day (reference date.py:248-326).  `_n` is the
+        integer day serial all date arithmetic runs on; `_t` adds the time of day for ordering and differences."""
+        if 1900 <= d < 2100 and 0 < y <= 31:
+            raise LibError("Date arguments must now be in the order Date(dd, mm, yyyy)")
+        if y < 1900:
+            raise LibError("Year cannot be before 1900")
         if not (1 <= m <= 12) or d < 1 or d > days_in_month(m, y):
             raise LibError(f"Date: invalid day/month/year {d}/{m}/{y}")
+        if hh < 0 or hh > 23:
+            raise LibError("Hours must be in range 0-23")
+        if mm < 0 or mm > 59:
+            raise LibError("Minutes must be in range 0-59")
+        if ss < 0 or ss > 59:
+            raise LibError("Seconds must be in range 0-59")
         self._d, self._m, self._y = int(d), int(m), int(y)
+        self._hh, self._mm, self._ss = hh, mm, ss
         self._n = _ordinal(self._d, self._m, self._y)
+        self._t = self._n if not (hh or mm or ss) else self._n + (hh / 24.0 + mm / 24.0 / 60.0 + ss / 24.0 / 60.0 / 60.0)
 
     @classmethod
     def _of(cls, n: int) -> "Date":
         return cls(*_from_ordinal(n))
 
+    @classmethod
+    def from_string(cls, date_string: str, format_string: str) -> "Date":
+        """Date.from_string("15-06-2023", "%d-%m-%Y") (reference date.py:353-360)"""
+        import datetime
+        t = datetime.datetime.strptime(date_string, format_string)
+        return cls(t.day, t.month, t.year)
+
+    @classmethod
+    def from_date(cls, date) -> "Date":
+        """From a datetime.date or a numpy datetime64 (reference date.py:362-380)"""
+        import datetime
+        import numpy as np
+        if isinstance(date, np.datetime64):
+            date = date.astype("datetime64[D]").astype(datetime.date)
+        if isinstance(date, datetime.date):
+            return cls(date.day, date.month, date.year)
+        raise LibError("from_date needs a datetime.date or a numpy datetime64")
+
+    def datetime(self):
+        import datetime
+        return datetime.date(self._y, self._m, self._d)
+
     def d(self): return self._d
     def m(self): return self._m
     def y(self): return self._y
     def serial(self) -> int: return self._n
+
+    def excel_dt(self) -> float:
+        """Days since the turn of 1900 in the spreadsheet convention the reference counts in (1 January 1900 is day 1 and the
+        year 1900 is given a 29 February), plus the time of day as a fraction (reference date.py:343-345, 382-392)."""
+        base = 693899 if self._n >= _ordinal(1, 3, 1900) else 693900
+        return float(self._n - base) + (self._t - self._n)
 
     def weekday(self) -> int:
         # 0000-03-01 is a Wednesday in the proleptic Gregorian calendar
@@ -114,14 +156,22 @@ class Date:
     def is_eom(self) -> bool:
         return self._d == days_in_month(self._m, self._y)
 
-    def __gt__(self, o): return self._n > o._n
-    def __lt__(self, o): return self._n < o._n
-    def __ge__(self, o): return self._n >= o._n
-    def __le__(self, o): return self._n <= o._n
-    def __eq__(self, o): return isinstance(o, Date) and self._n == o._n
+    def __gt__(self, o): return self._t > o._t
+    def __lt__(self, o): return self._t < o._t
+    def __ge__(self, o): return self._t >= o._t
+    def __le__(self, o): return self._t <= o._t
+    def __eq__(self, o): return isinstance(o, Date) and self._t == o._t
     def __ne__(self, o): return not self.__eq__(o)
-    def __hash__(self): return hash(self._n)
-    def __sub__(self, o): return self._n - o._n
+    def __hash__(self): return hash(self._t)
+    def __sub__(self, o): return self._t - o._t
+
+    def add_hours(self, hours) -> "Date":
+        """The date `hours` later, minutes and seconds kept (reference date.py:487-503)."""
+        if hours < 0:
+            raise LibError("Number of hours must be positive")
+        total = self._hh + hours
+        day = self.add_days(int(total / 24))
+        return Date(day._d, day._m, day._y, total % 24, self._mm, self._ss)
 
     def add_days(self, num_days: int = 1) -> "Date":
         return Date._of(self._n + int(num_days))
@@ -194,8 +244,7 @@ class Date:
         return dt
 
     def __repr__(self):
-        """The date in the format chosen by set_date_format (reference date.py:908-1008); dates carry no time of day here, so
-        DATETIME prints midnight."""
+        """The date in the format chosen by set_date_format (reference date.py:908-1008)."""
         day, mon, name, year = f"{self._d:02d}", f"{self._m:02d}", _MONTH_NAMES[self._m - 1], str(self._y)
         f = _date_format
         if f == DateFormatTypes.UK_LONGEST:
@@ -217,7 +266,7 @@ class Date:
         if f == DateFormatTypes.BLOOMBERG:
             return f"{mon}/{day}/{year[2:]}"
         if f == DateFormatTypes.DATETIME:
-            return f"{day}/{mon}/{year} 00:00:00"
+            return f"{day}/{mon}/{year} {self._hh:02d}:{self._mm:02d}:{self._ss:02d}"
         raise LibError("Unknown date format")
 
     def str(self):
@@ -226,6 +275,19 @@ class Date:
 
 def datediff(d1: Date, d2: Date) -> int:
     return d2 - d1
+
+
+def date_range(start_dt: Date, end_dt: Date, tenor: str = "1D") -> list:
+    """Dates from start_dt to end_dt, both included, `tenor` apart (reference date.py:1075-1093); the end date closes the list
+    even when the stride steps over it."""
+    if start_dt > end_dt:
+        return []
+    out, dt = [], start_dt
+    while dt < end_dt:
+        out.append(dt)
+        dt = dt.add_tenor(tenor)
+    out.append(end_dt)
+    return out
 
 
 # --------------------------------------------------------------------------------------
@@ -419,6 +481,14 @@ class DayCountTypes(Enum):
 
 def _last_day_of_feb(dt: Date) -> bool:
     return dt._m == 2 and dt._d == days_in_month(2, dt._y)
+
+
+def is_last_day_of_feb(dt: Date):
+    """The reference's public helper (day_count.py:64-74): True on the last day of February, False outside February - and
+    None on the other February days (its `if` falls through there)."""
+    if dt._m != 2:
+        return False
+    return True if _last_day_of_feb(dt) else None
 
 
 class DayCount:

@@ -265,9 +265,30 @@ class XccyBasisSwap:
         from .position import Position
         return Position(self, model)
 
-    def value(self, value_dt: Date, domestic_curve, foreign_curve, xccy_curve, spot_fx: float):
-        """Path-A PV in domestic currency: domestic leg on its own curve, foreign leg projected on the foreign
-        OIS curve and discounted on the XCCY curve, converted at spot (xccy_basis_swap.py:209-306)."""
-        pv_dom = self._domestic_leg.value(value_dt, domestic_curve, domestic_curve)
-        pv_for = self._foreign_leg.value(value_dt, xccy_curve, foreign_curve)
-        return pv_dom + spot_fx * pv_for
+    def value(self, value_dt: Date, domestic_discount_curve, foreign_discount_curve, xccy_discount_curve=None,
+              xccy_discount_curve_inverted=None, spot_fx: float = None, collateral_type=None,
+              first_fixing_rate_domestic: float = None, first_fixing_rate_foreign: float = None):
+        """Non-AD PV in the collateral currency (xccy_basis_swap.py:209-301).  Domestic collateral (the default): domestic leg
+        on its own OIS curve, foreign leg projected on the foreign OIS curve and discounted on the XCCY curve, converted as
+        `foreign / spot_fx`; foreign collateral: domestic leg discounted on the inverted XCCY curve, converted as
+        `domestic * spot_fx`.  (The XCCY bootstrap's own par condition is `domestic + spot_fx * foreign = 0`,
+        xccy_curve.py:465-474; for a calibration swap both legs are then at par, so either conversion gives zero.)"""
+        from .global_types import collateral_to_currency
+        collateral_ccy = self._domestic_currency if collateral_type is None else collateral_to_currency(collateral_type)
+        if collateral_ccy == self._domestic_currency:
+            dom_disc, for_disc = domestic_discount_curve, xccy_discount_curve
+            if for_disc is None:
+                raise ValueError(f"xccy_discount_curve required for domestic collateral ({self._domestic_currency.name})")
+        elif collateral_ccy == self._foreign_currency:
+            dom_disc, for_disc = xccy_discount_curve_inverted, foreign_discount_curve
+            if dom_disc is None:
+                raise ValueError(f"xccy_discount_curve_inverted required for foreign collateral "
+                                 f"({self._foreign_currency.name})")
+        else:
+            raise ValueError(f"Third-party collateral not yet supported: {collateral_type}. Only "
+                             f"{self._domestic_currency.name} or {self._foreign_currency.name} collateral allowed.")
+        pv_dom = self._domestic_leg.value(value_dt, dom_disc, domestic_discount_curve, first_fixing_rate_domestic)
+        pv_for = self._foreign_leg.value(value_dt, for_disc, foreign_discount_curve, first_fixing_rate_foreign)
+        if collateral_ccy == self._domestic_currency:
+            return pv_dom + pv_for / spot_fx
+        return pv_dom * spot_fx + pv_for

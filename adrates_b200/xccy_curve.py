@@ -148,7 +148,7 @@ class XccyCurve(DiscountCurve):
         self._pts, self._node_idx = pts, node_idx
         self._second = None                       # second-order tables, built on first use
         if self._check_refit:
-            self._check_refits(1e-8)
+            self._check_refits(1e-10)               # the reference's SWAP_TOL (xccy_curve.py:77)
 
     # ---------------------------------------------------------------------------------
     def scan_plan(self):
@@ -286,7 +286,24 @@ class XccyCurve(DiscountCurve):
         return DiscountCurve.df(self, dt, DayCountTypes.ACT_365F)
 
     def _check_refits(self, swap_tol: float):
+        """Reprices the calibration swaps through the non-AD `XccyBasisSwap.value` (xccy_curve.py:1238-1272).  Passes when the
+        OIS curves interpolate flat-forward; with another scheme the bootstrap's log-linear forward projection and the legs'
+        curve look-ups differ by ~1e-5 of the notional and the check raises - in the reference as here."""
         for swap in self._used_swaps:
-            v = swap.value(self._value_dt, self._domestic_curve, self._foreign_curve, self, self._spot_fx)
-            if abs(v / swap._domestic_notional) > swap_tol:
-                raise LibError("Basis swap not repriced.")
+            v = swap.value(value_dt=self._value_dt, domestic_discount_curve=self._domestic_curve,
+                           foreign_discount_curve=self._foreign_curve, xccy_discount_curve=self, spot_fx=self._spot_fx)
+            v_normalized = v / swap._domestic_notional
+            if abs(v_normalized) > swap_tol:
+                raise LibError(f"XCCY swap with maturity {swap._maturity_dt} not repriced. "
+                               f"Difference is {abs(v_normalized)}")
+
+    def par_residuals(self) -> list:
+        """(domestic PV + spot x foreign PV) / domestic notional of every calibration swap on the bootstrapped curve - the
+        condition the bootstrap solves (xccy_curve.py:465-474).  Zero to rounding when the OIS curves interpolate
+        flat-forward (the bootstrap projects forwards log-linearly).  A diagnostic beyond the reference's _check_refits."""
+        out = []
+        for swap in self._used_swaps:
+            pv_dom = swap._domestic_leg.value(self._value_dt, self._domestic_curve, self._domestic_curve)
+            pv_for = swap._foreign_leg.value(self._value_dt, self, self._foreign_curve)
+            out.append((pv_dom + self._spot_fx * pv_for) / swap._domestic_notional)
+        return out

@@ -30,13 +30,34 @@ def test_xccy_curve_matches_reference(xg):
 
 
 def test_calibration_basis_swaps_reprice(xg):
-    """tests/test_xccy_curve.py:213 / test_xccy_simple.py:131: abs(PV/N) < 1e-8 through the non-AD value().
-    Holds when the OIS curves interpolate flat-forward (the bootstrap projects forwards log-linearly)."""
-    from adrates_b200 import InterpTypes
+    """tests/test_xccy_curve.py:213 / test_xccy_simple.py:131 of the reference: abs(PV / N) < 1e-8 through the non-AD value(),
+    and the reference's refit check at its SWAP_TOL.  Holds when the OIS curves interpolate flat-forward (the bootstrap projects
+    forwards log-linearly); with LINEAR_ZERO_RATES curves the check raises, as the reference's does."""
+    from adrates_b200 import InterpTypes, LibError
     import tests.util_xccy as ux
     g = dict(xg)
     m = ux.build_xccy_model(g, ois_interp=InterpTypes.FLAT_FWD_RATES)
-    m.curves.GBP_USD_BASIS._check_refits(1e-8)
+    xc = m.curves.GBP_USD_BASIS
+    assert max(abs(r) for r in xc.par_residuals()) < 1e-12
+    xc._check_refits(1e-10)
+    lz = ux.build_xccy_model(dict(xg), ois_interp=InterpTypes.LINEAR_ZERO_RATES).curves.GBP_USD_BASIS
+    with pytest.raises(LibError, match="XCCY swap with maturity .* not repriced. Difference is"):
+        lz._check_refits(1e-10)
+    sw = xc._used_swaps[0]
+    kw = dict(value_dt=m.value_dt, domestic_discount_curve=xc._domestic_curve, foreign_discount_curve=xc._foreign_curve)
+    v = sw.value(xccy_discount_curve=xc, spot_fx=xc._spot_fx, **kw)
+    pv_dom = sw._domestic_leg.value(m.value_dt, xc._domestic_curve, xc._domestic_curve)
+    pv_for = sw._foreign_leg.value(m.value_dt, xc, xc._foreign_curve)
+    assert v == pv_dom + pv_for / xc._spot_fx
+    with pytest.raises(ValueError, match="xccy_discount_curve required for domestic collateral"):
+        sw.value(spot_fx=xc._spot_fx, **kw)
+    from adrates_b200 import CollateralType
+    foreign = CollateralType[sw._foreign_currency.name]
+    with pytest.raises(ValueError, match="xccy_discount_curve_inverted required for foreign collateral"):
+        sw.value(xccy_discount_curve=xc, spot_fx=xc._spot_fx, collateral_type=foreign, **kw)
+    vf = sw.value(xccy_discount_curve_inverted=xc, spot_fx=xc._spot_fx, collateral_type=foreign, **kw)
+    assert vf == sw._domestic_leg.value(m.value_dt, xc, xc._domestic_curve) * xc._spot_fx + \
+        sw._foreign_leg.value(m.value_dt, xc._foreign_curve, xc._foreign_curve)
 
 
 def test_flattened_xccy_trades_match_reference_engine(xg):

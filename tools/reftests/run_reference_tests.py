@@ -15,6 +15,7 @@ import sys
 import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+SHIM = os.path.join(ROOT, "tests", "golden", "gen", "refshim")      # `import jax.numpy as jnp` of the test files themselves
 REF_TESTS = "/root/reference/tests"
 
 # reference module -> the modules of this package whose public names stand in for it (first one wins on a clash)
@@ -28,7 +29,7 @@ ALIASES = {
     "cavour.utils.error": ["adrates_b200.error"],
     "cavour.utils.currency": ["adrates_b200.global_types"],
     "cavour.utils.global_types": ["adrates_b200.global_types", "adrates_b200.inflation"],
-    "cavour.market.curves.interpolator": ["adrates_b200.curves", "adrates_b200.global_types"],
+    "cavour.market.curves.interpolator": ["adrates_b200.interpolator", "adrates_b200.global_types"],
     "cavour.market.curves.discount_curve": ["adrates_b200.curves"],
     "cavour.market.curves.inflation_curve": ["adrates_b200.inflation"],
     "cavour.market.indices.inflation_index": ["adrates_b200.inflation"],
@@ -54,6 +55,7 @@ ALIASES = {
 
 def install_aliases():
     sys.path.insert(0, ROOT)
+    sys.path.insert(0, SHIM)
     made = {}
 
     def package(name):
