@@ -244,17 +244,9 @@ def yoy_cashflows(swap, discount_curve, inflation_curve, device: int = 0) -> Cas
     live = np.array([d > vd for d in dts])
     t = np.concatenate([_times([vd], vd, fixed._dc_type), _times(dts, vd, fixed._dc_type)])
     df = _curve_dfs(discount_curve, np.where(np.concatenate([[True], live]), t, 0.0), device)
-    # the inflation leg's valuation: nothing of it reaches the rows, its errors do
+    # the inflation leg's non-AD valuation: nothing of it reaches the rows, its errors (and the lists it keeps on the leg) do
+    leg.value(vd, discount_curve, inflation_curve)
     index = leg._inflation_index
-    if inflation_curve is not None:
-        index.set_inflation_curve(inflation_curve)
-    for i, dt in enumerate(leg._payment_dts):
-        if dt <= vd:
-            continue
-        start_cpi = index.get_index(leg._yoy_start_dts[i], apply_lag=True)
-        index.get_index(leg._yoy_end_dts[i], apply_lag=True)
-        if start_cpi <= 0.0:
-            raise LibError(f"Start CPI must be positive, got {start_cpi}")
     sign = -1.0 if fixed._leg_type == SwapTypes.PAY else 1.0
     name = "Fixed_Pay" if fixed._leg_type == SwapTypes.PAY else "Fixed_Rec"
     notl = float(fixed._notional)

@@ -101,6 +101,15 @@ class BondAnalytics:
         target = self._target_pv(settlement_dt, clean_price)
         return _root(lambda z: self.value(settlement_dt, discount_curve, z, settlement_dt) - target, -0.1, 0.5, 0.01, maxiter=100)
 
+    def g_spread(self, settlement_dt: Date, govt_curve, clean_price: float) -> float:
+        """Bond yield less the government curve's zero rate to maturity in the bond's frequency and day count (bond.py:576-609)."""
+        return self.yield_to_maturity(settlement_dt, clean_price) - \
+            govt_curve.zero_rate(self._maturity_dt, freq_type=self._freq_type, dc_type=self._dc_type)
+
+    def i_spread(self, settlement_dt: Date, discount_curve, clean_price: float) -> float:
+        """The same against the swap curve (bond.py:613-644)."""
+        return self.g_spread(settlement_dt, discount_curve, clean_price)
+
     # ---- risk ----------------------------------------------------------------------------------------------------------------
     def _yield_moment(self, settlement_dt: Date, discount_curve, z_spread: float, power: int) -> float:
         ytm = self.yield_to_maturity(settlement_dt, self.clean_price(settlement_dt, discount_curve, z_spread, settlement_dt))

@@ -24,7 +24,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from .dates import Date, DayCount, DayCountTypes, FrequencyTypes, times_from_dates
+from .dates import Date, DayCount, DayCountTypes, FrequencyTypes, annual_frequency, times_from_dates
 from .error import LibError
 from .global_types import InterpTypes
 
@@ -204,6 +204,124 @@ class DiscountCurve:
             fitted = self._interpolator = Interpolator(self._interp_type)
             fitted.fit(self._times, self._dfs)
         return float(np.asarray(fitted.interpolate(float(t))).reshape(-1)[0])
+
+    # -- rate views of the curve (discount_curve.py:96-296, 438-600): host arithmetic on df() --------------------------
+    def value_dt(self) -> Date:
+        return self._value_dt
+
+    def _df(self, t):
+        """DF at year offset(s) t in the curve's own scheme (discount_curve.py:417-436)."""
+        if isinstance(t, np.ndarray):
+            if np.any(t < 0.0):
+                raise LibError("Interpolate times must all be >= 0")
+            return np.array([self._node_df(float(u)) for u in t.ravel()])
+        if t < 0.0:
+            raise LibError("Interpolate times must all be >= 0")
+        return self._node_df(float(t))
+
+    def _zero_to_df(self, value_dt, rates, times, freq_type: FrequencyTypes, dc_type: DayCountTypes = None):
+        t = np.maximum(np.array([times]) if isinstance(times, float) else times, 1e-12)
+        if freq_type == FrequencyTypes.CONTINUOUS:
+            return np.exp(-rates * t)
+        if freq_type == FrequencyTypes.SIMPLE:
+            return 1.0 / (1.0 + rates * t)
+        if freq_type in (FrequencyTypes.ANNUAL, FrequencyTypes.SEMI_ANNUAL, FrequencyTypes.QUARTERLY, FrequencyTypes.MONTHLY):
+            f = annual_frequency(freq_type)
+            return 1.0 / np.power(1.0 + rates / f, f * t)
+        raise LibError("Unknown Frequency type")
+
+    def _df_to_zero(self, dfs, maturity_dts, freq_type: FrequencyTypes, dc_type: DayCountTypes) -> np.ndarray:
+        dates = [maturity_dts] if isinstance(maturity_dts, Date) else maturity_dts
+        values = [dfs] if isinstance(dfs, float) else dfs
+        if len(dates) != len(values):
+            raise LibError("Date list and df list do not have same length")
+        f = annual_frequency(freq_type)
+        times = times_from_dates(dates, self._value_dt, dc_type)
+        out = []
+        for df, t in zip(values, times):
+            t = max(t, 1e-12)
+            if freq_type == FrequencyTypes.CONTINUOUS:
+                out.append(-np.log(df) / t)
+            elif freq_type == FrequencyTypes.SIMPLE:
+                out.append((1.0 / df - 1.0) / t)
+            else:
+                out.append((np.power(df, -1.0 / (t * f)) - 1.0) * f)
+        return np.array(out)
+
+    def zero_rate(self, dts, freq_type: FrequencyTypes = FrequencyTypes.CONTINUOUS, dc_type: DayCountTypes = DayCountTypes.ACT_360):
+        """Zero rate(s) to the date(s) in the given compounding and day count (discount_curve.py:180-205)."""
+        if not isinstance(freq_type, FrequencyTypes):
+            raise LibError("Invalid Frequency type.")
+        if not isinstance(dc_type, DayCountTypes):
+            raise LibError("Invalid Day Count type.")
+        zeros = self._df_to_zero(self.df(dts), dts, freq_type, dc_type)
+        return zeros[0] if isinstance(dts, Date) else np.array(zeros)
+
+    def cc_rate(self, dts, dc_type: DayCountTypes = DayCountTypes.SIMPLE):
+        return self.zero_rate(dts, FrequencyTypes.CONTINUOUS, dc_type)
+
+    def swap_rate(self, effective_dt: Date, maturity_dt, freq_type=FrequencyTypes.ANNUAL,
+                  dc_type: DayCountTypes = DayCountTypes.THIRTY_E_360) -> np.ndarray:
+        """Par rate(s) of fixed-for-floating swaps off this one curve, (DF(start) - DF(end)) / annuity on an unadjusted-calendar
+        schedule whose first date is forced to the effective date; always an array (discount_curve.py:217-296)."""
+        from .dates import Schedule
+        if effective_dt < self._value_dt:
+            raise LibError("Swap starts before the curve valuation date.")
+        if not isinstance(freq_type, FrequencyTypes):
+            raise LibError("Invalid Frequency type.")
+        if freq_type == FrequencyTypes.SIMPLE:
+            raise LibError("Cannot calculate par rate with simple yield freq.")
+        if freq_type == FrequencyTypes.CONTINUOUS:
+            raise LibError("Cannot calculate par rate with continuous freq.")
+        dc = DayCount(dc_type)
+        rates = []
+        for mat in ([maturity_dt] if isinstance(maturity_dt, Date) else maturity_dt):
+            if mat <= effective_dt:
+                raise LibError("Maturity date is before the swap start date.")
+            flow = list(Schedule(effective_dt, mat, freq_type).generate())
+            flow[0] = effective_dt
+            annuity, df = 0.0, 1.0
+            for prev, nxt in zip(flow[:-1], flow[1:]):
+                df = self.df(nxt)
+                annuity += dc.year_frac(prev, nxt)[0] * df
+            rates.append(0.0 if abs(annuity) < 1e-12 else (self.df(effective_dt) - df) / annuity)
+        return np.array(rates)
+
+    def survival_prob(self, dt: Date):
+        return self.df(dt)
+
+    def fwd(self, dts):
+        """Continuously compounded one-day forward rate at the date(s) (discount_curve.py:446-468)."""
+        nxt = [dts.add_days(1)] if isinstance(dts, Date) else [d.add_days(1) for d in dts]
+        f = np.log(self.df(dts) / self.df(nxt)) / (1.0 / 365.0)
+        return f[0] if isinstance(dts, Date) else np.array(f)
+
+    def _fwd(self, times):
+        h = 1e-6
+        times = np.maximum(times, h)
+        return np.log(self._df(times - h) / self._df(times + h)) / (2.0 * h)
+
+    def bump(self, bump_size: float) -> "DiscountCurve":
+        """A new curve with every zero rate moved up by bump_size (discount_curve.py:488-507).  As in the reference the node
+        times are handed to the constructor as year offsets, so its `add_years` / 365-day round trip applies."""
+        values = self._dfs * np.exp(-bump_size * self._times)
+        return DiscountCurve(self._value_dt, self._times.tolist(), values, self._interp_type)
+
+    def fwd_rate(self, start_dt, date_or_tenor, dc_type: DayCountTypes = DayCountTypes.ACT_360):
+        """Simply compounded forward rate(s) from the start date(s) to a date / tenor (discount_curve.py:511-560)."""
+        if isinstance(start_dt, Date):
+            starts = [start_dt]
+        elif isinstance(start_dt, list):
+            starts = start_dt
+        else:
+            raise LibError("Start date and end date must be same types.")
+        dc = DayCount(dc_type)
+        out = []
+        for i, d1 in enumerate(starts):
+            d2 = d1.add_tenor(date_or_tenor) if isinstance(date_or_tenor, str) else \
+                (date_or_tenor if isinstance(date_or_tenor, Date) else date_or_tenor[i])
+            out.append((self.df(d1) / self.df(d2) - 1.0) / dc.year_frac(d1, d2)[0])
+        return out[0] if isinstance(start_dt, Date) else np.array(out)
 
     def df_ad(self, t, day_count=DayCountTypes.ACT_ACT_ISDA):
         """DF at time(s) t in years: linear interpolation of piecewise forward rates on the

@@ -165,6 +165,34 @@ class Date:
     def __hash__(self): return hash(self._t)
     def __sub__(self, o): return self._t - o._t
 
+    @staticmethod
+    def _next_quarter_end_month(m: int, d: int, y: int, roll_day: int):
+        """(month, year) of the next March / June / September / December date: the quarter month of m, or the following one
+        when the date is already on or past that month's roll day."""
+        q = 3 * ((m + 2) // 3)
+        if m == q and d >= roll_day:
+            q += 3
+        return (q, y) if q <= 12 else (3, y + 1)
+
+    def next_cds_date(self, mm: int = 0) -> "Date":
+        """The 20th of the next March / June / September / December after this date moved by mm months (date.py:698-732)."""
+        base = self.add_months(mm)
+        m, y = Date._next_quarter_end_month(base._m, base._d, base._y, 20)
+        return Date(20, m, y)
+
+    def third_wednesday_of_month(self, m: int, y: int) -> int:
+        """Day of the month of the third Wednesday - between the 15th and the 21st (date.py:736-755)."""
+        for d in range(15, 22):
+            if Date(d, m, y).weekday() == Date.WED:
+                return d
+        raise LibError("Third Wednesday not found")
+
+    def next_imm_date(self) -> "Date":
+        """Next third Wednesday of March / June / September / December after this date (date.py:759-795)."""
+        q = 3 * ((self._m + 2) // 3)
+        m, y = Date._next_quarter_end_month(self._m, self._d, self._y, self.third_wednesday_of_month(q, self._y))
+        return Date(self.third_wednesday_of_month(m, y), m, y)
+
     def add_hours(self, hours) -> "Date":
         """The date `hours` later, minutes and seconds kept (reference date.py:487-503)."""
         if hours < 0:
@@ -277,6 +305,20 @@ def datediff(d1: Date, d2: Date) -> int:
     return d2 - d1
 
 
+def from_datetime(dt) -> Date:
+    """Date of anything with .day / .month / .year (reference date.py:1051-1056)."""
+    return Date(dt.day, dt.month, dt.year)
+
+
+def daily_working_day_schedule(start_dt: Date, end_dt: Date) -> list:
+    """start_dt, then every following weekday until end_dt is reached or passed (reference date.py:1024-1037)."""
+    out, dt = [start_dt], start_dt
+    while dt < end_dt:
+        dt = dt.add_weekdays(1)
+        out.append(dt)
+    return out
+
+
 def date_range(start_dt: Date, end_dt: Date, tenor: str = "1D") -> list:
     """Dates from start_dt to end_dt, both included, `tenor` apart (reference date.py:1075-1093); the end date closes the list
     even when the stride steps over it."""
@@ -308,9 +350,7 @@ def annual_frequency(freq_type: FrequencyTypes) -> float:
     table = {FrequencyTypes.CONTINUOUS: -1, FrequencyTypes.ZERO: 1.0, FrequencyTypes.ANNUAL: 1.0,
              FrequencyTypes.SEMI_ANNUAL: 2.0, FrequencyTypes.TRI_ANNUAL: 3.0, FrequencyTypes.QUARTERLY: 4.0,
              FrequencyTypes.MONTHLY: 12.0}
-    if freq_type not in table:
-        raise LibError("Unknown frequency type")
-    return table[freq_type]
+    return table.get(freq_type)          # SIMPLE has no annual frequency: None, as the reference's function falls through
 
 
 class BusDayAdjustTypes(Enum):

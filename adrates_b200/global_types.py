@@ -72,7 +72,26 @@ class CurrencyTypes(Enum):
     NONE = 15
 
 
+class InflationIndexTypes(Enum):
+    """cavour/utils/global_types.py:93-112"""
+    UK_RPI = 1
+    UK_CPI = 2
+    UK_CPIH = 3
+    US_CPI_U = 4
+    EUR_HICP = 5
+    EUR_HICP_EX = 6
+
+
+class InflationInterpTypes(Enum):
+    """Daily CPI between monthly fixings (cavour/utils/global_types.py:113-123)"""
+    FLAT = 1
+    LINEAR = 2
+    COMPOUND = 3
+
+
 class CollateralType(Enum):
+    """Collateral of a CSA (cavour/utils/global_types.py:124-148): currencies discount on OIS / XCCY curves; the bond kinds are
+    names the reference reserves for later."""
     USD = 1
     GBP = 2
     EUR = 3
@@ -80,14 +99,53 @@ class CollateralType(Enum):
     CHF = 5
     AUD = 6
     CAD = 7
+    USD_TIPS = 10
+    EUR_OATS = 11
+    EUR_BUNDS = 12
+    GBP_GILTS = 13
+    JGB = 14
     UNCOLLATERALIZED = 99
 
 
+_BOND_COLLATERAL_CCY = {"USD_TIPS": "USD", "EUR_OATS": "EUR", "EUR_BUNDS": "EUR", "GBP_GILTS": "GBP", "JGB": "JPY"}
+_OIS_CURVE_NAME = {"USD": "USD_OIS_SOFR", "GBP": "GBP_OIS_SONIA", "EUR": "EUR_OIS_ESTR", "JPY": "JPY_OIS_TONAR",
+                   "CHF": "CHF_OIS_SARON", "AUD": "AUD_OIS_AONIA", "CAD": "CAD_OIS_CORRA"}
+
+
+def is_currency_collateral(collateral_type: CollateralType) -> bool:
+    return collateral_type in (CollateralType.USD, CollateralType.GBP, CollateralType.EUR, CollateralType.JPY,
+                               CollateralType.CHF, CollateralType.AUD, CollateralType.CAD)
+
+
+def is_bond_collateral(collateral_type: CollateralType) -> bool:
+    return isinstance(collateral_type, CollateralType) and collateral_type.name in _BOND_COLLATERAL_CCY
+
+
 def collateral_to_currency(collateral_type: CollateralType) -> CurrencyTypes:
-    """cavour/utils/global_types.py:157-190 (currency collateral only)."""
-    if collateral_type == CollateralType.UNCOLLATERALIZED or collateral_type.name not in CurrencyTypes.__members__:
-        raise ValueError(f"Cannot convert {collateral_type} to currency. Use is_currency_collateral() to check first.")
-    return CurrencyTypes[collateral_type.name]
+    """Currency a collateral type is denominated in (cavour/utils/global_types.py:157-190)."""
+    if is_currency_collateral(collateral_type):
+        return CurrencyTypes[collateral_type.name]
+    if is_bond_collateral(collateral_type):
+        return CurrencyTypes[_BOND_COLLATERAL_CCY[collateral_type.name]]
+    raise ValueError(f"Cannot convert {collateral_type} to currency. Use is_currency_collateral() to check first.")
+
+
+def get_discount_curve_name(cashflow_currency: CurrencyTypes, collateral_type: CollateralType) -> str:
+    """Name of the curve that discounts cashflows of one currency under a collateral type (global_types.py:227-300): the
+    currency's OIS curve under its own collateral, `<CCY>_<COLLATERAL>_XCCY` otherwise."""
+    if is_currency_collateral(collateral_type):
+        collateral_ccy = collateral_to_currency(collateral_type)
+        if cashflow_currency != collateral_ccy:
+            return f"{cashflow_currency.name}_{collateral_ccy.name}_XCCY"
+        if cashflow_currency.name not in _OIS_CURVE_NAME:
+            raise ValueError(f"No OIS curve defined for {cashflow_currency}")
+        return _OIS_CURVE_NAME[cashflow_currency.name]
+    if is_bond_collateral(collateral_type):
+        return f"{cashflow_currency.name}_{collateral_type.name}_XCCY"
+    if collateral_type == CollateralType.UNCOLLATERALIZED:
+        raise ValueError("Cannot generate curve name for UNCOLLATERALIZED. "
+                         "Uncollateralized discounting requires separate handling.")
+    raise ValueError(f"Unsupported collateral type: {collateral_type}")
 
 
 ONE_MILLION = 1000000

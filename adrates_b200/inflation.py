@@ -20,22 +20,8 @@ import numpy as np
 from .curves import DiscountCurve
 from .dates import BusDayAdjustTypes, Calendar, CalendarTypes, Date, DayCount, DayCountTypes, times_from_dates
 from .error import LibError
-from .global_types import CurrencyTypes, InstrumentTypes, InterpTypes, ONE_MILLION, SwapTypes
-
-
-class InflationIndexTypes(Enum):
-    UK_RPI = 1
-    UK_CPI = 2
-    UK_CPIH = 3
-    US_CPI_U = 4
-    EUR_HICP = 5
-    EUR_HICP_EX = 6
-
-
-class InflationInterpTypes(Enum):
-    FLAT = 1
-    LINEAR = 2
-    COMPOUND = 3
+from .global_types import (CurrencyTypes, InflationIndexTypes, InflationInterpTypes, InstrumentTypes, InterpTypes, ONE_MILLION,
+                           SwapTypes)
 
 
 class InflationIndex:
@@ -288,6 +274,14 @@ class ZeroCouponInflationSwap:
     def value(self, value_dt: Date, discount_curve: DiscountCurve, inflation_curve=None) -> float:
         return float(value_zcis_book([self], value_dt, discount_curve, inflation_curve)[0])
 
+    def pv01(self, value_dt: Date, discount_curve: DiscountCurve) -> float:
+        """|dPV / d fixed rate| x 1 bp of the compounded fixed payment (zcis.py:284-317)."""
+        yf = DayCount(self._dc_type).year_frac(self._effective_dt, self._maturity_dt)[0]
+        df = 0.0
+        if self._payment_dt > value_dt:
+            df = discount_curve.df(self._payment_dt, DayCountTypes.ACT_365F) / discount_curve.df(value_dt, DayCountTypes.ACT_365F)
+        return abs(self._notional * yf * ((1.0 + self._fixed_rate) ** (yf - 1.0)) * df) * 0.0001
+
     def breakeven_inflation_rate(self, value_dt: Date, discount_curve: DiscountCurve, inflation_curve=None) -> float:
         """zcis.py:242-290: annual rate whose compounded return equals the projected inflation return."""
         self._inflation_leg.payment(inflation_curve)
@@ -336,6 +330,34 @@ class SwapYoYInflationLeg:
             self._accrued_days.append(days)
             self._yoy_end_dts.append(end)                     # CPI reference dates: period end and one year before
             self._yoy_start_dts.append(end.add_months(-12))
+        self._start_cpis, self._end_cpis, self._yoy_rates, self._payments, self._dfs, self._pvs = [], [], [], [], [], []
+
+    def value(self, value_dt: Date, discount_curve: DiscountCurve, inflation_curve=None) -> float:
+        """Non-AD PV of the leg (swap_yoy_inflation_leg.py:267-366): per future payment the lagged CPI at both reference dates
+        (fixings first, then the curve - a reference date before the value date without a fixing raises), the year-on-year
+        rate plus spread on the accrual, discounted relative to the value date.  Host code as in the reference; Greeks and
+        batched valuation go through Position.compute."""
+        index = self._inflation_index
+        if inflation_curve is not None:
+            index.set_inflation_curve(inflation_curve)
+        n = len(self._payment_dts)
+        cols = [[0.0] * n for _ in range(6)]
+        self._start_cpis, self._end_cpis, self._yoy_rates, self._payments, self._dfs, self._pvs = cols
+        total = 0.0
+        for i, pay in enumerate(self._payment_dts):
+            if pay <= value_dt:
+                continue
+            start = index.get_index(self._yoy_start_dts[i], apply_lag=True)
+            end = index.get_index(self._yoy_end_dts[i], apply_lag=True)
+            if start <= 0.0:
+                raise LibError(f"Start CPI must be positive, got {start}")
+            rate = (end / start) - 1.0
+            amount = self._notional * self._year_fracs[i] * (rate + self._spread)
+            df = discount_curve.df(pay, self._dc_type) / discount_curve.df(value_dt, self._dc_type)
+            for col, v in zip(cols, (start, end, rate, amount, df, amount * df)):
+                col[i] = v
+            total += amount * df
+        return -total if self._leg_type == SwapTypes.PAY else total
 
 
 class YoYInflationSwap:
@@ -377,6 +399,29 @@ class YoYInflationSwap:
         """Convenience the reference lacks (its YoYInflationSwap has no .position); Position(swap, model) works too."""
         from .position import Position
         return Position(self, model)
+
+    def value(self, value_dt: Date, discount_curve: DiscountCurve, inflation_curve=None) -> float:
+        """Non-AD net PV, fixed leg then inflation leg (yoy_inflation_swap.py:224-260)."""
+        self._fixed_pv = self._fixed_leg.value(value_dt, discount_curve)
+        self._inflation_pv = self._inflation_leg.value(value_dt, discount_curve, inflation_curve)
+        return self._fixed_pv + self._inflation_pv
+
+    def _annuity(self, value_dt: Date, discount_curve: DiscountCurve) -> float:
+        df0 = discount_curve.df(value_dt, DayCountTypes.ACT_365F)
+        return sum(yf * discount_curve.df(dt, DayCountTypes.ACT_365F) / df0
+                   for dt, yf in zip(self._fixed_leg._payment_dts, self._fixed_leg._year_fracs) if dt > value_dt)
+
+    def breakeven_rate(self, value_dt: Date, discount_curve: DiscountCurve, inflation_curve=None) -> float:
+        """Fixed rate at which the swap is worth zero: inflation-leg PV over notional x annuity (yoy_inflation_swap.py:264-336)."""
+        inflation_pv = self._inflation_leg.value(value_dt, discount_curve, inflation_curve)
+        annuity = self._annuity(value_dt, discount_curve)
+        if annuity <= 0:
+            raise LibError("Annuity must be positive for breakeven calculation")
+        sign = 1.0 if self._fixed_leg_type == SwapTypes.PAY else -1.0
+        return sign * inflation_pv / (self._notional * annuity)
+
+    def pv01(self, value_dt: Date, discount_curve: DiscountCurve) -> float:
+        return abs(self._notional * self._annuity(value_dt, discount_curve) * 0.0001)
 
 
 def cashflow_pv(discount_curve: DiscountCurve, value_dt: Date, trades, device: int = 0) -> np.ndarray:

@@ -15,8 +15,24 @@ import numpy as np
 from .global_types import CurrencyTypes, CurveTypes
 
 
+class _Export:
+    """to_csv / to_excel over the container's `df` (the reference's export helpers, results.py:133-158 and per class)."""
+    _sheet = "Sheet1"
+
+    def to_csv(self, filepath: Optional[str] = None) -> Optional[str]:
+        if filepath:
+            self.df.to_csv(filepath)
+            return None
+        return self.df.to_csv()
+
+    def to_excel(self, filepath: str, sheet_name: Optional[str] = None):
+        self.df.to_excel(filepath, sheet_name=sheet_name or self._sheet)
+
+
 @dataclass(frozen=True)
-class Valuation:
+class Valuation(_Export):
+    _sheet = "Valuation"
+
     amount: float
     currency: CurrencyTypes = CurrencyTypes.NONE
 
@@ -57,6 +73,15 @@ class Valuation:
     def to_dict(self):
         return {"amount": float(self.amount), "currency": self.currency.name}
 
+    def to_json(self, indent: Optional[int] = 2) -> str:
+        import json
+        return json.dumps(self.to_dict(), indent=indent)
+
+    @property
+    def df(self):
+        import pandas as pd
+        return pd.DataFrame([self.to_dict()])
+
 
 Value = Valuation
 
@@ -66,11 +91,22 @@ class Ladder:
         self.data = data
         self._curve_name = curve_name
 
+    @property
+    def df(self):
+        """One column `<curve>_Risk` indexed by tenor label (results.py:204-217)"""
+        import pandas as pd
+        out = pd.DataFrame.from_dict(self.data, orient="index", columns=[f"{self._curve_name}_Risk"])
+        out.index.name = "Tenor"
+        return out
+
+    def to_dict(self) -> dict:
+        return dict(self.data)
+
     def __repr__(self):
         return f"Ladder(curve={self._curve_name}, points={len(self.data)}, curve_data={self.data})"
 
 
-class _Sensitivity:
+class _Sensitivity(_Export):
     risk_ladder: np.ndarray
     tenors: List[str]
     currency: CurrencyTypes
@@ -124,6 +160,16 @@ class Delta(_Sensitivity):
         return {"risk_ladder": self.risk_ladder.tolist(), "tenors": self.tenors, "currency": self.currency.name,
                 "curve_type": self.curve_type.name, "total": float(np.sum(self.risk_ladder))}
 
+    def to_json(self, indent: Optional[int] = 2) -> str:
+        import json
+        return json.dumps(self.to_dict(), indent=indent)
+
+    _sheet = "Delta"
+
+    @property
+    def df(self):
+        return self.ladder.df
+
 
 @dataclass(frozen=True, repr=False)
 class Gamma(_Sensitivity):
@@ -139,11 +185,45 @@ class Gamma(_Sensitivity):
     @property
     def to_dict(self) -> dict:
         g = np.asarray(self.risk_ladder)
+        if g.ndim != 2:
+            raise ValueError("Gamma risk_ladder must be 2D to access matrix")
         return {rt: {ct: float(g[i, j]) for j, ct in enumerate(self.tenors)} for i, rt in enumerate(self.tenors)}
+
+    _sheet = "Gamma"
+
+    @property
+    def df(self):
+        """Matrix indexed by tenor labels on both axes; a 1-D ladder becomes the diagonal (results.py:598-605)"""
+        import pandas as pd
+        g = np.asarray(self.risk_ladder)
+        return pd.DataFrame(np.diag(g) if g.ndim == 1 else g, index=self.tenors, columns=self.tenors)
+
+    @property
+    def matrix(self) -> None:
+        """Prints the matrix without its all-zero rows and columns as a grid table (results.py:443-462).  Built from the
+        tenor -> {tenor -> value} dictionary, so - as in the reference - pillars that share a tenor label collapse."""
+        import pandas as pd
+        from tabulate import tabulate
+        out = pd.DataFrame(self.to_dict)
+        out = out.loc[~(out == 0).all(axis=1)]
+        out = out.loc[:, ~(out == 0).all(axis=0)]
+        out.index = [f"{float(i):.2f}" if _is_number(i) else i for i in out.index]
+        out.columns = [f"{float(c):.2f}" if _is_number(c) else c for c in out.columns]
+        out.index.name = "Tenors"
+        print(tabulate(out, headers="keys", tablefmt="grid", floatfmt=".2f"))
+
+    def to_json(self, indent: Optional[int] = 2) -> str:
+        import json
+        return json.dumps({"matrix": self.to_dict, "tenors": self.tenors, "currency": self.currency.name,
+                           "curve_type": self.curve_type.name, "total": float(np.sum(self.risk_ladder))}, indent=indent)
+
+
+def _is_number(x) -> bool:
+    return isinstance(x, (int, float, np.integer, np.floating))
 
 
 @dataclass(frozen=True, repr=False)
-class CrossGamma:
+class CrossGamma(_Export):
     """Cross-curve second-order sensitivity: risk_matrix[i, j] = 1e-8 * d2PV / d(curve-1 rate i) d(curve-2 rate j)
     (cavour/requests/results.py:608-836: value, to_dict, df, addition, JSON / CSV export; plotting helpers are not
     part of the valuation path)."""
@@ -194,11 +274,17 @@ class CrossGamma:
                            "curve_type_1": self.curve_type_1.name, "curve_type_2": self.curve_type_2.name,
                            "currency": self.currency.name, "total": float(np.sum(self.risk_matrix))}, indent=indent)
 
-    def to_csv(self, filepath: Optional[str] = None):
-        if filepath:
-            self.df.to_csv(filepath)
-            return None
-        return self.df.to_csv()
+    _sheet = "CrossGamma"
+
+    @property
+    def matrix(self) -> None:
+        """Prints the full matrix as a grid table (results.py:683-697)"""
+        import pandas as pd
+        from tabulate import tabulate
+        out = pd.DataFrame(self.to_dict)
+        out.index.name = f"{self.curve_type_1.name} Tenors"
+        out.columns.name = f"{self.curve_type_2.name} Tenors"
+        print(tabulate(out, headers="keys", tablefmt="grid", floatfmt=".4f"))
 
     def __add__(self, other: Any) -> "CrossGamma":
         if not isinstance(other, CrossGamma):
@@ -250,8 +336,17 @@ class Risk:
     def cross_gamma(self, c1: CurveTypes, c2: CurveTypes):
         return self._cross_gammas.get((c1.name, c2.name), None)
 
+    def has_cross_gamma(self, c1: CurveTypes, c2: CurveTypes) -> bool:
+        return (c1.name, c2.name) in self._cross_gammas
+
+    @property
+    def all_cross_gammas(self) -> dict:
+        return self._cross_gammas.copy()
+
     def __repr__(self):
-        return f"Risk({', '.join(f'{k}={v!r}' for k, v in self._by_curve.items())})"
+        """Risk(<curve>=<total> <ccy>, ...) - results.py:937-942"""
+        parts = [f"{k}={v.value.amount:.6g} {v.value.currency.name}" for k, v in self._by_curve.items()]
+        return f"{self.__class__.__name__}({', '.join(parts)})"
 
 
 class AnalyticsResult:

@@ -212,6 +212,12 @@ class OIS:
         pv = self._fixed_leg.value(value_dt, discount_curve)
         return abs(pv / self._fixed_leg._cpn / self._fixed_leg._notional * 100)
 
+    def ir01(self, value_dt, discount_curve):
+        """PV change per basis point from revaluing on the curve bumped by -/+ 10 bp (ois.py:289-300)."""
+        down = self.value(value_dt, discount_curve.bump(-0.001))
+        up = self.value(value_dt, discount_curve.bump(0.001))
+        return (up - down) / 10 / 2
+
     def swap_rate(self, value_dt, ois_curve, first_fixing_rate=None):
         pv01 = self.pv01(value_dt, ois_curve)
         return self._float_leg.value(value_dt, ois_curve, ois_curve, first_fixing_rate) / pv01 / self._fixed_leg._notional

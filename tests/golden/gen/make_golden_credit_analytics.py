@@ -65,6 +65,9 @@ def main():
                 "convexity": float(b.convexity(s, c)), "dv01": float(b.dv01(s, c)), "cs01_z75": float(b.cs01(s, c, 0.0075)),
             }
         rec["current_yield"] = float(b.current_yield())
+        if not b._is_zero_coupon:          # a zero-coupon bond's frequency has no zero-rate compounding
+            rec["g_spread"] = float(b.g_spread(settle, ois["USD" if ccy == "GBP" else "GBP"], rec["settle"]["clean"] - 1.0))
+            rec["i_spread"] = float(b.i_spread(settle, c, rec["settle"]["clean"] - 1.0))
         out["bonds"].append(rec)
         print(bid, rec["vd"]["clean"], rec["vd"]["ytm"], rec["settle"]["duration"], flush=True)
     for fid, issue, mat, margin, freq, dc, ccy, index, face, lag, fixing in FRNS + DUAL:

@@ -56,6 +56,10 @@ def test_bond_analytics_match_reference(setup):
             _near(b.dv01(s, c), r["dv01"], TOL, face)
             _near(b.cs01(s, c, 0.0075), r["cs01_z75"], TOL, face)
         assert b.current_yield() == rec["current_yield"]
+        if "g_spread" in rec:
+            other = model.curves["USD_OIS_SOFR" if b._currency == CurrencyTypes.GBP else "GBP_OIS_SONIA"]
+            _near(b.g_spread(settle, other, rec["settle"]["clean"] - 1.0), rec["g_spread"], ROOT_TOL)
+            _near(b.i_spread(settle, c, rec["settle"]["clean"] - 1.0), rec["i_spread"], ROOT_TOL)
         if tag == "settle" and s is settle:
             assert b.value(vd, c) == b.value(vd, c, 0.0, vd)          # settlement defaults to the value date
     with pytest.raises(ValueError, match="Unknown duration type"):

@@ -1,5 +1,7 @@
 """Host date/schedule/day-count logic against vectors produced by the reference's own
 Schedule / DayCount / Date / to_tenor (tests/golden/gen/make_golden.py)."""
+import pytest
+
 from adrates_b200.dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
                                 DayCountTypes, FrequencyTypes, Schedule, to_tenor)
 from adrates_b200.error import LibError
@@ -71,3 +73,38 @@ def test_date_repr_formats_are_the_references():
     finally:
         set_date_format(DateFormatTypes.UK_LONG)
     assert [Date(*d).str() for d in dates] == ["30APR2024", "01JAN2000", "29FEB2028", "05NOV1999", "31DEC2199"]
+
+
+def test_quarterly_roll_dates_and_collateral_names_are_the_references():
+    """next_cds_date / next_imm_date / third_wednesday_of_month / daily_working_day_schedule / from_datetime (reference
+    date.py:698-795, 1024-1056) and the collateral helpers (global_types.py:157-300): known answers printed by the unmodified
+    reference in this container (the date rules were also compared on 4 000 random dates there)."""
+    import datetime
+    from adrates_b200.dates import daily_working_day_schedule, from_datetime
+    from adrates_b200.global_types import (CollateralType, CurrencyTypes, collateral_to_currency, get_discount_curve_name,
+                                           is_bond_collateral, is_currency_collateral)
+    cases = [(19, 3, 2024), (20, 3, 2024), (21, 12, 2024), (15, 6, 2025), (18, 6, 2025), (17, 9, 2025), (16, 9, 2025), (31, 12, 2030),
+             (1, 1, 2031), (30, 4, 2024)]
+    ref = [((20, 3, 2024), (20, 3, 2024)), ((20, 6, 2024), (19, 6, 2024)), ((20, 3, 2025), (19, 3, 2025)), ((20, 6, 2025), (18, 6, 2025)),
+           ((20, 6, 2025), (17, 9, 2025)), ((20, 9, 2025), (17, 12, 2025)), ((20, 9, 2025), (17, 9, 2025)), ((20, 3, 2031), (19, 3, 2031)),
+           ((20, 3, 2031), (19, 3, 2031)), ((20, 6, 2024), (19, 6, 2024))]
+    dmy = lambda x: (x.d(), x.m(), x.y())  # noqa: E731
+    assert [(dmy(Date(*c).next_cds_date()), dmy(Date(*c).next_imm_date())) for c in cases] == ref
+    assert [dmy(Date(30, 4, 2024).next_cds_date(mm)) for mm in (1, 2, 8, -5)] == [(20, 6, 2024), (20, 9, 2024), (20, 3, 2025), (20, 12, 2023)]
+    assert Date(1, 1, 2024).third_wednesday_of_month(5, 2024) == 15 and Date(1, 1, 2024).third_wednesday_of_month(8, 2024) == 21
+    days = daily_working_day_schedule(Date(27, 12, 2023), Date(8, 1, 2024))
+    assert len(days) == 9 and all(not d.is_weekend() for d in days) and days[-1] == Date(8, 1, 2024)
+    assert from_datetime(datetime.datetime(2024, 4, 30, 12, 0)) == Date(30, 4, 2024)
+    names = [[get_discount_curve_name(CurrencyTypes[c], CollateralType[k]) for k in ("USD", "GBP", "EUR", "GBP_GILTS")]
+             for c in ("GBP", "USD", "JPY")]
+    assert names == [["GBP_USD_XCCY", "GBP_OIS_SONIA", "GBP_EUR_XCCY", "GBP_GBP_GILTS_XCCY"],
+                     ["USD_OIS_SOFR", "USD_GBP_XCCY", "USD_EUR_XCCY", "USD_GBP_GILTS_XCCY"],
+                     ["JPY_USD_XCCY", "JPY_GBP_XCCY", "JPY_EUR_XCCY", "JPY_GBP_GILTS_XCCY"]]
+    assert [k.name for k in CollateralType if is_currency_collateral(k)] == ["USD", "GBP", "EUR", "JPY", "CHF", "AUD", "CAD"]
+    assert [k.name for k in CollateralType if is_bond_collateral(k)] == ["USD_TIPS", "EUR_OATS", "EUR_BUNDS", "GBP_GILTS", "JGB"]
+    assert collateral_to_currency(CollateralType.JGB) == CurrencyTypes.JPY
+    for bad in (lambda: collateral_to_currency(CollateralType.UNCOLLATERALIZED),
+                lambda: get_discount_curve_name(CurrencyTypes.GBP, CollateralType.UNCOLLATERALIZED),
+                lambda: get_discount_curve_name(CurrencyTypes.NZD, CollateralType.USD) and get_discount_curve_name(CurrencyTypes.SEK, CollateralType.UNCOLLATERALIZED)):
+        with pytest.raises(ValueError):
+            bad()

@@ -35,8 +35,8 @@ ALIASES = {
     "cavour.market.indices.inflation_index": ["adrates_b200.inflation"],
     "cavour.market.position.engine": ["adrates_b200.position"],
     "cavour.market.position.position": ["adrates_b200.position"],
-    "cavour.market.position.portfolio": ["adrates_b200.position"],
-    "cavour.market.analytics.results": ["adrates_b200.results", "adrates_b200.cashflows"],
+    "cavour.market.portfolio.portfolio": ["adrates_b200.position"],
+    "cavour.requests.results": ["adrates_b200.results", "adrates_b200.cashflows"],
     "cavour.models.models": ["adrates_b200.models"],
     "cavour.trades.rates.ois": ["adrates_b200.trades"],
     "cavour.trades.rates.ois_curve": ["adrates_b200.curves"],
