@@ -200,7 +200,7 @@ class DiscountCurve:
         if self._interp_type in _NODE_SCHEMES:
             return float(node_df(t, self._times, self._dfs, self._interp_type.value))
         fitted = getattr(self, "_interpolator", None)
-        if fitted is None or fitted._times is not self._times:          # spline schemes: fitted once per node set
+        if fitted is None or fitted._times is not self._times or fitted._dfs is not self._dfs:   # fitted once per node set
             fitted = self._interpolator = Interpolator(self._interp_type)
             fitted.fit(self._times, self._dfs)
         return float(np.asarray(fitted.interpolate(float(t))).reshape(-1)[0])
