@@ -46,10 +46,12 @@ def test_interpolator_class_matches_reference():
         t, d = (np.array(g["node_sets"][name][k]) for k in ("times", "dfs"))
         f = Interpolator(InterpTypes[scheme])
         f.fit(t, d)
-        res = [f.interpolate(float(q)) for q in rec["q"]]
+        with np.errstate(over="ignore"):         # far beyond the grid a cubic in the zero rate overflows exp: inf, as the reference
+            res = [f.interpolate(float(q)) for q in rec["q"]]
+            arr = f.interpolate(np.array(rec["q"]))
         assert [isinstance(r, np.ndarray) for r in res] == rec["is_array"]       # t < 1e-12 answers the float 1.0
         _close([np.asarray(r).reshape(-1)[0] for r in res], rec["v"], 1e-13)
-        _close(f.interpolate(np.array(rec["q"])), g["class_array"][key]["v"], 1e-13)
+        _close(arr, g["class_array"][key]["v"], 1e-13)
     # node schemes through the class: the same arithmetic as the function, a float for a float
     for scheme in NODE:
         t, d = (g["node_sets"]["from_zero"][k] for k in ("times", "dfs"))
