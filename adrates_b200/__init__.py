@@ -12,7 +12,7 @@ from .dates import (Date, DateFormatTypes, set_date_format, Calendar, CalendarTy
 from .global_types import (SwapTypes, InstrumentTypes, RequestTypes, InterpTypes, CurveTypes,
                            CurrencyTypes, CollateralType)
 
-from .trades import OIS, SwapFixedLeg, SwapFloatLeg, XccyBasisSwap
+from .trades import OIS, SwapFixedLeg, SwapFloatLeg, XccyBasisSwap, XccyFixFloat, XccyFixFix
 from .xccy_curve import XccyCurve
 from .curves import OISCurve, DiscountCurve
 from .models import Model
@@ -24,7 +24,7 @@ from .inflation import (InflationIndex, InflationCurve, InflationIndexTypes, Inf
                         ZeroCouponInflationSwap, SwapYoYInflationLeg, YoYInflationSwap)
 
 __all__ = [
-    "OIS", "SwapFixedLeg", "SwapFloatLeg", "XccyBasisSwap", "XccyCurve", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
+    "OIS", "SwapFixedLeg", "SwapFloatLeg", "XccyBasisSwap", "XccyFixFloat", "XccyFixFix", "XccyCurve", "OISCurve", "DiscountCurve", "Model", "Position", "Portfolio", "Engine",
     "Valuation", "Delta", "Gamma", "CrossGamma", "Risk", "AnalyticsResult", "CashflowItem", "Cashflows", "InflationIndex", "InflationCurve", "InflationIndexTypes",
     "InflationInterpTypes", "SwapInflationLeg", "ZeroCouponInflationSwap", "SwapYoYInflationLeg", "YoYInflationSwap", "Bond", "FRN",
     "LibError", "Date", "DateFormatTypes", "set_date_format", "Calendar", "CalendarTypes", "create_calendar_intersection", "BusDayAdjustTypes", "DateGenRuleTypes", "DayCount",

@@ -101,16 +101,48 @@ class SwapFixedLeg(_SwapLeg):
         self._payments = [a * self._notional * self._cpn for a in self._year_fracs]
 
     def value(self, value_dt: Date, discount_curve):
-        """Path-A (curve.df) PV of the fixed leg (swap_fixed_leg.py:200-245)."""
+        """Path-A (curve.df) PV of the fixed leg (swap_fixed_leg.py:200-245); keeps the per-payment discount factors, PVs and
+        running PV of this valuation for print_valuation, as the reference does."""
         df0 = discount_curve.df(value_dt, self._dc_type)
         pv, df_p = 0.0, 0.0
-        for dt, amt in zip(self._payment_dts, self._payments):
+        n = len(self._payment_dts)
+        self._payment_dfs, self._payment_pvs, self._cumulative_pvs = [0.0] * n, [0.0] * n, [0.0] * n
+        for i, (dt, amt) in enumerate(zip(self._payment_dts, self._payments)):
             if dt > value_dt:
                 df_p = discount_curve.df(dt, self._dc_type) / df0
                 pv += amt * df_p
+                self._payment_dfs[i], self._payment_pvs[i], self._cumulative_pvs[i] = df_p, amt * df_p, pv
         if self._payment_dts[-1] > value_dt:
             pv += self._principal * df_p * self._notional
+            self._payment_pvs[-1] += self._principal * df_p * self._notional
+            self._cumulative_pvs[-1] = pv
         return -pv if self._leg_type == SwapTypes.PAY else pv
+
+    def _header(self):
+        print("START DATE:", self._effective_dt)
+        print("MATURITY DATE:", self._maturity_dt)
+        print("COUPON (%):", self._cpn * 100)
+        print("FREQUENCY:", str(self._freq_type))
+        print("DAY COUNT:", str(self._dc_type))
+
+    def print_payments(self):
+        """Schedule table: accrual dates, days, year fraction, rate, payment (swap_fixed_leg.py:250-285)"""
+        self._header()
+        rows = [[i + 1, self._payment_dts[i], self._start_accrued_dts[i], self._end_accrued_dts[i], self._accrued_days[i],
+                 round(self._year_fracs[i], 4), round(self._rates[i] * 100.0, 4), round(self._payments[i], 2)]
+                for i in range(len(self._payment_dts))]
+        _print_table("PAYMENTS SCHEDULE:", ["PAY_NUM", "PAY_dt", "ACCR_START", "ACCR_END", "DAYS", "YEARFRAC", "RATE", "PMNT"], rows)
+
+    def print_valuation(self):
+        """Table of the last valuation: payment, discount factor, PV, running PV (swap_fixed_leg.py:289-325)"""
+        self._header()
+        if not getattr(self, "_payment_dfs", None):
+            print("Payments not calculated.")
+            return
+        rows = [[i + 1, self._payment_dts[i], round(self._notional, 0), round(self._rates[i] * 100.0, 4), round(self._payments[i], 2),
+                 round(self._payment_dfs[i], 4), round(self._payment_pvs[i], 2), round(self._cumulative_pvs[i], 2)]
+                for i in range(len(self._payment_dts))]
+        _print_table("PAYMENTS VALUATION:", ["PAY_NUM", "PAY_dt", "NOTIONAL", "RATE", "PMNT", "DF", "PV", "CUM_PV"], rows)
 
 
 class SwapFloatLeg(_SwapLeg):
@@ -142,6 +174,9 @@ class SwapFloatLeg(_SwapLeg):
         df0 = discount_curve.df(value_dt, self._dc_type)
         idx_dc = DayCount(index_curve._dc_type)
         pv, df_p, first = 0.0, 0.0, True
+        n = len(self._payment_dts)
+        # rows of this valuation for print_valuation (the coupon rows only: the exchanges are not inserted into the lists)
+        self._valuation_rows = [(0.0, 0.0, 0.0, 0.0)] * n
         for i, dt in enumerate(self._payment_dts):
             if not dt > value_dt:
                 continue
@@ -154,6 +189,8 @@ class SwapFloatLeg(_SwapLeg):
             first = False
             df_p = discount_curve.df(dt, self._dc_type) / df0
             pv += (fwd + self._spread) * self._year_fracs[i] * self._notional * df_p
+            amt = (fwd + self._spread) * self._year_fracs[i] * self._notional
+            self._valuation_rows[i] = (fwd, amt, df_p, amt * df_p)
         if self._notional_exchange:
             # -N at the effective date, +N at maturity, when not in the past (swap_float_leg.py:284-347);
             # unlike the reference this does not insert the exchange into the leg's date lists
@@ -162,6 +199,48 @@ class SwapFloatLeg(_SwapLeg):
             if self._maturity_dt >= value_dt and len(self._payment_dts) > 0:
                 pv += self._notional * discount_curve.df(self._maturity_dt, self._dc_type) / df0
         return -pv if self._leg_type == SwapTypes.PAY else pv
+
+
+    def _header(self):
+        print("START DATE:", self._effective_dt)
+        print("MATURITY DATE:", self._maturity_dt)
+        print("SPREAD (bp):", self._spread * 10000)
+        print("FREQUENCY:", str(self._freq_type))
+        print("DAY COUNT:", str(self._dc_type))
+
+    def print_payments(self):
+        """Schedule table (swap_float_leg.py:356-390)"""
+        self._header()
+        rows = [[i + 1, self._payment_dts[i], self._start_accrued_dts[i], self._end_accrued_dts[i], self._accrued_days[i],
+                 round(self._year_fracs[i], 4)] for i in range(len(self._payment_dts))]
+        _print_table("PAYMENTS SCHEDULE:", ["PAY_NUM", "PAY_dt", "ACCR_START", "ACCR_END", "DAYS", "YEARFRAC"], rows)
+
+    def print_valuation(self):
+        """Table of the last valuation: forward, payment, discount factor, PV, running PV (swap_float_leg.py:394-440)"""
+        self._header()
+        if not getattr(self, "_valuation_rows", None):
+            print("Rates not calculated.")
+            return
+        rows, run = [], 0.0
+        for i, (fwd, amt, df_p, pv) in enumerate(self._valuation_rows):
+            run += pv
+            rows.append([i + 1, self._payment_dts[i], round(self._notional, 0), round(fwd * 100.0, 4), round(amt, 2), round(df_p, 4),
+                         round(pv, 2), round(run, 2)])
+        _print_table("PAYMENTS VALUATION:", ["PAY_NUM", "PAY_dt", "NOTIONAL", "IBOR", "PMNT", "DF", "PV", "CUM_PV"], rows)
+
+
+def _print_table(title: str, header: list, rows: list):
+    from tabulate import tabulate
+    print("\n" + title)
+    print(tabulate([[str(c) if isinstance(c, Date) else c for c in r] for r in rows], headers=header))
+
+
+def _print_two_legs(first_title: str, first_leg, second_title: str, second_leg, method: str):
+    for k, (title, leg) in enumerate(((first_title, first_leg), (second_title, second_leg))):
+        print(("\n" if k else "") + "=" * 80)
+        print(title)
+        print("=" * 80)
+        getattr(leg, method)()
 
 
 class OIS:
@@ -211,6 +290,16 @@ class OIS:
     def pv01(self, value_dt, discount_curve):
         pv = self._fixed_leg.value(value_dt, discount_curve)
         return abs(pv / self._fixed_leg._cpn / self._fixed_leg._notional * 100)
+
+    def print_fixed_leg_pv(self):
+        self._fixed_leg.print_valuation()
+
+    def print_float_leg_pv(self):
+        self._float_leg.print_valuation()
+
+    def print_payments(self):
+        self._fixed_leg.print_payments()
+        self._float_leg.print_payments()
 
     def ir01(self, value_dt, discount_curve):
         """PV change per basis point from revaluing on the curve bumped by -/+ 10 bp (ois.py:289-300)."""
@@ -271,6 +360,12 @@ class XccyBasisSwap:
         from .position import Position
         return Position(self, model)
 
+    def print_payments(self):
+        _print_two_legs("DOMESTIC LEG:", self._domestic_leg, "FOREIGN LEG:", self._foreign_leg, "print_payments")
+
+    def print_valuation(self):
+        _print_two_legs("DOMESTIC LEG VALUATION:", self._domestic_leg, "FOREIGN LEG VALUATION:", self._foreign_leg, "print_valuation")
+
     def value(self, value_dt: Date, domestic_discount_curve, foreign_discount_curve, xccy_discount_curve=None,
               xccy_discount_curve_inverted=None, spot_fx: float = None, collateral_type=None,
               first_fixing_rate_domestic: float = None, first_fixing_rate_foreign: float = None):
@@ -298,3 +393,117 @@ class XccyBasisSwap:
         if collateral_ccy == self._domestic_currency:
             return pv_dom + pv_for / spot_fx
         return pv_dom * spot_fx + pv_for
+
+
+def _notional_exchange_pv(curve, value_dt: Date, effective_dt: Date, maturity_dt: Date, notional: float,
+                          leg_type: SwapTypes) -> float:
+    """PV of paying the notional away at the start and getting it back at maturity, from the receiver's side; the exchanges
+    count while their date is on or after the value date (xccy_fix_float_swap.py:218-236, xccy_fix_fix_swap.py:232-275)."""
+    pv = 0.0
+    if effective_dt >= value_dt:
+        pv -= notional * curve.df(effective_dt)
+    if maturity_dt >= value_dt:
+        pv += notional * curve.df(maturity_dt)
+    return pv if leg_type == SwapTypes.RECEIVE else -pv
+
+
+class _XccyFixedDomestic:
+    """What XccyFixFloat and XccyFixFix share: dates, notionals, currencies and the fixed domestic leg without principal (the
+    notional exchanges are added by value())."""
+
+    def _init_domestic(self, effective_dt, term_dt_or_tenor, domestic_notional, foreign_notional, domestic_leg_type,
+                       domestic_coupon, domestic_freq_type, domestic_dc_type, domestic_floating_index, foreign_floating_index,
+                       domestic_currency, foreign_currency, domestic_payment_lag, domestic_cal_type, domestic_bd_type,
+                       domestic_dg_type, domestic_end_of_month):
+        self.derivative_type = InstrumentTypes.XCCY_SWAP
+        self._termination_dt = _resolve_end(effective_dt, term_dt_or_tenor)
+        self._maturity_dt = Calendar(domestic_cal_type).adjust(self._termination_dt, domestic_bd_type)
+        if effective_dt > self._maturity_dt:
+            raise LibError("Start date after maturity date")
+        self._effective_dt = effective_dt
+        self._domestic_notional, self._foreign_notional = domestic_notional, foreign_notional
+        self._domestic_currency, self._foreign_currency = domestic_currency, foreign_currency
+        self._domestic_floating_index, self._foreign_floating_index = domestic_floating_index, foreign_floating_index
+        self._domestic_leg_type = domestic_leg_type
+        self._domestic_leg = SwapFixedLeg(effective_dt, self._termination_dt, domestic_leg_type, domestic_coupon,
+                                          domestic_freq_type, domestic_dc_type, domestic_floating_index, domestic_currency,
+                                          domestic_notional, 0.0, domestic_payment_lag, domestic_cal_type, domestic_bd_type,
+                                          domestic_dg_type, domestic_end_of_month)
+        return SwapTypes.PAY if domestic_leg_type == SwapTypes.RECEIVE else SwapTypes.RECEIVE
+
+    def print_valuation(self):
+        kind = "FLOATING" if isinstance(self._foreign_leg, SwapFloatLeg) else "FIXED"
+        _print_two_legs("DOMESTIC FIXED LEG VALUATION:", self._domestic_leg, f"FOREIGN {kind} LEG VALUATION:", self._foreign_leg,
+                        "print_valuation")
+
+    def _domestic_value(self, value_dt: Date, domestic_discount_curve) -> float:
+        return self._domestic_leg.value(value_dt, domestic_discount_curve) + _notional_exchange_pv(
+            domestic_discount_curve, value_dt, self._effective_dt, self._maturity_dt, self._domestic_notional,
+            self._domestic_leg_type)
+
+
+class XccyFixFloat(_XccyFixedDomestic):
+    """Fixed domestic coupons against foreign floating + spread, notionals exchanged on both legs; non-AD valuation only
+    (cavour/trades/rates/xccy_fix_float_swap.py:79-245).  The reference's engine route for cross-currency swaps reads
+    floating-leg attributes off both legs (engine.py:1476-1511), so - there as here - Position.compute is for XccyBasisSwap."""
+
+    def __init__(self, effective_dt: Date, term_dt_or_tenor, domestic_notional: float, foreign_notional: float,
+                 domestic_leg_type: SwapTypes, domestic_coupon: float, foreign_spread: float,
+                 domestic_freq_type: FrequencyTypes, foreign_freq_type: FrequencyTypes, domestic_dc_type: DayCountTypes,
+                 foreign_dc_type: DayCountTypes, domestic_floating_index: CurveTypes, foreign_floating_index: CurveTypes,
+                 domestic_currency: CurrencyTypes, foreign_currency: CurrencyTypes, domestic_payment_lag: int = 0,
+                 foreign_payment_lag: int = 0, domestic_cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 foreign_cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 domestic_bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 foreign_bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 domestic_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
+                 foreign_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
+                 domestic_end_of_month: bool = False, foreign_end_of_month: bool = False):
+        foreign_leg_type = self._init_domestic(
+            effective_dt, term_dt_or_tenor, domestic_notional, foreign_notional, domestic_leg_type, domestic_coupon,
+            domestic_freq_type, domestic_dc_type, domestic_floating_index, foreign_floating_index, domestic_currency,
+            foreign_currency, domestic_payment_lag, domestic_cal_type, domestic_bd_type, domestic_dg_type, domestic_end_of_month)
+        self._foreign_leg = SwapFloatLeg(effective_dt, self._termination_dt, foreign_leg_type, foreign_spread, foreign_freq_type,
+                                         foreign_dc_type, foreign_floating_index, foreign_currency, foreign_notional, 0.0,
+                                         foreign_payment_lag, foreign_cal_type, foreign_bd_type, foreign_dg_type,
+                                         foreign_end_of_month, True)
+
+    def value(self, value_dt: Date, domestic_discount_curve, foreign_discount_curve, xccy_discount_curve, spot_fx: float,
+              first_fixing_rate_foreign=None) -> float:
+        """Domestic-currency PV: fixed leg and its notional exchanges on the domestic OIS curve, foreign floating leg (which
+        carries its own exchanges) projected on the foreign OIS curve and discounted on the XCCY curve, divided by spot."""
+        foreign = self._foreign_leg.value(value_dt, xccy_discount_curve, foreign_discount_curve, first_fixing_rate_foreign)
+        return self._domestic_value(value_dt, domestic_discount_curve) + foreign / spot_fx
+
+
+class XccyFixFix(_XccyFixedDomestic):
+    """Fixed coupons in both currencies, notionals exchanged on both legs; non-AD valuation only
+    (cavour/trades/rates/xccy_fix_fix_swap.py:77-280)."""
+
+    def __init__(self, effective_dt: Date, term_dt_or_tenor, domestic_notional: float, foreign_notional: float,
+                 domestic_leg_type: SwapTypes, domestic_coupon: float, foreign_coupon: float,
+                 domestic_freq_type: FrequencyTypes, foreign_freq_type: FrequencyTypes, domestic_dc_type: DayCountTypes,
+                 foreign_dc_type: DayCountTypes, domestic_floating_index: CurveTypes, foreign_floating_index: CurveTypes,
+                 domestic_currency: CurrencyTypes, foreign_currency: CurrencyTypes, domestic_payment_lag: int = 0,
+                 foreign_payment_lag: int = 0, domestic_cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 foreign_cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 domestic_bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 foreign_bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 domestic_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
+                 foreign_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
+                 domestic_end_of_month: bool = False, foreign_end_of_month: bool = False):
+        self._foreign_leg_type = self._init_domestic(
+            effective_dt, term_dt_or_tenor, domestic_notional, foreign_notional, domestic_leg_type, domestic_coupon,
+            domestic_freq_type, domestic_dc_type, domestic_floating_index, foreign_floating_index, domestic_currency,
+            foreign_currency, domestic_payment_lag, domestic_cal_type, domestic_bd_type, domestic_dg_type, domestic_end_of_month)
+        self._foreign_leg = SwapFixedLeg(effective_dt, self._termination_dt, self._foreign_leg_type, foreign_coupon,
+                                         foreign_freq_type, foreign_dc_type, foreign_floating_index, foreign_currency,
+                                         foreign_notional, 0.0, foreign_payment_lag, foreign_cal_type, foreign_bd_type,
+                                         foreign_dg_type, foreign_end_of_month)
+
+    def value(self, value_dt: Date, domestic_discount_curve, foreign_discount_curve, xccy_discount_curve, spot_fx: float) -> float:
+        """Domestic-currency PV: each fixed leg with its notional exchanges, the domestic one on the domestic OIS curve, the
+        foreign one on the XCCY curve (the foreign OIS curve is not used), foreign PV divided by spot."""
+        foreign = self._foreign_leg.value(value_dt, xccy_discount_curve) + _notional_exchange_pv(
+            xccy_discount_curve, value_dt, self._effective_dt, self._maturity_dt, self._foreign_notional, self._foreign_leg_type)
+        return self._domestic_value(value_dt, domestic_discount_curve) + foreign / spot_fx

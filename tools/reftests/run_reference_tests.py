@@ -43,6 +43,8 @@ ALIASES = {
     "cavour.trades.rates.swap_fixed_leg": ["adrates_b200.trades"],
     "cavour.trades.rates.swap_float_leg": ["adrates_b200.trades"],
     "cavour.trades.rates.xccy_basis_swap": ["adrates_b200.trades"],
+    "cavour.trades.rates.xccy_fix_float_swap": ["adrates_b200.trades"],
+    "cavour.trades.rates.xccy_fix_fix_swap": ["adrates_b200.trades"],
     "cavour.trades.rates.xccy_curve": ["adrates_b200.xccy_curve"],
     "cavour.trades.rates.zcis": ["adrates_b200.inflation"],
     "cavour.trades.rates.swap_inflation_leg": ["adrates_b200.inflation"],
