@@ -127,17 +127,22 @@ class FRN(FRNAnalytics):
         if issue_dt >= self._maturity_dt:
             raise LibError("Issue date must be before maturity date")
         self.derivative_type = InstrumentTypes.FRN
-        dts = Schedule(issue_dt, self._maturity_dt, freq_type, cal_type, bd_type, dg_type,
-                       end_of_month=end_of_month)._adjusted_dts
+        self._generate_payment_schedule()
+
+    def _generate_payment_schedule(self):
+        """Accrual periods, payment dates (lagged by business days) and year fractions of the note (frn.py:173-220)"""
+        calendar = Calendar(self._cal_type)
+        dts = Schedule(self._issue_dt, self._maturity_dt, self._freq_type, self._cal_type, self._bd_type, self._dg_type,
+                       end_of_month=self._end_of_month)._adjusted_dts
         if len(dts) < 2:
             raise LibError("Schedule must have at least two dates")
-        dc = DayCount(dc_type)
+        dc = DayCount(self._dc_type)
         self._payment_dts, self._start_accrued_dts, self._end_accrued_dts = [], [], []
         self._year_fracs, self._accrued_days = [], []
         for prev, nxt in zip(dts[:-1], dts[1:]):
             self._start_accrued_dts.append(prev)
             self._end_accrued_dts.append(nxt)
-            self._payment_dts.append(nxt if payment_lag == 0 else calendar.add_business_days(nxt, payment_lag))
+            self._payment_dts.append(nxt if self._payment_lag == 0 else calendar.add_business_days(nxt, self._payment_lag))
             yf, days, _ = dc.year_frac(prev, nxt)
             self._year_fracs.append(yf)
             self._accrued_days.append(days)

@@ -323,14 +323,14 @@ class DiscountCurve:
             out.append((self.df(d1) / self.df(d2) - 1.0) / dc.year_frac(d1, d2)[0])
         return out[0] if isinstance(start_dt, Date) else np.array(out)
 
-    def df_ad(self, t, day_count=DayCountTypes.ACT_ACT_ISDA):
-        """DF at time(s) t in years: linear interpolation of piecewise forward rates on the
-        path-A nodes, independent of `_interp_type` (discount_curve.py:317-415).  Evaluated
-        by the CUDA library (cav_df_ad); there is no host fallback."""
+    def df_ad(self, dt, day_count=DayCountTypes.ACT_ACT_ISDA):
+        """DF at time(s) `dt` in years (the reference's name for the argument): linear interpolation of piecewise forward rates
+        on the path-A nodes, independent of `_interp_type` (discount_curve.py:317-415).  Evaluated by the CUDA library
+        (cav_df_ad); there is no host fallback."""
         from . import _native
-        tt = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        tt = np.atleast_1d(np.asarray(dt, dtype=np.float64))
         out = _native.lib().df_ad(self._times, self._dfs, tt)
-        return out[0] if np.ndim(t) == 0 else out
+        return out[0] if np.ndim(dt) == 0 else out
 
 
 class OISCurve(DiscountCurve):

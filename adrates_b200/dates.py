@@ -111,10 +111,10 @@ class Date:
         return cls(*_from_ordinal(n))
 
     @classmethod
-    def from_string(cls, date_string: str, format_string: str) -> "Date":
+    def from_string(cls, date_string: str, formatString: str) -> "Date":
         """Date.from_string("15-06-2023", "%d-%m-%Y") (reference date.py:353-360)"""
         import datetime
-        t = datetime.datetime.strptime(date_string, format_string)
+        t = datetime.datetime.strptime(date_string, formatString)
         return cls(t.day, t.month, t.year)
 
     @classmethod
@@ -534,10 +534,10 @@ def is_last_day_of_feb(dt: Date):
 class DayCount:
     """year_frac(dt1, dt2) -> (fraction, numerator, denominator) (day_count.py:122-330)."""
 
-    def __init__(self, dcc_type: DayCountTypes):
-        if dcc_type not in DayCountTypes:
+    def __init__(self, dccType: DayCountTypes):
+        if dccType not in DayCountTypes:
             raise LibError("Need to pass FinDayCountType")
-        self._type = dcc_type
+        self._type = dccType
 
     def year_frac(self, dt1: Date, dt2: Date, dt3: Date = None,
                   freq_type: FrequencyTypes = FrequencyTypes.ANNUAL, isTerminationDate: bool = False):

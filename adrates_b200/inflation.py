@@ -93,7 +93,8 @@ class InflationIndex:
             raise LibError(f"Start index must be positive, got {i0}")
         return i1 / i0
 
-    def _get_historical_index(self, lookup: Date) -> Optional[float]:
+    def _get_historical_index(self, lookup_date: Date) -> Optional[float]:
+        lookup = lookup_date
         if not self._fixings:
             return None
         keys = sorted(self._fixings.keys())
@@ -106,7 +107,8 @@ class InflationIndex:
         hi_d, hi_v = self._fixings[keys[hi]]
         return self._interpolate(lookup, lo_d, hi_d, lo_v, hi_v)
 
-    def _interpolate(self, target: Date, lo_d: Date, hi_d: Date, lo_v: float, hi_v: float) -> float:
+    def _interpolate(self, target_date: Date, lower_date: Date, upper_date: Date, lower_value: float, upper_value: float) -> float:
+        target, lo_d, hi_d, lo_v, hi_v = target_date, lower_date, upper_date, lower_value, upper_value
         if self._interp_type == InflationInterpTypes.FLAT:
             return lo_v
         dc = DayCount(DayCountTypes.ACT_365F)
@@ -314,11 +316,17 @@ class SwapYoYInflationLeg:
         self._cal_type, self._bd_type = cal_type, bd_type
         self._dg_type = dg_type or DateGenRuleTypes.BACKWARD
         self._end_of_month = end_of_month
-        dts = Schedule(effective_dt, self._termination_dt, freq_type, cal_type, bd_type, self._dg_type,
-                       end_of_month=end_of_month)._adjusted_dts
+        self.generate_payment_schedule()
+
+    def generate_payment_schedule(self):
+        """Accrual periods, payment dates and the two CPI reference dates of every coupon (swap_yoy_inflation_leg.py:193-262)"""
+        from .dates import Schedule
+        effective_dt, payment_lag, cal = self._effective_dt, self._payment_lag, Calendar(self._cal_type)
+        dts = Schedule(effective_dt, self._termination_dt, self._freq_type, self._cal_type, self._bd_type, self._dg_type,
+                       end_of_month=self._end_of_month)._adjusted_dts
         if len(dts) < 2:
             raise LibError("Schedule has none or only one date")
-        dc = DayCount(dc_type)
+        dc = DayCount(self._dc_type)
         self._start_accrued_dts, self._end_accrued_dts, self._payment_dts = [], [], []
         self._year_fracs, self._accrued_days, self._yoy_start_dts, self._yoy_end_dts = [], [], [], []
         for start, end in zip(dts[:-1], dts[1:]):

@@ -21,12 +21,13 @@ G_SMALL = 1e-12           # the reference's g_small (utils/global_vars.py:4)
 _FWD_SMALL = 1e-10        # regulariser of the first LINEAR_FWD_RATES segment (interpolator.py:75, 147-149)
 
 
-def node_df(t: float, x: np.ndarray, d: np.ndarray, method: int) -> float:
-    """One discount factor from node arrays (x, d) - interpolator.py:69-170.
+def node_df(t: float, times: np.ndarray, dfs: np.ndarray, method: int) -> float:
+    """One discount factor from node arrays (times, dfs) - interpolator.py:69-170.
 
     The bracket is the first node at or after t, found from the front (curves bootstrapped by the reference carry node times
     that differ by an ulp); past the last node the last segment extrapolates.  Index arithmetic is kept as the reference has
     it, including what it does for t before a first node that is not zero (the segment wraps to the last node)."""
+    x, d = times, dfs
     n = len(x)
     if t == x[0]:
         return d[0]
@@ -70,9 +71,9 @@ def _as_nodes(a):
     return np.asarray(a, dtype=np.float64)
 
 
-def _vinterpolate(t_values, times, dfs, method):
-    x, d = _as_nodes(times), _as_nodes(dfs)
-    return np.array([node_df(float(u), x, d, method) for u in np.asarray(t_values, dtype=np.float64).ravel()])
+def _vinterpolate(xValues, xvector, dfs, method):
+    x, d = _as_nodes(xvector), _as_nodes(dfs)
+    return np.array([node_df(float(u), x, d, method) for u in np.asarray(xValues, dtype=np.float64).ravel()])
 
 
 def interpolate(t, times, dfs, method: int):
@@ -127,8 +128,8 @@ class Interpolator:
     def _uinterpolate(self, t, times, dfs, method):
         return node_df(float(t), _as_nodes(times), _as_nodes(dfs), method)
 
-    def _vinterpolate(self, t_values, times, dfs, method):
-        out = _vinterpolate(t_values, times, dfs, method)
+    def _vinterpolate(self, xValues, xvector, dfs, method):
+        out = _vinterpolate(xValues, xvector, dfs, method)
         return out.item() if out.size == 1 else out
 
     def simple_interpolate(self, t, times, dfs, method: int):

@@ -307,9 +307,9 @@ class Risk:
     """Multi-curve container: attribute access by curve name, call with a CurveTypes
     (cavour/requests/results.py:839-942)."""
 
-    def __init__(self, items, cross_gammas=None):
+    def __init__(self, ladders, cross_gammas=None):
         self._by_curve = {}
-        for it in items:
+        for it in ladders:
             name = it.curve_type.name
             if name in self._by_curve:
                 raise ValueError(f"Duplicate curve {name} in Risk")
@@ -333,11 +333,11 @@ class Risk:
         except KeyError:
             raise AttributeError(f"No risk for curve {name}")
 
-    def cross_gamma(self, c1: CurveTypes, c2: CurveTypes):
-        return self._cross_gammas.get((c1.name, c2.name), None)
+    def cross_gamma(self, curve_type_1: CurveTypes, curve_type_2: CurveTypes):
+        return self._cross_gammas.get((curve_type_1.name, curve_type_2.name), None)
 
-    def has_cross_gamma(self, c1: CurveTypes, c2: CurveTypes) -> bool:
-        return (c1.name, c2.name) in self._cross_gammas
+    def has_cross_gamma(self, curve_type_1: CurveTypes, curve_type_2: CurveTypes) -> bool:
+        return (curve_type_1.name, curve_type_2.name) in self._cross_gammas
 
     @property
     def all_cross_gammas(self) -> dict:

@@ -11,6 +11,8 @@ are the reference's path-A (curve.df) arithmetic kept for API parity.
 """
 from __future__ import annotations
 
+from enum import Enum
+
 from .dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
                     DayCountTypes, FrequencyTypes, Schedule)
 from .error import LibError
@@ -243,6 +245,14 @@ def _print_two_legs(first_title: str, first_leg, second_title: str, second_leg, 
         getattr(leg, method)()
 
 
+class FinCompoundingTypes(Enum):
+    """Overnight compounding conventions the reference names next to OIS (ois.py:62-66); the legs compound as COMPOUNDED."""
+    COMPOUNDED = 1
+    OVERNIGHT_COMPOUNDED_ANNUAL_RATE = 2
+    AVERAGED = 3
+    AVERAGED_DAILY = 4
+
+
 class OIS:
     """Overnight index swap: fixed leg against compounded overnight floating leg."""
 
@@ -282,10 +292,28 @@ class OIS:
         return Position(self, model)
 
     # --- non-AD path-A helpers (ois.py:209-320) ---
-    def value(self, value_dt: Date, ois_curve=None, discount_curve=None, first_fixing_rate=None):
-        discount_curve = discount_curve or ois_curve
-        return self._fixed_leg.value(value_dt, discount_curve) + \
+    def value(self, value_dt: Date, ois_curve=None, discount_curve=None, xccy_discount_curve=None, spot_fx: float = None,
+              collateral_type=None, first_fixing_rate=None):
+        """Non-AD PV (ois.py:209-272): both legs discounted on `discount_curve` (default: the projection curve `ois_curve`);
+        with a collateral type in another currency the legs are discounted on `xccy_discount_curve` and the PV is converted
+        into the collateral currency as `value / spot_fx`."""
+        from .global_types import collateral_to_currency
+        if discount_curve is None and collateral_type is None:
+            discount_curve = ois_curve
+        foreign_collateral = False
+        if collateral_type is not None:
+            collateral_ccy = collateral_to_currency(collateral_type)
+            foreign_collateral = collateral_ccy != self._currency
+            if foreign_collateral:
+                if xccy_discount_curve is None or spot_fx is None:
+                    raise ValueError(f"xccy_discount_curve and spot_fx required for {self._currency.name} swap with "
+                                     f"{collateral_ccy.name} collateral")
+                discount_curve = xccy_discount_curve
+            else:
+                discount_curve = ois_curve
+        value = self._fixed_leg.value(value_dt, discount_curve) + \
             self._float_leg.value(value_dt, discount_curve, ois_curve, first_fixing_rate)
+        return value / spot_fx if (foreign_collateral and spot_fx is not None) else value
 
     def pv01(self, value_dt, discount_curve):
         pv = self._fixed_leg.value(value_dt, discount_curve)

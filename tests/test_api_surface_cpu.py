@@ -1,0 +1,142 @@
+"""The public surface of the reference modules on or next to the path - class names, enum members, methods, functions and
+the NAMES / order / optionality of their parameters (tests/golden/ref_api_names.json, read with `ast` from the unmodified
+reference by tests/golden/gen/make_api_names.py) - against this package: a user of the reference who calls by keyword or by
+position finds the same names here.  What is deliberately not mirrored is listed in EXCLUDED with the reason."""
+import enum
+import importlib
+import inspect
+
+import pytest
+
+from tests.conftest import load_golden
+
+# reference module -> modules of this package searched for its names, in order
+HOME = {
+    "cavour/utils/date.py": ["dates"], "cavour/utils/calendar.py": ["dates"], "cavour/utils/day_count.py": ["dates"],
+    "cavour/utils/schedule.py": ["dates"], "cavour/utils/frequency.py": ["dates"], "cavour/utils/global_types.py": ["global_types"],
+    "cavour/utils/currency.py": ["global_types"], "cavour/utils/error.py": ["error"],
+    "cavour/market/curves/interpolator.py": ["interpolator", "global_types"], "cavour/market/curves/discount_curve.py": ["curves"],
+    "cavour/market/curves/inflation_curve.py": ["inflation"], "cavour/market/indices/inflation_index.py": ["inflation"],
+    "cavour/market/position/position.py": ["position"], "cavour/market/portfolio/portfolio.py": ["position"],
+    "cavour/requests/results.py": ["results", "cashflows"], "cavour/models/models.py": ["models"],
+    "cavour/trades/rates/ois.py": ["trades"], "cavour/trades/rates/ois_curve.py": ["curves"],
+    "cavour/trades/rates/swap_fixed_leg.py": ["trades"], "cavour/trades/rates/swap_float_leg.py": ["trades"],
+    "cavour/trades/rates/xccy_basis_swap.py": ["trades"], "cavour/trades/rates/xccy_curve.py": ["xccy_curve"],
+    "cavour/trades/rates/xccy_fix_float_swap.py": ["trades"], "cavour/trades/rates/xccy_fix_fix_swap.py": ["trades"],
+    "cavour/trades/rates/zcis.py": ["inflation"], "cavour/trades/rates/swap_inflation_leg.py": ["inflation"],
+    "cavour/trades/rates/yoy_inflation_swap.py": ["inflation"], "cavour/trades/rates/swap_yoy_inflation_leg.py": ["inflation"],
+    "cavour/trades/credit/bond.py": ["credit"], "cavour/trades/credit/frn.py": ["credit"],
+}
+
+# names of the reference that are not mirrored, with the reason (checked: every entry must exist in the reference table)
+EXCLUDED = {
+    # internals of the reference's date counter / its own test hook
+    "cavour/utils/date.py": {"parse_dt", "calculate_list", "date_index", "date_from_index", "weekday", "vectorisation_helper",
+                             "test_type", "Date._refresh", "Date._print"},
+    # the per-country rule chains: evaluated once into day-serial tables (adrates_b200/holidays.py)
+    "cavour/utils/calendar.py": {"Calendar.holiday_" + c for c in (
+        "weekend", "australia", "united_kingdom", "france", "sweden", "germany", "switzerland", "japan", "new_zealand", "norway",
+        "united_states", "canada", "italy", "target", "none")},
+    "cavour/utils/schedule.py": {"Schedule._print"},
+    # bootstraps: one planner + device kernels replace the host builders (curves.py, xccy_curve.py, inflation.py)
+    "cavour/trades/rates/ois_curve.py": {"OISCurve._prepare_curve_builder_inputs", "OISCurve._build_curve_ad", "OISCurve._build_curve"},
+    "cavour/trades/rates/xccy_curve.py": {"XccyCurve._prepare_curve_builder_inputs", "XccyCurve._build_curve", "XccyCurve._build_curve_ad",
+                                          "XccyCurve._prepare_ad_inputs", "XccyCurve._run_jax_bootstrap", "XccyCurve._run_jax_bootstrap_impl"},
+    "cavour/market/curves/inflation_curve.py": {"InflationCurve._prepare_curve_builder_inputs", "InflationCurve._build_curve",
+                                                "InflationCurve._build_curve_ad"},
+    "cavour/market/curves/discount_curve.py": {"DiscountCurve._df_ad", "DiscountCurve._linear_forward_interp", "DiscountCurve._print"},
+    # Bloomberg market data
+    "cavour/models/models.py": {"Model.prebuilt_curve", "Model.prebuilt_fx", "Model.prebuilt_xccy_curve"},
+    # Plotly figures
+    "cavour/requests/results.py": {"Gamma.plot", "CrossGamma.plot"},
+}
+PRINTERS = ("_print", "print_payments", "print_valuation")     # console reports: offered for legs and swaps, not for every class
+
+
+def _find(ref_module, name):
+    for m in HOME[ref_module]:
+        mod = importlib.import_module("adrates_b200." + m)
+        if hasattr(mod, name):
+            return getattr(mod, name)
+    return None
+
+
+def _params(obj):
+    try:
+        sig = inspect.signature(obj)
+    except (TypeError, ValueError):
+        return None
+    return [p for p in sig.parameters.values()]
+
+
+def _check_signature(where, ref_params, ours, problems):
+    ours = _params(ours)
+    if ours is None:
+        return
+    ref = [p for p in ref_params if p["name"] not in ("self", "cls") and not p["name"].startswith("*")]
+    mine = [p for p in ours if p.name not in ("self", "cls") and p.kind not in (p.VAR_POSITIONAL, p.VAR_KEYWORD)]
+    names = [p.name for p in mine]
+    for i, rp in enumerate(ref):
+        if i >= len(names) or names[i] != rp["name"]:
+            problems.append(f"{where}: parameter {i} is '{names[i] if i < len(names) else None}', reference '{rp['name']}'")
+            return
+        if rp["default"] and mine[i].default is inspect.Parameter.empty:
+            problems.append(f"{where}: parameter '{rp['name']}' is optional in the reference")
+    for p in mine[len(ref):]:
+        if p.default is inspect.Parameter.empty:
+            problems.append(f"{where}: extra required parameter '{p.name}'")
+
+
+def test_public_surface_matches_reference():
+    table = load_golden("ref_api_names.json")
+    problems, seen_excluded = [], set()
+    for ref_module, spec in sorted(table.items()):
+        skip = EXCLUDED.get(ref_module, set())
+        for fname, f in spec["functions"].items():
+            if fname.startswith("_") and fname not in ("_uinterpolate", "_vinterpolate"):
+                continue
+            if fname in skip:
+                seen_excluded.add((ref_module, fname))
+                continue
+            ours = _find(ref_module, fname)
+            if ours is None:
+                problems.append(f"{ref_module}: function {fname} missing")
+            else:
+                _check_signature(f"{ref_module}:{fname}", f["params"], ours, problems)
+        for cname, c in spec["classes"].items():
+            if cname in skip:
+                seen_excluded.add((ref_module, cname))
+                continue
+            cls = _find(ref_module, cname)
+            if cls is None:
+                problems.append(f"{ref_module}: class {cname} missing")
+                continue
+            if inspect.isclass(cls) and issubclass(cls, enum.Enum):
+                missing = [m for m in c["assigned"] if m not in cls.__members__]
+                if missing:
+                    problems.append(f"{ref_module}: enum {cname} lacks {missing}")
+                continue
+            for mname, m in c["methods"].items():
+                key = f"{cname}.{mname}"
+                if key in skip:
+                    seen_excluded.add((ref_module, key))
+                    continue
+                if mname.startswith("__") and mname != "__init__":
+                    continue
+                if mname in PRINTERS and not hasattr(cls, mname):
+                    continue
+                if not hasattr(cls, mname):
+                    problems.append(f"{ref_module}: {key} missing")
+                    continue
+                attr = inspect.getattr_static(cls, mname)
+                if m["property"]:
+                    if not isinstance(attr, property):
+                        problems.append(f"{ref_module}: {key} is a property in the reference")
+                    continue
+                if isinstance(attr, property):
+                    problems.append(f"{ref_module}: {key} is a method in the reference, a property here")
+                    continue
+                _check_signature(f"{ref_module}:{key}", m["params"], getattr(cls, mname), problems)
+    assert not problems, "\n".join(problems)
+    stale = {(m, n) for m, names in EXCLUDED.items() for n in names} - seen_excluded
+    assert not stale, f"EXCLUDED lists names the reference does not have: {sorted(stale)}"
