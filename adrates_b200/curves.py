@@ -179,6 +179,9 @@ class DiscountCurve:
         self._df_dts = df_dts
         self._freq_type = FrequencyTypes.CONTINUOUS
         self._dc_type = DayCountTypes.ACT_ACT_ISDA
+        from .interpolator import Interpolator
+        self._interpolator = Interpolator(self._interp_type)
+        self._interpolator.fit(self._times, self._dfs)
 
     def df(self, dt, day_count=DayCountTypes.ACT_ACT_ISDA):
         times = times_from_dates(dt, self._value_dt, day_count)

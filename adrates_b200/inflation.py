@@ -162,6 +162,7 @@ class InflationCurve(DiscountCurve):
         self._dfs = np.array([1.0] + [(1.0 + r) ** t for t, r in zip(self.swap_times, rates)])
         if not all(self._times[i] < self._times[i + 1] for i in range(len(self._times) - 1)):
             raise LibError("Pillar times must be strictly increasing")
+        self._check_refit = check_refit
         if check_refit:
             self._check_refits(1e-10)
 
@@ -216,6 +217,7 @@ class SwapInflationLeg:
         self._inflation_index = inflation_index
         self._notional = notional
         self._payment_lag = payment_lag
+        self._cal_type, self._bd_type = cal_type, bd_type
         self._base_cpi_ref_dt = effective_dt
         self._final_cpi_ref_dt = self._maturity_dt
         self._base_index = self._final_index = self._inflation_return = self._payment_amount = None

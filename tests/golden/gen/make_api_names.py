@@ -44,6 +44,24 @@ def is_property(fn):
     return any(isinstance(d, ast.Name) and d.id == "property" for d in fn.decorator_list)
 
 
+def self_attrs(cls: ast.ClassDef):
+    """Attributes the constructor leaves on the object: `self.x = ...` in __init__ and in the schedule generators it calls."""
+    names = set()
+    for sub in cls.body:
+        if isinstance(sub, ast.FunctionDef) and (sub.name == "__init__" or "generate" in sub.name):
+            for node in ast.walk(sub):
+                targets = []
+                if isinstance(node, ast.Assign):
+                    targets = node.targets
+                elif isinstance(node, (ast.AugAssign, ast.AnnAssign)):
+                    targets = [node.target]
+                for t in targets:
+                    for leaf in ast.walk(t):
+                        if isinstance(leaf, ast.Attribute) and isinstance(leaf.value, ast.Name) and leaf.value.id == "self":
+                            names.add(leaf.attr)
+    return sorted(names)
+
+
 def main():
     out = {}
     for rel in MODULES:
@@ -58,7 +76,7 @@ def main():
                     elif isinstance(sub, ast.Assign) and all(isinstance(t, ast.Name) for t in sub.targets):
                         enum_members += [t.id for t in sub.targets]
                 mod["classes"][node.name] = {"methods": members, "assigned": enum_members,
-                                             "bases": [ast.unparse(b) for b in node.bases]}
+                                             "bases": [ast.unparse(b) for b in node.bases], "init_attrs": self_attrs(node)}
             elif isinstance(node, ast.FunctionDef):
                 mod["functions"][node.name] = {"params": signature(node)}
         out[rel] = mod

@@ -140,3 +140,85 @@ def test_public_surface_matches_reference():
     assert not problems, "\n".join(problems)
     stale = {(m, n) for m, names in EXCLUDED.items() for n in names} - seen_excluded
     assert not stale, f"EXCLUDED lists names the reference does not have: {sorted(stale)}"
+
+
+def _samples():
+    """One instance of every class of the table that can be built without a device."""
+    import numpy as np
+    from adrates_b200 import (Bond, BusDayAdjustTypes, Calendar, CalendarTypes, CurrencyTypes, CurveTypes, Date, DayCount, DayCountTypes,
+                              DiscountCurve, FRN, FrequencyTypes, InflationCurve, InflationIndex, InflationIndexTypes, InterpTypes,
+                              LibError, Model, OIS, Portfolio, Schedule, SwapFixedLeg, SwapFloatLeg, SwapInflationLeg,
+                              SwapTypes, SwapYoYInflationLeg, XccyBasisSwap, XccyCurve, XccyFixFix, XccyFixFloat, YoYInflationSwap,
+                              ZeroCouponInflationSwap)
+    from adrates_b200.interpolator import Interpolator
+    from adrates_b200.models import CurveAccessor
+    from adrates_b200.results import AnalyticsResult, Ladder, Risk
+    from adrates_b200.cashflows import Cashflows
+    vd = Date(30, 4, 2024)
+    gbp, usd = CurveTypes.GBP_OIS_SONIA, CurveTypes.USD_OIS_SOFR
+    ois = OIS(vd, "5Y", SwapTypes.PAY, 0.04, FrequencyTypes.ANNUAL, DayCountTypes.ACT_365F, gbp, CurrencyTypes.GBP)
+    xkw = dict(domestic_freq_type=FrequencyTypes.ANNUAL, foreign_freq_type=FrequencyTypes.ANNUAL, domestic_dc_type=DayCountTypes.ACT_365F,
+               foreign_dc_type=DayCountTypes.ACT_360, domestic_floating_index=gbp, foreign_floating_index=usd,
+               domestic_currency=CurrencyTypes.GBP, foreign_currency=CurrencyTypes.USD)
+    basis = XccyBasisSwap(vd, "2Y", 790_000.0, 1_000_000.0, 0.0, 0.002, **xkw)
+    model = Model(vd)
+    for name, dc, px in (("GBP_OIS_SONIA", DayCountTypes.ACT_365F, [4.5, 4.4, 4.3]), ("USD_OIS_SOFR", DayCountTypes.ACT_360, [5.2, 5.1, 5.0])):
+        model.build_curve(name=name, px_list=px, tenor_list=["1Y", "2Y", "3Y"], spot_days=0, swap_type=SwapTypes.PAY, fixed_dcc_type=dc,
+                          fixed_freq_type=FrequencyTypes.ANNUAL, float_freq_type=FrequencyTypes.ANNUAL, float_dc_type=dc,
+                          bus_day_type=BusDayAdjustTypes.MODIFIED_FOLLOWING, interp_type=InterpTypes.FLAT_FWD_RATES)
+    index = InflationIndex(InflationIndexTypes.UK_RPI, Date(1, 1, 2024), 290.0, CurrencyTypes.GBP)
+    zcis = ZeroCouponInflationSwap(vd, "5Y", SwapTypes.PAY, 0.03, index)
+    yoy = YoYInflationSwap(vd, "5Y", SwapTypes.PAY, 0.03, index, FrequencyTypes.ANNUAL)
+    fit = Interpolator(InterpTypes.FLAT_FWD_RATES)
+    return {
+        "Date": vd, "Calendar": Calendar(CalendarTypes.WEEKEND), "DayCount": DayCount(DayCountTypes.ACT_360),
+        "Schedule": Schedule(vd, vd.add_tenor("2Y")), "LibError": LibError("x"), "Interpolator": fit,
+        "DiscountCurve": DiscountCurve(vd, [1.0, 2.0], np.array([0.95, 0.9])), "OISCurve": model.curves.GBP_OIS_SONIA,
+        "CurveAccessor": CurveAccessor({}), "OIS": ois, "SwapFixedLeg": ois._fixed_leg, "SwapFloatLeg": ois._float_leg,
+        "XccyBasisSwap": basis, "XccyFixFloat": XccyFixFloat(vd, "2Y", 790_000.0, 1_000_000.0, SwapTypes.PAY, 0.04, 0.001, **xkw),
+        "XccyFixFix": XccyFixFix(vd, "2Y", 790_000.0, 1_000_000.0, SwapTypes.PAY, 0.04, 0.05, **xkw),
+        "XccyCurve": XccyCurve(vd, [basis], model.curves.GBP_OIS_SONIA, model.curves.USD_OIS_SOFR, 0.79),
+        "Bond": Bond(vd, "5Y", 0.04, FrequencyTypes.ANNUAL, DayCountTypes.ACT_365F, CurrencyTypes.GBP),
+        "FRN": FRN(vd, "3Y", 0.002, FrequencyTypes.QUARTERLY, DayCountTypes.ACT_365F, CurrencyTypes.GBP, gbp),
+        "InflationIndex": index, "ZeroCouponInflationSwap": zcis, "SwapInflationLeg": zcis._inflation_leg,
+        "InflationCurve": InflationCurve(vd, [zcis, ZeroCouponInflationSwap(vd, "10Y", SwapTypes.PAY, 0.032, index)], 293.8,
+                                         CurrencyTypes.GBP, InflationIndexTypes.UK_RPI),
+        "YoYInflationSwap": yoy, "SwapYoYInflationLeg": yoy._inflation_leg, "Portfolio": Portfolio([]),
+        "Position": ois.position(model), "AnalyticsResult": AnalyticsResult(), "Risk": Risk([]), "Ladder": Ladder({}, "c"),
+        "Cashflows": Cashflows([], CurrencyTypes.GBP),
+    }
+
+
+# constructor attributes of the reference that this package does not keep, with the reason
+ATTRS_NOT_KEPT = {
+    "Date": {"_excel_dt"},                                        # excel_dt() computes it from the day serial
+    "Position": {"_engine"},                                      # the engine is made per compute() call (its curve cache is the device session)
+    "XccyCurve": {"_use_ad", "_interpolator"},                    # one bootstrap (planner + exact tangents); node look-ups are functions of (_times, _dfs)
+    "SwapFixedLeg": {"_payment_dts_ad"}, "SwapFloatLeg": {"_payment_dts_ad", "_payment_dts_float"},   # float-year copies for jax tracing
+    "Schedule": {"_adjust_termination_dt", "_first_dt", "_next_to_last_dt"},   # stub-date options the reference stores and never uses
+    "FRN": {"_rates", "_coupon_payments", "_payment_dfs", "_payment_pvs"},     # empty until value() fills them (credit_analytics.py)
+    "LibError": set(),
+}
+
+
+def test_constructor_attributes_match_reference():
+    """Every attribute the reference's constructors (and the schedule generators they call) leave on an object exists on ours:
+    code that reads `swap._fixed_leg._payment_dts`, `curve._times`, `leg._year_fracs` ... keeps working."""
+    table = load_golden("ref_api_names.json")
+    samples = _samples()
+    missing, checked = [], 0
+    for spec in table.values():
+        for cname, c in spec["classes"].items():
+            if not c["init_attrs"]:
+                continue
+            assert cname in samples, f"no sample instance for {cname}"
+            skip = ATTRS_NOT_KEPT.get(cname, set())
+            assert skip <= set(c["init_attrs"]), (cname, skip - set(c["init_attrs"]))
+            for a in c["init_attrs"]:
+                if a in skip:
+                    continue
+                checked += 1
+                if not hasattr(samples[cname], a):
+                    missing.append(f"{cname}.{a}")
+    assert not missing, missing
+    assert checked > 300
