@@ -16,6 +16,7 @@ from __future__ import annotations
 from .dates import (BusDayAdjustTypes, Calendar, CalendarTypes, Date, DateGenRuleTypes, DayCount, DayCountTypes,
                     FrequencyTypes, Schedule)
 from .credit_analytics import BondAnalytics, FRNAnalytics
+from .argcheck import check_argument_types
 from .error import LibError
 from .global_types import CurrencyTypes, CurveTypes, InstrumentTypes
 
@@ -25,11 +26,12 @@ BOND_CURVE = {CurrencyTypes.GBP: CurveTypes.GBP_OIS_SONIA, CurrencyTypes.USD: Cu
 
 
 class Bond(BondAnalytics):
-    def __init__(self, issue_dt: Date, maturity_dt_or_tenor, coupon: float, freq_type: FrequencyTypes,
+    def __init__(self, issue_dt: Date, maturity_dt_or_tenor: (Date, str), coupon: float, freq_type: FrequencyTypes,
                  dc_type: DayCountTypes, currency: CurrencyTypes, face_value: float = 100.0, payment_lag: int = 0,
-                 amortization_schedule=None, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
+                 amortization_schedule: (list, type(None)) = None, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
                  bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
                  dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         self.derivative_type = InstrumentTypes.BOND
         self._maturity_dt = maturity_dt_or_tenor if isinstance(maturity_dt_or_tenor, Date) \
             else issue_dt.add_tenor(maturity_dt_or_tenor)
@@ -101,11 +103,13 @@ class Bond(BondAnalytics):
 
 
 class FRN(FRNAnalytics):
-    def __init__(self, issue_dt: Date, maturity_dt_or_tenor, quoted_margin: float, freq_type: FrequencyTypes,
+    def __init__(self, issue_dt: Date, maturity_dt_or_tenor: (Date, str), quoted_margin: float, freq_type: FrequencyTypes,
                  dc_type: DayCountTypes, currency: CurrencyTypes, floating_index: CurveTypes, face_value: float = 100.0,
-                 payment_lag: int = 0, cap_rate=None, floor_rate=None, first_fixing_rate=None,
+                 payment_lag: int = 0, cap_rate: (float, type(None)) = None, floor_rate: (float, type(None)) = None,
+                 first_fixing_rate: (float, type(None)) = None,
                  cal_type: CalendarTypes = CalendarTypes.WEEKEND, bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
                  dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         self._issue_dt = issue_dt
         self._quoted_margin = quoted_margin
         self._freq_type = freq_type

@@ -25,6 +25,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from .dates import Date, DayCount, DayCountTypes, FrequencyTypes, annual_frequency, times_from_dates
+from .argcheck import check_argument_types
 from .error import LibError
 from .global_types import InterpTypes
 
@@ -153,10 +154,11 @@ class DiscountCurve:
     _dfs: np.ndarray
     _interp_type: InterpTypes
 
-    def __init__(self, value_dt: Date, df_dts: list, df_values, interp_type: InterpTypes = InterpTypes.FLAT_FWD_RATES):
+    def __init__(self, value_dt: Date, df_dts: list, df_values: np.ndarray, interp_type: InterpTypes = InterpTypes.FLAT_FWD_RATES):
         """Curve from year offsets and discount factors (discount_curve.py:40-93): offsets become dates with
         `add_years`, times are ACT/365 from the value date, (0, 1) is prepended unless the first date is the
         value date."""
+        check_argument_types(self.__init__, locals())
         if len(df_dts) < 1:
             raise LibError("Times has zero length")
         if len(df_dts) != len(df_values):
@@ -342,6 +344,7 @@ class OISCurve(DiscountCurve):
 
     def __init__(self, value_dt: Date, ois_swaps: list, interp_type: InterpTypes = InterpTypes.FLAT_FWD_RATES,
                  check_refit: bool = False):
+        check_argument_types(self.__init__, locals())
         if not isinstance(value_dt, Date):
             raise LibError("value_dt must be a Date")
         if not ois_swaps:

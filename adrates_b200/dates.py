@@ -18,6 +18,7 @@ from __future__ import annotations
 import math
 from enum import Enum
 
+from .argcheck import check_argument_types
 from .error import LibError
 
 _MONTH_DAYS = (31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31)
@@ -637,6 +638,7 @@ class Schedule:
                  dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  adjust_termination_dt: bool = True, end_of_month: bool = False,
                  first_dt=None, next_to_last_dt=None):
+        check_argument_types(self.__init__, locals())
         if effective_dt >= termination_dt:
             raise LibError("Effective date must be before termination date.")
         self._effective_dt = effective_dt

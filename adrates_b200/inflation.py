@@ -18,7 +18,9 @@ from typing import Dict, Optional
 import numpy as np
 
 from .curves import DiscountCurve
-from .dates import BusDayAdjustTypes, Calendar, CalendarTypes, Date, DayCount, DayCountTypes, times_from_dates
+from .dates import (BusDayAdjustTypes, Calendar, CalendarTypes, Date, DateGenRuleTypes, DayCount, DayCountTypes, FrequencyTypes,
+                    times_from_dates)
+from .argcheck import check_argument_types
 from .error import LibError
 from .global_types import (CurrencyTypes, InflationIndexTypes, InflationInterpTypes, InstrumentTypes, InterpTypes, ONE_MILLION,
                            SwapTypes)
@@ -31,6 +33,7 @@ class InflationIndex:
     def __init__(self, index_type: InflationIndexTypes, base_date: Date, base_index: float, currency: CurrencyTypes,
                  lag_months: int = 3, interp_type: InflationInterpTypes = InflationInterpTypes.LINEAR,
                  seasonality_factors: Optional[Dict[int, float]] = None):
+        check_argument_types(self.__init__, locals())
         if base_index <= 0.0:
             raise LibError("Base index must be positive")
         if lag_months < 0:
@@ -135,6 +138,7 @@ class InflationCurve(DiscountCurve):
                  index_type: InflationIndexTypes, discount_curve: DiscountCurve = None,
                  interp_type: InflationInterpTypes = InflationInterpTypes.LINEAR,
                  dc_type: DayCountTypes = DayCountTypes.ACT_365F, check_refit: bool = False):
+        check_argument_types(self.__init__, locals())
         if base_cpi <= 0.0:
             raise LibError("Base CPI must be positive")
         if len(zcis_instruments) < 2:
@@ -206,9 +210,10 @@ def _maturity_and_payment(effective_dt, end, payment_lag, cal_type, bd_type):
 class SwapInflationLeg:
     """Single inflation-linked payment notional x [I(T - lag)/I(base - lag) - 1] (swap_inflation_leg.py:89-236)."""
 
-    def __init__(self, effective_dt: Date, end_dt, leg_type: SwapTypes, inflation_index: InflationIndex,
+    def __init__(self, effective_dt: Date, end_dt: (Date, str), leg_type: SwapTypes, inflation_index: InflationIndex,
                  notional: float = ONE_MILLION, payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
                  bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING):
+        check_argument_types(self.__init__, locals())
         self.instrument_type = InstrumentTypes.SWAP_INFLATION_LEG
         self._termination_dt, self._maturity_dt, self._payment_dt = _maturity_and_payment(
             effective_dt, end_dt, payment_lag, cal_type, bd_type)
@@ -245,10 +250,11 @@ class SwapInflationLeg:
 class ZeroCouponInflationSwap:
     """Fixed compounded return against cumulative inflation, one payment at maturity (zcis.py:79-238)."""
 
-    def __init__(self, effective_dt: Date, term_dt_or_tenor, fixed_leg_type: SwapTypes, fixed_rate: float,
+    def __init__(self, effective_dt: Date, term_dt_or_tenor: (Date, str), fixed_leg_type: SwapTypes, fixed_rate: float,
                  inflation_index: InflationIndex, notional: float = ONE_MILLION, payment_lag: int = 0,
                  dc_type: DayCountTypes = DayCountTypes.ACT_365F, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
                  bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING):
+        check_argument_types(self.__init__, locals())
         self.instrument_type = InstrumentTypes.ZCIS
         self.derivative_type = InstrumentTypes.ZCIS
         self._termination_dt, self._maturity_dt, self._payment_dt = _maturity_and_payment(
@@ -301,11 +307,12 @@ class SwapYoYInflationLeg:
     (cavour/trades/rates/swap_yoy_inflation_leg.py:95-262).  Schedule only; valuation and Greeks go through
     Position.compute -> yoy_engine (Engine._compute_yoy_iis)."""
 
-    def __init__(self, effective_dt: Date, end_dt, leg_type: SwapTypes, inflation_index: InflationIndex,
-                 freq_type, dc_type: DayCountTypes, notional: float = ONE_MILLION, spread: float = 0.0,
+    def __init__(self, effective_dt: Date, end_dt: (Date, str), leg_type: SwapTypes, inflation_index: InflationIndex,
+                 freq_type: FrequencyTypes, dc_type: DayCountTypes, notional: float = ONE_MILLION, spread: float = 0.0,
                  payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
-                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING, dg_type=None, end_of_month: bool = False):
-        from .dates import DateGenRuleTypes, Schedule
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         self.instrument_type = InstrumentTypes.SWAP_YOY_INFLATION_LEG
         self._termination_dt = end_dt if isinstance(end_dt, Date) else effective_dt.add_tenor(end_dt)
         cal = Calendar(cal_type)
@@ -374,12 +381,13 @@ class YoYInflationSwap:
     """Fixed coupons against year-on-year inflation coupons on one schedule
     (cavour/trades/rates/yoy_inflation_swap.py:85-220)."""
 
-    def __init__(self, effective_dt: Date, term_dt_or_tenor, fixed_leg_type: SwapTypes, fixed_rate: float,
-                 inflation_index: InflationIndex, freq_type, notional: float = ONE_MILLION,
+    def __init__(self, effective_dt: Date, term_dt_or_tenor: (Date, str), fixed_leg_type: SwapTypes, fixed_rate: float,
+                 inflation_index: InflationIndex, freq_type: FrequencyTypes, notional: float = ONE_MILLION,
                  inflation_spread: float = 0.0, dc_type: DayCountTypes = DayCountTypes.ACT_365F, payment_lag: int = 0,
                  cal_type: CalendarTypes = CalendarTypes.WEEKEND,
-                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING, dg_type=None, end_of_month: bool = False):
-        from .dates import DateGenRuleTypes
+                 bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
+                 dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         from .global_types import CurveTypes
         from .trades import SwapFixedLeg
         dg_type = dg_type or DateGenRuleTypes.BACKWARD

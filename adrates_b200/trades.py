@@ -15,6 +15,7 @@ from enum import Enum
 
 from .dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
                     DayCountTypes, FrequencyTypes, Schedule)
+from .argcheck import check_argument_types
 from .error import LibError
 from .global_types import SwapTypes, InstrumentTypes, CurveTypes, CurrencyTypes, ONE_MILLION
 
@@ -83,12 +84,13 @@ class _SwapLeg:
 
 
 class SwapFixedLeg(_SwapLeg):
-    def __init__(self, effective_dt: Date, end_dt, leg_type: SwapTypes, coupon: float,
+    def __init__(self, effective_dt: Date, end_dt: (Date, str), leg_type: SwapTypes, coupon: float,
                  freq_type: FrequencyTypes, dc_type: DayCountTypes, floating_index: CurveTypes,
                  currency: CurrencyTypes, notional: float = ONE_MILLION, principal: float = 0.0,
                  payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
                  bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
                  dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         self.intrument_type = InstrumentTypes.SWAP_FIXED_LEG
         self._init_common(effective_dt, end_dt, leg_type, freq_type, dc_type, floating_index, currency,
                           notional, payment_lag, cal_type, bd_type, dg_type, end_of_month, "Effective")
@@ -148,13 +150,14 @@ class SwapFixedLeg(_SwapLeg):
 
 
 class SwapFloatLeg(_SwapLeg):
-    def __init__(self, effective_dt: Date, end_dt, leg_type: SwapTypes, spread: float,
+    def __init__(self, effective_dt: Date, end_dt: (Date, str), leg_type: SwapTypes, spread: float,
                  freq_type: FrequencyTypes, dc_type: DayCountTypes, floating_index: CurveTypes,
                  currency: CurrencyTypes, notional: float = ONE_MILLION, principal: float = 0.0,
                  payment_lag: int = 0, cal_type: CalendarTypes = CalendarTypes.WEEKEND,
                  bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
                  dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD, end_of_month: bool = False,
                  notional_exchange: bool = False):
+        check_argument_types(self.__init__, locals())
         self.intrument_type = InstrumentTypes.SWAP_FLOAT_LEG
         self._init_common(effective_dt, end_dt, leg_type, freq_type, dc_type, floating_index, currency,
                           notional, payment_lag, cal_type, bd_type, dg_type, end_of_month, "Start")
@@ -256,7 +259,7 @@ class FinCompoundingTypes(Enum):
 class OIS:
     """Overnight index swap: fixed leg against compounded overnight floating leg."""
 
-    def __init__(self, effective_dt: Date, term_dt_or_tenor, fixed_leg_type: SwapTypes, fixed_coupon: float,
+    def __init__(self, effective_dt: Date, term_dt_or_tenor: (Date, str), fixed_leg_type: SwapTypes, fixed_coupon: float,
                  fixed_freq_type: FrequencyTypes, fixed_dc_type: DayCountTypes, floating_index: CurveTypes,
                  currency: CurrencyTypes, notional: float = ONE_MILLION, payment_lag: int = 0,
                  float_spread: float = 0.0, float_freq_type: FrequencyTypes = FrequencyTypes.ANNUAL,
@@ -264,6 +267,7 @@ class OIS:
                  cal_type: CalendarTypes = CalendarTypes.WEEKEND,
                  bd_type: BusDayAdjustTypes = BusDayAdjustTypes.FOLLOWING,
                  dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD):
+        check_argument_types(self.__init__, locals())
         if not isinstance(fixed_leg_type, SwapTypes):
             raise LibError("fixed_leg_type must be a SwapTypes")
         self.derivative_type = InstrumentTypes.OIS_SWAP
@@ -344,7 +348,7 @@ class XccyBasisSwap:
     """Cross-currency basis swap: receive domestic floating, pay foreign floating + basis spread,
     notionals exchanged at start and maturity (cavour/trades/rates/xccy_basis_swap.py:67-205)."""
 
-    def __init__(self, effective_dt: Date, term_dt_or_tenor, domestic_notional: float, foreign_notional: float,
+    def __init__(self, effective_dt: Date, term_dt_or_tenor: (Date, str), domestic_notional: float, foreign_notional: float,
                  domestic_spread: float, foreign_spread: float, domestic_freq_type: FrequencyTypes,
                  foreign_freq_type: FrequencyTypes, domestic_dc_type: DayCountTypes, foreign_dc_type: DayCountTypes,
                  domestic_floating_index: CurveTypes, foreign_floating_index: CurveTypes,
@@ -357,6 +361,7 @@ class XccyBasisSwap:
                  domestic_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  foreign_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  domestic_end_of_month: bool = False, foreign_end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         self.derivative_type = InstrumentTypes.XCCY_SWAP
         self._termination_dt = _resolve_end(effective_dt, term_dt_or_tenor)
         self._maturity_dt = Calendar(domestic_cal_type).adjust(self._termination_dt, domestic_bd_type)
@@ -475,7 +480,7 @@ class XccyFixFloat(_XccyFixedDomestic):
     (cavour/trades/rates/xccy_fix_float_swap.py:79-245).  The reference's engine route for cross-currency swaps reads
     floating-leg attributes off both legs (engine.py:1476-1511), so - there as here - Position.compute is for XccyBasisSwap."""
 
-    def __init__(self, effective_dt: Date, term_dt_or_tenor, domestic_notional: float, foreign_notional: float,
+    def __init__(self, effective_dt: Date, term_dt_or_tenor: (Date, str), domestic_notional: float, foreign_notional: float,
                  domestic_leg_type: SwapTypes, domestic_coupon: float, foreign_spread: float,
                  domestic_freq_type: FrequencyTypes, foreign_freq_type: FrequencyTypes, domestic_dc_type: DayCountTypes,
                  foreign_dc_type: DayCountTypes, domestic_floating_index: CurveTypes, foreign_floating_index: CurveTypes,
@@ -487,6 +492,7 @@ class XccyFixFloat(_XccyFixedDomestic):
                  domestic_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  foreign_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  domestic_end_of_month: bool = False, foreign_end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         foreign_leg_type = self._init_domestic(
             effective_dt, term_dt_or_tenor, domestic_notional, foreign_notional, domestic_leg_type, domestic_coupon,
             domestic_freq_type, domestic_dc_type, domestic_floating_index, foreign_floating_index, domestic_currency,
@@ -496,10 +502,11 @@ class XccyFixFloat(_XccyFixedDomestic):
                                          foreign_payment_lag, foreign_cal_type, foreign_bd_type, foreign_dg_type,
                                          foreign_end_of_month, True)
 
-    def value(self, value_dt: Date, domestic_discount_curve, foreign_discount_curve, xccy_discount_curve, spot_fx: float,
-              first_fixing_rate_foreign=None) -> float:
+    def value(self, value_dt: Date, domestic_discount_curve: DiscountCurve, foreign_discount_curve: DiscountCurve,
+              xccy_discount_curve: DiscountCurve, spot_fx: float, first_fixing_rate_foreign=None) -> float:
         """Domestic-currency PV: fixed leg and its notional exchanges on the domestic OIS curve, foreign floating leg (which
         carries its own exchanges) projected on the foreign OIS curve and discounted on the XCCY curve, divided by spot."""
+        check_argument_types(self.value, locals())
         foreign = self._foreign_leg.value(value_dt, xccy_discount_curve, foreign_discount_curve, first_fixing_rate_foreign)
         return self._domestic_value(value_dt, domestic_discount_curve) + foreign / spot_fx
 
@@ -508,7 +515,7 @@ class XccyFixFix(_XccyFixedDomestic):
     """Fixed coupons in both currencies, notionals exchanged on both legs; non-AD valuation only
     (cavour/trades/rates/xccy_fix_fix_swap.py:77-280)."""
 
-    def __init__(self, effective_dt: Date, term_dt_or_tenor, domestic_notional: float, foreign_notional: float,
+    def __init__(self, effective_dt: Date, term_dt_or_tenor: (Date, str), domestic_notional: float, foreign_notional: float,
                  domestic_leg_type: SwapTypes, domestic_coupon: float, foreign_coupon: float,
                  domestic_freq_type: FrequencyTypes, foreign_freq_type: FrequencyTypes, domestic_dc_type: DayCountTypes,
                  foreign_dc_type: DayCountTypes, domestic_floating_index: CurveTypes, foreign_floating_index: CurveTypes,
@@ -520,6 +527,7 @@ class XccyFixFix(_XccyFixedDomestic):
                  domestic_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  foreign_dg_type: DateGenRuleTypes = DateGenRuleTypes.BACKWARD,
                  domestic_end_of_month: bool = False, foreign_end_of_month: bool = False):
+        check_argument_types(self.__init__, locals())
         self._foreign_leg_type = self._init_domestic(
             effective_dt, term_dt_or_tenor, domestic_notional, foreign_notional, domestic_leg_type, domestic_coupon,
             domestic_freq_type, domestic_dc_type, domestic_floating_index, foreign_floating_index, domestic_currency,
@@ -529,9 +537,11 @@ class XccyFixFix(_XccyFixedDomestic):
                                          foreign_notional, 0.0, foreign_payment_lag, foreign_cal_type, foreign_bd_type,
                                          foreign_dg_type, foreign_end_of_month)
 
-    def value(self, value_dt: Date, domestic_discount_curve, foreign_discount_curve, xccy_discount_curve, spot_fx: float) -> float:
+    def value(self, value_dt: Date, domestic_discount_curve: DiscountCurve, foreign_discount_curve: DiscountCurve,
+              xccy_discount_curve: DiscountCurve, spot_fx: float) -> float:
         """Domestic-currency PV: each fixed leg with its notional exchanges, the domestic one on the domestic OIS curve, the
         foreign one on the XCCY curve (the foreign OIS curve is not used), foreign PV divided by spot."""
+        check_argument_types(self.value, locals())
         foreign = self._foreign_leg.value(value_dt, xccy_discount_curve) + _notional_exchange_pv(
             xccy_discount_curve, value_dt, self._effective_dt, self._maturity_dt, self._foreign_notional, self._foreign_leg_type)
         return self._domestic_value(value_dt, domestic_discount_curve) + foreign / spot_fx

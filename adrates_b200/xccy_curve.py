@@ -29,14 +29,17 @@ import numpy as np
 
 from .curves import DiscountCurve
 from .dates import Date, DayCountTypes, times_from_dates
+from .argcheck import check_argument_types
 from .error import LibError
 from .global_types import InterpTypes
 
 
 class XccyCurve(DiscountCurve):
-    def __init__(self, value_dt: Date, basis_swaps: list, domestic_curve, foreign_curve, spot_fx: float,
+    def __init__(self, value_dt: Date, basis_swaps: list, domestic_curve: DiscountCurve, foreign_curve: DiscountCurve,
+                 spot_fx: float,
                  interp_type: InterpTypes = InterpTypes.FLAT_FWD_RATES, check_refit: bool = False,
                  use_ad: bool = False):
+        check_argument_types(self.__init__, locals())
         if not basis_swaps:
             raise LibError("XccyCurve needs at least one basis swap")
         self._value_dt = value_dt

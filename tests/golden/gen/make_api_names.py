@@ -29,9 +29,13 @@ MODULES = [
 
 def signature(fn: ast.FunctionDef):
     a = fn.args
-    names = [x.arg for x in a.posonlyargs + a.args]
+    args = a.posonlyargs + a.args
+    names = [x.arg for x in args]
     n_default = len(a.defaults)
     out = [{"name": n, "default": i >= len(names) - n_default} for i, n in enumerate(names)]
+    for rec, x in zip(out, args):
+        if x.annotation is not None:
+            rec["ann"] = ast.unparse(x.annotation)
     out += [{"name": x.arg, "default": d is not None, "kwonly": True} for x, d in zip(a.kwonlyargs, a.kw_defaults)]
     if a.vararg:
         out.append({"name": "*" + a.vararg.arg})
@@ -72,7 +76,9 @@ def main():
                 members, enum_members = {}, []
                 for sub in node.body:
                     if isinstance(sub, ast.FunctionDef):
-                        members[sub.name] = {"params": signature(sub), "property": is_property(sub)}
+                        members[sub.name] = {"params": signature(sub), "property": is_property(sub),
+                                             "checks_types": any(isinstance(n, ast.Call) and getattr(n.func, "id", "") == "check_argument_types"
+                                                                 for n in ast.walk(sub))}
                     elif isinstance(sub, ast.Assign) and all(isinstance(t, ast.Name) for t in sub.targets):
                         enum_members += [t.id for t in sub.targets]
                 mod["classes"][node.name] = {"methods": members, "assigned": enum_members,

@@ -222,3 +222,44 @@ def test_constructor_attributes_match_reference():
                     missing.append(f"{cname}.{a}")
     assert not missing, missing
     assert checked > 300
+
+
+def test_argument_type_checks_match_reference():
+    """The constructors (and the two value() methods) that call `check_argument_types` in the reference do so here, over the
+    same annotations, with the same LibError("Argument Type Error") - helpers.py:618-636."""
+    from adrates_b200 import (CurrencyTypes, CurveTypes, Date, DayCountTypes, DiscountCurve, FrequencyTypes, LibError, OIS, Schedule,
+                              SwapTypes, Bond, FRN)
+    table = load_golden("ref_api_names.json")
+    n = 0
+    for ref_module, spec in table.items():
+        for cname, c in spec["classes"].items():
+            for mname, m in c["methods"].items():
+                if not m.get("checks_types"):
+                    continue
+                fn = getattr(_find(ref_module, cname), mname)
+                assert "check_argument_types(" in inspect.getsource(fn), f"{cname}.{mname} does not check its argument types"
+                ours = fn.__annotations__
+                for p in m["params"]:
+                    if "ann" in p:
+                        got = ours.get(p["name"])
+                        got = got if isinstance(got, str) else getattr(got, "__name__", str(got))
+                        assert (got or "").replace(" ", "") == p["ann"].replace(" ", ""), (cname, mname, p["name"], got, p["ann"])
+                n += 1
+    assert n == 20
+    vd = Date(30, 4, 2024)
+    ok = dict(effective_dt=vd, term_dt_or_tenor="5Y", fixed_leg_type=SwapTypes.PAY, fixed_coupon=0.04, fixed_freq_type=FrequencyTypes.ANNUAL,
+              fixed_dc_type=DayCountTypes.ACT_365F, floating_index=CurveTypes.GBP_OIS_SONIA, currency=CurrencyTypes.GBP)
+    OIS(**dict(ok, fixed_coupon=4, notional=1_000_000, term_dt_or_tenor=vd.add_tenor("5Y")))      # ints pass for floats, a Date for a tenor
+    for bad in (dict(effective_dt="2024-04-30"), dict(term_dt_or_tenor=5), dict(fixed_leg_type="PAY"), dict(fixed_coupon="4%"),
+                dict(fixed_freq_type=1), dict(currency="GBP"), dict(payment_lag=1.5), dict(notional=None)):
+        with pytest.raises(LibError, match="Argument Type Error"):
+            OIS(**dict(ok, **bad))
+    with pytest.raises(LibError, match="Argument Type Error"):
+        DiscountCurve(vd, [1.0, 2.0], [0.95, 0.9])                     # values must be an array, as in the reference
+    with pytest.raises(LibError, match="Argument Type Error"):
+        Schedule(vd, "5Y")
+    with pytest.raises(LibError, match="Argument Type Error"):
+        Bond(vd, "5Y", 0.04, FrequencyTypes.ANNUAL, DayCountTypes.ACT_365F, CurrencyTypes.GBP, amortization_schedule=(80.0, 60.0))
+    FRN(vd, "3Y", 0.002, FrequencyTypes.QUARTERLY, DayCountTypes.ACT_365F, CurrencyTypes.GBP, CurveTypes.GBP_OIS_SONIA, cap_rate=None)
+    with pytest.raises(LibError, match="Argument Type Error"):
+        FRN(vd, "3Y", 0.002, FrequencyTypes.QUARTERLY, DayCountTypes.ACT_365F, CurrencyTypes.GBP, CurveTypes.GBP_OIS_SONIA, cap_rate="5%")
