@@ -12,7 +12,6 @@ the path-A nodes (Interpolator._uinterpolate), runs on the device (`cav_cashflow
 """
 from __future__ import annotations
 
-from enum import Enum
 from typing import Dict, Optional
 
 import numpy as np
