@@ -115,7 +115,10 @@ class BondAnalytics:
         ytm = self.yield_to_maturity(settlement_dt, self.clean_price(settlement_dt, discount_curve, z_spread, settlement_dt))
         t, a = self._bullet_flows(settlement_dt)
         pv = a * np.exp(-ytm * t)
-        return float(np.sum(pv * t ** power) / np.sum(pv))
+        total = float(np.sum(pv))
+        if total == 0.0:                    # nothing left to pay after the settlement date: the reference divides by zero here
+            raise ZeroDivisionError("float division by zero")
+        return float(np.sum(pv * t ** power)) / total
 
     def duration(self, settlement_dt: Date, discount_curve, duration_type: str = "modified", z_spread: float = 0.0) -> float:
         """PV-weighted mean time of the flows at the bond's own yield (bond.py:648-701)."""

@@ -64,6 +64,10 @@ def test_bond_analytics_match_reference(setup):
             assert b.value(vd, c) == b.value(vd, c, 0.0, vd)          # settlement defaults to the value date
     with pytest.raises(ValueError, match="Unknown duration type"):
         b.duration(vd, c, "effective")
+    after = b._maturity_dt.add_days(5)                 # a matured bond: zero value, and the duration sums divide by zero as the reference's
+    assert b.value(vd, c, 0.0, after) == 0.0
+    with pytest.raises(ZeroDivisionError):
+        b.duration(after, c)
 
 
 def test_amortisation_schedules_match_reference(setup):
