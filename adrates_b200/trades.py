@@ -13,6 +13,8 @@ from __future__ import annotations
 
 from enum import Enum
 
+import numpy as np
+
 from .dates import (Date, Calendar, CalendarTypes, BusDayAdjustTypes, DateGenRuleTypes, DayCount,
                     DayCountTypes, FrequencyTypes, Schedule)
 from .argcheck import check_argument_types
@@ -321,7 +323,7 @@ class OIS:
 
     def pv01(self, value_dt, discount_curve):
         pv = self._fixed_leg.value(value_dt, discount_curve)
-        return abs(pv / self._fixed_leg._cpn / self._fixed_leg._notional * 100)
+        return np.abs(pv / self._fixed_leg._cpn / self._fixed_leg._notional * 100)   # a numpy float, so that swap_rate of a matured swap is nan, not an error - as in the reference
 
     def print_fixed_leg_pv(self):
         self._fixed_leg.print_valuation()
