@@ -7,7 +7,8 @@ INFRASTRUCTURE, nothing in tests/, smoke() or bench.py uses it.
     PYTHONPATH=tests/golden/gen/refshim:/root/reference python tools/reftests/differential_fuzz.py [seed]
 
 Covers Date arithmetic, DayCount.year_frac (all types, with and without the ICMA arguments), Schedule (all frequencies, rules,
-adjustments, holiday calendars), Calendar.adjust / add_business_days, Bond / FRN analytics, OIS / leg host values.
+adjustments, holiday calendars), Calendar.adjust / add_business_days, Bond / FRN analytics, OIS / leg host values, the path-A OIS
+bootstrap and the basis-curve bootstrap with its spread Jacobian.
 """
 import contextlib
 import io
@@ -33,6 +34,7 @@ from cavour.trades.credit.bond import Bond as RBond                             
 from cavour.trades.credit.frn import FRN as RFRN                                                          # noqa: E402
 from cavour.trades.rates.ois import OIS as ROIS                                                           # noqa: E402
 from cavour.trades.rates.swap_float_leg import SwapFloatLeg as RFloatLeg                                  # noqa: E402
+from cavour.models.models import Model as RModel                                                          # noqa: E402
 
 import adrates_b200 as O                                                                                  # noqa: E402
 
@@ -206,6 +208,85 @@ def swaps(rng, n):
             close("SwapFloatLeg.value(notional exchange)", lambda: rl.value(rvd, rc2, rc, fix), lambda: ol.value(ovd, oc2, oc, fix), N)
 
 
+def _model(M, D, DCt, F, B, S, I, vd, quotes, interp, freq="ANNUAL", bd="MODIFIED_FOLLOWING", lag=0):
+    m = M(D(*vd))
+    for name, tenors, px, dc in quotes:
+        m.build_curve(name=name, px_list=px, tenor_list=tenors, spot_days=0, swap_type=S.PAY, fixed_dcc_type=DCt[dc], fixed_freq_type=F[freq],
+                      float_freq_type=F[freq], float_dc_type=DCt[dc], bus_day_type=B[bd], interp_type=I[interp], payment_lag=lag)
+    return m
+
+
+def _both_models(*args, **kw):
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = _model(RModel, RDate, RDC, RFreq, RBd, RSwap, RInterp, *args, **kw)
+    return r, _model(O.Model, O.Date, O.DayCountTypes, O.FrequencyTypes, O.BusDayAdjustTypes, O.SwapTypes, O.InterpTypes, *args, **kw)
+
+
+def _nodes(c):
+    return np.asarray(c._times, dtype=np.float64), np.asarray(c._dfs, dtype=np.float64)
+
+
+def bootstraps(rng, n_ois, n_xccy):
+    """Path-A OIS curves from random quote sets (Model.build_curve) and basis curves as Model.build_xccy_curve builds them
+    (use_ad=True): node times exactly, discount factors and d DF / d spread to 1e-12."""
+    all_tenors = ["1D", "1W", "2W", "1M", "2M", "3M", "6M", "9M", "1Y", "18M", "2Y", "3Y", "4Y", "5Y", "7Y", "10Y", "12Y", "15Y", "20Y", "30Y",
+                  "40Y", "50Y"]
+    for _ in range(n_ois):
+        vd = (rng.randint(1, 28), rng.randint(1, 12), rng.randint(2020, 2026))
+        tenors = sorted(rng.sample(all_tenors, rng.randint(6, len(all_tenors))), key=all_tenors.index)
+        base = rng.uniform(1.0, 6.0)
+        px = [round(base + rng.uniform(-0.6, 0.6) - 0.02 * i, 4) for i in range(len(tenors))]
+        kw = dict(interp=rng.choice(["LINEAR_ZERO_RATES", "FLAT_FWD_RATES"]), freq=rng.choice(["ANNUAL", "SEMI_ANNUAL", "QUARTERLY"]),
+                  bd=rng.choice(["MODIFIED_FOLLOWING", "FOLLOWING"]), lag=rng.choice([0, 0, 2]))
+        quotes = [("GBP_OIS_SONIA", tenors, px, rng.choice(["ACT_365F", "ACT_360"]))]
+        calls["OISCurve (Model.build_curve)"] = calls.get("OISCurve (Model.build_curve)", 0) + 1
+        try:
+            rm, om = None, None
+            with contextlib.redirect_stdout(io.StringIO()):
+                rm = _model(RModel, RDate, RDC, RFreq, RBd, RSwap, RInterp, vd, quotes, **kw)
+        except Exception as ex:  # noqa: BLE001  (quote sets the reference cannot bootstrap: ours must fail the same way)
+            theirs = type(ex).__name__
+            mine = run(lambda: _model(O.Model, O.Date, O.DayCountTypes, O.FrequencyTypes, O.BusDayAdjustTypes, O.SwapTypes, O.InterpTypes, vd, quotes, **kw))
+            if mine != "raises " + theirs:
+                mismatch.setdefault("OISCurve (Model.build_curve) errors", []).append((theirs, mine))
+            continue
+        om = _model(O.Model, O.Date, O.DayCountTypes, O.FrequencyTypes, O.BusDayAdjustTypes, O.SwapTypes, O.InterpTypes, vd, quotes, **kw)
+        rc, oc = rm.curves.GBP_OIS_SONIA, om.curves.GBP_OIS_SONIA
+        (rt, rd), (ot, od) = _nodes(rc), _nodes(oc)
+        same = rt.shape == ot.shape and np.array_equal(rt, ot) and list(rc.swap_times) == list(oc.swap_times) and \
+            [list(map(float, x)) for x in rc.year_fracs] == [list(map(float, x)) for x in oc.year_fracs]
+        if not same:
+            mismatch.setdefault("OISCurve node times / swap_times / year_fracs", []).append((vd, tenors))
+            continue
+        worst["OISCurve._dfs"] = max(worst.get("OISCurve._dfs", 0.0), float(np.max(np.abs(rd - od))))
+    pillars = ["1Y", "2Y", "3Y", "4Y", "5Y", "7Y", "10Y", "15Y"]
+    ten = ["1Y", "2Y", "3Y", "5Y", "7Y", "10Y", "15Y", "20Y", "30Y"]
+    for _ in range(n_xccy):
+        vd = (rng.randint(1, 28), rng.randint(1, 12), rng.randint(2021, 2025))
+        gbp = [round(4.6 - 0.03 * i + rng.uniform(-0.1, 0.1), 4) for i in range(len(ten))]
+        usd = [round(5.1 - 0.04 * i + rng.uniform(-0.1, 0.1), 4) for i in range(len(ten))]
+        rm, om = _both_models(vd, [("GBP_OIS_SONIA", ten, gbp, "ACT_365F"), ("USD_OIS_SOFR", ten, usd, "ACT_360")],
+                              interp=rng.choice(["LINEAR_ZERO_RATES", "FLAT_FWD_RATES"]))
+        for c in (rm.curves.GBP_OIS_SONIA, rm.curves.USD_OIS_SOFR):      # the reference's non-AD look-ups need numpy node arrays
+            c._times, c._dfs = _nodes(c)                                 # (the jax stand-in's arrays have no integer `.size`)
+        pill = sorted(rng.sample(pillars, rng.randint(2, 7)), key=pillars.index)
+        kw = dict(name="GBP_USD_BASIS", domestic_curve_name="USD_OIS_SOFR", foreign_curve_name="GBP_OIS_SONIA",
+                  basis_spreads=[round(rng.uniform(-30, 40), 2) for _ in pill], tenor_list=pill, spot_fx=round(rng.uniform(1.0, 1.5), 4))
+        dfq, ffq = rng.choice(["ANNUAL", "SEMI_ANNUAL", "QUARTERLY"]), rng.choice(["ANNUAL", "SEMI_ANNUAL", "QUARTERLY"])
+        with contextlib.redirect_stdout(io.StringIO()):
+            rm.build_xccy_curve(domestic_freq_type=RFreq[dfq], foreign_freq_type=RFreq[ffq], **kw)
+        om.build_xccy_curve(domestic_freq_type=O.FrequencyTypes[dfq], foreign_freq_type=O.FrequencyTypes[ffq], **kw)
+        rx, ox = rm.curves.GBP_USD_BASIS, om.curves.GBP_USD_BASIS
+        (rt, rd), (ot, od) = _nodes(rx), _nodes(ox)
+        calls["XccyCurve (Model.build_xccy_curve)"] = calls.get("XccyCurve (Model.build_xccy_curve)", 0) + 1
+        if rt.shape != ot.shape or not np.array_equal(rt, ot):
+            mismatch.setdefault("XccyCurve node times", []).append((vd, pill, dfq, ffq))
+            continue
+        rj = np.asarray(rx._jac_basis, dtype=np.float64)
+        worst["XccyCurve._dfs"] = max(worst.get("XccyCurve._dfs", 0.0), float(np.max(np.abs(rd - od))))
+        worst["XccyCurve._jac_basis"] = max(worst.get("XccyCurve._jac_basis", 0.0), float(np.max(np.abs(rj - ox._jac_basis)) / np.max(np.abs(rj))))
+
+
 def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 20240430
     rng = random.Random(seed)
@@ -214,6 +295,7 @@ def main():
         day_counts_and_schedules(rng, 1500)
         credit(rng, 200)
         swaps(rng, 150)
+        bootstraps(rng, 200, 12)
     print(f"seed {seed}: {sum(calls.values())} paired calls over {len(calls)} functions")
     print("largest scaled difference per function:", {k: f"{v:.1e}" for k, v in sorted(worst.items())})
     print("mismatches:", {k: (len(v), v[:2]) for k, v in mismatch.items()} or "none")
