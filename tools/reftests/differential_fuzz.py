@@ -8,7 +8,8 @@ INFRASTRUCTURE, nothing in tests/, smoke() or bench.py uses it.
 
 Covers Date arithmetic, DayCount.year_frac (all types, with and without the ICMA arguments), Schedule (all frequencies, rules,
 adjustments, holiday calendars), Calendar.adjust / add_business_days, Bond / FRN analytics, OIS / leg host values, the path-A OIS
-bootstrap and the basis-curve bootstrap with its spread Jacobian.
+bootstrap, the basis-curve bootstrap with its spread Jacobian, inflation index look-ups / the inflation curve / the non-AD
+values of zero-coupon and year-on-year inflation swaps.
 """
 import contextlib
 import io
@@ -35,6 +36,11 @@ from cavour.trades.credit.frn import FRN as RFRN                                
 from cavour.trades.rates.ois import OIS as ROIS                                                           # noqa: E402
 from cavour.trades.rates.swap_float_leg import SwapFloatLeg as RFloatLeg                                  # noqa: E402
 from cavour.models.models import Model as RModel                                                          # noqa: E402
+from cavour.utils.global_types import InflationIndexTypes as RIdxT, InflationInterpTypes as RIdxI         # noqa: E402
+from cavour.market.indices.inflation_index import InflationIndex as RIndex                                # noqa: E402
+from cavour.market.curves.inflation_curve import InflationCurve as RInflCurve                             # noqa: E402
+from cavour.trades.rates.zcis import ZeroCouponInflationSwap as RZcis                                     # noqa: E402
+from cavour.trades.rates.yoy_inflation_swap import YoYInflationSwap as RYoY                               # noqa: E402
 
 import adrates_b200 as O                                                                                  # noqa: E402
 
@@ -287,6 +293,56 @@ def bootstraps(rng, n_ois, n_xccy):
         worst["XccyCurve._jac_basis"] = max(worst.get("XccyCurve._jac_basis", 0.0), float(np.max(np.abs(rj - ox._jac_basis)) / np.max(np.abs(rj))))
 
 
+def inflation(rng, n):
+    """Index look-ups (lag, FLAT / LINEAR / COMPOUND between monthly fixings, seasonality, curve projection), the inflation
+    curve from random ZCIS quotes, and the non-AD host values of zero-coupon and year-on-year swaps."""
+    rvd, ovd = RDate(*VD), O.Date(*VD)
+    rc, oc = curves("LINEAR_ZERO_RATES")
+    for _ in range(n):
+        lag, interp = rng.choice([2, 3]), rng.choice(["FLAT", "LINEAR", "COMPOUND"])
+        season = None if rng.random() < 0.5 else {m: round(1.0 + rng.uniform(-0.006, 0.006), 4) for m in range(1, 13)}
+        level, fix = 280.0, []
+        for k in range(18):                                   # monthly fixings Nov-2022 .. Apr-2024
+            level *= 1.0 + rng.uniform(-0.001, 0.006)
+            fix.append(((1, (10 + k) % 12 + 1, 2022 + (10 + k) // 12), round(level, 2)))
+        ri = RIndex(RIdxT.UK_RPI, RDate(*fix[0][0]), fix[0][1], RCcy.GBP, lag_months=lag, interp_type=RIdxI[interp], seasonality_factors=season)
+        oi = O.InflationIndex(O.InflationIndexTypes.UK_RPI, O.Date(*fix[0][0]), fix[0][1], O.CurrencyTypes.GBP, lag_months=lag,
+                              interp_type=O.InflationInterpTypes[interp], seasonality_factors=season)
+        for d, v in fix:
+            ri.add_fixing(RDate(*d), v)
+            oi.add_fixing(O.Date(*d), v)
+        quotes = [(t, round(0.03 + rng.uniform(-0.004, 0.006), 5)) for t in ("1Y", "2Y", "3Y", "5Y", "7Y", "10Y", "15Y", "20Y", "30Y")]
+        rz = [RZcis(rvd, t, RSwap.PAY, r, ri, 1_000_000) for t, r in quotes]
+        oz = [O.ZeroCouponInflationSwap(ovd, t, O.SwapTypes.PAY, r, oi, 1_000_000) for t, r in quotes]
+        curve_interp = rng.choice(["FLAT", "LINEAR"])
+        ric = RInflCurve(rvd, rz, fix[-1][1], RCcy.GBP, RIdxT.UK_RPI, discount_curve=rc, interp_type=RIdxI[curve_interp])
+        oic = O.InflationCurve(ovd, oz, fix[-1][1], O.CurrencyTypes.GBP, O.InflationIndexTypes.UK_RPI, discount_curve=oc,
+                               interp_type=O.InflationInterpTypes[curve_interp])
+        (rt, rd), (ot, od) = _nodes(ric), _nodes(oic)
+        calls["InflationCurve nodes"] = calls.get("InflationCurve nodes", 0) + 1
+        if rt.shape != ot.shape or not np.array_equal(rt, ot):
+            mismatch.setdefault("InflationCurve node times", []).append((lag, interp))
+            continue
+        worst["InflationCurve._dfs"] = max(worst.get("InflationCurve._dfs", 0.0), float(np.max(np.abs(rd - od))))
+        ri.set_inflation_curve(ric)
+        oi.set_inflation_curve(oic)
+        for _ in range(12):
+            y, m, d = rng.choice([2023, 2024, 2025, 2031, 2050]), rng.randint(1, 12), rng.randint(1, 28)
+            lagged = rng.random() < 0.7
+            close("InflationIndex.get_index", lambda: ri.get_index(RDate(d, m, y), apply_lag=lagged), lambda: oi.get_index(O.Date(d, m, y), apply_lag=lagged), 300.0)
+            close("InflationCurve.forward_index", lambda: ric.forward_index(RDate(d, m, y)), lambda: oic.forward_index(O.Date(d, m, y)), 300.0)
+        ten, side = rng.choice(["2Y", "5Y", "12Y"]), rng.choice(["PAY", "RECEIVE"])
+        rsw, osw = RZcis(rvd, ten, RSwap[side], 0.031, ri, 2e6), O.ZeroCouponInflationSwap(ovd, ten, O.SwapTypes[side], 0.031, oi, 2e6)
+        close("ZeroCouponInflationSwap.pv01", lambda: rsw.pv01(rvd, rc), lambda: osw.pv01(ovd, oc), 2e6)
+        close("ZeroCouponInflationSwap.breakeven_inflation_rate", lambda: rsw.breakeven_inflation_rate(rvd, rc, ric),
+              lambda: osw.breakeven_inflation_rate(ovd, oc, oic), 1.0)
+        ry = RYoY(rvd, ten, RSwap[side], 0.03, ri, RFreq.ANNUAL, 5e6, 0.001)
+        oy = O.YoYInflationSwap(ovd, ten, O.SwapTypes[side], 0.03, oi, O.FrequencyTypes.ANNUAL, 5e6, 0.001)
+        close("YoYInflationSwap.value", lambda: ry.value(rvd, rc, ric), lambda: oy.value(ovd, oc, oic), 5e6)
+        close("YoYInflationSwap.breakeven_rate", lambda: ry.breakeven_rate(rvd, rc, ric), lambda: oy.breakeven_rate(ovd, oc, oic), 1.0)
+        close("YoYInflationSwap.pv01", lambda: ry.pv01(rvd, rc), lambda: oy.pv01(ovd, oc), 5e6)
+
+
 def main():
     seed = int(sys.argv[1]) if len(sys.argv) > 1 else 20240430
     rng = random.Random(seed)
@@ -296,6 +352,7 @@ def main():
         credit(rng, 200)
         swaps(rng, 150)
         bootstraps(rng, 200, 12)
+        inflation(rng, 60)
     print(f"seed {seed}: {sum(calls.values())} paired calls over {len(calls)} functions")
     print("largest scaled difference per function:", {k: f"{v:.1e}" for k, v in sorted(worst.items())})
     print("mismatches:", {k: (len(v), v[:2]) for k, v in mismatch.items()} or "none")
