@@ -87,7 +87,7 @@ def main():
                 mod["functions"][node.name] = {"params": signature(node)}
         out[rel] = mod
     with open(OUT, "w") as f:
-        json.dump(out, f, indent=0, sort_keys=True)
+        json.dump(out, f, sort_keys=True)
     print("modules", len(out), "classes", sum(len(m["classes"]) for m in out.values()))
 
 
